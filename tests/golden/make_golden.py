@@ -1,0 +1,225 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (Dedalus v3.0.5,
+/root/reference) single-process under tests/golden/ref_shim.py.
+
+Run here (the build container), never on the GPU box:   python tests/golden/make_golden.py
+Outputs: tests/golden/*.npz (small; committed).  Each fixture stores the inputs, the reference outputs and the
+reference call that produced them, so tests can replay the same inputs through oracle/ and through the CUDA path.
+"""
+import sys, pathlib
+import numpy as np
+HERE = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+import ref_shim
+d3 = ref_shim.activate()
+from scipy import sparse
+from dedalus.core import transforms as rtr
+from dedalus.core import basis as rbasis
+from dedalus.core import timesteppers as rts
+
+
+def natural_matrices(sp):
+    """Reference pencil matrices expanded back to natural (field-major, un-permuted) ordering."""
+    out = {}
+    for name in ("M", "L"):
+        mat = (sp.pre_left.T @ getattr(sp, name + "_min") @ sp.pre_right.T).tocoo()
+        out[name] = mat
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 1. Transform vectors (reference classes: ScipyRealFFT / RealFourierMMT / ScipyComplexFFT / ScipyFastChebyshev / JacobiMMT)
+# ----------------------------------------------------------------------------------------------------------
+def gen_transforms():
+    rng = np.random.default_rng(1234)
+    out = {}
+    # Real Fourier: reference tests use N=16, dealias in {0.5, 1, 1.5} (tests/test_transforms.py:18-57); add odd and 3-D shapes
+    for (M, N) in [(16, 8), (16, 16), (16, 24), (16, 21), (32, 48), (12, 18), (10, 15)]:
+        for lib in ("scipy", "matrix"):
+            plan = rbasis.RealFourier.transforms[lib](N, M)
+            c = rng.standard_normal((3, M, 2))
+            g = np.zeros((3, N, 2))
+            plan.backward(c.copy(), g, 1)
+            gg = rng.standard_normal((3, N, 2))
+            cc = np.zeros((3, M, 2))
+            plan.forward(gg.copy(), cc, 1)
+            out[f"rf_{lib}_{M}_{N}_cin"] = c; out[f"rf_{lib}_{M}_{N}_gout"] = g
+            out[f"rf_{lib}_{M}_{N}_gin"] = gg; out[f"rf_{lib}_{M}_{N}_cout"] = cc
+    # Complex Fourier
+    for (M, N) in [(16, 8), (16, 16), (16, 24), (15, 22), (12, 18)]:
+        for lib in ("scipy", "matrix"):
+            plan = rbasis.ComplexFourier.transforms[lib](N, M)
+            c = rng.standard_normal((2, M, 3)) + 1j * rng.standard_normal((2, M, 3))
+            g = np.zeros((2, N, 3), dtype=complex)
+            plan.backward(c.copy(), g, 1)
+            gg = rng.standard_normal((2, N, 3)) + 1j * rng.standard_normal((2, N, 3))
+            cc = np.zeros((2, M, 3), dtype=complex)
+            plan.forward(gg.copy(), cc, 1)
+            out[f"cf_{lib}_{M}_{N}_cin"] = c; out[f"cf_{lib}_{M}_{N}_gout"] = g
+            out[f"cf_{lib}_{M}_{N}_gin"] = gg; out[f"cf_{lib}_{M}_{N}_cout"] = cc
+    # Chebyshev / ultraspherical with Chebyshev grid (tests/test_transforms.py:117-158: N in {15,16}, alpha in {0,1,2})
+    for (M, N) in [(16, 8), (16, 16), (16, 24), (15, 22), (15, 15), (32, 48)]:
+        for alpha in (0, 1, 2):
+            a = b = alpha - 0.5
+            for lib in ("scipy_dct", "matrix"):
+                plan = rbasis.Jacobi.transforms[lib](N, M, a, b, -0.5, -0.5)
+                c = rng.standard_normal((2, 3, M))
+                g = np.zeros((2, 3, N))
+                plan.backward(c.copy(), g, 2)
+                gg = rng.standard_normal((2, 3, N))
+                cc = np.zeros((2, 3, M))
+                plan.forward(gg.copy(), cc, 2)
+                key = f"ch_{lib}_{M}_{N}_{alpha}"
+                out[key + "_cin"] = c; out[key + "_gout"] = g; out[key + "_gin"] = gg; out[key + "_cout"] = cc
+    # Non-Chebyshev Jacobi (dense MMT, T4): Legendre and (a,b)=(1,0.5) on their own Gauss grids
+    for (M, N) in [(16, 24), (12, 12)]:
+        for (a, b) in [(0.0, 0.0), (1.0, 0.5)]:
+            plan = rbasis.Jacobi.transforms["matrix"](N, M, a, b, a, b)
+            out[f"jac_{M}_{N}_{a}_{b}_fwdmat"] = plan.forward_matrix
+            out[f"jac_{M}_{N}_{a}_{b}_bwdmat"] = plan.backward_matrix
+    # Jacobi helper quantities used in host matrix assembly
+    from dedalus.tools import jacobi as tj
+    for (a, b) in [(-0.5, -0.5), (0.5, 0.5), (1.5, 1.5), (0.0, 0.0)]:
+        N = 12
+        out[f"jop_D_{a}_{b}"] = tj.differentiation_matrix(N, a, b).toarray()
+        out[f"jop_C_{a}_{b}"] = tj.conversion_matrix(N, a, b, a + 1, b + 1).toarray()
+        out[f"jop_Z_{a}_{b}"] = tj.jacobi_matrix(N, a, b).toarray()
+        out[f"jop_int_{a}_{b}"] = tj.integration_vector(N, a, b)
+        out[f"jop_grid_{a}_{b}"] = tj.build_grid(N, a, b)
+        out[f"jop_wts_{a}_{b}"] = tj.build_weights(N, a, b)
+        out[f"jop_pm1_{a}_{b}"] = tj.build_polynomials(N, a, b, np.array([-1.0, 0.3, 1.0]))
+    np.savez_compressed(HERE / "transforms.npz", **out)
+    print("transforms.npz", len(out), "arrays")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 2. IVPs: KdV-Burgers (cfg 1), 2-D RB (cfg 2), 3-D RB (cfg 3) at oracle-friendly sizes
+# ----------------------------------------------------------------------------------------------------------
+def kdv(N=64, steps=20, tstep=2e-3, scheme="SBDF2"):
+    # examples/ivp_1d_kdv_burgers/kdv_burgers.py:22-54
+    Lx = 10; a = 1e-4; b = 2e-4
+    xcoord = d3.Coordinate('x')
+    dist = d3.Distributor(xcoord, dtype=np.float64)
+    xbasis = d3.RealFourier(xcoord, size=N, bounds=(0, Lx), dealias=3/2)
+    u = dist.Field(name='u', bases=xbasis)
+    dx = lambda A: d3.Differentiate(A, xcoord)
+    problem = d3.IVP([u], namespace=locals())
+    problem.add_equation("dt(u) - a*dx(dx(u)) - b*dx(dx(dx(u))) = - u*dx(u)")
+    x = dist.local_grid(xbasis)
+    n = 20
+    u['g'] = np.log(1 + np.cosh(n)**2/np.cosh(n*(x-0.2*Lx))**2) / (2*n)
+    solver = problem.build_solver(getattr(d3, scheme))
+    u0 = u['c'].copy()
+    for i in range(steps):
+        solver.step(tstep)
+    return dict(u0_c=u0, u_c=u['c'].copy(), u_g=u['g'].copy(), N=N, steps=steps, dt=tstep, scheme=scheme)
+
+
+def rb(dim, Nh, Nz, steps, tstep, Ra, scheme="RK222", dump_pencils=(), return_solver=False):
+    # examples/ivp_2d_rayleigh_benard/rayleigh_benard.py:33-89 (2-D) and SURVEY.md Appendix C (3-D)
+    Lx = Ly = 4; Lz = 1; Pr = 1
+    names = ('x', 'z') if dim == 2 else ('x', 'y', 'z')
+    coords = d3.CartesianCoordinates(*names)
+    dist = d3.Distributor(coords, dtype=np.float64)
+    hb = [d3.RealFourier(coords[n], size=Nh, bounds=(0, Lx), dealias=3/2) for n in names[:-1]]
+    zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, Lz), dealias=3/2)
+    bases = tuple(hb) + (zb,)
+    p = dist.Field(name='p', bases=bases); b = dist.Field(name='b', bases=bases)
+    u = dist.VectorField(coords, name='u', bases=bases)
+    tau_p = dist.Field(name='tau_p')
+    tau_b1 = dist.Field(name='tau_b1', bases=tuple(hb)); tau_b2 = dist.Field(name='tau_b2', bases=tuple(hb))
+    tau_u1 = dist.VectorField(coords, name='tau_u1', bases=tuple(hb)); tau_u2 = dist.VectorField(coords, name='tau_u2', bases=tuple(hb))
+    kappa = (Ra * Pr)**(-1/2); nu = (Ra / Pr)**(-1/2)
+    grids = dist.local_grids(*bases); z = grids[-1]
+    ez = coords.unit_vector_fields(dist)[-1]
+    lift_basis = zb.derivative_basis(1)
+    lift = lambda A: d3.Lift(A, lift_basis, -1)
+    grad_u = d3.grad(u) + ez*lift(tau_u1); grad_b = d3.grad(b) + ez*lift(tau_b1)
+    problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
+    problem.add_equation("trace(grad_u) + tau_p = 0")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*ez + lift(tau_u2) = - u@grad(u)")
+    problem.add_equation("b(z=0) = Lz"); problem.add_equation("u(z=0) = 0")
+    problem.add_equation("b(z=Lz) = 0"); problem.add_equation("u(z=Lz) = 0")
+    problem.add_equation("integ(p) = 0")
+    solver = problem.build_solver(getattr(d3, scheme))
+    b.fill_random('g', seed=42, distribution='normal', scale=1e-3)
+    b['g'] *= z * (Lz - z); b['g'] += Lz - z
+    out = dict(dim=dim, Nh=Nh, Nz=Nz, steps=steps, dt=tstep, Ra=Ra, scheme=scheme)
+    out['b0_c'] = b['c'].copy()
+    out['b0_g1'] = b['g'].copy()     # dealias-scale grid values? (scales=1 after fill_random + item access)
+    # pencil matrices in natural ordering
+    for grp in dump_pencils:
+        sp = [s for s in solver.subproblems if tuple(g for g in s.group if g is not None) == tuple(grp)][0]
+        nat = natural_matrices(sp)
+        tag = "pen_" + "_".join(str(g) for g in grp)
+        for name, mat in nat.items():
+            out[f"{tag}_{name}_row"] = mat.row.astype(np.int32); out[f"{tag}_{name}_col"] = mat.col.astype(np.int32)
+            out[f"{tag}_{name}_val"] = mat.data; out[f"{tag}_{name}_shape"] = np.array(mat.shape)
+        out[f"{tag}_valid_rows"] = np.asarray(sp.pre_left.sum(axis=0)).ravel().astype(bool)
+        out[f"{tag}_valid_cols"] = np.asarray(sp.pre_right.sum(axis=1)).ravel().astype(bool)
+    # F evaluation at the initial state (stage-1 RHS fields), after one evaluate of the F group
+    solver.evaluator.evaluate_group('F')
+    for i, F in enumerate(solver.F):
+        F.change_layout('c') if hasattr(F, 'change_layout') else None
+        out[f"F0_{i}"] = np.array(F['c']) if hasattr(F, '__getitem__') else np.array(F)
+    state_hist = []
+    for i in range(steps):
+        solver.step(tstep)
+        if i == 0:
+            for f in (p, b, u):
+                out[f"{f.name}_c_step1"] = f['c'].copy()
+    for f in (p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2):
+        out[f"{f.name}_c"] = f['c'].copy()
+    out['checks'] = np.array([np.sum(b['c']**2), np.sum(p['c']**2), np.sum(u['c']**2)])
+    if return_solver:
+        return out, solver
+    return out
+
+
+def heat(scheme, N=8, steps=20):
+    # tests/test_ivp.py:20-49 (complex Fourier heat equation, every timestepper)
+    xcoord = d3.Coordinate('x')
+    dist = d3.Distributor(xcoord, dtype=np.complex128)
+    xbasis = d3.ComplexFourier(xcoord, size=N, bounds=(0, 2*np.pi))
+    u = dist.Field(name='u', bases=xbasis); F = dist.Field(name='F', bases=xbasis)
+    x = dist.local_grid(xbasis)
+    F['g'] = -np.sin(x)
+    dx = lambda A: d3.Differentiate(A, xcoord)
+    problem = d3.IVP([u], namespace=locals())
+    problem.add_equation("-dt(u) + dx(dx(u)) = F")
+    solver = problem.build_solver(scheme)
+    for i in range(steps):
+        solver.step(1e-5)
+    return u['c'].copy()
+
+
+def gen_ivps():
+    out = {}
+    for k, v in kdv().items(): out["kdv_" + k] = v
+    for k, v in kdv(N=32, steps=8, tstep=1e-3, scheme="RK443").items(): out["kdv443_" + k] = v
+    np.savez_compressed(HERE / "kdv.npz", **out)
+    r2 = rb(2, 16, 16, steps=5, tstep=0.01, Ra=2e6, dump_pencils=[(0,), (1,), (5,)])
+    np.savez_compressed(HERE / "rb2d_16x16.npz", **r2)
+    r3 = rb(3, 8, 8, steps=5, tstep=0.01, Ra=1e6, dump_pencils=[(0, 0), (0, 2), (3, 0), (1, 2)])
+    np.savez_compressed(HERE / "rb3d_8.npz", **r3)
+    r3s = rb(3, 8, 12, steps=3, tstep=0.02, Ra=1e5, scheme="SBDF2")
+    np.savez_compressed(HERE / "rb3d_8x8x12_sbdf2.npz", **{k: v for k, v in r3s.items() if not k.startswith('pen_')})
+    # Known-answer checksums at larger sizes: only the three sums are stored
+    chk = {}
+    c2 = rb(2, 256, 128, steps=10, tstep=0.01, Ra=2e6)
+    chk['rb2d_256x128_10steps'] = c2['checks']
+    c3 = rb(3, 32, 32, steps=10, tstep=0.01, Ra=1e6)
+    chk['rb3d_32_10steps'] = c3['checks']
+    k = kdv(N=1024, steps=200, tstep=2e-3)
+    chk['kdv_1024_200steps_maxabs'] = np.array([np.max(np.abs(k['u_g']))])
+    heat_out = {}
+    for name, scheme in rts.schemes.items():
+        heat_out['heat_' + name] = heat(scheme)
+    np.savez_compressed(HERE / "checks.npz", **chk, **heat_out)
+    print({k: v for k, v in chk.items()})
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["transforms", "ivps"]
+    if "transforms" in which: gen_transforms()
+    if "ivps" in which: gen_ivps()
