@@ -1,0 +1,73 @@
+"""Coordinates (reference: dedalus/core/coords.py:20-190, Cartesian subset)."""
+import numpy as np
+
+
+class Coordinate:
+    dim = 1
+
+    def __init__(self, name, cs=None):
+        self.name = name
+        self.cs = cs
+        self.coords = (self,)
+
+    def __repr__(self):
+        return f"<Coordinate {self.name}>"
+
+    def check_bounds(self, bounds):
+        if bounds[0] >= bounds[1]:
+            raise ValueError("Bounds must be increasing.")
+
+
+class CartesianCoordinates:
+    """Cartesian coordinate system (reference coords.py:139-190)."""
+
+    def __init__(self, *names):
+        if len(set(names)) < len(names):
+            raise ValueError("Must specify unique names.")
+        self.names = names
+        self.dim = len(names)
+        self.coords = tuple(Coordinate(name, cs=self) for name in names)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.coords[self.names.index(key)]
+        return self.coords[key]
+
+    def __repr__(self):
+        return "{" + ",".join(self.names) + "}"
+
+    def unit_vector_fields(self, dist):
+        """Constant unit vector fields e_i (reference coords.py:183-189)."""
+        fields = []
+        for i, c in enumerate(self.coords):
+            ec = dist.VectorField(self, name=f"e{c.name}")
+            ec['c'][i] = 1
+            fields.append(ec)
+        return tuple(fields)
+
+
+class AffineCOV:
+    """Affine change of variables native<->problem interval (reference basis.py:60-93)."""
+
+    def __init__(self, native_bounds, problem_bounds):
+        self.native_bounds = native_bounds
+        self.problem_bounds = problem_bounds
+        self.native_left, self.native_right = native_bounds
+        self.native_length = native_bounds[1] - native_bounds[0]
+        self.problem_left, self.problem_right = problem_bounds
+        self.problem_length = problem_bounds[1] - problem_bounds[0]
+        self.native_center = (native_bounds[0] + native_bounds[1]) / 2
+        self.problem_center = (problem_bounds[0] + problem_bounds[1]) / 2
+        self.stretch = self.problem_length / self.native_length
+
+    def problem_coord(self, native_coord):
+        if isinstance(native_coord, str):
+            return {'left': self.problem_left, 'right': self.problem_right, 'center': self.problem_center}[native_coord]
+        neutral = (np.asarray(native_coord) - self.native_left) / self.native_length
+        return self.problem_left + neutral * self.problem_length
+
+    def native_coord(self, problem_coord):
+        if isinstance(problem_coord, str):
+            return {'left': self.native_left, 'right': self.native_right, 'center': self.native_center}[problem_coord]
+        neutral = (np.asarray(problem_coord) - self.problem_left) / self.problem_length
+        return self.native_left + neutral * self.native_length
