@@ -20,7 +20,6 @@ import itertools
 import numpy as np
 from scipy import sparse
 from scipy.sparse import csgraph
-from scipy.optimize import linear_sum_assignment
 from .operators import linear_map, Operand
 from .basis import RealFourier, ComplexFourier, Jacobi
 
@@ -329,20 +328,69 @@ class Batch:
         order = np.argsort(g.sum(axis=1), kind='stable')
         return g[order[len(order) // 2]]
 
-    def compute_ordering(self, a0, b0):
-        """Static column order: max-product transversal on a representative LHS (after row/col scaling)."""
-        A = self.matrix((a0, b0), self.representative_group(), cols=self.cols0).toarray()
-        absA = np.abs(A)
-        r = absA.max(axis=1); r[r == 0] = 1
-        Sc = absA / r[:, None]
-        c = Sc.max(axis=0); c[c == 0] = 1
-        Sc = Sc / c[None, :]
-        with np.errstate(divide='ignore'):
-            cost = np.where(Sc > 0, -np.log(Sc), 1e8)
-        ri, ci = linear_sum_assignment(cost)
-        if np.any(cost[ri, ci] >= 1e8):
-            raise ValueError("Pencil system is structurally singular (no perfect matching).")
-        self.cols = self.cols0[ci]
+    def representative_groups(self, nrep=6):
+        """A few member pencils spanning the wavenumber range (corners, median, skewed)."""
+        g = self.groups
+        if len(g) <= nrep:
+            return [r for r in g]
+        picks = []
+        tot = g.sum(axis=1)
+        order = np.argsort(tot, kind='stable')
+        picks += [order[0], order[-1], order[len(order) // 2]]
+        for i in range(g.shape[1]):
+            picks.append(np.lexsort((tot, -g[:, i]))[0])       # largest along axis i, smallest elsewhere
+            picks.append(np.lexsort((-tot, g[:, i]))[0])       # smallest along axis i, largest elsewhere
+        seen, out = set(), []
+        for p in picks:
+            if int(p) not in seen:
+                seen.add(int(p)); out.append(g[int(p)])
+        return out
+
+    def compute_ordering(self, a0, b0, threshold=0.1):
+        """Static column (pivot) order shared by every system of the batch.
+
+        Rows are processed in mode-major order (dense boundary rows last).  The pivot column of each row is
+        chosen by *joint* threshold pivoting over several representative member pencils: a candidate's score
+        is the minimum over representatives of |a_ij| / max_j |a_ij| (after the eliminations so far), so exact
+        cancellations (e.g. the proportional pressure-gradient rows of RB) and wavenumber-regime changes are
+        seen before the order is frozen.  Among candidates within `threshold` of the best score the one
+        with the fewest remaining column entries (Markowitz) and lowest index is taken, which keeps the fill
+        local.  This is what partial pivoting of A^T (reference matsolvers.py:179-183, SuperLU on A^T) does
+        per pencil; here it is done once per batch and the GPU factorisation needs no pivot search.
+        """
+        reps = self.representative_groups()
+        mats = np.stack([self.matrix((a0, b0), g, cols=self.cols0).toarray() for g in reps], axis=0)
+        R, n, _ = mats.shape
+        used = np.zeros(n, dtype=bool)
+        seq = np.zeros(n, dtype=np.int64)
+        tiny = 1e-13
+        for i in range(n):
+            rowabs = np.abs(mats[:, i, :])
+            rowabs[:, used] = 0
+            rmax = rowabs.max(axis=1)
+            if np.any(rmax == 0):
+                raise ValueError("Pencil system is singular for a representative wavenumber (zero row during ordering).")
+            rel = rowabs / rmax[:, None]
+            score = rel.min(axis=0)
+            best = score.max()
+            if best < 1e-8:
+                raise ValueError("No jointly acceptable pivot found while ordering the pencil system.")
+            cand = np.nonzero(score >= threshold * best)[0]
+            if len(cand) > 1:
+                below = (np.abs(mats[0, i + 1:, :][:, cand]) > tiny * rmax[0]).sum(axis=0)
+                cand = cand[np.lexsort((cand, below))]
+            j = int(cand[0])
+            seq[i] = j
+            used[j] = True
+            # eliminate column j from the remaining rows (all representatives)
+            piv = mats[:, i, j]
+            col = mats[:, i + 1:, j]
+            rows = np.nonzero(np.any(col != 0, axis=0))[0]
+            if rows.size:
+                f = col[:, rows] / piv[:, None]
+                mats[:, i + 1 + rows, :] -= f[:, :, None] * mats[:, i, :][:, None, :]
+                mats[:, i + 1 + rows, j] = 0
+        self.cols = self.cols0[seq]
         return self.cols
 
     # -- symbolic factorisation on the union pattern -------------------------------------------------
@@ -359,10 +407,212 @@ class Batch:
         """Fill pattern of LU without pivoting in the current ordering (boolean n x n)."""
         F = self.structural_pattern()
         n = self.n
-        if not np.all(np.diag(F)):
-            raise ValueError("Zero structural diagonal after matching.")
         for k in range(n - 1):
+            if not F[k, k]:
+                raise ValueError("Zero structural pivot in static ordering.")
             below = np.nonzero(F[k + 1:, k])[0]
             if below.size:
                 F[k + 1 + below, k + 1:] |= F[k, k + 1:]
         return F
+
+
+# ------------------------------------------------------------------------------------------------------
+# Program compilation
+# ------------------------------------------------------------------------------------------------------
+class BatchProgram:
+    """Integer programs + template values for one batch (all arrays are host numpy, uploaded by the solver)."""
+    pass
+
+
+def _permuted_templates(batch, name):
+    """List of (mono, coo in solver ordering) for M or L."""
+    out = []
+    for mono, T in batch.cls.templates[name].items():
+        P = T.tocsr()[batch.rows][:, batch.cols].tocoo()
+        out.append((mono, P))
+    return out
+
+
+def compile_batch(batch, a0, b0):
+    """Build ordering (if needed), symbolic LU and all programs for the LHS  a0*M + b0*L."""
+    if batch.cols is None:
+        batch.compute_ordering(a0, b0)
+    b = batch.builder
+    n = batch.n
+    F = batch.symbolic_lu()
+    prog = BatchProgram()
+    prog.n, prog.S = n, batch.S
+    # ---- entry numbering in solve-stream order
+    eid = -np.ones((n, n), dtype=np.int64)
+    fwd_ptr = np.zeros(n + 1, dtype=np.int32); fwd_col = []
+    e = 0
+    for i in range(n):
+        js = np.nonzero(F[i, :i])[0]
+        eid[i, js] = e + np.arange(js.size)
+        fwd_col.append(js); e += js.size
+        fwd_ptr[i + 1] = fwd_ptr[i] + js.size
+    nL = e
+    bwd_ptr = np.zeros(n + 1, dtype=np.int32); bwd_col = []; diag_eid = np.zeros(n, dtype=np.int32)
+    nUoff = 0
+    for pos, i in enumerate(range(n - 1, -1, -1)):
+        diag_eid[i] = e; eid[i, i] = e; e += 1
+        js = i + 1 + np.nonzero(F[i, i + 1:])[0]
+        eid[i, js] = e + np.arange(js.size)
+        bwd_col.append(js); e += js.size
+        nUoff += js.size
+        bwd_ptr[pos + 1] = nUoff
+    prog.nE = e
+    prog.fwd_ptr = fwd_ptr
+    prog.fwd_col = np.concatenate(fwd_col).astype(np.int32) if fwd_col else np.zeros(0, np.int32)
+    prog.bwd_ptr = bwd_ptr
+    prog.bwd_col = np.concatenate(bwd_col).astype(np.int32) if bwd_col else np.zeros(0, np.int32)
+    prog.diag_eid = diag_eid
+    # ---- factor program
+    fl_ptr = np.zeros(n + 1, dtype=np.int32); fu_ptr = np.zeros(n + 1, dtype=np.int32)
+    fl, fu, fd = [], [], []
+    for k in range(n):
+        li = k + 1 + np.nonzero(F[k + 1:, k])[0]
+        uj = k + 1 + np.nonzero(F[k, k + 1:])[0]
+        fl.append(eid[li, k]); fu.append(eid[k, uj])
+        if li.size and uj.size:
+            fd.append(eid[np.ix_(li, uj)].ravel())
+        fl_ptr[k + 1] = fl_ptr[k] + li.size
+        fu_ptr[k + 1] = fu_ptr[k] + uj.size
+    prog.fl_ptr, prog.fu_ptr = fl_ptr, fu_ptr
+    prog.fl_eid = np.concatenate(fl).astype(np.int32) if fl else np.zeros(0, np.int32)
+    prog.fu_eid = np.concatenate(fu).astype(np.int32) if fu else np.zeros(0, np.int32)
+    prog.fd_eid = np.concatenate(fd).astype(np.int32) if fd else np.zeros(0, np.int32)
+    assert np.all(prog.fd_eid >= 0)
+    # ---- monomials
+    monos = sorted(set(batch.cls.templates['M']) | set(batch.cls.templates['L']))
+    if not monos:
+        monos = [tuple(0 for _ in b.sep_axes)]
+    prog.monos = monos
+    prog.mono_vals = np.stack([b.monomial_values(batch.cls, m) for m in monos], axis=0)   # (nmono, S)
+    midx = {m: i for i, m in enumerate(monos)}
+    # ---- template term lists in solver ordering: (row, col, mono, value) for M and L
+    def terms(name):
+        r, c, m, v = [], [], [], []
+        for mono, P in _permuted_templates(batch, name):
+            r.append(P.row); c.append(P.col); m.append(np.full(P.nnz, midx[mono])); v.append(P.data)
+        if not r:
+            return (np.zeros(0, np.int64),) * 3 + (np.zeros(0),)
+        return np.concatenate(r), np.concatenate(c), np.concatenate(m), np.concatenate(v)
+    prog.terms = {name: terms(name) for name in ('M', 'L')}
+    # matvec programs (CSR by row over terms)
+    prog.mv = {}
+    for name in ('M', 'L'):
+        r, c, m, v = prog.terms[name]
+        order = np.lexsort((c, r))
+        r, c, m, v = r[order], c[order], m[order], v[order]
+        ptr = np.zeros(n + 1, dtype=np.int32)
+        np.add.at(ptr, r + 1, 1)
+        prog.mv[name] = (np.cumsum(ptr).astype(np.int32), c.astype(np.int32), m.astype(np.int32), np.asarray(v, dtype=np.float64))
+    batch.eid = eid
+    prog.nnz_lu = int(F.sum())
+    return prog
+
+
+def assembly_program(batch, prog, a0, b0):
+    """(entry id, mono, value) triples of  a0*M + b0*L  grouped by entry: CSR over entries."""
+    es, ms, vs = [], [], []
+    for name, w in (('M', a0), ('L', b0)):
+        r, c, m, v = prog.terms[name]
+        if w == 0 or len(r) == 0:
+            continue
+        es.append(batch.eid[r, c]); ms.append(m); vs.append(w * v)
+    e = np.concatenate(es); m = np.concatenate(ms); v = np.concatenate(vs)
+    assert np.all(e >= 0)
+    order = np.lexsort((m, e))
+    e, m, v = e[order], m[order], v[order]
+    ptr = np.zeros(prog.nE + 1, dtype=np.int64)
+    np.add.at(ptr, e + 1, 1)
+    return np.cumsum(ptr).astype(np.int32), m.astype(np.int32), np.asarray(v, dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Gather / scatter maps between field arenas and the SoA pencil vectors
+# ------------------------------------------------------------------------------------------------------
+class Arena:
+    """Concatenated coefficient arrays (local part) of a list of fields / equation outputs."""
+
+    def __init__(self, dist, items):
+        """items: list of (tshape, bases)."""
+        self.dist = dist
+        self.items = items
+        self.shapes, self.offsets = [], []
+        off = 0
+        for tshape, bases in items:
+            shp = []
+            for ax, bs in enumerate(bases):
+                sl = dist.coeff_local_slice(ax, bs)
+                shp.append(sl.stop - sl.start)
+            self.shapes.append((tuple(tshape), tuple(shp)))
+            self.offsets.append(off)
+            off += int(np.prod(tshape, dtype=int)) * int(np.prod(shp, dtype=int))
+        self.size = off
+
+
+def line_maps(batch, arena, side):
+    """For every coefficient line (slot) of the batch: arena base offset, system-offset kind, length and the
+    solver positions of its modes.  side = 'cols' (variables/state) or 'rows' (equations/F)."""
+    b, cls = batch.builder, batch.cls
+    dist = b.dist
+    if side == 'cols':
+        nat, slots, offs = batch.cols, cls.col_slots, cls.col_off
+    else:
+        nat, slots, offs = batch.rows, cls.row_slots, cls.row_off
+    pos_of_nat = {int(v): i for i, v in enumerate(nat)}
+    kinds, kind_tables = {}, []
+    lines = []
+    g0_start = 0
+    if dist.size > 1 and b.sep_axes:
+        g0_start = int(b.local_groups(0)[0])
+    for q, (slot, o) in enumerate(zip(slots, offs)):
+        members = [pos_of_nat.get(int(o + m), -1) for m in range(slot.size)]
+        if all(p < 0 for p in members):
+            continue
+        if any(p < 0 for p in members):
+            raise RuntimeError("Coefficient line split across components.")
+        tshape, bases = arena.items[slot.owner]
+        tsh, shp = arena.shapes[slot.owner]
+        # strides of the local coefficient array (C order)
+        strides = [1] * len(shp)
+        for ax in range(len(shp) - 2, -1, -1):
+            strides[ax] = strides[ax + 1] * shp[ax + 1]
+        comp_stride = int(np.prod(shp, dtype=int))
+        base = arena.offsets[slot.owner] + slot.comp * comp_stride
+        key = []
+        for i, ax in enumerate(b.sep_axes):
+            bs = bases[ax]
+            if bs is not None:
+                base += slot.par[i] * strides[ax]
+                key.append((ax, bs.group_size * strides[ax]))
+        key = tuple(key)
+        if key not in kinds:
+            kinds[key] = len(kind_tables)
+            off_s = np.zeros(batch.S, dtype=np.int64)
+            for ax, st in key:
+                i = b.sep_axes.index(ax)
+                g = batch.groups[:, i] - (g0_start if ax == 0 else 0)
+                off_s += g * st
+            kind_tables.append(off_s)
+        lines.append((base, kinds[key], slot.size, members))
+    m = BatchProgram()
+    m.line_base = np.array([l[0] for l in lines], dtype=np.int64)
+    m.line_kind = np.array([l[1] for l in lines], dtype=np.int32)
+    m.line_len = np.array([l[2] for l in lines], dtype=np.int32)
+    m.line_ptr = np.concatenate([[0], np.cumsum(m.line_len)]).astype(np.int32)
+    m.line_pos = np.concatenate([np.asarray(l[3], dtype=np.int32) for l in lines]) if lines else np.zeros(0, np.int32)
+    m.sys_off = np.stack(kind_tables, axis=0) if kind_tables else np.zeros((1, batch.S), dtype=np.int64)
+    return m
+
+
+def build_batches(builder):
+    batches = []
+    for cls in builder.classes.values():
+        if len(cls.groups) == 0 or cls.shape[0] == 0:
+            continue
+        for rows, cols in split_components(cls):
+            batches.append(Batch(builder, cls, rows, cols))
+    return batches

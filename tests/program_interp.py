@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE: numpy interpreters of the batch programs built by dedalus_b200/pencils.py.
+They execute exactly what csrc/pencil.cu executes per thread (one system per thread, SoA arrays
+[entry][system]) and are used by the CPU tests to validate the programs against dense/sparse solves."""
+import numpy as np
+
+
+def assemble(prog, asm):
+    ptr, mono, val = asm
+    LU = np.zeros((prog.nE, prog.S))
+    for e in range(prog.nE):
+        for t in range(ptr[e], ptr[e + 1]):
+            LU[e] += val[t] * prog.mono_vals[mono[t]]
+    return LU
+
+
+def factor(prog, LU):
+    n = prog.n
+    dp = 0
+    for k in range(n):
+        d = prog.diag_eid[k]
+        inv = 1.0 / LU[d]
+        LU[d] = inv
+        us = prog.fu_eid[prog.fu_ptr[k]:prog.fu_ptr[k + 1]]
+        for a in range(prog.fl_ptr[k], prog.fl_ptr[k + 1]):
+            le = prog.fl_eid[a]
+            l = LU[le] * inv
+            LU[le] = l
+            for ue in us:
+                LU[prog.fd_eid[dp]] -= l * LU[ue]
+                dp += 1
+    return LU
+
+
+def solve(prog, LU, rhs):
+    n = prog.n
+    y = np.array(rhs, dtype=float, copy=True)
+    e = 0
+    for i in range(n):
+        acc = y[i].copy()
+        for t in range(prog.fwd_ptr[i], prog.fwd_ptr[i + 1]):
+            acc -= LU[e] * y[prog.fwd_col[t]]
+            e += 1
+        y[i] = acc
+    for pos, i in enumerate(range(n - 1, -1, -1)):
+        inv = LU[e]; e += 1
+        acc = y[i].copy()
+        for t in range(prog.bwd_ptr[pos], prog.bwd_ptr[pos + 1]):
+            acc -= LU[e] * y[prog.bwd_col[t]]
+            e += 1
+        y[i] = acc * inv
+    assert e == prog.nE
+    return y
+
+
+def matvec(prog, name, x):
+    ptr, col, mono, val = prog.mv[name]
+    y = np.zeros_like(x)
+    for i in range(prog.n):
+        for t in range(ptr[i], ptr[i + 1]):
+            y[i] += val[t] * prog.mono_vals[mono[t]] * x[col[t]]
+    return y
+
+
+def gather(maps, arena, n, S):
+    X = np.zeros((n, S))
+    for q in range(len(maps.line_base)):
+        for m in range(maps.line_len[q]):
+            pos = maps.line_pos[maps.line_ptr[q] + m]
+            X[pos] = arena[maps.line_base[q] + maps.sys_off[maps.line_kind[q]] + m]
+    return X
+
+
+def scatter(maps, X, arena):
+    for q in range(len(maps.line_base)):
+        for m in range(maps.line_len[q]):
+            pos = maps.line_pos[maps.line_ptr[q] + m]
+            arena[maps.line_base[q] + maps.sys_off[maps.line_kind[q]] + m] = X[pos]
