@@ -1,0 +1,510 @@
+// Batched 1-D spectral transforms along one axis of an N-D array (T1, T2, T3).
+//
+// One CTA owns a tile of T adjacent lines of the (outer, n, inner) view, stages it in shared memory as
+// complex[nc][T+1], runs an in-place mixed-radix FFT (DIF forward: natural in -> digit-reversed out;
+// DIT backward: digit-reversed in -> natural out, so no separate permutation pass is ever made: the
+// reference's pack / scale / truncate / zero-pad steps read or write through the permutation), and fuses the
+// Dedalus conventions into the load and store stages:
+//   * RealFourier  : cos/-sin interleaving, 1/N and 2/N scaling, Nyquist drop, dealias pad / truncate,
+//                    optional coefficient-space derivative (i k)^m on the backward load
+//   * Chebyshev    : DCT-II / DCT-III through the same half-length complex FFT (even/odd reordering +
+//                    quarter-wave twiddle), Jacobi normalisation, odd-mode sign flip, truncation,
+//                    banded ultraspherical conversion apply (forward) / apply + back-substitution (backward)
+//   * ComplexFourier: [0..K,(Nyq),-K..-1] ordering, 1/N scaling
+// HBM traffic is exactly one read of the input and one write of the output; loads / stores are coalesced
+// along the contiguous direction of the view (across lines when inner > 1, along the line when inner == 1).
+#include "db_common.cuh"
+
+enum { K_RFWD = 0, K_RBWD = 1, K_CFWD = 2, K_CBWD = 3, K_CHFWD = 4, K_CHBWD = 5 };
+#define FFT_THREADS 256
+
+struct FftArgs {
+    db_fft_plan plan;
+    const double* in;
+    double* out;
+    int64_t outer, inner;
+    int32_t n_coeff;
+    int32_t T, TP;
+    int32_t deriv;
+    double kscale;
+    const double* diags_a; int32_t nd_a;    // forward: conversion apply ; backward: pre-apply
+    const double* diags_b; int32_t nd_b;    // backward: upper solve
+    int32_t cof_off;                        // offset (doubles) of the coefficient staging area in smem
+    int64_t tiles_per_outer;
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a * conj(b)
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double2 ldtw(const double* tw, int j) { return make_double2(tw[2 * j], tw[2 * j + 1]); }
+
+// small DFTs; INV selects exp(+i...) kernels
+template <bool INV> __device__ __forceinline__ void dft2(double2* v)
+{
+    double2 a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+}
+template <bool INV> __device__ __forceinline__ void dft4(double2* v)
+{
+    double2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+    // forward: -i*d ; inverse: +i*d
+    double2 jd = INV ? make_double2(-d.y, d.x) : make_double2(d.y, -d.x);
+    v[0] = cadd(a, c); v[2] = csub(a, c);
+    v[1] = cadd(b, jd); v[3] = csub(b, jd);
+}
+template <bool INV> __device__ __forceinline__ void dft3(double2* v)
+{
+    const double s = 0.86602540378443864676372317075294;   // sin(pi/3)
+    double2 t1 = cadd(v[1], v[2]);
+    double2 t2 = make_double2(v[0].x - 0.5 * t1.x, v[0].y - 0.5 * t1.y);
+    double2 d = csub(v[1], v[2]);
+    // forward: -i*s*d ; inverse: +i*s*d
+    double2 t3 = INV ? make_double2(-s * d.y, s * d.x) : make_double2(s * d.y, -s * d.x);
+    v[0] = cadd(v[0], t1);
+    v[1] = cadd(t2, t3);
+    v[2] = csub(t2, t3);
+}
+// generic radix (<= 16) through the twiddle table: w_r^j = tw[(nc/r) * j]
+template <bool INV> __device__ __forceinline__ void dftr(double2* v, int r, const double* tw, int nc)
+{
+    double2 y[16];
+    const int step = nc / r;
+    for (int qp = 0; qp < r; ++qp) {
+        double2 acc = v[0];
+        for (int q = 1; q < r; ++q) {
+            double2 w = ldtw(tw, step * ((q * qp) % r));
+            acc = cadd(acc, INV ? cmulc(v[q], w) : cmul(v[q], w));
+        }
+        y[qp] = acc;
+    }
+    for (int q = 0; q < r; ++q) v[q] = y[q];
+}
+
+template <bool INV>
+__device__ void fft_pass(double2* buf, int nc, int TP, int Tc, int r, int L, const double* tw)
+{
+    const int m = L / r;
+    const int nbf = nc / r;
+    const int tstep = nc / L;
+    for (int w = threadIdx.x; w < nbf * Tc; w += blockDim.x) {
+        const int t = w % Tc;
+        const int bf = w / Tc;
+        const int b = bf / m, k = bf - b * m;
+        double2 v[16];
+        const int i0 = b * L + k;
+        for (int q = 0; q < r; ++q) v[q] = buf[(i0 + q * m) * TP + t];
+        if (INV) {   // DIT: twiddle first (conjugate), then butterfly
+            for (int q = 1; q < r; ++q) v[q] = cmulc(v[q], ldtw(tw, (tstep * k * q) % nc));
+        }
+        if (r == 4) dft4<INV>(v);
+        else if (r == 2) dft2<INV>(v);
+        else if (r == 3) dft3<INV>(v);
+        else dftr<INV>(v, r, tw, nc);
+        if (!INV) {  // DIF: butterfly first, then twiddle
+            for (int q = 1; q < r; ++q) v[q] = cmul(v[q], ldtw(tw, (tstep * k * q) % nc));
+        }
+        for (int q = 0; q < r; ++q) buf[(i0 + q * m) * TP + t] = v[q];
+    }
+}
+
+__device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int Tc)
+{
+    int L = p.nc;
+    for (int s = 0; s < p.nrad; ++s) {
+        fft_pass<false>(buf, p.nc, TP, Tc, p.rad[s], L, p.tw);
+        L /= p.rad[s];
+        __syncthreads();
+    }
+}
+__device__ void fft_dit(double2* buf, const db_fft_plan& p, int TP, int Tc)
+{
+    int Ls[16];
+    int L = p.nc;
+    for (int s = 0; s < p.nrad; ++s) { Ls[s] = L; L /= p.rad[s]; }
+    for (int s = p.nrad - 1; s >= 0; --s) {
+        fft_pass<true>(buf, p.nc, TP, Tc, p.rad[s], Ls[s], p.tw);
+        __syncthreads();
+    }
+}
+
+// element (j, t) of the tile in global memory: lines are adjacent along `inner` (strided mode) or whole
+// contiguous lines (inner == 1)
+struct TileGeom {
+    int64_t base;     // offset of (line 0 of tile, element 0)
+    int64_t estride;  // stride between consecutive elements of a line
+    int64_t lstride;  // stride between consecutive lines of the tile
+    int Tc;           // lines in this tile
+};
+
+__device__ __forceinline__ TileGeom tile_geom(const FftArgs& a, int len, int cplx)
+{
+    TileGeom g;
+    const int64_t tile = blockIdx.x;
+    if (a.inner == 1) {
+        int64_t l0 = tile * a.T;
+        int64_t rem = a.outer - l0;
+        g.Tc = rem < a.T ? (int)rem : a.T;
+        g.base = l0 * len * cplx;
+        g.estride = cplx;
+        g.lstride = (int64_t)len * cplx;
+    } else {
+        int64_t o = tile / a.tiles_per_outer;
+        int64_t i0 = (tile - o * a.tiles_per_outer) * a.T;
+        int64_t rem = a.inner - i0;
+        g.Tc = rem < a.T ? (int)rem : a.T;
+        g.base = (o * len * a.inner + i0) * cplx;
+        g.estride = a.inner * cplx;
+        g.lstride = cplx;
+    }
+    return g;
+}
+
+// iterate over (j, t) with the global-memory-contiguous index fastest across threads
+#define TILE_FOR(len, g, contiguous, j, t)                                                   \
+    for (int _e = threadIdx.x, _tot = (len) * (g).Tc; _e < _tot; _e += blockDim.x)           \
+        for (int _once = 1, j = (contiguous) ? _e % (len) : _e / (g).Tc,                     \
+                 t = (contiguous) ? _e / (len) : _e % (g).Tc; _once; _once = 0)
+
+template <int KIND>
+__global__ void __launch_bounds__(FFT_THREADS) k_fft(FftArgs a)
+{
+    DB_SMEM(double, smem);
+    double2* buf = reinterpret_cast<double2*>(smem);
+    double* cof = smem + a.cof_off;
+    const db_fft_plan& p = a.plan;
+    const int n = p.n, nc = p.nc, M = a.n_coeff, TP = a.TP;
+    const bool contiguous = (a.inner == 1);
+    const bool is_fwd = (KIND == K_RFWD || KIND == K_CFWD || KIND == K_CHFWD);
+    const bool is_cplx = (KIND == K_CFWD || KIND == K_CBWD);
+    const int cplx = is_cplx ? 2 : 1;
+    const TileGeom gi = tile_geom(a, is_fwd ? n : M, cplx);
+    const TileGeom go = tile_geom(a, is_fwd ? M : n, cplx);
+    const int Tc = gi.Tc;
+
+    if (is_fwd) {
+        // ---------------- load grid data straight into the complex work buffer ----------------
+        if (KIND == K_CFWD) {
+            TILE_FOR(n, gi, contiguous, j, t) {
+                const double* src = a.in + gi.base + j * gi.estride + t * gi.lstride;
+                buf[j * TP + t] = make_double2(src[0], src[1]);
+            }
+        } else {
+            double* rb = smem;   // real view: element p of line t at ((p>>1)*TP + t)*2 + (p&1)   (half) or (p*TP+t)*2 (full)
+            TILE_FOR(n, gi, contiguous, j, t) {
+                double v = a.in[gi.base + j * gi.estride + t * gi.lstride];
+                int pp = j;
+                if (KIND == K_CHFWD) pp = (j & 1) ? (n - 1 - (j >> 1)) : (j >> 1);
+                if (p.half) rb[((pp >> 1) * TP + t) * 2 + (pp & 1)] = v;
+                else { rb[(pp * TP + t) * 2] = v; rb[(pp * TP + t) * 2 + 1] = 0.0; }
+            }
+        }
+        __syncthreads();
+        fft_dif(buf, p, TP, Tc);
+        // ---------------- post-processing into the coefficient staging area ----------------
+        if (KIND == K_CFWD) {
+            const int KM = (M - 1) / 2;
+            int Kmax = (n - 1) / 2; if (KM < Kmax) Kmax = KM;
+            const double sc = 1.0 / n;
+            for (int w = threadIdx.x; w < M * Tc; w += blockDim.x) {
+                const int t = w % Tc, c = w / Tc;
+                const int k = (c + KM) % M - KM;
+                double2 z = make_double2(0.0, 0.0);
+                if (k <= Kmax && -k <= Kmax) {
+                    const int kk = (k % n + n) % n;
+                    z = buf[p.iperm[kk] * TP + t];
+                    z.x *= sc; z.y *= sc;
+                }
+                cof[(c * TP + t) * 2] = z.x; cof[(c * TP + t) * 2 + 1] = z.y;
+            }
+        } else if (KIND == K_RFWD) {
+            int Kmax = (n - 1) / 2; { int KM = (M - 1) / 2; if (KM < Kmax) Kmax = KM; }
+            const int nk = (M + 1) / 2;
+            for (int w = threadIdx.x; w < nk * Tc; w += blockDim.x) {
+                const int t = w % Tc, k = w / Tc;
+                double re = 0.0, im = 0.0;
+                if (k <= Kmax) {
+                    double2 X;
+                    if (p.half) {
+                        double2 zk = buf[p.iperm[k % nc] * TP + t];
+                        double2 zn = cconj(buf[p.iperm[(nc - k) % nc] * TP + t]);
+                        double2 E = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
+                        double2 D = csub(zk, zn);
+                        double2 O = make_double2(0.5 * D.y, -0.5 * D.x);          // -i/2 * D
+                        X = cadd(E, cmul(ldtw(p.twr, k), O));
+                    } else {
+                        X = buf[p.iperm[k] * TP + t];
+                    }
+                    const double sc = (k == 0) ? 1.0 / n : 2.0 / n;
+                    re = X.x * sc; im = (k == 0) ? 0.0 : X.y * sc;
+                }
+                cof[(2 * k) * TP + t] = re;
+                if (2 * k + 1 < M) cof[(2 * k + 1) * TP + t] = im;
+            }
+        } else {  // K_CHFWD
+            const int Kin = (M < n) ? M : n;           // coefficients kept before conversion
+            const double s0 = 0.5 / n * 1.7724538509055160272981674833411;      // sqrt(pi)/(2N)
+            const double s1 = 1.0 / n * 1.2533141373155002512078826424055;      // sqrt(pi/2)/N
+            if (p.half) {
+                for (int w = threadIdx.x; w < (nc + 1) * Tc; w += blockDim.x) {
+                    const int t = w % Tc, k = w / Tc;
+                    double2 zk = buf[p.iperm[k % nc] * TP + t];
+                    double2 zn = cconj(buf[p.iperm[(nc - k) % nc] * TP + t]);
+                    double2 E = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
+                    double2 D = csub(zk, zn);
+                    double2 O = make_double2(0.5 * D.y, -0.5 * D.x);
+                    double2 X = cadd(E, cmul(ldtw(p.twr, k), O));
+                    double2 W = cmul(ldtw(p.twq, k), X);
+                    if (k < Kin) {
+                        double v = 2.0 * W.x * ((k == 0) ? s0 : s1);
+                        cof[k * TP + t] = (k & 1) ? -v : v;
+                    }
+                    const int k2 = n - k;
+                    if (k >= 1 && k2 > nc && k2 < Kin) {
+                        double v = -2.0 * W.y * s1;
+                        cof[k2 * TP + t] = (k2 & 1) ? -v : v;
+                    }
+                }
+            } else {
+                for (int w = threadIdx.x; w < Kin * Tc; w += blockDim.x) {
+                    const int t = w % Tc, k = w / Tc;
+                    double2 W = cmul(ldtw(p.twq, k), buf[p.iperm[k] * TP + t]);
+                    double v = 2.0 * W.x * ((k == 0) ? s0 : s1);
+                    cof[k * TP + t] = (k & 1) ? -v : v;
+                }
+            }
+            for (int w = threadIdx.x + Kin * Tc; w < M * Tc; w += blockDim.x) cof[(w / Tc) * TP + (w % Tc)] = 0.0;
+        }
+        __syncthreads();
+        // ---------------- store (with the banded conversion fused for Chebyshev) ----------------
+        if (KIND == K_CFWD) {
+            TILE_FOR(M, go, contiguous, c, t) {
+                double* dst = a.out + go.base + c * go.estride + t * go.lstride;
+                dst[0] = cof[(c * TP + t) * 2]; dst[1] = cof[(c * TP + t) * 2 + 1];
+            }
+        } else if (KIND == K_CHFWD && a.nd_a > 0) {
+            const int Kin = (M < n) ? M : n;
+            TILE_FOR(M, go, contiguous, i, t) {
+                double acc = 0.0;
+                if (i < Kin) {
+                    for (int d = 0; d < a.nd_a && i + d < Kin; ++d)
+                        acc = fma(a.diags_a[(int64_t)d * M + i], cof[(i + d) * TP + t], acc);
+                }
+                a.out[go.base + i * go.estride + t * go.lstride] = acc;
+            }
+        } else {
+            TILE_FOR(M, go, contiguous, c, t) {
+                a.out[go.base + c * go.estride + t * go.lstride] = cof[c * TP + t];
+            }
+        }
+    } else {
+        // ================= backward: stage coefficients =================
+        if (KIND == K_CBWD) {
+            TILE_FOR(M, gi, contiguous, c, t) {
+                const double* src = a.in + gi.base + c * gi.estride + t * gi.lstride;
+                cof[(c * TP + t) * 2] = src[0]; cof[(c * TP + t) * 2 + 1] = src[1];
+            }
+        } else {
+            TILE_FOR(M, gi, contiguous, c, t) {
+                cof[c * TP + t] = a.in[gi.base + c * gi.estride + t * gi.lstride];
+            }
+        }
+        __syncthreads();
+        if (KIND == K_CHBWD) {
+            int Kmax = n - 1; if (M - 1 < Kmax) Kmax = M - 1;
+            // per-line banded work: truncate, pre-apply (ascending, in place), back-substitution (descending)
+            if ((a.nd_a > 0 || a.nd_b > 0 || M > n) && (int)threadIdx.x < Tc) {
+                const int t = threadIdx.x;
+                if (M > n) for (int i = Kmax + 1; i < M; ++i) cof[i * TP + t] = 0.0;
+                if (a.nd_a > 0) {
+                    for (int i = 0; i < M; ++i) {
+                        double acc = 0.0;
+                        for (int d = 0; d < a.nd_a && i + d < M; ++d)
+                            acc = fma(a.diags_a[(int64_t)d * M + i], cof[(i + d) * TP + t], acc);
+                        cof[i * TP + t] = acc;
+                    }
+                }
+                if (a.nd_b > 0) {
+                    for (int i = M - 1; i >= 0; --i) {
+                        double acc = cof[i * TP + t];
+                        for (int d = 1; d < a.nd_b && i + d < M; ++d)
+                            acc = fma(-a.diags_b[(int64_t)d * M + i], cof[(i + d) * TP + t], acc);
+                        cof[i * TP + t] = acc / a.diags_b[i];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ================= build the (digit-reversed) spectrum for the DIT passes =================
+        if (KIND == K_CBWD) {
+            const int KM = (M - 1) / 2;
+            int Kmax = (n - 1) / 2; if (KM < Kmax) Kmax = KM;
+            for (int w = threadIdx.x; w < nc * Tc; w += blockDim.x) {
+                const int t = w % Tc, pos = w / Tc;
+                int k = p.perm[pos];
+                if (k > n / 2) k -= n;                       // signed wavenumber
+                double2 z = make_double2(0.0, 0.0);
+                if (k <= Kmax && -k <= Kmax) {
+                    const int c = (k >= 0) ? k : M + k;
+                    z = make_double2(cof[(c * TP + t) * 2], cof[(c * TP + t) * 2 + 1]);
+                    if (a.deriv > 0) {
+                        double f = 1.0;
+                        for (int d = 0; d < a.deriv; ++d) f *= a.kscale * k;
+                        const int ph = a.deriv & 3;
+                        double2 r = (ph == 0) ? make_double2(z.x, z.y) : (ph == 1) ? make_double2(-z.y, z.x)
+                                  : (ph == 2) ? make_double2(-z.x, -z.y) : make_double2(z.y, -z.x);
+                        z = make_double2(r.x * f, r.y * f);
+                    }
+                }
+                buf[pos * TP + t] = z;
+            }
+        } else {
+            // half-spectrum value X_k (k = 0..nc) as a function of the staged real coefficients
+            int Kmax;
+            if (KIND == K_RBWD) { Kmax = (n - 1) / 2; int KM = (M - 1) / 2; if (KM < Kmax) Kmax = KM; }
+            else { Kmax = n - 1; if (M - 1 < Kmax) Kmax = M - 1; }
+            const double c0 = 0.56418958354775628694807945156077;     // 1/sqrt(pi)
+            const double c1 = 0.39894228040143267793994605993438;     // 1/(2 sqrt(pi/2)) = 1/sqrt(2 pi)
+            auto chat = [&](int k, int t) -> double {              // scaled, sign-flipped Chebyshev coefficient
+                if (k > Kmax || k >= n) return 0.0;
+                double v = cof[k * TP + t] * ((k == 0) ? c0 : c1);
+                return (k & 1) ? -v : v;
+            };
+            auto getX = [&](int k, int t) -> double2 {
+                if (KIND == K_RBWD) {
+                    if (k > Kmax) return make_double2(0.0, 0.0);
+                    if (k == 0) {
+                        return make_double2((a.deriv > 0) ? 0.0 : cof[t], 0.0);
+                    }
+                    double2 z = make_double2(0.5 * cof[(2 * k) * TP + t], 0.5 * cof[(2 * k + 1) * TP + t]);
+                    if (a.deriv > 0) {
+                        double f = 1.0;
+                        for (int d = 0; d < a.deriv; ++d) f *= a.kscale * k;
+                        const int ph = a.deriv & 3;
+                        double2 r = (ph == 0) ? z : (ph == 1) ? make_double2(-z.y, z.x)
+                                  : (ph == 2) ? make_double2(-z.x, -z.y) : make_double2(z.y, -z.x);
+                        z = make_double2(r.x * f, r.y * f);
+                    }
+                    return z;
+                } else {
+                    if (k == 0) return make_double2(chat(0, t), 0.0);
+                    // H_k = exp(i pi k / 2n) (c_k - i c_{n-k})
+                    double2 w = cconj(ldtw(p.twq, k));
+                    double2 v = make_double2(chat(k, t), -chat(n - k, t));
+                    return cmul(w, v);
+                }
+            };
+            if (p.half) {
+                for (int w = threadIdx.x; w < nc * Tc; w += blockDim.x) {
+                    const int t = w % Tc, pos = w / Tc;
+                    const int k = p.perm[pos];
+                    double2 xk = getX(k, t);
+                    double2 xn = cconj(getX(nc - k, t));
+                    double2 E = cadd(xk, xn);
+                    double2 O = cmulc(csub(xk, xn), ldtw(p.twr, k));          // * w^{-k}
+                    buf[pos * TP + t] = make_double2(E.x - O.y, E.y + O.x);     // E + i O
+                }
+            } else {
+                for (int w = threadIdx.x; w < nc * Tc; w += blockDim.x) {
+                    const int t = w % Tc, pos = w / Tc;
+                    const int k = p.perm[pos];
+                    double2 z;
+                    if (KIND == K_RBWD) {
+                        // hermitian extension: Z_k = X_k (k <= n/2), Z_k = conj X_{n-k} otherwise; X holds c_k/2
+                        if (2 * k <= n) z = getX(k, t);
+                        else z = cconj(getX(n - k, t));
+                    } else {
+                        // G_k = c'_k exp(i pi k / 2n), c'_0 = c_0, c'_k = 2 c_k ; output = Re IDFT(G)
+                        double ck = chat(k, t) * ((k == 0) ? 1.0 : 2.0);
+                        double2 ww = cconj(ldtw(p.twq, k));
+                        z = make_double2(ww.x * ck, ww.y * ck);
+                    }
+                    buf[pos * TP + t] = z;
+                }
+            }
+        }
+        __syncthreads();
+        fft_dit(buf, p, TP, Tc);
+        // ================= store grid data =================
+        if (KIND == K_CBWD) {
+            TILE_FOR(n, go, contiguous, j, t) {
+                double2 z = buf[j * TP + t];
+                double* dst = a.out + go.base + j * go.estride + t * go.lstride;
+                dst[0] = z.x; dst[1] = z.y;
+            }
+        } else {
+            const double* rb = smem;
+            TILE_FOR(n, go, contiguous, j, t) {
+                int pp = j;
+                if (KIND == K_CHBWD) pp = (j & 1) ? (n - 1 - (j >> 1)) : (j >> 1);
+                double v = p.half ? rb[((pp >> 1) * TP + t) * 2 + (pp & 1)] : rb[(pp * TP + t) * 2];
+                a.out[go.base + j * go.estride + t * go.lstride] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+template <int KIND>
+static int launch_fft(const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff, int64_t inner,
+                      int32_t deriv, double kscale, const double* da, int32_t nda, const double* db_, int32_t ndb,
+                      void* stream, const char* name)
+{
+    if (outer <= 0 || inner <= 0) return 0;
+    if (plan->n <= 0 || plan->nc <= 0 || n_coeff <= 0) { db_set_error("%s: bad sizes", name); return 1; }
+    FftArgs a;
+    a.plan = *plan; a.in = in; a.out = out; a.outer = outer; a.inner = inner; a.n_coeff = n_coeff;
+    a.deriv = deriv; a.kscale = kscale; a.diags_a = da; a.nd_a = nda; a.diags_b = db_; a.nd_b = ndb;
+    const bool is_cplx = (KIND == K_CFWD || KIND == K_CBWD);
+    // choose the tile width: up to 16 lines, shrunk until the CTA fits ~110 KB (2 CTAs / SM) or, failing that,
+    // the 227 KB per-CTA limit
+    int T = 16;
+    const int64_t lines_dir = (inner == 1) ? outer : inner;
+    auto smem_bytes = [&](int t) -> size_t {
+        return ((size_t)2 * plan->nc * (t + 1) + (size_t)(is_cplx ? 2 : 1) * n_coeff * (t + 1)) * sizeof(double);
+    };
+    while (T > 1 && smem_bytes(T) > (size_t)110 * 1024) T /= 2;
+    while (T > 1 && T / 2 >= lines_dir) T /= 2;    // do not waste lanes on tiny problems
+    size_t bytes = smem_bytes(T);
+    if (bytes > (size_t)DB_MAX_SMEM) { db_set_error("%s: transform length %d too large for shared memory", name, plan->n); return 1; }
+    a.T = T; a.TP = T + 1;
+    a.cof_off = 2 * plan->nc * a.TP;
+    int64_t tiles;
+    if (inner == 1) { a.tiles_per_outer = 0; tiles = (outer + T - 1) / T; }
+    else { a.tiles_per_outer = (inner + T - 1) / T; tiles = outer * a.tiles_per_outer; }
+    if (tiles > 2147483647LL) { db_set_error("%s: too many tiles", name); return 1; }
+#ifndef DB_EMU
+    static bool attr_set[6] = {false, false, false, false, false, false};
+    if (!attr_set[KIND]) {
+        cudaFuncSetAttribute(k_fft<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        attr_set[KIND] = true;
+    }
+#endif
+    DB_LAUNCH(k_fft<KIND>, dim3((unsigned)tiles), dim3(FFT_THREADS), bytes, stream, a);
+    return db_check_launch(name);
+}
+
+extern "C" int db_rfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream)
+{ return launch_fft<K_RFWD>(plan, g, c, outer, n_coeff, inner, 0, 0.0, nullptr, 0, nullptr, 0, stream, "rfft_forward"); }
+
+extern "C" int db_rfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                                int32_t deriv, double kscale, void* stream)
+{ return launch_fft<K_RBWD>(plan, c, g, outer, n_coeff, inner, deriv, kscale, nullptr, 0, nullptr, 0, stream, "rfft_backward"); }
+
+extern "C" int db_cfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream)
+{ return launch_fft<K_CFWD>(plan, g, c, outer, n_coeff, inner, 0, 0.0, nullptr, 0, nullptr, 0, stream, "cfft_forward"); }
+
+extern "C" int db_cfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                                int32_t deriv, double kscale, void* stream)
+{ return launch_fft<K_CBWD>(plan, c, g, outer, n_coeff, inner, deriv, kscale, nullptr, 0, nullptr, 0, stream, "cfft_backward"); }
+
+extern "C" int db_cheb_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner,
+                               const double* conv_diags, int32_t conv_ndiag, void* stream)
+{ return launch_fft<K_CHFWD>(plan, g, c, outer, n_coeff, inner, 0, 0.0, conv_diags, conv_ndiag, nullptr, 0, stream, "cheb_forward"); }
+
+extern "C" int db_cheb_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                                const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream)
+{ return launch_fft<K_CHBWD>(plan, c, g, outer, n_coeff, inner, 0, 0.0, pre_diags, pre_ndiag, solve_diags, solve_ndiag, stream, "cheb_backward"); }

@@ -1,0 +1,205 @@
+// Grid-space products (P1): generic "sum of products" evaluator and dense matrix transform (T4).
+//
+// Reference: DotProduct.operate (np.einsum), MultiplyFields.operate, AddFields.operate evaluated one node at a
+// time on full grid arrays (core/arithmetic.py:246-251, 666-674, 855-866) -> every intermediate is a full HBM
+// round trip.  Here the whole right-hand-side polynomial of an equation set is one kernel: each CTA stages a
+// tile of all inputs in shared memory (every input element read from HBM exactly once, coalesced), evaluates
+// all outputs from it and writes each output once.
+#include "db_common.cuh"
+
+#define PW_TILE 256
+
+__global__ void __launch_bounds__(PW_TILE)
+k_pointwise(const double* __restrict__ in, double* __restrict__ out, int64_t npoints, int n_in, int n_out,
+            const int32_t* __restrict__ term_ptr, const double* __restrict__ coef,
+            const int32_t* __restrict__ fac_ptr, const int32_t* __restrict__ fac)
+{
+    DB_SMEM(double, tile);                         // [n_in][PW_TILE]
+    for (int64_t p0 = (int64_t)blockIdx.x * PW_TILE; p0 < npoints; p0 += (int64_t)gridDim.x * PW_TILE) {
+        const int64_t p = p0 + threadIdx.x;
+        const bool live = p < npoints;
+        for (int i = 0; i < n_in; ++i)
+            tile[i * PW_TILE + threadIdx.x] = live ? in[(int64_t)i * npoints + p] : 0.0;
+        // each thread only touches its own column: no barrier needed
+        if (live) {
+            for (int o = 0; o < n_out; ++o) {
+                double acc = 0.0;
+                for (int t = term_ptr[o]; t < term_ptr[o + 1]; ++t) {
+                    double prod = coef[t];
+                    for (int f = fac_ptr[t]; f < fac_ptr[t + 1]; ++f)
+                        prod *= tile[fac[f] * PW_TILE + threadIdx.x];
+                    acc += prod;
+                }
+                out[(int64_t)o * npoints + p] = acc;
+            }
+        }
+    }
+}
+
+extern "C" int db_pointwise(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
+                            const int32_t* term_ptr, const double* coef, const int32_t* fac_ptr, const int32_t* fac, int32_t nfac_total,
+                            void* stream)
+{
+    (void)nfac_total;
+    if (npoints <= 0 || n_out <= 0) return 0;
+    size_t smem = (size_t)n_in * PW_TILE * sizeof(double);
+    if (smem > (size_t)DB_MAX_SMEM) { db_set_error("pointwise: too many inputs (%d)", n_in); return 1; }
+    int64_t blocks = (npoints + PW_TILE - 1) / PW_TILE;
+    const int64_t cap = 148 * 8;
+    if (blocks > cap) blocks = cap;
+#ifndef DB_EMU
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_pointwise, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM); attr = true; }
+#endif
+    DB_LAUNCH(k_pointwise, dim3((unsigned)blocks), dim3(PW_TILE), smem, stream, in, out, npoints, n_in, n_out, term_ptr, coef, fac_ptr, fac);
+    return db_check_launch("pointwise");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dense matrix transform along an axis (T4): out(o, i, r) = sum_j mat[i][j] in(o, j, r)
+// 64x64 output tiles, k-blocks of 16 staged in shared memory, 4x4 register micro-tiles (fp64 FMA pipe).
+// ---------------------------------------------------------------------------------------------------------
+#define MM_BM 64
+#define MM_BN 64
+#define MM_BK 16
+__global__ void __launch_bounds__(256)
+k_mmt(const double* __restrict__ mat, int m, int n, const double* __restrict__ in, double* __restrict__ out, int64_t outer, int64_t inner)
+{
+    DB_SMEM(double, sm);
+    double* As = sm;                     // [BK][BM]   (mat tile, transposed)
+    double* Bs = sm + MM_BK * MM_BM;     // [BK][BN]
+    const int64_t o = blockIdx.z;
+    const int i0 = blockIdx.y * MM_BM;
+    const int64_t r0 = (int64_t)blockIdx.x * MM_BN;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    double acc[4][4];
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const double* inb = in + o * n * inner;
+    for (int k0 = 0; k0 < n; k0 += MM_BK) {
+        for (int e = threadIdx.x; e < MM_BK * MM_BM; e += 256) {
+            int kk = e % MM_BK, ii = e / MM_BK;
+            int gi = i0 + ii, gk = k0 + kk;
+            As[kk * MM_BM + ii] = (gi < m && gk < n) ? mat[(int64_t)gi * n + gk] : 0.0;
+        }
+        for (int e = threadIdx.x; e < MM_BK * MM_BN; e += 256) {
+            int rr = e % MM_BN, kk = e / MM_BN;
+            int64_t gr = r0 + rr; int gk = k0 + kk;
+            Bs[kk * MM_BN + rr] = (gr < inner && gk < n) ? inb[(int64_t)gk * inner + gr] : 0.0;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < MM_BK; ++kk) {
+            double av[4], bv[4];
+            for (int a = 0; a < 4; ++a) av[a] = As[kk * MM_BM + ty * 4 + a];
+            for (int b = 0; b < 4; ++b) bv[b] = Bs[kk * MM_BN + tx * 4 + b];
+            for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+    double* outb = out + o * m * inner;
+    for (int a = 0; a < 4; ++a) {
+        int gi = i0 + ty * 4 + a;
+        if (gi >= m) continue;
+        for (int b = 0; b < 4; ++b) {
+            int64_t gr = r0 + tx * 4 + b;
+            if (gr < inner) outb[(int64_t)gi * inner + gr] = acc[a][b];
+        }
+    }
+}
+
+extern "C" int db_mmt_apply(const double* mat, int32_t m, int32_t n, const double* in, double* out, int64_t outer, int64_t inner, void* stream)
+{
+    if (outer <= 0 || inner <= 0 || m <= 0 || n <= 0) return 0;
+    if (outer > 65535) { db_set_error("mmt_apply: outer too large (%lld)", (long long)outer); return 1; }
+    dim3 grid((unsigned)((inner + MM_BN - 1) / MM_BN), (unsigned)((m + MM_BM - 1) / MM_BM), (unsigned)outer);
+    DB_LAUNCH(k_mmt, grid, dim3(256), (MM_BK * MM_BM + MM_BK * MM_BN) * sizeof(double), stream, mat, m, n, in, out, outer, inner);
+    return db_check_launch("mmt_apply");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Distributed-transpose pack / unpack (X1)
+// forward hop (towards grid space): local A (B, n1loc, n2, n3), n2 split in P blocks of n2blk:
+//   send[p][b][i][j][r] = A[b][i][p*n2blk + j][r]                       (contiguous per destination rank)
+//   after all-to-all rank holds recv[p][b][i][j][r] = rows i of source p -> out (B, n1 = P*n1blk, n2loc, n3):
+//   out[b][p*n1blk + i][j][r] = recv[p][b][i][j][r]
+// The reverse hop swaps the roles.  Blocks are assumed equal (n2 % P == 0, n1 % P == 0).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_tr_pack(const double* __restrict__ a, double* __restrict__ send, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int P)
+{
+    const int64_t n2blk = n2 / P;
+    const int64_t total = B * n1loc * n2 * n3;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e % n3; int64_t q = e / n3;
+        int64_t j2 = q % n2; q /= n2;
+        int64_t i = q % n1loc; int64_t b = q / n1loc;
+        int64_t p = j2 / n2blk, j = j2 - p * n2blk;
+        send[(((p * B + b) * n1loc + i) * n2blk + j) * n3 + r] = a[e];
+    }
+}
+__global__ void k_tr_unpack(const double* __restrict__ recv, double* __restrict__ out, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int P)
+{
+    const int64_t n1blk = n1 / P;
+    const int64_t total = B * n1 * n2loc * n3;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e % n3; int64_t q = e / n3;
+        int64_t j = q % n2loc; q /= n2loc;
+        int64_t i1 = q % n1; int64_t b = q / n1;
+        int64_t p = i1 / n1blk, i = i1 - p * n1blk;
+        out[e] = recv[(((p * B + b) * n1blk + i) * n2loc + j) * n3 + r];
+    }
+}
+// reverse hop: A (B, n1, n2loc, n3) -> send[p][b][i][j][r] = A[b][p*n1blk+i][j][r]; recv -> out (B, n1loc, n2, n3)
+__global__ void k_tr_pack_rev(const double* __restrict__ a, double* __restrict__ send, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int P)
+{
+    const int64_t n1blk = n1 / P;
+    const int64_t total = B * n1 * n2loc * n3;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e % n3; int64_t q = e / n3;
+        int64_t j = q % n2loc; q /= n2loc;
+        int64_t i1 = q % n1; int64_t b = q / n1;
+        int64_t p = i1 / n1blk, i = i1 - p * n1blk;
+        send[(((p * B + b) * n1blk + i) * n2loc + j) * n3 + r] = a[e];
+    }
+}
+__global__ void k_tr_unpack_rev(const double* __restrict__ recv, double* __restrict__ out, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int P)
+{
+    const int64_t n2blk = n2 / P;
+    const int64_t total = B * n1loc * n2 * n3;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = e % n3; int64_t q = e / n3;
+        int64_t j2 = q % n2; q /= n2;
+        int64_t i = q % n1loc; int64_t b = q / n1loc;
+        int64_t p = j2 / n2blk, j = j2 - p * n2blk;
+        out[e] = recv[(((p * B + b) * n1loc + i) * n2blk + j) * n3 + r];
+    }
+}
+
+static inline unsigned tr_blocks(int64_t total) { int64_t b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16; return (unsigned)b; }
+
+extern "C" int db_transpose_pack(const double* a, double* sendbuf, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int32_t P, void* stream)
+{
+    if (n2 % P) { db_set_error("transpose_pack: n2 not divisible by P"); return 1; }
+    int64_t total = B * n1loc * n2 * n3; if (total <= 0) return 0;
+    DB_LAUNCH(k_tr_pack, dim3(tr_blocks(total)), dim3(256), 0, stream, a, sendbuf, B, n1loc, n2, n3, P);
+    return db_check_launch("transpose_pack");
+}
+extern "C" int db_transpose_unpack(const double* recvbuf, double* out, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int32_t P, void* stream)
+{
+    if (n1 % P) { db_set_error("transpose_unpack: n1 not divisible by P"); return 1; }
+    int64_t total = B * n1 * n2loc * n3; if (total <= 0) return 0;
+    DB_LAUNCH(k_tr_unpack, dim3(tr_blocks(total)), dim3(256), 0, stream, recvbuf, out, B, n1, n2loc, n3, P);
+    return db_check_launch("transpose_unpack");
+}
+extern "C" int db_transpose_pack_rev(const double* a, double* sendbuf, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int32_t P, void* stream)
+{
+    if (n1 % P) { db_set_error("transpose_pack_rev: n1 not divisible by P"); return 1; }
+    int64_t total = B * n1 * n2loc * n3; if (total <= 0) return 0;
+    DB_LAUNCH(k_tr_pack_rev, dim3(tr_blocks(total)), dim3(256), 0, stream, a, sendbuf, B, n1, n2loc, n3, P);
+    return db_check_launch("transpose_pack_rev");
+}
+extern "C" int db_transpose_unpack_rev(const double* recvbuf, double* out, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int32_t P, void* stream)
+{
+    if (n2 % P) { db_set_error("transpose_unpack_rev: n2 not divisible by P"); return 1; }
+    int64_t total = B * n1loc * n2 * n3; if (total <= 0) return 0;
+    DB_LAUNCH(k_tr_unpack_rev, dim3(tr_blocks(total)), dim3(256), 0, stream, recvbuf, out, B, n1loc, n2, n3, P);
+    return db_check_launch("transpose_unpack_rev");
+}

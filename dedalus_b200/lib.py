@@ -1,0 +1,104 @@
+"""ctypes binding of the C ABI declared in include/dedalus_b200.h.
+
+The product loads ONLY dedalus_b200/libdedalus_b200.so (nvcc, sm_100a).  If it is missing or cannot be loaded
+the import of any compute path raises: there is no CPU fallback.  `bind()` is also used by the test-only CPU
+emulation (tests/emu/emu_lib.py) to attach the same prototypes to tests/emu/libdedalus_b200_emu.so.
+"""
+import ctypes as C
+import pathlib
+
+PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = PKG / "libdedalus_b200.so"
+
+i32, i64, f64, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+
+
+class FftPlan(C.Structure):
+    _fields_ = [("n", i32), ("nc", i32), ("half", i32), ("nrad", i32), ("rad", i32 * 16),
+                ("tw", vp), ("twr", vp), ("twq", vp), ("perm", vp), ("iperm", vp)]
+
+
+class LinComb(C.Structure):
+    _fields_ = [("nvec", i32), ("vec", vp * 16), ("coef", f64 * 16)]
+
+
+PFFT = C.POINTER(FftPlan)
+PLIN = C.POINTER(LinComb)
+
+SIGNATURES = {
+    "db_last_error": (C.c_char_p, []),
+    "db_version": (C.c_int, []),
+    "db_device_arch": (C.c_int, []),
+    "db_rfft_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp]),
+    "db_rfft_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, vp]),
+    "db_cfft_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp]),
+    "db_cfft_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, vp]),
+    "db_cheb_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp, i32, vp]),
+    "db_cheb_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp, i32, vp, i32, vp]),
+    "db_mmt_apply": (C.c_int, [vp, i32, i32, vp, vp, i64, i64, vp]),
+    "db_pointwise": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp]),
+    "db_pencil_gather": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
+    "db_pencil_scatter": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
+    "db_pencil_matvec": (C.c_int, [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "db_pencil_assemble": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "db_pencil_factor": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "db_pencil_solve": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, PLIN, vp, vp]),
+    "db_lincomb_apply": (C.c_int, [PLIN, vp, i64, vp]),
+    "db_transpose_pack": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
+    "db_transpose_unpack": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
+    "db_transpose_pack_rev": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
+    "db_transpose_unpack_rev": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
+    "db_absmax": (C.c_int, [vp, i64, vp, vp]),
+}
+
+
+class DedalusB200Error(RuntimeError):
+    pass
+
+
+class BoundLib:
+    def __init__(self, cdll):
+        self._cdll = cdll
+        missing = []
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(cdll, name)
+            except AttributeError:
+                missing.append(name)
+                continue
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, "_raw_" + name, fn)
+        if missing:
+            raise DedalusB200Error(f"library is missing C-ABI symbols: {missing}")
+
+    def call(self, name, *args):
+        rc = getattr(self, "_raw_" + name)(*args)
+        if rc != 0:
+            msg = self._raw_db_last_error()
+            raise DedalusB200Error(f"{name} failed (code {rc}): {msg.decode() if msg else ''}")
+
+    def version(self):
+        return self._raw_db_version()
+
+    def device_arch(self):
+        return self._raw_db_device_arch()
+
+
+def bind(path):
+    return BoundLib(C.CDLL(str(path)))
+
+
+_LIB = None
+
+
+def get_lib():
+    """Load the CUDA library (built in-tree by dedalus_b200/build.py). Fails loudly if it is absent."""
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise DedalusB200Error(
+                f"{LIB_PATH} not found: build it with `python -m dedalus_b200.build` (nvcc, sm_100a). "
+                "dedalus_b200 has no CPU fallback.")
+        _LIB = bind(LIB_PATH)
+    return _LIB

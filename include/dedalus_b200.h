@@ -1,0 +1,147 @@
+/* dedalus_b200 C ABI -- the drop-in boundary for the Dedalus per-timestep hot loop on B200 (sm_100a).
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer (fp64 unless stated; complex = interleaved re,im);
+ *     integer "program" arrays are device int32 pointers; `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = success, nonzero = error (message via db_last_error());
+ *   - no call synchronises the host; all work is enqueued on `stream`;
+ *   - arrays are C-contiguous views (outer, n, inner) with the transform along the middle axis, exactly the
+ *     (axis, shape) convention of the reference plugins' forward(gdata, cdata, axis) / backward(...)
+ *     (dedalus/core/transforms.py:54-75, basis.py:416-428); input and output buffers must not overlap.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef DEDALUS_B200_H
+#define DEDALUS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* db_last_error(void);
+int db_version(void);
+/* device / arch probe: returns compute capability major*10+minor of the current device, <0 on error */
+int db_device_arch(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Spectral transforms (T1-T4).  A "plan" is a small table block built by the host (dedalus_b200/fftplan.py)
+ * and uploaded once: radices, twiddles, digit-reversal permutation.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n;            /* transform length on the grid (real length for real transforms)          */
+    int32_t nc;           /* length of the in-shared-memory complex FFT (n/2 for even real, n else)   */
+    int32_t half;         /* 1 if the real transform uses the half-length complex trick (n even)      */
+    int32_t nrad;         /* number of radix passes                                                   */
+    int32_t rad[16];      /* radices, DIF order                                                       */
+    const double* tw;     /* [nc][2]  exp(-2 pi i j / nc)                                             */
+    const double* twr;    /* [nc+1][2] exp(-2 pi i k / n)   (real <-> half-complex post/pre twiddle)   */
+    const double* twq;    /* [n][2]  exp(-i pi k / (2n))    (DCT quarter-wave twiddle)                 */
+    const int32_t* perm;  /* [nc] frequency index held at position p after the DIF passes            */
+    const int32_t* iperm; /* [nc] position holding frequency k (inverse of perm)                      */
+} db_fft_plan;
+
+/* Real Fourier, cos/-sin interleaved coefficients, unit-amplitude normalisation, Nyquist dropped.
+ * Replaces FFTWRealFFT.forward/backward + RealFFT.unpack_rescale/repack_rescale
+ * (core/transforms.py:469-509, 537-565; libraries/fftw/fftw_wrappers.pyx:141-154, 188-207).
+ * g: (outer, n_grid, inner) real;  c: (outer, n_coeff, inner) real.
+ * backward: `deriv` >= 0 applies (d/dx)^deriv in coefficient space first, wavenumber spacing `kscale`
+ * (fuses DifferentiateRealFourier, core/basis.py:1203-1224, into the transform's load stage). */
+int db_rfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream);
+int db_rfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                     int32_t deriv, double kscale, void* stream);
+
+/* Complex Fourier, ordering [0..KM,(Nyq),-KM..-1], forward scaled by 1/N.
+ * Replaces FFTWComplexFFT (core/transforms.py:243-267, 302-330).  Arrays are interleaved complex. */
+int db_cfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream);
+int db_cfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                     int32_t deriv, double kscale, void* stream);
+
+/* Chebyshev / ultraspherical transforms on the Gauss-Chebyshev grid: DCT-II / DCT-III with the Jacobi
+ * unit-weight normalisation, sign flip of odd modes, truncation / zero padding, and optional banded
+ * spectral matrices.  Replaces FFTWFastChebyshevTransform (core/transforms.py:715-746, 771-902) and the
+ * apply_sparse / solve_upper_sparse calls inside it (tools/linalg.pyx:20-82, 189-258).
+ * Banded matrices are upper triangular, stored by diagonals: diag[d][i] = A[i][i+d], d < ndiag, row length n_coeff.
+ *   forward : coefficients = conv_apply( truncate( scale( DCT-II(g) ) ) )        (conv_ndiag = 0: none)
+ *   backward: g = DCT-III( scale( solve_upper(conv_solve, apply(pre_apply, c)) ) ) (either may be absent) */
+int db_cheb_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner,
+                    const double* conv_diags, int32_t conv_ndiag, void* stream);
+int db_cheb_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                     const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream);
+
+/* Dense matrix transform along an axis: out(o, i, r) = sum_j mat[i][j] * in(o, j, r).
+ * Replaces SeparableMatrixTransform -> apply_dense (core/transforms.py:54-75, tools/array.py:104-129). */
+int db_mmt_apply(const double* mat, int32_t m, int32_t n, const double* in, double* out, int64_t outer, int64_t inner, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Grid-space products (P1): every output is a sum of coef * product of inputs, evaluated pointwise.
+ * Replaces DotProduct.operate / MultiplyFields.operate / AddFields.operate chains
+ * (core/arithmetic.py:246-251, 666-674, 855-866).
+ * in: (n_in, npoints) stacked inputs, out: (n_out, npoints).  Program: for output o, terms
+ * term_ptr[o]..term_ptr[o+1]; term t has coefficient coef[t] and factors fac[fac_ptr[t]..fac_ptr[t+1]). */
+int db_pointwise(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
+                 const int32_t* term_ptr, const double* coef, const int32_t* fac_ptr, const int32_t* fac, int32_t nfac_total,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Pencil systems (S1-S4).  A batch holds S structurally identical systems of size n, stored
+ * structure-of-arrays: vec[i*ld + s], LU[e*ld + s]  (ld >= S, multiple of 32).  One thread owns one system.
+ * ------------------------------------------------------------------------------------------------------- */
+/* gather: field arena -> pencil vectors (Subproblem.gather_inputs/gather_outputs, core/subsystems.py:340-362)
+ * scatter: pencil vectors -> field arena (Subproblem.scatter_inputs, core/subsystems.py:364-371).
+ * Line q: arena offset line_base[q] + sys_off[line_kind[q]*ld_sys + s] + m  <->  vec[line_pos[line_ptr[q]+m]*ld + s]. */
+int db_pencil_gather(const double* arena, double* vec, int32_t S, int32_t ld, int32_t nlines, int32_t max_len,
+                     const int64_t* line_base, const int32_t* line_kind, const int32_t* line_ptr, const int32_t* line_pos,
+                     const int64_t* sys_off, int32_t ld_sys, void* stream);
+int db_pencil_scatter(const double* vec, double* arena, int32_t S, int32_t ld, int32_t nlines, int32_t max_len,
+                      const int64_t* line_base, const int32_t* line_kind, const int32_t* line_ptr, const int32_t* line_pos,
+                      const int64_t* sys_off, int32_t ld_sys, void* stream);
+
+/* y = A(k) x with A(k) = sum_mono mono_vals[mono][s] * T_mono, CSR-by-row term lists
+ * (apply_sparse(sp.M_min / sp.L_min, X): core/timesteppers.py:144-147, 590-591, 604; tools/linalg.pyx:284-303).
+ * Either output may be NULL. */
+int db_pencil_matvec(int32_t n, int32_t S, int32_t ld, const double* mono_vals, const double* x,
+                     const int32_t* m_ptr, const int32_t* m_col, const int32_t* m_mono, const double* m_val, double* y_m,
+                     const int32_t* l_ptr, const int32_t* l_col, const int32_t* l_mono, const double* l_val, double* y_l,
+                     void* stream);
+
+/* LHS assembly from templates, LU = a0*M + b0*L on the static fill pattern
+ * (sp.LHS = a0*sp.M_min + b0*sp.L_min: core/timesteppers.py:173-180, 632-639). */
+int db_pencil_assemble(double* lu, int32_t n_entries, int32_t S, int32_t ld, const double* mono_vals,
+                       const int32_t* asm_ptr, const int32_t* asm_mono, const double* asm_val, void* stream);
+
+/* in-place LU without pivoting on the static ordering (matsolver construction: libraries/matsolvers.py:126-157).
+ * info[0] receives the number of systems that hit a zero / non-finite pivot. */
+int db_pencil_factor(double* lu, int32_t n, int32_t S, int32_t ld, const int32_t* diag_eid,
+                     const int32_t* fl_ptr, const int32_t* fl_eid, const int32_t* fu_ptr, const int32_t* fu_eid,
+                     const int32_t* fd_eid, int32_t* info, void* stream);
+
+/* x = LU^{-1} ( sum_j coef[j] * vecs[j] ): the right-hand-side combination of the IMEX schemes is fused into
+ * the load (RHS build core/timesteppers.py:156-166, 617-623; solve 182-184, 641-642; matsolvers.py:141-157). */
+typedef struct {
+    int32_t nvec;
+    const double* vec[16];
+    double coef[16];
+} db_lincomb;
+int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
+                    const int32_t* fwd_ptr, const int32_t* fwd_col, const int32_t* bwd_ptr, const int32_t* bwd_col,
+                    const db_lincomb* rhs, double* x, void* stream);
+
+/* out = sum_j coef[j]*vecs[j] over `count` doubles (explicit RHS build, used by tests and diagnostics). */
+int db_lincomb_apply(const db_lincomb* terms, double* out, int64_t count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Distributed transpose pack / unpack (X1): local permutes either side of the NCCL all-to-all.
+ * Replaces the np.copyto pack/unpack around fftw_mpi_plan_many_transpose (core/transposes.pyx:106-113, 211-246).
+ * A: (B, N1loc, N2, N3) -> send buffer (P, B, N1loc, N2blk, N3); recv (P, B, N1blk, N2loc, N3) -> (B, N1, N2loc, N3). */
+int db_transpose_pack(const double* a, double* sendbuf, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int32_t P, void* stream);
+int db_transpose_unpack(const double* recvbuf, double* out, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int32_t P, void* stream);
+int db_transpose_pack_rev(const double* a, double* sendbuf, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int32_t P, void* stream);
+int db_transpose_unpack_rev(const double* recvbuf, double* out, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int32_t P, void* stream);
+
+/* max |x| reduction (CFL / flow properties; extras/flow_tools.py:33-37 before the Allreduce) */
+int db_absmax(const double* x, int64_t count, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

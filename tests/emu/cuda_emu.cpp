@@ -1,0 +1,75 @@
+// TEST INFRASTRUCTURE ONLY: fiber scheduler for tests/emu/cuda_emu.h
+#include "cuda_emu.h"
+#include <stdexcept>
+
+thread_local EmuState emu_cur;
+
+namespace {
+struct Fiber {
+    ucontext_t ctx;
+    std::vector<unsigned char> stack;
+    EmuState st;
+    bool done = false;
+};
+thread_local ucontext_t sched_ctx;
+thread_local Fiber* running = nullptr;
+thread_local const std::function<void()>* cur_body = nullptr;
+
+void fiber_entry() {
+    (*cur_body)();
+    running->done = true;
+    swapcontext(&running->ctx, &sched_ctx);
+}
+}  // namespace
+
+void emu_syncthreads() {
+    Fiber* f = running;
+    f->st = emu_cur;
+    swapcontext(&f->ctx, &sched_ctx);
+    emu_cur = f->st;
+}
+
+void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+    const size_t nthreads = (size_t)block.x * block.y * block.z;
+    std::vector<unsigned char> shared(smem + 64);
+    std::vector<Fiber> fibers(nthreads);
+    const size_t STACK = 256 * 1024;
+    for (auto& f : fibers) f.stack.resize(STACK);
+    cur_body = &body;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::memset(shared.data(), 0xA5, shared.size());   // poison shared memory
+        size_t i = 0;
+        for (unsigned tz = 0; tz < block.z; ++tz)
+        for (unsigned ty = 0; ty < block.y; ++ty)
+        for (unsigned tx = 0; tx < block.x; ++tx, ++i) {
+            Fiber& f = fibers[i];
+            f.done = false;
+            f.st.tid = {tx, ty, tz}; f.st.bid = {bx, by, bz}; f.st.bdim = block; f.st.gdim = grid;
+            f.st.smem = shared.data();
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack.data();
+            f.ctx.uc_stack.ss_size = f.stack.size();
+            f.ctx.uc_link = &sched_ctx;
+            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+        }
+        size_t remaining = nthreads;
+        while (remaining) {
+            size_t finished_this_round = 0, waiting = 0;
+            for (auto& f : fibers) {
+                if (f.done) continue;
+                running = &f;
+                emu_cur = f.st;
+                swapcontext(&sched_ctx, &f.ctx);
+                if (f.done) { ++finished_this_round; } else { ++waiting; }
+            }
+            remaining -= finished_this_round;
+            if (finished_this_round && waiting) {
+                // some threads exited while others wait at a barrier: allowed in CUDA only if exited threads
+                // never reach the barrier; continue scheduling the waiting ones.
+            }
+        }
+    }
+    running = nullptr;
+}

@@ -1,0 +1,43 @@
+"""TEST INFRASTRUCTURE: load the CPU emulation build of the CUDA kernels (tests/emu/libdedalus_b200_emu.so)
+and expose numpy-array wrappers with the same argument order as the C ABI.  Never imported by the product."""
+import ctypes as C
+import numpy as np
+import pathlib, sys
+ROOT = pathlib.Path(__file__).resolve().parents[2]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+from dedalus_b200 import lib as dlib
+from dedalus_b200 import build as dbuild
+from dedalus_b200.fftplan import HostPlan
+
+_emu = None
+
+
+def emu():
+    global _emu
+    if _emu is None:
+        _emu = dlib.bind(dbuild.build_emu())
+    return _emu
+
+
+def ptr(a):
+    if a is None:
+        return None
+    assert a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class EmuPlan:
+    def __init__(self, n, kind):
+        hp = HostPlan(n, kind)
+        self.hp = hp
+        self._keep = [np.ascontiguousarray(x) for x in (hp.tw, hp.twr, hp.twq, hp.perm, hp.iperm)]
+        s = dlib.FftPlan()
+        s.n, s.nc, s.half, s.nrad = hp.n, hp.nc, hp.half, len(hp.radices)
+        for i, r in enumerate(hp.radices):
+            s.rad[i] = r
+        s.tw, s.twr, s.twq, s.perm, s.iperm = [ptr(x) for x in self._keep]
+        self.struct = s
+
+    def ref(self):
+        return C.byref(self.struct)

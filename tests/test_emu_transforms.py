@@ -1,0 +1,105 @@
+"""Kernel logic of csrc/fft.cu executed under the test-only CPU emulation (tests/emu) against the reference
+outputs in tests/golden/transforms.npz (ScipyRealFFT / RealFourierMMT / ScipyComplexFFT / ScipyFastChebyshev /
+JacobiMMT dumped by make_golden.py).  The same comparisons run on the real GPU in test_gpu_transforms.py."""
+import numpy as np, pytest, ctypes as C
+from dedalus_b200 import jacobi
+from emu import emu_lib as E
+
+
+def _axis_view(shape, axis):
+    outer = int(np.prod(shape[:axis], dtype=int)); inner = int(np.prod(shape[axis + 1:], dtype=int))
+    return outer, inner
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (16, 21), (32, 48), (12, 18), (10, 15)])
+def test_rfft(golden, M, N):
+    g = golden("transforms.npz"); lib = E.emu(); plan = E.EmuPlan(N, 'real')
+    for ref in ("matrix", "scipy"):
+        cin, gout = g[f"rf_{ref}_{M}_{N}_cin"], g[f"rf_{ref}_{M}_{N}_gout"]
+        outer, inner = _axis_view(cin.shape, 1)
+        out = np.zeros_like(gout)
+        lib.call("db_rfft_backward", plan.ref(), E.ptr(np.ascontiguousarray(cin)), E.ptr(out), outer, M, inner, 0, 0.0, None)
+        assert np.allclose(out, gout, rtol=1e-13, atol=1e-13)
+        gin, cout = g[f"rf_{ref}_{M}_{N}_gin"], g[f"rf_{ref}_{M}_{N}_cout"]
+        out = np.zeros_like(cout)
+        lib.call("db_rfft_forward", plan.ref(), E.ptr(np.ascontiguousarray(gin)), E.ptr(out), outer, M, inner, None)
+        assert np.allclose(out, cout, rtol=1e-13, atol=1e-13)
+
+
+def test_rfft_last_axis_and_derivative():
+    lib = E.emu(); N, M = 24, 16; plan = E.EmuPlan(N, 'real')
+    rng = np.random.default_rng(5)
+    c = rng.standard_normal((5, 3, M)); c[..., 1] = 0
+    out = np.zeros((5, 3, N))
+    kscale = 2 * np.pi / 4.0
+    lib.call("db_rfft_backward", plan.ref(), E.ptr(c), E.ptr(out), 15, M, 1, 1, kscale, None)
+    x = np.arange(N) / N * 4.0
+    k = np.arange(M // 2) * kscale
+    ref = np.zeros_like(out)
+    for kk in range(1, (M - 1) // 2 + 1):
+        a, b = c[..., 2 * kk], c[..., 2 * kk + 1]
+        ref += (-a * k[kk])[..., None] * np.sin(k[kk] * x) + (-b * k[kk])[..., None] * np.cos(k[kk] * x)
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (15, 22), (12, 18)])
+def test_cfft(golden, M, N):
+    g = golden("transforms.npz"); lib = E.emu(); plan = E.EmuPlan(N, 'complex')
+    for ref in ("matrix", "scipy"):
+        cin, gout = g[f"cf_{ref}_{M}_{N}_cin"], g[f"cf_{ref}_{M}_{N}_gout"]
+        outer, inner = _axis_view(cin.shape, 1)
+        out = np.zeros_like(gout)
+        lib.call("db_cfft_backward", plan.ref(), E.ptr(np.ascontiguousarray(cin)), E.ptr(out), outer, M, inner, 0, 0.0, None)
+        assert np.allclose(out, gout, rtol=1e-13, atol=1e-13)
+        gin, cout = g[f"cf_{ref}_{M}_{N}_gin"], g[f"cf_{ref}_{M}_{N}_cout"]
+        out = np.zeros_like(cout)
+        lib.call("db_cfft_forward", plan.ref(), E.ptr(np.ascontiguousarray(gin)), E.ptr(out), outer, M, inner, None)
+        assert np.allclose(out, cout, rtol=1e-13, atol=1e-13)
+
+
+def _conv_diags(M, N, a, b):
+    """Upper diagonals of the (-1/2,-1/2)->(a,b) conversion restricted to the first M rows (row length M)."""
+    K = max(M, N)
+    Cm = jacobi.conversion_matrix(K, -0.5, -0.5, a, b).toarray()
+    nd = int(round((a + 0.5) + (b + 0.5))) + 1
+    d = np.zeros((nd, M))
+    for k in range(nd):
+        for i in range(M):
+            if i + k < K:
+                d[k, i] = Cm[i, i + k]
+    return np.ascontiguousarray(d)
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (15, 22), (15, 15), (32, 48)])
+@pytest.mark.parametrize("alpha", [0, 1, 2])
+def test_chebyshev(golden, M, N, alpha):
+    g = golden("transforms.npz"); lib = E.emu(); plan = E.EmuPlan(N, 'real')
+    a = b = alpha - 0.5
+    diags = _conv_diags(M, N, a, b) if alpha else None
+    nd = diags.shape[0] if alpha else 0
+    for ref in ("matrix", "scipy_dct"):
+        key = f"ch_{ref}_{M}_{N}_{alpha}"
+        cin, gout, gin, cout = g[key + "_cin"], g[key + "_gout"], g[key + "_gin"], g[key + "_cout"]
+        outer, inner = _axis_view(cin.shape, 2)
+        out = np.zeros_like(gout)
+        lib.call("db_cheb_backward", plan.ref(), E.ptr(np.ascontiguousarray(cin)), E.ptr(out), outer, M, inner,
+                 None, 0, E.ptr(diags), nd, None)
+        assert np.allclose(out, gout, rtol=1e-12, atol=1e-12), (ref, "backward")
+        out = np.zeros_like(cout)
+        lib.call("db_cheb_forward", plan.ref(), E.ptr(np.ascontiguousarray(gin)), E.ptr(out), outer, M, inner,
+                 E.ptr(diags), nd, None)
+        assert np.allclose(out, cout, rtol=1e-12, atol=1e-12), (ref, "forward")
+
+
+def test_chebyshev_strided_axis_matches_last_axis():
+    lib = E.emu(); N, M = 24, 16; plan = E.EmuPlan(N, 'real')
+    rng = np.random.default_rng(3)
+    c = rng.standard_normal((3, M, 37))
+    out = np.zeros((3, N, 37))
+    lib.call("db_cheb_backward", plan.ref(), E.ptr(c), E.ptr(out), 3, M, 37, None, 0, None, 0, None)
+    c2 = np.ascontiguousarray(np.moveaxis(c, 1, 2)); out2 = np.zeros((3, 37, N))
+    lib.call("db_cheb_backward", plan.ref(), E.ptr(c2), E.ptr(out2), 3 * 37, M, 1, None, 0, None, 0, None)
+    assert np.allclose(np.moveaxis(out, 1, 2), out2, rtol=0, atol=1e-14)
+    back = np.zeros_like(c)
+    lib.call("db_cheb_forward", plan.ref(), E.ptr(out), E.ptr(back), 3, M, 37, None, 0, None)
+    assert np.allclose(back, c, rtol=1e-12, atol=1e-12)
