@@ -1,0 +1,363 @@
+"""Right-hand-side evaluation plan (D3 + P1 + the transform chain of T1/T2).
+
+Reference: Evaluator.evaluate_handlers (core/evaluator.py:95-146) walks every field of every F expression up
+and down the layout chain, one transform call per field per axis and one numpy call per operator node
+(probe: 18 backward + 4 forward scalar 3-D transforms per RB3D stage).
+Here each equation's RHS is lowered ONCE at build time to
+        F_out = sum_terms coef * prod_factors  d^alpha(field component)
+and evaluated as three fused phases on the device:
+  1. backward transforms of the unique grid inputs, sharing partial transforms along a prefix tree
+     (z-stage results are reused by every x/y derivative of the same field; derivatives are applied inside the
+     transform kernels' load stage, not as separate coefficient-space passes),
+  2. one pointwise kernel for all products of all equations (csrc/pointwise.cu),
+  3. forward transforms of the outputs; the last (coupled-axis) pass applies the conversion to the equation's
+     basis and writes straight into the equation arena that the pencil gather reads.
+"""
+import numbers
+import numpy as np
+from . import operators as ops
+from .operators import Operand
+from .field import Field
+from .basis import RealFourier, ComplexFourier, Jacobi
+
+
+class NonPolynomialError(NotImplementedError):
+    pass
+
+
+def lower(expr):
+    """Lower an expression to {flat component index: [(coef, ((field, comp, derivs), ...)), ...]}."""
+    dim = expr.dist.dim if isinstance(expr, Operand) else 0
+
+    def rec(e):
+        if isinstance(e, numbers.Number):
+            return {0: [(e, ())]} if e != 0 else {0: []}
+        if isinstance(e, Field):
+            out = {}
+            if all(b is None for b in e.bases):
+                vals = np.asarray(e['c']).reshape(-1)
+                for c in range(e.ncomp):
+                    out[c] = [(vals[c], ())] if vals[c] != 0 else []
+                return out
+            for c in range(e.ncomp):
+                out[c] = [(1.0, ((e, c, (0,) * dim),))]
+            return out
+        if isinstance(e, ops.Add):
+            out = {}
+            for a in e.args:
+                for c, terms in rec(a).items():
+                    out.setdefault(c, []).extend(terms)
+            return out
+        if isinstance(e, ops.ScalarMul):
+            return {c: [(coef * e.c, f) for coef, f in terms] for c, terms in rec(e.args[0]).items()}
+        if isinstance(e, (ops.Convert, ops.TransposeComponents, ops.Trace)) and False:
+            pass
+        if isinstance(e, ops.Convert):
+            return rec(e.args[0])
+        if isinstance(e, ops.Multiply):
+            A, B = e.args
+            ra, rb = rec(A), rec(B)
+            nb = B.ncomp
+            out = {}
+            for ca, ta in ra.items():
+                for cb, tb in rb.items():
+                    out[ca * nb + cb] = [(x * y, fx + fy) for x, fx in ta for y, fy in tb]
+            return out
+        if isinstance(e, ops.DotProduct):
+            A, B = e.args
+            ra, rb = rec(A), rec(B)
+            d = A.tensorsig[-1].dim
+            na, nb = A.ncomp // d, B.ncomp // d
+            out = {}
+            for ia in range(na):
+                for ib in range(nb):
+                    terms = []
+                    for i in range(d):
+                        for x, fx in ra.get(ia * d + i, []):
+                            for y, fy in rb.get(i * nb + ib, []):
+                                terms.append((x * y, fx + fy))
+                    out[ia * nb + ib] = terms
+            return out
+        if isinstance(e, ops.Power):
+            base = rec(e.args[0])[0]
+            cur = base
+            for _ in range(e.n - 1):
+                cur = [(x * y, fx + fy) for x, fx in cur for y, fy in base]
+            return {0: cur}
+
+        def diff_terms(terms, axis):
+            new = []
+            for coef, facs in terms:
+                if len(facs) != 1:
+                    raise NonPolynomialError(
+                        "Differentiating a product on the RHS is not supported: expand it or introduce an auxiliary field.")
+                f, c, dv = facs[0]
+                if f.bases[axis] is None:
+                    continue
+                dv = list(dv); dv[axis] += 1
+                new.append((coef, ((f, c, tuple(dv)),)))
+            return new
+
+        if isinstance(e, ops.Differentiate):
+            return {c: diff_terms(t, e.axis) for c, t in rec(e.args[0]).items()}
+        if isinstance(e, ops.Gradient):
+            sub = rec(e.args[0]); nin = e.args[0].ncomp
+            out = {}
+            for i, coord in enumerate(e.cs.coords):
+                ax = e.dist.get_axis(coord)
+                for c, t in sub.items():
+                    out[i * nin + c] = diff_terms(t, ax)
+            return out
+        if isinstance(e, ops.Divergence):
+            sub = rec(e.args[0]); nrest = e.ncomp
+            out = {r: [] for r in range(nrest)}
+            for i, coord in enumerate(e.cs.coords):
+                ax = e.dist.get_axis(coord)
+                for r in range(nrest):
+                    out[r].extend(diff_terms(sub.get(i * nrest + r, []), ax))
+            return out
+        if isinstance(e, ops.Laplacian):
+            sub = rec(e.args[0])
+            out = {c: [] for c in sub}
+            for coord in e.cs.coords:
+                ax = e.dist.get_axis(coord)
+                for c, t in sub.items():
+                    out[c].extend(diff_terms(diff_terms(t, ax), ax))
+            return out
+        if isinstance(e, ops.Trace):
+            sub = rec(e.args[0]); d = e.args[0].tensorsig[0].dim; nrest = e.ncomp
+            return {r: [t for i in range(d) for t in sub.get((i * d + i) * nrest + r, [])] for r in range(nrest)}
+        if isinstance(e, ops.TransposeComponents):
+            sub = rec(e.args[0]); d0, d1 = e.args[0].tensorsig[0].dim, e.args[0].tensorsig[1].dim
+            nrest = e.ncomp // (d0 * d1)
+            return {(j * d0 + i) * nrest + r: sub.get((i * d1 + j) * nrest + r, []) for i in range(d0) for j in range(d1) for r in range(nrest)}
+        raise NonPolynomialError(f"{type(e).__name__} is not supported on the right-hand side of the B200 hot path.")
+
+    return rec(expr)
+
+
+class RHSPlan:
+    """Compiled evaluation of all equation right-hand sides into the equation arena."""
+
+    def __init__(self, solver):
+        import torch
+        self.solver = solver
+        problem = solver.problem
+        dist = problem.dist
+        self.dist = dist
+        dim = dist.dim
+        self.device = solver.device
+        arena = solver.eq_arena
+        self.static_entries = []      # (arena offset, value) for constant RHS
+        inputs = {}                   # (id(field), comp, derivs) -> index
+        self.input_keys = []
+        outputs = []                  # (eq index, comp, terms)
+        for ie, eq in enumerate(problem.equations):
+            rhs = eq['RHS']
+            if isinstance(rhs, numbers.Number):
+                if rhs != 0:
+                    self._add_constant(ie, eq, float(rhs))
+                continue
+            low = lower(rhs)
+            for comp, terms in low.items():
+                const = sum(c for c, f in terms if len(f) == 0)
+                terms = [(c, f) for c, f in terms if len(f) > 0]
+                if const != 0:
+                    self._add_constant(ie, eq, float(const), comp)
+                if not terms:
+                    continue
+                tl = []
+                for coef, facs in terms:
+                    idxs = []
+                    for (f, c, dv) in facs:
+                        if any(b is None for b in f.bases):
+                            raise NotImplementedError("RHS factors must have bases along every axis (no broadcasting on the hot path yet).")
+                        key = (id(f), c, dv)
+                        if key not in inputs:
+                            inputs[key] = len(self.input_keys)
+                            self.input_keys.append((f, c, dv))
+                        idxs.append(inputs[key])
+                    tl.append((coef, idxs))
+                if any(b is None for b in eq['bases']):
+                    raise NotImplementedError("Field-dependent RHS of a lower-dimensional equation is not supported yet.")
+                outputs.append((ie, comp, tl))
+        self.outputs = outputs
+        self.n_in, self.n_out = len(self.input_keys), len(outputs)
+        if self.n_out == 0:
+            return
+        # ---- bases / shapes (all inputs share the variable bases up to Jacobi parameters)
+        f0 = self.input_keys[0][0]
+        self.bases = f0.bases
+        self.dealias = tuple(b.dealias[0] for b in self.bases)
+        self.cshape = tuple(dist.coeff_local_slice(ax, b).stop - dist.coeff_local_slice(ax, b).start for ax, b in enumerate(self.bases))
+        self.gshape_full = tuple(b.grid_size(s) for b, s in zip(self.bases, self.dealias))
+        if dist.size > 1:
+            raise NotImplementedError("use DistributedRHSPlan")
+        self.gshape = self.gshape_full
+        self.npoints = int(np.prod(self.gshape))
+        # ---- pointwise program
+        term_ptr, coef, fac_ptr, fac = [0], [], [0], []
+        for ie, comp, tl in outputs:
+            for c, idxs in tl:
+                coef.append(c); fac.extend(idxs); fac_ptr.append(len(fac))
+            term_ptr.append(len(coef))
+        dev = self.device
+        self.term_ptr = torch.tensor(term_ptr, dtype=torch.int32, device=dev)
+        self.coef = torch.tensor(coef, dtype=torch.float64, device=dev)
+        self.fac_ptr = torch.tensor(fac_ptr, dtype=torch.int32, device=dev)
+        self.fac = torch.tensor(fac, dtype=torch.int32, device=dev)
+        self.nfac = len(fac)
+        # ---- backward prefix tree: level order = axes from last to first
+        self.axes_order = list(range(dim - 1, -1, -1))
+        self._build_tree()
+        # ---- buffers
+        self.grid_in = torch.empty((self.n_in,) + self.gshape, dtype=torch.float64, device=dev)
+        self.grid_out = torch.empty((self.n_out,) + self.gshape, dtype=torch.float64, device=dev)
+        # ---- output destinations in the equation arena and forward plans
+        self.out_dest = []
+        for ie, comp, tl in outputs:
+            eq = problem.equations[ie]
+            tsh, shp = arena.shapes[ie]
+            off = arena.offsets[ie] + comp * int(np.prod(shp))
+            self.out_dest.append((off, shp, eq['bases']))
+
+    # ------------------------------------------------------------------------------------------------
+    def _add_constant(self, ie, eq, value, comp=0):
+        """Constant RHS: coefficient of the constant mode of the equation's domain (group (0,..,0), cos slot)."""
+        arena = self.solver.eq_arena
+        tsh, shp = arena.shapes[ie]
+        factor = 1.0
+        for ax, b in enumerate(eq['bases']):
+            if b is None:
+                continue
+            sl = self.dist.coeff_local_slice(ax, b)
+            if sl.start != 0:
+                return            # mode 0 lives on another rank
+            if isinstance(b, Jacobi):
+                factor /= b.constant_mode_value
+        off = arena.offsets[ie] + comp * int(np.prod(shp))
+        self.static_entries.append((off, value * factor))
+
+    def _build_tree(self):
+        """nodes[level] = list of dicts(parent, field, comp, deriv) ; leaves map to grid-input slots."""
+        from .transforms import cached_plan
+        dim = self.dist.dim
+        levels = [dict() for _ in range(dim)]
+        self.leaf_of_input = []
+        for (f, c, dv) in self.input_keys:
+            parent = None
+            for lvl, ax in enumerate(self.axes_order):
+                key = (id(f), c) + tuple(dv[a] for a in self.axes_order[:lvl + 1])
+                if key not in levels[lvl]:
+                    levels[lvl][key] = dict(parent=parent, field=f, comp=c, axis=ax, deriv=dv[ax], index=len(levels[lvl]))
+                parent = key
+            self.leaf_of_input.append(parent)
+        self.levels = levels
+        # shapes after each level
+        shp = list(self.cshape)
+        self.level_shapes = []
+        for lvl, ax in enumerate(self.axes_order):
+            shp[ax] = self.gshape[ax]
+            self.level_shapes.append(tuple(shp))
+
+    def set_static(self, arena_tensor):
+        for off, val in self.static_entries:
+            arena_tensor[off] = val
+
+    # ------------------------------------------------------------------------------------------------
+    def evaluate(self, eq_arena_tensor):
+        """Evaluate all RHS outputs into eq_arena_tensor (state fields must be in coefficient space on device)."""
+        import torch, ctypes as C
+        from .transforms import cached_plan, _dptr, _stream
+        from .lib import get_lib
+        if self.n_out == 0:
+            return
+        dim = self.dist.dim
+        dev = self.device
+        last = dim - 1
+        # ---- phase 1: backward transforms along the prefix tree
+        bufs = [None] * dim
+        for lvl, ax in enumerate(self.axes_order):
+            nodes = self.levels[lvl]
+            final = (lvl == dim - 1)
+            if not final:
+                bufs[lvl] = self._scratch(('bwd', lvl), (len(nodes),) + self.level_shapes[lvl])
+            for key, nd in nodes.items():
+                f = nd['field']
+                basis = f.bases[ax]
+                plan = cached_plan(basis, self.dealias[ax])
+                if lvl == 0:
+                    src = f.device_data()[self._comp_index(f, nd['comp'])]
+                else:
+                    src = bufs[lvl - 1][self.levels[lvl - 1][nd['parent']]['index']]
+                if final:
+                    dst = self.grid_in[self._input_slot(key)]
+                else:
+                    dst = bufs[lvl][nd['index']]
+                plan.backward(src, dst, ax, deriv=nd['deriv'])
+        # ---- phase 2: pointwise products
+        get_lib().call("db_pointwise", _dptr(self.grid_in), _dptr(self.grid_out), self.npoints, self.n_in, self.n_out,
+                       _dptr(self.term_ptr), _dptr(self.coef), _dptr(self.fac_ptr), _dptr(self.fac), self.nfac, _stream())
+        # ---- phase 3: forward transforms (axes first -> last), all outputs stacked
+        cur = self.grid_out
+        for ax in range(dim):
+            basis = self.bases[ax]
+            if ax < last:
+                plan = cached_plan(basis, self.dealias[ax])
+                shp = list(cur.shape); shp[1 + ax] = plan.M
+                out = self._scratch(('fwd', ax), tuple(shp))
+                plan.forward(cur, out, 1 + ax)
+                cur = out
+            else:
+                for o, (off, shp, eq_bases) in enumerate(self.out_dest):
+                    eqb = eq_bases[ax]
+                    if isinstance(basis, Jacobi):
+                        prod_basis = basis.clone_with(a=basis.a0, b=basis.b0)
+                        tb = eqb if eqb is not None else prod_basis
+                        plan = self._fwd_plan_last(prod_basis, tb)
+                    else:
+                        plan = cached_plan(basis, self.dealias[ax])
+                    n = int(np.prod(shp))
+                    dst = eq_arena_tensor[off:off + n].view(shp)
+                    plan.forward(cur[o], dst, ax)
+
+    def _fwd_plan_last(self, prod_basis, target_basis):
+        from .transforms import FastChebyshevTransform, cached_plan
+        key = ('fwdlast', target_basis)
+        if not hasattr(self, '_plans'):
+            self._plans = {}
+        if key not in self._plans:
+            N = prod_basis.grid_size(self.dealias[-1])
+            if prod_basis.a0 == prod_basis.b0 == -0.5:
+                self._plans[key] = FastChebyshevTransform(N, prod_basis.size, target_basis.a, target_basis.b, -0.5, -0.5,
+                                                          stretch=prod_basis.COV.stretch)
+            else:
+                from .transforms import JacobiMatrixTransform
+                self._plans[key] = JacobiMatrixTransform(N, prod_basis.size, target_basis.a, target_basis.b, prod_basis.a0, prod_basis.b0)
+        return self._plans[key]
+
+    def _scratch(self, key, shape):
+        import torch
+        if not hasattr(self, '_scr'):
+            self._scr = {}
+        t = self._scr.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=torch.float64, device=self.device)
+            self._scr[key] = t
+        return t
+
+    def _comp_index(self, f, comp):
+        if not f.tensorsig:
+            return ()
+        return tuple(int(i) for i in np.unravel_index(comp, f.tshape))
+
+    def _input_slot(self, leaf_key):
+        if not hasattr(self, '_slot'):
+            self._slot = {}
+            for i, lk in enumerate(self.leaf_of_input):
+                self._slot[lk] = i
+        return self._slot[leaf_key]
+
+
+def evaluate_expression(expr):
+    raise NotImplementedError("Stand-alone expression evaluation is not implemented yet; use solver RHS plans.")

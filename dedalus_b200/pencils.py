@@ -160,6 +160,13 @@ class PencilSystemBuilder:
         cls.shape = (nrows, ncols)
         cls.valid_rows = np.concatenate([np.full(s.size, s.valid) for s in cls.row_slots]) if cls.row_slots else np.zeros(0, bool)
         cls.valid_cols = np.concatenate([np.full(s.size, s.valid) for s in cls.col_slots]) if cls.col_slots else np.zeros(0, bool)
+        # invalid modes along a coupled Fourier axis (-sin(0x) slot, Nyquist): reference basis.py:1123-1134
+        for slots, offs, items, valid in ((cls.row_slots, cls.row_off, eq_items, cls.valid_rows),
+                                          (cls.col_slots, cls.col_off, var_items, cls.valid_cols)):
+            for s, o in zip(slots, offs):
+                lb = items[s.owner][1][self.last_axis]
+                if s.has_last and isinstance(lb, (RealFourier, ComplexFourier)):
+                    valid[o:o + s.size] &= lb.valid_coeff_mask()
         # natural block offsets per owner
         def owner_ranges(slots, offs, total):
             r = {}

@@ -1,0 +1,306 @@
+"""Device transform plans behind the reference's transform-plugin contract.
+
+Reference contract (core/transforms.py:27-75, basis.py:416-428, 924-936): a plan is built as
+`cls(grid_size, coeff_size)` (Fourier) or `cls(grid_size, coeff_size, a, b, a0, b0)` (Jacobi) and exposes
+`forward(gdata, cdata, axis)` / `backward(cdata, gdata, axis)` on N-D C-contiguous arrays.  Here the arrays are
+torch CUDA tensors (float64, or complex128 for ComplexFourier) and the work is one CUDA kernel launch
+(csrc/fft.cu) per call; results are written into the output tensor, which must not alias the input.
+"""
+import ctypes as C
+import numpy as np
+from . import jacobi
+from .lib import get_lib, FftPlan, DedalusB200Error
+from .fftplan import HostPlan
+from .basis import RealFourier, ComplexFourier, Jacobi
+
+_transform_registry = {}
+
+
+def register_transform(basis_cls, name):
+    def wrapper(cls):
+        _transform_registry.setdefault(basis_cls, {})[name] = cls
+        return cls
+    return wrapper
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _dptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _split(shape, axis):
+    outer = int(np.prod(shape[:axis], dtype=np.int64))
+    inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    return outer, inner
+
+
+class DevicePlan:
+    """FFT tables uploaded once; struct kept alive with its tensors."""
+    _cache = {}
+
+    def __new__(cls, n, kind, device):
+        key = (n, kind, str(device))
+        if key not in cls._cache:
+            self = object.__new__(cls)
+            torch = _torch()
+            hp = HostPlan(n, kind)
+            self.hp = hp
+            self.tensors = [torch.from_numpy(np.ascontiguousarray(x)).to(device) for x in (hp.tw, hp.twr, hp.twq, hp.perm, hp.iperm)]
+            s = FftPlan()
+            s.n, s.nc, s.half, s.nrad = hp.n, hp.nc, hp.half, len(hp.radices)
+            for i, r in enumerate(hp.radices):
+                s.rad[i] = r
+            s.tw, s.twr, s.twq, s.perm, s.iperm = [t.data_ptr() for t in self.tensors]
+            self.struct = s
+            cls._cache[key] = self
+        return cls._cache[key]
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def _check(x, name):
+    if not x.is_cuda or not x.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous CUDA tensor.")
+
+
+@register_transform(RealFourier, 'b200')
+class RealFourierTransform:
+    """cos/-sin real Fourier transform (reference FFTWRealFFT, transforms.py:537-565)."""
+
+    def __init__(self, grid_size, coeff_size, kscale=1.0):
+        self.N, self.M = int(grid_size), int(coeff_size)
+        self.kscale = kscale
+
+    def forward(self, gdata, cdata, axis):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        if gdata.shape[axis] != self.N or cdata.shape[axis] != self.M:
+            raise ValueError("Array shapes do not match the transform plan.")
+        plan = DevicePlan(self.N, 'real', gdata.device)
+        outer, inner = _split(gdata.shape, axis)
+        get_lib().call("db_rfft_forward", plan.ref(), _dptr(gdata), _dptr(cdata), outer, self.M, inner, _stream())
+
+    def backward(self, cdata, gdata, axis, deriv=0):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        if gdata.shape[axis] != self.N or cdata.shape[axis] != self.M:
+            raise ValueError("Array shapes do not match the transform plan.")
+        plan = DevicePlan(self.N, 'real', gdata.device)
+        outer, inner = _split(gdata.shape, axis)
+        get_lib().call("db_rfft_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner, int(deriv), float(self.kscale), _stream())
+
+
+@register_transform(ComplexFourier, 'b200')
+class ComplexFourierTransform:
+    """Complex Fourier transform (reference FFTWComplexFFT, transforms.py:302-330)."""
+
+    def __init__(self, grid_size, coeff_size, kscale=1.0):
+        self.N, self.M = int(grid_size), int(coeff_size)
+        self.kscale = kscale
+
+    def forward(self, gdata, cdata, axis):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        plan = DevicePlan(self.N, 'complex', gdata.device)
+        outer, inner = _split(gdata.shape, axis)
+        get_lib().call("db_cfft_forward", plan.ref(), _dptr(gdata), _dptr(cdata), outer, self.M, inner, _stream())
+
+    def backward(self, cdata, gdata, axis, deriv=0):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        plan = DevicePlan(self.N, 'complex', gdata.device)
+        outer, inner = _split(gdata.shape, axis)
+        get_lib().call("db_cfft_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner, int(deriv), float(self.kscale), _stream())
+
+
+def banded_upper_diags(mat, M, ndiag):
+    """Diagonals 0..ndiag-1 of a sparse upper-triangular matrix, rows < M, as (ndiag, M) float64."""
+    A = mat.tocsr()
+    out = np.zeros((ndiag, M))
+    nrow, ncol = A.shape
+    for d in range(ndiag):
+        diag = A.diagonal(d)
+        L = min(len(diag), M)
+        out[d, :L] = diag[:L]
+    return np.ascontiguousarray(out)
+
+
+@register_transform(Jacobi, 'b200_dct')
+class FastChebyshevTransform:
+    """Chebyshev-grid ultraspherical transform (reference FFTWFastChebyshevTransform, transforms.py:801-902).
+
+    `backward(..., deriv=d)` additionally applies (d/dz)^d in coefficient space before the transform, i.e. it
+    is the backward transform of the derivative basis (a+d, b+d) composed with DifferentiateJacobi
+    (basis.py:701-718); `stretch` is the affine map factor of the problem interval."""
+
+    def __init__(self, grid_size, coeff_size, a, b, a0, b0, stretch=1.0):
+        if not (a0 == b0 == -0.5):
+            raise ValueError("Fast Chebyshev transform requires a0 == b0 == -1/2.")
+        self.N, self.M = int(grid_size), int(coeff_size)
+        self.a, self.b, self.a0, self.b0 = a, b, a0, b0
+        self.stretch = stretch
+        self._dev = {}
+
+    def _diags(self, key, device):
+        k = (key, str(device))
+        if k not in self._dev:
+            torch = _torch()
+            kind, d = key
+            M, N = self.M, self.N
+            if kind == 'fwd':
+                K = max(M, N)
+                Cm = jacobi.conversion_matrix(K, self.a0, self.b0, self.a, self.b)
+                nd = int(round((self.a - self.a0) + (self.b - self.b0))) + 1
+                arr = banded_upper_diags(Cm, M, nd)
+            elif kind == 'solve':
+                Cm = jacobi.conversion_matrix(M, self.a0, self.b0, self.a + d, self.b + d)
+                nd = int(round((self.a + d - self.a0) + (self.b + d - self.b0))) + 1
+                arr = banded_upper_diags(Cm, M, nd)
+            else:  # 'pre': derivative chain (a,b) -> (a+d,b+d)
+                P = None
+                for j in range(d):
+                    Dj = jacobi.differentiation_matrix(M, self.a + j, self.b + j) / self.stretch
+                    P = Dj if P is None else Dj @ P
+                arr = banded_upper_diags(P, M, d + 1)
+            self._dev[k] = (torch.from_numpy(arr).to(device), arr.shape[0])
+        return self._dev[k]
+
+    def forward(self, gdata, cdata, axis):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        if gdata.shape[axis] != self.N or cdata.shape[axis] != self.M:
+            raise ValueError("Array shapes do not match the transform plan.")
+        if gdata.is_complex():   # complex data = interleaved real lines (reference fftw_wrappers.pyx:244-246)
+            gdata, cdata = _torch().view_as_real(gdata), _torch().view_as_real(cdata)
+        plan = DevicePlan(self.N, 'real', gdata.device)
+        outer, inner = _split(gdata.shape, axis)
+        if (self.a, self.b) != (self.a0, self.b0):
+            dg, nd = self._diags(('fwd', 0), gdata.device)
+        else:
+            dg, nd = None, 0
+        get_lib().call("db_cheb_forward", plan.ref(), _dptr(gdata), _dptr(cdata), outer, self.M, inner, _dptr(dg), nd, _stream())
+
+    def backward(self, cdata, gdata, axis, deriv=0):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        if gdata.shape[axis] != self.N or cdata.shape[axis] != self.M:
+            raise ValueError("Array shapes do not match the transform plan.")
+        if gdata.is_complex():
+            gdata, cdata = _torch().view_as_real(gdata), _torch().view_as_real(cdata)
+        plan = DevicePlan(self.N, 'real', gdata.device)
+        outer, inner = _split(gdata.shape, axis)
+        pre, npre = (self._diags(('pre', deriv), gdata.device) if deriv > 0 else (None, 0))
+        if (self.a + deriv, self.b + deriv) != (self.a0, self.b0):
+            sol, nsol = self._diags(('solve', deriv), gdata.device)
+        else:
+            sol, nsol = None, 0
+        get_lib().call("db_cheb_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner,
+                       _dptr(pre), npre, _dptr(sol), nsol, _stream())
+
+
+@register_transform(Jacobi, 'b200_matrix')
+class JacobiMatrixTransform:
+    """Dense Jacobi transform on its own Gauss grid (reference JacobiMMT, transforms.py:114-158), fp64 GEMM kernel."""
+
+    def __init__(self, grid_size, coeff_size, a, b, a0, b0, stretch=1.0):
+        self.N, self.M = int(grid_size), int(coeff_size)
+        self.a, self.b, self.a0, self.b0 = a, b, a0, b0
+        N, M = self.N, self.M
+        grid, weights = jacobi.gauss_grid(N, a0, b0)
+        base = jacobi.polynomials(max(M, N), a0, b0, grid) * weights
+        base[N:, :] = 0
+        base = base[:M, :]          # DEALIAS_BEFORE_CONVERTING = True (reference dedalus.cfg:54)
+        if (a, b) != (a0, b0):
+            fwd = jacobi.conversion_matrix(base.shape[0], a0, b0, a, b) @ base
+        else:
+            fwd = base
+        self.forward_matrix = np.ascontiguousarray(fwd[:M])
+        poly = jacobi.polynomials(M, a, b, grid)
+        poly[N:, :] = 0
+        self.backward_matrix = np.ascontiguousarray(poly.T)
+        self._dev = {}
+
+    def _mat(self, which, device):
+        k = (which, str(device))
+        if k not in self._dev:
+            self._dev[k] = _torch().from_numpy(self.forward_matrix if which == 'f' else self.backward_matrix).to(device)
+        return self._dev[k]
+
+    def forward(self, gdata, cdata, axis):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        outer, inner = _split(gdata.shape, axis)
+        get_lib().call("db_mmt_apply", _dptr(self._mat('f', gdata.device)), self.M, self.N, _dptr(gdata), _dptr(cdata), outer, inner, _stream())
+
+    def backward(self, cdata, gdata, axis, deriv=0):
+        if deriv:
+            raise NotImplementedError("fused derivative is only available in the fast Chebyshev transform")
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        outer, inner = _split(gdata.shape, axis)
+        get_lib().call("db_mmt_apply", _dptr(self._mat('b', gdata.device)), self.N, self.M, _dptr(cdata), _dptr(gdata), outer, inner, _stream())
+
+
+def transform_plan(basis, scale):
+    """Plan for one basis at one scale (reference basis.transform_plan, basis.py:506-509, 915-922)."""
+    N = basis.grid_size(scale)
+    if isinstance(basis, RealFourier):
+        return RealFourierTransform(N, basis.size, kscale=1.0 / basis.COV.stretch)
+    if isinstance(basis, ComplexFourier):
+        return ComplexFourierTransform(N, basis.size, kscale=1.0 / basis.COV.stretch)
+    if isinstance(basis, Jacobi):
+        if basis.a0 == basis.b0 == -0.5:
+            return FastChebyshevTransform(N, basis.size, basis.a, basis.b, basis.a0, basis.b0, stretch=basis.COV.stretch)
+        return JacobiMatrixTransform(N, basis.size, basis.a, basis.b, basis.a0, basis.b0, stretch=basis.COV.stretch)
+    raise NotImplementedError(f"No transform for basis {basis}")
+
+
+_plan_cache = {}
+
+
+def cached_plan(basis, scale):
+    key = (basis, scale)
+    if key not in _plan_cache:
+        _plan_cache[key] = transform_plan(basis, scale)
+    return _plan_cache[key]
+
+
+def transform_field(field, layout):
+    """Move a Field between full coefficient ('c') and full grid ('g') layouts on the device.
+
+    Single-GPU chain: axes last -> first towards grid space (reference Distributor._build_layouts,
+    distributor.py:131-175, with an empty mesh); the multi-GPU chain with its transpose hop is handled by
+    dedalus_b200/transposes.py."""
+    torch = _torch()
+    if field.dist.size > 1:
+        from .transposes import transform_field_distributed
+        return transform_field_distributed(field, layout)
+    data = field.device_data()
+    nt = len(field.tensorsig)
+    dim = field.dist.dim
+    scales = field.scales
+    if layout == 'g':
+        cur = data
+        for ax in range(dim - 1, -1, -1):
+            b = field.bases[ax]
+            if b is None:
+                continue
+            plan = cached_plan(b, scales[ax])
+            shp = list(cur.shape); shp[nt + ax] = plan.N
+            out = torch.empty(shp, dtype=cur.dtype, device=cur.device)
+            plan.backward(cur.contiguous(), out, nt + ax)
+            cur = out
+        field.set_device_data(cur, 'g')
+    else:
+        cur = data
+        for ax in range(dim):
+            b = field.bases[ax]
+            if b is None:
+                continue
+            plan = cached_plan(b, scales[ax])
+            shp = list(cur.shape); shp[nt + ax] = plan.M
+            out = torch.empty(shp, dtype=cur.dtype, device=cur.device)
+            plan.forward(cur.contiguous(), out, nt + ax)
+            cur = out
+        field.set_device_data(cur, 'c')

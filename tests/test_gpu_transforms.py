@@ -1,0 +1,121 @@
+"""GPU parity of the transform plugins (dedalus_b200/transforms.py -> csrc/fft.cu through the C ABI) against the
+reference outputs in tests/golden/transforms.npz, mirroring the reference's own cross-implementation tests
+(dedalus/tests/test_transforms.py:18-57 real Fourier, 117-158 Chebyshev) plus round trips at benchmark sizes."""
+import numpy as np, pytest
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=1e-12, atol=1e-12)   # fp64: max|d| <= 1e-13*log2(N) scale, stated in SURVEY.md section 8c
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (16, 21), (32, 48), (12, 18), (10, 15)])
+def test_real_fourier_vs_reference(golden, M, N):
+    import torch
+    from dedalus_b200.transforms import RealFourierTransform
+    g = golden("transforms.npz"); plan = RealFourierTransform(N, M)
+    for ref in ("matrix", "scipy"):
+        cin, gout = g[f"rf_{ref}_{M}_{N}_cin"], g[f"rf_{ref}_{M}_{N}_gout"]
+        out = torch.zeros(gout.shape, dtype=torch.float64, device='cuda')
+        plan.backward(_t(cin), out, 1)
+        assert np.allclose(out.cpu().numpy(), gout, **TOL)
+        gin, cout = g[f"rf_{ref}_{M}_{N}_gin"], g[f"rf_{ref}_{M}_{N}_cout"]
+        out = torch.zeros(cout.shape, dtype=torch.float64, device='cuda')
+        plan.forward(_t(gin), out, 1)
+        assert np.allclose(out.cpu().numpy(), cout, **TOL)
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (15, 22), (12, 18)])
+def test_complex_fourier_vs_reference(golden, M, N):
+    import torch
+    from dedalus_b200.transforms import ComplexFourierTransform
+    g = golden("transforms.npz"); plan = ComplexFourierTransform(N, M)
+    for ref in ("matrix", "scipy"):
+        cin, gout = g[f"cf_{ref}_{M}_{N}_cin"], g[f"cf_{ref}_{M}_{N}_gout"]
+        out = torch.zeros(gout.shape, dtype=torch.complex128, device='cuda')
+        plan.backward(_t(cin), out, 1)
+        assert np.allclose(out.cpu().numpy(), gout, **TOL)
+        gin, cout = g[f"cf_{ref}_{M}_{N}_gin"], g[f"cf_{ref}_{M}_{N}_cout"]
+        out = torch.zeros(cout.shape, dtype=torch.complex128, device='cuda')
+        plan.forward(_t(gin), out, 1)
+        assert np.allclose(out.cpu().numpy(), cout, **TOL)
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (15, 22), (15, 15), (32, 48)])
+@pytest.mark.parametrize("alpha", [0, 1, 2])
+def test_chebyshev_vs_reference(golden, M, N, alpha):
+    import torch
+    from dedalus_b200.transforms import FastChebyshevTransform
+    g = golden("transforms.npz"); a = b = alpha - 0.5
+    plan = FastChebyshevTransform(N, M, a, b, -0.5, -0.5)
+    for ref in ("matrix", "scipy_dct"):
+        key = f"ch_{ref}_{M}_{N}_{alpha}"
+        out = torch.zeros(g[key + "_gout"].shape, dtype=torch.float64, device='cuda')
+        plan.backward(_t(g[key + "_cin"]), out, 2)
+        assert np.allclose(out.cpu().numpy(), g[key + "_gout"], **TOL)
+        out = torch.zeros(g[key + "_cout"].shape, dtype=torch.float64, device='cuda')
+        plan.forward(_t(g[key + "_gin"]), out, 2)
+        assert np.allclose(out.cpu().numpy(), g[key + "_cout"], **TOL)
+
+
+@pytest.mark.parametrize("M,N", [(16, 24), (12, 12)])
+@pytest.mark.parametrize("ab", [(0.0, 0.0), (1.0, 0.5)])
+def test_jacobi_matrix_transform_vs_reference(golden, M, N, ab):
+    import torch
+    from dedalus_b200.transforms import JacobiMatrixTransform
+    g = golden("transforms.npz"); a, b = ab
+    plan = JacobiMatrixTransform(N, M, a, b, a, b)
+    assert np.allclose(plan.forward_matrix, g[f"jac_{M}_{N}_{a}_{b}_fwdmat"], rtol=1e-11, atol=1e-12)
+    assert np.allclose(plan.backward_matrix, g[f"jac_{M}_{N}_{a}_{b}_bwdmat"], rtol=1e-11, atol=1e-12)
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((3, M, 5)); out = torch.zeros((3, N, 5), dtype=torch.float64, device='cuda')
+    plan.backward(_t(c), out, 1)
+    assert np.allclose(out.cpu().numpy(), np.einsum('ij,ojr->oir', g[f"jac_{M}_{N}_{a}_{b}_bwdmat"], c), **TOL)
+    back = torch.zeros((3, M, 5), dtype=torch.float64, device='cuda')
+    plan.forward(out, back, 1)
+    assert np.allclose(back.cpu().numpy(), c, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_round_trips_at_benchmark_sizes(axis):
+    """Size-independent property at the 256^3 / 3/2-dealias line length: backward then forward is the identity."""
+    import torch
+    from dedalus_b200.transforms import RealFourierTransform, FastChebyshevTransform
+    torch.manual_seed(0)
+    M, N = 256, 384
+    shape = [40, 36, 33]; shape[axis] = M
+    c = torch.randn(shape, dtype=torch.float64, device='cuda')
+    gshape = list(shape); gshape[axis] = N
+    g = torch.empty(gshape, dtype=torch.float64, device='cuda'); back = torch.empty_like(c)
+    cheb = FastChebyshevTransform(N, M, 1.5, 1.5, -0.5, -0.5)
+    cheb.backward(c, g, axis); cheb.forward(g, back, axis)
+    assert torch.allclose(back, c, rtol=1e-9, atol=1e-9)       # conversion back-solve conditioning ~1e3
+    rf = RealFourierTransform(N, M)
+    idx = [slice(None)] * 3; idx[axis] = 1
+    c[tuple(idx)] = 0                                            # -sin(0 x) slot carries no data
+    rf.backward(c, g, axis); rf.forward(g, back, axis)
+    assert torch.allclose(back, c, rtol=1e-12, atol=1e-12)
+
+
+def test_fused_derivatives_match_matrices():
+    import torch
+    from dedalus_b200.transforms import RealFourierTransform, FastChebyshevTransform
+    from dedalus_b200 import jacobi
+    rng = np.random.default_rng(3)
+    M, N = 24, 36
+    c = rng.standard_normal((5, M))
+    # Chebyshev: d/dz fused == (D c) transformed from the derivative basis
+    stretch = 0.5
+    plan = FastChebyshevTransform(N, M, -0.5, -0.5, -0.5, -0.5, stretch=stretch)
+    for d in (1, 2):
+        out = torch.empty((5, N), dtype=torch.float64, device='cuda')
+        plan.backward(_t(c), out, 1, deriv=d)
+        dc = c.copy(); a = -0.5
+        for j in range(d):
+            dc = (jacobi.differentiation_matrix(M, a + j, a + j) / stretch @ dc.T).T
+        z = jacobi.gauss_grid(N, -0.5, -0.5)[0]
+        ref = dc @ jacobi.polynomials(M, a + d, a + d, z)
+        assert np.allclose(out.cpu().numpy(), ref, rtol=1e-10, atol=1e-9)
