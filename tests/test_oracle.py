@@ -1,0 +1,77 @@
+"""Pin the oracle (oracle/) to outputs of the unmodified reference (tests/golden/*.npz)."""
+import numpy as np, pytest
+from scipy import sparse
+from oracle import transforms_oracle as T
+from oracle import rb_oracle, kdv_oracle
+
+TOL = dict(rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (16, 21), (32, 48), (12, 18), (10, 15)])
+def test_real_fourier(golden, M, N):
+    g = golden("transforms.npz")
+    fwd, bwd = T.rf_matrices(N, M)
+    for ref in ("matrix", "scipy"):
+        assert np.allclose(T.apply_along(bwd, g[f"rf_{ref}_{M}_{N}_cin"], 1), g[f"rf_{ref}_{M}_{N}_gout"], **TOL)
+        assert np.allclose(T.apply_along(fwd, g[f"rf_{ref}_{M}_{N}_gin"], 1), g[f"rf_{ref}_{M}_{N}_cout"], **TOL)
+        assert np.allclose(T.rf_backward_fft(g[f"rf_{ref}_{M}_{N}_cin"], N, 1), g[f"rf_{ref}_{M}_{N}_gout"], **TOL)
+        assert np.allclose(T.rf_forward_fft(g[f"rf_{ref}_{M}_{N}_gin"], M, 1), g[f"rf_{ref}_{M}_{N}_cout"], **TOL)
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (15, 22), (12, 18)])
+def test_complex_fourier(golden, M, N):
+    g = golden("transforms.npz")
+    fwd, bwd = T.cf_matrices(N, M)
+    assert np.allclose(T.apply_along(bwd, g[f"cf_scipy_{M}_{N}_cin"], 1), g[f"cf_scipy_{M}_{N}_gout"], **TOL)
+    assert np.allclose(T.apply_along(fwd, g[f"cf_scipy_{M}_{N}_gin"], 1), g[f"cf_scipy_{M}_{N}_cout"], **TOL)
+
+
+@pytest.mark.parametrize("M,N", [(16, 8), (16, 16), (16, 24), (15, 22), (15, 15), (32, 48)])
+@pytest.mark.parametrize("alpha", [0, 1, 2])
+def test_chebyshev(golden, M, N, alpha):
+    g = golden("transforms.npz"); a = alpha - 0.5
+    fwd, bwd = T.jacobi_matrices(N, M, a, a, -0.5, -0.5)
+    for ref in ("matrix", "scipy_dct"):
+        key = f"ch_{ref}_{M}_{N}_{alpha}"
+        assert np.allclose(T.apply_along(bwd, g[key + "_cin"], 2), g[key + "_gout"], rtol=1e-11, atol=1e-11)
+        assert np.allclose(T.apply_along(fwd, g[key + "_gin"], 2), g[key + "_cout"], rtol=1e-11, atol=1e-11)
+        assert np.allclose(T.cheb_backward_fft(g[key + "_cin"], N, 2, a, a), g[key + "_gout"], rtol=1e-11, atol=1e-11)
+        assert np.allclose(T.cheb_forward_fft(g[key + "_gin"], M, 2, a, a), g[key + "_cout"], rtol=1e-11, atol=1e-11)
+
+
+def _golden_matrix(g, tag, name):
+    shape = tuple(g[f"{tag}_{name}_shape"])
+    return sparse.coo_matrix((g[f"{tag}_{name}_val"], (g[f"{tag}_{name}_row"], g[f"{tag}_{name}_col"])), shape=shape).tocsr()
+
+
+@pytest.mark.parametrize("fname,groups", [("rb3d_8.npz", [(0, 0), (0, 2), (3, 0), (1, 2)]), ("rb2d_16x16.npz", [(0,), (1,), (5,)])])
+def test_rb_pencil_matrices(golden, fname, groups):
+    g = golden(fname)
+    orc = rb_oracle.RBOracle(int(g['dim']), int(g['Nh']), int(g['Nz']), float(g['Ra']))
+    for grp in groups:
+        tag = "pen_" + "_".join(str(k) for k in grp)
+        M, L, vr, vc, _, _ = orc.pencil_matrices(grp)
+        assert np.array_equal(vr, g[f"{tag}_valid_rows"]) and np.array_equal(vc, g[f"{tag}_valid_cols"])
+        for name, mine in (("M", M), ("L", L)):
+            ref = _golden_matrix(g, tag, name)
+            assert abs(mine - ref).max() <= 1e-11 * max(1.0, abs(ref).max()), (grp, name, abs(mine - ref).max())
+
+
+@pytest.mark.parametrize("fname,transforms", [("rb3d_8.npz", "fft"), ("rb3d_8.npz", "matrix"), ("rb2d_16x16.npz", "fft"),
+                                              ("rb3d_8x8x12_sbdf2.npz", "fft")])
+def test_rb_states(golden, fname, transforms):
+    g = golden(fname)
+    st = rb_oracle.run(int(g['dim']), int(g['Nh']), int(g['Nz']), float(g['Ra']), g['b0_c'], int(g['steps']), float(g['dt']),
+                       scheme=str(g['scheme']), transforms=transforms)
+    for name in ("p", "b", "u", "tau_b1", "tau_b2", "tau_u1", "tau_u2"):
+        ref = g[f"{name}_c"]
+        got = np.asarray(st[name]).reshape(ref.shape)
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-12), (name, np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("prefix", ["kdv_", "kdv443_"])
+def test_kdv(golden, prefix):
+    g = golden("kdv.npz")
+    orc = kdv_oracle.KdVOracle(int(g[prefix + "N"]))
+    u = orc.run(g[prefix + "u0_c"], int(g[prefix + "steps"]), float(g[prefix + "dt"]), scheme=str(g[prefix + "scheme"]))
+    assert np.allclose(u, g[prefix + "u_c"], rtol=1e-9, atol=1e-13)
