@@ -117,7 +117,7 @@ class RealFourier(FourierBase):
     # --- full matrices (used when this is the coupled last axis)
     def derivative_matrix(self):
         k = self.wavenumbers[::2]
-        blocks = [np.array([[0., -kk], [kk, 0.]]) for kk in k]
+        blocks = [sparse.coo_matrix(np.array([[0., -kk], [kk, 0.]])) for kk in k]
         return sparse.block_diag(blocks, format='csr')
 
     def embed_constant_vector(self):

@@ -82,9 +82,8 @@ class Field(Operand):
     def device_data(self):
         """Device tensor in the current layout (uploads the host mirror if it is newer)."""
         import torch
-        dev = self.dist.device or ('cuda' if torch.cuda.is_available() else None)
-        if dev is None:
-            raise RuntimeError("dedalus_b200: a CUDA device is required for device data (no CPU fallback).")
+        from .lib import compute_device
+        dev = compute_device()
         if self._fresh == 'host' or self._dev is None:
             self._dev = torch.from_numpy(np.ascontiguousarray(self._host)).to(dev)
             self._fresh = 'both'

@@ -72,7 +72,10 @@ class BoundLib:
         if missing:
             raise DedalusB200Error(f"library is missing C-ABI symbols: {missing}")
 
+    launches = 0      # number of kernel-launching C-ABI calls made through this binding
+
     def call(self, name, *args):
+        self.launches += 1
         rc = getattr(self, "_raw_" + name)(*args)
         if rc != 0:
             msg = self._raw_db_last_error()
@@ -90,11 +93,42 @@ def bind(path):
 
 
 _LIB = None
+_TEST_EMULATION = None      # set ONLY by tests/emu/emu_lib.install(): kernels compiled for the host, CPU tensors
+
+
+def install_test_emulation(bound):
+    """TEST HOOK (tests/emu only): route C-ABI calls to the CPU emulation build of the same kernels so the
+    Python orchestration can be exercised on the GPU-less build container.  Never called by the product."""
+    global _TEST_EMULATION
+    _TEST_EMULATION = bound
+
+
+def emulation_active():
+    return _TEST_EMULATION is not None
+
+
+def compute_device():
+    """torch device for all data: the current CUDA device (required), or 'cpu' under the test emulation."""
+    import torch
+    if _TEST_EMULATION is not None:
+        return torch.device('cpu')
+    if not torch.cuda.is_available():
+        raise DedalusB200Error("dedalus_b200 requires a CUDA device (sm_100a); there is no CPU fallback.")
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def current_stream():
+    import torch
+    if _TEST_EMULATION is not None:
+        return None
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def get_lib():
     """Load the CUDA library (built in-tree by dedalus_b200/build.py). Fails loudly if it is absent."""
     global _LIB
+    if _TEST_EMULATION is not None:
+        return _TEST_EMULATION
     if _LIB is None:
         if not LIB_PATH.exists():
             raise DedalusB200Error(

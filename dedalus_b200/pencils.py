@@ -579,8 +579,6 @@ def line_maps(batch, arena, side):
         members = [pos_of_nat.get(int(o + m), -1) for m in range(slot.size)]
         if all(p < 0 for p in members):
             continue
-        if any(p < 0 for p in members):
-            raise RuntimeError("Coefficient line split across components.")
         tshape, bases = arena.items[slot.owner]
         tsh, shp = arena.shapes[slot.owner]
         # strides of the local coefficient array (C order)
@@ -604,7 +602,18 @@ def line_maps(batch, arena, side):
                 g = batch.groups[:, i] - (g0_start if ax == 0 else 0)
                 off_s += g * st
             kind_tables.append(off_s)
-        lines.append((base, kinds[key], slot.size, members))
+        # a line may belong to this batch only in part (e.g. fully separable problems split per wavenumber
+        # block, or invalid modes): emit one entry per maximal run of consecutive member modes
+        m = 0
+        while m < slot.size:
+            if members[m] < 0:
+                m += 1
+                continue
+            m1 = m
+            while m1 < slot.size and members[m1] >= 0:
+                m1 += 1
+            lines.append((base + m, kinds[key], m1 - m, members[m:m1]))
+            m = m1
     m = BatchProgram()
     m.line_base = np.array([l[0] for l in lines], dtype=np.int64)
     m.line_kind = np.array([l[1] for l in lines], dtype=np.int32)

@@ -151,15 +151,14 @@ class InitialValueSolver:
 
     # ------------------------------------------------------------------------------------------------
     def stream(self):
-        import torch
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        from .lib import current_stream
+        return current_stream()
 
     def _init_device(self):
         import torch
-        if not torch.cuda.is_available():
-            raise DedalusB200Error("dedalus_b200 requires a CUDA device (sm_100a); there is no CPU fallback.")
+        from .lib import compute_device
+        self.device = compute_device()        # raises without a CUDA device: no CPU fallback
         self.lib = get_lib()
-        self.device = torch.device('cuda', torch.cuda.current_device())
         self.dist.device = self.device
         if np.issubdtype(self.dtype, np.complexfloating):
             raise NotImplementedError("complex-dtype IVPs run through the complex pencil path (not in this build)")
@@ -200,8 +199,11 @@ class InitialValueSolver:
                 v.set_device_data(view, 'c')
 
     def _mark_state_on_device(self):
+        # like the reference, state fields are left in coefficient space at their dealias scales after the
+        # RHS evaluation (core/evaluator.py:116-133), so e.g. u['g'] returns the dealiased grid unless the user
+        # calls change_scales(1) first (as the stock scripts do)
         for v, view in zip(self.state, self.state_views):
-            v.set_device_data(view, 'c')
+            v.set_device_data(view, 'c', scales=v.dealias)
 
     def _check_factor_info(self):
         bad = sum(int(db.info.item()) for db in self.dbatches)
@@ -237,7 +239,8 @@ class InitialValueSolver:
 
     def _sync_clock(self):
         import torch
-        torch.cuda.synchronize()
+        if self.device.type == 'cuda':
+            torch.cuda.synchronize()
         return time.time()
 
     # ---- Runge-Kutta IMEX (reference timesteppers.py:552-644) -------------------------------------------

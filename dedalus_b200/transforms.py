@@ -29,7 +29,8 @@ def _torch():
 
 
 def _stream():
-    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+    from .lib import current_stream
+    return current_stream()
 
 
 def _dptr(t):
@@ -68,7 +69,8 @@ class DevicePlan:
 
 
 def _check(x, name):
-    if not x.is_cuda or not x.is_contiguous():
+    from .lib import emulation_active
+    if not (x.is_cuda or emulation_active()) or not x.is_contiguous():
         raise ValueError(f"{name} must be a contiguous CUDA tensor.")
 
 

@@ -7,10 +7,16 @@ thread_local EmuState emu_cur;
 namespace {
 struct Fiber {
     ucontext_t ctx;
-    std::vector<unsigned char> stack;
+    unsigned char* stack = nullptr;
     EmuState st;
     bool done = false;
 };
+const size_t STACK = 128 * 1024;
+thread_local std::vector<unsigned char*> stack_pool;    // allocated once, reused by every launch
+unsigned char* get_stack(size_t i) {
+    while (stack_pool.size() <= i) stack_pool.push_back((unsigned char*)malloc(STACK));
+    return stack_pool[i];
+}
 thread_local ucontext_t sched_ctx;
 thread_local Fiber* running = nullptr;
 thread_local const std::function<void()>* cur_body = nullptr;
@@ -33,8 +39,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
     const size_t nthreads = (size_t)block.x * block.y * block.z;
     std::vector<unsigned char> shared(smem + 64);
     std::vector<Fiber> fibers(nthreads);
-    const size_t STACK = 256 * 1024;
-    for (auto& f : fibers) f.stack.resize(STACK);
+    for (size_t i = 0; i < nthreads; ++i) fibers[i].stack = get_stack(i);
     cur_body = &body;
     for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
@@ -49,8 +54,8 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
             f.st.tid = {tx, ty, tz}; f.st.bid = {bx, by, bz}; f.st.bdim = block; f.st.gdim = grid;
             f.st.smem = shared.data();
             getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack.data();
-            f.ctx.uc_stack.ss_size = f.stack.size();
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = STACK;
             f.ctx.uc_link = &sched_ctx;
             makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }

@@ -41,3 +41,12 @@ class EmuPlan:
 
     def ref(self):
         return C.byref(self.struct)
+
+
+def install():
+    """Route the product's C-ABI calls to the emulated kernels (CPU tensors). Test-only."""
+    dlib.install_test_emulation(emu())
+
+
+def uninstall():
+    dlib.install_test_emulation(None)

@@ -1,0 +1,41 @@
+"""Whole-solver orchestration (dedalus_b200/solvers.py, evaluator.py, transforms.py) executed on the CPU through
+the test-only kernel emulation, against reference states.  The GPU versions of these tests are in
+test_gpu_solver.py; this file exists so the launch sequences can be checked on the GPU-less build container."""
+import numpy as np, pytest
+import dedalus_b200 as d3
+from dedalus_b200 import examples
+from emu import emu_lib as E
+
+TOL = dict(rtol=1e-8, atol=1e-12)
+
+
+@pytest.fixture(autouse=True)
+def emulation():
+    E.install()
+    yield
+    E.uninstall()
+
+
+def test_rb3d_steps(golden):
+    g = golden("rb3d_8.npz")
+    pb = examples.rayleigh_benard(dim=3, Nh=8, Nz=8, Rayleigh=1e6)
+    solver = pb['problem'].build_solver(d3.RK222)
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    assert np.allclose(pb['b']['c'], g['b0_c'], rtol=1e-12, atol=1e-14)
+    for i in range(2):
+        solver.step(0.01)
+        if i == 0:
+            for name in ('p', 'b', 'u'):
+                assert np.allclose(pb[name]['c'], g[f"{name}_c_step1"], **TOL), name
+
+
+@pytest.mark.parametrize("prefix", ["kdv_", "kdv443_"])
+def test_kdv(golden, prefix):
+    g = golden("kdv.npz")
+    pk = examples.kdv_burgers(N=int(g[prefix + "N"]))
+    examples.kdv_initial_condition(pk['u'], pk['xbasis'], pk['Lx'])
+    solver = pk['problem'].build_solver(getattr(d3, str(g[prefix + "scheme"])))
+    for i in range(int(g[prefix + "steps"])):
+        solver.step(float(g[prefix + "dt"]))
+    assert np.allclose(pk['u']['c'], g[prefix + "u_c"], **TOL)
+    assert np.allclose(pk['u']['g'], g[prefix + "u_g"], **TOL)
