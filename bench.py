@@ -1,0 +1,239 @@
+#!/usr/bin/env python
+"""Headline benchmark: timesteps/sec of 3-D Rayleigh-Benard (Fourier x Fourier x Chebyshev, RK222, fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 256] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full solver.step(dt): 2 IMEX stages, each = RHS evaluation (15 backward + 4 forward 3-D
+transforms and the fused products), template mat-vecs, RHS combination + per-pencil LU solves, scatter.
+`value` times K steps with the state resident in HBM (CUDA events, barrier + synchronize both sides, max over
+ranks); `e2e` times the same K steps through the public API with the state uploaded from pinned host memory and
+read back every step.  `--impl reference` times the oracle's CPU restatement of the reference algorithm
+(oracle/cpu_bench.py) on a bounded sample with all host cores.
+"""
+import argparse, json, os, subprocess, sys, threading, time, pathlib
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "timesteps/sec 3D Rayleigh-Benard 256^3 fp64"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--dim", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    N = args.size
+    return dict(workload=f"3-D Rayleigh-Benard Fourier x Fourier x Chebyshev {N}^3, dealias 3/2 ({int(1.5*N)}^3 grid), "
+                         f"Ra=1e6 Pr=1, RK222, fixed dt, seed-42 initial condition (SURVEY.md Appendix C)",
+                N=N, dim=args.dim, timestepper="RK222", dt=1e-2 * 64.0 / N,
+                l2_policy="working set (state + factors, tens of GB) exceeds the 126 MB L2 every step; no explicit flush needed")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_reference(args):
+    """CPU arm: oracle restatement of the reference algorithm, bounded sample, all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    cfg = workload(args)
+    cores = os.cpu_count() or 1
+    vals, infos = [], []
+    n_runs = max(1, min(args.steps, 3))
+    slab = 16 if args.size >= 128 else 8
+    for _ in range(min(args.warmup, 1) + n_runs):
+        r = cpu_bench.sampled_step(dim=args.dim, N=args.size, dt=cfg['dt'], cores=cores, slab=min(slab, args.size),
+                                   n_pencils=4 * cores)
+        vals.append(r['steps_per_sec']); infos.append(r)
+    vals = vals[min(args.warmup, 1):]
+    v = float(np.median(vals))
+    info = infos[-1]
+    line = dict(impl="reference", metric=METRIC, value=v, unit="steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 / v, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                config=cfg,
+                cpu_baseline=dict(value=v, unit="steps/s", cores=info['cores'], kind="port", sample=info['sample']),
+                e2e=dict(value=v, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="oracle port of the reference CPU path (scipy pocketfft + SuperLU); the Python reference itself cannot travel to the GPU box")
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import dedalus_b200 as d3
+    from dedalus_b200 import examples
+    from dedalus_b200.lib import get_lib
+    cfg = workload(args)
+    N, dt = args.size, cfg['dt']
+    t_setup = time.time()
+    pb = examples.rayleigh_benard(dim=args.dim, Nh=N, Nz=N, Rayleigh=1e6, mesh=(world,) if world > 1 else None)
+    solver = pb['problem'].build_solver(d3.RK222)
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    lib = get_lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        solver.step(dt)
+    barrier()
+    setup_s = time.time() - t_setup
+    # ---- timed region: K device-resident steps, per-launch events recorded for the roofline accounting
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    solver.prof = []
+    l0 = lib.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        solver.step(dt)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = solver.prof
+    solver.prof = None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = args.steps / (ms * 1e-3)
+    # ---- per-kernel accounting
+    agg = {}
+    for name, a, b, nbytes in prof:
+        d = agg.setdefault(name, dict(ms=0.0, bytes=0, launches=0))
+        d['ms'] += a.elapsed_time(b); d['bytes'] += nbytes; d['launches'] += 1
+    total_kernel_ms = sum(d['ms'] for d in agg.values()) or 1.0
+    kernels = {k: dict(ms_per_step=d['ms'] / args.steps, launches_per_step=d['launches'] / args.steps,
+                       gbps=d['bytes'] / (d['ms'] * 1e-3) / 1e9 if d['ms'] > 0 else None,
+                       share=d['ms'] / total_kernel_ms) for k, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])}
+    peaks = {}
+    try:
+        peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = next(iter(kernels)) if kernels else None
+    roofline = None
+    if dom:
+        d = agg[dom]
+        ach = d['bytes'] / (d['ms'] * 1e-3) / 1e9
+        roofline = dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                        peak_source="MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                        algorithmic_bytes_per_launch=d['bytes'] / d['launches'], avg_launch_ms=d['ms'] / d['launches'],
+                        traffic=None)
+    # ---- end-to-end: state uploaded from pinned host memory and read back every step, through solver.step()
+    e2e = None
+    if not args.no_e2e:
+        nst = solver.state_t.numel()
+        h_in = torch.empty(nst, dtype=torch.float64).pin_memory()
+        h_out = torch.empty(nst, dtype=torch.float64).pin_memory()
+        h_in.copy_(solver.state_t)
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        ksteps = max(2, min(args.steps, 5))
+        f0.record()
+        for _ in range(ksteps):
+            solver.state_t.copy_(h_in, non_blocking=True)        # H2D: this step's input state
+            solver.step(dt)
+            h_out.copy_(solver.state_t, non_blocking=True)       # D2H: this step's result
+        f1.record()
+        barrier()
+        ms2 = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms2], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        e2e = dict(value=ksteps / (ms2 * 1e-3), unit="steps/s", h2d_bytes_per_step=int(nst * 8 * world), d2h_bytes_per_step=int(nst * 8 * world),
+                   path="solver.step(dt) with the coefficient state copied host->device from pinned memory before and device->host after every step")
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+        r = cpu_bench.sampled_step(dim=args.dim, N=N, dt=dt, cores=os.cpu_count() or 1, slab=min(16, N), n_pencils=4 * (os.cpu_count() or 1))
+        cpu = dict(value=r['steps_per_sec'], unit="steps/s", cores=r['cores'], kind="port", sample=r['sample'])
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                    data="synthetic", config=dict(cfg, parallelism=f"pencil{world}" if world > 1 else "single", setup_seconds=setup_s,
+                                                  pencil_systems=sum(b.S for b in solver.batches), total_modes=solver.total_modes),
+                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -191,9 +191,17 @@ class RHSPlan:
         self.dealias = tuple(b.dealias[0] for b in self.bases)
         self.cshape = tuple(dist.coeff_local_slice(ax, b).stop - dist.coeff_local_slice(ax, b).start for ax, b in enumerate(self.bases))
         self.gshape_full = tuple(b.grid_size(s) for b, s in zip(self.bases, self.dealias))
-        if dist.size > 1:
-            raise NotImplementedError("use DistributedRHSPlan")
-        self.gshape = self.gshape_full
+        self.P = dist.size
+        if self.P > 1:
+            from .transposes import check_divisible, get_planner
+            if dim < 2:
+                raise NotImplementedError("1-D problems cannot be distributed.")
+            check_divisible(dist, self.bases, self.dealias)
+            self.planner = get_planner(dist)
+            # full grid layout: axis 1 distributed (after the single transpose hop)
+            self.gshape = (self.gshape_full[0], self.gshape_full[1] // self.P) + tuple(self.gshape_full[2:])
+        else:
+            self.gshape = self.gshape_full
         self.npoints = int(np.prod(self.gshape))
         # ---- pointwise program
         term_ptr, coef, fac_ptr, fac = [0], [], [0], []
@@ -253,11 +261,11 @@ class RHSPlan:
                 parent = key
             self.leaf_of_input.append(parent)
         self.levels = levels
-        # shapes after each level
+        # shapes after each level (before the transpose hop axis 1 is still complete and axis 0 block-local)
         shp = list(self.cshape)
         self.level_shapes = []
         for lvl, ax in enumerate(self.axes_order):
-            shp[ax] = self.gshape[ax]
+            shp[ax] = self.gshape_full[ax]
             self.level_shapes.append(tuple(shp))
 
     def set_static(self, arena_tensor):
@@ -270,6 +278,7 @@ class RHSPlan:
         import torch, ctypes as C
         from .transforms import cached_plan, _dptr, _stream
         from .lib import get_lib
+        from .solvers import Timed
         if self.n_out == 0:
             return
         dim = self.dist.dim
@@ -282,6 +291,17 @@ class RHSPlan:
             final = (lvl == dim - 1)
             if not final:
                 bufs[lvl] = self._scratch(('bwd', lvl), (len(nodes),) + self.level_shapes[lvl])
+            prev = bufs[lvl - 1] if lvl > 0 else None
+            if final and self.P > 1:
+                # transpose hop (axis 0 <-> axis 1) for the whole stack of level-(dim-2) arrays in ONE all-to-all
+                nn = prev.shape[0]
+                n1loc, n2 = prev.shape[1], prev.shape[2]
+                n3 = int(np.prod(prev.shape[3:], dtype=int))
+                tshape = (nn, n1loc * self.P, n2 // self.P) + tuple(prev.shape[3:])
+                tr = self._scratch(('tr_bwd',), tshape)
+                with Timed(self.solver.prof, "transpose_bwd", 8 * 2 * prev.numel()):
+                    self.planner.localize_columns(prev.view(nn, n1loc, n2, n3), tr.view(nn, n1loc * self.P, n2 // self.P, n3))
+                prev = tr
             for key, nd in nodes.items():
                 f = nd['field']
                 basis = f.bases[ax]
@@ -289,14 +309,16 @@ class RHSPlan:
                 if lvl == 0:
                     src = f.device_data()[self._comp_index(f, nd['comp'])]
                 else:
-                    src = bufs[lvl - 1][self.levels[lvl - 1][nd['parent']]['index']]
+                    src = prev[self.levels[lvl - 1][nd['parent']]['index']]
                 if final:
                     dst = self.grid_in[self._input_slot(key)]
                 else:
                     dst = bufs[lvl][nd['index']]
-                plan.backward(src, dst, ax, deriv=nd['deriv'])
+                with Timed(self.solver.prof, f"transform_bwd_axis{ax}", 8 * (src.numel() + dst.numel())):
+                    plan.backward(src, dst, ax, deriv=nd['deriv'])
         # ---- phase 2: pointwise products
-        get_lib().call("db_pointwise", _dptr(self.grid_in), _dptr(self.grid_out), self.npoints, self.n_in, self.n_out,
+        with Timed(self.solver.prof, "pointwise", 8 * self.npoints * (self.n_in + self.n_out)):
+          get_lib().call("db_pointwise", _dptr(self.grid_in), _dptr(self.grid_out), self.npoints, self.n_in, self.n_out,
                        _dptr(self.term_ptr), _dptr(self.coef), _dptr(self.fac_ptr), _dptr(self.fac), self.nfac, _stream())
         # ---- phase 3: forward transforms (axes first -> last), all outputs stacked
         cur = self.grid_out
@@ -306,8 +328,17 @@ class RHSPlan:
                 plan = cached_plan(basis, self.dealias[ax])
                 shp = list(cur.shape); shp[1 + ax] = plan.M
                 out = self._scratch(('fwd', ax), tuple(shp))
-                plan.forward(cur, out, 1 + ax)
+                with Timed(self.solver.prof, f"transform_fwd_axis{ax}", 8 * (cur.numel() + out.numel())):
+                    plan.forward(cur, out, 1 + ax)
                 cur = out
+                if ax == 0 and self.P > 1:
+                    nn, n1, n2loc = cur.shape[0], cur.shape[1], cur.shape[2]
+                    n3 = int(np.prod(cur.shape[3:], dtype=int))
+                    tshape = (nn, n1 // self.P, n2loc * self.P) + tuple(cur.shape[3:])
+                    tr = self._scratch(('tr_fwd',), tshape)
+                    with Timed(self.solver.prof, "transpose_fwd", 8 * 2 * cur.numel()):
+                        self.planner.localize_rows(cur.view(nn, n1, n2loc, n3), tr.view(nn, n1 // self.P, n2loc * self.P, n3))
+                    cur = tr
             else:
                 for o, (off, shp, eq_bases) in enumerate(self.out_dest):
                     eqb = eq_bases[ax]
@@ -319,7 +350,8 @@ class RHSPlan:
                         plan = cached_plan(basis, self.dealias[ax])
                     n = int(np.prod(shp))
                     dst = eq_arena_tensor[off:off + n].view(shp)
-                    plan.forward(cur[o], dst, ax)
+                    with Timed(self.solver.prof, f"transform_fwd_axis{ax}", 8 * (cur[o].numel() + dst.numel())):
+                        plan.forward(cur[o], dst, ax)
 
     def _fwd_plan_last(self, prod_basis, target_basis):
         from .transforms import FastChebyshevTransform, cached_plan

@@ -20,6 +20,26 @@ def _i32(t, a, dev):
     return t.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
 
 
+class Timed:
+    """Optional CUDA-event bracket around one kernel launch (bench.py roofline accounting)."""
+
+    def __init__(self, prof, name, nbytes):
+        self.prof, self.name, self.nbytes = prof, name, nbytes
+
+    def __enter__(self):
+        if self.prof is not None:
+            import torch
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.prof is not None:
+            self.e1.record()
+            self.prof.append((self.name, self.e0, self.e1, self.nbytes))
+        return False
+
+
 class DeviceBatch:
     """Device copies of one batch's programs and work vectors."""
 
@@ -65,20 +85,24 @@ class DeviceBatch:
     # ---- kernels -----------------------------------------------------------------------------------
     def gather(self, side, arena_t, vec):
         m = self.maps[side]
-        self.solver.lib.call("db_pencil_gather", arena_t.data_ptr(), vec.data_ptr(), self.S, self.ld, m['nlines'], m['max_len'],
+        with Timed(self.solver.prof, "pencil_gather", 16 * self.n * self.S):
+          self.solver.lib.call("db_pencil_gather", arena_t.data_ptr(), vec.data_ptr(), self.S, self.ld, m['nlines'], m['max_len'],
                              m['base'].data_ptr(), m['kind'].data_ptr(), m['ptr'].data_ptr(), m['pos'].data_ptr(),
                              m['sys_off'].data_ptr(), self.ld, self.solver.stream())
 
     def scatter(self, vec, arena_t):
         m = self.maps['cols']
-        self.solver.lib.call("db_pencil_scatter", vec.data_ptr(), arena_t.data_ptr(), self.S, self.ld, m['nlines'], m['max_len'],
+        with Timed(self.solver.prof, "pencil_scatter", 16 * self.n * self.S):
+          self.solver.lib.call("db_pencil_scatter", vec.data_ptr(), arena_t.data_ptr(), self.S, self.ld, m['nlines'], m['max_len'],
                              m['base'].data_ptr(), m['kind'].data_ptr(), m['ptr'].data_ptr(), m['pos'].data_ptr(),
                              m['sys_off'].data_ptr(), self.ld, self.solver.stream())
 
     def matvec(self, x, y_m=None, y_l=None):
         M, L = self.mv['M'], self.mv['L']
         p = lambda t: t.data_ptr() if t is not None else None
-        self.solver.lib.call("db_pencil_matvec", self.n, self.S, self.ld, self.mono.data_ptr(), x.data_ptr(),
+        nout = (y_m is not None) + (y_l is not None)
+        with Timed(self.solver.prof, "pencil_matvec", 8 * self.n * self.S * (1 + nout)):
+          self.solver.lib.call("db_pencil_matvec", self.n, self.S, self.ld, self.mono.data_ptr(), x.data_ptr(),
                              M[0].data_ptr(), M[1].data_ptr(), M[2].data_ptr(), M[3].data_ptr(), p(y_m),
                              L[0].data_ptr(), L[1].data_ptr(), L[2].data_ptr(), L[3].data_ptr(), p(y_l), self.solver.stream())
 
@@ -105,7 +129,10 @@ class DeviceBatch:
         lc.nvec = len(terms)
         for j, (v, c) in enumerate(terms):
             lc.vec[j] = v.data_ptr(); lc.coef[j] = c
-        self.solver.lib.call("db_pencil_solve", lu.data_ptr(), self.n, self.S, self.ld, self.fwd_ptr.data_ptr(), self.fwd_col.data_ptr(),
+        # algorithmic bytes: every stored LU entry once + each RHS vector once + the solution written once
+        nbytes = 8 * self.S * (self.prog.nE + self.n * (len(terms) + 1))
+        with Timed(self.solver.prof, "pencil_solve", nbytes):
+          self.solver.lib.call("db_pencil_solve", lu.data_ptr(), self.n, self.S, self.ld, self.fwd_ptr.data_ptr(), self.fwd_col.data_ptr(),
                              self.bwd_ptr.data_ptr(), self.bwd_col.data_ptr(), C.byref(lc), x.data_ptr(), self.solver.stream())
 
 
@@ -143,6 +170,7 @@ class InitialValueSolver:
         self.total_modes = sum(int(c.valid_cols.sum()) * len(c.groups) for c in self.builder.classes.values())
         self.setup_time = time.time() - t0
         self._device_ready = False
+        self.prof = None            # set to a list to collect (name, start_event, end_event, bytes) per launch
         self._lhs_key = None
         self._ts_iteration = 0
         self._dt_hist = deque([0.0] * getattr(timestepper, 'steps', 1))

@@ -1,0 +1,148 @@
+"""Distributed pencil transposes between the two layouts of a 1-D process mesh (X1).
+
+Reference: Transpose (core/distributor.py:696-924) driving FFTWTranspose (core/transposes.pyx:22-246): every rank
+copies its slab into a (N1, n2_local, N0, N3) buffer, FFTW-MPI exchanges blocks (MPI alltoall inside FFTW) and the
+result is copied out again; with GROUP_TRANSPOSES all fields sharing a shape travel together (842-871).
+Here one hop is: pack kernel (per-destination contiguous blocks) -> one NCCL all-to-all over NVLink/NVSwitch for
+the whole stack of fields -> unpack kernel (csrc/pointwise.cu: db_transpose_*).  The planner keeps the reference's
+method names: localize_columns (towards grid space) / localize_rows (towards coefficient space).
+"""
+import ctypes as C
+import numpy as np
+from .lib import get_lib, current_stream
+
+
+class TransposePlanner:
+    def __init__(self, dist):
+        import torch.distributed as td
+        self.dist = dist
+        self.P = dist.size
+        self.td = td
+        self._bufs = {}
+
+    def _buf(self, key, numel, like):
+        import torch
+        t = self._bufs.get(key)
+        if t is None or t.numel() < numel or t.device != like.device:
+            t = torch.empty(numel, dtype=like.dtype, device=like.device)
+            self._bufs[key] = t
+        return t[:numel]
+
+    def _alltoall(self, recv, send):
+        td = self.td
+        if td.get_backend() == "gloo":
+            # gloo has no all_to_all for CPU tensors in every build: exchange blocks with paired send/recv
+            P, rank = self.P, td.get_rank()
+            sb, rb = send.view(P, -1), recv.view(P, -1)
+            rb[rank].copy_(sb[rank])
+            reqs = []
+            for p in range(P):
+                if p != rank:
+                    reqs.append(td.isend(sb[p].contiguous(), p))
+                    reqs.append(td.irecv(rb[p], p))
+            for r in reqs:
+                r.wait()
+        else:
+            td.all_to_all_single(recv, send)
+
+    def localize_columns(self, a, out):
+        """(B, n1_local, n2, n3) distributed along axis 1  ->  (B, n1, n2_local, n3) distributed along axis 2."""
+        B, n1loc, n2, n3 = a.shape
+        P = self.P
+        send = self._buf('send', a.numel(), a); recv = self._buf('recv', out.numel(), a)
+        lib = get_lib()
+        lib.call("db_transpose_pack", a.data_ptr(), send.data_ptr(), B, n1loc, n2, n3, P, current_stream())
+        self._alltoall(recv, send)
+        lib.call("db_transpose_unpack", recv.data_ptr(), out.data_ptr(), B, n1loc * P, n2 // P, n3, P, current_stream())
+
+    def localize_rows(self, a, out):
+        """(B, n1, n2_local, n3) distributed along axis 2  ->  (B, n1_local, n2, n3) distributed along axis 1."""
+        B, n1, n2loc, n3 = a.shape
+        P = self.P
+        send = self._buf('send', a.numel(), a); recv = self._buf('recv', out.numel(), a)
+        lib = get_lib()
+        lib.call("db_transpose_pack_rev", a.data_ptr(), send.data_ptr(), B, n1, n2loc, n3, P, current_stream())
+        self._alltoall(recv, send)
+        lib.call("db_transpose_unpack_rev", recv.data_ptr(), out.data_ptr(), B, n1 // P, n2loc * P, n3, P, current_stream())
+
+
+_planners = {}
+
+
+def get_planner(dist):
+    if id(dist) not in _planners:
+        _planners[id(dist)] = TransposePlanner(dist)
+    return _planners[id(dist)]
+
+
+def check_divisible(dist, bases, scales):
+    P = dist.size
+    b0, b1 = bases[0], bases[1] if len(bases) > 1 else None
+    if b0 is None or b1 is None:
+        raise NotImplementedError("Distributed fields need bases along the first two axes.")
+    if (b0.size // b0.group_size) % P:
+        raise ValueError(f"Axis-0 groups ({b0.size // b0.group_size}) must divide evenly over {P} ranks.")
+    if b1.grid_size(scales[1]) % P:
+        raise ValueError(f"Axis-1 grid size ({b1.grid_size(scales[1])}) must divide evenly over {P} ranks.")
+
+
+def transform_field_distributed(field, layout):
+    """Coefficient <-> grid layout change of one field on a 1-D mesh:
+    coeff (x local blocks) -> T(last..1) -> transpose(0 <-> 1) -> T(0) -> grid (axis 1 local blocks)
+    (reference Distributor._build_layouts, distributor.py:131-175 with R=1)."""
+    import torch
+    from .transforms import cached_plan
+    dist = field.dist
+    dim = dist.dim
+    if any(b is None for b in field.bases[:2]):
+        if all(b is None for b in field.bases):
+            field.layout = field._layout_name(layout)
+            return
+        raise NotImplementedError("Distributed layout changes need bases along the first two axes.")
+    check_divisible(dist, field.bases, field.scales)
+    planner = get_planner(dist)
+    nt = len(field.tensorsig)
+    scales = field.scales
+    cur = field.device_data()
+    B = int(np.prod(cur.shape[:nt], dtype=int))
+    if layout == 'g':
+        for ax in range(dim - 1, 0, -1):
+            b = field.bases[ax]
+            if b is None:
+                continue
+            plan = cached_plan(b, scales[ax])
+            shp = list(cur.shape); shp[nt + ax] = plan.N
+            out = torch.empty(shp, dtype=cur.dtype, device=cur.device)
+            plan.backward(cur.contiguous(), out, nt + ax)
+            cur = out
+        n1loc, n2 = cur.shape[nt], cur.shape[nt + 1]
+        n3 = int(np.prod(cur.shape[nt + 2:], dtype=int))
+        out = torch.empty(cur.shape[:nt] + (n1loc * dist.size, n2 // dist.size) + cur.shape[nt + 2:], dtype=cur.dtype, device=cur.device)
+        planner.localize_columns(cur.contiguous().view(B, n1loc, n2, n3), out.view(B, n1loc * dist.size, n2 // dist.size, n3))
+        cur = out
+        plan = cached_plan(field.bases[0], scales[0])
+        shp = list(cur.shape); shp[nt] = plan.N
+        out = torch.empty(shp, dtype=cur.dtype, device=cur.device)
+        plan.backward(cur, out, nt)
+        field.set_device_data(out, 'g')
+    else:
+        plan = cached_plan(field.bases[0], scales[0])
+        shp = list(cur.shape); shp[nt] = plan.M
+        out = torch.empty(shp, dtype=cur.dtype, device=cur.device)
+        plan.forward(cur.contiguous(), out, nt)
+        cur = out
+        n1, n2loc = cur.shape[nt], cur.shape[nt + 1]
+        n3 = int(np.prod(cur.shape[nt + 2:], dtype=int))
+        out = torch.empty(cur.shape[:nt] + (n1 // dist.size, n2loc * dist.size) + cur.shape[nt + 2:], dtype=cur.dtype, device=cur.device)
+        planner.localize_rows(cur.view(B, n1, n2loc, n3), out.view(B, n1 // dist.size, n2loc * dist.size, n3))
+        cur = out
+        for ax in range(1, dim):
+            b = field.bases[ax]
+            if b is None:
+                continue
+            plan = cached_plan(b, scales[ax])
+            shp = list(cur.shape); shp[nt + ax] = plan.M
+            out = torch.empty(shp, dtype=cur.dtype, device=cur.device)
+            plan.forward(cur.contiguous(), out, nt + ax)
+            cur = out
+        field.set_device_data(cur, 'c')

@@ -3,8 +3,11 @@
 Each function cites the reference code it follows (paths under /root/reference/dedalus).  Two flavours:
 matrix transforms (the reference's ground-truth MMT classes) and fast transforms (its scipy-FFT classes).
 """
+import functools
 import numpy as np
 import scipy.fft
+import scipy.linalg
+from scipy import sparse
 from scipy.special import eval_jacobi, gammaln, roots_jacobi
 
 
@@ -108,6 +111,24 @@ def _quad(a, b, K):
     return roots_jacobi(K, a, b)
 
 
+@functools.lru_cache(maxsize=64)
+def _conversion_cached(N, a0, b0, a1, b1):
+    C = jacobi_conversion(N, a0, b0, a1, b1)
+    C[np.abs(C) < 1e-13] = 0
+    nd = int(round((a1 - a0) + (b1 - b0))) + 1
+    ab = np.zeros((nd, N))                       # LAPACK upper-band storage for solve_banded((0, nd-1), ...)
+    for d in range(nd):
+        ab[nd - 1 - d, d:] = np.diagonal(C, d)
+    return sparse.csr_matrix(C), ab, nd
+
+
+def _apply_sparse_along(Cs, data, axis):
+    """tools/array.py:171-203 apply_sparse along an axis."""
+    moved = np.moveaxis(data, axis, 0)
+    out = Cs @ moved.reshape(moved.shape[0], -1)
+    return np.moveaxis(out.reshape((Cs.shape[0],) + moved.shape[1:]), 0, axis)
+
+
 def jacobi_conversion(N, a0, b0, a1, b1):
     """tools/jacobi.py:229-245 conversion_matrix, computed here by exact Gauss quadrature projection
     C_ij = int w1 p_i^(a1,b1) p_j^(a0,b0)."""
@@ -163,8 +184,8 @@ def cheb_forward_fft(g, M, axis, a=-0.5, b=-0.5):
     if not convert:
         return out
     Kin = min(M, N)
-    Cm = jacobi_conversion(max(M, N), -0.5, -0.5, a, b)[:M, :Kin]
-    return apply_along(Cm, out[axslice(axis, 0, Kin)], axis)
+    Cs = _conversion_cached(max(M, N), -0.5, -0.5, a, b)[0][:M, :Kin]
+    return _apply_sparse_along(Cs, out[axslice(axis, 0, Kin)], axis)
 
 
 def cheb_backward_fft(c, N, axis, a=-0.5, b=-0.5):
@@ -176,8 +197,10 @@ def cheb_backward_fft(c, N, axis, a=-0.5, b=-0.5):
     if M > N:
         data[axslice(axis, Kmax + 1, None)] = 0
     if (a, b) != (-0.5, -0.5):
-        Cm = jacobi_conversion(M, -0.5, -0.5, a, b)
-        data = apply_along(np.linalg.inv(np.triu(Cm)), data, axis)
+        _, ab, nd = _conversion_cached(M, -0.5, -0.5, a, b)
+        moved = np.moveaxis(data, axis, 0)
+        sol = scipy.linalg.solve_banded((0, nd - 1), ab, moved.reshape(M, -1))      # upper-triangular banded back-substitution
+        data = np.moveaxis(sol.reshape(moved.shape), 0, axis).copy()
     data[axslice(axis, 1, Kmax + 1, 2)] *= -1
     shp = list(c.shape); shp[axis] = N
     temp = np.zeros(shp)
