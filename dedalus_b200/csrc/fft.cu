@@ -66,46 +66,100 @@ template <bool INV> __device__ __forceinline__ void dft3(double2* v)
     v[1] = cadd(t2, t3);
     v[2] = csub(t2, t3);
 }
-// generic radix (<= 16) through the twiddle table: w_r^j = tw[(nc/r) * j]
-template <bool INV> __device__ __forceinline__ void dftr(double2* v, int r, const double* tw, int nc)
+// generic odd radix through the twiddle table: w_r^j = tw[(nc/r) * j]
+template <bool INV, int R> __device__ __forceinline__ void dftr(double2* v, const double* tw, int nc)
 {
-    double2 y[16];
-    const int step = nc / r;
-    for (int qp = 0; qp < r; ++qp) {
+    double2 y[R];
+    const int step = nc / R;
+#pragma unroll
+    for (int qp = 0; qp < R; ++qp) {
         double2 acc = v[0];
-        for (int q = 1; q < r; ++q) {
-            double2 w = ldtw(tw, step * ((q * qp) % r));
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+            double2 w = ldtw(tw, step * ((q * qp) % R));
             acc = cadd(acc, INV ? cmulc(v[q], w) : cmul(v[q], w));
         }
         y[qp] = acc;
     }
-    for (int q = 0; q < r; ++q) v[q] = y[q];
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = y[q];
 }
 
-template <bool INV>
-__device__ void fft_pass(double2* buf, int nc, int TP, int Tc, int r, int L, const double* tw)
+// one radix-R pass over the whole tile; R is a template parameter so the butterfly lives in registers
+template <bool INV, int R>
+__device__ __forceinline__ void fft_pass_r(double2* buf, int nc, int TP, int Tc, int L, const double* tw)
 {
-    const int m = L / r;
-    const int nbf = nc / r;
+    const int m = L / R;
+    const int nbf = nc / R;
     const int tstep = nc / L;
     for (int w = threadIdx.x; w < nbf * Tc; w += blockDim.x) {
         const int t = w % Tc;
         const int bf = w / Tc;
         const int b = bf / m, k = bf - b * m;
-        double2 v[16];
+        double2 v[R];
         const int i0 = b * L + k;
-        for (int q = 0; q < r; ++q) v[q] = buf[(i0 + q * m) * TP + t];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = buf[(i0 + q * m) * TP + t];
         if (INV) {   // DIT: twiddle first (conjugate), then butterfly
-            for (int q = 1; q < r; ++q) v[q] = cmulc(v[q], ldtw(tw, (tstep * k * q) % nc));
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], ldtw(tw, (tstep * k * q) % nc));
         }
-        if (r == 4) dft4<INV>(v);
-        else if (r == 2) dft2<INV>(v);
-        else if (r == 3) dft3<INV>(v);
-        else dftr<INV>(v, r, tw, nc);
+        if (R == 4) dft4<INV>(v);
+        else if (R == 2) dft2<INV>(v);
+        else if (R == 3) dft3<INV>(v);
+        else dftr<INV, R>(v, tw, nc);
         if (!INV) {  // DIF: butterfly first, then twiddle
-            for (int q = 1; q < r; ++q) v[q] = cmul(v[q], ldtw(tw, (tstep * k * q) % nc));
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, (tstep * k * q) % nc));
         }
-        for (int q = 0; q < r; ++q) buf[(i0 + q * m) * TP + t] = v[q];
+#pragma unroll
+        for (int q = 0; q < R; ++q) buf[(i0 + q * m) * TP + t] = v[q];
+    }
+}
+
+// rare large odd radices (7, 11, 13): runtime-radix fallback with the butterfly in local memory
+template <bool INV>
+__device__ __noinline__ void fft_pass_generic(double2* buf, int nc, int TP, int Tc, int r, int L, const double* tw)
+{
+    const int m = L / r;
+    const int nbf = nc / r;
+    const int tstep = nc / L;
+    const int step = nc / r;
+    for (int w = threadIdx.x; w < nbf * Tc; w += blockDim.x) {
+        const int t = w % Tc;
+        const int bf = w / Tc;
+        const int b = bf / m, k = bf - b * m;
+        double2 v[16], y[16];
+        const int i0 = b * L + k;
+        for (int q = 0; q < r; ++q) {
+            v[q] = buf[(i0 + q * m) * TP + t];
+            if (INV && q > 0) v[q] = cmulc(v[q], ldtw(tw, (tstep * k * q) % nc));
+        }
+        for (int qp = 0; qp < r; ++qp) {
+            double2 acc = v[0];
+            for (int q = 1; q < r; ++q) {
+                double2 ww = ldtw(tw, step * ((q * qp) % r));
+                acc = cadd(acc, INV ? cmulc(v[q], ww) : cmul(v[q], ww));
+            }
+            y[qp] = acc;
+        }
+        for (int q = 0; q < r; ++q) {
+            double2 o = y[q];
+            if (!INV && q > 0) o = cmul(o, ldtw(tw, (tstep * k * q) % nc));
+            buf[(i0 + q * m) * TP + t] = o;
+        }
+    }
+}
+
+template <bool INV>
+__device__ void fft_pass(double2* buf, int nc, int TP, int Tc, int r, int L, const double* tw)
+{
+    switch (r) {
+        case 4: fft_pass_r<INV, 4>(buf, nc, TP, Tc, L, tw); break;
+        case 2: fft_pass_r<INV, 2>(buf, nc, TP, Tc, L, tw); break;
+        case 3: fft_pass_r<INV, 3>(buf, nc, TP, Tc, L, tw); break;
+        case 5: fft_pass_r<INV, 5>(buf, nc, TP, Tc, L, tw); break;
+        default: fft_pass_generic<INV>(buf, nc, TP, Tc, r, L, tw); break;
     }
 }
 
@@ -168,7 +222,7 @@ __device__ __forceinline__ TileGeom tile_geom(const FftArgs& a, int len, int cpl
                  t = (contiguous) ? _e / (len) : _e % (g).Tc; _once; _once = 0)
 
 template <int KIND>
-__global__ void __launch_bounds__(FFT_THREADS) k_fft(FftArgs a)
+__global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
 {
     DB_SMEM(double, smem);
     double2* buf = reinterpret_cast<double2*>(smem);
@@ -326,11 +380,12 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft(FftArgs a)
                     }
                 }
                 if (a.nd_b > 0) {
+                    // back-substitution; diags_b row 0 holds the RECIPROCAL diagonal (host precomputes it)
                     for (int i = M - 1; i >= 0; --i) {
                         double acc = cof[i * TP + t];
                         for (int d = 1; d < a.nd_b && i + d < M; ++d)
                             acc = fma(-a.diags_b[(int64_t)d * M + i], cof[(i + d) * TP + t], acc);
-                        cof[i * TP + t] = acc / a.diags_b[i];
+                        cof[i * TP + t] = acc * a.diags_b[i];
                     }
                 }
             }

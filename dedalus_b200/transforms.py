@@ -163,6 +163,7 @@ class FastChebyshevTransform:
                 Cm = jacobi.conversion_matrix(M, self.a0, self.b0, self.a + d, self.b + d)
                 nd = int(round((self.a + d - self.a0) + (self.b + d - self.b0))) + 1
                 arr = banded_upper_diags(Cm, M, nd)
+                arr[0] = 1.0 / arr[0]            # kernel contract: row 0 of the solve matrix holds 1/diagonal
             else:  # 'pre': derivative chain (a,b) -> (a+d,b+d)
                 P = None
                 for j in range(d):

@@ -62,7 +62,8 @@ int db_cfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_
  * apply_sparse / solve_upper_sparse calls inside it (tools/linalg.pyx:20-82, 189-258).
  * Banded matrices are upper triangular, stored by diagonals: diag[d][i] = A[i][i+d], d < ndiag, row length n_coeff.
  *   forward : coefficients = conv_apply( truncate( scale( DCT-II(g) ) ) )        (conv_ndiag = 0: none)
- *   backward: g = DCT-III( scale( solve_upper(conv_solve, apply(pre_apply, c)) ) ) (either may be absent) */
+ *   backward: g = DCT-III( scale( solve_upper(conv_solve, apply(pre_apply, c)) ) ) (either may be absent);
+ *             row 0 of solve_diags holds the RECIPROCAL of the diagonal. */
 int db_cheb_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner,
                     const double* conv_diags, int32_t conv_ndiag, void* stream);
 int db_cheb_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,

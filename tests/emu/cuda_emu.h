@@ -19,6 +19,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __noinline__
 #define __align__(x)
 
 struct uint3e { unsigned x, y, z; };
