@@ -185,44 +185,48 @@ extern "C" int db_pencil_factor(double* lu, int32_t n, int32_t S, int32_t ld, co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// triangular solves streaming the factors; RHS linear combination fused into the load
+// triangular solves streaming the factors (single batch; the fused multi-batch version is below)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int ld,
-                               const int32_t* __restrict__ fwd_ptr, const int32_t* __restrict__ fwd_col,
-                               const int32_t* __restrict__ bwd_ptr, const int32_t* __restrict__ bwd_col,
-                               db_lincomb rhs, double* __restrict__ x)
+                               const int32_t* __restrict__ prog, int n_fwd, int n_entries,
+                               db_lincomb rhs, double* __restrict__ xg)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const double* __restrict__ f = lu + s;      // stream pointer (entry-major)
-    int64_t e = 0;
-    for (int i = 0; i < n; ++i) {
-        double acc = 0.0;
-        for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][(int64_t)i * ld + s], acc);
-        const int t1 = fwd_ptr[i + 1];
-        for (int t = fwd_ptr[i]; t < t1; ++t, ++e)
-            acc = fma(-f[e * ld], x[(int64_t)fwd_col[t] * ld + s], acc);
-        x[(int64_t)i * ld + s] = acc;
+    const double* __restrict__ f = lu + s;
+    double* __restrict__ x = xg + s;
+    int row = 0;
+    double acc = 0.0;
+    for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][s], acc);
+    for (int e = 0; e < n_fwd; ++e) {
+        const int c = prog[e];
+        if (!(c & DB_I_NOP)) acc = fma(-f[(int64_t)e * ld], x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
+        if (c & DB_I_ENDROW) {
+            x[(int64_t)row * ld] = acc;
+            ++row;
+            acc = 0.0;
+            if (row < n) for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][(int64_t)row * ld + s], acc);
+        }
     }
-    for (int p = 0; p < n; ++p) {
-        const int i = n - 1 - p;
-        const double inv = f[e * ld]; ++e;
-        double acc = x[(int64_t)i * ld + s];
-        const int t1 = bwd_ptr[p + 1];
-        for (int t = bwd_ptr[p]; t < t1; ++t, ++e)
-            acc = fma(-f[e * ld], x[(int64_t)bwd_col[t] * ld + s], acc);
-        x[(int64_t)i * ld + s] = acc * inv;
+    row = n - 1;
+    double inv = 0.0;
+    for (int e = n_fwd; e < n_entries; ++e) {
+        const int c = prog[e];
+        const double v = f[(int64_t)e * ld];
+        if (c & DB_I_DIAG) { inv = v; acc = x[(int64_t)row * ld]; }
+        else if (!(c & DB_I_NOP)) acc = fma(-v, x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
+        if (c & DB_I_ENDROW) { x[(int64_t)row * ld] = acc * inv; --row; }
     }
 }
 
 extern "C" int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
-                               const int32_t* fwd_ptr, const int32_t* fwd_col, const int32_t* bwd_ptr, const int32_t* bwd_col,
+                               const int32_t* prog, int32_t n_fwd, int32_t n_entries,
                                const db_lincomb* rhs, double* x, void* stream)
 {
     if (S <= 0 || n <= 0) return 0;
     if (rhs->nvec < 0 || rhs->nvec > 16) { db_set_error("pencil_solve: nvec out of range"); return 1; }
     dim3 grid((S + 63) / 64), block(64);
-    DB_LAUNCH(k_pencil_solve, grid, block, 0, stream, lu, n, S, ld, fwd_ptr, fwd_col, bwd_ptr, bwd_col, *rhs, x);
+    DB_LAUNCH(k_pencil_solve, grid, block, 0, stream, lu, n, S, ld, prog, n_fwd, n_entries, *rhs, x);
     return db_check_launch("pencil_solve");
 }
 
@@ -243,4 +247,251 @@ extern "C" int db_lincomb_apply(const db_lincomb* terms, double* out, int64_t co
     if (blocks > 148 * 16) blocks = 148 * 16;
     DB_LAUNCH(k_lincomb, dim3((unsigned)blocks), dim3(256), 0, stream, *terms, out, count);
     return db_check_launch("lincomb");
+}
+
+// =========================================================================================================
+// Fused launches over all batches of a solver
+// =========================================================================================================
+__device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nbatch, int blk, int which)
+{
+    // which: 0 solve, 1 matvec, 2 move side 0, 3 move side 1, 4 assemble.  Uniform linear scan (nbatch is small).
+    int lo = 0;
+    for (int i = 1; i < nbatch; ++i) {
+        int start = (which == 0) ? b[i].blk_solve : (which == 1) ? b[i].blk_matvec : (which == 2) ? b[i].blk_move[0]
+                  : (which == 3) ? b[i].blk_move[1] : b[i].blk_assemble;
+        if (blk >= start) lo = i;
+    }
+    return lo;
+}
+
+#define SOLVE_THREADS 64
+#define SOLVE_PF 16
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs)
+{
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
+    if (s >= B.S) return;
+    const int ld = B.ld, n = B.n;
+    const double* __restrict__ f = B.lu[lu_slot] + s;
+    const int32_t* __restrict__ prog = B.prog;
+    double* __restrict__ x = B.vec[x_slot] + s;
+    const double* rv[16];
+    for (int j = 0; j < rhs.nvec; ++j) rv[j] = B.vec[rhs.slot[j]] + s;
+    // ---- forward substitution: flat stream, SOLVE_PF-deep register prefetch of the factor values
+    int row = 0;
+    double acc = 0.0;
+    for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rv[j][0], acc);
+    const int nf = B.n_fwd;
+    for (int e0 = 0; e0 < nf; e0 += SOLVE_PF) {
+        double v[SOLVE_PF]; int ins[SOLVE_PF];
+#pragma unroll
+        for (int j = 0; j < SOLVE_PF; ++j) {
+            const int e = e0 + j;
+            if (e < nf) { v[j] = f[(int64_t)e * ld]; ins[j] = prog[e]; } else { v[j] = 0.0; ins[j] = DB_I_NOP; }
+        }
+#pragma unroll
+        for (int j = 0; j < SOLVE_PF; ++j) {
+            const int c = ins[j];
+            if (!(c & DB_I_NOP)) acc = fma(-v[j], x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
+            if (c & DB_I_ENDROW) {
+                x[(int64_t)row * ld] = acc;
+                ++row;
+                acc = 0.0;
+                if (row < n) for (int q = 0; q < rhs.nvec; ++q) acc = fma(rhs.coef[q], rv[q][(int64_t)row * ld], acc);
+            }
+        }
+    }
+    // ---- backward substitution
+    row = n - 1;
+    double inv = 0.0;
+    const int nE = B.n_entries;
+    for (int e0 = nf; e0 < nE; e0 += SOLVE_PF) {
+        double v[SOLVE_PF]; int ins[SOLVE_PF];
+#pragma unroll
+        for (int j = 0; j < SOLVE_PF; ++j) {
+            const int e = e0 + j;
+            if (e < nE) { v[j] = f[(int64_t)e * ld]; ins[j] = prog[e]; } else { v[j] = 0.0; ins[j] = DB_I_NOP; }
+        }
+#pragma unroll
+        for (int j = 0; j < SOLVE_PF; ++j) {
+            const int c = ins[j];
+            if (c & DB_I_DIAG) { inv = v[j]; acc = x[(int64_t)row * ld]; }
+            else if (!(c & DB_I_NOP)) acc = fma(-v[j], x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
+            if (c & DB_I_ENDROW) { x[(int64_t)row * ld] = acc * inv; --row; }
+        }
+    }
+}
+
+extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
+                                const db_slotcomb* rhs, void* stream)
+{
+    if (nbatch <= 0 || total_blocks <= 0) return 0;
+    if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
+    DB_LAUNCH(k_batches_solve, dim3(total_blocks), dim3(SOLVE_THREADS), 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    return db_check_launch("batches_solve");
+}
+
+__global__ void __launch_bounds__(PB_THREADS)
+k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, int ym_slot, int yl_slot)
+{
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 1);
+    const db_batch& B = batches[bi];
+    const int local = blockIdx.x - B.blk_matvec;
+    const int sblocks = (B.S + PB_THREADS - 1) / PB_THREADS;
+    const int s = (local % sblocks) * PB_THREADS + threadIdx.x;
+    if (s >= B.S) return;
+    const int r0 = (local / sblocks) * MV_ROWS_PER_BLOCK;
+    const int n = B.n, ld = B.ld;
+    const int r1 = (r0 + MV_ROWS_PER_BLOCK < n) ? r0 + MV_ROWS_PER_BLOCK : n;
+    const double* __restrict__ x = B.vec[x_slot] + s;
+    const double* __restrict__ mono = B.mono + s;
+    if (ym_slot >= 0) {
+        double* __restrict__ y = B.vec[ym_slot] + s;
+        for (int i = r0; i < r1; ++i) {
+            double acc = 0.0;
+            for (int t = B.m_ptr[i]; t < B.m_ptr[i + 1]; ++t)
+                acc = fma(B.m_val[t] * mono[(int64_t)B.m_mono[t] * ld], x[(int64_t)B.m_col[t] * ld], acc);
+            y[(int64_t)i * ld] = acc;
+        }
+    }
+    if (yl_slot >= 0) {
+        double* __restrict__ y = B.vec[yl_slot] + s;
+        for (int i = r0; i < r1; ++i) {
+            double acc = 0.0;
+            for (int t = B.l_ptr[i]; t < B.l_ptr[i + 1]; ++t)
+                acc = fma(B.l_val[t] * mono[(int64_t)B.l_mono[t] * ld], x[(int64_t)B.l_col[t] * ld], acc);
+            y[(int64_t)i * ld] = acc;
+        }
+    }
+}
+
+extern "C" int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t x_slot, int32_t ym_slot, int32_t yl_slot, void* stream)
+{
+    if (nbatch <= 0 || total_blocks <= 0) return 0;
+    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(PB_THREADS), 0, stream, batches, nbatch, x_slot, ym_slot, yl_slot);
+    return db_check_launch("batches_matvec");
+}
+
+template <bool GATHER>
+__global__ void k_batches_move(const db_batch* __restrict__ batches, int nbatch, int side, int slot, double* __restrict__ arena)
+{
+    DB_SMEM(double, tile);
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 2 + side);
+    const db_batch& B = batches[bi];
+    int local = blockIdx.x - B.blk_move[side];
+    const int sblocks = (B.S + 31) / 32;
+    const int mblocks = (B.max_len[side] + 31) / 32;
+    const int q = local / (sblocks * mblocks);
+    local -= q * sblocks * mblocks;
+    const int m0 = (local / sblocks) * 32, s0 = (local % sblocks) * 32;
+    const int32_t* lp = B.line_ptr[side];
+    const int len = lp[q + 1] - lp[q];
+    if (m0 >= len) return;
+    const int S = B.S, ld = B.ld;
+    const int64_t base = B.line_base[side][q];
+    const int64_t* so = B.sys_off[side] + (int64_t)B.line_kind[side][q] * ld;
+    const int32_t* pos = B.line_pos[side] + lp[q];
+    double* vec = B.vec[slot];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (GATHER) {
+        for (int r = ty; r < 32; r += 8) {
+            int s = s0 + r, m = m0 + tx;
+            if (s < S && m < len) tile[r * 33 + tx] = arena[base + so[s] + m];
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            int m = m0 + r, s = s0 + tx;
+            if (s < S && m < len) vec[(int64_t)pos[m] * ld + s] = tile[tx * 33 + r];
+        }
+    } else {
+        for (int r = ty; r < 32; r += 8) {
+            int m = m0 + r, s = s0 + tx;
+            if (s < S && m < len) tile[tx * 33 + r] = vec[(int64_t)pos[m] * ld + s];
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            int s = s0 + r, m = m0 + tx;
+            if (s < S && m < len) arena[base + so[s] + m] = tile[r * 33 + tx];
+        }
+    }
+}
+
+extern "C" int db_batches_move(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t side, int32_t gather,
+                               int32_t slot, double* arena, void* stream)
+{
+    if (nbatch <= 0 || total_blocks <= 0) return 0;
+    if (side < 0 || side > 1 || slot < 0 || slot >= DB_MAX_VECS) { db_set_error("batches_move: bad arguments"); return 1; }
+    if (gather) DB_LAUNCH(k_batches_move<true>, dim3(total_blocks), dim3(32, 8), 32 * 33 * sizeof(double), stream, batches, nbatch, side, slot, arena);
+    else DB_LAUNCH(k_batches_move<false>, dim3(total_blocks), dim3(32, 8), 32 * 33 * sizeof(double), stream, batches, nbatch, side, slot, arena);
+    return db_check_launch("batches_move");
+}
+
+__global__ void __launch_bounds__(PB_THREADS)
+k_batches_assemble(const db_batch* __restrict__ batches, int nbatch, int lu_slot)
+{
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 4);
+    const db_batch& B = batches[bi];
+    const int local = blockIdx.x - B.blk_assemble;
+    const int sblocks = (B.S + PB_THREADS - 1) / PB_THREADS;
+    const int s = (local % sblocks) * PB_THREADS + threadIdx.x;
+    if (s >= B.S) return;
+    const int e0 = (local / sblocks) * ASM_ENTRIES_PER_BLOCK;
+    const int e1 = (e0 + ASM_ENTRIES_PER_BLOCK < B.n_entries) ? e0 + ASM_ENTRIES_PER_BLOCK : B.n_entries;
+    double* __restrict__ lu = B.lu[lu_slot] + s;
+    const double* __restrict__ mono = B.mono + s;
+    const int ld = B.ld;
+    for (int e = e0; e < e1; ++e) {
+        double v = 0.0;
+        for (int t = B.asm_ptr[e]; t < B.asm_ptr[e + 1]; ++t)
+            v = fma(B.asm_val[t], mono[(int64_t)B.asm_mono[t] * ld], v);
+        lu[(int64_t)e * ld] = v;
+    }
+}
+
+extern "C" int db_batches_assemble(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, void* stream)
+{
+    if (nbatch <= 0 || total_blocks <= 0) return 0;
+    DB_LAUNCH(k_batches_assemble, dim3(total_blocks), dim3(PB_THREADS), 0, stream, batches, nbatch, lu_slot);
+    return db_check_launch("batches_assemble");
+}
+
+// factorisation shares the solve's block map (one thread per system, SOLVE_THREADS per block)
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_batches_factor(const db_batch* __restrict__ batches, int nbatch, int lu_slot)
+{
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
+    if (s >= B.S) return;
+    const int ld = B.ld, n = B.n;
+    double* __restrict__ lu = B.lu[lu_slot] + s;
+    int64_t dp = 0;
+    bool bad = false;
+    for (int k = 0; k < n; ++k) {
+        const int64_t d = (int64_t)B.diag_eid[k] * ld;
+        const double piv = lu[d];
+        if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1e300)) bad = true;
+        const double inv = 1.0 / piv;
+        lu[d] = inv;
+        const int u0 = B.fu_ptr[k], u1 = B.fu_ptr[k + 1];
+        for (int a = B.fl_ptr[k]; a < B.fl_ptr[k + 1]; ++a) {
+            const int64_t le = (int64_t)B.fl_eid[a] * ld;
+            const double l = lu[le] * inv;
+            lu[le] = l;
+            for (int b = u0; b < u1; ++b, ++dp) {
+                const int64_t de = (int64_t)B.fd_eid[dp] * ld;
+                lu[de] = fma(-l, lu[(int64_t)B.fu_eid[b] * ld], lu[de]);
+            }
+        }
+    }
+    if (bad) atomicAdd(B.info, 1);
+}
+
+extern "C" int db_batches_factor(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, void* stream)
+{
+    if (nbatch <= 0 || total_blocks <= 0) return 0;
+    DB_LAUNCH(k_batches_factor, dim3(total_blocks), dim3(SOLVE_THREADS), 0, stream, batches, nbatch, lu_slot);
+    return db_check_launch("batches_factor");
 }

@@ -22,6 +22,26 @@ class LinComb(C.Structure):
     _fields_ = [("nvec", i32), ("vec", vp * 16), ("coef", f64 * 16)]
 
 
+DB_MAX_VECS, DB_MAX_LU = 24, 4
+
+
+class Batch(C.Structure):
+    """include/dedalus_b200.h: db_batch"""
+    _fields_ = [("n", i32), ("S", i32), ("ld", i32), ("n_entries", i32), ("n_fwd", i32), ("n_bwd", i32),
+                ("blk_solve", i32), ("blk_matvec", i32), ("blk_move", i32 * 2), ("blk_assemble", i32),
+                ("nlines", i32 * 2), ("max_len", i32 * 2),
+                ("prog", vp), ("mono", vp), ("vec", vp * DB_MAX_VECS), ("lu", vp * DB_MAX_LU),
+                ("m_ptr", vp), ("m_col", vp), ("m_mono", vp), ("m_val", vp),
+                ("l_ptr", vp), ("l_col", vp), ("l_mono", vp), ("l_val", vp),
+                ("line_base", vp * 2), ("line_kind", vp * 2), ("line_ptr", vp * 2), ("line_pos", vp * 2), ("sys_off", vp * 2),
+                ("diag_eid", vp), ("fl_ptr", vp), ("fl_eid", vp), ("fu_ptr", vp), ("fu_eid", vp), ("fd_eid", vp),
+                ("asm_ptr", vp), ("asm_mono", vp), ("asm_val", vp), ("info", vp)]
+
+
+class SlotComb(C.Structure):
+    _fields_ = [("nvec", i32), ("slot", i32 * 16), ("coef", f64 * 16)]
+
+
 PFFT = C.POINTER(FftPlan)
 PLIN = C.POINTER(LinComb)
 
@@ -42,7 +62,12 @@ SIGNATURES = {
     "db_pencil_matvec": (C.c_int, [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "db_pencil_assemble": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "db_pencil_factor": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "db_pencil_solve": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, PLIN, vp, vp]),
+    "db_pencil_solve": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, PLIN, vp, vp]),
+    "db_batches_move": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
+    "db_batches_matvec": (C.c_int, [vp, i32, i32, i32, i32, i32, vp]),
+    "db_batches_solve": (C.c_int, [vp, i32, i32, i32, i32, C.c_void_p, vp]),
+    "db_batches_assemble": (C.c_int, [vp, i32, i32, i32, vp]),
+    "db_batches_factor": (C.c_int, [vp, i32, i32, i32, vp]),
     "db_lincomb_apply": (C.c_int, [PLIN, vp, i64, vp]),
     "db_transpose_pack": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
     "db_transpose_unpack": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),

@@ -449,30 +449,30 @@ def compile_batch(batch, a0, b0):
     F = batch.symbolic_lu()
     prog = BatchProgram()
     prog.n, prog.S = n, batch.S
-    # ---- entry numbering in solve-stream order
+    # ---- entry numbering in solve-stream order + flat instruction stream (see include/dedalus_b200.h DB_I_*)
+    ENDROW, DIAG, NOP = 0x40000000, 0x20000000, 0x10000000
     eid = -np.ones((n, n), dtype=np.int64)
-    fwd_ptr = np.zeros(n + 1, dtype=np.int32); fwd_col = []
+    instr = []
     e = 0
     for i in range(n):
         js = np.nonzero(F[i, :i])[0]
+        if js.size == 0:
+            instr.append(np.array([NOP | ENDROW], dtype=np.int64)); e += 1      # placeholder entry (value stays 0)
+            continue
         eid[i, js] = e + np.arange(js.size)
-        fwd_col.append(js); e += js.size
-        fwd_ptr[i + 1] = fwd_ptr[i] + js.size
-    nL = e
-    bwd_ptr = np.zeros(n + 1, dtype=np.int32); bwd_col = []; diag_eid = np.zeros(n, dtype=np.int32)
-    nUoff = 0
-    for pos, i in enumerate(range(n - 1, -1, -1)):
+        code = js.astype(np.int64); code[-1] |= ENDROW
+        instr.append(code); e += js.size
+    prog.n_fwd = e
+    diag_eid = np.zeros(n, dtype=np.int32)
+    for i in range(n - 1, -1, -1):
         diag_eid[i] = e; eid[i, i] = e; e += 1
         js = i + 1 + np.nonzero(F[i, i + 1:])[0]
         eid[i, js] = e + np.arange(js.size)
-        bwd_col.append(js); e += js.size
-        nUoff += js.size
-        bwd_ptr[pos + 1] = nUoff
+        code = np.concatenate([[i | DIAG], js]).astype(np.int64); code[-1] |= ENDROW
+        instr.append(code); e += js.size
     prog.nE = e
-    prog.fwd_ptr = fwd_ptr
-    prog.fwd_col = np.concatenate(fwd_col).astype(np.int32) if fwd_col else np.zeros(0, np.int32)
-    prog.bwd_ptr = bwd_ptr
-    prog.bwd_col = np.concatenate(bwd_col).astype(np.int32) if bwd_col else np.zeros(0, np.int32)
+    prog.prog = np.concatenate(instr).astype(np.int32)
+    assert len(prog.prog) == prog.nE
     prog.diag_eid = diag_eid
     # ---- factor program
     fl_ptr = np.zeros(n + 1, dtype=np.int32); fu_ptr = np.zeros(n + 1, dtype=np.int32)
@@ -525,7 +525,7 @@ def assembly_program(batch, prog, a0, b0):
     es, ms, vs = [], [], []
     for name, w in (('M', a0), ('L', b0)):
         r, c, m, v = prog.terms[name]
-        if w == 0 or len(r) == 0:
+        if len(r) == 0:
             continue
         es.append(batch.eid[r, c]); ms.append(m); vs.append(w * v)
     e = np.concatenate(es); m = np.concatenate(ms); v = np.concatenate(vs)

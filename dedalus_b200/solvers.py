@@ -41,99 +41,130 @@ class Timed:
 
 
 class DeviceBatch:
-    """Device copies of one batch's programs and work vectors."""
+    """Device copies of one batch's programs and work vectors (kept alive for the fused descriptors)."""
 
-    def __init__(self, solver, batch):
+    def __init__(self, solver, batch, a0, b0, nslots):
         import torch
-        self.batch = batch
-        self.solver = solver
-        self.prog = None
-        self.lu = {}          # b0/a0 ratio key -> LU tensor
-
-    def upload(self, a0, b0):
-        import torch
-        dev = self.solver.device
-        batch = self.batch
+        self.batch, self.solver = batch, solver
+        dev = solver.device
         prog = compile_batch(batch, a0, b0)
         self.prog = prog
-        n, S = prog.n, prog.S
-        self.n, self.S = n, S
-        self.ld = ld = ((S + 31) // 32) * 32
-        mono = np.zeros((len(prog.monos), ld)); mono[:, :S] = prog.mono_vals
-        self.mono = torch.from_numpy(mono).to(dev)
+        self.n, self.S = prog.n, prog.S
+        self.ld = ld = ((prog.S + 31) // 32) * 32
+        mono = np.zeros((len(prog.monos), ld)); mono[:, :prog.S] = prog.mono_vals
         f = lambda a: _i32(torch, a, dev)
-        self.diag_eid, self.fl_ptr, self.fl_eid = f(prog.diag_eid), f(prog.fl_ptr), f(prog.fl_eid)
-        self.fu_ptr, self.fu_eid, self.fd_eid = f(prog.fu_ptr), f(prog.fu_eid), f(prog.fd_eid)
-        self.fwd_ptr, self.fwd_col, self.bwd_ptr, self.bwd_col = f(prog.fwd_ptr), f(prog.fwd_col), f(prog.bwd_ptr), f(prog.bwd_col)
-        self.mv = {}
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        self.t = dict(mono=d(mono), prog=f(prog.prog), diag_eid=f(prog.diag_eid), fl_ptr=f(prog.fl_ptr), fl_eid=f(prog.fl_eid),
+                      fu_ptr=f(prog.fu_ptr), fu_eid=f(prog.fu_eid), fd_eid=f(prog.fd_eid))
         for name in ('M', 'L'):
             ptr, col, mono_i, val = prog.mv[name]
-            self.mv[name] = (f(ptr), f(col), f(mono_i), torch.from_numpy(np.ascontiguousarray(val)).to(dev))
-        self.maps = {}
-        for side, arena in (('cols', self.solver.var_arena), ('rows', self.solver.eq_arena)):
+            k = name.lower()
+            self.t[k + '_ptr'], self.t[k + '_col'], self.t[k + '_mono'], self.t[k + '_val'] = f(ptr), f(col), f(mono_i), d(val)
+        self.maps = []
+        for side, arena in (('cols', solver.var_arena), ('rows', solver.eq_arena)):
             m = line_maps(batch, arena, side)
-            so = np.zeros((m.sys_off.shape[0], ld), dtype=np.int64); so[:, :S] = m.sys_off
-            self.maps[side] = dict(nlines=len(m.line_base), max_len=int(m.line_len.max()) if len(m.line_len) else 0,
-                                   base=torch.from_numpy(m.line_base).to(dev), kind=f(m.line_kind), ptr=f(m.line_ptr),
-                                   pos=f(m.line_pos), sys_off=torch.from_numpy(so).to(dev))
+            so = np.zeros((m.sys_off.shape[0], ld), dtype=np.int64); so[:, :prog.S] = m.sys_off
+            self.maps.append(dict(nlines=len(m.line_base), max_len=int(m.line_len.max()) if len(m.line_len) else 0,
+                                  base=torch.from_numpy(m.line_base).to(dev), kind=f(m.line_kind), ptr=f(m.line_ptr),
+                                  pos=f(m.line_pos), sys_off=torch.from_numpy(so).to(dev)))
+        ptr, mono_i, val = assembly_program(batch, prog, a0, b0)
+        self.t['asm_ptr'], self.t['asm_mono'], self.t['asm_val'] = f(ptr), f(mono_i), d(val)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.vecs = [torch.zeros((self.n, ld), dtype=torch.float64, device=dev) for _ in range(nslots)]
+        self.lu = {}
 
-    def vec(self):
+    def lu_tensor(self, slot):
         import torch
-        return torch.zeros((self.n, self.ld), dtype=torch.float64, device=self.solver.device)
+        if slot not in self.lu:
+            self.lu[slot] = torch.empty((self.prog.nE, self.ld), dtype=torch.float64, device=self.solver.device)
+        return self.lu[slot]
 
-    # ---- kernels -----------------------------------------------------------------------------------
-    def gather(self, side, arena_t, vec):
-        m = self.maps[side]
-        with Timed(self.solver.prof, "pencil_gather", 16 * self.n * self.S):
-          self.solver.lib.call("db_pencil_gather", arena_t.data_ptr(), vec.data_ptr(), self.S, self.ld, m['nlines'], m['max_len'],
-                             m['base'].data_ptr(), m['kind'].data_ptr(), m['ptr'].data_ptr(), m['pos'].data_ptr(),
-                             m['sys_off'].data_ptr(), self.ld, self.solver.stream())
-
-    def scatter(self, vec, arena_t):
-        m = self.maps['cols']
-        with Timed(self.solver.prof, "pencil_scatter", 16 * self.n * self.S):
-          self.solver.lib.call("db_pencil_scatter", vec.data_ptr(), arena_t.data_ptr(), self.S, self.ld, m['nlines'], m['max_len'],
-                             m['base'].data_ptr(), m['kind'].data_ptr(), m['ptr'].data_ptr(), m['pos'].data_ptr(),
-                             m['sys_off'].data_ptr(), self.ld, self.solver.stream())
-
-    def matvec(self, x, y_m=None, y_l=None):
-        M, L = self.mv['M'], self.mv['L']
-        p = lambda t: t.data_ptr() if t is not None else None
-        nout = (y_m is not None) + (y_l is not None)
-        with Timed(self.solver.prof, "pencil_matvec", 8 * self.n * self.S * (1 + nout)):
-          self.solver.lib.call("db_pencil_matvec", self.n, self.S, self.ld, self.mono.data_ptr(), x.data_ptr(),
-                             M[0].data_ptr(), M[1].data_ptr(), M[2].data_ptr(), M[3].data_ptr(), p(y_m),
-                             L[0].data_ptr(), L[1].data_ptr(), L[2].data_ptr(), L[3].data_ptr(), p(y_l), self.solver.stream())
-
-    def factor(self, key, a0, b0):
+    def set_lhs(self, a0, b0):
         import torch
-        dev = self.solver.device
         ptr, mono_i, val = assembly_program(self.batch, self.prog, a0, b0)
-        lu = self.lu.get(key)
-        if lu is None:
-            lu = torch.empty((self.prog.nE, self.ld), dtype=torch.float64, device=dev)
-            self.lu[key] = lu
-        t_ptr, t_mono, t_val = _i32(torch, ptr, dev), _i32(torch, mono_i, dev), torch.from_numpy(val).to(dev)
-        lib = self.solver.lib
-        lib.call("db_pencil_assemble", lu.data_ptr(), self.prog.nE, self.S, self.ld, self.mono.data_ptr(),
-                 t_ptr.data_ptr(), t_mono.data_ptr(), t_val.data_ptr(), self.solver.stream())
-        self.info.zero_()
-        lib.call("db_pencil_factor", lu.data_ptr(), self.n, self.S, self.ld, self.diag_eid.data_ptr(), self.fl_ptr.data_ptr(),
-                 self.fl_eid.data_ptr(), self.fu_ptr.data_ptr(), self.fu_eid.data_ptr(), self.fd_eid.data_ptr(),
-                 self.info.data_ptr(), self.solver.stream())
-        return lu
+        self.t['asm_val'].copy_(torch.from_numpy(np.ascontiguousarray(val)))
 
-    def solve(self, lu, terms, x):
-        lc = LinComb()
-        lc.nvec = len(terms)
-        for j, (v, c) in enumerate(terms):
-            lc.vec[j] = v.data_ptr(); lc.coef[j] = c
+
+class BatchSet:
+    """All batches of a solver behind ONE device descriptor array (include/dedalus_b200.h: db_batch)."""
+
+    def __init__(self, solver, a0, b0, nslots, nlu):
+        import torch
+        from .lib import Batch as CBatch, DB_MAX_VECS, DB_MAX_LU
+        if nslots > DB_MAX_VECS or nlu > DB_MAX_LU:
+            raise NotImplementedError("too many work vectors / factor sets for the fused batch descriptor")
+        self.solver = solver
+        self.items = [DeviceBatch(solver, b, a0, b0, nslots) for b in solver.batches]
+        self.nb = len(self.items)
+        arr = (CBatch * max(self.nb, 1))()
+        blk = dict(solve=0, matvec=0, move0=0, move1=0, asm=0)
+        for i, db in enumerate(self.items):
+            c = arr[i]
+            c.n, c.S, c.ld, c.n_entries = db.n, db.S, db.ld, db.prog.nE
+            c.n_fwd, c.n_bwd = db.prog.n_fwd, db.prog.nE - db.prog.n_fwd
+            c.blk_solve = blk['solve']; blk['solve'] += (db.S + 63) // 64
+            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 127) // 128) * ((db.n + 15) // 16)
+            c.blk_assemble = blk['asm']; blk['asm'] += ((db.S + 127) // 128) * ((db.prog.nE + 63) // 64)
+            for side in (0, 1):
+                m = db.maps[side]
+                c.nlines[side], c.max_len[side] = m['nlines'], m['max_len']
+                c.blk_move[side] = blk[f'move{side}']
+                blk[f'move{side}'] += m['nlines'] * ((db.S + 31) // 32) * ((m['max_len'] + 31) // 32)
+                c.line_base[side], c.line_kind[side] = m['base'].data_ptr(), m['kind'].data_ptr()
+                c.line_ptr[side], c.line_pos[side], c.sys_off[side] = m['ptr'].data_ptr(), m['pos'].data_ptr(), m['sys_off'].data_ptr()
+            t = db.t
+            c.prog, c.mono = t['prog'].data_ptr(), t['mono'].data_ptr()
+            for j, v in enumerate(db.vecs):
+                c.vec[j] = v.data_ptr()
+            for j in range(nlu):
+                c.lu[j] = db.lu_tensor(j).data_ptr()
+            c.m_ptr, c.m_col, c.m_mono, c.m_val = (t[k].data_ptr() for k in ('m_ptr', 'm_col', 'm_mono', 'm_val'))
+            c.l_ptr, c.l_col, c.l_mono, c.l_val = (t[k].data_ptr() for k in ('l_ptr', 'l_col', 'l_mono', 'l_val'))
+            c.diag_eid, c.fl_ptr, c.fl_eid = t['diag_eid'].data_ptr(), t['fl_ptr'].data_ptr(), t['fl_eid'].data_ptr()
+            c.fu_ptr, c.fu_eid, c.fd_eid = t['fu_ptr'].data_ptr(), t['fu_eid'].data_ptr(), t['fd_eid'].data_ptr()
+            c.asm_ptr, c.asm_mono, c.asm_val = t['asm_ptr'].data_ptr(), t['asm_mono'].data_ptr(), t['asm_val'].data_ptr()
+            c.info = db.info.data_ptr()
+        self.blocks = blk
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.desc = torch.from_numpy(raw).to(solver.device)
+        self.host_desc = arr
+        # byte counts for the roofline accounting
+        self.sum_nS = sum(db.n * db.S for db in self.items)
+        self.sum_ES = sum(db.prog.nE * db.S for db in self.items)
+
+    def _call(self, name, *args):
+        self.solver.lib.call(name, self.desc.data_ptr(), self.nb, *args, self.solver.stream())
+
+    def move(self, side, gather, slot, arena_t):
+        with Timed(self.solver.prof, "pencil_gather" if gather else "pencil_scatter", 16 * self.sum_nS):
+            self._call("db_batches_move", self.blocks[f'move{side}'], side, 1 if gather else 0, slot, arena_t.data_ptr())
+
+    def matvec(self, x_slot, ym_slot=-1, yl_slot=-1):
+        nout = (ym_slot >= 0) + (yl_slot >= 0)
+        with Timed(self.solver.prof, "pencil_matvec", 8 * self.sum_nS * (1 + nout)):
+            self._call("db_batches_matvec", self.blocks['matvec'], x_slot, ym_slot, yl_slot)
+
+    def solve(self, lu_slot, x_slot, terms):
+        from .lib import SlotComb
+        sc = SlotComb()
+        sc.nvec = len(terms)
+        for j, (slot, coef) in enumerate(terms):
+            sc.slot[j] = slot; sc.coef[j] = coef
         # algorithmic bytes: every stored LU entry once + each RHS vector once + the solution written once
-        nbytes = 8 * self.S * (self.prog.nE + self.n * (len(terms) + 1))
-        with Timed(self.solver.prof, "pencil_solve", nbytes):
-          self.solver.lib.call("db_pencil_solve", lu.data_ptr(), self.n, self.S, self.ld, self.fwd_ptr.data_ptr(), self.fwd_col.data_ptr(),
-                             self.bwd_ptr.data_ptr(), self.bwd_col.data_ptr(), C.byref(lc), x.data_ptr(), self.solver.stream())
+        with Timed(self.solver.prof, "pencil_solve", 8 * (self.sum_ES + self.sum_nS * (len(terms) + 1))):
+            self._call("db_batches_solve", self.blocks['solve'], lu_slot, x_slot, C.byref(sc))
+
+    def factor(self, lu_slot, a0, b0):
+        for db in self.items:
+            db.set_lhs(a0, b0)
+            db.info.zero_()
+        self._call("db_batches_assemble", self.blocks['asm'], lu_slot)
+        self._call("db_batches_factor", self.blocks['solve'], lu_slot)
+
+    def check_info(self):
+        bad = sum(int(db.info.item()) for db in self.items)
+        if bad:
+            raise DedalusB200Error(f"{bad} pencil systems hit a zero / non-finite pivot during factorisation.")
 
 
 class InitialValueSolver:
@@ -199,23 +230,29 @@ class InitialValueSolver:
         from .evaluator import RHSPlan
         self.rhs_plan = RHSPlan(self)
         self.rhs_plan.set_static(self.eq_t)
-        self.dbatches = [DeviceBatch(self, b) for b in self.batches]
+        self.bset = None
         self._device_ready = True
 
     def _prepare_batches(self, a0, b0):
+        if getattr(self, 'bset', None) is not None:
+            return
         cls = self.timestepper_class
-        for db in self.dbatches:
-            if db.prog is None:
-                db.upload(a0, b0)
-                db.X = db.vec()
-                if cls.kind == "rk":
-                    db.MX0 = db.vec()
-                    db.LX = [db.vec() for _ in range(cls.stages)]
-                    db.F = [db.vec() for _ in range(cls.stages)]
-                else:
-                    db.MX = deque(db.vec() for _ in range(cls.amax))
-                    db.LX = deque(db.vec() for _ in range(cls.bmax))
-                    db.F = deque(db.vec() for _ in range(cls.cmax))
+        if cls.kind == "rk":
+            # slots: 0 X, 1 MX0, 2.. LX[i], 2+stages.. F[i]
+            s = cls.stages
+            self.slot_X, self.slot_MX0 = 0, 1
+            self.slot_LX = [2 + i for i in range(s)]
+            self.slot_F = [2 + s + i for i in range(s)]
+            nslots = 2 + 2 * s
+            nlu = len({float(cls.H[i, i]) for i in range(1, s + 1)})
+        else:
+            self.slot_X = 0
+            self.slot_MX = deque(1 + j for j in range(cls.amax))
+            self.slot_LX = deque(1 + cls.amax + j for j in range(cls.bmax))
+            self.slot_F = deque(1 + cls.amax + cls.bmax + j for j in range(cls.cmax))
+            nslots = 1 + cls.amax + cls.bmax + cls.cmax
+            nlu = 1
+        self.bset = BatchSet(self, a0, b0, nslots, nlu)
 
     def _sync_state_to_device(self):
         """Make the state arena hold the current coefficient data of every variable (uploads host edits)."""
@@ -234,9 +271,7 @@ class InitialValueSolver:
             v.set_device_data(view, 'c', scales=v.dealias)
 
     def _check_factor_info(self):
-        bad = sum(int(db.info.item()) for db in self.dbatches)
-        if bad:
-            raise DedalusB200Error(f"{bad} pencil systems hit a zero / non-finite pivot during factorisation.")
+        self.bset.check_info()
 
     # ------------------------------------------------------------------------------------------------
     @property
@@ -281,36 +316,33 @@ class InitialValueSolver:
         self._prepare_batches(1.0, k * H[1, 1])
         self._sync_state_to_device()
         sim_time_0 = self.sim_time
+        bs = self.bset
         if update:
             # one factorisation per distinct H_ii (RK222 and RK443 share a single one across stages)
-            self._stage_keys = []
+            self._stage_lu = []
             done = {}
             for i in range(1, cls.stages + 1):
                 hii = float(H[i, i])
                 if hii not in done:
-                    done[hii] = True
-                    for db in self.dbatches:
-                        db.factor(hii, 1.0, k * hii)
-                self._stage_keys.append(hii)
+                    done[hii] = len(done)
+                    bs.factor(done[hii], 1.0, k * hii)
+                self._stage_lu.append(done[hii])
             self._check_factor_info()
-        for db in self.dbatches:
-            db.gather('cols', self.state_t, db.X)
-            db.matvec(db.X, y_m=db.MX0, y_l=db.LX[0])
+        bs.move(0, True, self.slot_X, self.state_t)
+        bs.matvec(self.slot_X, self.slot_MX0, self.slot_LX[0])
         for i in range(1, cls.stages + 1):
             if i > 1:
-                for db in self.dbatches:
-                    db.matvec(db.X, y_l=db.LX[i - 1])
+                bs.matvec(self.slot_X, -1, self.slot_LX[i - 1])
             self.rhs_plan.evaluate(self.eq_t)
-            for db in self.dbatches:
-                db.gather('rows', self.eq_t, db.F[i - 1])
-                terms = [(db.MX0, 1.0)]
-                for j in range(i):
-                    if A[i, j] != 0:
-                        terms.append((db.F[j], k * float(A[i, j])))
-                    if H[i, j] != 0:
-                        terms.append((db.LX[j], -k * float(H[i, j])))
-                db.solve(db.lu[self._stage_keys[i - 1]], terms, db.X)
-                db.scatter(db.X, self.state_t)
+            bs.move(1, True, self.slot_F[i - 1], self.eq_t)
+            terms = [(self.slot_MX0, 1.0)]
+            for j in range(i):
+                if A[i, j] != 0:
+                    terms.append((self.slot_F[j], k * float(A[i, j])))
+                if H[i, j] != 0:
+                    terms.append((self.slot_LX[j], -k * float(H[i, j])))
+            bs.solve(self._stage_lu[i - 1], self.slot_X, terms)
+            bs.move(0, False, self.slot_X, self.state_t)
             self._mark_state_on_device()
             self.sim_time = sim_time_0 + k * c[i]
 
@@ -326,29 +358,27 @@ class InitialValueSolver:
         key = (float(a[0]), float(b[0]))
         update = (key != self._lhs_key)
         self._lhs_key = key
+        bs = self.bset
         if update:
-            for db in self.dbatches:
-                db.lu_cur = db.factor('ms', a[0], b[0])
+            bs.factor(0, float(a[0]), float(b[0]))
             self._check_factor_info()
-        for db in self.dbatches:
-            db.MX.rotate(); db.LX.rotate(); db.F.rotate()
-            db.gather('cols', self.state_t, db.X)
-            db.matvec(db.X, y_m=db.MX[0], y_l=db.LX[0])
+        self.slot_MX.rotate(); self.slot_LX.rotate(); self.slot_F.rotate()
+        bs.move(0, True, self.slot_X, self.state_t)
+        bs.matvec(self.slot_X, self.slot_MX[0], self.slot_LX[0])
         self.rhs_plan.evaluate(self.eq_t)
-        for db in self.dbatches:
-            db.gather('rows', self.eq_t, db.F[0])
-            terms = []
-            for j in range(1, len(c)):
-                if c[j] != 0:
-                    terms.append((db.F[j - 1], float(c[j])))
-            for j in range(1, len(a)):
-                if a[j] != 0:
-                    terms.append((db.MX[j - 1], -float(a[j])))
-            for j in range(1, len(b)):
-                if b[j] != 0:
-                    terms.append((db.LX[j - 1], -float(b[j])))
-            db.solve(db.lu_cur, terms, db.X)
-            db.scatter(db.X, self.state_t)
+        bs.move(1, True, self.slot_F[0], self.eq_t)
+        terms = []
+        for j in range(1, len(c)):
+            if c[j] != 0:
+                terms.append((self.slot_F[j - 1], float(c[j])))
+        for j in range(1, len(a)):
+            if a[j] != 0:
+                terms.append((self.slot_MX[j - 1], -float(a[j])))
+        for j in range(1, len(b)):
+            if b[j] != 0:
+                terms.append((self.slot_LX[j - 1], -float(b[j])))
+        bs.solve(0, self.slot_X, terms)
+        bs.move(0, False, self.slot_X, self.state_t)
         self._mark_state_on_device()
         self.sim_time += dt
 

@@ -124,8 +124,60 @@ typedef struct {
     double coef[16];
 } db_lincomb;
 int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
-                    const int32_t* fwd_ptr, const int32_t* fwd_col, const int32_t* bwd_ptr, const int32_t* bwd_col,
+                    const int32_t* prog, int32_t n_fwd, int32_t n_entries,
                     const db_lincomb* rhs, double* x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused launches over ALL batches of a solver ("batch set").  The per-stage pencil work of one IMEX stage is then
+ * 4 launches (mat-vec, gather F, solve, scatter) however many classes / parity components the problem has, and small
+ * batches (kx = 0 or ky = 0 pencils) run concurrently with the large ones instead of serialising on the stream.
+ * `batches` is a DEVICE array of db_batch built once by the host; per-call arguments are slot indices.
+ * The solve program is a flat instruction stream aligned with the LU value stream:
+ *   prog[e] = column | DB_I_ENDROW (row finished after this entry) | DB_I_DIAG (entry is the reciprocal pivot)
+ *                    | DB_I_NOP (placeholder of an empty row: value ignored)
+ * ------------------------------------------------------------------------------------------------------- */
+#define DB_MAX_VECS 24
+#define DB_MAX_LU 4
+#define DB_I_ENDROW 0x40000000
+#define DB_I_DIAG   0x20000000
+#define DB_I_NOP    0x10000000
+#define DB_I_COLMASK 0x0FFFFFFF
+typedef struct {
+    int32_t n, S, ld, n_entries;
+    int32_t n_fwd, n_bwd;
+    int32_t blk_solve, blk_matvec, blk_move[2], blk_assemble;   /* first block of this batch in each fused launch */
+    int32_t nlines[2], max_len[2];
+    const int32_t* prog;
+    const double* mono;
+    double* vec[DB_MAX_VECS];
+    double* lu[DB_MAX_LU];
+    const int32_t *m_ptr, *m_col, *m_mono; const double* m_val;
+    const int32_t *l_ptr, *l_col, *l_mono; const double* l_val;
+    const int64_t* line_base[2]; const int32_t* line_kind[2]; const int32_t* line_ptr[2]; const int32_t* line_pos[2];
+    const int64_t* sys_off[2];
+    /* factorisation programs */
+    const int32_t *diag_eid, *fl_ptr, *fl_eid, *fu_ptr, *fu_eid, *fd_eid;
+    const int32_t *asm_ptr, *asm_mono; const double* asm_val;
+    int32_t* info;
+} db_batch;
+
+typedef struct {
+    int32_t nvec;
+    int32_t slot[16];
+    double coef[16];
+} db_slotcomb;
+
+/* side: 0 = variables/state arena (columns), 1 = equations arena (rows); gather != 0: arena -> vec[slot], else vec[slot] -> arena */
+int db_batches_move(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t side, int32_t gather,
+                    int32_t slot, double* arena, void* stream);
+/* vec[ym_slot] = M vec[x_slot], vec[yl_slot] = L vec[x_slot]; a negative slot skips that product */
+int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t x_slot, int32_t ym_slot, int32_t yl_slot, void* stream);
+/* vec[x_slot] = LU[lu_slot]^{-1} (sum_j coef[j] vec[slot[j]]) */
+int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
+                     const db_slotcomb* rhs, void* stream);
+/* LU[lu_slot] = assembled LHS (asm_* programs), then in-place factorisation */
+int db_batches_assemble(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, void* stream);
+int db_batches_factor(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, void* stream);
 
 /* out = sum_j coef[j]*vecs[j] over `count` doubles (explicit RHS build, used by tests and diagnostics). */
 int db_lincomb_apply(const db_lincomb* terms, double* out, int64_t count, void* stream);

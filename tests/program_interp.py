@@ -32,23 +32,31 @@ def factor(prog, LU):
 
 
 def solve(prog, LU, rhs):
+    ENDROW, DIAG, NOP, MASK = 0x40000000, 0x20000000, 0x10000000, 0x0FFFFFFF
     n = prog.n
     y = np.array(rhs, dtype=float, copy=True)
-    e = 0
-    for i in range(n):
-        acc = y[i].copy()
-        for t in range(prog.fwd_ptr[i], prog.fwd_ptr[i + 1]):
-            acc -= LU[e] * y[prog.fwd_col[t]]
-            e += 1
-        y[i] = acc
-    for pos, i in enumerate(range(n - 1, -1, -1)):
-        inv = LU[e]; e += 1
-        acc = y[i].copy()
-        for t in range(prog.bwd_ptr[pos], prog.bwd_ptr[pos + 1]):
-            acc -= LU[e] * y[prog.bwd_col[t]]
-            e += 1
-        y[i] = acc * inv
-    assert e == prog.nE
+    row = 0
+    acc = y[0].copy()
+    for e in range(prog.n_fwd):
+        c = int(prog.prog[e])
+        if not (c & NOP):
+            acc = acc - LU[e] * y[c & MASK]
+        if c & ENDROW:
+            y[row] = acc
+            row += 1
+            if row < n:
+                acc = y[row].copy()
+    row = n - 1
+    inv = None
+    for e in range(prog.n_fwd, prog.nE):
+        c = int(prog.prog[e])
+        if c & DIAG:
+            inv = LU[e]; acc = y[row].copy()
+        elif not (c & NOP):
+            acc = acc - LU[e] * y[c & MASK]
+        if c & ENDROW:
+            y[row] = acc * inv
+            row -= 1
     return y
 
 

@@ -63,8 +63,7 @@ def test_pencil_kernels_match_interpreters():
         for j, (v, c) in enumerate(((yM, 1.0), (F, 0.3), (yL, -0.7))):
             lc.vec[j] = v.ctypes.data; lc.coef[j] = c
         xs = np.zeros((n, ld))
-        lib.call("db_pencil_solve", E.ptr(LU), n, S, ld, E.ptr(_i32(prog.fwd_ptr)), E.ptr(_i32(prog.fwd_col)), E.ptr(_i32(prog.bwd_ptr)),
-                 E.ptr(_i32(prog.bwd_col)), C.byref(lc), E.ptr(xs), None)
+        lib.call("db_pencil_solve", E.ptr(LU), n, S, ld, E.ptr(_i32(prog.prog)), prog.n_fwd, prog.nE, C.byref(lc), E.ptr(xs), None)
         rhs = yM + 0.3 * F - 0.7 * yL
         for s in range(0, S, max(1, S // 3)):
             A = batch.matrix((a0, b0), batch.groups[s]).tocsc()
