@@ -24,7 +24,7 @@ struct FftArgs {
     double* out;
     int64_t outer, inner;
     int32_t n_coeff;
-    int32_t T, TP;
+    int32_t T, TP, lgT;
     int32_t deriv;
     double kscale;
     const double* diags_a; int32_t nd_a;    // forward: conversion apply ; backward: pre-apply
@@ -87,22 +87,28 @@ template <bool INV, int R> __device__ __forceinline__ void dftr(double2* v, cons
 
 // one radix-R pass over the whole tile; R is a template parameter so the butterfly lives in registers
 template <bool INV, int R>
-__device__ __forceinline__ void fft_pass_r(double2* buf, int nc, int TP, int Tc, int L, const double* tw)
+__device__ __forceinline__ void fft_pass_r(double2* buf, int nc, int TP, int lgT, int L, const double* tw)
 {
+    // all T = 2^lgT columns of the tile are processed (unused columns of a partial tile hold garbage that is never
+    // stored), so the column index is a mask and the butterfly index a shift; the division by m uses a 24-bit
+    // reciprocal (exact for bf * m < 2^24, i.e. any nc that fits shared memory)
     const int m = L / R;
     const int nbf = nc / R;
     const int tstep = nc / L;
-    for (int w = threadIdx.x; w < nbf * Tc; w += blockDim.x) {
-        const int t = w % Tc;
-        const int bf = w / Tc;
-        const int b = bf / m, k = bf - b * m;
+    const unsigned inv_m = (unsigned)(((1u << 24) + m - 1) / m);
+    const int Tmask = (1 << lgT) - 1;
+    for (int w = threadIdx.x; w < (nbf << lgT); w += blockDim.x) {
+        const int t = w & Tmask;
+        const int bf = w >> lgT;
+        const int b = (int)(((unsigned long long)bf * inv_m) >> 24), k = bf - b * m;
         double2 v[R];
         const int i0 = b * L + k;
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = buf[(i0 + q * m) * TP + t];
+        const int tk = tstep * k;          // tk * q < nc for all q < R: no modulo needed
         if (INV) {   // DIT: twiddle first (conjugate), then butterfly
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], ldtw(tw, (tstep * k * q) % nc));
+            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], ldtw(tw, tk * q));
         }
         if (R == 4) dft4<INV>(v);
         else if (R == 2) dft2<INV>(v);
@@ -110,7 +116,7 @@ __device__ __forceinline__ void fft_pass_r(double2* buf, int nc, int TP, int Tc,
         else dftr<INV, R>(v, tw, nc);
         if (!INV) {  // DIF: butterfly first, then twiddle
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, (tstep * k * q) % nc));
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, tk * q));
         }
 #pragma unroll
         for (int q = 0; q < R; ++q) buf[(i0 + q * m) * TP + t] = v[q];
@@ -133,7 +139,7 @@ __device__ __noinline__ void fft_pass_generic(double2* buf, int nc, int TP, int 
         const int i0 = b * L + k;
         for (int q = 0; q < r; ++q) {
             v[q] = buf[(i0 + q * m) * TP + t];
-            if (INV && q > 0) v[q] = cmulc(v[q], ldtw(tw, (tstep * k * q) % nc));
+            if (INV && q > 0) v[q] = cmulc(v[q], ldtw(tw, tstep * k * q));
         }
         for (int qp = 0; qp < r; ++qp) {
             double2 acc = v[0];
@@ -145,40 +151,40 @@ __device__ __noinline__ void fft_pass_generic(double2* buf, int nc, int TP, int 
         }
         for (int q = 0; q < r; ++q) {
             double2 o = y[q];
-            if (!INV && q > 0) o = cmul(o, ldtw(tw, (tstep * k * q) % nc));
+            if (!INV && q > 0) o = cmul(o, ldtw(tw, tstep * k * q));
             buf[(i0 + q * m) * TP + t] = o;
         }
     }
 }
 
 template <bool INV>
-__device__ void fft_pass(double2* buf, int nc, int TP, int Tc, int r, int L, const double* tw)
+__device__ void fft_pass(double2* buf, int nc, int TP, int lgT, int r, int L, const double* tw)
 {
     switch (r) {
-        case 4: fft_pass_r<INV, 4>(buf, nc, TP, Tc, L, tw); break;
-        case 2: fft_pass_r<INV, 2>(buf, nc, TP, Tc, L, tw); break;
-        case 3: fft_pass_r<INV, 3>(buf, nc, TP, Tc, L, tw); break;
-        case 5: fft_pass_r<INV, 5>(buf, nc, TP, Tc, L, tw); break;
-        default: fft_pass_generic<INV>(buf, nc, TP, Tc, r, L, tw); break;
+        case 4: fft_pass_r<INV, 4>(buf, nc, TP, lgT, L, tw); break;
+        case 2: fft_pass_r<INV, 2>(buf, nc, TP, lgT, L, tw); break;
+        case 3: fft_pass_r<INV, 3>(buf, nc, TP, lgT, L, tw); break;
+        case 5: fft_pass_r<INV, 5>(buf, nc, TP, lgT, L, tw); break;
+        default: fft_pass_generic<INV>(buf, nc, TP, 1 << lgT, r, L, tw); break;
     }
 }
 
-__device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int Tc)
+__device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) {
-        fft_pass<false>(buf, p.nc, TP, Tc, p.rad[s], L, p.tw);
+        fft_pass<false>(buf, p.nc, TP, lgT, p.rad[s], L, p.tw);
         L /= p.rad[s];
         __syncthreads();
     }
 }
-__device__ void fft_dit(double2* buf, const db_fft_plan& p, int TP, int Tc)
+__device__ void fft_dit(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
     int Ls[16];
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) { Ls[s] = L; L /= p.rad[s]; }
     for (int s = p.nrad - 1; s >= 0; --s) {
-        fft_pass<true>(buf, p.nc, TP, Tc, p.rad[s], Ls[s], p.tw);
+        fft_pass<true>(buf, p.nc, TP, lgT, p.rad[s], Ls[s], p.tw);
         __syncthreads();
     }
 }
@@ -217,9 +223,9 @@ __device__ __forceinline__ TileGeom tile_geom(const FftArgs& a, int len, int cpl
 
 // iterate over (j, t) with the global-memory-contiguous index fastest across threads
 #define TILE_FOR(len, g, contiguous, j, t)                                                   \
-    for (int _e = threadIdx.x, _tot = (len) * (g).Tc; _e < _tot; _e += blockDim.x)           \
-        for (int _once = 1, j = (contiguous) ? _e % (len) : _e / (g).Tc,                     \
-                 t = (contiguous) ? _e / (len) : _e % (g).Tc; _once; _once = 0)
+    for (int _e = threadIdx.x, _tot = (len) * (g).Tc, _full = ((g).Tc == a.T); _e < _tot; _e += blockDim.x) \
+        for (int _once = 1, j = (contiguous) ? _e % (len) : (_full ? (_e >> a.lgT) : _e / (g).Tc),          \
+                 t = (contiguous) ? _e / (len) : (_full ? (_e & (a.T - 1)) : _e % (g).Tc); _once; _once = 0)
 
 template <int KIND>
 __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
@@ -255,14 +261,14 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
             }
         }
         __syncthreads();
-        fft_dif(buf, p, TP, Tc);
+        fft_dif(buf, p, TP, a.lgT);
         // ---------------- post-processing into the coefficient staging area ----------------
         if (KIND == K_CFWD) {
             const int KM = (M - 1) / 2;
             int Kmax = (n - 1) / 2; if (KM < Kmax) Kmax = KM;
             const double sc = 1.0 / n;
-            for (int w = threadIdx.x; w < M * Tc; w += blockDim.x) {
-                const int t = w % Tc, c = w / Tc;
+            for (int w = threadIdx.x; w < ((M) << a.lgT); w += blockDim.x) {
+                const int t = w & (a.T - 1), c = w >> a.lgT;
                 const int k = (c + KM) % M - KM;
                 double2 z = make_double2(0.0, 0.0);
                 if (k <= Kmax && -k <= Kmax) {
@@ -275,8 +281,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
         } else if (KIND == K_RFWD) {
             int Kmax = (n - 1) / 2; { int KM = (M - 1) / 2; if (KM < Kmax) Kmax = KM; }
             const int nk = (M + 1) / 2;
-            for (int w = threadIdx.x; w < nk * Tc; w += blockDim.x) {
-                const int t = w % Tc, k = w / Tc;
+            for (int w = threadIdx.x; w < ((nk) << a.lgT); w += blockDim.x) {
+                const int t = w & (a.T - 1), k = w >> a.lgT;
                 double re = 0.0, im = 0.0;
                 if (k <= Kmax) {
                     double2 X;
@@ -301,8 +307,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
             const double s0 = 0.5 / n * 1.7724538509055160272981674833411;      // sqrt(pi)/(2N)
             const double s1 = 1.0 / n * 1.2533141373155002512078826424055;      // sqrt(pi/2)/N
             if (p.half) {
-                for (int w = threadIdx.x; w < (nc + 1) * Tc; w += blockDim.x) {
-                    const int t = w % Tc, k = w / Tc;
+                for (int w = threadIdx.x; w < (((nc + 1)) << a.lgT); w += blockDim.x) {
+                    const int t = w & (a.T - 1), k = w >> a.lgT;
                     double2 zk = buf[p.iperm[k % nc] * TP + t];
                     double2 zn = cconj(buf[p.iperm[(nc - k) % nc] * TP + t]);
                     double2 E = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
@@ -321,14 +327,14 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
                     }
                 }
             } else {
-                for (int w = threadIdx.x; w < Kin * Tc; w += blockDim.x) {
-                    const int t = w % Tc, k = w / Tc;
+                for (int w = threadIdx.x; w < ((Kin) << a.lgT); w += blockDim.x) {
+                    const int t = w & (a.T - 1), k = w >> a.lgT;
                     double2 W = cmul(ldtw(p.twq, k), buf[p.iperm[k] * TP + t]);
                     double v = 2.0 * W.x * ((k == 0) ? s0 : s1);
                     cof[k * TP + t] = (k & 1) ? -v : v;
                 }
             }
-            for (int w = threadIdx.x + Kin * Tc; w < M * Tc; w += blockDim.x) cof[(w / Tc) * TP + (w % Tc)] = 0.0;
+            for (int w = threadIdx.x + (Kin << a.lgT); w < (M << a.lgT); w += blockDim.x) cof[(w >> a.lgT) * TP + (w & (a.T - 1))] = 0.0;
         }
         __syncthreads();
         // ---------------- store (with the banded conversion fused for Chebyshev) ----------------
@@ -367,36 +373,60 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
         __syncthreads();
         if (KIND == K_CHBWD) {
             int Kmax = n - 1; if (M - 1 < Kmax) Kmax = M - 1;
-            // per-line banded work: truncate, pre-apply (ascending, in place), back-substitution (descending)
-            if ((a.nd_a > 0 || a.nd_b > 0 || M > n) && (int)threadIdx.x < Tc) {
-                const int t = threadIdx.x;
-                if (M > n) for (int i = Kmax + 1; i < M; ++i) cof[i * TP + t] = 0.0;
-                if (a.nd_a > 0) {
-                    for (int i = 0; i < M; ++i) {
-                        double acc = 0.0;
+            // banded work on the staged coefficients: truncate, pre-apply (parallel, cof -> tmp), back-substitution
+            // (one thread per line, solved values kept in a register window; tmp -> cof)
+            double* tmp = smem;                           // the complex work buffer is still unused here
+            if (M > n) {
+                for (int w = threadIdx.x + ((Kmax + 1) << a.lgT); w < (M << a.lgT); w += blockDim.x)
+                    cof[(w >> a.lgT) * TP + (w & (a.T - 1))] = 0.0;
+                __syncthreads();
+            }
+            if (a.nd_a > 0 || a.nd_b > 0) {
+                for (int w = threadIdx.x; w < (M << a.lgT); w += blockDim.x) {
+                    const int t = w & (a.T - 1), i = w >> a.lgT;
+                    double acc;
+                    if (a.nd_a > 0) {
+                        acc = 0.0;
                         for (int d = 0; d < a.nd_a && i + d < M; ++d)
                             acc = fma(a.diags_a[(int64_t)d * M + i], cof[(i + d) * TP + t], acc);
-                        cof[i * TP + t] = acc;
+                    } else {
+                        acc = cof[i * TP + t];
                     }
+                    tmp[i * TP + t] = acc;
                 }
+                __syncthreads();
                 if (a.nd_b > 0) {
-                    // back-substitution; diags_b row 0 holds the RECIPROCAL diagonal (host precomputes it)
-                    for (int i = M - 1; i >= 0; --i) {
-                        double acc = cof[i * TP + t];
-                        for (int d = 1; d < a.nd_b && i + d < M; ++d)
-                            acc = fma(-a.diags_b[(int64_t)d * M + i], cof[(i + d) * TP + t], acc);
-                        cof[i * TP + t] = acc * a.diags_b[i];
+                    if ((int)threadIdx.x < a.T) {
+                        const int t = threadIdx.x;
+                        double win[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};       // x_{i+1} .. x_{i+7}
+                        const int nd = a.nd_b < 8 ? a.nd_b : 8;
+                        for (int i = M - 1; i >= 0; --i) {
+                            double acc = tmp[i * TP + t];
+#pragma unroll
+                            for (int d = 1; d < 8; ++d)
+                                if (d < nd) acc = fma(-a.diags_b[(int64_t)d * M + i], win[d - 1], acc);
+                            const double xi = acc * a.diags_b[i];                  // row 0 = reciprocal diagonal
+#pragma unroll
+                            for (int d = 6; d > 0; --d) win[d] = win[d - 1];
+                            win[0] = xi;
+                            cof[i * TP + t] = xi;
+                        }
+                    }
+                } else {
+                    for (int w = threadIdx.x; w < (M << a.lgT); w += blockDim.x) {
+                        const int t = w & (a.T - 1), i = w >> a.lgT;
+                        cof[i * TP + t] = tmp[i * TP + t];
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
         // ================= build the (digit-reversed) spectrum for the DIT passes =================
         if (KIND == K_CBWD) {
             const int KM = (M - 1) / 2;
             int Kmax = (n - 1) / 2; if (KM < Kmax) Kmax = KM;
-            for (int w = threadIdx.x; w < nc * Tc; w += blockDim.x) {
-                const int t = w % Tc, pos = w / Tc;
+            for (int w = threadIdx.x; w < ((nc) << a.lgT); w += blockDim.x) {
+                const int t = w & (a.T - 1), pos = w >> a.lgT;
                 int k = p.perm[pos];
                 if (k > n / 2) k -= n;                       // signed wavenumber
                 double2 z = make_double2(0.0, 0.0);
@@ -451,8 +481,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
                 }
             };
             if (p.half) {
-                for (int w = threadIdx.x; w < nc * Tc; w += blockDim.x) {
-                    const int t = w % Tc, pos = w / Tc;
+                for (int w = threadIdx.x; w < ((nc) << a.lgT); w += blockDim.x) {
+                    const int t = w & (a.T - 1), pos = w >> a.lgT;
                     const int k = p.perm[pos];
                     double2 xk = getX(k, t);
                     double2 xn = cconj(getX(nc - k, t));
@@ -461,8 +491,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
                     buf[pos * TP + t] = make_double2(E.x - O.y, E.y + O.x);     // E + i O
                 }
             } else {
-                for (int w = threadIdx.x; w < nc * Tc; w += blockDim.x) {
-                    const int t = w % Tc, pos = w / Tc;
+                for (int w = threadIdx.x; w < ((nc) << a.lgT); w += blockDim.x) {
+                    const int t = w & (a.T - 1), pos = w >> a.lgT;
                     const int k = p.perm[pos];
                     double2 z;
                     if (KIND == K_RBWD) {
@@ -480,7 +510,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
             }
         }
         __syncthreads();
-        fft_dit(buf, p, TP, Tc);
+        fft_dit(buf, p, TP, a.lgT);
         // ================= store grid data =================
         if (KIND == K_CBWD) {
             TILE_FOR(n, go, contiguous, j, t) {
@@ -518,15 +548,20 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
     // the 227 KB per-CTA limit
     int T = 16;
     const int64_t lines_dir = (inner == 1) ? outer : inner;
+    // work-buffer rows (doubles per column): the complex FFT buffer, which the Chebyshev backward kernel also uses
+    // as scratch for n_coeff staged coefficients
+    size_t buf_rows = (size_t)2 * plan->nc;
+    if (KIND == K_CHBWD && (size_t)n_coeff > buf_rows) buf_rows = (size_t)n_coeff;
     auto smem_bytes = [&](int t) -> size_t {
-        return ((size_t)2 * plan->nc * (t + 1) + (size_t)(is_cplx ? 2 : 1) * n_coeff * (t + 1)) * sizeof(double);
+        return (buf_rows * (t + 1) + (size_t)(is_cplx ? 2 : 1) * n_coeff * (t + 1)) * sizeof(double);
     };
     while (T > 1 && smem_bytes(T) > (size_t)110 * 1024) T /= 2;
     while (T > 1 && T / 2 >= lines_dir) T /= 2;    // do not waste lanes on tiny problems
     size_t bytes = smem_bytes(T);
     if (bytes > (size_t)DB_MAX_SMEM) { db_set_error("%s: transform length %d too large for shared memory", name, plan->n); return 1; }
     a.T = T; a.TP = T + 1;
-    a.cof_off = 2 * plan->nc * a.TP;
+    a.lgT = 0; while ((1 << a.lgT) < T) ++a.lgT;
+    a.cof_off = (int32_t)(buf_rows * a.TP);
     int64_t tiles;
     if (inner == 1) { a.tiles_per_outer = 0; tiles = (outer + T - 1) / T; }
     else { a.tiles_per_outer = (inner + T - 1) / T; tiles = outer * a.tiles_per_outer; }
