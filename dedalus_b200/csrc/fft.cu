@@ -14,6 +14,7 @@
 // HBM traffic is exactly one read of the input and one write of the output; loads / stores are coalesced
 // along the contiguous direction of the view (across lines when inner > 1, along the line when inner == 1).
 #include "db_common.cuh"
+#include <cstdlib>
 
 enum { K_RFWD = 0, K_RBWD = 1, K_CFWD = 2, K_CBWD = 3, K_CHFWD = 4, K_CHBWD = 5 };
 #define FFT_THREADS 256
@@ -38,7 +39,7 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_dou
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
-__device__ __forceinline__ double2 ldtw(const double* tw, int j) { return make_double2(tw[2 * j], tw[2 * j + 1]); }
+__device__ __forceinline__ double2 ldtw(const double* tw, int j) { return reinterpret_cast<const double2*>(tw)[j]; }
 
 // small DFTs; INV selects exp(+i...) kernels
 template <bool INV> __device__ __forceinline__ void dft2(double2* v)
@@ -221,11 +222,34 @@ __device__ __forceinline__ TileGeom tile_geom(const FftArgs& a, int len, int cpl
     return g;
 }
 
-// iterate over (j, t) with the global-memory-contiguous index fastest across threads
-#define TILE_FOR(len, g, contiguous, j, t)                                                   \
-    for (int _e = threadIdx.x, _tot = (len) * (g).Tc, _full = ((g).Tc == a.T); _e < _tot; _e += blockDim.x) \
-        for (int _once = 1, j = (contiguous) ? _e % (len) : (_full ? (_e >> a.lgT) : _e / (g).Tc),          \
-                 t = (contiguous) ? _e / (len) : (_full ? (_e & (a.T - 1)) : _e % (g).Tc); _once; _once = 0)
+// Visit every element (j, t) of the tile with the global-memory-contiguous index fastest across lanes and
+// only additions in the inner loop: f(j, t, global offset).
+template <class F>
+__device__ __forceinline__ void tile_iter(int len, const TileGeom& g, bool contiguous, int lgT, F f)
+{
+    if (contiguous) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int t = warp; t < g.Tc; t += nw) {
+            const int64_t off = g.base + t * g.lstride;
+            for (int j = lane; j < len; j += 32) f(j, t, off + j * g.estride);
+        }
+    } else {
+        const int t = threadIdx.x & ((1 << lgT) - 1);
+        if (t < g.Tc) {
+            const int js = blockDim.x >> lgT;
+            int j = threadIdx.x >> lgT;
+            int64_t off = g.base + t * g.lstride + j * g.estride;
+            const int64_t step = js * g.estride;
+            for (; j < len; j += js, off += step) f(j, t, off);
+        }
+    }
+}
+
+__device__ __forceinline__ double2 rot_i_pow(double2 z, int ph)
+{
+    // z * i^ph
+    return (ph == 0) ? z : (ph == 1) ? make_double2(-z.y, z.x) : (ph == 2) ? make_double2(-z.x, -z.y) : make_double2(z.y, -z.x);
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
@@ -234,141 +258,161 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
     double2* buf = reinterpret_cast<double2*>(smem);
     double* cof = smem + a.cof_off;
     const db_fft_plan& p = a.plan;
-    const int n = p.n, nc = p.nc, M = a.n_coeff, TP = a.TP;
+    const int n = p.n, nc = p.nc, M = a.n_coeff, TP = a.TP, lgT = a.lgT, T = a.T;
     const bool contiguous = (a.inner == 1);
     const bool is_fwd = (KIND == K_RFWD || KIND == K_CFWD || KIND == K_CHFWD);
     const bool is_cplx = (KIND == K_CFWD || KIND == K_CBWD);
     const int cplx = is_cplx ? 2 : 1;
     const TileGeom gi = tile_geom(a, is_fwd ? n : M, cplx);
     const TileGeom go = tile_geom(a, is_fwd ? M : n, cplx);
-    const int Tc = gi.Tc;
+    const int Tmask = T - 1;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const double* __restrict__ gin = a.in;
+    double* __restrict__ gout = a.out;
 
     if (is_fwd) {
         // ---------------- load grid data straight into the complex work buffer ----------------
         if (KIND == K_CFWD) {
-            TILE_FOR(n, gi, contiguous, j, t) {
-                const double* src = a.in + gi.base + j * gi.estride + t * gi.lstride;
-                buf[j * TP + t] = make_double2(src[0], src[1]);
-            }
+            tile_iter(n, gi, contiguous, lgT, [&](int j, int t, int64_t off) {
+                buf[j * TP + t] = make_double2(gin[off], gin[off + 1]);
+            });
         } else {
-            double* rb = smem;   // real view: element p of line t at ((p>>1)*TP + t)*2 + (p&1)   (half) or (p*TP+t)*2 (full)
-            TILE_FOR(n, gi, contiguous, j, t) {
-                double v = a.in[gi.base + j * gi.estride + t * gi.lstride];
+            double* rb = smem;   // real view: element pp of line t at ((pp>>1)*TP + t)*2 + (pp&1) (half) or (pp*TP+t)*2 (full)
+            const int half = p.half;
+            tile_iter(n, gi, contiguous, lgT, [&](int j, int t, int64_t off) {
+                const double v = gin[off];
                 int pp = j;
                 if (KIND == K_CHFWD) pp = (j & 1) ? (n - 1 - (j >> 1)) : (j >> 1);
-                if (p.half) rb[((pp >> 1) * TP + t) * 2 + (pp & 1)] = v;
-                else { rb[(pp * TP + t) * 2] = v; rb[(pp * TP + t) * 2 + 1] = 0.0; }
-            }
+                if (half) rb[(((pp >> 1) * TP + t) << 1) + (pp & 1)] = v;
+                else { rb[(pp * TP + t) << 1] = v; rb[((pp * TP + t) << 1) + 1] = 0.0; }
+            });
         }
         __syncthreads();
-        fft_dif(buf, p, TP, a.lgT);
+        fft_dif(buf, p, TP, lgT);
         // ---------------- post-processing into the coefficient staging area ----------------
         if (KIND == K_CFWD) {
             const int KM = (M - 1) / 2;
             int Kmax = (n - 1) / 2; if (KM < Kmax) Kmax = KM;
             const double sc = 1.0 / n;
-            for (int w = threadIdx.x; w < ((M) << a.lgT); w += blockDim.x) {
-                const int t = w & (a.T - 1), c = w >> a.lgT;
+            for (int w = tid; w < (M << lgT); w += nthreads) {
+                const int t = w & Tmask, c = w >> lgT;
                 const int k = (c + KM) % M - KM;
                 double2 z = make_double2(0.0, 0.0);
                 if (k <= Kmax && -k <= Kmax) {
-                    const int kk = (k % n + n) % n;
+                    const int kk = (k < 0) ? k + n : k;
                     z = buf[p.iperm[kk] * TP + t];
                     z.x *= sc; z.y *= sc;
                 }
                 cof[(c * TP + t) * 2] = z.x; cof[(c * TP + t) * 2 + 1] = z.y;
             }
+        } else if (p.half) {
+            // pairs (k, nc-k): X_k = E + w^k O, X_{nc-k} = conj(E - w^k O)
+            const int npair = nc / 2 + 1;
+            int Kmax, Kin = 0;
+            double s0 = 0.0, s1 = 0.0;
+            if (KIND == K_RFWD) {
+                Kmax = (n - 1) / 2; { int KM = (M - 1) / 2; if (KM < Kmax) Kmax = KM; }
+                // coefficient slots beyond the pairs' reach (M > n + 2) are zero
+                for (int w = tid + ((2 * (nc + 1)) << lgT); w < (M << lgT); w += nthreads) cof[(w >> lgT) * TP + (w & Tmask)] = 0.0;
+            } else {
+                Kmax = 0;
+                Kin = (M < n) ? M : n;
+                s0 = 0.5 / n * 1.7724538509055160272981674833411;      // sqrt(pi)/(2N)
+                s1 = 1.0 / n * 1.2533141373155002512078826424055;      // sqrt(pi/2)/N
+                for (int w = tid + (Kin << lgT); w < (M << lgT); w += nthreads) cof[(w >> lgT) * TP + (w & Tmask)] = 0.0;
+            }
+            const double rsc = 2.0 / n;
+            for (int w = tid; w < (npair << lgT); w += nthreads) {
+                const int t = w & Tmask, ka = w >> lgT, kb = nc - ka;
+                const double2 za = buf[p.iperm[ka] * TP + t];
+                const double2 zb = buf[p.iperm[(kb == nc) ? 0 : kb] * TP + t];
+                const double2 E = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));
+                const double2 D = make_double2(za.x - zb.x, za.y + zb.y);          // za - conj(zb)
+                const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);             // -i/2 * D
+                const double2 W = cmul(ldtw(p.twr, ka), O);
+                const double2 Xa = cadd(E, W);
+                const double2 Xb = make_double2(E.x - W.x, -(E.y - W.y));
+                if (KIND == K_RFWD) {
+                    // coefficient pair (2k, 2k+1) = (2/N) (Re, Im) X_k ; k = 0: (Re X_0 / N, 0); k > Kmax: 0
+                    if (2 * ka < M) {
+                        const bool ok = ka <= Kmax;
+                        cof[(2 * ka) * TP + t] = ok ? Xa.x * ((ka == 0) ? 0.5 * rsc : rsc) : 0.0;
+                        if (2 * ka + 1 < M) cof[(2 * ka + 1) * TP + t] = (ok && ka > 0) ? Xa.y * rsc : 0.0;
+                    }
+                    if (kb != ka && 2 * kb < M) {
+                        const bool ok = kb <= Kmax;
+                        cof[(2 * kb) * TP + t] = ok ? Xb.x * rsc : 0.0;
+                        if (2 * kb + 1 < M) cof[(2 * kb + 1) * TP + t] = ok ? Xb.y * rsc : 0.0;
+                    }
+                } else {
+                    // C_k = 2 Re(q^k X_k) (k <= nc), C_{n-k} = -2 Im(q^k X_k) (0 < k < nc); scaled, odd modes negated
+                    const double2 Wa = cmul(ldtw(p.twq, ka), Xa);
+                    if (ka < Kin) { double v = 2.0 * Wa.x * ((ka == 0) ? s0 : s1); cof[ka * TP + t] = (ka & 1) ? -v : v; }
+                    const int ka2 = n - ka;
+                    if (ka >= 1 && ka < nc && ka2 < Kin) { double v = -2.0 * Wa.y * s1; cof[ka2 * TP + t] = (ka2 & 1) ? -v : v; }
+                    if (kb != ka) {
+                        const double2 Wb = cmul(ldtw(p.twq, kb), Xb);
+                        if (kb < Kin) { double v = 2.0 * Wb.x * s1; cof[kb * TP + t] = (kb & 1) ? -v : v; }
+                        const int kb2 = n - kb;
+                        if (kb < nc && kb2 < Kin) { double v = -2.0 * Wb.y * s1; cof[kb2 * TP + t] = (kb2 & 1) ? -v : v; }
+                    }
+                }
+            }
         } else if (KIND == K_RFWD) {
             int Kmax = (n - 1) / 2; { int KM = (M - 1) / 2; if (KM < Kmax) Kmax = KM; }
             const int nk = (M + 1) / 2;
-            for (int w = threadIdx.x; w < ((nk) << a.lgT); w += blockDim.x) {
-                const int t = w & (a.T - 1), k = w >> a.lgT;
+            for (int w = tid; w < (nk << lgT); w += nthreads) {
+                const int t = w & Tmask, k = w >> lgT;
                 double re = 0.0, im = 0.0;
                 if (k <= Kmax) {
-                    double2 X;
-                    if (p.half) {
-                        double2 zk = buf[p.iperm[k % nc] * TP + t];
-                        double2 zn = cconj(buf[p.iperm[(nc - k) % nc] * TP + t]);
-                        double2 E = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
-                        double2 D = csub(zk, zn);
-                        double2 O = make_double2(0.5 * D.y, -0.5 * D.x);          // -i/2 * D
-                        X = cadd(E, cmul(ldtw(p.twr, k), O));
-                    } else {
-                        X = buf[p.iperm[k] * TP + t];
-                    }
+                    const double2 X = buf[p.iperm[k] * TP + t];
                     const double sc = (k == 0) ? 1.0 / n : 2.0 / n;
                     re = X.x * sc; im = (k == 0) ? 0.0 : X.y * sc;
                 }
                 cof[(2 * k) * TP + t] = re;
                 if (2 * k + 1 < M) cof[(2 * k + 1) * TP + t] = im;
             }
-        } else {  // K_CHFWD
-            const int Kin = (M < n) ? M : n;           // coefficients kept before conversion
-            const double s0 = 0.5 / n * 1.7724538509055160272981674833411;      // sqrt(pi)/(2N)
-            const double s1 = 1.0 / n * 1.2533141373155002512078826424055;      // sqrt(pi/2)/N
-            if (p.half) {
-                for (int w = threadIdx.x; w < (((nc + 1)) << a.lgT); w += blockDim.x) {
-                    const int t = w & (a.T - 1), k = w >> a.lgT;
-                    double2 zk = buf[p.iperm[k % nc] * TP + t];
-                    double2 zn = cconj(buf[p.iperm[(nc - k) % nc] * TP + t]);
-                    double2 E = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
-                    double2 D = csub(zk, zn);
-                    double2 O = make_double2(0.5 * D.y, -0.5 * D.x);
-                    double2 X = cadd(E, cmul(ldtw(p.twr, k), O));
-                    double2 W = cmul(ldtw(p.twq, k), X);
-                    if (k < Kin) {
-                        double v = 2.0 * W.x * ((k == 0) ? s0 : s1);
-                        cof[k * TP + t] = (k & 1) ? -v : v;
-                    }
-                    const int k2 = n - k;
-                    if (k >= 1 && k2 > nc && k2 < Kin) {
-                        double v = -2.0 * W.y * s1;
-                        cof[k2 * TP + t] = (k2 & 1) ? -v : v;
-                    }
-                }
-            } else {
-                for (int w = threadIdx.x; w < ((Kin) << a.lgT); w += blockDim.x) {
-                    const int t = w & (a.T - 1), k = w >> a.lgT;
-                    double2 W = cmul(ldtw(p.twq, k), buf[p.iperm[k] * TP + t]);
-                    double v = 2.0 * W.x * ((k == 0) ? s0 : s1);
-                    cof[k * TP + t] = (k & 1) ? -v : v;
-                }
+        } else {  // K_CHFWD, odd n: full complex FFT of the reordered real data
+            const int Kin = (M < n) ? M : n;
+            const double s0 = 0.5 / n * 1.7724538509055160272981674833411;
+            const double s1 = 1.0 / n * 1.2533141373155002512078826424055;
+            for (int w = tid; w < (Kin << lgT); w += nthreads) {
+                const int t = w & Tmask, k = w >> lgT;
+                const double2 W = cmul(ldtw(p.twq, k), buf[p.iperm[k] * TP + t]);
+                const double v = 2.0 * W.x * ((k == 0) ? s0 : s1);
+                cof[k * TP + t] = (k & 1) ? -v : v;
             }
-            for (int w = threadIdx.x + (Kin << a.lgT); w < (M << a.lgT); w += blockDim.x) cof[(w >> a.lgT) * TP + (w & (a.T - 1))] = 0.0;
+            for (int w = tid + (Kin << lgT); w < (M << lgT); w += nthreads) cof[(w >> lgT) * TP + (w & Tmask)] = 0.0;
         }
         __syncthreads();
         // ---------------- store (with the banded conversion fused for Chebyshev) ----------------
         if (KIND == K_CFWD) {
-            TILE_FOR(M, go, contiguous, c, t) {
-                double* dst = a.out + go.base + c * go.estride + t * go.lstride;
-                dst[0] = cof[(c * TP + t) * 2]; dst[1] = cof[(c * TP + t) * 2 + 1];
-            }
+            tile_iter(M, go, contiguous, lgT, [&](int c, int t, int64_t off) {
+                gout[off] = cof[(c * TP + t) * 2]; gout[off + 1] = cof[(c * TP + t) * 2 + 1];
+            });
         } else if (KIND == K_CHFWD && a.nd_a > 0) {
             const int Kin = (M < n) ? M : n;
-            TILE_FOR(M, go, contiguous, i, t) {
+            const int nd = a.nd_a;
+            const double* __restrict__ dg = a.diags_a;
+            tile_iter(M, go, contiguous, lgT, [&](int i, int t, int64_t off) {
                 double acc = 0.0;
                 if (i < Kin) {
-                    for (int d = 0; d < a.nd_a && i + d < Kin; ++d)
-                        acc = fma(a.diags_a[(int64_t)d * M + i], cof[(i + d) * TP + t], acc);
+                    for (int d = 0; d < nd && i + d < Kin; ++d)
+                        acc = fma(dg[d * M + i], cof[(i + d) * TP + t], acc);
                 }
-                a.out[go.base + i * go.estride + t * go.lstride] = acc;
-            }
+                gout[off] = acc;
+            });
         } else {
-            TILE_FOR(M, go, contiguous, c, t) {
-                a.out[go.base + c * go.estride + t * go.lstride] = cof[c * TP + t];
-            }
+            tile_iter(M, go, contiguous, lgT, [&](int c, int t, int64_t off) { gout[off] = cof[c * TP + t]; });
         }
     } else {
         // ================= backward: stage coefficients =================
         if (KIND == K_CBWD) {
-            TILE_FOR(M, gi, contiguous, c, t) {
-                const double* src = a.in + gi.base + c * gi.estride + t * gi.lstride;
-                cof[(c * TP + t) * 2] = src[0]; cof[(c * TP + t) * 2 + 1] = src[1];
-            }
+            tile_iter(M, gi, contiguous, lgT, [&](int c, int t, int64_t off) {
+                cof[(c * TP + t) * 2] = gin[off]; cof[(c * TP + t) * 2 + 1] = gin[off + 1];
+            });
         } else {
-            TILE_FOR(M, gi, contiguous, c, t) {
-                cof[c * TP + t] = a.in[gi.base + c * gi.estride + t * gi.lstride];
-            }
+            tile_iter(M, gi, contiguous, lgT, [&](int c, int t, int64_t off) { cof[c * TP + t] = gin[off]; });
         }
         __syncthreads();
         if (KIND == K_CHBWD) {
@@ -377,13 +421,13 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
             // (one thread per line, solved values kept in a register window; tmp -> cof)
             double* tmp = smem;                           // the complex work buffer is still unused here
             if (M > n) {
-                for (int w = threadIdx.x + ((Kmax + 1) << a.lgT); w < (M << a.lgT); w += blockDim.x)
-                    cof[(w >> a.lgT) * TP + (w & (a.T - 1))] = 0.0;
+                for (int w = tid + ((Kmax + 1) << lgT); w < (M << lgT); w += nthreads)
+                    cof[(w >> lgT) * TP + (w & Tmask)] = 0.0;
                 __syncthreads();
             }
             if (a.nd_a > 0 || a.nd_b > 0) {
-                for (int w = threadIdx.x; w < (M << a.lgT); w += blockDim.x) {
-                    const int t = w & (a.T - 1), i = w >> a.lgT;
+                for (int w = tid; w < (M << lgT); w += nthreads) {
+                    const int t = w & Tmask, i = w >> lgT;
                     double acc;
                     if (a.nd_a > 0) {
                         acc = 0.0;
@@ -396,8 +440,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
                 }
                 __syncthreads();
                 if (a.nd_b > 0) {
-                    if ((int)threadIdx.x < a.T) {
-                        const int t = threadIdx.x;
+                    if (tid < T) {
+                        const int t = tid;
                         double win[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};       // x_{i+1} .. x_{i+7}
                         const int nd = a.nd_b < 8 ? a.nd_b : 8;
                         for (int i = M - 1; i >= 0; --i) {
@@ -413,8 +457,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
                         }
                     }
                 } else {
-                    for (int w = threadIdx.x; w < (M << a.lgT); w += blockDim.x) {
-                        const int t = w & (a.T - 1), i = w >> a.lgT;
+                    for (int w = tid; w < (M << lgT); w += nthreads) {
+                        const int t = w & Tmask, i = w >> lgT;
                         cof[i * TP + t] = tmp[i * TP + t];
                     }
                 }
@@ -425,8 +469,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
         if (KIND == K_CBWD) {
             const int KM = (M - 1) / 2;
             int Kmax = (n - 1) / 2; if (KM < Kmax) Kmax = KM;
-            for (int w = threadIdx.x; w < ((nc) << a.lgT); w += blockDim.x) {
-                const int t = w & (a.T - 1), pos = w >> a.lgT;
+            for (int w = tid; w < (nc << lgT); w += nthreads) {
+                const int t = w & Tmask, pos = w >> lgT;
                 int k = p.perm[pos];
                 if (k > n / 2) k -= n;                       // signed wavenumber
                 double2 z = make_double2(0.0, 0.0);
@@ -436,10 +480,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
                     if (a.deriv > 0) {
                         double f = 1.0;
                         for (int d = 0; d < a.deriv; ++d) f *= a.kscale * k;
-                        const int ph = a.deriv & 3;
-                        double2 r = (ph == 0) ? make_double2(z.x, z.y) : (ph == 1) ? make_double2(-z.y, z.x)
-                                  : (ph == 2) ? make_double2(-z.x, -z.y) : make_double2(z.y, -z.x);
-                        z = make_double2(r.x * f, r.y * f);
+                        z = rot_i_pow(z, a.deriv & 3);
+                        z.x *= f; z.y *= f;
                     }
                 }
                 buf[pos * TP + t] = z;
@@ -450,49 +492,48 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
             if (KIND == K_RBWD) { Kmax = (n - 1) / 2; int KM = (M - 1) / 2; if (KM < Kmax) Kmax = KM; }
             else { Kmax = n - 1; if (M - 1 < Kmax) Kmax = M - 1; }
             const double c0 = 0.56418958354775628694807945156077;     // 1/sqrt(pi)
-            const double c1 = 0.39894228040143267793994605993438;     // 1/(2 sqrt(pi/2)) = 1/sqrt(2 pi)
+            const double c1 = 0.39894228040143267793994605993438;     // 1/sqrt(2 pi)
+            const int deriv = a.deriv, dph = a.deriv & 3;
+            const double kscale = a.kscale;
             auto chat = [&](int k, int t) -> double {              // scaled, sign-flipped Chebyshev coefficient
                 if (k > Kmax || k >= n) return 0.0;
-                double v = cof[k * TP + t] * ((k == 0) ? c0 : c1);
+                const double v = cof[k * TP + t] * ((k == 0) ? c0 : c1);
                 return (k & 1) ? -v : v;
             };
             auto getX = [&](int k, int t) -> double2 {
                 if (KIND == K_RBWD) {
                     if (k > Kmax) return make_double2(0.0, 0.0);
-                    if (k == 0) {
-                        return make_double2((a.deriv > 0) ? 0.0 : cof[t], 0.0);
-                    }
+                    if (k == 0) return make_double2((deriv > 0) ? 0.0 : cof[t], 0.0);
                     double2 z = make_double2(0.5 * cof[(2 * k) * TP + t], 0.5 * cof[(2 * k + 1) * TP + t]);
-                    if (a.deriv > 0) {
+                    if (deriv > 0) {
                         double f = 1.0;
-                        for (int d = 0; d < a.deriv; ++d) f *= a.kscale * k;
-                        const int ph = a.deriv & 3;
-                        double2 r = (ph == 0) ? z : (ph == 1) ? make_double2(-z.y, z.x)
-                                  : (ph == 2) ? make_double2(-z.x, -z.y) : make_double2(z.y, -z.x);
-                        z = make_double2(r.x * f, r.y * f);
+                        for (int d = 0; d < deriv; ++d) f *= kscale * k;
+                        z = rot_i_pow(z, dph);
+                        z.x *= f; z.y *= f;
                     }
                     return z;
                 } else {
                     if (k == 0) return make_double2(chat(0, t), 0.0);
-                    // H_k = exp(i pi k / 2n) (c_k - i c_{n-k})
-                    double2 w = cconj(ldtw(p.twq, k));
-                    double2 v = make_double2(chat(k, t), -chat(n - k, t));
-                    return cmul(w, v);
+                    const double2 w = cconj(ldtw(p.twq, k));                  // exp(+i pi k / 2n)
+                    return cmul(w, make_double2(chat(k, t), -chat(n - k, t))); // H_k = q^-k (c_k - i c_{n-k})
                 }
             };
             if (p.half) {
-                for (int w = threadIdx.x; w < ((nc) << a.lgT); w += blockDim.x) {
-                    const int t = w & (a.T - 1), pos = w >> a.lgT;
-                    const int k = p.perm[pos];
-                    double2 xk = getX(k, t);
-                    double2 xn = cconj(getX(nc - k, t));
-                    double2 E = cadd(xk, xn);
-                    double2 O = cmulc(csub(xk, xn), ldtw(p.twr, k));          // * w^{-k}
-                    buf[pos * TP + t] = make_double2(E.x - O.y, E.y + O.x);     // E + i O
+                // pairs (k, nc-k): Z_k = E + iO, Z_{nc-k} = conj(E - iO), E = X_k + conj X_{nc-k}, O = (X_k - conj X_{nc-k}) w^{-k}
+                const int npair = nc / 2 + 1;
+                for (int w = tid; w < (npair << lgT); w += nthreads) {
+                    const int t = w & Tmask, ka = w >> lgT, kb = nc - ka;
+                    const double2 xa = getX(ka, t);
+                    const double2 xb = getX(kb, t);
+                    const double2 E = make_double2(xa.x + xb.x, xa.y - xb.y);
+                    const double2 D = make_double2(xa.x - xb.x, xa.y + xb.y);
+                    const double2 O = cmulc(D, ldtw(p.twr, ka));
+                    buf[p.iperm[ka] * TP + t] = make_double2(E.x - O.y, E.y + O.x);
+                    if (kb != ka && kb < nc) buf[p.iperm[kb] * TP + t] = make_double2(E.x + O.y, -(E.y - O.x));
                 }
             } else {
-                for (int w = threadIdx.x; w < ((nc) << a.lgT); w += blockDim.x) {
-                    const int t = w & (a.T - 1), pos = w >> a.lgT;
+                for (int w = tid; w < (nc << lgT); w += nthreads) {
+                    const int t = w & Tmask, pos = w >> lgT;
                     const int k = p.perm[pos];
                     double2 z;
                     if (KIND == K_RBWD) {
@@ -501,8 +542,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
                         else z = cconj(getX(n - k, t));
                     } else {
                         // G_k = c'_k exp(i pi k / 2n), c'_0 = c_0, c'_k = 2 c_k ; output = Re IDFT(G)
-                        double ck = chat(k, t) * ((k == 0) ? 1.0 : 2.0);
-                        double2 ww = cconj(ldtw(p.twq, k));
+                        const double ck = chat(k, t) * ((k == 0) ? 1.0 : 2.0);
+                        const double2 ww = cconj(ldtw(p.twq, k));
                         z = make_double2(ww.x * ck, ww.y * ck);
                     }
                     buf[pos * TP + t] = z;
@@ -510,22 +551,21 @@ __global__ void __launch_bounds__(FFT_THREADS, 2) k_fft(FftArgs a)
             }
         }
         __syncthreads();
-        fft_dit(buf, p, TP, a.lgT);
+        fft_dit(buf, p, TP, lgT);
         // ================= store grid data =================
         if (KIND == K_CBWD) {
-            TILE_FOR(n, go, contiguous, j, t) {
-                double2 z = buf[j * TP + t];
-                double* dst = a.out + go.base + j * go.estride + t * go.lstride;
-                dst[0] = z.x; dst[1] = z.y;
-            }
+            tile_iter(n, go, contiguous, lgT, [&](int j, int t, int64_t off) {
+                const double2 z = buf[j * TP + t];
+                gout[off] = z.x; gout[off + 1] = z.y;
+            });
         } else {
             const double* rb = smem;
-            TILE_FOR(n, go, contiguous, j, t) {
+            const int half = p.half;
+            tile_iter(n, go, contiguous, lgT, [&](int j, int t, int64_t off) {
                 int pp = j;
                 if (KIND == K_CHBWD) pp = (j & 1) ? (n - 1 - (j >> 1)) : (j >> 1);
-                double v = p.half ? rb[((pp >> 1) * TP + t) * 2 + (pp & 1)] : rb[(pp * TP + t) * 2];
-                a.out[go.base + j * go.estride + t * go.lstride] = v;
-            }
+                gout[off] = half ? rb[(((pp >> 1) * TP + t) << 1) + (pp & 1)] : rb[(pp * TP + t) << 1];
+            });
         }
     }
 }
@@ -547,6 +587,7 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
     // choose the tile width: up to 16 lines, shrunk until the CTA fits ~110 KB (2 CTAs / SM) or, failing that,
     // the 227 KB per-CTA limit
     int T = 16;
+    { const char* e = getenv("DB_FFT_T"); if (e) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) T = v; } }
     const int64_t lines_dir = (inner == 1) ? outer : inner;
     // work-buffer rows (doubles per column): the complex FFT buffer, which the Chebyshev backward kernel also uses
     // as scratch for n_coeff staged coefficients

@@ -278,11 +278,16 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     const int32_t* __restrict__ prog = B.prog;
     double* __restrict__ x = B.vec[x_slot] + s;
     const double* rv[16];
-    for (int j = 0; j < rhs.nvec; ++j) rv[j] = B.vec[rhs.slot[j]] + s;
-    // ---- forward substitution: flat stream, SOLVE_PF-deep register prefetch of the factor values
+    for (int j = 0; j < 16; ++j) rv[j] = (j < rhs.nvec) ? B.vec[rhs.slot[j]] + s : nullptr;
+    // ---- forward substitution: flat stream, SOLVE_PF-deep register prefetch of the factor values; the RHS
+    //      combination of the next two rows is loaded ahead so its HBM latency is off the dependent chain
+    auto rhs_at = [&](int r) -> double {
+        double a = 0.0;
+        if (r < n) for (int q = 0; q < rhs.nvec; ++q) a = fma(rhs.coef[q], rv[q][(int64_t)r * ld], a);
+        return a;
+    };
     int row = 0;
-    double acc = 0.0;
-    for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rv[j][0], acc);
+    double acc = rhs_at(0), r1 = rhs_at(1), r2 = rhs_at(2);
     const int nf = B.n_fwd;
     for (int e0 = 0; e0 < nf; e0 += SOLVE_PF) {
         double v[SOLVE_PF]; int ins[SOLVE_PF];
@@ -298,14 +303,16 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
             if (c & DB_I_ENDROW) {
                 x[(int64_t)row * ld] = acc;
                 ++row;
-                acc = 0.0;
-                if (row < n) for (int q = 0; q < rhs.nvec; ++q) acc = fma(rhs.coef[q], rv[q][(int64_t)row * ld], acc);
+                acc = r1; r1 = r2; r2 = rhs_at(row + 2);
             }
         }
     }
-    // ---- backward substitution
+    // ---- backward substitution (the forward result of the next two rows is prefetched the same way)
     row = n - 1;
     double inv = 0.0;
+    double y0 = x[(int64_t)row * ld];
+    double y1 = (row >= 1) ? x[(int64_t)(row - 1) * ld] : 0.0;
+    double y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
     const int nE = B.n_entries;
     for (int e0 = nf; e0 < nE; e0 += SOLVE_PF) {
         double v[SOLVE_PF]; int ins[SOLVE_PF];
@@ -317,9 +324,13 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
             const int c = ins[j];
-            if (c & DB_I_DIAG) { inv = v[j]; acc = x[(int64_t)row * ld]; }
+            if (c & DB_I_DIAG) { inv = v[j]; acc = y0; }
             else if (!(c & DB_I_NOP)) acc = fma(-v[j], x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
-            if (c & DB_I_ENDROW) { x[(int64_t)row * ld] = acc * inv; --row; }
+            if (c & DB_I_ENDROW) {
+                x[(int64_t)row * ld] = acc * inv;
+                --row;
+                y0 = y1; y1 = y2; y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
+            }
         }
     }
 }
