@@ -75,3 +75,52 @@ extern "C" int db_absmax(const double* x, int64_t count, double* out, void* stre
     DB_LAUNCH(k_absmax, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), stream, x, count, reinterpret_cast<unsigned long long*>(out));
     return db_check_launch("absmax");
 }
+
+
+// advective CFL frequency maximum
+struct CflArgs { const double* u[3]; const double* idx[3]; int ncomp; int64_t g0, g1, g2; };
+
+__global__ void k_cfl_max(CflArgs a, unsigned long long* __restrict__ out)
+{
+    DB_SMEM(double, red);
+    const int64_t total = a.g0 * a.g1 * a.g2;
+    double m = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i2 = e % a.g2; const int64_t q = e / a.g2;
+        const int64_t i1 = q % a.g1; const int64_t i0 = q / a.g1;
+        const int64_t ix[3] = {i0, i1, i2};
+        double f = 0.0;
+        for (int c = 0; c < a.ncomp; ++c) f += fabs(a.u[c][e]) * a.idx[c][ix[3 - a.ncomp + c]];
+        m = (f > m) ? f : m;
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { double o = red[threadIdx.x + s]; if (o > red[threadIdx.x]) red[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long bits; double v = red[0];
+        memcpy(&bits, &v, sizeof(bits));
+#ifdef DB_EMU
+        if (bits > *out) *out = bits;
+#else
+        atomicMax(out, bits);
+#endif
+    }
+}
+
+extern "C" int db_cfl_max(const double* const* u, const double* const* inv_dx, int32_t ncomp, int64_t g0, int64_t g1, int64_t g2,
+                          double* out, void* stream)
+{
+    if (ncomp < 1 || ncomp > 3) { db_set_error("cfl_max: ncomp must be 1..3"); return 1; }
+    CflArgs a;
+    for (int c = 0; c < 3; ++c) { a.u[c] = (c < ncomp) ? u[c] : nullptr; a.idx[c] = (c < ncomp) ? inv_dx[c] : nullptr; }
+    a.ncomp = ncomp; a.g0 = g0; a.g1 = g1; a.g2 = g2;
+    const int64_t total = g0 * g1 * g2;
+    if (total <= 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    DB_LAUNCH(k_cfl_max, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), stream, a, reinterpret_cast<unsigned long long*>(out));
+    return db_check_launch("cfl_max");
+}

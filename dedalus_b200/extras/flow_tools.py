@@ -1,0 +1,132 @@
+"""CFL timestep controller and global flow properties evaluated on the device
+(reference extras/flow_tools.py:64-233; operators.AdvectiveCFL core/operators.py:4342-4400).
+
+The advective frequency  sum_i |u_i| / dx_i  is reduced to its grid maximum by one kernel (csrc/core.cu
+k_cfl_max) on the dealiased grid values of the velocity, every `cadence` iterations at the start of the step
+(the reference evaluates its dictionary handler inside stage 1, core/timesteppers.py:607-608); only the scalar
+maximum crosses to the host (and, on several GPUs, an all-reduce of one double)."""
+import ctypes as C
+import numpy as np
+
+
+class CFL:
+    def __init__(self, solver, initial_dt, cadence=1, safety=1., max_dt=np.inf, min_dt=0., max_change=np.inf,
+                 min_change=0., threshold=0.):
+        self.solver = solver
+        self.stored_dt = initial_dt
+        self.cadence = cadence
+        self.safety = safety
+        self.max_dt, self.min_dt = max_dt, min_dt
+        self.max_change, self.min_change = max_change, min_change
+        self.threshold = threshold
+        self.velocities = []
+        self.max_freq = None
+        solver.step_hooks.append(self._on_step)
+
+    def add_velocity(self, velocity):
+        if len(velocity.tensorsig) != 1:
+            raise ValueError("Velocity must be a vector")
+        self.velocities.append(velocity)
+
+    # called by the solver at the start of every step, state in coefficient space on the device
+    def _on_step(self, solver):
+        if solver.iteration % self.cadence != 0 or not self.velocities:
+            return
+        import torch
+        from ..lib import get_lib, current_stream
+        from ..transforms import cached_plan
+        lib = get_lib()
+        out = torch.zeros(1, dtype=torch.float64, device=solver.device)
+        for u in self.velocities:
+            dist = u.dist
+            scales = u.dealias
+            # grid values of every component at dealias scales (own buffers: the state stays in coefficient space)
+            g = self._to_grid(u)
+            dim = dist.dim
+            comps = [g[i] for i in range(g.shape[0])]
+            inv = []
+            for i, coord in enumerate(u.tensorsig[0].coords):
+                ax = dist.get_axis(coord)
+                b = u.bases[ax]
+                dx = self._cfl_spacing(b, scales[ax])
+                sl = dist.grid_local_slice(ax, b, scales[ax])
+                inv.append(torch.from_numpy(np.ascontiguousarray(1.0 / np.abs(dx[sl]))).to(solver.device))
+            shape = [1, 1, 1]
+            gs = list(comps[0].shape)
+            shape[3 - len(gs):] = gs
+            up = (C.c_void_p * len(comps))(*[c.data_ptr() for c in comps])
+            ip = (C.c_void_p * len(inv))(*[t.data_ptr() for t in inv])
+            lib.call("db_cfl_max", up, ip, len(comps), shape[0], shape[1], shape[2], out.data_ptr(), current_stream())
+        if solver.dist.size > 1:
+            import torch.distributed as td
+            td.all_reduce(out, op=td.ReduceOp.MAX)
+        self.max_freq = out       # read lazily in compute_timestep (one host sync every `cadence` steps)
+
+    @staticmethod
+    def _cfl_spacing(basis, dealias):
+        """Effective grid spacing used by the reference's CartesianAdvectiveCFL.cfl_spacing (core/basis.py:6083-6104)."""
+        from ..basis import Jacobi, RealFourier, ComplexFourier
+        N = basis.grid_size(dealias)
+        if isinstance(basis, Jacobi) and basis.a == -0.5 and basis.b == -0.5:
+            theta = np.pi * (np.arange(N) + 0.5) / N
+            return dealias * basis.COV.stretch * np.sin(theta) * np.pi / N
+        if isinstance(basis, (RealFourier, ComplexFourier)):
+            return np.full(N, dealias * (2 * np.pi / N) * basis.COV.stretch)
+        grid = basis.global_grid(dealias)
+        return np.gradient(grid, edge_order=2) * dealias
+
+    def _to_grid(self, u):
+        import torch
+        tmp = u.copy_device_to_grid()
+        return tmp
+
+    def compute_timestep(self):
+        """Same update rule as the reference (flow_tools.py:191-214)."""
+        iteration = self.solver.iteration
+        if (iteration - 1) % self.cadence == 0:
+            if (iteration - 1) <= self.solver.initial_iteration or self.max_freq is None:
+                return self.stored_dt
+            max_global_freq = float(self.max_freq.item())
+            dt = np.inf if max_global_freq == 0. else 1 / max_global_freq
+            dt *= self.safety
+            dt = min(dt, self.max_dt, self.max_change * self.stored_dt)
+            dt = max(dt, self.min_dt, self.min_change * self.stored_dt)
+            if abs(dt - self.stored_dt) > self.threshold * self.stored_dt:
+                self.stored_dt = dt
+        return self.stored_dt
+
+    compute_dt = compute_timestep
+
+
+class GlobalFlowProperty:
+    """Scalar reductions of grid-space quantities (reference flow_tools.py:64-130): max / min / mean of a field."""
+
+    def __init__(self, solver, cadence=1):
+        self.solver = solver
+        self.cadence = cadence
+        self.properties = {}
+
+    def add_property(self, field, name):
+        self.properties[name] = field
+
+    def _grid(self, name):
+        f = self.properties[name]
+        if not hasattr(f, 'copy_device_to_grid'):
+            raise NotImplementedError("Only fields are supported as flow properties on the hot path.")
+        return f.copy_device_to_grid()
+
+    def max(self, name):
+        import torch
+        v = self._grid(name).max()
+        if self.solver.dist.size > 1:
+            import torch.distributed as td
+            td.all_reduce(v, op=td.ReduceOp.MAX)
+        return float(v.item())
+
+    def min(self, name):
+        import torch
+        v = self._grid(name).min()
+        if self.solver.dist.size > 1:
+            import torch.distributed as td
+            td.all_reduce(v, op=td.ReduceOp.MIN)
+        return float(v.item())

@@ -165,6 +165,17 @@ class Field(Operand):
         self.preset_layout(layout)
         np.copyto(self.data, value)
 
+    def copy_device_to_grid(self):
+        """Grid values (dealias scales) of this field as a NEW device tensor; the field itself is left untouched."""
+        tmp = Field(self.dist, bases=tuple(b for b in self.bases if b is not None), tensorsig=self.tensorsig, dtype=self.dtype)
+        self.dist._fields.pop()
+        if self.layout != 'c':
+            self.change_layout('c')
+        tmp.scales = self.dealias
+        tmp.set_device_data(self.device_data().clone(), 'c')
+        tmp.change_layout('g')
+        return tmp.device_data()
+
     def copy(self):
         out = Field(self.dist, bases=tuple(b for b in self.bases if b is not None), tensorsig=self.tensorsig, dtype=self.dtype)
         out.preset_scales(self.scales)

@@ -74,6 +74,7 @@ SIGNATURES = {
     "db_transpose_pack_rev": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
     "db_transpose_unpack_rev": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
     "db_absmax": (C.c_int, [vp, i64, vp, vp]),
+    "db_cfl_max": (C.c_int, [C.POINTER(vp), C.POINTER(vp), i32, i64, i64, i64, vp, vp]),
 }
 
 

@@ -201,6 +201,7 @@ class InitialValueSolver:
         self.total_modes = sum(int(c.valid_cols.sum()) * len(c.groups) for c in self.builder.classes.values())
         self.setup_time = time.time() - t0
         self._device_ready = False
+        self.step_hooks = []        # callables(solver) run at the start of each step (CFL, flow properties)
         self.prof = None            # set to a list to collect (name, start_event, end_event, bytes) per launch
         self._lhs_key = None
         self._ts_iteration = 0
@@ -294,11 +295,37 @@ class InitialValueSolver:
             self.run_time_start = self._sync_clock()
             self.warmup_time = self.run_time_start - self.start_time
         self.dt = dt
+        if self.step_hooks:
+            self._prepare_hooks()
         if self.timestepper_class.kind == "rk":
             self._step_rk(dt)
         else:
             self._step_multistep(dt)
+        # Hermitian-symmetry enforcement for real variables, same cadence rule as the reference (solvers.py:704-708)
+        if self.enforce_real_cadence and np.issubdtype(self.dtype, np.floating):
+            if self.iteration % self.enforce_real_cadence < getattr(self.timestepper_class, 'steps', 1):
+                self.enforce_hermitian_symmetry(self.state)
         self.iteration += 1
+
+    def _prepare_hooks(self):
+        """Scheduled evaluations at the start of the step (the reference fires its handlers in stage 1 of the step,
+        core/timesteppers.py:150-151, 607-608): state is brought to coefficient space first."""
+        for v in self.state:
+            v.change_layout('c')
+        for hook in self.step_hooks:
+            hook(self)
+
+    def enforce_hermitian_symmetry(self, fields):
+        """Transform fields to the dealiased grid and back (reference solvers.py:675-681)."""
+        for f in fields:
+            if all(b is None for b in f.bases):
+                continue
+            try:
+                f.change_scales(f.dealias)
+                f.change_layout('g')
+                f.change_layout('c')
+            except NotImplementedError:
+                continue     # partially-based fields on a distributed mesh: not supported yet
 
     def _sync_clock(self):
         import torch

@@ -194,6 +194,13 @@ int db_transpose_unpack_rev(const double* recvbuf, double* out, int64_t B, int64
 /* max |x| reduction (CFL / flow properties; extras/flow_tools.py:33-37 before the Allreduce) */
 int db_absmax(const double* x, int64_t count, double* out, void* stream);
 
+/* Advective CFL frequency: out = max over grid points of sum_i |u_i| * inv_dx_i[index along axis i]
+ * (operators.AdvectiveCFL, core/operators.py:4342-4400, basis.py:6078-6112, followed by the max of
+ * extras/flow_tools.py:191-214).  u_i: ncomp grid arrays of shape (g0, g1, g2) (use 1 for missing axes);
+ * inv_dx_i: device vectors of the local inverse grid spacings along axis i.  `out` must be zero-initialised. */
+int db_cfl_max(const double* const* u, const double* const* inv_dx, int32_t ncomp, int64_t g0, int64_t g1, int64_t g2,
+               double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

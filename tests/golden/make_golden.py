@@ -223,3 +223,45 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["transforms", "ivps"]
     if "transforms" in which: gen_transforms()
     if "ivps" in which: gen_ivps()
+
+
+def gen_cfl():
+    """2-D RB with the reference CFL controller (extras/flow_tools.py:139-233): dt sequence and final state."""
+    Lx, Lz, Ra, Pr, Nh, Nz = 4, 1, 2e6, 1, 32, 16
+    coords = d3.CartesianCoordinates('x', 'z')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    xb = d3.RealFourier(coords['x'], size=Nh, bounds=(0, Lx), dealias=3/2)
+    zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, Lz), dealias=3/2)
+    p = dist.Field(name='p', bases=(xb, zb)); b = dist.Field(name='b', bases=(xb, zb)); u = dist.VectorField(coords, name='u', bases=(xb, zb))
+    tau_p = dist.Field(name='tau_p'); tau_b1 = dist.Field(name='tau_b1', bases=xb); tau_b2 = dist.Field(name='tau_b2', bases=xb)
+    tau_u1 = dist.VectorField(coords, name='tau_u1', bases=xb); tau_u2 = dist.VectorField(coords, name='tau_u2', bases=xb)
+    kappa = (Ra * Pr)**(-1/2); nu = (Ra / Pr)**(-1/2)
+    x, z = dist.local_grids(xb, zb); ex, ez = coords.unit_vector_fields(dist)
+    lift_basis = zb.derivative_basis(1); lift = lambda A: d3.Lift(A, lift_basis, -1)
+    grad_u = d3.grad(u) + ez*lift(tau_u1); grad_b = d3.grad(b) + ez*lift(tau_b1)
+    problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
+    problem.add_equation("trace(grad_u) + tau_p = 0")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*ez + lift(tau_u2) = - u@grad(u)")
+    problem.add_equation("b(z=0) = Lz"); problem.add_equation("u(z=0) = 0"); problem.add_equation("b(z=Lz) = 0"); problem.add_equation("u(z=Lz) = 0")
+    problem.add_equation("integ(p) = 0")
+    solver = problem.build_solver(d3.RK222)
+    b.fill_random('g', seed=42, distribution='normal', scale=1e-3); b['g'] *= z * (Lz - z); b['g'] += Lz - z
+    u['g'][0] = 3.0 * np.sin(2 * np.pi * x / Lx) * z * (Lz - z) * 4
+    u['g'][1] = 1.0 * np.cos(2 * np.pi * x / Lx) * np.sin(np.pi * z / Lz)
+    CFL = d3.CFL(solver, initial_dt=0.01, cadence=2, safety=0.5, threshold=0.05, max_change=1.5, min_change=0.5, max_dt=0.05)
+    CFL.add_velocity(u)
+    out = dict(b0_c=b['c'].copy(), u0_c=u['c'].copy())
+    dts = []
+    for i in range(12):
+        tstep = CFL.compute_timestep()
+        dts.append(tstep)
+        solver.step(tstep)
+    out['dts'] = np.array(dts)
+    out['b_c'] = b['c'].copy(); out['u_c'] = u['c'].copy()
+    np.savez_compressed(HERE / "rb2d_cfl.npz", **out)
+    print("cfl dts", dts)
+
+
+if __name__ == "__main__" and "cfl" in sys.argv[1:]:
+    gen_cfl()

@@ -39,3 +39,20 @@ def test_kdv(golden, prefix):
         solver.step(float(g[prefix + "dt"]))
     assert np.allclose(pk['u']['c'], g[prefix + "u_c"], **TOL)
     assert np.allclose(pk['u']['g'], g[prefix + "u_g"], **TOL)
+
+
+def test_cfl_controller_matches_reference(golden):
+    """dt sequence of the CFL controller and the resulting state vs the reference (extras/flow_tools.py:139-233)."""
+    g = golden("rb2d_cfl.npz")
+    pb = examples.rayleigh_benard(dim=2, Nh=32, Nz=16, Rayleigh=2e6)
+    solver = pb['problem'].build_solver(d3.RK222)
+    pb['b']['c'] = g['b0_c']; pb['u']['c'] = g['u0_c']
+    cfl = d3.CFL(solver, initial_dt=0.01, cadence=2, safety=0.5, threshold=0.05, max_change=1.5, min_change=0.5, max_dt=0.05)
+    cfl.add_velocity(pb['u'])
+    dts = []
+    for i in range(len(g['dts'])):
+        dt = cfl.compute_timestep(); dts.append(dt)
+        solver.step(dt)
+    assert np.allclose(dts, g['dts'], rtol=1e-9, atol=0), (dts, g['dts'])
+    assert np.allclose(pb['b']['c'], g['b_c'], **TOL)
+    assert np.allclose(pb['u']['c'], g['u_c'], **TOL)
