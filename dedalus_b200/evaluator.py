@@ -285,6 +285,9 @@ class RHSPlan:
         dev = self.device
         last = dim - 1
         # ---- phase 1: backward transforms along the prefix tree
+        for f in {id(k[0]): k[0] for k in self.input_keys}.values():
+            if f.layout != 'c':
+                f.change_layout('c')          # non-state fields (forcings, NCCs) may have been set on the grid
         bufs = [None] * dim
         for lvl, ax in enumerate(self.axes_order):
             nodes = self.levels[lvl]

@@ -56,3 +56,26 @@ def test_cfl_controller_matches_reference(golden):
     assert np.allclose(dts, g['dts'], rtol=1e-9, atol=0), (dts, g['dts'])
     assert np.allclose(pb['b']['c'], g['b_c'], **TOL)
     assert np.allclose(pb['u']['c'], g['u_c'], **TOL)
+
+
+@pytest.mark.parametrize("timestepper", list(d3.schemes.keys()) + ["RKGFY"])
+def test_heat_periodic_every_timestepper(timestepper):
+    """Reference integration test tests/test_ivp.py:18-49 (1-D heat equation, every scheme in `schemes`, 20 steps,
+    analytic solution), here on the real Fourier basis: dt(u) - dx(dx(u)) = F, F = sin(x)."""
+    from dedalus_b200 import timesteppers as ts
+    scheme = ts.schemes.get(timestepper, getattr(ts, timestepper))
+    c = d3.Coordinate('x')
+    d = d3.Distributor(c, dtype=np.float64)
+    b = d3.RealFourier(c, size=8, bounds=(0, 2 * np.pi), dealias=1)
+    x = d.local_grid(b, scale=1)
+    u = d.Field(bases=b); F = d.Field(bases=b)
+    F['g'] = np.sin(x)
+    dx = lambda A: d3.Differentiate(A, c)
+    problem = d3.IVP([u], namespace=locals())
+    problem.add_equation("dt(u) - dx(dx(u)) = F")
+    solver = problem.build_solver(scheme)
+    for i in range(20):
+        solver.step(1e-5)
+    amp = 1 - np.exp(-solver.sim_time)
+    u.change_scales(1)
+    assert np.allclose(u['g'], amp * np.sin(x))
