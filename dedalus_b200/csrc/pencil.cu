@@ -289,13 +289,20 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     int row = 0;
     double acc = rhs_at(0), r1 = rhs_at(1), r2 = rhs_at(2);
     const int nf = B.n_fwd;
+    const int nE = B.n_entries;
+    // software pipeline: the factor values / instructions of chunk c+1 are in flight while chunk c is consumed
+    double vn[SOLVE_PF]; int in_[SOLVE_PF];
+#define SOLVE_LOAD(E0, END)                                                                         \
+    _Pragma("unroll") for (int j = 0; j < SOLVE_PF; ++j) {                                          \
+        const int e = (E0) + j;                                                                     \
+        if (e < (END)) { vn[j] = f[(int64_t)e * ld]; in_[j] = prog[e]; } else { vn[j] = 0.0; in_[j] = DB_I_NOP; } \
+    }
+    SOLVE_LOAD(0, nf)
     for (int e0 = 0; e0 < nf; e0 += SOLVE_PF) {
         double v[SOLVE_PF]; int ins[SOLVE_PF];
 #pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) {
-            const int e = e0 + j;
-            if (e < nf) { v[j] = f[(int64_t)e * ld]; ins[j] = prog[e]; } else { v[j] = 0.0; ins[j] = DB_I_NOP; }
-        }
+        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; ins[j] = in_[j]; }
+        SOLVE_LOAD(e0 + SOLVE_PF, nf)
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
             const int c = ins[j];
@@ -313,14 +320,12 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     double y0 = x[(int64_t)row * ld];
     double y1 = (row >= 1) ? x[(int64_t)(row - 1) * ld] : 0.0;
     double y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
-    const int nE = B.n_entries;
+    SOLVE_LOAD(nf, nE)
     for (int e0 = nf; e0 < nE; e0 += SOLVE_PF) {
         double v[SOLVE_PF]; int ins[SOLVE_PF];
 #pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) {
-            const int e = e0 + j;
-            if (e < nE) { v[j] = f[(int64_t)e * ld]; ins[j] = prog[e]; } else { v[j] = 0.0; ins[j] = DB_I_NOP; }
-        }
+        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; ins[j] = in_[j]; }
+        SOLVE_LOAD(e0 + SOLVE_PF, nE)
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
             const int c = ins[j];
@@ -333,6 +338,7 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
             }
         }
     }
+#undef SOLVE_LOAD
 }
 
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,

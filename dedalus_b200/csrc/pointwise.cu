@@ -6,6 +6,7 @@
 // tile of all inputs in shared memory (every input element read from HBM exactly once, coalesced), evaluates
 // all outputs from it and writes each output once.
 #include "db_common.cuh"
+#include <cstdint>
 
 #define PW_TILE 256
 
@@ -36,22 +37,60 @@ k_pointwise(const double* __restrict__ in, double* __restrict__ out, int64_t npo
     }
 }
 
+// two points per thread, 128-bit global and shared accesses (npoints even, 16-byte aligned arrays)
+__global__ void __launch_bounds__(PW_TILE)
+k_pointwise_v2(const double* __restrict__ in, double* __restrict__ out, int64_t npoints, int n_in, int n_out,
+               const int32_t* __restrict__ term_ptr, const double* __restrict__ coef,
+               const int32_t* __restrict__ fac_ptr, const int32_t* __restrict__ fac)
+{
+    DB_SMEM(double, tile);                         // [n_in][2*PW_TILE]
+    double2* tile2 = reinterpret_cast<double2*>(tile);
+    const int64_t np2 = npoints >> 1;
+    for (int64_t q0 = (int64_t)blockIdx.x * PW_TILE; q0 < np2; q0 += (int64_t)gridDim.x * PW_TILE) {
+        const int64_t q = q0 + threadIdx.x;
+        const bool live = q < np2;
+        for (int i = 0; i < n_in; ++i)
+            tile2[i * PW_TILE + threadIdx.x] = live ? reinterpret_cast<const double2*>(in + (int64_t)i * npoints)[q] : make_double2(0.0, 0.0);
+        if (live) {
+            for (int o = 0; o < n_out; ++o) {
+                double a0 = 0.0, a1 = 0.0;
+                for (int t = term_ptr[o]; t < term_ptr[o + 1]; ++t) {
+                    double p0 = coef[t], p1 = p0;
+                    for (int f = fac_ptr[t]; f < fac_ptr[t + 1]; ++f) {
+                        const double2 v = tile2[fac[f] * PW_TILE + threadIdx.x];
+                        p0 *= v.x; p1 *= v.y;
+                    }
+                    a0 += p0; a1 += p1;
+                }
+                reinterpret_cast<double2*>(out + (int64_t)o * npoints)[q] = make_double2(a0, a1);
+            }
+        }
+    }
+}
+
 extern "C" int db_pointwise(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
                             const int32_t* term_ptr, const double* coef, const int32_t* fac_ptr, const int32_t* fac, int32_t nfac_total,
                             void* stream)
 {
     (void)nfac_total;
     if (npoints <= 0 || n_out <= 0) return 0;
-    size_t smem = (size_t)n_in * PW_TILE * sizeof(double);
+    const bool vec = (npoints % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    size_t smem = (size_t)n_in * PW_TILE * sizeof(double) * (vec ? 2 : 1);
     if (smem > (size_t)DB_MAX_SMEM) { db_set_error("pointwise: too many inputs (%d)", n_in); return 1; }
-    int64_t blocks = (npoints + PW_TILE - 1) / PW_TILE;
+    const int64_t items = vec ? npoints / 2 : npoints;
+    int64_t blocks = (items + PW_TILE - 1) / PW_TILE;
     const int64_t cap = 148 * 8;
     if (blocks > cap) blocks = cap;
 #ifndef DB_EMU
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_pointwise, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM); attr = true; }
+    if (!attr) {
+        cudaFuncSetAttribute(k_pointwise, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_pointwise_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        attr = true;
+    }
 #endif
-    DB_LAUNCH(k_pointwise, dim3((unsigned)blocks), dim3(PW_TILE), smem, stream, in, out, npoints, n_in, n_out, term_ptr, coef, fac_ptr, fac);
+    if (vec) DB_LAUNCH(k_pointwise_v2, dim3((unsigned)blocks), dim3(PW_TILE), smem, stream, in, out, npoints, n_in, n_out, term_ptr, coef, fac_ptr, fac);
+    else DB_LAUNCH(k_pointwise, dim3((unsigned)blocks), dim3(PW_TILE), smem, stream, in, out, npoints, n_in, n_out, term_ptr, coef, fac_ptr, fac);
     return db_check_launch("pointwise");
 }
 

@@ -200,8 +200,23 @@ class FastChebyshevTransform:
             sol, nsol = self._diags(('solve', deriv), gdata.device)
         else:
             sol, nsol = None, 0
-        get_lib().call("db_cheb_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner,
-                       _dptr(pre), npre, _dptr(sol), nsol, _stream())
+        if inner == 1 and (npre or nsol):
+            # contiguous lines: run the serial banded recurrence in its own one-thread-per-line kernel, then the
+            # plain transform (keeps the recurrence off the FFT kernel's critical path)
+            tmp = self._scratch(cdata)
+            get_lib().call("db_band_lines", _dptr(cdata), _dptr(tmp), outer, self.M, _dptr(pre), npre, _dptr(sol), nsol, _stream())
+            get_lib().call("db_cheb_backward", plan.ref(), _dptr(tmp), _dptr(gdata), outer, self.M, inner, None, 0, None, 0, _stream())
+        else:
+            get_lib().call("db_cheb_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner,
+                           _dptr(pre), npre, _dptr(sol), nsol, _stream())
+
+    def _scratch(self, like):
+        key = (tuple(like.shape), str(like.device))
+        t = self._dev.get(('scratch',) + key)
+        if t is None:
+            t = _torch().empty_like(like)
+            self._dev[('scratch',) + key] = t
+        return t
 
 
 @register_transform(Jacobi, 'b200_matrix')

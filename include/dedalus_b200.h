@@ -69,6 +69,14 @@ int db_cheb_forward(const db_fft_plan* plan, const double* g, double* c, int64_t
 int db_cheb_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
                      const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream);
 
+/* Banded coefficient-space work along CONTIGUOUS lines (inner == 1), used ahead of db_cheb_backward when a spectral
+ * derivative / ultraspherical back-conversion is fused in: out = solve_upper(solve_diags, apply(pre_diags, in)).
+ * One thread per line with the line staged in shared memory: decouples the O(n) serial recurrence from the FFT
+ * kernel's CTA shape (core/transforms.py:876-884 solve_upper_sparse; tools/linalg.pyx:20-82).
+ * Diagonal storage as in db_cheb_backward (row 0 of solve_diags = reciprocal diagonal). */
+int db_band_lines(const double* in, double* out, int64_t lines, int32_t n,
+                  const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream);
+
 /* Dense matrix transform along an axis: out(o, i, r) = sum_j mat[i][j] * in(o, j, r).
  * Replaces SeparableMatrixTransform -> apply_dense (core/transforms.py:54-75, tools/array.py:104-129). */
 int db_mmt_apply(const double* mat, int32_t m, int32_t n, const double* in, double* out, int64_t outer, int64_t inner, void* stream);

@@ -81,7 +81,12 @@ def test_pencil_kernels_match_interpreters():
 def test_pointwise_program():
     lib = E.emu()
     rng = np.random.default_rng(2)
-    npts, nin = 1000, 7
+    for npts in (1000, 999):        # vectorised (even) and scalar (odd) kernels
+        _check_pointwise(lib, rng, npts)
+
+
+def _check_pointwise(lib, rng, npts):
+    nin = 7
     x = rng.standard_normal((nin, npts))
     # out0 = -x0*x3 - x1*x4 - x2*x5 ; out1 = 2*x6*x6*x0 + 0.5*x1
     term_ptr = _i32([0, 3, 5]); coef = np.array([-1.0, -1.0, -1.0, 2.0, 0.5])
