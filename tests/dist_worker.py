@@ -10,10 +10,16 @@ import torch.distributed as dist
 
 
 def main():
-    dist.init_process_group("gloo")
+    backend = os.environ.get("DB_DIST_BACKEND", "gloo")
+    if backend == "nccl":
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+        from emu import emu_lib as E
+        E.install()                      # CPU run: test-only kernel emulation
     rank, world = dist.get_rank(), dist.get_world_size()
-    from emu import emu_lib as E
-    E.install()
     import dedalus_b200 as d3
     from dedalus_b200 import examples
     which = sys.argv[1] if len(sys.argv) > 1 else "rb3d_8.npz"
@@ -37,7 +43,7 @@ def main():
     b.change_scales(1)
     _ = b['g']
     ok = ok and bool(np.allclose(b['c'], c0, rtol=1e-11, atol=1e-12))
-    flag = torch.tensor([1 if ok else 0])
+    flag = torch.tensor([1 if ok else 0], device='cuda' if backend == "nccl" else 'cpu')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
