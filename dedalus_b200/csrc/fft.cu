@@ -683,21 +683,25 @@ extern "C" int db_cheb_backward(const db_fft_plan* plan, const double* c, double
 // banded apply + upper back-substitution along contiguous lines: one warp per 32 lines
 // ---------------------------------------------------------------------------------------------------------
 #define BL_LINES 32
-__global__ void __launch_bounds__(BL_LINES)
+#define BL_THREADS 256
+__global__ void __launch_bounds__(BL_THREADS)
 k_band_lines(const double* __restrict__ in, double* __restrict__ out, int64_t lines, int n,
              const double* __restrict__ pre, int npre, const double* __restrict__ sol, int nsol)
 {
+    // 32 lines per CTA staged as sm[j][line] (conflict-free for both phases); all 8 warps move data, warp 0 runs the
+    // 32 independent recurrences (one per lane)
     DB_SMEM(double, sm);                       // [n][BL_LINES + 1]
     const int P = BL_LINES + 1;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = BL_THREADS / 32;
     const int64_t l0 = (int64_t)blockIdx.x * BL_LINES;
     const int nl = (lines - l0 < BL_LINES) ? (int)(lines - l0) : BL_LINES;
-    for (int l = 0; l < nl; ++l) {
-        const double* src = in + (l0 + l) * n;
-        for (int j = lane; j < n; j += BL_LINES) sm[j * P + l] = src[j];
+    for (int l = warp; l < nl; l += nw) {
+        const double* __restrict__ src = in + (l0 + l) * n;
+#pragma unroll 8
+        for (int j = lane; j < n; j += 32) sm[j * P + l] = src[j];
     }
     __syncthreads();
-    if (lane < nl) {
+    if (warp == 0 && lane < nl) {
         if (npre > 0) {                        // ascending, in place: row i only reads rows >= i
             for (int i = 0; i < n; ++i) {
                 double acc = 0.0;
@@ -722,9 +726,10 @@ k_band_lines(const double* __restrict__ in, double* __restrict__ out, int64_t li
         }
     }
     __syncthreads();
-    for (int l = 0; l < nl; ++l) {
-        double* dst = out + (l0 + l) * n;
-        for (int j = lane; j < n; j += BL_LINES) dst[j] = sm[j * P + l];
+    for (int l = warp; l < nl; l += nw) {
+        double* __restrict__ dst = out + (l0 + l) * n;
+#pragma unroll 8
+        for (int j = lane; j < n; j += 32) dst[j] = sm[j * P + l];
     }
 }
 
@@ -739,6 +744,6 @@ extern "C" int db_band_lines(const double* in, double* out, int64_t lines, int32
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_band_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM); attr = true; }
 #endif
-    DB_LAUNCH(k_band_lines, dim3((unsigned)blocks), dim3(BL_LINES), smem, stream, in, out, lines, n, pre_diags, pre_ndiag, solve_diags, solve_ndiag);
+    DB_LAUNCH(k_band_lines, dim3((unsigned)blocks), dim3(BL_THREADS), smem, stream, in, out, lines, n, pre_diags, pre_ndiag, solve_diags, solve_ndiag);
     return db_check_launch("band_lines");
 }

@@ -200,8 +200,8 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
     for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][s], acc);
     for (int e = 0; e < n_fwd; ++e) {
         const int c = prog[e];
-        if (!(c & DB_I_NOP)) acc = fma(-f[(int64_t)e * ld], x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
-        if (c & DB_I_ENDROW) {
+        if (c >= 0) acc = fma(-f[(int64_t)e * ld], x[c], acc);
+        else if (c == DB_I_END) {
             x[(int64_t)row * ld] = acc;
             ++row;
             acc = 0.0;
@@ -209,13 +209,16 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
         }
     }
     row = n - 1;
-    double inv = 0.0;
+    acc = x[(int64_t)row * ld];
     for (int e = n_fwd; e < n_entries; ++e) {
         const int c = prog[e];
         const double v = f[(int64_t)e * ld];
-        if (c & DB_I_DIAG) { inv = v; acc = x[(int64_t)row * ld]; }
-        else if (!(c & DB_I_NOP)) acc = fma(-v, x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
-        if (c & DB_I_ENDROW) { x[(int64_t)row * ld] = acc * inv; --row; }
+        if (c >= 0) acc = fma(-v, x[c], acc);
+        else if (c == DB_I_END) {
+            x[(int64_t)row * ld] = acc * v;
+            --row;
+            if (row >= 0) acc = x[(int64_t)row * ld];
+        }
     }
 }
 
@@ -265,7 +268,7 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 }
 
 #define SOLVE_THREADS 64
-#define SOLVE_PF 16
+#define SOLVE_PF 8
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs)
 {
@@ -274,67 +277,59 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
     if (s >= B.S) return;
     const int ld = B.ld, n = B.n;
-    const double* __restrict__ f = B.lu[lu_slot] + s;
-    const int32_t* __restrict__ prog = B.prog;
+    const double* __restrict__ fp = B.lu[lu_slot] + s;        // factor stream pointer, advances by ld per entry
+    const int32_t* __restrict__ pp = B.prog;                  // instruction stream pointer
     double* __restrict__ x = B.vec[x_slot] + s;
     const double* rv[16];
     for (int j = 0; j < 16; ++j) rv[j] = (j < rhs.nvec) ? B.vec[rhs.slot[j]] + s : nullptr;
-    // ---- forward substitution: flat stream, SOLVE_PF-deep register prefetch of the factor values; the RHS
-    //      combination of the next two rows is loaded ahead so its HBM latency is off the dependent chain
+    const int nvec = rhs.nvec;
     auto rhs_at = [&](int r) -> double {
         double a = 0.0;
-        if (r < n) for (int q = 0; q < rhs.nvec; ++q) a = fma(rhs.coef[q], rv[q][(int64_t)r * ld], a);
+        if (r < n) for (int q = 0; q < nvec; ++q) a = fma(rhs.coef[q], rv[q][(int64_t)r * ld], a);
         return a;
     };
+    // Both sections are padded to multiples of SOLVE_PF, so chunks are loaded without bounds checks.  The values and
+    // instructions of chunk c+1 are in flight while chunk c is consumed; RHS combinations / forward results of the
+    // next two rows are loaded ahead so that no HBM latency sits on the dependent chain.
+    double vn[SOLVE_PF]; int cn[SOLVE_PF];
+#define SOLVE_LOAD()                                                                       \
+    _Pragma("unroll") for (int j = 0; j < SOLVE_PF; ++j) { vn[j] = fp[0]; cn[j] = pp[j]; fp += ld; } \
+    pp += SOLVE_PF;
+    const int nchunk_f = B.n_fwd / SOLVE_PF, nchunk_b = (B.n_entries - B.n_fwd) / SOLVE_PF;
     int row = 0;
     double acc = rhs_at(0), r1 = rhs_at(1), r2 = rhs_at(2);
-    const int nf = B.n_fwd;
-    const int nE = B.n_entries;
-    // software pipeline: the factor values / instructions of chunk c+1 are in flight while chunk c is consumed
-    double vn[SOLVE_PF]; int in_[SOLVE_PF];
-#define SOLVE_LOAD(E0, END)                                                                         \
-    _Pragma("unroll") for (int j = 0; j < SOLVE_PF; ++j) {                                          \
-        const int e = (E0) + j;                                                                     \
-        if (e < (END)) { vn[j] = f[(int64_t)e * ld]; in_[j] = prog[e]; } else { vn[j] = 0.0; in_[j] = DB_I_NOP; } \
-    }
-    SOLVE_LOAD(0, nf)
-    for (int e0 = 0; e0 < nf; e0 += SOLVE_PF) {
-        double v[SOLVE_PF]; int ins[SOLVE_PF];
+    SOLVE_LOAD()
+    for (int ch = 0; ch < nchunk_f; ++ch) {
+        double v[SOLVE_PF]; int c[SOLVE_PF];
 #pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; ins[j] = in_[j]; }
-        SOLVE_LOAD(e0 + SOLVE_PF, nf)
+        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; c[j] = cn[j]; }
+        if (ch + 1 < nchunk_f + nchunk_b) { SOLVE_LOAD() }     // the last forward chunk already prefetches the backward stream
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
-            const int c = ins[j];
-            if (!(c & DB_I_NOP)) acc = fma(-v[j], x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
-            if (c & DB_I_ENDROW) {
+            if (c[j] >= 0) acc = fma(-v[j], x[c[j]], acc);
+            else if (c[j] == DB_I_END) {
                 x[(int64_t)row * ld] = acc;
                 ++row;
                 acc = r1; r1 = r2; r2 = rhs_at(row + 2);
             }
         }
     }
-    // ---- backward substitution (the forward result of the next two rows is prefetched the same way)
     row = n - 1;
-    double inv = 0.0;
-    double y0 = x[(int64_t)row * ld];
+    acc = x[(int64_t)row * ld];
     double y1 = (row >= 1) ? x[(int64_t)(row - 1) * ld] : 0.0;
     double y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
-    SOLVE_LOAD(nf, nE)
-    for (int e0 = nf; e0 < nE; e0 += SOLVE_PF) {
-        double v[SOLVE_PF]; int ins[SOLVE_PF];
+    for (int ch = 0; ch < nchunk_b; ++ch) {
+        double v[SOLVE_PF]; int c[SOLVE_PF];
 #pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; ins[j] = in_[j]; }
-        SOLVE_LOAD(e0 + SOLVE_PF, nE)
+        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; c[j] = cn[j]; }
+        if (ch + 1 < nchunk_b) { SOLVE_LOAD() }
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
-            const int c = ins[j];
-            if (c & DB_I_DIAG) { inv = v[j]; acc = y0; }
-            else if (!(c & DB_I_NOP)) acc = fma(-v[j], x[(int64_t)(c & DB_I_COLMASK) * ld], acc);
-            if (c & DB_I_ENDROW) {
-                x[(int64_t)row * ld] = acc * inv;
+            if (c[j] >= 0) acc = fma(-v[j], x[c[j]], acc);
+            else if (c[j] == DB_I_END) {
+                x[(int64_t)row * ld] = acc * v[j];
                 --row;
-                y0 = y1; y1 = y2; y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
+                acc = y1; y1 = y2; y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
             }
         }
     }
@@ -364,21 +359,22 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
     const int r1 = (r0 + MV_ROWS_PER_BLOCK < n) ? r0 + MV_ROWS_PER_BLOCK : n;
     const double* __restrict__ x = B.vec[x_slot] + s;
     const double* __restrict__ mono = B.mono + s;
-    if (ym_slot >= 0) {
-        double* __restrict__ y = B.vec[ym_slot] + s;
+    // two passes over the same rows (M then L); program pointers are copied to registers so the stores to y
+    // cannot force reloads of the descriptor
+    for (int which = 0; which < 2; ++which) {
+        const int slot = which ? yl_slot : ym_slot;
+        if (slot < 0) continue;
+        const int32_t* __restrict__ ptr = which ? B.l_ptr : B.m_ptr;
+        const int32_t* __restrict__ col = which ? B.l_col : B.m_col;
+        const int32_t* __restrict__ mon = which ? B.l_mono : B.m_mono;
+        const double* __restrict__ val = which ? B.l_val : B.m_val;
+        double* __restrict__ y = B.vec[slot] + s;
+        int t = ptr[r0];
         for (int i = r0; i < r1; ++i) {
+            const int t1 = ptr[i + 1];
             double acc = 0.0;
-            for (int t = B.m_ptr[i]; t < B.m_ptr[i + 1]; ++t)
-                acc = fma(B.m_val[t] * mono[(int64_t)B.m_mono[t] * ld], x[(int64_t)B.m_col[t] * ld], acc);
-            y[(int64_t)i * ld] = acc;
-        }
-    }
-    if (yl_slot >= 0) {
-        double* __restrict__ y = B.vec[yl_slot] + s;
-        for (int i = r0; i < r1; ++i) {
-            double acc = 0.0;
-            for (int t = B.l_ptr[i]; t < B.l_ptr[i + 1]; ++t)
-                acc = fma(B.l_val[t] * mono[(int64_t)B.l_mono[t] * ld], x[(int64_t)B.l_col[t] * ld], acc);
+            for (; t < t1; ++t)
+                acc = fma(val[t] * mono[(int64_t)mon[t] * ld], x[(int64_t)col[t] * ld], acc);
             y[(int64_t)i * ld] = acc;
         }
     }

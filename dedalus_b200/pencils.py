@@ -449,27 +449,34 @@ def compile_batch(batch, a0, b0):
     F = batch.symbolic_lu()
     prog = BatchProgram()
     prog.n, prog.S = n, batch.S
-    # ---- entry numbering in solve-stream order + flat instruction stream (see include/dedalus_b200.h DB_I_*)
-    ENDROW, DIAG, NOP = 0x40000000, 0x20000000, 0x10000000
+    # ---- entry numbering in solve-stream order + flat instruction stream (include/dedalus_b200.h):
+    #   code >= 0 : acc -= LU[e] * x[code]        (code = column * ld, the element offset of that row in the vector)
+    #   DB_I_END  : end of row. forward: x[row] = acc (LU value unused); backward: x[row] = acc * LU[e] (reciprocal pivot)
+    #   DB_I_SKIP : padding so that each section is a multiple of the kernels' prefetch depth
+    END, SKIP, PAD = -1, -2, 8
+    ld = ((batch.S + 31) // 32) * 32
+    prog.ld = ld
+    if (n + 1) * ld >= 2**31:
+        raise NotImplementedError("batch too large for 32-bit vector offsets")
     eid = -np.ones((n, n), dtype=np.int64)
     instr = []
     e = 0
     for i in range(n):
         js = np.nonzero(F[i, :i])[0]
-        if js.size == 0:
-            instr.append(np.array([NOP | ENDROW], dtype=np.int64)); e += 1      # placeholder entry (value stays 0)
-            continue
         eid[i, js] = e + np.arange(js.size)
-        code = js.astype(np.int64); code[-1] |= ENDROW
-        instr.append(code); e += js.size
+        instr.append(np.concatenate([js.astype(np.int64) * ld, [END]])); e += js.size + 1
+    pad = (-e) % PAD
+    instr.append(np.full(pad, SKIP, dtype=np.int64)); e += pad
     prog.n_fwd = e
     diag_eid = np.zeros(n, dtype=np.int32)
     for i in range(n - 1, -1, -1):
-        diag_eid[i] = e; eid[i, i] = e; e += 1
         js = i + 1 + np.nonzero(F[i, i + 1:])[0]
         eid[i, js] = e + np.arange(js.size)
-        code = np.concatenate([[i | DIAG], js]).astype(np.int64); code[-1] |= ENDROW
-        instr.append(code); e += js.size
+        e += js.size
+        diag_eid[i] = e; eid[i, i] = e; e += 1
+        instr.append(np.concatenate([js.astype(np.int64) * ld, [END]]))
+    pad = (-e) % PAD
+    instr.append(np.full(pad, SKIP, dtype=np.int64)); e += pad
     prog.nE = e
     prog.prog = np.concatenate(instr).astype(np.int32)
     assert len(prog.prog) == prog.nE

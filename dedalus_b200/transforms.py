@@ -200,7 +200,7 @@ class FastChebyshevTransform:
             sol, nsol = self._diags(('solve', deriv), gdata.device)
         else:
             sol, nsol = None, 0
-        if inner == 1 and (npre or nsol):
+        if inner == 1 and (npre or nsol) and self.M <= self.N:
             # contiguous lines: run the serial banded recurrence in its own one-thread-per-line kernel, then the
             # plain transform (keeps the recurrence off the FFT kernel's critical path)
             tmp = self._scratch(cdata)

@@ -140,16 +140,16 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
  * 4 launches (mat-vec, gather F, solve, scatter) however many classes / parity components the problem has, and small
  * batches (kx = 0 or ky = 0 pencils) run concurrently with the large ones instead of serialising on the stream.
  * `batches` is a DEVICE array of db_batch built once by the host; per-call arguments are slot indices.
- * The solve program is a flat instruction stream aligned with the LU value stream:
- *   prog[e] = column | DB_I_ENDROW (row finished after this entry) | DB_I_DIAG (entry is the reciprocal pivot)
- *                    | DB_I_NOP (placeholder of an empty row: value ignored)
+ * The solve program is a flat instruction stream aligned one-to-one with the LU value stream (forward rows
+ * 0..n-1, then backward rows n-1..0), each section padded to a multiple of 8 entries:
+ *   prog[e] >= 0       : acc -= LU[e] * x[prog[e]]      (prog[e] = column * ld: element offset of that row in a vector)
+ *   prog[e] == DB_I_END: row finished.  forward: x[row] = acc ; backward: x[row] = acc * LU[e] (reciprocal pivot)
+ *   prog[e] == DB_I_SKIP: padding
  * ------------------------------------------------------------------------------------------------------- */
 #define DB_MAX_VECS 24
 #define DB_MAX_LU 4
-#define DB_I_ENDROW 0x40000000
-#define DB_I_DIAG   0x20000000
-#define DB_I_NOP    0x10000000
-#define DB_I_COLMASK 0x0FFFFFFF
+#define DB_I_END  (-1)
+#define DB_I_SKIP (-2)
 typedef struct {
     int32_t n, S, ld, n_entries;
     int32_t n_fwd, n_bwd;

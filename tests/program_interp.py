@@ -32,31 +32,31 @@ def factor(prog, LU):
 
 
 def solve(prog, LU, rhs):
-    ENDROW, DIAG, NOP, MASK = 0x40000000, 0x20000000, 0x10000000, 0x0FFFFFFF
-    n = prog.n
+    END, SKIP = -1, -2
+    n, ld = prog.n, prog.ld
     y = np.array(rhs, dtype=float, copy=True)
     row = 0
     acc = y[0].copy()
     for e in range(prog.n_fwd):
         c = int(prog.prog[e])
-        if not (c & NOP):
-            acc = acc - LU[e] * y[c & MASK]
-        if c & ENDROW:
+        if c >= 0:
+            acc = acc - LU[e] * y[c // ld]
+        elif c == END:
             y[row] = acc
             row += 1
             if row < n:
                 acc = y[row].copy()
     row = n - 1
-    inv = None
+    acc = y[row].copy()
     for e in range(prog.n_fwd, prog.nE):
         c = int(prog.prog[e])
-        if c & DIAG:
-            inv = LU[e]; acc = y[row].copy()
-        elif not (c & NOP):
-            acc = acc - LU[e] * y[c & MASK]
-        if c & ENDROW:
-            y[row] = acc * inv
+        if c >= 0:
+            acc = acc - LU[e] * y[c // ld]
+        elif c == END:
+            y[row] = acc * LU[e]
             row -= 1
+            if row >= 0:
+                acc = y[row].copy()
     return y
 
 
