@@ -14,6 +14,12 @@
     type* name = reinterpret_cast<type*>(db_smem_raw)
 #endif
 
+#ifdef DB_EMU
+#define DB_LDCS(p) (*(p))
+#else
+#define DB_LDCS(p) __ldcs(p)           // streaming (evict-first) load: one-pass data must not displace reused lines
+#endif
+
 #include "../../include/dedalus_b200.h"
 
 // error plumbing (thread-compatible: one stream per rank, last error per process)

@@ -201,19 +201,19 @@ struct TileGeom {
 
 __device__ __forceinline__ TileGeom tile_geom(const FftArgs& a, int len, int cplx)
 {
+    // strided axis: grid = (tiles per outer slab, outer) so no division is needed; contiguous axis: grid.x = tile
     TileGeom g;
-    const int64_t tile = blockIdx.x;
     if (a.inner == 1) {
-        int64_t l0 = tile * a.T;
-        int64_t rem = a.outer - l0;
+        const int64_t l0 = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * a.T;
+        const int64_t rem = a.outer - l0;
         g.Tc = rem < a.T ? (int)rem : a.T;
         g.base = l0 * len * cplx;
         g.estride = cplx;
         g.lstride = (int64_t)len * cplx;
     } else {
-        int64_t o = tile / a.tiles_per_outer;
-        int64_t i0 = (tile - o * a.tiles_per_outer) * a.T;
-        int64_t rem = a.inner - i0;
+        const int64_t o = blockIdx.y;
+        const int64_t i0 = (int64_t)blockIdx.x * a.T;
+        const int64_t rem = a.inner - i0;
         g.Tc = rem < a.T ? (int)rem : a.T;
         g.base = (o * len * a.inner + i0) * cplx;
         g.estride = a.inner * cplx;
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
     const int cplx = is_cplx ? 2 : 1;
     const TileGeom gi = tile_geom(a, is_fwd ? n : M, cplx);
     const TileGeom go = tile_geom(a, is_fwd ? M : n, cplx);
+    if (gi.Tc <= 0) return;                       // padding block of a 2-D grid over contiguous lines
     const int Tmask = T - 1;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const double* __restrict__ gin = a.in;
@@ -639,10 +640,19 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
     a.T = T; a.TP = T + 1;
     a.lgT = 0; while ((1 << a.lgT) < T) ++a.lgT;
     a.cof_off = (int32_t)(buf_rows * a.TP);
-    int64_t tiles;
-    if (inner == 1) { a.tiles_per_outer = 0; tiles = (outer + T - 1) / T; }
-    else { a.tiles_per_outer = (inner + T - 1) / T; tiles = outer * a.tiles_per_outer; }
-    if (tiles > 2147483647LL) { db_set_error("%s: too many tiles", name); return 1; }
+    dim3 grid;
+    if (inner == 1) {
+        a.tiles_per_outer = 0;
+        const int64_t tiles = (outer + T - 1) / T;
+        const int64_t gx = tiles < 32768 ? tiles : 32768;
+        const int64_t gy = (tiles + gx - 1) / gx;
+        if (gy > 65535) { db_set_error("%s: too many tiles", name); return 1; }
+        grid = dim3((unsigned)gx, (unsigned)gy);
+    } else {
+        a.tiles_per_outer = (inner + T - 1) / T;
+        if (outer > 65535 || a.tiles_per_outer > 2147483647LL) { db_set_error("%s: outer extent %lld too large for a strided transform", name, (long long)outer); return 1; }
+        grid = dim3((unsigned)a.tiles_per_outer, (unsigned)outer);
+    }
 #ifndef DB_EMU
     static bool attr_set[6][2] = {{false, false}, {false, false}, {false, false}, {false, false}, {false, false}, {false, false}};
     if (!attr_set[KIND][direct ? 1 : 0]) {
@@ -651,8 +661,8 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
         attr_set[KIND][direct ? 1 : 0] = true;
     }
 #endif
-    if (direct) DB_LAUNCH((k_fft<KIND, true>), dim3((unsigned)tiles), dim3(FFT_THREADS), bytes, stream, a);
-    else DB_LAUNCH((k_fft<KIND, false>), dim3((unsigned)tiles), dim3(FFT_THREADS), bytes, stream, a);
+    if (direct) DB_LAUNCH((k_fft<KIND, true>), grid, dim3(FFT_THREADS), bytes, stream, a);
+    else DB_LAUNCH((k_fft<KIND, false>), grid, dim3(FFT_THREADS), bytes, stream, a);
     return db_check_launch(name);
 }
 

@@ -454,17 +454,23 @@ def compile_batch(batch, a0, b0):
     #   DB_I_END  : end of row. forward: x[row] = acc (LU value unused); backward: x[row] = acc * LU[e] (reciprocal pivot)
     #   DB_I_SKIP : padding so that each section is a multiple of the kernels' prefetch depth
     END, SKIP, PAD = -1, -2, 8
+    NEAR, W = 1 << 30, 64           # DB_I_NEAR, DB_SOLVE_WINDOW: recent rows are served from a shared-memory ring
     ld = ((batch.S + 31) // 32) * 32
     prog.ld = ld
-    if (n + 1) * ld >= 2**31:
-        raise NotImplementedError("batch too large for 32-bit vector offsets")
+    if (n + 1) * ld >= 2**30:
+        raise NotImplementedError("batch too large for 30-bit vector offsets")
+
+    def codes(row, js):
+        js = js.astype(np.int64)
+        near = np.abs(row - js) < W
+        return np.where(near, NEAR | (js % W), js * ld)
     eid = -np.ones((n, n), dtype=np.int64)
     instr = []
     e = 0
     for i in range(n):
         js = np.nonzero(F[i, :i])[0]
         eid[i, js] = e + np.arange(js.size)
-        instr.append(np.concatenate([js.astype(np.int64) * ld, [END]])); e += js.size + 1
+        instr.append(np.concatenate([codes(i, js), [END]])); e += js.size + 1
     pad = (-e) % PAD
     instr.append(np.full(pad, SKIP, dtype=np.int64)); e += pad
     prog.n_fwd = e
@@ -474,7 +480,7 @@ def compile_batch(batch, a0, b0):
         eid[i, js] = e + np.arange(js.size)
         e += js.size
         diag_eid[i] = e; eid[i, i] = e; e += 1
-        instr.append(np.concatenate([js.astype(np.int64) * ld, [END]]))
+        instr.append(np.concatenate([codes(i, js), [END]]))
     pad = (-e) % PAD
     instr.append(np.full(pad, SKIP, dtype=np.int64)); e += pad
     prog.nE = e

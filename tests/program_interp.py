@@ -32,17 +32,21 @@ def factor(prog, LU):
 
 
 def solve(prog, LU, rhs):
-    END, SKIP = -1, -2
+    END, SKIP, NEAR, W = -1, -2, 1 << 30, 64
     n, ld = prog.n, prog.ld
     y = np.array(rhs, dtype=float, copy=True)
+    ring = np.zeros((W,) + y.shape[1:])
+
+    def xval(c):
+        return ring[c & (W - 1)] if (c & NEAR) else y[c // ld]
     row = 0
     acc = y[0].copy()
     for e in range(prog.n_fwd):
         c = int(prog.prog[e])
         if c >= 0:
-            acc = acc - LU[e] * y[c // ld]
+            acc = acc - LU[e] * xval(c)
         elif c == END:
-            y[row] = acc
+            y[row] = acc; ring[row % W] = acc
             row += 1
             if row < n:
                 acc = y[row].copy()
@@ -51,9 +55,9 @@ def solve(prog, LU, rhs):
     for e in range(prog.n_fwd, prog.nE):
         c = int(prog.prog[e])
         if c >= 0:
-            acc = acc - LU[e] * y[c // ld]
+            acc = acc - LU[e] * xval(c)
         elif c == END:
-            y[row] = acc * LU[e]
+            y[row] = acc * LU[e]; ring[row % W] = y[row]
             row -= 1
             if row >= 0:
                 acc = y[row].copy()
