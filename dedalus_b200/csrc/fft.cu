@@ -170,8 +170,76 @@ __device__ void fft_pass(double2* buf, int nc, int TP, int lgT, int r, int L, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Compile-time specialised passes for the benchmark line lengths (tile width 16): every index, stride and twiddle
+// step is a constant, the per-thread butterfly loop is fully unrolled and the division bf / m is by a constant.
+// ---------------------------------------------------------------------------------------------------------
+template <bool INV, int NC, int L, int R>
+__device__ __forceinline__ void fft_pass_static(double2* buf, const double* __restrict__ tw)
+{
+    constexpr int m = L / R, nbf = NC / R, tstep = NC / L, TP = 17;
+    constexpr int ITER = (nbf * 16 + FFT_THREADS - 1) / FFT_THREADS;
+    const int t = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int bf = ty + 16 * it;
+        if ((nbf % 16 != 0) && bf >= nbf) break;
+        const int b = bf / m, k = bf - b * m;
+        double2* base = buf + (b * L + k) * TP + t;
+        double2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) v[q] = base[q * m * TP];
+        const int tk = tstep * k;
+        if (INV) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], ldtw(tw, tk * q));
+        }
+        if (R == 4) dft4<INV>(v);
+        else if (R == 2) dft2<INV>(v);
+        else if (R == 3) dft3<INV>(v);
+        else dftr<INV, R>(v, tw, NC);
+        if (!INV) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, tk * q));
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) base[q * m * TP] = v[q];
+    }
+}
+
+template <int NC, int L, int R, int... REST>
+__device__ __forceinline__ void static_dif(double2* buf, const double* tw)
+{
+    fft_pass_static<false, NC, L, R>(buf, tw);
+    __syncthreads();
+    if constexpr (sizeof...(REST) > 0) static_dif<NC, L / R, REST...>(buf, tw);
+}
+template <int NC, int L, int R, int... REST>
+__device__ __forceinline__ void static_dit(double2* buf, const double* tw)
+{
+    if constexpr (sizeof...(REST) > 0) static_dit<NC, L / R, REST...>(buf, tw);
+    fft_pass_static<true, NC, L, R>(buf, tw);
+    __syncthreads();
+}
+
+// returns true if a specialised path handled the transform (radix lists must match dedalus_b200/fftplan.py factorize)
+template <bool INV>
+__device__ __forceinline__ bool fft_static_dispatch(double2* buf, const db_fft_plan& p, int T)
+{
+    if (T != 16) return false;
+    const double* tw = p.tw;
+    switch (p.nc) {
+        case 192: if (INV) static_dit<192, 192, 4, 4, 4, 3>(buf, tw); else static_dif<192, 192, 4, 4, 4, 3>(buf, tw); return true;
+        case 384: if (INV) static_dit<384, 384, 4, 4, 4, 2, 3>(buf, tw); else static_dif<384, 384, 4, 4, 4, 2, 3>(buf, tw); return true;
+        case 96:  if (INV) static_dit<96, 96, 4, 4, 2, 3>(buf, tw); else static_dif<96, 96, 4, 4, 2, 3>(buf, tw); return true;
+        case 48:  if (INV) static_dit<48, 48, 4, 4, 3>(buf, tw); else static_dif<48, 48, 4, 4, 3>(buf, tw); return true;
+        default: return false;
+    }
+}
+
 __device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
+    if (fft_static_dispatch<false>(buf, p, 1 << lgT)) return;
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) {
         fft_pass<false>(buf, p.nc, TP, lgT, p.rad[s], L, p.tw);
@@ -181,6 +249,7 @@ __device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int lgT)
 }
 __device__ void fft_dit(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
+    if (fft_static_dispatch<true>(buf, p, 1 << lgT)) return;
     int Ls[16];
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) { Ls[s] = L; L /= p.rad[s]; }
@@ -698,41 +767,44 @@ __global__ void __launch_bounds__(BL_THREADS)
 k_band_lines(const double* __restrict__ in, double* __restrict__ out, int64_t lines, int n,
              const double* __restrict__ pre, int npre, const double* __restrict__ sol, int nsol)
 {
-    // 32 lines per CTA staged as sm[j][line] (conflict-free for both phases); all 8 warps move data, warp 0 runs the
-    // 32 independent recurrences (one per lane)
-    DB_SMEM(double, sm);                       // [n][BL_LINES + 1]
+    // 32 lines per CTA staged as sm[j][line] (conflict-free for both phases).  The banded pre-apply is evaluated
+    // while loading (each output element reads its npre neighbours straight from global memory: fully parallel,
+    // overlapping reads hit L1); the back-substitution diagonals are staged in shared memory so that the serial
+    // recurrence of warp 0 (one line per lane, solved values in a register window) never waits on global memory.
+    DB_SMEM(double, sm);                       // [n][BL_LINES + 1] then [nsol][n]
     const int P = BL_LINES + 1;
+    double* sols = sm + (size_t)n * P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = BL_THREADS / 32;
     const int64_t l0 = (int64_t)blockIdx.x * BL_LINES;
     const int nl = (lines - l0 < BL_LINES) ? (int)(lines - l0) : BL_LINES;
+    for (int e = threadIdx.x; e < nsol * n; e += BL_THREADS) sols[e] = sol[e];
     for (int l = warp; l < nl; l += nw) {
         const double* __restrict__ src = in + (l0 + l) * n;
+        if (npre > 0) {
+            for (int j = lane; j < n; j += 32) {
+                double acc = 0.0;
+                for (int d = 0; d < npre && j + d < n; ++d) acc = fma(pre[(int64_t)d * n + j], src[j + d], acc);
+                sm[j * P + l] = acc;
+            }
+        } else {
 #pragma unroll 8
-        for (int j = lane; j < n; j += 32) sm[j * P + l] = src[j];
+            for (int j = lane; j < n; j += 32) sm[j * P + l] = src[j];
+        }
     }
     __syncthreads();
-    if (warp == 0 && lane < nl) {
-        if (npre > 0) {                        // ascending, in place: row i only reads rows >= i
-            for (int i = 0; i < n; ++i) {
-                double acc = 0.0;
-                for (int d = 0; d < npre && i + d < n; ++d) acc = fma(pre[(int64_t)d * n + i], sm[(i + d) * P + lane], acc);
-                sm[i * P + lane] = acc;
-            }
-        }
-        if (nsol > 0) {
-            double win[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            const int nd = nsol < 8 ? nsol : 8;
-            for (int i = n - 1; i >= 0; --i) {
-                double acc = sm[i * P + lane];
+    if (nsol > 0 && warp == 0 && lane < nl) {
+        double win[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const int nd = nsol < 8 ? nsol : 8;
+        for (int i = n - 1; i >= 0; --i) {
+            double acc = sm[i * P + lane];
 #pragma unroll
-                for (int d = 1; d < 8; ++d)
-                    if (d < nd) acc = fma(-sol[(int64_t)d * n + i], win[d - 1], acc);
-                const double xi = acc * sol[i];
+            for (int d = 1; d < 8; ++d)
+                if (d < nd) acc = fma(-sols[d * n + i], win[d - 1], acc);
+            const double xi = acc * sols[i];
 #pragma unroll
-                for (int d = 6; d > 0; --d) win[d] = win[d - 1];
-                win[0] = xi;
-                sm[i * P + lane] = xi;
-            }
+            for (int d = 6; d > 0; --d) win[d] = win[d - 1];
+            win[0] = xi;
+            sm[i * P + lane] = xi;
         }
     }
     __syncthreads();
@@ -747,7 +819,7 @@ extern "C" int db_band_lines(const double* in, double* out, int64_t lines, int32
                              const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream)
 {
     if (lines <= 0 || n <= 0) return 0;
-    size_t smem = (size_t)n * (BL_LINES + 1) * sizeof(double);
+    size_t smem = ((size_t)n * (BL_LINES + 1) + (size_t)(solve_ndiag > 0 ? solve_ndiag : 0) * n) * sizeof(double);
     if (smem > (size_t)DB_MAX_SMEM) { db_set_error("band_lines: line length %d too large", n); return 1; }
     int64_t blocks = (lines + BL_LINES - 1) / BL_LINES;
 #ifndef DB_EMU

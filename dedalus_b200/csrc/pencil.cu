@@ -191,11 +191,8 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
                                const int32_t* __restrict__ prog, int n_fwd, int n_entries,
                                db_lincomb rhs, double* __restrict__ xg)
 {
-    DB_SMEM(double, ring);                      // [DB_SOLVE_WINDOW][blockDim.x]
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const int nt = blockDim.x;
-    double* myring = ring + threadIdx.x;
     const double* __restrict__ f = lu + s;
     double* __restrict__ x = xg + s;
     int row = 0;
@@ -203,9 +200,9 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
     for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][s], acc);
     for (int e = 0; e < n_fwd; ++e) {
         const int c = prog[e];
-        if (c >= 0) acc = fma(-f[(int64_t)e * ld], (c & DB_I_NEAR) ? myring[(c & (DB_SOLVE_WINDOW - 1)) * nt] : x[c], acc);
+        if (c >= 0) acc = fma(-f[(int64_t)e * ld], x[c], acc);
         else if (c == DB_I_END) {
-            x[(int64_t)row * ld] = acc; myring[(row & (DB_SOLVE_WINDOW - 1)) * nt] = acc;
+            x[(int64_t)row * ld] = acc;
             ++row;
             acc = 0.0;
             if (row < n) for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][(int64_t)row * ld + s], acc);
@@ -216,10 +213,9 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
     for (int e = n_fwd; e < n_entries; ++e) {
         const int c = prog[e];
         const double v = f[(int64_t)e * ld];
-        if (c >= 0) acc = fma(-v, (c & DB_I_NEAR) ? myring[(c & (DB_SOLVE_WINDOW - 1)) * nt] : x[c], acc);
+        if (c >= 0) acc = fma(-v, x[c], acc);
         else if (c == DB_I_END) {
-            const double xi = acc * v;
-            x[(int64_t)row * ld] = xi; myring[(row & (DB_SOLVE_WINDOW - 1)) * nt] = xi;
+            x[(int64_t)row * ld] = acc * v;
             --row;
             if (row >= 0) acc = x[(int64_t)row * ld];
         }
@@ -233,7 +229,7 @@ extern "C" int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t l
     if (S <= 0 || n <= 0) return 0;
     if (rhs->nvec < 0 || rhs->nvec > 16) { db_set_error("pencil_solve: nvec out of range"); return 1; }
     dim3 grid((S + 63) / 64), block(64);
-    DB_LAUNCH(k_pencil_solve, grid, block, DB_SOLVE_WINDOW * 64 * sizeof(double), stream, lu, n, S, ld, prog, n_fwd, n_entries, *rhs, x);
+    DB_LAUNCH(k_pencil_solve, grid, block, 0, stream, lu, n, S, ld, prog, n_fwd, n_entries, *rhs, x);
     return db_check_launch("pencil_solve");
 }
 
@@ -281,8 +277,6 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
     if (s >= B.S) return;
     const int ld = B.ld, n = B.n;
-    DB_SMEM(double, ring);                                    // [DB_SOLVE_WINDOW][SOLVE_THREADS]: most recent rows of x
-    double* myring = ring + threadIdx.x;
     const double* __restrict__ fp = B.lu[lu_slot] + s;        // factor stream pointer, advances by ld per entry
     const int32_t* __restrict__ pp = B.prog;                  // instruction stream pointer
     double* __restrict__ x = B.vec[x_slot] + s;
@@ -312,9 +306,9 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
         if (ch + 1 < nchunk_f + nchunk_b) { SOLVE_LOAD() }     // the last forward chunk already prefetches the backward stream
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
-            if (c[j] >= 0) acc = fma(-v[j], (c[j] & DB_I_NEAR) ? myring[(c[j] & (DB_SOLVE_WINDOW - 1)) * SOLVE_THREADS] : x[c[j]], acc);
+            if (c[j] >= 0) acc = fma(-v[j], x[c[j]], acc);
             else if (c[j] == DB_I_END) {
-                x[(int64_t)row * ld] = acc; myring[(row & (DB_SOLVE_WINDOW - 1)) * SOLVE_THREADS] = acc;
+                x[(int64_t)row * ld] = acc;
                 ++row;
                 acc = r1; r1 = r2; r2 = rhs_at(row + 2);
             }
@@ -331,10 +325,9 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
         if (ch + 1 < nchunk_b) { SOLVE_LOAD() }
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
-            if (c[j] >= 0) acc = fma(-v[j], (c[j] & DB_I_NEAR) ? myring[(c[j] & (DB_SOLVE_WINDOW - 1)) * SOLVE_THREADS] : x[c[j]], acc);
+            if (c[j] >= 0) acc = fma(-v[j], x[c[j]], acc);
             else if (c[j] == DB_I_END) {
-                const double xi = acc * v[j];
-                x[(int64_t)row * ld] = xi; myring[(row & (DB_SOLVE_WINDOW - 1)) * SOLVE_THREADS] = xi;
+                x[(int64_t)row * ld] = acc * v[j];
                 --row;
                 acc = y1; y1 = y2; y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
             }
@@ -348,7 +341,7 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
-    DB_LAUNCH(k_batches_solve, dim3(total_blocks), dim3(SOLVE_THREADS), DB_SOLVE_WINDOW * SOLVE_THREADS * sizeof(double), stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    DB_LAUNCH(k_batches_solve, dim3(total_blocks), dim3(SOLVE_THREADS), 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
     return db_check_launch("batches_solve");
 }
 

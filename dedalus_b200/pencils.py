@@ -454,16 +454,13 @@ def compile_batch(batch, a0, b0):
     #   DB_I_END  : end of row. forward: x[row] = acc (LU value unused); backward: x[row] = acc * LU[e] (reciprocal pivot)
     #   DB_I_SKIP : padding so that each section is a multiple of the kernels' prefetch depth
     END, SKIP, PAD = -1, -2, 8
-    NEAR, W = 1 << 30, 64           # DB_I_NEAR, DB_SOLVE_WINDOW: recent rows are served from a shared-memory ring
     ld = ((batch.S + 31) // 32) * 32
     prog.ld = ld
     if (n + 1) * ld >= 2**30:
         raise NotImplementedError("batch too large for 30-bit vector offsets")
 
     def codes(row, js):
-        js = js.astype(np.int64)
-        near = np.abs(row - js) < W
-        return np.where(near, NEAR | (js % W), js * ld)
+        return js.astype(np.int64) * ld
     eid = -np.ones((n, n), dtype=np.int64)
     instr = []
     e = 0

@@ -142,10 +142,7 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
  * `batches` is a DEVICE array of db_batch built once by the host; per-call arguments are slot indices.
  * The solve program is a flat instruction stream aligned one-to-one with the LU value stream (forward rows
  * 0..n-1, then backward rows n-1..0), each section padded to a multiple of 8 entries:
- *   prog[e] >= 0       : acc -= LU[e] * x_col ; without DB_I_NEAR the code is column * ld (element offset of that row in
- *                        the vector, read from global memory); with DB_I_NEAR set the column lies within
- *                        DB_SOLVE_WINDOW rows of the current one and the low bits hold column % DB_SOLVE_WINDOW,
- *                        the slot of a shared-memory ring holding the most recent rows
+ *   prog[e] >= 0       : acc -= LU[e] * x[prog[e]]      (prog[e] = column * ld: element offset of that row in a vector)
  *   prog[e] == DB_I_END: row finished.  forward: x[row] = acc ; backward: x[row] = acc * LU[e] (reciprocal pivot)
  *   prog[e] == DB_I_SKIP: padding
  * ------------------------------------------------------------------------------------------------------- */
@@ -153,8 +150,6 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
 #define DB_MAX_LU 4
 #define DB_I_END  (-1)
 #define DB_I_SKIP (-2)
-#define DB_I_NEAR 0x40000000
-#define DB_SOLVE_WINDOW 64
 typedef struct {
     int32_t n, S, ld, n_entries;
     int32_t n_fwd, n_bwd;

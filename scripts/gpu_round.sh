@@ -1,5 +1,4 @@
 #!/bin/bash
-# tests + microbench + bench + ncu captures of the two dominant kernels
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
 timeout 600 python scripts/fft_microbench.py 256 2>&1 | tee gpurun_out/fft_microbench.log
@@ -11,5 +10,5 @@ print("value", d['value'], "ms/step", d['ms_per_step'], "e2e", d['e2e']['value']
 for k, v in d['kernels'].items(): print(f"  {k:24s} {v['ms_per_step']:8.2f} ms/step  {v['gbps']:8.1f} GB/s  share {v['share']:.3f}")
 PY
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_batches_solve -s 4 -c 1 -o gpurun_out/prof_solve python bench.py --size 256 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_solve.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fft -s 36 -c 2 -o gpurun_out/prof_fft3 python scripts/fft_microbench.py 256 > gpurun_out/ncu_fft.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_band_lines -s 3 -c 1 -o gpurun_out/prof_band python scripts/fft_microbench.py 256 > gpurun_out/ncu_band.log 2>&1
 ls -la gpurun_out/*.ncu-rep

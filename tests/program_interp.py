@@ -32,13 +32,11 @@ def factor(prog, LU):
 
 
 def solve(prog, LU, rhs):
-    END, SKIP, NEAR, W = -1, -2, 1 << 30, 64
+    END, SKIP = -1, -2
     n, ld = prog.n, prog.ld
     y = np.array(rhs, dtype=float, copy=True)
-    ring = np.zeros((W,) + y.shape[1:])
-
     def xval(c):
-        return ring[c & (W - 1)] if (c & NEAR) else y[c // ld]
+        return y[c // ld]
     row = 0
     acc = y[0].copy()
     for e in range(prog.n_fwd):
@@ -46,7 +44,7 @@ def solve(prog, LU, rhs):
         if c >= 0:
             acc = acc - LU[e] * xval(c)
         elif c == END:
-            y[row] = acc; ring[row % W] = acc
+            y[row] = acc
             row += 1
             if row < n:
                 acc = y[row].copy()
@@ -57,7 +55,7 @@ def solve(prog, LU, rhs):
         if c >= 0:
             acc = acc - LU[e] * xval(c)
         elif c == END:
-            y[row] = acc * LU[e]; ring[row % W] = y[row]
+            y[row] = acc * LU[e]
             row -= 1
             if row >= 0:
                 acc = y[row].copy()

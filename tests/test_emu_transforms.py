@@ -106,3 +106,25 @@ def test_chebyshev_strided_axis_matches_last_axis():
     back = np.zeros_like(c)
     lib.call("db_cheb_forward", plan.ref(), E.ptr(out), E.ptr(back), 3, M, 37, None, 0, None)
     assert np.allclose(back, c, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("M,N", [(256, 384), (128, 192), (64, 96), (32, 48), (512, 768)])
+def test_benchmark_line_lengths_use_static_passes(M, N):
+    """The compile-time specialised FFT passes (nc = 192, 96, 48, 24->generic, 384) against the oracle transforms."""
+    from oracle import transforms_oracle as T
+    lib = E.emu(); plan = E.EmuPlan(N, 'real')
+    rng = np.random.default_rng(7)
+    inner = 18                                       # > 8 lines so the tile width stays 16
+    c = rng.standard_normal((2, M, inner)); c[:, 1, :] = 0
+    g = np.zeros((2, N, inner))
+    lib.call("db_rfft_backward", plan.ref(), E.ptr(c), E.ptr(g), 2, M, inner, 0, 0.0, None)
+    assert np.allclose(g, T.rf_backward_fft(c, N, 1), rtol=1e-12, atol=1e-12)
+    back = np.zeros_like(c)
+    lib.call("db_rfft_forward", plan.ref(), E.ptr(g), E.ptr(back), 2, M, inner, None)
+    assert np.allclose(back, c, rtol=1e-12, atol=1e-12)
+    cz = rng.standard_normal((20, M)); gz = np.zeros((20, N))
+    lib.call("db_cheb_backward", plan.ref(), E.ptr(cz), E.ptr(gz), 20, M, 1, None, 0, None, 0, None)
+    assert np.allclose(gz, T.cheb_backward_fft(cz, N, 1), rtol=1e-11, atol=1e-11)
+    bz = np.zeros_like(cz)
+    lib.call("db_cheb_forward", plan.ref(), E.ptr(gz), E.ptr(bz), 20, M, 1, None, 0, None)
+    assert np.allclose(bz, cz, rtol=1e-11, atol=1e-11)
