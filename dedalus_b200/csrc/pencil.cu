@@ -196,13 +196,14 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
     const double* __restrict__ f = lu + s;
     double* __restrict__ x = xg + s;
     int row = 0;
-    double acc = 0.0;
+    double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
     for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][s], acc);
     for (int e = 0; e < n_fwd; ++e) {
         const int c = prog[e];
-        if (c >= 0) acc = fma(-f[(int64_t)e * ld], x[c], acc);
+        if (c >= 0) acc = fma(-f[(int64_t)e * ld], (c & DB_I_FRESH_REG) ? ((c & 3) == 1 ? l1 : (c & 3) == 2 ? l2 : l3) : x[c & DB_I_OFFMASK], acc);
         else if (c == DB_I_END) {
             x[(int64_t)row * ld] = acc;
+            l3 = l2; l2 = l1; l1 = acc;
             ++row;
             acc = 0.0;
             if (row < n) for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][(int64_t)row * ld + s], acc);
@@ -213,9 +214,11 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
     for (int e = n_fwd; e < n_entries; ++e) {
         const int c = prog[e];
         const double v = f[(int64_t)e * ld];
-        if (c >= 0) acc = fma(-v, x[c], acc);
+        if (c >= 0) acc = fma(-v, (c & DB_I_FRESH_REG) ? ((c & 3) == 1 ? l1 : (c & 3) == 2 ? l2 : l3) : x[c & DB_I_OFFMASK], acc);
         else if (c == DB_I_END) {
-            x[(int64_t)row * ld] = acc * v;
+            const double xi = acc * v;
+            x[(int64_t)row * ld] = xi;
+            l3 = l2; l2 = l1; l1 = xi;
             --row;
             if (row >= 0) acc = x[(int64_t)row * ld];
         }
@@ -298,17 +301,27 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     const int nchunk_f = B.n_fwd / SOLVE_PF, nchunk_b = (B.n_entries - B.n_fwd) / SOLVE_PF;
     int row = 0;
     double acc = rhs_at(0), r1 = rhs_at(1), r2 = rhs_at(2);
+    double l1 = 0.0, l2 = 0.0, l3 = 0.0;           // the three most recently completed rows
     SOLVE_LOAD()
     for (int ch = 0; ch < nchunk_f; ++ch) {
         double v[SOLVE_PF]; int c[SOLVE_PF];
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; c[j] = cn[j]; }
         if (ch + 1 < nchunk_f + nchunk_b) { SOLVE_LOAD() }     // the last forward chunk already prefetches the backward stream
+        double xv[SOLVE_PF];
+#pragma unroll
+        for (int j = 0; j < SOLVE_PF; ++j) xv[j] = ((unsigned)c[j] < (unsigned)DB_I_FRESH_MEM) ? x[c[j]] : 0.0;   // plain codes only
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
-            if (c[j] >= 0) acc = fma(-v[j], x[c[j]], acc);
-            else if (c[j] == DB_I_END) {
+            const int cj = c[j];
+            if (cj >= 0) {
+                double xx = xv[j];
+                if (cj & (DB_I_FRESH_REG | DB_I_FRESH_MEM))
+                    xx = (cj & DB_I_FRESH_REG) ? (((cj & 3) == 1) ? l1 : ((cj & 3) == 2) ? l2 : l3) : x[cj & DB_I_OFFMASK];
+                acc = fma(-v[j], xx, acc);
+            } else if (cj == DB_I_END) {
                 x[(int64_t)row * ld] = acc;
+                l3 = l2; l2 = l1; l1 = acc;
                 ++row;
                 acc = r1; r1 = r2; r2 = rhs_at(row + 2);
             }
@@ -323,11 +336,21 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; c[j] = cn[j]; }
         if (ch + 1 < nchunk_b) { SOLVE_LOAD() }
+        double xv[SOLVE_PF];
+#pragma unroll
+        for (int j = 0; j < SOLVE_PF; ++j) xv[j] = ((unsigned)c[j] < (unsigned)DB_I_FRESH_MEM) ? x[c[j]] : 0.0;
 #pragma unroll
         for (int j = 0; j < SOLVE_PF; ++j) {
-            if (c[j] >= 0) acc = fma(-v[j], x[c[j]], acc);
-            else if (c[j] == DB_I_END) {
-                x[(int64_t)row * ld] = acc * v[j];
+            const int cj = c[j];
+            if (cj >= 0) {
+                double xx = xv[j];
+                if (cj & (DB_I_FRESH_REG | DB_I_FRESH_MEM))
+                    xx = (cj & DB_I_FRESH_REG) ? (((cj & 3) == 1) ? l1 : ((cj & 3) == 2) ? l2 : l3) : x[cj & DB_I_OFFMASK];
+                acc = fma(-v[j], xx, acc);
+            } else if (cj == DB_I_END) {
+                const double xi = acc * v[j];
+                x[(int64_t)row * ld] = xi;
+                l3 = l2; l2 = l1; l1 = xi;
                 --row;
                 acc = y1; y1 = y2; y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
             }

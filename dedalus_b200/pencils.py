@@ -481,8 +481,29 @@ def compile_batch(batch, a0, b0):
     pad = (-e) % PAD
     instr.append(np.full(pad, SKIP, dtype=np.int64)); e += pad
     prog.nE = e
-    prog.prog = np.concatenate(instr).astype(np.int32)
-    assert len(prog.prog) == prog.nE
+    code = np.concatenate(instr).astype(np.int64)
+    assert len(code) == prog.nE
+    # ---- hazard marking for the kernels' chunk-wise preloading of x (PAD entries per chunk): an entry whose column
+    #      is completed earlier in the SAME chunk must not use the preloaded value.  The k-th most recently completed
+    #      row (k <= 3) is kept in registers (DB_I_FRESH_REG | k); anything else re-reads memory (DB_I_FRESH_MEM | off).
+    FRESH_REG, FRESH_MEM = 1 << 30, 1 << 29
+    if (n + 1) * ld >= FRESH_MEM:
+        raise NotImplementedError("batch too large for 29-bit vector offsets")
+    for sec0, sec1, step in ((0, prog.n_fwd, +1), (prog.n_fwd, prog.nE, -1)):
+        row = 0 if step > 0 else n - 1
+        done_at = {}                       # row -> stream position of its END entry
+        for pos in range(sec0, sec1):
+            c = code[pos]
+            if c == END:
+                done_at[row] = pos
+                row += step
+            elif c >= 0:
+                col = int(c // ld)
+                p_end = done_at.get(col)
+                if p_end is not None and p_end >= (pos // PAD) * PAD:
+                    k = (row - col) * step
+                    code[pos] = (FRESH_REG | k) if 1 <= k <= 3 else (FRESH_MEM | int(c))
+    prog.prog = code.astype(np.int32)
     prog.diag_eid = diag_eid
     # ---- factor program
     fl_ptr = np.zeros(n + 1, dtype=np.int32); fu_ptr = np.zeros(n + 1, dtype=np.int32)

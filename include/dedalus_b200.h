@@ -142,7 +142,10 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
  * `batches` is a DEVICE array of db_batch built once by the host; per-call arguments are slot indices.
  * The solve program is a flat instruction stream aligned one-to-one with the LU value stream (forward rows
  * 0..n-1, then backward rows n-1..0), each section padded to a multiple of 8 entries:
- *   prog[e] >= 0       : acc -= LU[e] * x[prog[e]]      (prog[e] = column * ld: element offset of that row in a vector)
+ *   prog[e] >= 0       : acc -= LU[e] * x_col.  Plain code = column * ld (element offset of that row in a vector); the
+ *                        kernels preload these x values for a whole chunk of 8 entries at once.  Entries whose
+ *                        column is completed earlier in the same chunk carry DB_I_FRESH_REG | k (k = 1..3: the k-th
+ *                        most recently completed row, kept in registers) or DB_I_FRESH_MEM | offset (re-read memory)
  *   prog[e] == DB_I_END: row finished.  forward: x[row] = acc ; backward: x[row] = acc * LU[e] (reciprocal pivot)
  *   prog[e] == DB_I_SKIP: padding
  * ------------------------------------------------------------------------------------------------------- */
@@ -150,6 +153,9 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
 #define DB_MAX_LU 4
 #define DB_I_END  (-1)
 #define DB_I_SKIP (-2)
+#define DB_I_FRESH_REG 0x40000000
+#define DB_I_FRESH_MEM 0x20000000
+#define DB_I_OFFMASK   0x1FFFFFFF
 typedef struct {
     int32_t n, S, ld, n_entries;
     int32_t n_fwd, n_bwd;

@@ -32,33 +32,35 @@ def factor(prog, LU):
 
 
 def solve(prog, LU, rhs):
-    END, SKIP = -1, -2
+    """Mirrors the kernels: chunks of 8 entries, plain x values preloaded at chunk start, FRESH entries served from the
+    three most recently completed rows or re-read."""
+    END, SKIP, FRESH_REG, FRESH_MEM, MASK, PF = -1, -2, 1 << 30, 1 << 29, (1 << 29) - 1, 8
     n, ld = prog.n, prog.ld
     y = np.array(rhs, dtype=float, copy=True)
-    def xval(c):
-        return y[c // ld]
-    row = 0
-    acc = y[0].copy()
-    for e in range(prog.n_fwd):
-        c = int(prog.prog[e])
-        if c >= 0:
-            acc = acc - LU[e] * xval(c)
-        elif c == END:
-            y[row] = acc
-            row += 1
-            if row < n:
-                acc = y[row].copy()
-    row = n - 1
-    acc = y[row].copy()
-    for e in range(prog.n_fwd, prog.nE):
-        c = int(prog.prog[e])
-        if c >= 0:
-            acc = acc - LU[e] * xval(c)
-        elif c == END:
-            y[row] = acc * LU[e]
-            row -= 1
-            if row >= 0:
-                acc = y[row].copy()
+    for sec0, sec1, step in ((0, prog.n_fwd, +1), (prog.n_fwd, prog.nE, -1)):
+        row = 0 if step > 0 else n - 1
+        acc = y[row].copy()
+        last = [None, None, None]
+        for e0 in range(sec0, sec1, PF):
+            codes = [int(prog.prog[e]) for e in range(e0, e0 + PF)]
+            pre = [y[c // ld].copy() if (c >= 0 and not (c & (FRESH_REG | FRESH_MEM))) else None for c in codes]
+            for j, c in enumerate(codes):
+                e = e0 + j
+                if c >= 0:
+                    if c & FRESH_REG:
+                        xv = last[(c & 3) - 1]
+                    elif c & FRESH_MEM:
+                        xv = y[(c & MASK) // ld]
+                    else:
+                        xv = pre[j]
+                    acc = acc - LU[e] * xv
+                elif c == END:
+                    val = acc if step > 0 else acc * LU[e]
+                    y[row] = val
+                    last = [val.copy(), last[0], last[1]]
+                    row += step
+                    if 0 <= row < n:
+                        acc = y[row].copy()
     return y
 
 
