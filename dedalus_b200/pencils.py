@@ -221,6 +221,11 @@ class PencilSystemBuilder:
                 T.sum_duplicates()
                 if np.iscomplexobj(T.data) and np.all(T.data.imag == 0) and self.problem.dtype in (np.float64,):
                     T = T.real
+                # entry cutoff as in the reference (subsystems.py:536: |a| < entry_cutoff dropped after assembly), applied
+                # to the template with the largest monomial value of the class: rounding-noise entries of sparse
+                # products (1e-16) would otherwise bloat the structural pattern and the LU fill
+                scale = float(np.max(np.abs(self.monomial_values(cls, mono)))) if len(cls.groups) else 1.0
+                T.data[np.abs(T.data) * max(scale, 1e-300) < self.entry_cutoff] = 0
                 T.eliminate_zeros()
                 templates[name][mono] = T.tocsr()
                 if T.nnz == 0:
