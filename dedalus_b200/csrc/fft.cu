@@ -487,9 +487,12 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
                 gout[off] = cof[(c * TP + t) * 2]; gout[off + 1] = cof[(c * TP + t) * 2 + 1];
             });
         } else if (KIND == K_CHFWD && a.nd_a > 0) {
+            // banded conversion fused into the store; its diagonals are staged in the (now free) work buffer
             const int Kin = (M < n) ? M : n;
             const int nd = a.nd_a;
-            const double* __restrict__ dg = a.diags_a;
+            double* dg = smem;
+            for (int e = tid; e < nd * M; e += nthreads) dg[e] = a.diags_a[e];
+            __syncthreads();
             tile_iter(M, go, contiguous, lgT, [&](int i, int t, int64_t off) {
                 double acc = 0.0;
                 if (i < Kin) {
@@ -699,6 +702,7 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
     // as scratch for n_coeff staged coefficients
     size_t buf_rows = (size_t)2 * plan->nc;
     if (KIND == K_CHBWD && (size_t)n_coeff > buf_rows) buf_rows = (size_t)n_coeff;
+    if (KIND == K_CHFWD && nda > 0 && (size_t)nda * n_coeff > buf_rows * 2) buf_rows = ((size_t)nda * n_coeff + 1) / 2;   // >= nd*M doubles even at T = 1
     auto smem_bytes = [&](int t) -> size_t {
         return (buf_rows * (t + 1) + (direct ? 0 : (size_t)(is_cplx ? 2 : 1) * n_coeff * (t + 1))) * sizeof(double);
     };

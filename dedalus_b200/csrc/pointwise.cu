@@ -162,83 +162,84 @@ extern "C" int db_mmt_apply(const double* mat, int32_t m, int32_t n, const doubl
 //   out[b][p*n1blk + i][j][r] = recv[p][b][i][j][r]
 // The reverse hop swaps the roles.  Blocks are assumed equal (n2 % P == 0, n1 % P == 0).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_tr_pack(const double* __restrict__ a, double* __restrict__ send, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int P)
+// All four permutes move whole contiguous chunks: for fixed (batch b, row i, peer p) the block of `clen` doubles is
+// contiguous on both sides.  One CTA (or several, via blockIdx.y) copies one chunk with 128-bit accesses; the only
+// index arithmetic is per chunk.
+//   mode 0 pack    : chunk (b, i, p): src ((b*n1loc + i)*n2 + p*n2blk)*n3        -> dst (((p*B + b)*n1loc + i)*n2blk)*n3,   clen = n2blk*n3
+//   mode 1 unpack  : chunk (p, b, i): src (((p*B + b)*n1blk + i)*n2loc)*n3       -> dst ((b*n1 + p*n1blk + i)*n2loc)*n3,    clen = n2loc*n3
+//   mode 2 pack_rev: chunk (b, p, i): src ((b*n1 + p*n1blk + i)*n2loc)*n3        -> dst (((p*B + b)*n1blk + i)*n2loc)*n3,   clen = n2loc*n3
+//   mode 3 unp_rev : chunk (p, b, i): src (((p*B + b)*n1loc + i)*n2blk)*n3       -> dst ((b*n1loc + i)*n2 + p*n2blk)*n3,    clen = n2blk*n3
+struct TrArgs { int64_t B, nA, nB, n3; int P; int mode; int64_t clen; };
+
+__global__ void __launch_bounds__(256) k_tr_chunks(const double* __restrict__ src, double* __restrict__ dst, TrArgs a)
 {
-    const int64_t n2blk = n2 / P;
-    const int64_t total = B * n1loc * n2 * n3;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = e % n3; int64_t q = e / n3;
-        int64_t j2 = q % n2; q /= n2;
-        int64_t i = q % n1loc; int64_t b = q / n1loc;
-        int64_t p = j2 / n2blk, j = j2 - p * n2blk;
-        send[(((p * B + b) * n1loc + i) * n2blk + j) * n3 + r] = a[e];
+    const int64_t chunk = blockIdx.x;
+    int64_t so, dof;
+    if (a.mode == 0) {            // nA = n1loc, nB = n2
+        const int64_t p = chunk % a.P; int64_t q = chunk / a.P; const int64_t i = q % a.nA, b = q / a.nA;
+        const int64_t n2blk = a.nB / a.P;
+        so = ((b * a.nA + i) * a.nB + p * n2blk) * a.n3;
+        dof = (((p * a.B + b) * a.nA + i) * n2blk) * a.n3;
+    } else if (a.mode == 1) {     // nA = n1, nB = n2loc
+        const int64_t n1blk = a.nA / a.P;
+        const int64_t i = chunk % n1blk; int64_t q = chunk / n1blk; const int64_t b = q % a.B, p = q / a.B;
+        so = (((p * a.B + b) * n1blk + i) * a.nB) * a.n3;
+        dof = ((b * a.nA + p * n1blk + i) * a.nB) * a.n3;
+    } else if (a.mode == 2) {     // nA = n1, nB = n2loc
+        const int64_t n1blk = a.nA / a.P;
+        const int64_t i = chunk % n1blk; int64_t q = chunk / n1blk; const int64_t p = q % a.P, b = q / a.P;
+        so = ((b * a.nA + p * n1blk + i) * a.nB) * a.n3;
+        dof = (((p * a.B + b) * n1blk + i) * a.nB) * a.n3;
+    } else {                      // nA = n1loc, nB = n2
+        const int64_t n2blk = a.nB / a.P;
+        const int64_t i = chunk % a.nA; int64_t q = chunk / a.nA; const int64_t b = q % a.B, p = q / a.B;
+        so = (((p * a.B + b) * a.nA + i) * n2blk) * a.n3;
+        dof = ((b * a.nA + i) * a.nB + p * n2blk) * a.n3;
     }
-}
-__global__ void k_tr_unpack(const double* __restrict__ recv, double* __restrict__ out, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int P)
-{
-    const int64_t n1blk = n1 / P;
-    const int64_t total = B * n1 * n2loc * n3;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = e % n3; int64_t q = e / n3;
-        int64_t j = q % n2loc; q /= n2loc;
-        int64_t i1 = q % n1; int64_t b = q / n1;
-        int64_t p = i1 / n1blk, i = i1 - p * n1blk;
-        out[e] = recv[(((p * B + b) * n1blk + i) * n2loc + j) * n3 + r];
-    }
-}
-// reverse hop: A (B, n1, n2loc, n3) -> send[p][b][i][j][r] = A[b][p*n1blk+i][j][r]; recv -> out (B, n1loc, n2, n3)
-__global__ void k_tr_pack_rev(const double* __restrict__ a, double* __restrict__ send, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int P)
-{
-    const int64_t n1blk = n1 / P;
-    const int64_t total = B * n1 * n2loc * n3;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = e % n3; int64_t q = e / n3;
-        int64_t j = q % n2loc; q /= n2loc;
-        int64_t i1 = q % n1; int64_t b = q / n1;
-        int64_t p = i1 / n1blk, i = i1 - p * n1blk;
-        send[(((p * B + b) * n1blk + i) * n2loc + j) * n3 + r] = a[e];
-    }
-}
-__global__ void k_tr_unpack_rev(const double* __restrict__ recv, double* __restrict__ out, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int P)
-{
-    const int64_t n2blk = n2 / P;
-    const int64_t total = B * n1loc * n2 * n3;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = e % n3; int64_t q = e / n3;
-        int64_t j2 = q % n2; q /= n2;
-        int64_t i = q % n1loc; int64_t b = q / n1loc;
-        int64_t p = j2 / n2blk, j = j2 - p * n2blk;
-        out[e] = recv[(((p * B + b) * n1loc + i) * n2blk + j) * n3 + r];
+    const double* __restrict__ s = src + so;
+    double* __restrict__ d = dst + dof;
+    const int64_t start = (int64_t)blockIdx.y * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.y * blockDim.x;
+    if (((so | dof | a.clen) & 1) == 0) {
+        const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s);
+        double2* __restrict__ d2 = reinterpret_cast<double2*>(d);
+        for (int64_t e = start; e < (a.clen >> 1); e += stride) d2[e] = s2[e];
+    } else {
+        for (int64_t e = start; e < a.clen; e += stride) d[e] = s[e];
     }
 }
 
-static inline unsigned tr_blocks(int64_t total) { int64_t b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16; return (unsigned)b; }
+static int tr_launch(const double* src, double* dst, int mode, int64_t B, int64_t nA, int64_t nB, int64_t n3, int P, void* stream, const char* name)
+{
+    TrArgs a; a.B = B; a.nA = nA; a.nB = nB; a.n3 = n3; a.P = P; a.mode = mode;
+    int64_t nchunks;
+    if (mode == 0 || mode == 3) { a.clen = (nB / P) * n3; nchunks = B * nA * P; }
+    else { a.clen = nB * n3; nchunks = B * nA; }
+    if (nchunks <= 0 || a.clen <= 0) return 0;
+    if (nchunks > 2147483647LL) { db_set_error("%s: too many chunks", name); return 1; }
+    int64_t gy = (a.clen / 2 + 256 * 8 - 1) / (256 * 8);       // ~8 vector elements per thread
+    if (gy < 1) gy = 1;
+    if (gy > 64) gy = 64;
+    DB_LAUNCH(k_tr_chunks, dim3((unsigned)nchunks, (unsigned)gy), dim3(256), 0, stream, src, dst, a);
+    return db_check_launch(name);
+}
 
 extern "C" int db_transpose_pack(const double* a, double* sendbuf, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int32_t P, void* stream)
 {
     if (n2 % P) { db_set_error("transpose_pack: n2 not divisible by P"); return 1; }
-    int64_t total = B * n1loc * n2 * n3; if (total <= 0) return 0;
-    DB_LAUNCH(k_tr_pack, dim3(tr_blocks(total)), dim3(256), 0, stream, a, sendbuf, B, n1loc, n2, n3, P);
-    return db_check_launch("transpose_pack");
+    return tr_launch(a, sendbuf, 0, B, n1loc, n2, n3, P, stream, "transpose_pack");
 }
 extern "C" int db_transpose_unpack(const double* recvbuf, double* out, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int32_t P, void* stream)
 {
     if (n1 % P) { db_set_error("transpose_unpack: n1 not divisible by P"); return 1; }
-    int64_t total = B * n1 * n2loc * n3; if (total <= 0) return 0;
-    DB_LAUNCH(k_tr_unpack, dim3(tr_blocks(total)), dim3(256), 0, stream, recvbuf, out, B, n1, n2loc, n3, P);
-    return db_check_launch("transpose_unpack");
+    return tr_launch(recvbuf, out, 1, B, n1, n2loc, n3, P, stream, "transpose_unpack");
 }
 extern "C" int db_transpose_pack_rev(const double* a, double* sendbuf, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int32_t P, void* stream)
 {
     if (n1 % P) { db_set_error("transpose_pack_rev: n1 not divisible by P"); return 1; }
-    int64_t total = B * n1 * n2loc * n3; if (total <= 0) return 0;
-    DB_LAUNCH(k_tr_pack_rev, dim3(tr_blocks(total)), dim3(256), 0, stream, a, sendbuf, B, n1, n2loc, n3, P);
-    return db_check_launch("transpose_pack_rev");
+    return tr_launch(a, sendbuf, 2, B, n1, n2loc, n3, P, stream, "transpose_pack_rev");
 }
 extern "C" int db_transpose_unpack_rev(const double* recvbuf, double* out, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int32_t P, void* stream)
 {
     if (n2 % P) { db_set_error("transpose_unpack_rev: n2 not divisible by P"); return 1; }
-    int64_t total = B * n1loc * n2 * n3; if (total <= 0) return 0;
-    DB_LAUNCH(k_tr_unpack_rev, dim3(tr_blocks(total)), dim3(256), 0, stream, recvbuf, out, B, n1loc, n2, n3, P);
-    return db_check_launch("transpose_unpack_rev");
+    return tr_launch(recvbuf, out, 3, B, n1loc, n2, n3, P, stream, "transpose_unpack_rev");
 }
