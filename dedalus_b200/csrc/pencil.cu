@@ -272,6 +272,8 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 
 #define SOLVE_THREADS 64
 #define SOLVE_PF 8
+// NV = number of right-hand-side vectors (compile time: pointers and coefficients stay in registers)
+template <int NV>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs)
 {
@@ -283,12 +285,17 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     const double* __restrict__ fp = B.lu[lu_slot] + s;        // factor stream pointer, advances by ld per entry
     const int32_t* __restrict__ pp = B.prog;                  // instruction stream pointer
     double* __restrict__ x = B.vec[x_slot] + s;
-    const double* rv[16];
-    for (int j = 0; j < 16; ++j) rv[j] = (j < rhs.nvec) ? B.vec[rhs.slot[j]] + s : nullptr;
-    const int nvec = rhs.nvec;
+    const double* rv[NV];
+    double cf[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + s; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
     auto rhs_at = [&](int r) -> double {
         double a = 0.0;
-        if (r < n) for (int q = 0; q < nvec; ++q) a = fma(rhs.coef[q], DB_LDCS(rv[q] + (int64_t)r * ld), a);
+        if (r < n) {
+            const int64_t o = (int64_t)r * ld;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) a = fma(cf[q], DB_LDCS(rv[q] + o), a);
+        }
         return a;
     };
     // Both sections are padded to multiples of SOLVE_PF, so chunks are loaded without bounds checks.  The values and
@@ -364,7 +371,17 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
-    DB_LAUNCH(k_batches_solve, dim3(total_blocks), dim3(SOLVE_THREADS), 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    const dim3 g(total_blocks), b(SOLVE_THREADS);
+    const int nv = rhs->nvec;
+    if (nv <= 1) DB_LAUNCH(k_batches_solve<1>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 2) DB_LAUNCH(k_batches_solve<2>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 3) DB_LAUNCH(k_batches_solve<3>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 4) DB_LAUNCH(k_batches_solve<4>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 5) DB_LAUNCH(k_batches_solve<5>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 6) DB_LAUNCH(k_batches_solve<6>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv <= 8) DB_LAUNCH(k_batches_solve<8>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv <= 12) DB_LAUNCH(k_batches_solve<12>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else DB_LAUNCH(k_batches_solve<16>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
     return db_check_launch("batches_solve");
 }
 
