@@ -191,36 +191,31 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
                                const int32_t* __restrict__ prog, int n_fwd, int n_entries,
                                db_lincomb rhs, double* __restrict__ xg)
 {
+    // plain sequential interpreter of the solve stream (reference implementation; the pipelined fused kernel below
+    // must agree with it)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const double* __restrict__ f = lu + s;
     double* __restrict__ x = xg + s;
-    int row = 0;
-    double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
-    for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][s], acc);
-    for (int e = 0; e < n_fwd; ++e) {
-        const int c = prog[e];
-        if (c >= 0) acc = fma(-f[(int64_t)e * ld], (c & DB_I_FRESH_REG) ? ((c & 3) == 1 ? l1 : (c & 3) == 2 ? l2 : l3) : x[c & DB_I_OFFMASK], acc);
-        else if (c == DB_I_END) {
-            x[(int64_t)row * ld] = acc;
-            l3 = l2; l2 = l1; l1 = acc;
-            ++row;
-            acc = 0.0;
-            if (row < n) for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][(int64_t)row * ld + s], acc);
-        }
-    }
-    row = n - 1;
-    acc = x[(int64_t)row * ld];
-    for (int e = n_fwd; e < n_entries; ++e) {
-        const int c = prog[e];
-        const double v = f[(int64_t)e * ld];
-        if (c >= 0) acc = fma(-v, (c & DB_I_FRESH_REG) ? ((c & 3) == 1 ? l1 : (c & 3) == 2 ? l2 : l3) : x[c & DB_I_OFFMASK], acc);
-        else if (c == DB_I_END) {
-            const double xi = acc * v;
-            x[(int64_t)row * ld] = xi;
-            l3 = l2; l2 = l1; l1 = xi;
-            --row;
-            if (row >= 0) acc = x[(int64_t)row * ld];
+    for (int sec = 0; sec < 2; ++sec) {
+        const int e0 = sec ? n_fwd : 0, e1 = sec ? n_entries : n_fwd;
+        int cur = -1;
+        double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+        for (int e = e0; e < e1; ++e) {
+            const int c = prog[e];
+            if (c == DB_I_SKIP) continue;
+            if (c < 0) {
+                if (cur >= 0) {
+                    const double val = sec ? acc * f[(int64_t)e * ld] : acc;
+                    x[cur] = val; l3 = l2; l2 = l1; l1 = val;
+                }
+                cur = -1 - c;
+                if (sec) acc = x[cur];
+                else { acc = 0.0; for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][cur + s], acc); }
+            } else {
+                const double xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK];
+                acc = fma(-f[(int64_t)e * ld], xx, acc);
+            }
         }
     }
 }
@@ -271,7 +266,9 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 }
 
 #define SOLVE_THREADS 64
-#define SOLVE_PF 8
+#define SOLVE_CH 8
+struct SolveChunk { double v[SOLVE_CH]; int c[SOLVE_CH]; double xv[SOLVE_CH]; };
+
 // NV = number of right-hand-side vectors (compile time: pointers and coefficients stay in registers)
 template <int NV>
 __global__ void __launch_bounds__(SOLVE_THREADS)
@@ -281,7 +278,7 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     const db_batch& B = batches[bi];
     const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
     if (s >= B.S) return;
-    const int ld = B.ld, n = B.n;
+    const int ld = B.ld;
     const double* __restrict__ fp = B.lu[lu_slot] + s;        // factor stream pointer, advances by ld per entry
     const int32_t* __restrict__ pp = B.prog;                  // instruction stream pointer
     double* __restrict__ x = B.vec[x_slot] + s;
@@ -289,81 +286,72 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     double cf[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + s; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
-    auto rhs_at = [&](int r) -> double {
-        double a = 0.0;
-        if (r < n) {
-            const int64_t o = (int64_t)r * ld;
-#pragma unroll
-            for (int q = 0; q < NV; ++q) a = fma(cf[q], DB_LDCS(rv[q] + o), a);
-        }
-        return a;
-    };
-    // Both sections are padded to multiples of SOLVE_PF, so chunks are loaded without bounds checks.  The values and
-    // instructions of chunk c+1 are in flight while chunk c is consumed; RHS combinations / forward results of the
-    // next two rows are loaded ahead so that no HBM latency sits on the dependent chain.
-    double vn[SOLVE_PF]; int cn[SOLVE_PF];
-#define SOLVE_LOAD()                                                                       \
-    _Pragma("unroll") for (int j = 0; j < SOLVE_PF; ++j) { vn[j] = DB_LDCS(fp); cn[j] = pp[j]; fp += ld; } \
-    pp += SOLVE_PF;
-    const int nchunk_f = B.n_fwd / SOLVE_PF, nchunk_b = (B.n_entries - B.n_fwd) / SOLVE_PF;
-    int row = 0;
-    double acc = rhs_at(0), r1 = rhs_at(1), r2 = rhs_at(2);
-    double l1 = 0.0, l2 = 0.0, l3 = 0.0;           // the three most recently completed rows
-    SOLVE_LOAD()
-    for (int ch = 0; ch < nchunk_f; ++ch) {
-        double v[SOLVE_PF]; int c[SOLVE_PF];
-#pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; c[j] = cn[j]; }
-        if (ch + 1 < nchunk_f + nchunk_b) { SOLVE_LOAD() }     // the last forward chunk already prefetches the backward stream
-        double xv[SOLVE_PF];
-#pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) xv[j] = ((unsigned)c[j] < (unsigned)DB_I_FRESH_MEM) ? x[c[j]] : 0.0;   // plain codes only
-#pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) {
-            const int cj = c[j];
-            if (cj >= 0) {
-                double xx = xv[j];
-                if (cj & (DB_I_FRESH_REG | DB_I_FRESH_MEM))
-                    xx = (cj & DB_I_FRESH_REG) ? (((cj & 3) == 1) ? l1 : ((cj & 3) == 2) ? l2 : l3) : x[cj & DB_I_OFFMASK];
-                acc = fma(-v[j], xx, acc);
-            } else if (cj == DB_I_END) {
-                x[(int64_t)row * ld] = acc;
-                l3 = l2; l2 = l1; l1 = acc;
-                ++row;
-                acc = r1; r1 = r2; r2 = rhs_at(row + 2);
-            }
-        }
+    // Three-stage software pipeline over chunks of SOLVE_CH entries (all state in registers, roles rotate by unrolling):
+    //   stage A  load the factor values + instructions of chunk q+2        (HBM stream, evict-first)
+    //   stage B  preload the x values / row start values of chunk q+1      (L1 / L2)
+    //   stage C  consume chunk q                                           (dependent FMA chain only)
+    // Hazards of stage B running ahead of stage C are resolved by the host (DB_I_FRESH_* codes).
+#define SOLVE_LOADA(K)                                                                              \
+    _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) { K.v[j] = DB_LDCS(fp); K.c[j] = pp[j]; fp += ld; } \
+    pp += SOLVE_CH;
+#define SOLVE_PRELOAD(K, FWD)                                                                       \
+    _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) {                                          \
+        const int c = K.c[j];                                                                       \
+        double val = 0.0;                                                                           \
+        if (c >= 0) { if (c < DB_I_FRESH_MEM) val = x[c]; }                                         \
+        else if (c != DB_I_SKIP) {                                                                  \
+            const int o = -1 - c;                                                                   \
+            if (FWD) { _Pragma("unroll") for (int q = 0; q < NV; ++q) val = fma(cf[q], DB_LDCS(rv[q] + o), val); } \
+            else val = x[o];                                                                        \
+        }                                                                                           \
+        K.xv[j] = val;                                                                              \
     }
-    row = n - 1;
-    acc = x[(int64_t)row * ld];
-    double y1 = (row >= 1) ? x[(int64_t)(row - 1) * ld] : 0.0;
-    double y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
-    for (int ch = 0; ch < nchunk_b; ++ch) {
-        double v[SOLVE_PF]; int c[SOLVE_PF];
-#pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) { v[j] = vn[j]; c[j] = cn[j]; }
-        if (ch + 1 < nchunk_b) { SOLVE_LOAD() }
-        double xv[SOLVE_PF];
-#pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) xv[j] = ((unsigned)c[j] < (unsigned)DB_I_FRESH_MEM) ? x[c[j]] : 0.0;
-#pragma unroll
-        for (int j = 0; j < SOLVE_PF; ++j) {
-            const int cj = c[j];
-            if (cj >= 0) {
-                double xx = xv[j];
-                if (cj & (DB_I_FRESH_REG | DB_I_FRESH_MEM))
-                    xx = (cj & DB_I_FRESH_REG) ? (((cj & 3) == 1) ? l1 : ((cj & 3) == 2) ? l2 : l3) : x[cj & DB_I_OFFMASK];
-                acc = fma(-v[j], xx, acc);
-            } else if (cj == DB_I_END) {
-                const double xi = acc * v[j];
-                x[(int64_t)row * ld] = xi;
-                l3 = l2; l2 = l1; l1 = xi;
-                --row;
-                acc = y1; y1 = y2; y2 = (row >= 2) ? x[(int64_t)(row - 2) * ld] : 0.0;
-            }
-        }
+#define SOLVE_COMPUTE(K, FWD)                                                                       \
+    _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) {                                          \
+        const int c = K.c[j];                                                                       \
+        if (c >= 0) {                                                                               \
+            double xx = K.xv[j];                                                                    \
+            if (c >= DB_I_FRESH_MEM)                                                                \
+                xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK]; \
+            acc = fma(-K.v[j], xx, acc);                                                            \
+        } else if (c != DB_I_SKIP) {                                                                \
+            if (cur >= 0) {                                                                         \
+                const double val = (FWD) ? acc : acc * K.v[j];                                      \
+                x[cur] = val; l3 = l2; l2 = l1; l1 = val;                                           \
+            }                                                                                       \
+            cur = -1 - c;                                                                           \
+            acc = K.xv[j];                                                                          \
+        }                                                                                           \
     }
-#undef SOLVE_LOAD
+#define SOLVE_SECTION(NCH, FWD)                                                                     \
+    {                                                                                               \
+        const int nch = (NCH);                                                                      \
+        int cur = -1;                                                                               \
+        double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;                                             \
+        SolveChunk K0, K1, K2;                                                                      \
+        SOLVE_LOADA(K0)                                                                             \
+        if (nch > 1) { SOLVE_LOADA(K1) }                                                            \
+        SOLVE_PRELOAD(K0, FWD)                                                                      \
+        for (int ch = 0; ch < nch; ch += 3) {                                                       \
+            if (ch + 2 < nch) { SOLVE_LOADA(K2) }                                                   \
+            if (ch + 1 < nch) { SOLVE_PRELOAD(K1, FWD) }                                            \
+            SOLVE_COMPUTE(K0, FWD)                                                                  \
+            if (ch + 1 >= nch) break;                                                               \
+            if (ch + 3 < nch) { SOLVE_LOADA(K0) }                                                   \
+            if (ch + 2 < nch) { SOLVE_PRELOAD(K2, FWD) }                                            \
+            SOLVE_COMPUTE(K1, FWD)                                                                  \
+            if (ch + 2 >= nch) break;                                                               \
+            if (ch + 4 < nch) { SOLVE_LOADA(K1) }                                                   \
+            if (ch + 3 < nch) { SOLVE_PRELOAD(K0, FWD) }                                            \
+            SOLVE_COMPUTE(K2, FWD)                                                                  \
+        }                                                                                           \
+    }
+    SOLVE_SECTION(B.n_fwd / SOLVE_CH, true)
+    SOLVE_SECTION((B.n_entries - B.n_fwd) / SOLVE_CH, false)
+#undef SOLVE_SECTION
+#undef SOLVE_COMPUTE
+#undef SOLVE_PRELOAD
+#undef SOLVE_LOADA
 }
 
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,

@@ -454,61 +454,76 @@ def compile_batch(batch, a0, b0):
     F = batch.symbolic_lu()
     prog = BatchProgram()
     prog.n, prog.S = n, batch.S
-    # ---- entry numbering in solve-stream order + flat instruction stream (include/dedalus_b200.h):
-    #   code >= 0 : acc -= LU[e] * x[code]        (code = column * ld, the element offset of that row in the vector)
-    #   DB_I_END  : end of row. forward: x[row] = acc (LU value unused); backward: x[row] = acc * LU[e] (reciprocal pivot)
-    #   DB_I_SKIP : padding so that each section is a multiple of the kernels' prefetch depth
-    END, SKIP, PAD = -1, -2, 8
+    # ---- solve stream (include/dedalus_b200.h).  Rows of each triangular solve are processed in LEVEL order of its
+    #      dependency DAG (rows of one level are mutually independent), which keeps a row's inputs several rows behind it
+    #      in the stream and lets the kernels preload x values two chunks ahead.  Codes:
+    #        c >= 0          : acc -= LU[e] * x_col ; plain: c = column*ld ; DB_I_FRESH_REG | k : k-th most recently
+    #                          completed row (registers) ; DB_I_FRESH_MEM | column*ld : re-read memory at compute time
+    #        c <  0, != SKIP : end of the current row (store; backward: multiply by LU[e] = reciprocal pivot) and start of
+    #                          row (-1 - c)/ld ; the first entry of a section only starts a row
+    #        DB_I_SKIP       : padding to a multiple of the chunk size
+    SKIP, CH = -2**31, 8
+    FRESH_REG, FRESH_MEM = 1 << 30, 1 << 29
     ld = ((batch.S + 31) // 32) * 32
     prog.ld = ld
-    if (n + 1) * ld >= 2**30:
-        raise NotImplementedError("batch too large for 30-bit vector offsets")
-
-    def codes(row, js):
-        return js.astype(np.int64) * ld
-    eid = -np.ones((n, n), dtype=np.int64)
-    instr = []
-    e = 0
-    for i in range(n):
-        js = np.nonzero(F[i, :i])[0]
-        eid[i, js] = e + np.arange(js.size)
-        instr.append(np.concatenate([codes(i, js), [END]])); e += js.size + 1
-    pad = (-e) % PAD
-    instr.append(np.full(pad, SKIP, dtype=np.int64)); e += pad
-    prog.n_fwd = e
-    diag_eid = np.zeros(n, dtype=np.int32)
-    for i in range(n - 1, -1, -1):
-        js = i + 1 + np.nonzero(F[i, i + 1:])[0]
-        eid[i, js] = e + np.arange(js.size)
-        e += js.size
-        diag_eid[i] = e; eid[i, i] = e; e += 1
-        instr.append(np.concatenate([codes(i, js), [END]]))
-    pad = (-e) % PAD
-    instr.append(np.full(pad, SKIP, dtype=np.int64)); e += pad
-    prog.nE = e
-    code = np.concatenate(instr).astype(np.int64)
-    assert len(code) == prog.nE
-    # ---- hazard marking for the kernels' chunk-wise preloading of x (PAD entries per chunk): an entry whose column
-    #      is completed earlier in the SAME chunk must not use the preloaded value.  The k-th most recently completed
-    #      row (k <= 3) is kept in registers (DB_I_FRESH_REG | k); anything else re-reads memory (DB_I_FRESH_MEM | off).
-    FRESH_REG, FRESH_MEM = 1 << 30, 1 << 29
     if (n + 1) * ld >= FRESH_MEM:
         raise NotImplementedError("batch too large for 29-bit vector offsets")
-    for sec0, sec1, step in ((0, prog.n_fwd, +1), (prog.n_fwd, prog.nE, -1)):
-        row = 0 if step > 0 else n - 1
-        done_at = {}                       # row -> stream position of its END entry
-        for pos in range(sec0, sec1):
-            c = code[pos]
-            if c == END:
-                done_at[row] = pos
-                row += step
-            elif c >= 0:
+    lev_f = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        js = np.nonzero(F[i, :i])[0]
+        lev_f[i] = 1 + (lev_f[js].max() if js.size else 0)
+    lev_b = np.zeros(n, dtype=np.int64)
+    for i in range(n - 1, -1, -1):
+        js = i + 1 + np.nonzero(F[i, i + 1:])[0]
+        lev_b[i] = 1 + (lev_b[js].max() if js.size else 0)
+    order_f = np.lexsort((np.arange(n), lev_f))
+    order_b = np.lexsort((-np.arange(n), lev_b))
+    prog.levels = (int(lev_f.max()), int(lev_b.max()))
+    eid = -np.ones((n, n), dtype=np.int64)
+    diag_eid = np.zeros(n, dtype=np.int32)
+    code = []
+    e = 0
+
+    def emit_section(order, forward):
+        nonlocal e
+        sec = [-1 - int(order[0]) * ld]                 # start of the first row (its LU slot is unused)
+        e += 1
+        for idx, i in enumerate(order):
+            js = np.nonzero(F[i, :i])[0] if forward else i + 1 + np.nonzero(F[i, i + 1:])[0]
+            eid[i, js] = e + np.arange(js.size)
+            sec.extend((js.astype(np.int64) * ld).tolist())
+            e += js.size
+            if not forward:
+                diag_eid[i] = e; eid[i, i] = e
+            nxt = order[idx + 1] if idx + 1 < len(order) else i
+            sec.append(-1 - int(nxt) * ld)
+            e += 1
+        pad = (-len(sec)) % CH
+        sec.extend([SKIP] * pad); e += pad
+        # hazard marking: x values of chunk q are preloaded before chunk q-1 is computed
+        sec = np.array(sec, dtype=np.int64)
+        done_at, completed, cur = {}, [], None
+        for pos in range(len(sec)):
+            c = sec[pos]
+            if c == SKIP:
+                continue
+            if c < 0:
+                if cur is not None:
+                    done_at[cur] = pos; completed.append(cur)
+                cur = int((-1 - c) // ld)
+            else:
                 col = int(c // ld)
                 p_end = done_at.get(col)
-                if p_end is not None and p_end >= (pos // PAD) * PAD:
-                    k = (row - col) * step
-                    code[pos] = (FRESH_REG | k) if 1 <= k <= 3 else (FRESH_MEM | int(c))
-    prog.prog = code.astype(np.int32)
+                if p_end is not None and p_end >= (pos // CH - 1) * CH:
+                    k = len(completed) - completed.index(col)
+                    sec[pos] = (FRESH_REG | k) if k <= 3 else (FRESH_MEM | int(c))
+        return sec
+    sec_f = emit_section(order_f, True)
+    prog.n_fwd = len(sec_f)
+    sec_b = emit_section(order_b, False)
+    prog.nE = e
+    prog.prog = np.concatenate([sec_f, sec_b]).astype(np.int32)
+    assert len(prog.prog) == prog.nE
     prog.diag_eid = diag_eid
     # ---- factor program
     fl_ptr = np.zeros(n + 1, dtype=np.int32); fu_ptr = np.zeros(n + 1, dtype=np.int32)

@@ -140,19 +140,21 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
  * 4 launches (mat-vec, gather F, solve, scatter) however many classes / parity components the problem has, and small
  * batches (kx = 0 or ky = 0 pencils) run concurrently with the large ones instead of serialising on the stream.
  * `batches` is a DEVICE array of db_batch built once by the host; per-call arguments are slot indices.
- * The solve program is a flat instruction stream aligned one-to-one with the LU value stream (forward rows
- * 0..n-1, then backward rows n-1..0), each section padded to a multiple of 8 entries:
- *   prog[e] >= 0       : acc -= LU[e] * x_col.  Plain code = column * ld (element offset of that row in a vector); the
- *                        kernels preload these x values for a whole chunk of 8 entries at once.  Entries whose
- *                        column is completed earlier in the same chunk carry DB_I_FRESH_REG | k (k = 1..3: the k-th
- *                        most recently completed row, kept in registers) or DB_I_FRESH_MEM | offset (re-read memory)
- *   prog[e] == DB_I_END: row finished.  forward: x[row] = acc ; backward: x[row] = acc * LU[e] (reciprocal pivot)
- *   prog[e] == DB_I_SKIP: padding
+ * The solve program is a flat instruction stream aligned one-to-one with the LU value stream: a forward section
+ * then a backward section, each padded to a multiple of 8 entries.  Rows are visited in LEVEL order of the triangular
+ * solve's dependency DAG (rows of one level are independent), so a row's inputs sit several rows upstream and the
+ * kernel can preload x values two chunks ahead:
+ *   c >= 0            : acc -= LU[e] * x_col.  Plain code = column * ld (element offset of that row in a vector).
+ *                       DB_I_FRESH_REG | k: the column was completed too recently for the preload; it is the k-th most
+ *                       recently completed row (k = 1..3), held in registers.  DB_I_FRESH_MEM | column*ld: re-read memory.
+ *   c < 0, != DB_I_SKIP: end of the current row (forward: x[row] = acc; backward: x[row] = acc * LU[e], the reciprocal
+ *                       pivot) and start of row (-1 - c) / ld, whose start value (RHS combination / forward result) is
+ *                       preloaded like an x value.  The first entry of a section only starts a row.
+ *   DB_I_SKIP         : padding
  * ------------------------------------------------------------------------------------------------------- */
 #define DB_MAX_VECS 24
 #define DB_MAX_LU 4
-#define DB_I_END  (-1)
-#define DB_I_SKIP (-2)
+#define DB_I_SKIP ((int32_t)0x80000000)
 #define DB_I_FRESH_REG 0x40000000
 #define DB_I_FRESH_MEM 0x20000000
 #define DB_I_OFFMASK   0x1FFFFFFF

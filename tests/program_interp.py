@@ -32,21 +32,45 @@ def factor(prog, LU):
 
 
 def solve(prog, LU, rhs):
-    """Mirrors the kernels: chunks of 8 entries, plain x values preloaded at chunk start, FRESH entries served from the
-    three most recently completed rows or re-read."""
-    END, SKIP, FRESH_REG, FRESH_MEM, MASK, PF = -1, -2, 1 << 30, 1 << 29, (1 << 29) - 1, 8
+    """Mirrors csrc/pencil.cu k_batches_solve: chunks of 8 entries; plain x values (and the start value of the next row)
+    of chunk q are preloaded BEFORE chunk q-1 is computed; FRESH entries come from the three most recently completed rows
+    or are re-read at compute time."""
+    SKIP, FRESH_REG, FRESH_MEM, MASK, CH = -2**31, 1 << 30, 1 << 29, (1 << 29) - 1, 8
     n, ld = prog.n, prog.ld
     y = np.array(rhs, dtype=float, copy=True)
-    for sec0, sec1, step in ((0, prog.n_fwd, +1), (prog.n_fwd, prog.nE, -1)):
-        row = 0 if step > 0 else n - 1
-        acc = y[row].copy()
-        last = [None, None, None]
-        for e0 in range(sec0, sec1, PF):
-            codes = [int(prog.prog[e]) for e in range(e0, e0 + PF)]
-            pre = [y[c // ld].copy() if (c >= 0 and not (c & (FRESH_REG | FRESH_MEM))) else None for c in codes]
-            for j, c in enumerate(codes):
-                e = e0 + j
-                if c >= 0:
+    for sec0, sec1, forward in ((0, prog.n_fwd, True), (prog.n_fwd, prog.nE, False)):
+        nch = (sec1 - sec0) // CH
+
+        def preload(q):
+            out = []
+            for e in range(sec0 + q * CH, sec0 + (q + 1) * CH):
+                c = int(prog.prog[e])
+                if c == SKIP:
+                    out.append(None)
+                elif c < 0:
+                    out.append(y[(-1 - c) // ld].copy())          # rhs (forward) / forward result (backward) of the next row
+                elif c & (FRESH_REG | FRESH_MEM):
+                    out.append(None)
+                else:
+                    out.append(y[c // ld].copy())
+            return out
+        cur, acc, last = None, None, [None, None, None]
+        pre = preload(0)
+        for q in range(nch):
+            nxt = preload(q + 1) if q + 1 < nch else None
+            for j in range(CH):
+                e = sec0 + q * CH + j
+                c = int(prog.prog[e])
+                if c == SKIP:
+                    continue
+                if c < 0:
+                    if cur is not None:
+                        val = acc if forward else acc * LU[e]
+                        y[cur] = val
+                        last = [val.copy(), last[0], last[1]]
+                    cur = (-1 - c) // ld
+                    acc = pre[j]
+                else:
                     if c & FRESH_REG:
                         xv = last[(c & 3) - 1]
                     elif c & FRESH_MEM:
@@ -54,13 +78,7 @@ def solve(prog, LU, rhs):
                     else:
                         xv = pre[j]
                     acc = acc - LU[e] * xv
-                elif c == END:
-                    val = acc if step > 0 else acc * LU[e]
-                    y[row] = val
-                    last = [val.copy(), last[0], last[1]]
-                    row += step
-                    if 0 <= row < n:
-                        acc = y[row].copy()
+            pre = nxt
     return y
 
 
