@@ -10,11 +10,17 @@
 
 #define PB_THREADS 128
 
+// Tile-major storage of every [rows][systems] array of a batch (vectors: rows = n, factors: rows = n_entries):
+//   element (i, s)  ->  ((s / DB_TILE) * rows + i) * DB_TILE + (s % DB_TILE)
+// Each group of DB_TILE = 64 systems (one solve CTA) owns ONE contiguous slab that it streams front to back, so the
+// dominant factor stream is sequential in DRAM (row-buffer and TLB friendly) instead of striding by the batch size.
+__device__ __forceinline__ int64_t db_tbase(int s, int rows) { return ((int64_t)(s / DB_TILE) * rows) * DB_TILE + (s % DB_TILE); }
+
 // ---------------------------------------------------------------------------------------------------------
 // gather / scatter: tiled transposes between z-contiguous field lines and system-contiguous pencil vectors
 // ---------------------------------------------------------------------------------------------------------
 template <bool GATHER>
-__global__ void k_pencil_move(const double* __restrict__ src, double* __restrict__ dst, int S, int ld,
+__global__ void k_pencil_move(const double* __restrict__ src, double* __restrict__ dst, int S, int nrows,
                               const int64_t* __restrict__ line_base, const int32_t* __restrict__ line_kind,
                               const int32_t* __restrict__ line_ptr, const int32_t* __restrict__ line_pos,
                               const int64_t* __restrict__ sys_off, int ld_sys)
@@ -38,12 +44,12 @@ __global__ void k_pencil_move(const double* __restrict__ src, double* __restrict
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {       // write vec: tx -> system (contiguous)
             int m = m0 + r, s = s0 + tx;
-            if (s < S && m < len) dst[(int64_t)pos[m] * ld + s] = tile[tx * 33 + r];
+            if (s < S && m < len) dst[db_tbase(s, nrows) + (int64_t)pos[m] * DB_TILE] = tile[tx * 33 + r];
         }
     } else {
         for (int r = ty; r < 32; r += 8) {
             int m = m0 + r, s = s0 + tx;
-            if (s < S && m < len) tile[tx * 33 + r] = src[(int64_t)pos[m] * ld + s];
+            if (s < S && m < len) tile[tx * 33 + r] = src[db_tbase(s, nrows) + (int64_t)pos[m] * DB_TILE];
         }
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
@@ -53,23 +59,23 @@ __global__ void k_pencil_move(const double* __restrict__ src, double* __restrict
     }
 }
 
-extern "C" int db_pencil_gather(const double* arena, double* vec, int32_t S, int32_t ld, int32_t nlines, int32_t max_len,
+extern "C" int db_pencil_gather(const double* arena, double* vec, int32_t S, int32_t n, int32_t nlines, int32_t max_len,
                                 const int64_t* line_base, const int32_t* line_kind, const int32_t* line_ptr, const int32_t* line_pos,
                                 const int64_t* sys_off, int32_t ld_sys, void* stream)
 {
     if (S <= 0 || nlines <= 0 || max_len <= 0) return 0;
     dim3 grid((S + 31) / 32, (max_len + 31) / 32, nlines), block(32, 8);
-    DB_LAUNCH(k_pencil_move<true>, grid, block, 32 * 33 * sizeof(double), stream, arena, vec, S, ld, line_base, line_kind, line_ptr, line_pos, sys_off, ld_sys);
+    DB_LAUNCH(k_pencil_move<true>, grid, block, 32 * 33 * sizeof(double), stream, arena, vec, S, n, line_base, line_kind, line_ptr, line_pos, sys_off, ld_sys);
     return db_check_launch("pencil_gather");
 }
 
-extern "C" int db_pencil_scatter(const double* vec, double* arena, int32_t S, int32_t ld, int32_t nlines, int32_t max_len,
+extern "C" int db_pencil_scatter(const double* vec, double* arena, int32_t S, int32_t n, int32_t nlines, int32_t max_len,
                                  const int64_t* line_base, const int32_t* line_kind, const int32_t* line_ptr, const int32_t* line_pos,
                                  const int64_t* sys_off, int32_t ld_sys, void* stream)
 {
     if (S <= 0 || nlines <= 0 || max_len <= 0) return 0;
     dim3 grid((S + 31) / 32, (max_len + 31) / 32, nlines), block(32, 8);
-    DB_LAUNCH(k_pencil_move<false>, grid, block, 32 * 33 * sizeof(double), stream, vec, arena, S, ld, line_base, line_kind, line_ptr, line_pos, sys_off, ld_sys);
+    DB_LAUNCH(k_pencil_move<false>, grid, block, 32 * 33 * sizeof(double), stream, vec, arena, S, n, line_base, line_kind, line_ptr, line_pos, sys_off, ld_sys);
     return db_check_launch("pencil_scatter");
 }
 
@@ -78,26 +84,28 @@ extern "C" int db_pencil_scatter(const double* vec, double* arena, int32_t S, in
 // grid: (ceil(S/128), row chunks)
 // ---------------------------------------------------------------------------------------------------------
 #define MV_ROWS_PER_BLOCK 16
-__global__ void k_pencil_matvec(int n, int S, int ld, const double* __restrict__ mono_vals, const double* __restrict__ x,
-                                const int32_t* __restrict__ m_ptr, const int32_t* __restrict__ m_col, const int32_t* __restrict__ m_mono, const double* __restrict__ m_val, double* __restrict__ y_m,
-                                const int32_t* __restrict__ l_ptr, const int32_t* __restrict__ l_col, const int32_t* __restrict__ l_mono, const double* __restrict__ l_val, double* __restrict__ y_l)
+__global__ void k_pencil_matvec(int n, int S, int ld, const double* __restrict__ mono_vals, const double* x,
+                                const int32_t* __restrict__ m_ptr, const int32_t* __restrict__ m_col, const int32_t* __restrict__ m_mono, const double* __restrict__ m_val, double* y_m,
+                                const int32_t* __restrict__ l_ptr, const int32_t* __restrict__ l_col, const int32_t* __restrict__ l_mono, const double* __restrict__ l_val, double* y_l)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int r0 = blockIdx.y * MV_ROWS_PER_BLOCK;
     const int r1 = (r0 + MV_ROWS_PER_BLOCK < n) ? r0 + MV_ROWS_PER_BLOCK : n;
+    const int64_t tb = db_tbase(s, n);
+    x += tb; if (y_m) y_m += tb; if (y_l) y_l += tb;
     for (int i = r0; i < r1; ++i) {
         if (y_m) {
             double acc = 0.0;
             for (int t = m_ptr[i]; t < m_ptr[i + 1]; ++t)
-                acc = fma(m_val[t] * mono_vals[(int64_t)m_mono[t] * ld + s], x[(int64_t)m_col[t] * ld + s], acc);
-            y_m[(int64_t)i * ld + s] = acc;
+                acc = fma(m_val[t] * mono_vals[(int64_t)m_mono[t] * ld + s], x[(int64_t)m_col[t] * DB_TILE], acc);
+            y_m[(int64_t)i * DB_TILE] = acc;
         }
         if (y_l) {
             double acc = 0.0;
             for (int t = l_ptr[i]; t < l_ptr[i + 1]; ++t)
-                acc = fma(l_val[t] * mono_vals[(int64_t)l_mono[t] * ld + s], x[(int64_t)l_col[t] * ld + s], acc);
-            y_l[(int64_t)i * ld + s] = acc;
+                acc = fma(l_val[t] * mono_vals[(int64_t)l_mono[t] * ld + s], x[(int64_t)l_col[t] * DB_TILE], acc);
+            y_l[(int64_t)i * DB_TILE] = acc;
         }
     }
 }
@@ -128,7 +136,7 @@ __global__ void k_pencil_assemble(double* __restrict__ lu, int n_entries, int S,
         double v = 0.0;
         for (int t = asm_ptr[e]; t < asm_ptr[e + 1]; ++t)
             v = fma(asm_val[t], mono_vals[(int64_t)asm_mono[t] * ld + s], v);
-        lu[(int64_t)e * ld + s] = v;
+        lu[db_tbase(s, n_entries) + (int64_t)e * DB_TILE] = v;
     }
 }
 
@@ -145,7 +153,7 @@ extern "C" int db_pencil_assemble(double* lu, int32_t n_entries, int32_t S, int3
 // numeric LU on the static schedule (no pivot search: the order was fixed by the host's joint threshold
 // pivoting); reciprocal pivots are stored on the diagonal
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_pencil_factor(double* __restrict__ lu, int n, int S, int ld, const int32_t* __restrict__ diag_eid,
+__global__ void k_pencil_factor(double* __restrict__ lu, int n, int S, int n_entries, const int32_t* __restrict__ diag_eid,
                                 const int32_t* __restrict__ fl_ptr, const int32_t* __restrict__ fl_eid,
                                 const int32_t* __restrict__ fu_ptr, const int32_t* __restrict__ fu_eid,
                                 const int32_t* __restrict__ fd_eid, int32_t* __restrict__ info)
@@ -154,33 +162,34 @@ __global__ void k_pencil_factor(double* __restrict__ lu, int n, int S, int ld, c
     if (s >= S) return;
     int64_t dp = 0;
     bool bad = false;
+    lu += db_tbase(s, n_entries);
     for (int k = 0; k < n; ++k) {
-        const int64_t d = (int64_t)diag_eid[k] * ld + s;
+        const int64_t d = (int64_t)diag_eid[k] * DB_TILE;
         const double piv = lu[d];
         if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1e300)) bad = true;
         const double inv = 1.0 / piv;
         lu[d] = inv;
         const int u0 = fu_ptr[k], u1 = fu_ptr[k + 1];
         for (int a = fl_ptr[k]; a < fl_ptr[k + 1]; ++a) {
-            const int64_t le = (int64_t)fl_eid[a] * ld + s;
+            const int64_t le = (int64_t)fl_eid[a] * DB_TILE;
             const double l = lu[le] * inv;
             lu[le] = l;
             for (int b = u0; b < u1; ++b, ++dp) {
-                const int64_t de = (int64_t)fd_eid[dp] * ld + s;
-                lu[de] = fma(-l, lu[(int64_t)fu_eid[b] * ld + s], lu[de]);
+                const int64_t de = (int64_t)fd_eid[dp] * DB_TILE;
+                lu[de] = fma(-l, lu[(int64_t)fu_eid[b] * DB_TILE], lu[de]);
             }
         }
     }
     if (bad) atomicAdd(info, 1);
 }
 
-extern "C" int db_pencil_factor(double* lu, int32_t n, int32_t S, int32_t ld, const int32_t* diag_eid,
+extern "C" int db_pencil_factor(double* lu, int32_t n, int32_t S, int32_t n_entries, const int32_t* diag_eid,
                                 const int32_t* fl_ptr, const int32_t* fl_eid, const int32_t* fu_ptr, const int32_t* fu_eid,
                                 const int32_t* fd_eid, int32_t* info, void* stream)
 {
     if (S <= 0 || n <= 0) return 0;
     dim3 grid((S + 63) / 64), block(64);
-    DB_LAUNCH(k_pencil_factor, grid, block, 0, stream, lu, n, S, ld, diag_eid, fl_ptr, fl_eid, fu_ptr, fu_eid, fd_eid, info);
+    DB_LAUNCH(k_pencil_factor, grid, block, 0, stream, lu, n, S, n_entries, diag_eid, fl_ptr, fl_eid, fu_ptr, fu_eid, fd_eid, info);
     return db_check_launch("pencil_factor");
 }
 
@@ -195,8 +204,10 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
     // must agree with it)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const double* __restrict__ f = lu + s;
-    double* __restrict__ x = xg + s;
+    (void)ld;
+    const double* __restrict__ f = lu + db_tbase(s, n_entries);
+    const int64_t tb = db_tbase(s, n);
+    double* __restrict__ x = xg + tb;
     for (int sec = 0; sec < 2; ++sec) {
         const int e0 = sec ? n_fwd : 0, e1 = sec ? n_entries : n_fwd;
         int cur = -1;
@@ -206,15 +217,15 @@ __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int 
             if (c == DB_I_SKIP) continue;
             if (c < 0) {
                 if (cur >= 0) {
-                    const double val = sec ? acc * f[(int64_t)e * ld] : acc;
+                    const double val = sec ? acc * f[(int64_t)e * DB_TILE] : acc;
                     x[cur] = val; l3 = l2; l2 = l1; l1 = val;
                 }
                 cur = -1 - c;
                 if (sec) acc = x[cur];
-                else { acc = 0.0; for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][cur + s], acc); }
+                else { acc = 0.0; for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][tb + cur], acc); }
             } else {
                 const double xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK];
-                acc = fma(-f[(int64_t)e * ld], xx, acc);
+                acc = fma(-f[(int64_t)e * DB_TILE], xx, acc);
             }
         }
     }
@@ -278,21 +289,22 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     const db_batch& B = batches[bi];
     const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
     if (s >= B.S) return;
-    const int ld = B.ld;
-    const double* __restrict__ fp = B.lu[lu_slot] + s;        // factor stream pointer, advances by ld per entry
+    const int64_t tb = db_tbase(s, B.n);
+    const double* __restrict__ fp = B.lu[lu_slot] + db_tbase(s, B.n_entries);   // factor stream: contiguous slab per CTA
     const int32_t* __restrict__ pp = B.prog;                  // instruction stream pointer
-    double* __restrict__ x = B.vec[x_slot] + s;
+    double* __restrict__ x = B.vec[x_slot] + tb;
     const double* rv[NV];
     double cf[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + s; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
     // Three-stage software pipeline over chunks of SOLVE_CH entries (all state in registers, roles rotate by unrolling):
     //   stage A  load the factor values + instructions of chunk q+2        (HBM stream, evict-first)
     //   stage B  preload the x values / row start values of chunk q+1      (L1 / L2)
     //   stage C  consume chunk q                                           (dependent FMA chain only)
     // Hazards of stage B running ahead of stage C are resolved by the host (DB_I_FRESH_* codes).
 #define SOLVE_LOADA(K)                                                                              \
-    _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) { K.v[j] = DB_LDCS(fp); K.c[j] = pp[j]; fp += ld; } \
+    _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) { K.v[j] = DB_LDCS(fp + j * DB_TILE); K.c[j] = pp[j]; } \
+    fp += SOLVE_CH * DB_TILE;                                                                       \
     pp += SOLVE_CH;
 #define SOLVE_PRELOAD(K, FWD)                                                                       \
     _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) {                                          \
@@ -385,7 +397,8 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
     const int r0 = (local / sblocks) * MV_ROWS_PER_BLOCK;
     const int n = B.n, ld = B.ld;
     const int r1 = (r0 + MV_ROWS_PER_BLOCK < n) ? r0 + MV_ROWS_PER_BLOCK : n;
-    const double* __restrict__ x = B.vec[x_slot] + s;
+    const int64_t tb = db_tbase(s, n);
+    const double* __restrict__ x = B.vec[x_slot] + tb;
     const double* __restrict__ mono = B.mono + s;
     // two passes over the same rows (M then L); program pointers are copied to registers so the stores to y
     // cannot force reloads of the descriptor
@@ -396,14 +409,14 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
         const int32_t* __restrict__ col = which ? B.l_col : B.m_col;
         const int32_t* __restrict__ mon = which ? B.l_mono : B.m_mono;
         const double* __restrict__ val = which ? B.l_val : B.m_val;
-        double* __restrict__ y = B.vec[slot] + s;
+        double* __restrict__ y = B.vec[slot] + tb;
         int t = ptr[r0];
         for (int i = r0; i < r1; ++i) {
             const int t1 = ptr[i + 1];
             double acc = 0.0;
             for (; t < t1; ++t)
-                acc = fma(val[t] * mono[(int64_t)mon[t] * ld], x[(int64_t)col[t] * ld], acc);
-            y[(int64_t)i * ld] = acc;
+                acc = fma(val[t] * mono[(int64_t)mon[t] * ld], x[(int64_t)col[t] * DB_TILE], acc);
+            y[(int64_t)i * DB_TILE] = acc;
         }
     }
 }
@@ -444,12 +457,12 @@ __global__ void k_batches_move(const db_batch* __restrict__ batches, int nbatch,
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
             int m = m0 + r, s = s0 + tx;
-            if (s < S && m < len) vec[(int64_t)pos[m] * ld + s] = tile[tx * 33 + r];
+            if (s < S && m < len) vec[db_tbase(s, B.n) + (int64_t)pos[m] * DB_TILE] = tile[tx * 33 + r];
         }
     } else {
         for (int r = ty; r < 32; r += 8) {
             int m = m0 + r, s = s0 + tx;
-            if (s < S && m < len) tile[tx * 33 + r] = vec[(int64_t)pos[m] * ld + s];
+            if (s < S && m < len) tile[tx * 33 + r] = vec[db_tbase(s, B.n) + (int64_t)pos[m] * DB_TILE];
         }
         __syncthreads();
         for (int r = ty; r < 32; r += 8) {
@@ -480,14 +493,14 @@ k_batches_assemble(const db_batch* __restrict__ batches, int nbatch, int lu_slot
     if (s >= B.S) return;
     const int e0 = (local / sblocks) * ASM_ENTRIES_PER_BLOCK;
     const int e1 = (e0 + ASM_ENTRIES_PER_BLOCK < B.n_entries) ? e0 + ASM_ENTRIES_PER_BLOCK : B.n_entries;
-    double* __restrict__ lu = B.lu[lu_slot] + s;
+    double* __restrict__ lu = B.lu[lu_slot] + db_tbase(s, B.n_entries);
     const double* __restrict__ mono = B.mono + s;
     const int ld = B.ld;
     for (int e = e0; e < e1; ++e) {
         double v = 0.0;
         for (int t = B.asm_ptr[e]; t < B.asm_ptr[e + 1]; ++t)
             v = fma(B.asm_val[t], mono[(int64_t)B.asm_mono[t] * ld], v);
-        lu[(int64_t)e * ld] = v;
+        lu[(int64_t)e * DB_TILE] = v;
     }
 }
 
@@ -506,24 +519,24 @@ k_batches_factor(const db_batch* __restrict__ batches, int nbatch, int lu_slot)
     const db_batch& B = batches[bi];
     const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
     if (s >= B.S) return;
-    const int ld = B.ld, n = B.n;
-    double* __restrict__ lu = B.lu[lu_slot] + s;
+    const int n = B.n;
+    double* __restrict__ lu = B.lu[lu_slot] + db_tbase(s, B.n_entries);
     int64_t dp = 0;
     bool bad = false;
     for (int k = 0; k < n; ++k) {
-        const int64_t d = (int64_t)B.diag_eid[k] * ld;
+        const int64_t d = (int64_t)B.diag_eid[k] * DB_TILE;
         const double piv = lu[d];
         if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1e300)) bad = true;
         const double inv = 1.0 / piv;
         lu[d] = inv;
         const int u0 = B.fu_ptr[k], u1 = B.fu_ptr[k + 1];
         for (int a = B.fl_ptr[k]; a < B.fl_ptr[k + 1]; ++a) {
-            const int64_t le = (int64_t)B.fl_eid[a] * ld;
+            const int64_t le = (int64_t)B.fl_eid[a] * DB_TILE;
             const double l = lu[le] * inv;
             lu[le] = l;
             for (int b = u0; b < u1; ++b, ++dp) {
-                const int64_t de = (int64_t)B.fd_eid[dp] * ld;
-                lu[de] = fma(-l, lu[(int64_t)B.fu_eid[b] * ld], lu[de]);
+                const int64_t de = (int64_t)B.fd_eid[dp] * DB_TILE;
+                lu[de] = fma(-l, lu[(int64_t)B.fu_eid[b] * DB_TILE], lu[de]);
             }
         }
     }

@@ -464,10 +464,11 @@ def compile_batch(batch, a0, b0):
     #        DB_I_SKIP       : padding to a multiple of the chunk size
     SKIP, CH = -2**31, 8
     FRESH_REG, FRESH_MEM = 1 << 30, 1 << 29
-    ld = ((batch.S + 31) // 32) * 32
-    prog.ld = ld
-    if (n + 1) * ld >= FRESH_MEM:
-        raise NotImplementedError("batch too large for 29-bit vector offsets")
+    TILE = 64                        # DB_TILE: vectors / factors are stored tile-major, 64 systems per slab
+    ld = ((batch.S + TILE - 1) // TILE) * TILE
+    prog.ld, prog.tile = ld, TILE
+    if (n + 1) * TILE >= FRESH_MEM:
+        raise NotImplementedError("system too large for 29-bit vector offsets")
     lev_f = np.zeros(n, dtype=np.int64)
     for i in range(n):
         js = np.nonzero(F[i, :i])[0]
@@ -486,17 +487,17 @@ def compile_batch(batch, a0, b0):
 
     def emit_section(order, forward):
         nonlocal e
-        sec = [-1 - int(order[0]) * ld]                 # start of the first row (its LU slot is unused)
+        sec = [-1 - int(order[0]) * TILE]               # start of the first row (its LU slot is unused)
         e += 1
         for idx, i in enumerate(order):
             js = np.nonzero(F[i, :i])[0] if forward else i + 1 + np.nonzero(F[i, i + 1:])[0]
             eid[i, js] = e + np.arange(js.size)
-            sec.extend((js.astype(np.int64) * ld).tolist())
+            sec.extend((js.astype(np.int64) * TILE).tolist())
             e += js.size
             if not forward:
                 diag_eid[i] = e; eid[i, i] = e
             nxt = order[idx + 1] if idx + 1 < len(order) else i
-            sec.append(-1 - int(nxt) * ld)
+            sec.append(-1 - int(nxt) * TILE)
             e += 1
         pad = (-len(sec)) % CH
         sec.extend([SKIP] * pad); e += pad
@@ -510,9 +511,9 @@ def compile_batch(batch, a0, b0):
             if c < 0:
                 if cur is not None:
                     done_at[cur] = pos; completed.append(cur)
-                cur = int((-1 - c) // ld)
+                cur = int((-1 - c) // TILE)
             else:
-                col = int(c // ld)
+                col = int(c // TILE)
                 p_end = done_at.get(col)
                 if p_end is not None and p_end >= (pos // CH - 1) * CH:
                     k = len(completed) - completed.index(col)

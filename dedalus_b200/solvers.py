@@ -50,7 +50,7 @@ class DeviceBatch:
         prog = compile_batch(batch, a0, b0)
         self.prog = prog
         self.n, self.S = prog.n, prog.S
-        self.ld = ld = ((prog.S + 31) // 32) * 32
+        self.ld = ld = prog.ld          # systems padded to whole tiles of 64 (tile-major storage, see include/dedalus_b200.h)
         mono = np.zeros((len(prog.monos), ld)); mono[:, :prog.S] = prog.mono_vals
         f = lambda a: _i32(torch, a, dev)
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
@@ -70,13 +70,13 @@ class DeviceBatch:
         ptr, mono_i, val = assembly_program(batch, prog, a0, b0)
         self.t['asm_ptr'], self.t['asm_mono'], self.t['asm_val'] = f(ptr), f(mono_i), d(val)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.vecs = [torch.zeros((self.n, ld), dtype=torch.float64, device=dev) for _ in range(nslots)]
+        self.vecs = [torch.zeros(self.n * ld, dtype=torch.float64, device=dev) for _ in range(nslots)]
         self.lu = {}
 
     def lu_tensor(self, slot):
         import torch
         if slot not in self.lu:
-            self.lu[slot] = torch.empty((self.prog.nE, self.ld), dtype=torch.float64, device=self.solver.device)
+            self.lu[slot] = torch.zeros(self.prog.nE * self.ld, dtype=torch.float64, device=self.solver.device)
         return self.lu[slot]
 
     def set_lhs(self, a0, b0):

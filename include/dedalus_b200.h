@@ -92,16 +92,20 @@ int db_pointwise(const double* in, double* out, int64_t npoints, int32_t n_in, i
                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Pencil systems (S1-S4).  A batch holds S structurally identical systems of size n, stored
- * structure-of-arrays: vec[i*ld + s], LU[e*ld + s]  (ld >= S, multiple of 32).  One thread owns one system.
+ * Pencil systems (S1-S4).  A batch holds S structurally identical systems of size n; one thread owns one system.
+ * Every [rows][systems] array (vectors: rows = n; factors: rows = n_entries) is stored TILE-MAJOR:
+ *     element (i, s)  at  ((s / DB_TILE) * rows + i) * DB_TILE + (s % DB_TILE),      DB_TILE = 64
+ * so each group of 64 systems owns one contiguous slab (coalesced across systems, sequential along rows / entries).
+ * Arrays are allocated for ceil(S / DB_TILE) tiles.  `ld` (>= S) is the stride of the small per-system tables
+ * (mono_vals[m*ld + s], sys_off[kind*ld + s]).
  * ------------------------------------------------------------------------------------------------------- */
 /* gather: field arena -> pencil vectors (Subproblem.gather_inputs/gather_outputs, core/subsystems.py:340-362)
  * scatter: pencil vectors -> field arena (Subproblem.scatter_inputs, core/subsystems.py:364-371).
- * Line q: arena offset line_base[q] + sys_off[line_kind[q]*ld_sys + s] + m  <->  vec[line_pos[line_ptr[q]+m]*ld + s]. */
-int db_pencil_gather(const double* arena, double* vec, int32_t S, int32_t ld, int32_t nlines, int32_t max_len,
+ * Line q: arena offset line_base[q] + sys_off[line_kind[q]*ld_sys + s] + m  <->  vec element (line_pos[line_ptr[q]+m], s). */
+int db_pencil_gather(const double* arena, double* vec, int32_t S, int32_t n, int32_t nlines, int32_t max_len,
                      const int64_t* line_base, const int32_t* line_kind, const int32_t* line_ptr, const int32_t* line_pos,
                      const int64_t* sys_off, int32_t ld_sys, void* stream);
-int db_pencil_scatter(const double* vec, double* arena, int32_t S, int32_t ld, int32_t nlines, int32_t max_len,
+int db_pencil_scatter(const double* vec, double* arena, int32_t S, int32_t n, int32_t nlines, int32_t max_len,
                       const int64_t* line_base, const int32_t* line_kind, const int32_t* line_ptr, const int32_t* line_pos,
                       const int64_t* sys_off, int32_t ld_sys, void* stream);
 
@@ -120,12 +124,14 @@ int db_pencil_assemble(double* lu, int32_t n_entries, int32_t S, int32_t ld, con
 
 /* in-place LU without pivoting on the static ordering (matsolver construction: libraries/matsolvers.py:126-157).
  * info[0] receives the number of systems that hit a zero / non-finite pivot. */
-int db_pencil_factor(double* lu, int32_t n, int32_t S, int32_t ld, const int32_t* diag_eid,
+int db_pencil_factor(double* lu, int32_t n, int32_t S, int32_t n_entries, const int32_t* diag_eid,
                      const int32_t* fl_ptr, const int32_t* fl_eid, const int32_t* fu_ptr, const int32_t* fu_eid,
                      const int32_t* fd_eid, int32_t* info, void* stream);
 
 /* x = LU^{-1} ( sum_j coef[j] * vecs[j] ): the right-hand-side combination of the IMEX schemes is fused into
  * the load (RHS build core/timesteppers.py:156-166, 617-623; solve 182-184, 641-642; matsolvers.py:141-157). */
+#define DB_TILE 64
+
 typedef struct {
     int32_t nvec;
     const double* vec[16];

@@ -36,7 +36,7 @@ def solve(prog, LU, rhs):
     of chunk q are preloaded BEFORE chunk q-1 is computed; FRESH entries come from the three most recently completed rows
     or are re-read at compute time."""
     SKIP, FRESH_REG, FRESH_MEM, MASK, CH = -2**31, 1 << 30, 1 << 29, (1 << 29) - 1, 8
-    n, ld = prog.n, prog.ld
+    n, ld = prog.n, prog.tile
     y = np.array(rhs, dtype=float, copy=True)
     for sec0, sec1, forward in ((0, prog.n_fwd, True), (prog.n_fwd, prog.nE, False)):
         nch = (sec1 - sec0) // CH
@@ -105,3 +105,13 @@ def scatter(maps, X, arena):
         for m in range(maps.line_len[q]):
             pos = maps.line_pos[maps.line_ptr[q] + m]
             arena[maps.line_base[q] + maps.sys_off[maps.line_kind[q]] + m] = X[pos]
+
+
+def to_tiles(a, tile=64):
+    """(rows, ld) row-major array -> flat tile-major storage used by the kernels (ld multiple of `tile`)."""
+    rows, ld = a.shape
+    return np.ascontiguousarray(a.reshape(rows, ld // tile, tile).transpose(1, 0, 2)).reshape(-1)
+
+
+def from_tiles(flat, rows, ld, tile=64):
+    return np.ascontiguousarray(flat.reshape(ld // tile, rows, tile).transpose(1, 0, 2)).reshape(rows, ld)

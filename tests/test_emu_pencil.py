@@ -28,48 +28,52 @@ def test_pencil_kernels_match_interpreters():
     for batch in batches:
         prog = compile_batch(batch, a0, b0)
         n, S = prog.n, prog.S
-        ld = ((S + 31) // 32) * 32
+        ld = prog.ld
         mono = np.zeros((len(prog.monos), ld)); mono[:, :S] = prog.mono_vals
         # --- assemble + factor
         aptr, amono, aval = assembly_program(batch, prog, a0, b0)
-        LU = np.zeros((prog.nE, ld))
-        lib.call("db_pencil_assemble", E.ptr(LU), prog.nE, S, ld, E.ptr(mono), E.ptr(_i32(aptr)), E.ptr(_i32(amono)), E.ptr(aval), None)
+        LUt = np.zeros(prog.nE * ld)
+        lib.call("db_pencil_assemble", E.ptr(LUt), prog.nE, S, ld, E.ptr(mono), E.ptr(_i32(aptr)), E.ptr(_i32(amono)), E.ptr(aval), None)
         ref_LU = pi.assemble(prog, (aptr, amono, aval))
-        assert np.allclose(LU[:, :S], ref_LU, rtol=0, atol=0)
+        assert np.allclose(pi.from_tiles(LUt, prog.nE, ld)[:, :S], ref_LU, rtol=0, atol=0)
         info = np.zeros(1, dtype=np.int32)
-        lib.call("db_pencil_factor", E.ptr(LU), n, S, ld, E.ptr(_i32(prog.diag_eid)), E.ptr(_i32(prog.fl_ptr)), E.ptr(_i32(prog.fl_eid)),
+        lib.call("db_pencil_factor", E.ptr(LUt), n, S, prog.nE, E.ptr(_i32(prog.diag_eid)), E.ptr(_i32(prog.fl_ptr)), E.ptr(_i32(prog.fl_eid)),
                  E.ptr(_i32(prog.fu_ptr)), E.ptr(_i32(prog.fu_eid)), E.ptr(_i32(prog.fd_eid)), E.ptr(info), None)
         assert info[0] == 0
         ref_LU = pi.factor(prog, ref_LU)
-        assert np.allclose(LU[:, :S], ref_LU, rtol=1e-13, atol=1e-13)
+        assert np.allclose(pi.from_tiles(LUt, prog.nE, ld)[:, :S], ref_LU, rtol=1e-13, atol=1e-13)
         # --- gather state -> X, matvec, solve with a fused 3-term RHS, scatter back
         maps = line_maps(batch, var_arena, 'cols')
-        X = np.zeros((n, ld))
+        Xt = np.zeros(n * ld)
         kind_ext = _i32(maps.line_kind)
         sys_off = np.zeros((maps.sys_off.shape[0], ld), dtype=np.int64); sys_off[:, :S] = maps.sys_off
         max_len = int(maps.line_len.max())
-        lib.call("db_pencil_gather", E.ptr(state), E.ptr(X), S, ld, len(maps.line_base), max_len, E.ptr(maps.line_base), E.ptr(kind_ext),
+        lib.call("db_pencil_gather", E.ptr(state), E.ptr(Xt), S, n, len(maps.line_base), max_len, E.ptr(maps.line_base), E.ptr(kind_ext),
                  E.ptr(_i32(maps.line_ptr)), E.ptr(_i32(maps.line_pos)), E.ptr(sys_off), ld, None)
         Xref = pi.gather(maps, state, n, S)
+        X = pi.from_tiles(Xt, n, ld)
         assert np.array_equal(X[:, :S], Xref)
-        yM = np.zeros((n, ld)); yL = np.zeros((n, ld))
+        yMt = np.zeros(n * ld); yLt = np.zeros(n * ld)
         mM, mL = prog.mv['M'], prog.mv['L']
-        lib.call("db_pencil_matvec", n, S, ld, E.ptr(mono), E.ptr(X), E.ptr(mM[0]), E.ptr(mM[1]), E.ptr(mM[2]), E.ptr(mM[3]), E.ptr(yM),
-                 E.ptr(mL[0]), E.ptr(mL[1]), E.ptr(mL[2]), E.ptr(mL[3]), E.ptr(yL), None)
+        lib.call("db_pencil_matvec", n, S, ld, E.ptr(mono), E.ptr(Xt), E.ptr(mM[0]), E.ptr(mM[1]), E.ptr(mM[2]), E.ptr(mM[3]), E.ptr(yMt),
+                 E.ptr(mL[0]), E.ptr(mL[1]), E.ptr(mL[2]), E.ptr(mL[3]), E.ptr(yLt), None)
+        yM, yL = pi.from_tiles(yMt, n, ld), pi.from_tiles(yLt, n, ld)
         assert np.allclose(yM[:, :S], pi.matvec(prog, 'M', Xref), rtol=1e-13, atol=1e-13)
         assert np.allclose(yL[:, :S], pi.matvec(prog, 'L', Xref), rtol=1e-13, atol=1e-12)
         F = np.zeros((n, ld)); F[:, :S] = rng.standard_normal((n, S))
+        Ft = pi.to_tiles(F)
         lc = dlib.LinComb(); lc.nvec = 3
-        for j, (v, c) in enumerate(((yM, 1.0), (F, 0.3), (yL, -0.7))):
+        for j, (v, c) in enumerate(((yMt, 1.0), (Ft, 0.3), (yLt, -0.7))):
             lc.vec[j] = v.ctypes.data; lc.coef[j] = c
-        xs = np.zeros((n, ld))
-        lib.call("db_pencil_solve", E.ptr(LU), n, S, ld, E.ptr(_i32(prog.prog)), prog.n_fwd, prog.nE, C.byref(lc), E.ptr(xs), None)
+        xst = np.zeros(n * ld)
+        lib.call("db_pencil_solve", E.ptr(LUt), n, S, ld, E.ptr(_i32(prog.prog)), prog.n_fwd, prog.nE, C.byref(lc), E.ptr(xst), None)
+        xs = pi.from_tiles(xst, n, ld)
         rhs = yM + 0.3 * F - 0.7 * yL
         for s in range(0, S, max(1, S // 3)):
             A = batch.matrix((a0, b0), batch.groups[s]).tocsc()
             ref = spsolve(A, rhs[:, s])
             assert np.abs(xs[:, s] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
-        lib.call("db_pencil_scatter", E.ptr(X), E.ptr(state_out), S, ld, len(maps.line_base), max_len, E.ptr(maps.line_base), E.ptr(kind_ext),
+        lib.call("db_pencil_scatter", E.ptr(Xt), E.ptr(state_out), S, n, len(maps.line_base), max_len, E.ptr(maps.line_base), E.ptr(kind_ext),
                  E.ptr(_i32(maps.line_ptr)), E.ptr(_i32(maps.line_pos)), E.ptr(sys_off), ld, None)
         tmp = np.zeros(var_arena.size); pi.scatter(maps, np.ones((n, S)), tmp); covered |= tmp > 0
     # scatter(gather(state)) reproduces every valid state entry; invalid (sin 0) slots are never touched
