@@ -300,6 +300,7 @@ __device__ __forceinline__ void tile_iter(int len, const TileGeom& g, bool conti
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
         for (int t = warp; t < g.Tc; t += nw) {
             const int64_t off = g.base + t * g.lstride;
+#pragma unroll 4
             for (int j = lane; j < len; j += 32) f(j, t, off + j * g.estride);
         }
     } else {
@@ -309,6 +310,7 @@ __device__ __forceinline__ void tile_iter(int len, const TileGeom& g, bool conti
             int j = threadIdx.x >> lgT;
             int64_t off = g.base + t * g.lstride + j * g.estride;
             const int64_t step = js * g.estride;
+#pragma unroll 8
             for (; j < len; j += js, off += step) f(j, t, off);
         }
     }
@@ -628,16 +630,28 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
             };
             if (p.half) {
                 // pairs (k, nc-k): Z_k = E + iO, Z_{nc-k} = conj(E - iO), E = X_k + conj X_{nc-k}, O = (X_k - conj X_{nc-k}) w^{-k}
+                // batches of 4 pairs per thread: all coefficient loads of a batch are issued before any is consumed
                 const int npair = nc / 2 + 1;
-                for (int w = tid; w < (npair << lgT); w += nthreads) {
-                    const int t = w & Tmask, ka = w >> lgT, kb = nc - ka;
-                    const double2 xa = getX(ka, t);
-                    const double2 xb = getX(kb, t);
-                    const double2 E = make_double2(xa.x + xb.x, xa.y - xb.y);
-                    const double2 D = make_double2(xa.x - xb.x, xa.y + xb.y);
-                    const double2 O = cmulc(D, ldtw(p.twr, ka));
-                    buf[p.iperm[ka] * TP + t] = make_double2(E.x - O.y, E.y + O.x);
-                    if (kb != ka && kb < nc) buf[p.iperm[kb] * TP + t] = make_double2(E.x + O.y, -(E.y - O.x));
+                const int total = npair << lgT;
+                for (int w0 = tid; w0 < total; w0 += 4 * nthreads) {
+                    double2 xa[4], xb[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int w = w0 + it * nthreads;
+                        if (w < total) { const int t = w & Tmask, ka = w >> lgT; xa[it] = getX(ka, t); xb[it] = getX(nc - ka, t); }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int w = w0 + it * nthreads;
+                        if (w < total) {
+                            const int t = w & Tmask, ka = w >> lgT, kb = nc - ka;
+                            const double2 E = make_double2(xa[it].x + xb[it].x, xa[it].y - xb[it].y);
+                            const double2 D = make_double2(xa[it].x - xb[it].x, xa[it].y + xb[it].y);
+                            const double2 O = cmulc(D, ldtw(p.twr, ka));
+                            buf[p.iperm[ka] * TP + t] = make_double2(E.x - O.y, E.y + O.x);
+                            if (kb != ka && kb < nc) buf[p.iperm[kb] * TP + t] = make_double2(E.x + O.y, -(E.y - O.x));
+                        }
+                    }
                 }
             } else {
                 for (int w = tid; w < (nc << lgT); w += nthreads) {

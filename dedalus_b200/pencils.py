@@ -477,8 +477,12 @@ def compile_batch(batch, a0, b0):
     for i in range(n - 1, -1, -1):
         js = i + 1 + np.nonzero(F[i, i + 1:])[0]
         lev_b[i] = 1 + (lev_b[js].max() if js.size else 0)
-    order_f = np.lexsort((np.arange(n), lev_f))
-    order_b = np.lexsort((-np.arange(n), lev_b))
+    import os
+    if os.environ.get("DB_SOLVE_ORDER", "level") == "natural":
+        order_f = np.arange(n); order_b = np.arange(n - 1, -1, -1)
+    else:
+        order_f = np.lexsort((np.arange(n), lev_f))
+        order_b = np.lexsort((-np.arange(n), lev_b))
     prog.levels = (int(lev_f.max()), int(lev_b.max()))
     eid = -np.ones((n, n), dtype=np.int64)
     diag_eid = np.zeros(n, dtype=np.int32)
