@@ -20,6 +20,25 @@
 #define DB_LDCS(p) __ldcs(p)           // streaming (evict-first) load: one-pass data must not displace reused lines
 #endif
 
+// asynchronous global -> shared copies (LDGSTS) used for deep software prefetch without register cost
+#ifdef DB_EMU
+__device__ __forceinline__ void db_cp_async8(void* dst, const void* src) { *reinterpret_cast<double*>(dst) = *reinterpret_cast<const double*>(src); }
+__device__ __forceinline__ void db_cp_async4(void* dst, const void* src) { *reinterpret_cast<int*>(dst) = *reinterpret_cast<const int*>(src); }
+__device__ __forceinline__ void db_cp_commit() {}
+template <int N> __device__ __forceinline__ void db_cp_wait() {}
+#else
+__device__ __forceinline__ void db_cp_async8(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void db_cp_async4(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void db_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void db_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
 #include "../../include/dedalus_b200.h"
 
 // error plumbing (thread-compatible: one stream per rank, last error per process)

@@ -55,9 +55,12 @@ def solve(prog, LU, rhs):
                     out.append(y[c // ld].copy())
             return out
         cur, acc, last = None, None, [None, None, None]
-        pre = preload(0)
+        DB = 2                                         # S_DB: x values of chunk q are preloaded before chunk q-2 is computed
+        pres = {q: preload(q) for q in range(min(DB, nch))}
         for q in range(nch):
-            nxt = preload(q + 1) if q + 1 < nch else None
+            if q + DB < nch:
+                pres[q + DB] = preload(q + DB)
+            pre = pres.pop(q)
             for j in range(CH):
                 e = sec0 + q * CH + j
                 c = int(prog.prog[e])
@@ -78,7 +81,6 @@ def solve(prog, LU, rhs):
                     else:
                         xv = pre[j]
                     acc = acc - LU[e] * xv
-            pre = nxt
     return y
 
 
