@@ -277,105 +277,85 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 }
 
 #define SOLVE_THREADS 64
-#define S_CH 8                            // entries per chunk
-#define S_DA 5                            // factor / instruction lookahead in chunks  (must be >= 2 * S_DB + 1)
-#define S_DB 2                            // x-value lookahead in chunks (the host marks hazards for exactly this distance)
-#define S_R ((S_DA + 1) * S_CH)           // ring slots per thread
+#define SOLVE_CH 8
+struct SolveChunk { double v[SOLVE_CH]; int c[SOLVE_CH]; };
 
-// x[x_slot] = sum_j coef[j] * vec[slot[j]]   (right-hand-side combination of the IMEX schemes, one pass)
-__global__ void __launch_bounds__(256)
-k_batches_lincomb(const db_batch* __restrict__ batches, int nbatch, int x_slot, db_slotcomb rhs)
-{
-    // grid: blocks of the solve map (one CTA = one tile of 64 systems); 256 threads sweep the tile's n*64 elements
-    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
-    const db_batch& B = batches[bi];
-    const int tile = blockIdx.x - B.blk_solve;
-    const int64_t base = (int64_t)tile * B.n * DB_TILE;
-    const int64_t count = (int64_t)B.n * DB_TILE;
-    double* __restrict__ x = B.vec[x_slot] + base;
-    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
-        double a = 0.0;
-        for (int q = 0; q < rhs.nvec; ++q) a = fma(rhs.coef[q], DB_LDCS(B.vec[rhs.slot[q]] + base + i), a);
-        x[i] = a;
-    }
-}
-
-// Triangular solves, in place on vec[x_slot] (which holds the right-hand side on entry).
-// Deep software pipeline through shared-memory rings filled by asynchronous copies (LDGSTS), per thread:
-//   stage A  factor value + instruction of chunk q + S_DA   (HBM stream)        -> rv, rc
-//   stage B  x value / row-start value of chunk q + S_DB    (L1 / L2)           -> rx    (needs the instruction: A ran S_DA - S_DB chunks earlier)
-//   stage C  consume chunk q from shared memory: only the FMA chain is on the critical path
-// One commit group per chunk; a single wait_group<S_DB> per iteration orders all three stages because S_DA >= 2 S_DB + 1.
+// Triangular solves with the right-hand-side combination fused into the row starts.
+// NV = number of right-hand-side vectors (compile time: pointers and coefficients stay in registers).
+// Two-stage register pipeline over chunks of SOLVE_CH entries: the factor values + instructions of chunk q+1 are in
+// flight while chunk q is consumed; the x values / row-start values of chunk q are gathered in one burst right before
+// it is consumed (the host marks entries whose column completes inside the preload window, DB_I_FRESH_*).  Each CTA
+// streams one contiguous slab of the tile-major factor array.
+template <int NV>
 __global__ void __launch_bounds__(SOLVE_THREADS)
-k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot)
+k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs)
 {
-    DB_SMEM(double, smem);
-    double* rv = smem + threadIdx.x;                                  // [S_R][64]
-    double* rx = smem + S_R * SOLVE_THREADS + threadIdx.x;            // [S_R][64]
-    int* rc = reinterpret_cast<int*>(smem + 2 * S_R * SOLVE_THREADS) + threadIdx.x;   // [S_R][64]
     const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
     const db_batch& B = batches[bi];
     const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
     if (s >= B.S) return;
-    double* __restrict__ x = B.vec[x_slot] + db_tbase(s, B.n);
-    const double* __restrict__ lu = B.lu[lu_slot] + db_tbase(s, B.n_entries);
-    const int32_t* __restrict__ prog = B.prog;
-    for (int sec = 0; sec < 2; ++sec) {
-        const int e_base = sec ? B.n_fwd : 0;
-        const int nch = (sec ? (B.n_entries - B.n_fwd) : B.n_fwd) / S_CH;
-        const double* __restrict__ fp = lu + (int64_t)e_base * DB_TILE;
-        const int32_t* __restrict__ pp = prog + e_base;
-        int cur = -1;
-        double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
-        int slotA = 0, slotB = 0, slotC = 0;                          // ring positions of the chunk each stage handles next
-        for (int q = -S_DA; q < nch; ++q) {
-            // ---- stage A: chunk q + S_DA
-            if (q + S_DA < nch) {
-                const int64_t e0 = (int64_t)(q + S_DA) * S_CH;
+    const int64_t tb = db_tbase(s, B.n);
+    const double* __restrict__ fp = B.lu[lu_slot] + db_tbase(s, B.n_entries);
+    const int32_t* __restrict__ pp = B.prog;
+    double* __restrict__ x = B.vec[x_slot] + tb;
+    const double* rv[NV];
+    double cf[NV];
 #pragma unroll
-                for (int j = 0; j < S_CH; ++j) {
-                    db_cp_async8(rv + (slotA + j) * SOLVE_THREADS, fp + (e0 + j) * DB_TILE);
-                    db_cp_async4(rc + (slotA + j) * SOLVE_THREADS, pp + e0 + j);
-                }
-                slotA += S_CH; if (slotA == S_R) slotA = 0;
-            }
-            // ---- stage B: chunk q + S_DB (its instructions landed: group of iteration q + S_DB - S_DA <= q - 1 - S_DB)
-            if (q + S_DB >= 0 && q + S_DB < nch) {
-#pragma unroll
-                for (int j = 0; j < S_CH; ++j) {
-                    const int c = rc[(slotB + j) * SOLVE_THREADS];
-                    if (c >= 0) { if (c < DB_I_FRESH_MEM) db_cp_async8(rx + (slotB + j) * SOLVE_THREADS, x + c); }
-                    else if (c != DB_I_SKIP) db_cp_async8(rx + (slotB + j) * SOLVE_THREADS, x + (-1 - c));
-                }
-                slotB += S_CH; if (slotB == S_R) slotB = 0;
-            }
-            db_cp_commit();
-            db_cp_wait<S_DB>();
-            // ---- stage C: chunk q
-            if (q >= 0) {
-#pragma unroll
-                for (int j = 0; j < S_CH; ++j) {
-                    const int c = rc[(slotC + j) * SOLVE_THREADS];
-                    const double v = rv[(slotC + j) * SOLVE_THREADS];
-                    if (c >= 0) {
-                        double xx;
-                        if (c < DB_I_FRESH_MEM) xx = rx[(slotC + j) * SOLVE_THREADS];
-                        else xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK];
-                        acc = fma(-v, xx, acc);
-                    } else if (c != DB_I_SKIP) {
-                        if (cur >= 0) {
-                            const double val = sec ? acc * v : acc;
-                            x[cur] = val; l3 = l2; l2 = l1; l1 = val;
-                        }
-                        cur = -1 - c;
-                        acc = rx[(slotC + j) * SOLVE_THREADS];
-                    }
-                }
-                slotC += S_CH; if (slotC == S_R) slotC = 0;
-            }
-        }
-        db_cp_wait<0>();
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+#define SOLVE_LOADA(K)                                                                              \
+    _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) { K.v[j] = DB_LDCS(fp + j * DB_TILE); K.c[j] = pp[j]; } \
+    fp += SOLVE_CH * DB_TILE; pp += SOLVE_CH;
+#define SOLVE_COMPUTE(K, FWD)                                                                       \
+    {                                                                                               \
+        double xv[SOLVE_CH];                                                                        \
+        _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) {                                      \
+            const int c = K.c[j];                                                                   \
+            double val = 0.0;                                                                       \
+            if (c >= 0) { if (c < DB_I_FRESH_MEM) val = x[c]; }                                     \
+            else if (c != DB_I_SKIP) {                                                              \
+                const int o = -1 - c;                                                               \
+                if (FWD) { _Pragma("unroll") for (int q = 0; q < NV; ++q) val = fma(cf[q], DB_LDCS(rv[q] + o), val); } \
+                else val = x[o];                                                                    \
+            }                                                                                       \
+            xv[j] = val;                                                                            \
+        }                                                                                           \
+        _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) {                                      \
+            const int c = K.c[j];                                                                   \
+            if (c >= 0) {                                                                           \
+                double xx = xv[j];                                                                  \
+                if (c >= DB_I_FRESH_MEM)                                                            \
+                    xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK]; \
+                acc = fma(-K.v[j], xx, acc);                                                        \
+            } else if (c != DB_I_SKIP) {                                                            \
+                if (cur >= 0) {                                                                     \
+                    const double val = (FWD) ? acc : acc * K.v[j];                                  \
+                    x[cur] = val; l3 = l2; l2 = l1; l1 = val;                                       \
+                }                                                                                   \
+                cur = -1 - c;                                                                       \
+                acc = xv[j];                                                                        \
+            }                                                                                       \
+        }                                                                                           \
     }
+#define SOLVE_SECTION(NCH, FWD)                                                                     \
+    {                                                                                               \
+        const int nch = (NCH);                                                                      \
+        int cur = -1;                                                                               \
+        double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;                                             \
+        SolveChunk K0, K1;                                                                          \
+        SOLVE_LOADA(K0)                                                                             \
+        for (int ch = 0; ch < nch; ch += 2) {                                                       \
+            if (ch + 1 < nch) { SOLVE_LOADA(K1) }                                                   \
+            SOLVE_COMPUTE(K0, FWD)                                                                  \
+            if (ch + 1 >= nch) break;                                                               \
+            if (ch + 2 < nch) { SOLVE_LOADA(K0) }                                                   \
+            SOLVE_COMPUTE(K1, FWD)                                                                  \
+        }                                                                                           \
+    }
+    SOLVE_SECTION(B.n_fwd / SOLVE_CH, true)
+    SOLVE_SECTION((B.n_entries - B.n_fwd) / SOLVE_CH, false)
+#undef SOLVE_SECTION
+#undef SOLVE_COMPUTE
+#undef SOLVE_LOADA
 }
 
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
@@ -383,15 +363,17 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
-    // pass 1: right-hand-side combination into vec[x_slot]; pass 2: in-place triangular solves
-    DB_LAUNCH(k_batches_lincomb, dim3(total_blocks), dim3(256), 0, stream, batches, nbatch, x_slot, *rhs);
-    if (int rc = db_check_launch("batches_lincomb")) return rc;
-    const size_t smem = (size_t)S_R * SOLVE_THREADS * (2 * sizeof(double) + sizeof(int));
-#ifndef DB_EMU
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_batches_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM); attr = true; }
-#endif
-    DB_LAUNCH(k_batches_solve, dim3(total_blocks), dim3(SOLVE_THREADS), smem, stream, batches, nbatch, lu_slot, x_slot);
+    const dim3 g(total_blocks), b(SOLVE_THREADS);
+    const int nv = rhs->nvec;
+    if (nv <= 1) DB_LAUNCH(k_batches_solve<1>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 2) DB_LAUNCH(k_batches_solve<2>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 3) DB_LAUNCH(k_batches_solve<3>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 4) DB_LAUNCH(k_batches_solve<4>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 5) DB_LAUNCH(k_batches_solve<5>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv == 6) DB_LAUNCH(k_batches_solve<6>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv <= 8) DB_LAUNCH(k_batches_solve<8>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else if (nv <= 12) DB_LAUNCH(k_batches_solve<12>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    else DB_LAUNCH(k_batches_solve<16>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
     return db_check_launch("batches_solve");
 }
 

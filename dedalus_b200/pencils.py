@@ -505,7 +505,7 @@ def compile_batch(batch, a0, b0):
             e += 1
         pad = (-len(sec)) % CH
         sec.extend([SKIP] * pad); e += pad
-        # hazard marking: x values of chunk q are preloaded before chunk q-2 is computed (S_DB = 2 in csrc/pencil.cu)
+        # hazard marking: the x values of a chunk are gathered in one burst right before the chunk is consumed
         sec = np.array(sec, dtype=np.int64)
         done_at, completed, cur = {}, [], None
         for pos in range(len(sec)):
@@ -519,7 +519,7 @@ def compile_batch(batch, a0, b0):
             else:
                 col = int(c // TILE)
                 p_end = done_at.get(col)
-                if p_end is not None and p_end >= (pos // CH - 2) * CH:
+                if p_end is not None and p_end >= (pos // CH) * CH:
                     k = len(completed) - completed.index(col)
                     sec[pos] = (FRESH_REG | k) if k <= 3 else (FRESH_MEM | int(c))
         return sec

@@ -55,12 +55,9 @@ def solve(prog, LU, rhs):
                     out.append(y[c // ld].copy())
             return out
         cur, acc, last = None, None, [None, None, None]
-        DB = 2                                         # S_DB: x values of chunk q are preloaded before chunk q-2 is computed
-        pres = {q: preload(q) for q in range(min(DB, nch))}
+        DB = 0                                         # x values of chunk q are gathered right before chunk q is computed
         for q in range(nch):
-            if q + DB < nch:
-                pres[q + DB] = preload(q + DB)
-            pre = pres.pop(q)
+            pre = preload(q)
             for j in range(CH):
                 e = sec0 + q * CH + j
                 c = int(prog.prog[e])
