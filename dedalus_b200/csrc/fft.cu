@@ -222,24 +222,18 @@ __device__ __forceinline__ void static_dit(double2* buf, const double* tw)
     __syncthreads();
 }
 
-// returns true if a specialised path handled the transform (radix lists must match dedalus_b200/fftplan.py factorize)
-template <bool INV>
-__device__ __forceinline__ bool fft_static_dispatch(double2* buf, const db_fft_plan& p, int T)
+// compile-time selected pass sequences (radix lists must match dedalus_b200/fftplan.py factorize)
+template <bool INV, int NCS>
+__device__ __forceinline__ void fft_static(double2* buf, const double* tw)
 {
-    if (T != 16) return false;
-    const double* tw = p.tw;
-    switch (p.nc) {
-        case 192: if (INV) static_dit<192, 192, 4, 4, 4, 3>(buf, tw); else static_dif<192, 192, 4, 4, 4, 3>(buf, tw); return true;
-        case 384: if (INV) static_dit<384, 384, 4, 4, 4, 2, 3>(buf, tw); else static_dif<384, 384, 4, 4, 4, 2, 3>(buf, tw); return true;
-        case 96:  if (INV) static_dit<96, 96, 4, 4, 2, 3>(buf, tw); else static_dif<96, 96, 4, 4, 2, 3>(buf, tw); return true;
-        case 48:  if (INV) static_dit<48, 48, 4, 4, 3>(buf, tw); else static_dif<48, 48, 4, 4, 3>(buf, tw); return true;
-        default: return false;
-    }
+    if constexpr (NCS == 192) { if (INV) static_dit<192, 192, 4, 4, 4, 3>(buf, tw); else static_dif<192, 192, 4, 4, 4, 3>(buf, tw); }
+    else if constexpr (NCS == 384) { if (INV) static_dit<384, 384, 4, 4, 4, 2, 3>(buf, tw); else static_dif<384, 384, 4, 4, 4, 2, 3>(buf, tw); }
+    else if constexpr (NCS == 96) { if (INV) static_dit<96, 96, 4, 4, 2, 3>(buf, tw); else static_dif<96, 96, 4, 4, 2, 3>(buf, tw); }
+    else if constexpr (NCS == 48) { if (INV) static_dit<48, 48, 4, 4, 3>(buf, tw); else static_dif<48, 48, 4, 4, 3>(buf, tw); }
 }
 
 __device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
-    if (fft_static_dispatch<false>(buf, p, 1 << lgT)) return;
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) {
         fft_pass<false>(buf, p.nc, TP, lgT, p.rad[s], L, p.tw);
@@ -249,7 +243,6 @@ __device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int lgT)
 }
 __device__ void fft_dit(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
-    if (fft_static_dispatch<true>(buf, p, 1 << lgT)) return;
     int Ls[16];
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) { Ls[s] = L; L /= p.rad[s]; }
@@ -325,7 +318,8 @@ __device__ __forceinline__ double2 rot_i_pow(double2 z, int ph)
 // DIRECT: real-Fourier kernels on a strided axis read / write the coefficient rows straight from / to global memory
 // (each row segment is already a coalesced run across the tile's lines), skipping the shared-memory staging area:
 // one fewer shared round trip and barrier, and 40% less shared memory per CTA (-> 3-4 CTAs per SM)
-template <int KIND, bool DIRECT>
+// NCS > 0: complex FFT length fixed at compile time (tile width 16) -> only the specialised passes are compiled in
+template <int KIND, bool DIRECT, int NCS>
 __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
 {
     DB_SMEM(double, smem);
@@ -740,16 +734,35 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
         if (outer > 65535 || a.tiles_per_outer > 2147483647LL) { db_set_error("%s: outer extent %lld too large for a strided transform", name, (long long)outer); return 1; }
         grid = dim3((unsigned)a.tiles_per_outer, (unsigned)outer);
     }
-#ifndef DB_EMU
-    static bool attr_set[6][2] = {{false, false}, {false, false}, {false, false}, {false, false}, {false, false}, {false, false}};
-    if (!attr_set[KIND][direct ? 1 : 0]) {
-        if (direct) cudaFuncSetAttribute(k_fft<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
-        else cudaFuncSetAttribute(k_fft<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
-        attr_set[KIND][direct ? 1 : 0] = true;
+    int ncs = 0;
+    if (T == 16 && (plan->nc == 192 || plan->nc == 384 || plan->nc == 96 || plan->nc == 48)) ncs = plan->nc;
+#define FFT_LAUNCH_ONE(D, N)                                                                                          \
+    {                                                                                                                 \
+        auto kern = k_fft<KIND, D, N>;                                                                                \
+        FFT_SET_ATTR(kern)                                                                                            \
+        DB_LAUNCH(kern, grid, dim3(FFT_THREADS), bytes, stream, a);                                                   \
     }
+#ifdef DB_EMU
+#define FFT_SET_ATTR(kern)
+#else
+#define FFT_SET_ATTR(kern) { static bool done = false; if (!done) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM); done = true; } }
 #endif
-    if (direct) DB_LAUNCH((k_fft<KIND, true>), grid, dim3(FFT_THREADS), bytes, stream, a);
-    else DB_LAUNCH((k_fft<KIND, false>), grid, dim3(FFT_THREADS), bytes, stream, a);
+#define FFT_LAUNCH_D(D)                                                                                               \
+    switch (ncs) {                                                                                                    \
+        case 192: FFT_LAUNCH_ONE(D, 192) break;                                                                       \
+        case 384: FFT_LAUNCH_ONE(D, 384) break;                                                                       \
+        case 96: FFT_LAUNCH_ONE(D, 96) break;                                                                         \
+        case 48: FFT_LAUNCH_ONE(D, 48) break;                                                                         \
+        default: FFT_LAUNCH_ONE(D, 0) break;                                                                          \
+    }
+    if constexpr (KIND == K_RFWD || KIND == K_RBWD) {
+        if (direct) { FFT_LAUNCH_D(true) } else { FFT_LAUNCH_D(false) }
+    } else {
+        FFT_LAUNCH_D(false)
+    }
+#undef FFT_LAUNCH_D
+#undef FFT_LAUNCH_ONE
+#undef FFT_SET_ATTR
     return db_check_launch(name);
 }
 
