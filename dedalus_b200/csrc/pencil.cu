@@ -7,6 +7,7 @@
 // integer program (shared by all systems) is read uniformly.  The LU values are stored in the exact order
 // the triangular solves consume them, so the solve is a pure stream over the factors.
 #include "db_common.cuh"
+#include <cstdlib>
 
 #define PB_THREADS 128
 
@@ -277,8 +278,7 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 }
 
 #define SOLVE_THREADS 64
-#define SOLVE_CH 8
-struct SolveChunk { double v[SOLVE_CH]; int c[SOLVE_CH]; };
+template <int CH> struct SolveChunk { double v[CH]; int c[CH]; };
 
 // Triangular solves with the right-hand-side combination fused into the row starts.
 // NV = number of right-hand-side vectors (compile time: pointers and coefficients stay in registers).
@@ -286,7 +286,7 @@ struct SolveChunk { double v[SOLVE_CH]; int c[SOLVE_CH]; };
 // flight while chunk q is consumed; the x values / row-start values of chunk q are gathered in one burst right before
 // it is consumed (the host marks entries whose column completes inside the preload window, DB_I_FRESH_*).  Each CTA
 // streams one contiguous slab of the tile-major factor array.
-template <int NV>
+template <int NV, int SOLVE_CH>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs)
 {
@@ -341,7 +341,7 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
         const int nch = (NCH);                                                                      \
         int cur = -1;                                                                               \
         double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;                                             \
-        SolveChunk K0, K1;                                                                          \
+        SolveChunk<SOLVE_CH> K0, K1;                                                                \
         SOLVE_LOADA(K0)                                                                             \
         for (int ch = 0; ch < nch; ch += 2) {                                                       \
             if (ch + 1 < nch) { SOLVE_LOADA(K1) }                                                   \
@@ -365,15 +365,13 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
     const dim3 g(total_blocks), b(SOLVE_THREADS);
     const int nv = rhs->nvec;
-    if (nv <= 1) DB_LAUNCH(k_batches_solve<1>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else if (nv == 2) DB_LAUNCH(k_batches_solve<2>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else if (nv == 3) DB_LAUNCH(k_batches_solve<3>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else if (nv == 4) DB_LAUNCH(k_batches_solve<4>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else if (nv == 5) DB_LAUNCH(k_batches_solve<5>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else if (nv == 6) DB_LAUNCH(k_batches_solve<6>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else if (nv <= 8) DB_LAUNCH(k_batches_solve<8>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else if (nv <= 12) DB_LAUNCH(k_batches_solve<12>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
-    else DB_LAUNCH(k_batches_solve<16>, g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs);
+    static int ch = 0;
+    if (ch == 0) { const char* e = getenv("DB_SOLVE_CH"); ch = (e && atoi(e) == 16) ? 16 : 8; }
+#define SOLVE_GO(NV_) { if (ch == 16) DB_LAUNCH((k_batches_solve<NV_, 16>), g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs); \
+                        else DB_LAUNCH((k_batches_solve<NV_, 8>), g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs); }
+    if (nv <= 1) SOLVE_GO(1) else if (nv == 2) SOLVE_GO(2) else if (nv == 3) SOLVE_GO(3) else if (nv == 4) SOLVE_GO(4)
+    else if (nv == 5) SOLVE_GO(5) else if (nv == 6) SOLVE_GO(6) else if (nv <= 8) SOLVE_GO(8) else if (nv <= 12) SOLVE_GO(12) else SOLVE_GO(16)
+#undef SOLVE_GO
     return db_check_launch("batches_solve");
 }
 

@@ -462,7 +462,7 @@ def compile_batch(batch, a0, b0):
     #        c <  0, != SKIP : end of the current row (store; backward: multiply by LU[e] = reciprocal pivot) and start of
     #                          row (-1 - c)/ld ; the first entry of a section only starts a row
     #        DB_I_SKIP       : padding to a multiple of the chunk size
-    SKIP, CH = -2**31, 8
+    SKIP, CH = -2**31, 16           # sections padded / hazards marked for 16-entry chunks (kernels use 8 or 16)
     FRESH_REG, FRESH_MEM = 1 << 30, 1 << 29
     TILE = 64                        # DB_TILE: vectors / factors are stored tile-major, 64 systems per slab
     ld = ((batch.S + TILE - 1) // TILE) * TILE

@@ -35,7 +35,7 @@ def solve(prog, LU, rhs):
     """Mirrors csrc/pencil.cu k_batches_solve: chunks of 8 entries; plain x values (and the start value of the next row)
     of chunk q are preloaded BEFORE chunk q-1 is computed; FRESH entries come from the three most recently completed rows
     or are re-read at compute time."""
-    SKIP, FRESH_REG, FRESH_MEM, MASK, CH = -2**31, 1 << 30, 1 << 29, (1 << 29) - 1, 8
+    SKIP, FRESH_REG, FRESH_MEM, MASK, CH = -2**31, 1 << 30, 1 << 29, (1 << 29) - 1, 16
     n, ld = prog.n, prog.tile
     y = np.array(rhs, dtype=float, copy=True)
     for sec0, sec1, forward in ((0, prog.n_fwd, True), (prog.n_fwd, prog.nE, False)):
