@@ -222,18 +222,24 @@ __device__ __forceinline__ void static_dit(double2* buf, const double* tw)
     __syncthreads();
 }
 
-// compile-time selected pass sequences (radix lists must match dedalus_b200/fftplan.py factorize)
-template <bool INV, int NCS>
-__device__ __forceinline__ void fft_static(double2* buf, const double* tw)
+// returns true if a specialised path handled the transform (radix lists must match dedalus_b200/fftplan.py factorize)
+template <bool INV>
+__device__ __forceinline__ bool fft_static_dispatch(double2* buf, const db_fft_plan& p, int T)
 {
-    if constexpr (NCS == 192) { if (INV) static_dit<192, 192, 4, 4, 4, 3>(buf, tw); else static_dif<192, 192, 4, 4, 4, 3>(buf, tw); }
-    else if constexpr (NCS == 384) { if (INV) static_dit<384, 384, 4, 4, 4, 2, 3>(buf, tw); else static_dif<384, 384, 4, 4, 4, 2, 3>(buf, tw); }
-    else if constexpr (NCS == 96) { if (INV) static_dit<96, 96, 4, 4, 2, 3>(buf, tw); else static_dif<96, 96, 4, 4, 2, 3>(buf, tw); }
-    else if constexpr (NCS == 48) { if (INV) static_dit<48, 48, 4, 4, 3>(buf, tw); else static_dif<48, 48, 4, 4, 3>(buf, tw); }
+    if (T != 16) return false;
+    const double* tw = p.tw;
+    switch (p.nc) {
+        case 192: if (INV) static_dit<192, 192, 4, 4, 4, 3>(buf, tw); else static_dif<192, 192, 4, 4, 4, 3>(buf, tw); return true;
+        case 384: if (INV) static_dit<384, 384, 4, 4, 4, 2, 3>(buf, tw); else static_dif<384, 384, 4, 4, 4, 2, 3>(buf, tw); return true;
+        case 96:  if (INV) static_dit<96, 96, 4, 4, 2, 3>(buf, tw); else static_dif<96, 96, 4, 4, 2, 3>(buf, tw); return true;
+        case 48:  if (INV) static_dit<48, 48, 4, 4, 3>(buf, tw); else static_dif<48, 48, 4, 4, 3>(buf, tw); return true;
+        default: return false;
+    }
 }
 
 __device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
+    if (fft_static_dispatch<false>(buf, p, 1 << lgT)) return;
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) {
         fft_pass<false>(buf, p.nc, TP, lgT, p.rad[s], L, p.tw);
@@ -243,6 +249,7 @@ __device__ void fft_dif(double2* buf, const db_fft_plan& p, int TP, int lgT)
 }
 __device__ void fft_dit(double2* buf, const db_fft_plan& p, int TP, int lgT)
 {
+    if (fft_static_dispatch<true>(buf, p, 1 << lgT)) return;
     int Ls[16];
     int L = p.nc;
     for (int s = 0; s < p.nrad; ++s) { Ls[s] = L; L /= p.rad[s]; }
@@ -293,7 +300,6 @@ __device__ __forceinline__ void tile_iter(int len, const TileGeom& g, bool conti
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
         for (int t = warp; t < g.Tc; t += nw) {
             const int64_t off = g.base + t * g.lstride;
-#pragma unroll 4
             for (int j = lane; j < len; j += 32) f(j, t, off + j * g.estride);
         }
     } else {
@@ -303,7 +309,6 @@ __device__ __forceinline__ void tile_iter(int len, const TileGeom& g, bool conti
             int j = threadIdx.x >> lgT;
             int64_t off = g.base + t * g.lstride + j * g.estride;
             const int64_t step = js * g.estride;
-#pragma unroll 8
             for (; j < len; j += js, off += step) f(j, t, off);
         }
     }
@@ -318,8 +323,7 @@ __device__ __forceinline__ double2 rot_i_pow(double2 z, int ph)
 // DIRECT: real-Fourier kernels on a strided axis read / write the coefficient rows straight from / to global memory
 // (each row segment is already a coalesced run across the tile's lines), skipping the shared-memory staging area:
 // one fewer shared round trip and barrier, and 40% less shared memory per CTA (-> 3-4 CTAs per SM)
-// NCS > 0: complex FFT length fixed at compile time (tile width 16) -> only the specialised passes are compiled in
-template <int KIND, bool DIRECT, int NCS>
+template <int KIND, bool DIRECT>
 __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
 {
     DB_SMEM(double, smem);
@@ -624,28 +628,16 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
             };
             if (p.half) {
                 // pairs (k, nc-k): Z_k = E + iO, Z_{nc-k} = conj(E - iO), E = X_k + conj X_{nc-k}, O = (X_k - conj X_{nc-k}) w^{-k}
-                // batches of 4 pairs per thread: all coefficient loads of a batch are issued before any is consumed
                 const int npair = nc / 2 + 1;
-                const int total = npair << lgT;
-                for (int w0 = tid; w0 < total; w0 += 4 * nthreads) {
-                    double2 xa[4], xb[4];
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int w = w0 + it * nthreads;
-                        if (w < total) { const int t = w & Tmask, ka = w >> lgT; xa[it] = getX(ka, t); xb[it] = getX(nc - ka, t); }
-                    }
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int w = w0 + it * nthreads;
-                        if (w < total) {
-                            const int t = w & Tmask, ka = w >> lgT, kb = nc - ka;
-                            const double2 E = make_double2(xa[it].x + xb[it].x, xa[it].y - xb[it].y);
-                            const double2 D = make_double2(xa[it].x - xb[it].x, xa[it].y + xb[it].y);
-                            const double2 O = cmulc(D, ldtw(p.twr, ka));
-                            buf[p.iperm[ka] * TP + t] = make_double2(E.x - O.y, E.y + O.x);
-                            if (kb != ka && kb < nc) buf[p.iperm[kb] * TP + t] = make_double2(E.x + O.y, -(E.y - O.x));
-                        }
-                    }
+                for (int w = tid; w < (npair << lgT); w += nthreads) {
+                    const int t = w & Tmask, ka = w >> lgT, kb = nc - ka;
+                    const double2 xa = getX(ka, t);
+                    const double2 xb = getX(kb, t);
+                    const double2 E = make_double2(xa.x + xb.x, xa.y - xb.y);
+                    const double2 D = make_double2(xa.x - xb.x, xa.y + xb.y);
+                    const double2 O = cmulc(D, ldtw(p.twr, ka));
+                    buf[p.iperm[ka] * TP + t] = make_double2(E.x - O.y, E.y + O.x);
+                    if (kb != ka && kb < nc) buf[p.iperm[kb] * TP + t] = make_double2(E.x + O.y, -(E.y - O.x));
                 }
             } else {
                 for (int w = tid; w < (nc << lgT); w += nthreads) {
@@ -734,35 +726,16 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
         if (outer > 65535 || a.tiles_per_outer > 2147483647LL) { db_set_error("%s: outer extent %lld too large for a strided transform", name, (long long)outer); return 1; }
         grid = dim3((unsigned)a.tiles_per_outer, (unsigned)outer);
     }
-    int ncs = 0;
-    if (T == 16 && (plan->nc == 192 || plan->nc == 384 || plan->nc == 96 || plan->nc == 48)) ncs = plan->nc;
-#define FFT_LAUNCH_ONE(D, N)                                                                                          \
-    {                                                                                                                 \
-        auto kern = k_fft<KIND, D, N>;                                                                                \
-        FFT_SET_ATTR(kern)                                                                                            \
-        DB_LAUNCH(kern, grid, dim3(FFT_THREADS), bytes, stream, a);                                                   \
+#ifndef DB_EMU
+    static bool attr_set[6][2] = {{false, false}, {false, false}, {false, false}, {false, false}, {false, false}, {false, false}};
+    if (!attr_set[KIND][direct ? 1 : 0]) {
+        if (direct) cudaFuncSetAttribute(k_fft<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        else cudaFuncSetAttribute(k_fft<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        attr_set[KIND][direct ? 1 : 0] = true;
     }
-#ifdef DB_EMU
-#define FFT_SET_ATTR(kern)
-#else
-#define FFT_SET_ATTR(kern) { static bool done = false; if (!done) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM); done = true; } }
 #endif
-#define FFT_LAUNCH_D(D)                                                                                               \
-    switch (ncs) {                                                                                                    \
-        case 192: FFT_LAUNCH_ONE(D, 192) break;                                                                       \
-        case 384: FFT_LAUNCH_ONE(D, 384) break;                                                                       \
-        case 96: FFT_LAUNCH_ONE(D, 96) break;                                                                         \
-        case 48: FFT_LAUNCH_ONE(D, 48) break;                                                                         \
-        default: FFT_LAUNCH_ONE(D, 0) break;                                                                          \
-    }
-    if constexpr (KIND == K_RFWD || KIND == K_RBWD) {
-        if (direct) { FFT_LAUNCH_D(true) } else { FFT_LAUNCH_D(false) }
-    } else {
-        FFT_LAUNCH_D(false)
-    }
-#undef FFT_LAUNCH_D
-#undef FFT_LAUNCH_ONE
-#undef FFT_SET_ATTR
+    if (direct) DB_LAUNCH((k_fft<KIND, true>), grid, dim3(FFT_THREADS), bytes, stream, a);
+    else DB_LAUNCH((k_fft<KIND, false>), grid, dim3(FFT_THREADS), bytes, stream, a);
     return db_check_launch(name);
 }
 

@@ -84,7 +84,7 @@ extern "C" int db_pencil_scatter(const double* vec, double* arena, int32_t S, in
 // template mat-vecs  y = (sum_mono mono_vals[mono][s] T_mono) x   for M and L in one pass over rows
 // grid: (ceil(S/128), row chunks)
 // ---------------------------------------------------------------------------------------------------------
-#define MV_ROWS_PER_BLOCK 16
+#define MV_ROWS_PER_BLOCK 64
 __global__ void k_pencil_matvec(int n, int S, int ld, const double* __restrict__ mono_vals, const double* x,
                                 const int32_t* __restrict__ m_ptr, const int32_t* __restrict__ m_col, const int32_t* __restrict__ m_mono, const double* __restrict__ m_val, double* y_m,
                                 const int32_t* __restrict__ l_ptr, const int32_t* __restrict__ l_col, const int32_t* __restrict__ l_mono, const double* __restrict__ l_val, double* y_l)

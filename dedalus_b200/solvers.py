@@ -103,7 +103,7 @@ class BatchSet:
             c.n, c.S, c.ld, c.n_entries = db.n, db.S, db.ld, db.prog.nE
             c.n_fwd, c.n_bwd = db.prog.n_fwd, db.prog.nE - db.prog.n_fwd
             c.blk_solve = blk['solve']; blk['solve'] += (db.S + 63) // 64
-            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 127) // 128) * ((db.n + 15) // 16)
+            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 127) // 128) * ((db.n + 63) // 64)   # MV_ROWS_PER_BLOCK in csrc/pencil.cu
             c.blk_assemble = blk['asm']; blk['asm'] += ((db.S + 127) // 128) * ((db.prog.nE + 63) // 64)
             for side in (0, 1):
                 m = db.maps[side]
