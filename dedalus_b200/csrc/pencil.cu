@@ -365,8 +365,11 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
     const dim3 g(total_blocks), b(SOLVE_THREADS);
     const int nv = rhs->nvec;
-    static int ch = 0;
-    if (ch == 0) { const char* e = getenv("DB_SOLVE_CH"); ch = (e && atoi(e) == 16) ? 16 : 8; }
+    // chunk size: 8 keeps 7 CTAs / SM resident when there are many tiles; with few tiles per SM (multi-GPU strong
+    // scaling) occupancy is not the limit and the 16-entry chunk doubles each warp's loads in flight
+    static int ch_env = -1;
+    if (ch_env < 0) { const char* e = getenv("DB_SOLVE_CH"); ch_env = e ? atoi(e) : 0; }
+    const int ch = (ch_env == 8 || ch_env == 16) ? ch_env : (total_blocks < 148 * 3 ? 16 : 8);
 #define SOLVE_GO(NV_) { if (ch == 16) DB_LAUNCH((k_batches_solve<NV_, 16>), g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs); \
                         else DB_LAUNCH((k_batches_solve<NV_, 8>), g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs); }
     if (nv <= 1) SOLVE_GO(1) else if (nv == 2) SOLVE_GO(2) else if (nv == 3) SOLVE_GO(3) else if (nv == 4) SOLVE_GO(4)
