@@ -8,7 +8,7 @@ import os, subprocess, sys, pathlib, shutil
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-SOURCES = ["core.cu", "fft.cu", "pencil.cu", "pointwise.cu"]
+SOURCES = ["core.cu", "fft.cu", "rfft_regs.cu", "pencil.cu", "pointwise.cu"]
 LIB = PKG / "libdedalus_b200.so"
 EMU_DIR = ROOT / "tests" / "emu"
 EMU_LIB = EMU_DIR / "libdedalus_b200_emu.so"
@@ -24,7 +24,7 @@ def _newer(target, deps):
 def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     srcs = [str(CSRC / s) for s in SOURCES]
-    deps = srcs + [str(CSRC / "db_common.cuh"), str(ROOT / "include" / "dedalus_b200.h")]
+    deps = srcs + [str(CSRC / "db_common.cuh"), str(CSRC / "tw96.inc"), str(ROOT / "include" / "dedalus_b200.h")]
     if not force and not _newer(LIB, deps):
         return LIB
     if not pathlib.Path(nvcc).exists():

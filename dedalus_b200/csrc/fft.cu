@@ -681,6 +681,9 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
+                     int64_t inner, int32_t deriv, double kscale, void* stream);       // rfft_regs.cu
+
 template <int KIND>
 static int launch_fft(const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff, int64_t inner,
                       int32_t deriv, double kscale, const double* da, int32_t nda, const double* db_, int32_t ndb,
@@ -688,6 +691,11 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
 {
     if (outer <= 0 || inner <= 0) return 0;
     if (plan->n <= 0 || plan->nc <= 0 || n_coeff <= 0) { db_set_error("%s: bad sizes", name); return 1; }
+    if (KIND == K_RFWD || KIND == K_RBWD) {
+        // dealiased sizes on a strided axis: register-resident two-stage kernels (rfft_regs.cu)
+        const int rc = db_rfft_regs_try(KIND == K_RFWD, plan, in, out, outer, n_coeff, inner, deriv, kscale, stream);
+        if (rc >= 0) return rc;
+    }
     FftArgs a;
     a.plan = *plan; a.in = in; a.out = out; a.outer = outer; a.inner = inner; a.n_coeff = n_coeff;
     a.deriv = deriv; a.kscale = kscale; a.diags_a = da; a.nd_a = nda; a.diags_b = db_; a.nd_b = ndb;

@@ -1,0 +1,338 @@
+// Register-resident real Fourier transforms for the dealiased (3/2-rule) sizes on a strided axis (T1 hot path).
+//
+// The generic kernel in fft.cu runs log-many shared-memory passes and is bound by instruction issue, not HBM.  Here a
+// line of n = 3 * Q * NB grid points is transformed in TWO register stages with ONE shared-memory exchange:
+//   * two adjacent real lines (2p, 2p+1) are packed as one complex line z = g1 + i g2 ("two for one"), so every global
+//     access is a 16-byte load / store covering both lines, and the real <-> half-complex pre / post processing of the
+//     generic kernel collapses to four additions per mode;
+//   * length n = NA * NB with NA = 3Q: stage A is a register DFT of size NA, stage B one of size NB; the twiddle between
+//     them comes from the plan's exp(-2 pi i j / n) table;
+//   * dealias padding is structural: coefficient modes k >= n/3 are zero, which is exactly the middle third of the
+//     first radix-3 split of stage A (backward) / the discarded third of its outputs (forward), so that third of the
+//     butterflies is never computed and the padded zeros / truncated modes are never touched in memory.
+// One CTA = 16 lines (8 complex pairs, 128-byte rows) x the whole line; 48 KB of shared memory.
+// Conventions as in fft.cu (reference core/transforms.py:469-509, 537-565): cos / -sin interleaved coefficients,
+// forward scaled by 2/n (1/n for k = 0), sin(0) slot zero, Nyquist dropped.
+#include "db_common.cuh"
+#include <cstdlib>
+#include <utility>
+#include "tw96.inc"
+
+namespace {
+
+struct RegArgs {
+    const double* in;
+    double* out;
+    const double* twn;      // exp(-2 pi i j / n), j < n, interleaved
+    int64_t inner;          // stride between line elements (lines are adjacent along inner)
+    int32_t M;              // coefficient rows (even, <= 2n/3)
+    int32_t deriv;
+    double kscale;
+};
+
+__device__ __forceinline__ double2 cadd2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub2(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+// a * exp(-/+ 2 pi i NUM / DEN) with the twiddle a compile-time constant (forward: minus sign, INV: plus)
+template <int NUM, int DEN, bool INV> __device__ __forceinline__ double2 mul_tw(double2 a)
+{
+    static_assert(96 % DEN == 0, "twiddle denominators must divide 96");
+    constexpr int j = ((NUM % DEN) * (96 / DEN)) % 96;
+    if constexpr (j == 0) return a;
+    else if constexpr (j == 24) return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+    else if constexpr (j == 48) return make_double2(-a.x, -a.y);
+    else if constexpr (j == 72) return INV ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+    else {
+        constexpr double c = tw96_cos(j);
+        constexpr double s = INV ? tw96_sin(j) : -tw96_sin(j);
+        return make_double2(a.x * c - a.y * s, a.x * s + a.y * c);
+    }
+}
+
+// natural-order in-register DFT of a power-of-two length (radix-2 decimation in time down to length 4 / 2)
+template <int N, bool INV> struct DftP2 {
+    template <int... K>
+    static __device__ __forceinline__ void combine(double2 (&v)[N], const double2 (&e)[N / 2], const double2 (&o)[N / 2],
+                                                   std::integer_sequence<int, K...>)
+    {
+        ((void)([&] {
+            const double2 t = mul_tw<K, N, INV>(o[K]);
+            v[K] = cadd2(e[K], t);
+            v[K + N / 2] = csub2(e[K], t);
+        }()), ...);
+    }
+    static __device__ __forceinline__ void run(double2 (&v)[N])
+    {
+        double2 e[N / 2], o[N / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        DftP2<N / 2, INV>::run(e);
+        DftP2<N / 2, INV>::run(o);
+        combine(v, e, o, std::make_integer_sequence<int, N / 2>{});
+    }
+};
+template <bool INV> struct DftP2<4, INV> {
+    static __device__ __forceinline__ void run(double2 (&v)[4])
+    {
+        const double2 a = cadd2(v[0], v[2]), b = csub2(v[0], v[2]), c = cadd2(v[1], v[3]), d = csub2(v[1], v[3]);
+        const double2 jd = INV ? make_double2(-d.y, d.x) : make_double2(d.y, -d.x);
+        v[0] = cadd2(a, c); v[2] = csub2(a, c);
+        v[1] = cadd2(b, jd); v[3] = csub2(b, jd);
+    }
+};
+template <bool INV> struct DftP2<2, INV> {
+    static __device__ __forceinline__ void run(double2 (&v)[2])
+    {
+        const double2 a = v[0], b = v[1];
+        v[0] = cadd2(a, b); v[1] = csub2(a, b);
+    }
+};
+
+// u[b] *= exp(-/+ 2 pi i b C / NA) for b = 0..Q-1
+template <int C, int NA, bool INV, int Q, int... B>
+__device__ __forceinline__ void twiddle_row(double2 (&u)[Q], std::integer_sequence<int, B...>)
+{
+    ((void)(u[B] = mul_tw<(B * C) % NA, NA, INV>(u[B])), ...);
+}
+
+__device__ __forceinline__ double2 ldtwn(const double* __restrict__ tw, int j) { return reinterpret_cast<const double2*>(tw)[j]; }
+// a * conj(w)
+__device__ __forceinline__ double2 cmulc2(double2 a, double2 w) { return make_double2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
+__device__ __forceinline__ double2 cmul2(double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+
+#define RR_P 8          // complex line pairs per CTA (16 real lines)
+
+// ---------------------------------------------------------------------------------------------------------
+// backward: coefficients (M rows) -> grid (n rows)
+// ---------------------------------------------------------------------------------------------------------
+template <int Q, int NB, bool DERIV>
+__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P)
+k_rbwd_regs(RegArgs a)
+{
+    constexpr int NA = 3 * Q, N = NA * NB, P = RR_P;
+    DB_SMEM(double2, sm);                                   // [NA][NB][P]
+    const int p = threadIdx.x & (P - 1), r = threadIdx.x >> 3;
+    const int64_t inner = a.inner;
+    const int64_t col = (int64_t)blockIdx.x * (2 * P) + 2 * p;
+    const int Kmax = (a.M - 1) / 2;
+    if (r < NB) {
+        const int n2 = r;
+        const double* __restrict__ gin = a.in + (int64_t)blockIdx.y * a.M * inner + col;
+        const int deriv = DERIV ? a.deriv : 0;
+        // (i k kscale)^deriv = (ur + i ui) (k kscale)^deriv
+        const double ur = ((deriv & 3) == 0) ? 1.0 : ((deriv & 3) == 2) ? -1.0 : 0.0;
+        const double ui = ((deriv & 3) == 1) ? 1.0 : ((deriv & 3) == 3) ? -1.0 : 0.0;
+        // Z_k = X1_k + i X2_k (k <= Kmax), Z_{n-k} = conj X1_k + i conj X2_k, X_k = (c_2k + i c_2k+1) / 2, X_0 = c_0
+        auto spec = [&](int k, bool mirrored) -> double2 {
+            if (k > Kmax) return make_double2(0.0, 0.0);
+            const double* row = gin + (int64_t)(2 * k) * inner;
+            double2 R = *reinterpret_cast<const double2*>(row);            // (re line 1, re line 2)
+            if (k == 0) return DERIV ? make_double2(0.0, 0.0) : R;
+            double2 I = *reinterpret_cast<const double2*>(row + inner);    // (im line 1, im line 2)
+            if (DERIV) {
+                const double ks = a.kscale * k;
+                double f = 0.5;
+#pragma unroll 1
+                for (int d = 0; d < deriv; ++d) f *= ks;
+                const double mr = ur * f, mi = ui * f;
+                const double2 R2 = make_double2(mr * R.x - mi * I.x, mr * R.y - mi * I.y);
+                const double2 I2 = make_double2(mi * R.x + mr * I.x, mi * R.y + mr * I.y);
+                return mirrored ? make_double2(R2.x + I2.y, R2.y - I2.x) : make_double2(R2.x - I2.y, I2.x + R2.y);
+            }
+            return mirrored ? make_double2(0.5 * (R.x + I.y), 0.5 * (R.y - I.x)) : make_double2(0.5 * (R.x - I.y), 0.5 * (I.x + R.y));
+        };
+        double2 lo[Q], hi[Q];
+#pragma unroll
+        for (int b = 0; b < Q; ++b) {
+            lo[b] = spec(NB * b + n2, false);                  // Z[NB b + n2]
+            hi[b] = spec(NB * (Q - b) - n2, true);             // Z[NB (2Q + b) + n2] = mirror of mode n - that
+        }
+        // stage A: size-NA DFT over n1 = Q a + b with the a = 1 third identically zero; output k1 = c + 3 kb
+        const double* __restrict__ tw = a.twn;
+        double2* dst = sm + n2 * P + p;
+        {
+            double2 u[Q];
+#pragma unroll
+            for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], hi[b]);
+            DftP2<Q, true>::run(u);
+#pragma unroll
+            for (int kb = 0; kb < Q; ++kb) {
+                const int k1 = 3 * kb;
+                dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+            }
+        }
+        {
+            double2 u[Q];
+#pragma unroll
+            for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<2, 3, true>(hi[b]));
+            twiddle_row<1, NA, true>(u, std::make_integer_sequence<int, Q>{});
+            DftP2<Q, true>::run(u);
+#pragma unroll
+            for (int kb = 0; kb < Q; ++kb) {
+                const int k1 = 3 * kb + 1;
+                dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+            }
+        }
+        {
+            double2 u[Q];
+#pragma unroll
+            for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<1, 3, true>(hi[b]));
+            twiddle_row<2, NA, true>(u, std::make_integer_sequence<int, Q>{});
+            DftP2<Q, true>::run(u);
+#pragma unroll
+            for (int kb = 0; kb < Q; ++kb) {
+                const int k1 = 3 * kb + 2;
+                dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+            }
+        }
+    }
+    __syncthreads();
+    if (r < NA) {
+        // stage B: size-NB DFT over n2 for fixed k1 = r; grid index j = k1 + NA k2
+        const int k1 = r;
+        double2 v[NB];
+        const double2* src = sm + (k1 * NB) * P + p;
+#pragma unroll
+        for (int n2 = 0; n2 < NB; ++n2) v[n2] = src[n2 * P];
+        DftP2<NB, true>::run(v);
+        double* __restrict__ gout = a.out + ((int64_t)blockIdx.y * N + k1) * inner + col;
+#pragma unroll
+        for (int k2 = 0; k2 < NB; ++k2)
+            *reinterpret_cast<double2*>(gout + (int64_t)(NA * k2) * inner) = v[k2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward: grid (n rows) -> coefficients (M rows)
+// ---------------------------------------------------------------------------------------------------------
+template <int Q, int NB>
+__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P)
+k_rfwd_regs(RegArgs a)
+{
+    constexpr int NA = 3 * Q, N = NA * NB, P = RR_P;
+    DB_SMEM(double2, sm);                                   // [NA][NB][P]
+    const int p = threadIdx.x & (P - 1), r = threadIdx.x >> 3;
+    const int64_t inner = a.inner;
+    const int64_t col = (int64_t)blockIdx.x * (2 * P) + 2 * p;
+    const int Kmax = (a.M - 1) / 2;
+    if (r < NA) {
+        // stage 1: size-NB DFT over j2 for fixed j1 = r (grid index j = j1 + NA j2), then twiddle W_n^(j1 k2)
+        const int j1 = r;
+        const double* __restrict__ gin = a.in + ((int64_t)blockIdx.y * N + j1) * inner + col;
+        double2 v[NB];
+#pragma unroll
+        for (int j2 = 0; j2 < NB; ++j2) v[j2] = *reinterpret_cast<const double2*>(gin + (int64_t)(NA * j2) * inner);
+        DftP2<NB, false>::run(v);
+        const double* __restrict__ tw = a.twn;
+        double2* dst = sm + (j1 * NB) * P + p;
+#pragma unroll
+        for (int k2 = 0; k2 < NB; ++k2) dst[k2 * P] = (k2 == 0) ? v[0] : cmul2(v[k2], ldtwn(tw, j1 * k2));
+    }
+    __syncthreads();
+    double2 zlo[Q], zhi[Q];
+    const int k2 = r;
+    if (r < NB) {
+        // stage 2: size-NA DFT over j1 = 3 jb + c for fixed k2, keeping only outputs k1 = kb (low third) and 2Q + kb
+        const double2* src = sm + k2 * P + p;
+        double2 s0[Q], s1[Q], s2[Q];
+#pragma unroll
+        for (int jb = 0; jb < Q; ++jb) {
+            s0[jb] = src[(3 * jb) * NB * P];
+            s1[jb] = src[(3 * jb + 1) * NB * P];
+            s2[jb] = src[(3 * jb + 2) * NB * P];
+        }
+        DftP2<Q, false>::run(s0);
+        DftP2<Q, false>::run(s1);
+        DftP2<Q, false>::run(s2);
+        twiddle_row<1, NA, false>(s1, std::make_integer_sequence<int, Q>{});
+        twiddle_row<2, NA, false>(s2, std::make_integer_sequence<int, Q>{});
+#pragma unroll
+        for (int kb = 0; kb < Q; ++kb) {
+            zlo[kb] = cadd2(s0[kb], cadd2(s1[kb], s2[kb]));                                        // Z[NB kb + k2]
+            zhi[kb] = cadd2(s0[kb], cadd2(mul_tw<2, 3, false>(s1[kb]), mul_tw<1, 3, false>(s2[kb])));   // Z[NB (2Q + kb) + k2]
+        }
+    }
+    __syncthreads();
+    if (r < NB) {
+        double2* dst = sm + k2 * P + p;
+#pragma unroll
+        for (int kb = 0; kb < Q; ++kb) dst[kb * NB * P] = zhi[kb];
+    }
+    __syncthreads();
+    if (r < NB) {
+        // Z_{n-k} for k = NB kb + k2 sits at (kb', k2') = (Q - 1 - kb, NB - k2) for k2 > 0, (Q - kb, 0) for k2 = 0
+        const double sc = 1.0 / N;
+        double* __restrict__ gout = a.out + (int64_t)blockIdx.y * a.M * inner + col;
+        const int k2p = (k2 == 0) ? 0 : NB - k2;
+        const double2* src = sm + k2p * P + p;
+#pragma unroll
+        for (int kb = 0; kb < Q; ++kb) {
+            const int k = NB * kb + k2;
+            if (k > Kmax) continue;
+            double* row = gout + (int64_t)(2 * k) * inner;
+            const double2 za = zlo[kb];
+            if (k == 0) {
+                *reinterpret_cast<double2*>(row) = make_double2(za.x * sc, za.y * sc);
+                *reinterpret_cast<double2*>(row + inner) = make_double2(0.0, 0.0);
+            } else {
+                const int kbp = (k2 == 0) ? Q - kb : Q - 1 - kb;
+                const double2 zb = src[kbp * NB * P];
+                *reinterpret_cast<double2*>(row) = make_double2((za.x + zb.x) * sc, (za.y + zb.y) * sc);
+                *reinterpret_cast<double2*>(row + inner) = make_double2((za.y - zb.y) * sc, (zb.x - za.x) * sc);
+            }
+        }
+    }
+}
+
+template <int Q, int NB>
+int launch_regs(bool fwd, const RegArgs& a, int64_t outer, void* stream)
+{
+    constexpr int NA = 3 * Q, THREADS = (NA > NB ? NA : NB) * RR_P;
+    const size_t bytes = (size_t)NA * NB * RR_P * sizeof(double2);
+    dim3 grid((unsigned)(a.inner / (2 * RR_P)), (unsigned)outer);
+#ifndef DB_EMU
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_rbwd_regs<Q, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_rbwd_regs<Q, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_rfwd_regs<Q, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        attr = true;
+    }
+#endif
+    if (fwd) DB_LAUNCH((k_rfwd_regs<Q, NB>), grid, dim3(THREADS), bytes, stream, a);
+    else if (a.deriv > 0) DB_LAUNCH((k_rbwd_regs<Q, NB, true>), grid, dim3(THREADS), bytes, stream, a);
+    else DB_LAUNCH((k_rbwd_regs<Q, NB, false>), grid, dim3(THREADS), bytes, stream, a);
+    return db_check_launch(fwd ? "rfft_forward(regs)" : "rfft_backward(regs)");
+}
+
+static long long g_regs_launches = 0;
+}  // namespace
+
+extern "C" long long db_rfft_regs_launches(void) { return g_regs_launches; }
+
+// Returns -1 if the register kernels do not cover this case (the caller falls back to the generic shared-memory
+// kernel), otherwise the launch status.
+int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
+                     int64_t inner, int32_t deriv, double kscale, void* stream)
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("DB_FFT_REGS"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!enabled) return -1;
+    const int n = plan->n;
+    if (!plan->half || plan->twn == nullptr) return -1;
+    if (inner < 2 * RR_P || inner % (2 * RR_P) != 0 || outer > 65535) return -1;
+    if (n_coeff % 2 != 0 || n_coeff < 2 || (int64_t)3 * n_coeff > (int64_t)2 * n) return -1;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
+    RegArgs a;
+    a.in = in; a.out = out; a.twn = plan->twn; a.inner = inner; a.M = n_coeff; a.deriv = deriv; a.kscale = kscale;
+    ++g_regs_launches;
+    switch (n) {
+        case 384: return launch_regs<8, 16>(fwd, a, outer, stream);
+        case 192: return launch_regs<4, 16>(fwd, a, outer, stream);
+        case 96:  return launch_regs<4, 8>(fwd, a, outer, stream);
+        case 48:  return launch_regs<2, 8>(fwd, a, outer, stream);
+        case 24:  return launch_regs<2, 4>(fwd, a, outer, stream);
+        case 768: return launch_regs<8, 32>(fwd, a, outer, stream);
+        default: --g_regs_launches; return -1;
+    }
+}

@@ -65,3 +65,4 @@ class HostPlan:
         self.tw = _cis(np.arange(self.nc), self.nc)                       # exp(-2 pi i j / nc)
         self.twr = _cis(np.arange(self.nc + 1), self.n)                   # exp(-2 pi i k / n)
         self.twq = _cis(np.arange(self.n), 4 * self.n)                    # exp(-i pi k / (2 n))
+        self.twn = _cis(np.arange(self.n), self.n)                        # exp(-2 pi i j / n)

@@ -15,7 +15,7 @@ i32, i64, f64, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
 
 class FftPlan(C.Structure):
     _fields_ = [("n", i32), ("nc", i32), ("half", i32), ("nrad", i32), ("rad", i32 * 16),
-                ("tw", vp), ("twr", vp), ("twq", vp), ("perm", vp), ("iperm", vp)]
+                ("tw", vp), ("twr", vp), ("twq", vp), ("perm", vp), ("iperm", vp), ("twn", vp)]
 
 
 class LinComb(C.Structure):
@@ -49,6 +49,7 @@ SIGNATURES = {
     "db_last_error": (C.c_char_p, []),
     "db_version": (C.c_int, []),
     "db_device_arch": (C.c_int, []),
+    "db_rfft_regs_launches": (C.c_longlong, []),
     "db_rfft_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp]),
     "db_rfft_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, vp]),
     "db_cfft_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp]),
@@ -110,6 +111,9 @@ class BoundLib:
 
     def version(self):
         return self._raw_db_version()
+
+    def rfft_regs_launches(self):
+        return self._raw_db_rfft_regs_launches()
 
     def device_arch(self):
         return self._raw_db_device_arch()

@@ -54,12 +54,12 @@ class DevicePlan:
             torch = _torch()
             hp = HostPlan(n, kind)
             self.hp = hp
-            self.tensors = [torch.from_numpy(np.ascontiguousarray(x)).to(device) for x in (hp.tw, hp.twr, hp.twq, hp.perm, hp.iperm)]
+            self.tensors = [torch.from_numpy(np.ascontiguousarray(x)).to(device) for x in (hp.tw, hp.twr, hp.twq, hp.perm, hp.iperm, hp.twn)]
             s = FftPlan()
             s.n, s.nc, s.half, s.nrad = hp.n, hp.nc, hp.half, len(hp.radices)
             for i, r in enumerate(hp.radices):
                 s.rad[i] = r
-            s.tw, s.twr, s.twq, s.perm, s.iperm = [t.data_ptr() for t in self.tensors]
+            s.tw, s.twr, s.twq, s.perm, s.iperm, s.twn = [t.data_ptr() for t in self.tensors]
             self.struct = s
             cls._cache[key] = self
         return cls._cache[key]

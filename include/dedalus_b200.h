@@ -38,6 +38,7 @@ typedef struct {
     const double* twq;    /* [n][2]  exp(-i pi k / (2n))    (DCT quarter-wave twiddle)                 */
     const int32_t* perm;  /* [nc] frequency index held at position p after the DIF passes            */
     const int32_t* iperm; /* [nc] position holding frequency k (inverse of perm)                      */
+    const double* twn;    /* [n][2]  exp(-2 pi i j / n)     (register-resident two-stage kernels)      */
 } db_fft_plan;
 
 /* Real Fourier, cos/-sin interleaved coefficients, unit-amplitude normalisation, Nyquist dropped.
@@ -46,6 +47,8 @@ typedef struct {
  * g: (outer, n_grid, inner) real;  c: (outer, n_coeff, inner) real.
  * backward: `deriv` >= 0 applies (d/dx)^deriv in coefficient space first, wavenumber spacing `kscale`
  * (fuses DifferentiateRealFourier, core/basis.py:1203-1224, into the transform's load stage). */
+/* diagnostic: number of db_rfft_* calls served by the register-resident kernels (csrc/rfft_regs.cu) so far */
+long long db_rfft_regs_launches(void);
 int db_rfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream);
 int db_rfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
                      int32_t deriv, double kscale, void* stream);

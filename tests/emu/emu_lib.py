@@ -31,12 +31,12 @@ class EmuPlan:
     def __init__(self, n, kind):
         hp = HostPlan(n, kind)
         self.hp = hp
-        self._keep = [np.ascontiguousarray(x) for x in (hp.tw, hp.twr, hp.twq, hp.perm, hp.iperm)]
+        self._keep = [np.ascontiguousarray(x) for x in (hp.tw, hp.twr, hp.twq, hp.perm, hp.iperm, hp.twn)]
         s = dlib.FftPlan()
         s.n, s.nc, s.half, s.nrad = hp.n, hp.nc, hp.half, len(hp.radices)
         for i, r in enumerate(hp.radices):
             s.rad[i] = r
-        s.tw, s.twr, s.twq, s.perm, s.iperm = [ptr(x) for x in self._keep]
+        s.tw, s.twr, s.twq, s.perm, s.iperm, s.twn = [ptr(x) for x in self._keep]
         self.struct = s
 
     def ref(self):

@@ -128,3 +128,36 @@ def test_benchmark_line_lengths_use_static_passes(M, N):
     bz = np.zeros_like(cz)
     lib.call("db_cheb_forward", plan.ref(), E.ptr(gz), E.ptr(bz), 20, M, 1, None, 0, None)
     assert np.allclose(bz, cz, rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("M,N", [(256, 384), (128, 192), (64, 96), (32, 48), (16, 24), (512, 768), (100, 192), (2, 24)])
+@pytest.mark.parametrize("deriv", [0, 1, 2, 3])
+def test_register_resident_rfft(M, N, deriv):
+    """csrc/rfft_regs.cu (two-stage register FFT, two real lines per complex line) against the oracle transforms:
+    strided axis with the line count a multiple of 16, dealiased sizes, coefficient-space derivative fused."""
+    from oracle import transforms_oracle as T
+    lib = E.emu(); plan = E.EmuPlan(N, 'real')
+    rng = np.random.default_rng(11 + deriv)
+    inner, outer = 32, 2
+    c = rng.standard_normal((outer, M, inner)); c[:, 1, :] = 0
+    kscale = 2 * np.pi / 3.0
+    cd = c.copy()
+    for _ in range(deriv):                         # d/dx on cos/-sin pairs: (a, b) -> k (-b, a)
+        k = (np.arange(M) // 2) * kscale
+        a, b = cd[:, 0::2, :].copy(), cd[:, 1::2, :].copy()
+        cd[:, 0::2, :] = -b * k[0::2, None]; cd[:, 1::2, :] = a * k[1::2, None]
+    g = np.full((outer, N, inner), np.nan)
+    served = lib.rfft_regs_launches()
+    lib.call("db_rfft_backward", plan.ref(), E.ptr(c), E.ptr(g), outer, M, inner, deriv, kscale, None)
+    assert lib.rfft_regs_launches() == served + 1      # not the generic fallback
+    ref = T.rf_backward_fft(cd, N, 1)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.allclose(g, ref, rtol=0, atol=1e-13 * scale)
+    if deriv == 0:
+        back = np.full_like(c, np.nan)
+        lib.call("db_rfft_forward", plan.ref(), E.ptr(g), E.ptr(back), outer, M, inner, None)
+        assert np.allclose(back, c, rtol=0, atol=1e-13)
+        gr = rng.standard_normal((outer, N, inner))
+        out = np.full_like(c, np.nan)
+        lib.call("db_rfft_forward", plan.ref(), E.ptr(gr), E.ptr(out), outer, M, inner, None)
+        assert np.allclose(out, T.rf_forward_fft(gr, M, 1), rtol=0, atol=1e-13)

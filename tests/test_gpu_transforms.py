@@ -119,3 +119,34 @@ def test_fused_derivatives_match_matrices():
         z = jacobi.gauss_grid(N, -0.5, -0.5)[0]
         ref = dc @ jacobi.polynomials(M, a + d, a + d, z)
         assert np.allclose(out.cpu().numpy(), ref, rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("M,N", [(256, 384), (128, 192), (64, 96), (32, 48), (16, 24), (512, 768), (100, 192)])
+@pytest.mark.parametrize("deriv", [0, 1, 2])
+def test_register_resident_real_fourier(M, N, deriv):
+    """csrc/rfft_regs.cu (the path the 256^3 benchmark takes on its two Fourier axes) against the CPU oracle."""
+    import torch
+    from dedalus_b200.transforms import RealFourierTransform
+    from dedalus_b200.lib import get_lib
+    from oracle import transforms_oracle as T
+    rng = np.random.default_rng(11 + deriv)
+    inner, outer = 48, 3
+    kscale = 2 * np.pi / 3.0
+    rf = RealFourierTransform(N, M, kscale=kscale)
+    c = rng.standard_normal((outer, M, inner)); c[:, 1, :] = 0
+    cd = c.copy()
+    for _ in range(deriv):
+        k = (np.arange(M) // 2) * kscale
+        a, b = cd[:, 0::2, :].copy(), cd[:, 1::2, :].copy()
+        cd[:, 0::2, :] = -b * k[0::2, None]; cd[:, 1::2, :] = a * k[1::2, None]
+    g = torch.full((outer, N, inner), float('nan'), dtype=torch.float64, device='cuda')
+    served = get_lib().rfft_regs_launches()
+    rf.backward(_t(c), g, 1, deriv=deriv)
+    assert get_lib().rfft_regs_launches() == served + 1
+    ref = T.rf_backward_fft(cd, N, 1)
+    assert np.allclose(g.cpu().numpy(), ref, rtol=0, atol=1e-13 * max(1.0, np.abs(ref).max()))
+    if deriv == 0:
+        gr = rng.standard_normal((outer, N, inner))
+        out = torch.full((outer, M, inner), float('nan'), dtype=torch.float64, device='cuda')
+        rf.forward(_t(gr), out, 1)
+        assert np.allclose(out.cpu().numpy(), T.rf_forward_fft(gr, M, 1), rtol=0, atol=1e-13)
