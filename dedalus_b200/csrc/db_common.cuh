@@ -12,6 +12,7 @@
 #define DB_SMEM(type, name) \
     extern __shared__ __align__(16) unsigned char db_smem_raw[]; \
     type* name = reinterpret_cast<type*>(db_smem_raw)
+#define DB_SET_SMEM_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
 #endif
 
 #ifdef DB_EMU

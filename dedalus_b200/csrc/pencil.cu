@@ -358,6 +358,131 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
 #undef SOLVE_LOADA
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Triangular solves, bulk-copy ring variant.  The tile-major factor array makes everything one CTA (64 systems) reads
+// a single contiguous stream of n_entries * 512 bytes, so one elected thread feeds it through a ring of shared-memory
+// stages with 1-D bulk async copies (cp.async.bulk -> UBLKCP) completing on mbarriers; the instruction words of each
+// chunk ride in the same stage.  The copy engine keeps `nstages` chunks in flight per CTA no matter how few warps are
+// resident, which is what a latency-bound, one-thread-per-system recurrence needs when there are only a few tiles
+// per SM (multi-GPU strong scaling); registers hold only the 16 gathered x values of the chunk being consumed.
+// ---------------------------------------------------------------------------------------------------------
+#define SOLVE_CE 16
+#define SOLVE_STAGE_BYTES (SOLVE_CE * DB_TILE * 8 + SOLVE_CE * 4)
+#ifdef DB_EMU
+typedef unsigned long long db_mbar_t;
+__device__ __forceinline__ void db_mbar_init(db_mbar_t*, int) {}
+__device__ __forceinline__ void db_mbar_fence_init() {}
+__device__ __forceinline__ void db_mbar_expect_tx(db_mbar_t*, unsigned) {}
+__device__ __forceinline__ void db_bulk_g2s(void* dst, const void* src, unsigned bytes, db_mbar_t*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void db_mbar_wait(db_mbar_t*, unsigned) {}
+#else
+typedef unsigned long long db_mbar_t;
+__device__ __forceinline__ unsigned db_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void db_mbar_init(db_mbar_t* bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(db_smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void db_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void db_mbar_expect_tx(db_mbar_t* bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(db_smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void db_bulk_g2s(void* dst, const void* src, unsigned bytes, db_mbar_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(db_smem_u32(dst)), "l"(src), "r"(bytes), "r"(db_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(db_smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
+template <int NV>
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_batches_solve_ring(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
+{
+    DB_SMEM(unsigned char, ring);
+    db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_STAGE_BYTES);
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int tile = blockIdx.x - B.blk_solve;
+    const int s = tile * SOLVE_THREADS + threadIdx.x;          // padded lanes (s >= S) run on the zero padding
+    const int64_t tb = db_tbase(s, B.n);
+    const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
+    const int32_t* __restrict__ prog = B.prog;
+    const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
+    double* __restrict__ x = B.vec[x_slot] + tb;
+    const double* rv[NV];
+    double cf[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+    auto issue = [&](int q, int slot) {
+        unsigned char* st = ring + (size_t)slot * SOLVE_STAGE_BYTES;
+        db_mbar_expect_tx(&bars[slot], SOLVE_STAGE_BYTES);
+        db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &bars[slot]);
+        db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, prog + (int64_t)q * SOLVE_CE, SOLVE_CE * 4, &bars[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) db_mbar_init(&bars[i], 1);
+        db_mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
+    int slot = 0;
+    unsigned phase = 0;
+    int cur = -1;
+    double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+    for (int q = 0; q < nchunks; ++q) {
+        const bool fwd = q < nfwd;
+        if (q == nfwd) { cur = -1; acc = 0.0; l1 = l2 = l3 = 0.0; }
+        db_mbar_wait(&bars[slot], phase);
+        const unsigned char* st = ring + (size_t)slot * SOLVE_STAGE_BYTES;
+        const double* __restrict__ vals = reinterpret_cast<const double*>(st) + threadIdx.x;
+        const int* __restrict__ codes = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+        double xv[SOLVE_CE];
+#pragma unroll
+        for (int j = 0; j < SOLVE_CE; ++j) {
+            const int c = codes[j];
+            double val = 0.0;
+            if (c >= 0) { if (c < DB_I_FRESH_MEM) val = x[c]; }
+            else if (c != DB_I_SKIP) {
+                const int o = -1 - c;
+                if (fwd) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) val = fma(cf[k], DB_LDCS(rv[k] + o), val);
+                } else val = x[o];
+            }
+            xv[j] = val;
+        }
+#pragma unroll
+        for (int j = 0; j < SOLVE_CE; ++j) {
+            const int c = codes[j];
+            if (c >= 0) {
+                double xx = xv[j];
+                if (c >= DB_I_FRESH_MEM)
+                    xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK];
+                acc = fma(-vals[j * DB_TILE], xx, acc);
+            } else if (c != DB_I_SKIP) {
+                if (cur >= 0) {
+                    const double val = fwd ? acc : acc * vals[j * DB_TILE];
+                    x[cur] = val; l3 = l2; l2 = l1; l1 = val;
+                }
+                cur = -1 - c;
+                acc = xv[j];
+            }
+        }
+        __syncthreads();                                   // both warps are done with this stage
+        if (threadIdx.x == 0 && q + nstages < nchunks) issue(q + nstages, slot);
+        if (++slot == nstages) { slot = 0; phase ^= 1; }
+    }
+}
+
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
                                 const db_slotcomb* rhs, void* stream)
 {
@@ -365,6 +490,27 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
     const dim3 g(total_blocks), b(SOLVE_THREADS);
     const int nv = rhs->nvec;
+    // DB_SOLVE_IMPL=regs selects the register-pipelined kernel; default is the bulk-copy ring.  Ring depth: enough
+    // stages that (CTAs per SM) x (stages) x 8 KB covers the HBM latency-bandwidth product (~40 KB per SM) several
+    // times over, without taking more shared memory than leaves the L1 useful for the x re-reads.
+    static int impl = -1, st_env = 0;
+    if (impl < 0) {
+        const char* e = getenv("DB_SOLVE_IMPL"); impl = (e && strcmp(e, "regs") == 0) ? 0 : 1;
+        const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
+    }
+    if (impl == 1) {
+        const int per_sm = (total_blocks + 147) / 148;
+        int nst = per_sm >= 7 ? 3 : per_sm >= 4 ? 4 : per_sm >= 2 ? 8 : 16;
+        if (st_env >= 2 && st_env <= 24) nst = st_env;
+        const size_t smem = (size_t)nst * SOLVE_STAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
+#define RING_GO(NV_) { static int attr_st = 0; \
+        if (attr_st < nst) { DB_SET_SMEM_ATTR((k_batches_solve_ring<NV_>)); attr_st = 1 << 30; } \
+        DB_LAUNCH((k_batches_solve_ring<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
+        if (nv <= 1) RING_GO(1) else if (nv == 2) RING_GO(2) else if (nv == 3) RING_GO(3) else if (nv == 4) RING_GO(4)
+        else if (nv == 5) RING_GO(5) else if (nv == 6) RING_GO(6) else if (nv <= 8) RING_GO(8) else if (nv <= 12) RING_GO(12) else RING_GO(16)
+#undef RING_GO
+        return db_check_launch("batches_solve");
+    }
     // chunk size: 8 keeps 7 CTAs / SM resident when there are many tiles; with few tiles per SM (multi-GPU strong
     // scaling) occupancy is not the limit and the 16-entry chunk doubles each warp's loads in flight
     static int ch_env = -1;

@@ -60,3 +60,4 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
 #define DB_LAUNCH(kern, grid, block, smem, stream, ...) \
     emu_launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
 #define DB_SMEM(type, name) type* name = reinterpret_cast<type*>(emu_cur.smem)
+#define DB_SET_SMEM_ATTR(kern) ((void)0)
