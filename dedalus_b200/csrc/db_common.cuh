@@ -25,6 +25,7 @@
 #ifdef DB_EMU
 __device__ __forceinline__ void db_cp_async8(void* dst, const void* src) { *reinterpret_cast<double*>(dst) = *reinterpret_cast<const double*>(src); }
 __device__ __forceinline__ void db_cp_async4(void* dst, const void* src) { *reinterpret_cast<int*>(dst) = *reinterpret_cast<const int*>(src); }
+__device__ __forceinline__ void db_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
 __device__ __forceinline__ void db_cp_commit() {}
 template <int N> __device__ __forceinline__ void db_cp_wait() {}
 #else
@@ -35,6 +36,10 @@ __device__ __forceinline__ void db_cp_async8(void* dst, const void* src)
 __device__ __forceinline__ void db_cp_async4(void* dst, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void db_cp_async16(void* dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void db_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void db_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -827,10 +827,80 @@ k_band_lines(const double* __restrict__ in, double* __restrict__ out, int64_t li
     }
 }
 
+// Parity-structured conversions (ultraspherical: only even diagonals) with one off-diagonal: the back-substitution
+// x_i = r_i (t_i - u_i x_{i+2}) is two interleaved first-order linear recurrences, i.e. a suffix scan over the affine
+// maps x -> A_i x + B_i.  One warp per line, lane l of round q owns the element pair (2m, 2m+1), m = 32 q + l, the
+// scan runs on shuffles: no shared memory, no block barrier, every global access a coalesced 16-byte load / store.
+__device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+__device__ __forceinline__ double shfl_idx_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__global__ void __launch_bounds__(BL_THREADS)
+k_band_scan2(const double* __restrict__ in, double* __restrict__ out, int64_t lines, int n,
+             const double* __restrict__ pre, int npre, const double* __restrict__ sol)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t line = (int64_t)blockIdx.x * (BL_THREADS / 32) + (threadIdx.x >> 5);
+    if (line >= lines) return;
+    const double* __restrict__ src = in + line * n;
+    double* __restrict__ dst = out + line * n;
+    const int rounds = (n + 63) / 64;
+    double carry0 = 0.0, carry1 = 0.0;                      // x_{i+2} entering the round from above (even / odd chain)
+    for (int q = rounds - 1; q >= 0; --q) {
+        const int i0 = 2 * (32 * q + lane);
+        // c_{i0 .. i0+3}: own pair + the next lane's pair (the last lane reads it from memory)
+        double c0 = 0.0, c1 = 0.0;
+        if (i0 + 1 < n) { const double2 v = *reinterpret_cast<const double2*>(src + i0); c0 = v.x; c1 = v.y; }
+        else if (i0 < n) c0 = src[i0];
+        double c2 = shfl_down_d(c0, 1), c3 = shfl_down_d(c1, 1);
+        if (lane == 31) { c2 = (i0 + 2 < n) ? src[i0 + 2] : 0.0; c3 = (i0 + 3 < n) ? src[i0 + 3] : 0.0; }
+        double t0 = c0, t1 = c1;
+        if (npre > 0) {
+            t0 = 0.0; t1 = 0.0;
+            if (i0 < n) {
+                t0 = pre[i0] * c0;
+                if (npre > 1) t0 = fma(pre[n + i0], c1, t0);
+                if (npre > 2) t0 = fma(pre[2 * n + i0], c2, t0);
+            }
+            if (i0 + 1 < n) {
+                t1 = pre[i0 + 1] * c1;
+                if (npre > 1) t1 = fma(pre[n + i0 + 1], c2, t1);
+                if (npre > 2) t1 = fma(pre[2 * n + i0 + 1], c3, t1);
+            }
+        }
+        // affine maps x_i = A x_{i+2} + B
+        double A0 = 0.0, B0 = 0.0, A1 = 0.0, B1 = 0.0;
+        if (i0 < n) { const double r = sol[i0]; B0 = r * t0; A0 = (i0 + 2 < n) ? -r * sol[n + i0] : 0.0; }
+        if (i0 + 1 < n) { const double r = sol[i0 + 1]; B1 = r * t1; A1 = (i0 + 3 < n) ? -r * sol[n + i0 + 1] : 0.0; }
+        // inclusive suffix scan over lanes: compose with the maps of higher lanes
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double a0 = shfl_down_d(A0, off), b0 = shfl_down_d(B0, off);
+            const double a1 = shfl_down_d(A1, off), b1 = shfl_down_d(B1, off);
+            if (lane + off < 32) { B0 = fma(A0, b0, B0); A0 *= a0; B1 = fma(A1, b1, B1); A1 *= a1; }
+        }
+        const double x0 = fma(A0, carry0, B0), x1 = fma(A1, carry1, B1);
+        if (i0 + 1 < n) *reinterpret_cast<double2*>(dst + i0) = make_double2(x0, x1);
+        else if (i0 < n) dst[i0] = x0;
+        carry0 = shfl_idx_d(x0, 0); carry1 = shfl_idx_d(x1, 0);
+    }
+}
+
 extern "C" int db_band_lines(const double* in, double* out, int64_t lines, int32_t n,
-                             const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream)
+                             const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag,
+                             int32_t solve_stride, void* stream)
 {
     if (lines <= 0 || n <= 0) return 0;
+    if (solve_ndiag > 0 && solve_stride == 2) {
+        // compact even-diagonal storage: only the two-diagonal (first-order) case has a kernel
+        if (solve_ndiag != 2 || pre_ndiag > 3 || (n & 1) || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+            db_set_error("band_lines: stride-2 solve needs 2 stored diagonals, <= 3 pre-apply diagonals, even n, 16-byte aligned lines");
+            return 1;
+        }
+        const int64_t blocks = (lines + BL_THREADS / 32 - 1) / (BL_THREADS / 32);
+        DB_LAUNCH(k_band_scan2, dim3((unsigned)blocks), dim3(BL_THREADS), 0, stream, in, out, lines, n, pre_diags, pre_ndiag, solve_diags);
+        return db_check_launch("band_lines(scan)");
+    }
+    if (solve_ndiag > 0 && solve_stride != 1) { db_set_error("band_lines: unsupported diagonal stride %d", solve_stride); return 1; }
     size_t smem = ((size_t)n * (BL_LINES + 1) + (size_t)(solve_ndiag > 0 ? solve_ndiag : 0) * n) * sizeof(double);
     if (smem > (size_t)DB_MAX_SMEM) { db_set_error("band_lines: line length %d too large", n); return 1; }
     int64_t blocks = (lines + BL_LINES - 1) / BL_LINES;

@@ -100,208 +100,283 @@ __device__ __forceinline__ double2 ldtwn(const double* __restrict__ tw, int j) {
 __device__ __forceinline__ double2 cmulc2(double2 a, double2 w) { return make_double2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
 __device__ __forceinline__ double2 cmul2(double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 
-#define RR_P 8          // complex line pairs per CTA (16 real lines)
+#define RR_P 8          // complex line pairs per CTA tile (16 real lines)
+
+// Persistent CTAs walk the tiles (tile = 16 adjacent lines x the whole line length) with the NEXT tile's input rows in
+// flight (16-byte cp.async, L1-bypassing) while the current tile is transformed: two shared-memory buffers of
+// n x 128 bytes; the stage A -> stage B exchange reuses the buffer the current tile's input was staged in.
+struct TileWalk {
+    int64_t tiles_per_outer, total;
+};
+
+// stage `rows` rows of 16 doubles (row stride `inner`) into buf[row][16]
+__device__ __forceinline__ void stage_rows(double* buf, const double* __restrict__ src, int rows, int64_t inner)
+{
+    for (int idx = threadIdx.x; idx < rows * 8; idx += blockDim.x) {
+        const int row = idx >> 3, seg = idx & 7;
+        db_cp_async16(buf + row * 16 + seg * 2, src + (int64_t)row * inner + seg * 2);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // backward: coefficients (M rows) -> grid (n rows)
 // ---------------------------------------------------------------------------------------------------------
 template <int Q, int NB, bool DERIV>
-__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P)
-k_rbwd_regs(RegArgs a)
+__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P, (3 * Q * NB <= 384 ? 2 : 1))
+k_rbwd_regs(RegArgs a, TileWalk tw_)
 {
     constexpr int NA = 3 * Q, N = NA * NB, P = RR_P;
-    DB_SMEM(double2, sm);                                   // [NA][NB][P]
+    DB_SMEM(double2, sm);                                   // 2 buffers of [N][P] double2
     const int p = threadIdx.x & (P - 1), r = threadIdx.x >> 3;
     const int64_t inner = a.inner;
-    const int64_t col = (int64_t)blockIdx.x * (2 * P) + 2 * p;
-    const int Kmax = (a.M - 1) / 2;
-    if (r < NB) {
-        const int n2 = r;
-        const double* __restrict__ gin = a.in + (int64_t)blockIdx.y * a.M * inner + col;
-        const int deriv = DERIV ? a.deriv : 0;
-        // (i k kscale)^deriv = (ur + i ui) (k kscale)^deriv
-        const double ur = ((deriv & 3) == 0) ? 1.0 : ((deriv & 3) == 2) ? -1.0 : 0.0;
-        const double ui = ((deriv & 3) == 1) ? 1.0 : ((deriv & 3) == 3) ? -1.0 : 0.0;
-        // Z_k = X1_k + i X2_k (k <= Kmax), Z_{n-k} = conj X1_k + i conj X2_k, X_k = (c_2k + i c_2k+1) / 2, X_0 = c_0
-        auto spec = [&](int k, bool mirrored) -> double2 {
-            if (k > Kmax) return make_double2(0.0, 0.0);
-            const double* row = gin + (int64_t)(2 * k) * inner;
-            double2 R = *reinterpret_cast<const double2*>(row);            // (re line 1, re line 2)
-            if (k == 0) return DERIV ? make_double2(0.0, 0.0) : R;
-            double2 I = *reinterpret_cast<const double2*>(row + inner);    // (im line 1, im line 2)
-            if (DERIV) {
-                const double ks = a.kscale * k;
-                double f = 0.5;
-#pragma unroll 1
-                for (int d = 0; d < deriv; ++d) f *= ks;
-                const double mr = ur * f, mi = ui * f;
-                const double2 R2 = make_double2(mr * R.x - mi * I.x, mr * R.y - mi * I.y);
-                const double2 I2 = make_double2(mi * R.x + mr * I.x, mi * R.y + mr * I.y);
-                return mirrored ? make_double2(R2.x + I2.y, R2.y - I2.x) : make_double2(R2.x - I2.y, I2.x + R2.y);
-            }
-            return mirrored ? make_double2(0.5 * (R.x + I.y), 0.5 * (R.y - I.x)) : make_double2(0.5 * (R.x - I.y), 0.5 * (I.x + R.y));
-        };
+    const int M = a.M, Kmax = (a.M - 1) / 2;
+    const int deriv = DERIV ? a.deriv : 0;
+    // (i k kscale)^deriv = (ur + i ui) (k kscale)^deriv
+    const double ur = ((deriv & 3) == 0) ? 1.0 : ((deriv & 3) == 2) ? -1.0 : 0.0;
+    const double ui = ((deriv & 3) == 1) ? 1.0 : ((deriv & 3) == 3) ? -1.0 : 0.0;
+    const double* __restrict__ tw = a.twn;
+    auto tile_src = [&](int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
+                                     return a.in + o * M * inner + xt * (2 * P); };
+    int64_t t = blockIdx.x;
+    int cur = 0;
+    if (t < tw_.total) stage_rows(reinterpret_cast<double*>(sm), tile_src(t), M, inner);
+    db_cp_commit();
+    for (; t < tw_.total; t += gridDim.x, cur ^= 1) {
+        double2* in = sm + cur * (N * P);
+        const int64_t tn = t + gridDim.x;
+        if (tn < tw_.total) stage_rows(reinterpret_cast<double*>(sm + (cur ^ 1) * (N * P)), tile_src(tn), M, inner);
+        db_cp_commit();
+        db_cp_wait<1>();
+        __syncthreads();
         double2 lo[Q], hi[Q];
+        const int n2 = r;
+        if (r < NB) {
+            // Z_k = X1_k + i X2_k (k <= Kmax), Z_{n-k} = conj X1_k + i conj X2_k, X_k = (c_2k + i c_2k+1) / 2, X_0 = c_0
+            auto spec = [&](int k, bool mirrored) -> double2 {
+                if (k > Kmax) return make_double2(0.0, 0.0);
+                const double2 R = in[(2 * k) * P + p];                      // (re line 1, re line 2)
+                if (k == 0) return DERIV ? make_double2(0.0, 0.0) : R;
+                const double2 I = in[(2 * k + 1) * P + p];                  // (im line 1, im line 2)
+                if (DERIV) {
+                    const double ks = a.kscale * k, ks2 = ks * ks;
+                    const double f = 0.5 * ((deriv == 1) ? ks : (deriv == 2) ? ks2 : (deriv == 3) ? ks2 * ks : ks2 * ks2);
+                    const double mr = ur * f, mi = ui * f;
+                    const double2 R2 = make_double2(mr * R.x - mi * I.x, mr * R.y - mi * I.y);
+                    const double2 I2 = make_double2(mi * R.x + mr * I.x, mi * R.y + mr * I.y);
+                    return mirrored ? make_double2(R2.x + I2.y, R2.y - I2.x) : make_double2(R2.x - I2.y, I2.x + R2.y);
+                }
+                return mirrored ? make_double2(0.5 * (R.x + I.y), 0.5 * (R.y - I.x)) : make_double2(0.5 * (R.x - I.y), 0.5 * (I.x + R.y));
+            };
 #pragma unroll
-        for (int b = 0; b < Q; ++b) {
-            lo[b] = spec(NB * b + n2, false);                  // Z[NB b + n2]
-            hi[b] = spec(NB * (Q - b) - n2, true);             // Z[NB (2Q + b) + n2] = mirror of mode n - that
-        }
-        // stage A: size-NA DFT over n1 = Q a + b with the a = 1 third identically zero; output k1 = c + 3 kb
-        const double* __restrict__ tw = a.twn;
-        double2* dst = sm + n2 * P + p;
-        {
-            double2 u[Q];
-#pragma unroll
-            for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], hi[b]);
-            DftP2<Q, true>::run(u);
-#pragma unroll
-            for (int kb = 0; kb < Q; ++kb) {
-                const int k1 = 3 * kb;
-                dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+            for (int b = 0; b < Q; ++b) {
+                lo[b] = spec(NB * b + n2, false);                  // Z[NB b + n2]
+                hi[b] = spec(NB * (Q - b) - n2, true);             // Z[NB (2Q + b) + n2] = mirror of mode n - that
             }
         }
-        {
-            double2 u[Q];
+        __syncthreads();                                           // every input value is in registers: reuse `in` as exchange
+        if (r < NB) {
+            // stage A: size-NA DFT over n1 = Q a + b with the a = 1 third identically zero; output k1 = c + 3 kb
+            double2* dst = in + n2 * P + p;
+            {
+                double2 u[Q];
 #pragma unroll
-            for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<2, 3, true>(hi[b]));
-            twiddle_row<1, NA, true>(u, std::make_integer_sequence<int, Q>{});
-            DftP2<Q, true>::run(u);
+                for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], hi[b]);
+                DftP2<Q, true>::run(u);
 #pragma unroll
-            for (int kb = 0; kb < Q; ++kb) {
-                const int k1 = 3 * kb + 1;
-                dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+                for (int kb = 0; kb < Q; ++kb) {
+                    const int k1 = 3 * kb;
+                    dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+                }
+            }
+            {
+                double2 u[Q];
+#pragma unroll
+                for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<2, 3, true>(hi[b]));
+                twiddle_row<1, NA, true>(u, std::make_integer_sequence<int, Q>{});
+                DftP2<Q, true>::run(u);
+#pragma unroll
+                for (int kb = 0; kb < Q; ++kb) {
+                    const int k1 = 3 * kb + 1;
+                    dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+                }
+            }
+            {
+                double2 u[Q];
+#pragma unroll
+                for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<1, 3, true>(hi[b]));
+                twiddle_row<2, NA, true>(u, std::make_integer_sequence<int, Q>{});
+                DftP2<Q, true>::run(u);
+#pragma unroll
+                for (int kb = 0; kb < Q; ++kb) {
+                    const int k1 = 3 * kb + 2;
+                    dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
+                }
             }
         }
-        {
-            double2 u[Q];
+        __syncthreads();
+        if (r < NA) {
+            // stage B: size-NB DFT over n2 for fixed k1 = r; grid index j = k1 + NA k2
+            const int k1 = r;
+            double2 v[NB];
+            const double2* src = in + (k1 * NB) * P + p;
 #pragma unroll
-            for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<1, 3, true>(hi[b]));
-            twiddle_row<2, NA, true>(u, std::make_integer_sequence<int, Q>{});
-            DftP2<Q, true>::run(u);
+            for (int n2b = 0; n2b < NB; ++n2b) v[n2b] = src[n2b * P];
+            DftP2<NB, true>::run(v);
+            const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
+            double* __restrict__ gout = a.out + (o * N + k1) * inner + xt * (2 * P) + 2 * p;
 #pragma unroll
-            for (int kb = 0; kb < Q; ++kb) {
-                const int k1 = 3 * kb + 2;
-                dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
-            }
+            for (int k2 = 0; k2 < NB; ++k2)
+                *reinterpret_cast<double2*>(gout + (int64_t)(NA * k2) * inner) = v[k2];
         }
+        __syncthreads();                                           // exchange reads done before the next prefetch lands here
     }
-    __syncthreads();
-    if (r < NA) {
-        // stage B: size-NB DFT over n2 for fixed k1 = r; grid index j = k1 + NA k2
-        const int k1 = r;
-        double2 v[NB];
-        const double2* src = sm + (k1 * NB) * P + p;
-#pragma unroll
-        for (int n2 = 0; n2 < NB; ++n2) v[n2] = src[n2 * P];
-        DftP2<NB, true>::run(v);
-        double* __restrict__ gout = a.out + ((int64_t)blockIdx.y * N + k1) * inner + col;
-#pragma unroll
-        for (int k2 = 0; k2 < NB; ++k2)
-            *reinterpret_cast<double2*>(gout + (int64_t)(NA * k2) * inner) = v[k2];
-    }
+    db_cp_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // forward: grid (n rows) -> coefficients (M rows)
 // ---------------------------------------------------------------------------------------------------------
 template <int Q, int NB>
-__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P)
-k_rfwd_regs(RegArgs a)
+__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P, (3 * Q * NB <= 384 ? 2 : 1))
+k_rfwd_regs(RegArgs a, TileWalk tw_)
 {
     constexpr int NA = 3 * Q, N = NA * NB, P = RR_P;
-    DB_SMEM(double2, sm);                                   // [NA][NB][P]
+    DB_SMEM(double2, sm);                                   // 2 buffers of [N][P] double2
     const int p = threadIdx.x & (P - 1), r = threadIdx.x >> 3;
     const int64_t inner = a.inner;
-    const int64_t col = (int64_t)blockIdx.x * (2 * P) + 2 * p;
-    const int Kmax = (a.M - 1) / 2;
-    if (r < NA) {
-        // stage 1: size-NB DFT over j2 for fixed j1 = r (grid index j = j1 + NA j2), then twiddle W_n^(j1 k2)
-        const int j1 = r;
-        const double* __restrict__ gin = a.in + ((int64_t)blockIdx.y * N + j1) * inner + col;
+    const int M = a.M, Kmax = (a.M - 1) / 2;
+    const double* __restrict__ tw = a.twn;
+    auto tile_src = [&](int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
+                                     return a.in + o * N * inner + xt * (2 * P); };
+    int64_t t = blockIdx.x;
+    int cur = 0;
+    if (t < tw_.total) stage_rows(reinterpret_cast<double*>(sm), tile_src(t), N, inner);
+    db_cp_commit();
+    for (; t < tw_.total; t += gridDim.x, cur ^= 1) {
+        double2* in = sm + cur * (N * P);
+        const int64_t tn = t + gridDim.x;
+        if (tn < tw_.total) stage_rows(reinterpret_cast<double*>(sm + (cur ^ 1) * (N * P)), tile_src(tn), N, inner);
+        db_cp_commit();
+        db_cp_wait<1>();
+        __syncthreads();
         double2 v[NB];
+        if (r < NA) {
+            // stage 1: size-NB DFT over j2 for fixed j1 = r (grid index j = j1 + NA j2)
 #pragma unroll
-        for (int j2 = 0; j2 < NB; ++j2) v[j2] = *reinterpret_cast<const double2*>(gin + (int64_t)(NA * j2) * inner);
-        DftP2<NB, false>::run(v);
-        const double* __restrict__ tw = a.twn;
-        double2* dst = sm + (j1 * NB) * P + p;
-#pragma unroll
-        for (int k2 = 0; k2 < NB; ++k2) dst[k2 * P] = (k2 == 0) ? v[0] : cmul2(v[k2], ldtwn(tw, j1 * k2));
-    }
-    __syncthreads();
-    double2 zlo[Q], zhi[Q];
-    const int k2 = r;
-    if (r < NB) {
-        // stage 2: size-NA DFT over j1 = 3 jb + c for fixed k2, keeping only outputs k1 = kb (low third) and 2Q + kb
-        const double2* src = sm + k2 * P + p;
-        double2 s0[Q], s1[Q], s2[Q];
-#pragma unroll
-        for (int jb = 0; jb < Q; ++jb) {
-            s0[jb] = src[(3 * jb) * NB * P];
-            s1[jb] = src[(3 * jb + 1) * NB * P];
-            s2[jb] = src[(3 * jb + 2) * NB * P];
+            for (int j2 = 0; j2 < NB; ++j2) v[j2] = in[(r + NA * j2) * P + p];
         }
-        DftP2<Q, false>::run(s0);
-        DftP2<Q, false>::run(s1);
-        DftP2<Q, false>::run(s2);
-        twiddle_row<1, NA, false>(s1, std::make_integer_sequence<int, Q>{});
-        twiddle_row<2, NA, false>(s2, std::make_integer_sequence<int, Q>{});
+        __syncthreads();                                           // inputs are in registers: reuse `in` as exchange
+        if (r < NA) {
+            const int j1 = r;
+            DftP2<NB, false>::run(v);
+            double2* dst = in + (j1 * NB) * P + p;
 #pragma unroll
-        for (int kb = 0; kb < Q; ++kb) {
-            zlo[kb] = cadd2(s0[kb], cadd2(s1[kb], s2[kb]));                                        // Z[NB kb + k2]
-            zhi[kb] = cadd2(s0[kb], cadd2(mul_tw<2, 3, false>(s1[kb]), mul_tw<1, 3, false>(s2[kb])));   // Z[NB (2Q + kb) + k2]
+            for (int k2 = 0; k2 < NB; ++k2) dst[k2 * P] = (k2 == 0) ? v[0] : cmul2(v[k2], ldtwn(tw, j1 * k2));
         }
-    }
-    __syncthreads();
-    if (r < NB) {
-        double2* dst = sm + k2 * P + p;
+        __syncthreads();
+        double2 zlo[Q], zhi[Q];
+        const int k2 = r;
+        if (r < NB) {
+            // stage 2: size-NA DFT over j1 = 3 jb + c for fixed k2, keeping only outputs k1 = kb (low third) and 2Q + kb
+            const double2* src = in + k2 * P + p;
+            double2 s0[Q], s1[Q], s2[Q];
 #pragma unroll
-        for (int kb = 0; kb < Q; ++kb) dst[kb * NB * P] = zhi[kb];
-    }
-    __syncthreads();
-    if (r < NB) {
-        // Z_{n-k} for k = NB kb + k2 sits at (kb', k2') = (Q - 1 - kb, NB - k2) for k2 > 0, (Q - kb, 0) for k2 = 0
-        const double sc = 1.0 / N;
-        double* __restrict__ gout = a.out + (int64_t)blockIdx.y * a.M * inner + col;
-        const int k2p = (k2 == 0) ? 0 : NB - k2;
-        const double2* src = sm + k2p * P + p;
+            for (int jb = 0; jb < Q; ++jb) {
+                s0[jb] = src[(3 * jb) * NB * P];
+                s1[jb] = src[(3 * jb + 1) * NB * P];
+                s2[jb] = src[(3 * jb + 2) * NB * P];
+            }
+            DftP2<Q, false>::run(s0);
+            DftP2<Q, false>::run(s1);
+            DftP2<Q, false>::run(s2);
+            twiddle_row<1, NA, false>(s1, std::make_integer_sequence<int, Q>{});
+            twiddle_row<2, NA, false>(s2, std::make_integer_sequence<int, Q>{});
 #pragma unroll
-        for (int kb = 0; kb < Q; ++kb) {
-            const int k = NB * kb + k2;
-            if (k > Kmax) continue;
-            double* row = gout + (int64_t)(2 * k) * inner;
-            const double2 za = zlo[kb];
-            if (k == 0) {
-                *reinterpret_cast<double2*>(row) = make_double2(za.x * sc, za.y * sc);
-                *reinterpret_cast<double2*>(row + inner) = make_double2(0.0, 0.0);
-            } else {
-                const int kbp = (k2 == 0) ? Q - kb : Q - 1 - kb;
-                const double2 zb = src[kbp * NB * P];
-                *reinterpret_cast<double2*>(row) = make_double2((za.x + zb.x) * sc, (za.y + zb.y) * sc);
-                *reinterpret_cast<double2*>(row + inner) = make_double2((za.y - zb.y) * sc, (zb.x - za.x) * sc);
+            for (int kb = 0; kb < Q; ++kb) {
+                zlo[kb] = cadd2(s0[kb], cadd2(s1[kb], s2[kb]));                                        // Z[NB kb + k2]
+                zhi[kb] = cadd2(s0[kb], cadd2(mul_tw<2, 3, false>(s1[kb]), mul_tw<1, 3, false>(s2[kb])));   // Z[NB (2Q + kb) + k2]
             }
         }
+        __syncthreads();
+        if (r < NB) {
+            double2* dst = in + k2 * P + p;
+#pragma unroll
+            for (int kb = 0; kb < Q; ++kb) dst[kb * NB * P] = zhi[kb];
+        }
+        __syncthreads();
+        if (r < NB) {
+            // Z_{n-k} for k = NB kb + k2 sits at (kb', k2') = (Q - 1 - kb, NB - k2) for k2 > 0, (Q - kb, 0) for k2 = 0
+            const double sc = 1.0 / N;
+            const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
+            double* __restrict__ gout = a.out + o * M * inner + xt * (2 * P) + 2 * p;
+            const int k2p = (k2 == 0) ? 0 : NB - k2;
+            const double2* src = in + k2p * P + p;
+#pragma unroll
+            for (int kb = 0; kb < Q; ++kb) {
+                const int k = NB * kb + k2;
+                if (k > Kmax) continue;
+                double* row = gout + (int64_t)(2 * k) * inner;
+                const double2 za = zlo[kb];
+                if (k == 0) {
+                    *reinterpret_cast<double2*>(row) = make_double2(za.x * sc, za.y * sc);
+                    *reinterpret_cast<double2*>(row + inner) = make_double2(0.0, 0.0);
+                } else {
+                    const int kbp = (k2 == 0) ? Q - kb : Q - 1 - kb;
+                    const double2 zb = src[kbp * NB * P];
+                    *reinterpret_cast<double2*>(row) = make_double2((za.x + zb.x) * sc, (za.y + zb.y) * sc);
+                    *reinterpret_cast<double2*>(row + inner) = make_double2((za.y - zb.y) * sc, (zb.x - za.x) * sc);
+                }
+            }
+        }
+        __syncthreads();
     }
+    db_cp_wait<0>();
+}
+
+static int regs_num_sms()
+{
+#ifdef DB_EMU
+    return 1;                    // tests: several tiles per persistent CTA
+#else
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+#endif
 }
 
 template <int Q, int NB>
 int launch_regs(bool fwd, const RegArgs& a, int64_t outer, void* stream)
 {
     constexpr int NA = 3 * Q, THREADS = (NA > NB ? NA : NB) * RR_P;
-    const size_t bytes = (size_t)NA * NB * RR_P * sizeof(double2);
-    dim3 grid((unsigned)(a.inner / (2 * RR_P)), (unsigned)outer);
+    const size_t bytes = (size_t)2 * NA * NB * RR_P * sizeof(double2);
+    TileWalk w;
+    w.tiles_per_outer = a.inner / (2 * RR_P);
+    w.total = w.tiles_per_outer * outer;
+    // persistent grid: as many CTAs as fit (2 per SM at n = 384: 96 KB each), never more than there are tiles
+    int per_sm = (int)((size_t)(226 * 1024) / (bytes + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t nblk = (int64_t)regs_num_sms() * per_sm;
+    if (nblk > w.total) nblk = w.total;
+    dim3 grid((unsigned)nblk);
 #ifndef DB_EMU
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_rbwd_regs<Q, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
         cudaFuncSetAttribute(k_rbwd_regs<Q, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
         cudaFuncSetAttribute(k_rfwd_regs<Q, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_rbwd_regs<Q, NB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_rbwd_regs<Q, NB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_rfwd_regs<Q, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr = true;
     }
 #endif
-    if (fwd) DB_LAUNCH((k_rfwd_regs<Q, NB>), grid, dim3(THREADS), bytes, stream, a);
-    else if (a.deriv > 0) DB_LAUNCH((k_rbwd_regs<Q, NB, true>), grid, dim3(THREADS), bytes, stream, a);
-    else DB_LAUNCH((k_rbwd_regs<Q, NB, false>), grid, dim3(THREADS), bytes, stream, a);
+    if (fwd) DB_LAUNCH((k_rfwd_regs<Q, NB>), grid, dim3(THREADS), bytes, stream, a, w);
+    else if (a.deriv > 0) DB_LAUNCH((k_rbwd_regs<Q, NB, true>), grid, dim3(THREADS), bytes, stream, a, w);
+    else DB_LAUNCH((k_rbwd_regs<Q, NB, false>), grid, dim3(THREADS), bytes, stream, a, w);
     return db_check_launch(fwd ? "rfft_forward(regs)" : "rfft_backward(regs)");
 }
 
@@ -320,7 +395,7 @@ int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double
     if (!enabled) return -1;
     const int n = plan->n;
     if (!plan->half || plan->twn == nullptr) return -1;
-    if (inner < 2 * RR_P || inner % (2 * RR_P) != 0 || outer > 65535) return -1;
+    if (inner < 2 * RR_P || inner % (2 * RR_P) != 0 || deriv > 4) return -1;
     if (n_coeff % 2 != 0 || n_coeff < 2 || (int64_t)3 * n_coeff > (int64_t)2 * n) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
     RegArgs a;

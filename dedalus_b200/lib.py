@@ -56,7 +56,7 @@ SIGNATURES = {
     "db_cfft_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, vp]),
     "db_cheb_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp, i32, vp]),
     "db_cheb_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp, i32, vp, i32, vp]),
-    "db_band_lines": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i32, vp]),
+    "db_band_lines": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i32, i32, vp]),
     "db_mmt_apply": (C.c_int, [vp, i32, i32, vp, vp, i64, i64, vp]),
     "db_pointwise": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp]),
     "db_pencil_gather": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),

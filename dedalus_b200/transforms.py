@@ -164,6 +164,9 @@ class FastChebyshevTransform:
                 nd = int(round((self.a + d - self.a0) + (self.b + d - self.b0))) + 1
                 arr = banded_upper_diags(Cm, M, nd)
                 arr[0] = 1.0 / arr[0]            # kernel contract: row 0 of the solve matrix holds 1/diagonal
+                if nd == 3 and not arr[1].any() and M % 2 == 0:
+                    # parity-structured conversion: store diagonals 0 and 2 only (stride 2) -> warp-scan kernel
+                    self._dev[(('solve2', d), str(device))] = (torch.from_numpy(np.ascontiguousarray(arr[[0, 2]])).to(device), 2)
             else:  # 'pre': derivative chain (a,b) -> (a+d,b+d)
                 P = None
                 for j in range(d):
@@ -204,7 +207,11 @@ class FastChebyshevTransform:
             # contiguous lines: run the serial banded recurrence in its own one-thread-per-line kernel, then the
             # plain transform (keeps the recurrence off the FFT kernel's critical path)
             tmp = self._scratch(cdata)
-            get_lib().call("db_band_lines", _dptr(cdata), _dptr(tmp), outer, self.M, _dptr(pre), npre, _dptr(sol), nsol, _stream())
+            compact = self._dev.get((('solve2', deriv), str(gdata.device))) if (nsol and npre <= 3) else None
+            if compact is not None and cdata.data_ptr() % 16 == 0:
+                get_lib().call("db_band_lines", _dptr(cdata), _dptr(tmp), outer, self.M, _dptr(pre), npre, _dptr(compact[0]), 2, 2, _stream())
+            else:
+                get_lib().call("db_band_lines", _dptr(cdata), _dptr(tmp), outer, self.M, _dptr(pre), npre, _dptr(sol), nsol, 1, _stream())
             get_lib().call("db_cheb_backward", plan.ref(), _dptr(tmp), _dptr(gdata), outer, self.M, inner, None, 0, None, 0, _stream())
         else:
             get_lib().call("db_cheb_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner,

@@ -78,7 +78,8 @@ int db_cheb_backward(const db_fft_plan* plan, const double* c, double* g, int64_
  * kernel's CTA shape (core/transforms.py:876-884 solve_upper_sparse; tools/linalg.pyx:20-82).
  * Diagonal storage as in db_cheb_backward (row 0 of solve_diags = reciprocal diagonal). */
 int db_band_lines(const double* in, double* out, int64_t lines, int32_t n,
-                  const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream);
+                  const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag,
+                  int32_t solve_stride, void* stream);
 
 /* Dense matrix transform along an axis: out(o, i, r) = sum_j mat[i][j] * in(o, j, r).
  * Replaces SeparableMatrixTransform -> apply_dense (core/transforms.py:54-75, tools/array.py:104-129). */

@@ -35,6 +35,16 @@ void emu_syncthreads() {
     emu_cur = f->st;
 }
 
+static double shfl_slots[4096];
+double emu_shfl_exchange(double v, int src_lane) {
+    const unsigned tid = emu_cur.tid.x;            // 1-D blocks only
+    shfl_slots[tid] = v;
+    emu_syncthreads();
+    const double r = shfl_slots[(tid & ~31u) + (unsigned)src_lane];
+    emu_syncthreads();
+    return r;
+}
+
 void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     const size_t nthreads = (size_t)block.x * block.y * block.z;
     std::vector<unsigned char> shared(smem + 64);

@@ -48,6 +48,15 @@ extern thread_local EmuState emu_cur;           // state of the running fiber
 void emu_syncthreads();
 #define __syncthreads() emu_syncthreads()
 #define __syncwarp(...) ((void)0)
+// warp shuffles: every lane of the warp publishes its value, yields once (all live fibers advance one step per
+// scheduler round), reads the source lane's slot, and yields again before any slot can be overwritten
+double emu_shfl_exchange(double v, int src_lane);
+static inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl_exchange(v, src & 31); }
+static inline double __shfl_down_sync(unsigned, double v, int off)
+{
+    const int lane = (int)(emu_cur.tid.x & 31);
+    return emu_shfl_exchange(v, lane + off < 32 ? lane + off : lane);
+}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p += v; return o; }

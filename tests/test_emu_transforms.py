@@ -138,7 +138,7 @@ def test_register_resident_rfft(M, N, deriv):
     from oracle import transforms_oracle as T
     lib = E.emu(); plan = E.EmuPlan(N, 'real')
     rng = np.random.default_rng(11 + deriv)
-    inner, outer = 32, 2
+    inner, outer = 48, 5                          # 15 tiles over at most 8 persistent CTAs: ragged multi-tile walks
     c = rng.standard_normal((outer, M, inner)); c[:, 1, :] = 0
     kscale = 2 * np.pi / 3.0
     cd = c.copy()
@@ -161,3 +161,33 @@ def test_register_resident_rfft(M, N, deriv):
         out = np.full_like(c, np.nan)
         lib.call("db_rfft_forward", plan.ref(), E.ptr(gr), E.ptr(out), outer, M, inner, None)
         assert np.allclose(out, T.rf_forward_fft(gr, M, 1), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("M", [256, 64, 50, 6])
+@pytest.mark.parametrize("npre", [0, 2, 3])
+def test_band_lines_warp_scan_matches_serial_recurrence(M, npre):
+    """db_band_lines: compact even-diagonal storage (stride 2, warp suffix scan over affine maps) against the general
+    one-thread-per-line recurrence and a dense numpy solve."""
+    lib = E.emu()
+    rng = np.random.default_rng(M + npre)
+    lines = 11
+    c = rng.standard_normal((lines, M))
+    Cm = jacobi.conversion_matrix(M, -0.5, -0.5, 0.5, 0.5).toarray()          # diagonals 0 and 2
+    full = np.zeros((3, M)); full[0] = np.diag(Cm); full[2, :M - 2] = np.diag(Cm, 2)
+    pre = np.zeros((max(npre, 1), M))
+    P = np.eye(M)
+    if npre:
+        P = np.zeros((M, M))
+        for d in range(npre):
+            pre[d, :M - d] = rng.standard_normal(M - d)
+            P += np.diag(pre[d, :M - d], d)
+    ref = np.linalg.solve(Cm, (P @ c.T)).T
+    sol_full = full.copy(); sol_full[0] = 1.0 / full[0]
+    sol_compact = np.ascontiguousarray(sol_full[[0, 2]])
+    out_serial = np.full_like(c, np.nan); out_scan = np.full_like(c, np.nan)
+    pre_ptr = E.ptr(pre) if npre else None
+    lib.call("db_band_lines", E.ptr(c), E.ptr(out_serial), lines, M, pre_ptr, npre, E.ptr(sol_full), 3, 1, None)
+    lib.call("db_band_lines", E.ptr(c), E.ptr(out_scan), lines, M, pre_ptr, npre, E.ptr(sol_compact), 2, 2, None)
+    scale = np.abs(ref).max()
+    assert np.allclose(out_serial, ref, rtol=0, atol=1e-12 * scale)
+    assert np.allclose(out_scan, ref, rtol=0, atol=1e-12 * scale)
