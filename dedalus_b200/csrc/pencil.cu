@@ -280,6 +280,29 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 #define SOLVE_THREADS 64
 template <int CH> struct SolveChunk { double v[CH]; int c[CH]; };
 
+// Right-hand side first: x <- sum_q cf[q] * rv[q] for every row, as one fully parallel streaming pass (many
+// independent loads in flight per thread).  The forward sweep then starts each row from x[row] like the backward sweep
+// does; folding the combination into the row starts instead puts NV dependent DRAM loads on the recurrence's critical
+// path two or three times per 16-entry chunk (rows are short), which is what the sweep's time was made of.
+#define SOLVE_PROLOGUE(NV_, NROWS)                                                                  \
+    {                                                                                               \
+        const int nrows_ = (NROWS);                                                                 \
+        int i_ = 0;                                                                                 \
+        for (; i_ + 4 <= nrows_; i_ += 4) {                                                         \
+            double a_[4] = {0.0, 0.0, 0.0, 0.0};                                                    \
+            _Pragma("unroll") for (int q_ = 0; q_ < NV_; ++q_) {                                    \
+                _Pragma("unroll") for (int u_ = 0; u_ < 4; ++u_)                                    \
+                    a_[u_] = fma(cf[q_], DB_LDCS(rv[q_] + (int64_t)(i_ + u_) * DB_TILE), a_[u_]);   \
+            }                                                                                       \
+            _Pragma("unroll") for (int u_ = 0; u_ < 4; ++u_) x[(int64_t)(i_ + u_) * DB_TILE] = a_[u_]; \
+        }                                                                                           \
+        for (; i_ < nrows_; ++i_) {                                                                 \
+            double a_ = 0.0;                                                                        \
+            _Pragma("unroll") for (int q_ = 0; q_ < NV_; ++q_) a_ = fma(cf[q_], DB_LDCS(rv[q_] + (int64_t)i_ * DB_TILE), a_); \
+            x[(int64_t)i_ * DB_TILE] = a_;                                                          \
+        }                                                                                           \
+    }
+
 // Triangular solves with the right-hand-side combination fused into the row starts.
 // NV = number of right-hand-side vectors (compile time: pointers and coefficients stay in registers).
 // Two-stage register pipeline over chunks of SOLVE_CH entries: the factor values + instructions of chunk q+1 are in
@@ -302,6 +325,7 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
     double cf[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+    SOLVE_PROLOGUE(NV, B.n)
 #define SOLVE_LOADA(K)                                                                              \
     _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) { K.v[j] = DB_LDCS(fp + j * DB_TILE); K.c[j] = pp[j]; } \
     fp += SOLVE_CH * DB_TILE; pp += SOLVE_CH;
@@ -314,8 +338,7 @@ k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, i
             if (c >= 0) { if (c < DB_I_FRESH_MEM) val = x[c]; }                                     \
             else if (c != DB_I_SKIP) {                                                              \
                 const int o = -1 - c;                                                               \
-                if (FWD) { _Pragma("unroll") for (int q = 0; q < NV; ++q) val = fma(cf[q], DB_LDCS(rv[q] + o), val); } \
-                else val = x[o];                                                                    \
+                val = x[o];                                                                        \
             }                                                                                       \
             xv[j] = val;                                                                            \
         }                                                                                           \
@@ -434,6 +457,7 @@ k_batches_solve_ring(const db_batch* __restrict__ batches, int nbatch, int lu_sl
     __syncthreads();
     if (threadIdx.x == 0)
         for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
+    SOLVE_PROLOGUE(NV, B.n)
     int slot = 0;
     unsigned phase = 0;
     int cur = -1;
@@ -452,11 +476,7 @@ k_batches_solve_ring(const db_batch* __restrict__ batches, int nbatch, int lu_sl
             double val = 0.0;
             if (c >= 0) { if (c < DB_I_FRESH_MEM) val = x[c]; }
             else if (c != DB_I_SKIP) {
-                const int o = -1 - c;
-                if (fwd) {
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) val = fma(cf[k], DB_LDCS(rv[k] + o), val);
-                } else val = x[o];
+                val = x[-1 - c];
             }
             xv[j] = val;
         }
