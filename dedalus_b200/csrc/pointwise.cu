@@ -68,6 +68,53 @@ k_pointwise_v2(const double* __restrict__ in, double* __restrict__ out, int64_t 
     }
 }
 
+// v3: the per-thread staging of v2 with the copies made asynchronous (16-byte cp.async, L1 bypass) and double buffered:
+// the n_in loads of the NEXT tile are in flight while the current tile's products are evaluated, and no load result
+// ever sits on a register dependency.  Each thread only reads the slots it filled itself, so no block barrier.
+#define PW3_T 128
+__global__ void __launch_bounds__(PW3_T)
+k_pointwise_v3(const double* __restrict__ in, double* __restrict__ out, int64_t npoints, int n_in, int n_out,
+               const int32_t* __restrict__ term_ptr, const double* __restrict__ coef,
+               const int32_t* __restrict__ fac_ptr, const int32_t* __restrict__ fac)
+{
+    DB_SMEM(double, tile);                         // 2 buffers of [n_in][PW3_T] double2
+    double2* tile2 = reinterpret_cast<double2*>(tile);
+    const int64_t np2 = npoints >> 1;
+    const int64_t stride = (int64_t)gridDim.x * PW3_T;
+    int64_t q = (int64_t)blockIdx.x * PW3_T + threadIdx.x;
+    auto stage = [&](int64_t qq, int buf) {
+        if (qq < np2) {
+            double2* dst = tile2 + (size_t)buf * n_in * PW3_T + threadIdx.x;
+            const double* src = in + 2 * qq;
+            for (int i = 0; i < n_in; ++i) db_cp_async16(dst + i * PW3_T, src + (int64_t)i * npoints);
+        }
+    };
+    int buf = 0;
+    stage(q, 0);
+    db_cp_commit();
+    for (; q - threadIdx.x < np2; q += stride, buf ^= 1) {        // block-uniform trip count
+        stage(q + stride, buf ^ 1);
+        db_cp_commit();
+        db_cp_wait<1>();
+        if (q < np2) {
+            const double2* mine = tile2 + (size_t)buf * n_in * PW3_T + threadIdx.x;
+            for (int o = 0; o < n_out; ++o) {
+                double a0 = 0.0, a1 = 0.0;
+                for (int t = term_ptr[o]; t < term_ptr[o + 1]; ++t) {
+                    double p0 = coef[t], p1 = p0;
+                    for (int f = fac_ptr[t]; f < fac_ptr[t + 1]; ++f) {
+                        const double2 v = mine[fac[f] * PW3_T];
+                        p0 *= v.x; p1 *= v.y;
+                    }
+                    a0 += p0; a1 += p1;
+                }
+                reinterpret_cast<double2*>(out + (int64_t)o * npoints)[q] = make_double2(a0, a1);
+            }
+        }
+    }
+    db_cp_wait<0>();
+}
+
 extern "C" int db_pointwise(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
                             const int32_t* term_ptr, const double* coef, const int32_t* fac_ptr, const int32_t* fac, int32_t nfac_total,
                             void* stream)
@@ -75,6 +122,23 @@ extern "C" int db_pointwise(const double* in, double* out, int64_t npoints, int3
     (void)nfac_total;
     if (npoints <= 0 || n_out <= 0) return 0;
     const bool vec = (npoints % 2 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const size_t smem3 = (size_t)2 * n_in * PW3_T * sizeof(double2);
+    if (vec && smem3 <= (size_t)DB_MAX_SMEM) {
+        int per_sm = (int)((size_t)(226 * 1024) / (smem3 + 1024));
+        if (per_sm > 8) per_sm = 8;
+        int64_t blocks3 = (npoints / 2 + PW3_T - 1) / PW3_T;
+        if (blocks3 > (int64_t)148 * per_sm) blocks3 = (int64_t)148 * per_sm;
+#ifndef DB_EMU
+        static bool attr3 = false;
+        if (!attr3) {
+            cudaFuncSetAttribute(k_pointwise_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+            cudaFuncSetAttribute(k_pointwise_v3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            attr3 = true;
+        }
+#endif
+        DB_LAUNCH(k_pointwise_v3, dim3((unsigned)blocks3), dim3(PW3_T), smem3, stream, in, out, npoints, n_in, n_out, term_ptr, coef, fac_ptr, fac);
+        return db_check_launch("pointwise");
+    }
     size_t smem = (size_t)n_in * PW_TILE * sizeof(double) * (vec ? 2 : 1);
     if (smem > (size_t)DB_MAX_SMEM) { db_set_error("pointwise: too many inputs (%d)", n_in); return 1; }
     const int64_t items = vec ? npoints / 2 : npoints;
