@@ -544,9 +544,25 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     return db_check_launch("batches_solve");
 }
 
+#define MV_MAX_MONO 16
+struct MvTerm { double val; int col_off; int mono; };
+__device__ __forceinline__ MvTerm mv_load(const db_term* __restrict__ rec, int t)
+{
+    // one 16-byte load (the records are 16-byte aligned: the array comes from its own allocation)
+#ifdef DB_EMU
+    MvTerm r; r.val = rec[t].val; r.col_off = rec[t].col_off; r.mono = rec[t].mono; return r;
+#else
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + t);
+    MvTerm r; r.val = __hiloint2double(raw.y, raw.x); r.col_off = raw.z; r.mono = raw.w; return r;
+#endif
+}
 __global__ void __launch_bounds__(PB_THREADS)
 k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, int ym_slot, int yl_slot)
 {
+    // y = (sum_m mono_m T_m) x for the M and L templates: one thread per system, MV_ROWS_PER_BLOCK rows per CTA.
+    // Terms are 16-byte records read with one warp-uniform load each; the system's monomial values (powers of its
+    // wavenumbers) sit in shared memory, one private column per thread.
+    DB_SMEM(double, monos);                       // [MV_MAX_MONO][PB_THREADS]
     const int bi = find_batch(batches, nbatch, blockIdx.x, 1);
     const db_batch& B = batches[bi];
     const int local = blockIdx.x - B.blk_matvec;
@@ -558,24 +574,32 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
     const int r1 = (r0 + MV_ROWS_PER_BLOCK < n) ? r0 + MV_ROWS_PER_BLOCK : n;
     const int64_t tb = db_tbase(s, n);
     const double* __restrict__ x = B.vec[x_slot] + tb;
-    const double* __restrict__ mono = B.mono + s;
-    // two passes over the same rows (M then L); program pointers are copied to registers so the stores to y
-    // cannot force reloads of the descriptor
+    const int nm = B.n_mono < MV_MAX_MONO ? B.n_mono : MV_MAX_MONO;
+    double* mine = monos + threadIdx.x;
+    for (int m = 0; m < nm; ++m) mine[m * PB_THREADS] = B.mono[(int64_t)m * ld + s];
     for (int which = 0; which < 2; ++which) {
         const int slot = which ? yl_slot : ym_slot;
         if (slot < 0) continue;
         const int32_t* __restrict__ ptr = which ? B.l_ptr : B.m_ptr;
-        const int32_t* __restrict__ col = which ? B.l_col : B.m_col;
-        const int32_t* __restrict__ mon = which ? B.l_mono : B.m_mono;
-        const double* __restrict__ val = which ? B.l_val : B.m_val;
+        const db_term* __restrict__ rec = which ? B.l_rec : B.m_rec;
         double* __restrict__ y = B.vec[slot] + tb;
         int t = ptr[r0];
         for (int i = r0; i < r1; ++i) {
             const int t1 = ptr[i + 1];
-            double acc = 0.0;
-            for (; t < t1; ++t)
-                acc = fma(val[t] * mono[(int64_t)mon[t] * ld], x[(int64_t)col[t] * DB_TILE], acc);
-            y[(int64_t)i * DB_TILE] = acc;
+            double acc0 = 0.0, acc1 = 0.0;
+            for (; t + 2 <= t1; t += 2) {
+                const MvTerm a = mv_load(rec, t), b = mv_load(rec, t + 1);
+                const double xa = x[a.col_off], xb = x[b.col_off];
+                const double ma = mine[a.mono * PB_THREADS], mb = mine[b.mono * PB_THREADS];
+                acc0 = fma(a.val * ma, xa, acc0);
+                acc1 = fma(b.val * mb, xb, acc1);
+            }
+            if (t < t1) {
+                const MvTerm a = mv_load(rec, t);
+                acc0 = fma(a.val * mine[a.mono * PB_THREADS], x[a.col_off], acc0);
+                ++t;
+            }
+            y[(int64_t)i * DB_TILE] = acc0 + acc1;
         }
     }
 }
@@ -583,7 +607,7 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
 extern "C" int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t x_slot, int32_t ym_slot, int32_t yl_slot, void* stream)
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
-    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(PB_THREADS), 0, stream, batches, nbatch, x_slot, ym_slot, yl_slot);
+    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(PB_THREADS), MV_MAX_MONO * PB_THREADS * sizeof(double), stream, batches, nbatch, x_slot, ym_slot, yl_slot);
     return db_check_launch("batches_matvec");
 }
 

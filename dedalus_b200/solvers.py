@@ -60,6 +60,9 @@ class DeviceBatch:
             ptr, col, mono_i, val = prog.mv[name]
             k = name.lower()
             self.t[k + '_ptr'], self.t[k + '_col'], self.t[k + '_mono'], self.t[k + '_val'] = f(ptr), f(col), f(mono_i), d(val)
+            rec = np.zeros(len(col), dtype=np.dtype([('val', '<f8'), ('col_off', '<i4'), ('mono', '<i4')]))     # db_term
+            rec['val'], rec['col_off'], rec['mono'] = val, np.asarray(col, dtype=np.int64) * prog.tile, mono_i
+            self.t[k + '_rec'] = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()).to(dev)
         self.maps = []
         for side, arena in (('cols', solver.var_arena), ('rows', solver.eq_arena)):
             m = line_maps(batch, arena, side)
@@ -120,6 +123,9 @@ class BatchSet:
                 c.lu[j] = db.lu_tensor(j).data_ptr()
             c.m_ptr, c.m_col, c.m_mono, c.m_val = (t[k].data_ptr() for k in ('m_ptr', 'm_col', 'm_mono', 'm_val'))
             c.l_ptr, c.l_col, c.l_mono, c.l_val = (t[k].data_ptr() for k in ('l_ptr', 'l_col', 'l_mono', 'l_val'))
+            c.m_rec, c.l_rec, c.n_mono = t['m_rec'].data_ptr(), t['l_rec'].data_ptr(), len(db.prog.monos)
+            if len(db.prog.monos) > 16:
+                raise NotImplementedError("more than 16 wavenumber monomials in one class (MV_MAX_MONO in csrc/pencil.cu)")
             c.diag_eid, c.fl_ptr, c.fl_eid = t['diag_eid'].data_ptr(), t['fl_ptr'].data_ptr(), t['fl_eid'].data_ptr()
             c.fu_ptr, c.fu_eid, c.fd_eid = t['fu_ptr'].data_ptr(), t['fu_eid'].data_ptr(), t['fd_eid'].data_ptr()
             c.asm_ptr, c.asm_mono, c.asm_val = t['asm_ptr'].data_ptr(), t['asm_mono'].data_ptr(), t['asm_val'].data_ptr()

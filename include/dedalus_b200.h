@@ -168,6 +168,8 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
 #define DB_I_FRESH_REG 0x40000000
 #define DB_I_FRESH_MEM 0x20000000
 #define DB_I_OFFMASK   0x1FFFFFFF
+/* one term of a template mat-vec: y[row] += val * mono[mono][s] * x[col_off + s']; col_off = column * DB_TILE */
+typedef struct { double val; int32_t col_off; int32_t mono; } db_term;
 typedef struct {
     int32_t n, S, ld, n_entries;
     int32_t n_fwd, n_bwd;
@@ -179,6 +181,8 @@ typedef struct {
     double* lu[DB_MAX_LU];
     const int32_t *m_ptr, *m_col, *m_mono; const double* m_val;
     const int32_t *l_ptr, *l_col, *l_mono; const double* l_val;
+    const db_term *m_rec, *l_rec;      /* the same term lists packed 16 bytes per term (fused mat-vec kernel) */
+    int32_t n_mono, pad_;
     const int64_t* line_base[2]; const int32_t* line_kind[2]; const int32_t* line_ptr[2]; const int32_t* line_pos[2];
     const int64_t* sys_off[2];
     /* factorisation programs */
