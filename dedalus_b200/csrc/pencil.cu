@@ -503,6 +503,113 @@ k_batches_solve_ring(const db_batch* __restrict__ batches, int nbatch, int lu_sl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Triangular solves, branch-free variant on the same bulk-copy ring.  The interpreter above decodes one instruction
+// word per entry (load -> compare -> branch), which with one or two warps per scheduler costs ~200 cycles per entry
+// and is what kept the sweep from scaling to fewer systems per GPU.  Here the host pre-decodes each 16-entry chunk
+// into a control block (gather offsets, finished-row offsets, three 16-bit masks; dedalus_b200/pencils.py
+// solve_control_blocks) and the chunk is straight-line code: 16 gathers, then per entry one shared-memory load, one
+// FMA, a predicated store and a select; chunks made only of multiply-accumulates (the dense boundary rows: a third of
+// all entries) take a shorter path.
+// ---------------------------------------------------------------------------------------------------------
+#define SOLVE_CTRL_WORDS 36
+#define SOLVE_FSTAGE_BYTES (SOLVE_CE * DB_TILE * 8 + SOLVE_CTRL_WORDS * 4)
+
+template <bool FWD, bool LATE>
+__device__ __forceinline__ double solve_chunk_flat(const double* __restrict__ vals, const int* __restrict__ ctrl, double* x, double acc)
+{
+    int goff[SOLVE_CE], foff[SOLVE_CE];
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; j += 4) {
+        const int4 g = *reinterpret_cast<const int4*>(ctrl + j);
+        goff[j] = g.x; goff[j + 1] = g.y; goff[j + 2] = g.z; goff[j + 3] = g.w;
+    }
+    double xv[SOLVE_CE];
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; ++j) xv[j] = x[goff[j]];
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; j += 4) {
+        const int4 f = *reinterpret_cast<const int4*>(ctrl + SOLVE_CE + j);
+        foff[j] = f.x; foff[j + 1] = f.y; foff[j + 2] = f.z; foff[j + 3] = f.w;
+    }
+    const unsigned maskE = (unsigned)ctrl[2 * SOLVE_CE], maskB = (unsigned)ctrl[2 * SOLVE_CE + 1], maskF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; ++j) {
+        const double v = vals[j * DB_TILE];
+        if (LATE) { if (maskF & (1u << j)) xv[j] = x[goff[j]]; }
+        const double acc_a = fma(-v, xv[j], acc);
+        const double val = FWD ? acc : acc * v;
+        if (maskE & (1u << j)) x[foff[j]] = val;
+        acc = (maskB & (1u << j)) ? xv[j] : acc_a;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ double solve_chunk_pure(const double* __restrict__ vals, const int* __restrict__ ctrl, const double* x, double acc)
+{
+    double xv[SOLVE_CE];
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; j += 4) {
+        const int4 g = *reinterpret_cast<const int4*>(ctrl + j);
+        xv[j] = x[g.x]; xv[j + 1] = x[g.y]; xv[j + 2] = x[g.z]; xv[j + 3] = x[g.w];
+    }
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; ++j) acc = fma(-vals[j * DB_TILE], xv[j], acc);
+    return acc;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
+{
+    DB_SMEM(unsigned char, ring);
+    db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int tile = blockIdx.x - B.blk_solve;
+    const int s = tile * SOLVE_THREADS + threadIdx.x;          // padded lanes (s >= S) run on the zero padding
+    const int64_t tb = db_tbase(s, B.n);
+    const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
+    const int32_t* __restrict__ ctrl_g = B.ctrl;
+    const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
+    double* x = B.vec[x_slot] + tb;
+    const double* rv[NV];
+    double cf[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+    auto issue = [&](int q, int slot) {
+        unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+        db_mbar_expect_tx(&bars[slot], SOLVE_FSTAGE_BYTES);
+        db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &bars[slot]);
+        db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, ctrl_g + (int64_t)q * SOLVE_CTRL_WORDS, SOLVE_CTRL_WORDS * 4, &bars[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) db_mbar_init(&bars[i], 1);
+        db_mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
+    SOLVE_PROLOGUE(NV, B.n)
+    int slot = 0;
+    unsigned phase = 0;
+    double acc = 0.0;
+    for (int q = 0; q < nchunks; ++q) {
+        db_mbar_wait(&bars[slot], phase);
+        const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+        const double* __restrict__ vals = reinterpret_cast<const double*>(st) + threadIdx.x;
+        const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+        const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+        if ((mB | mF) == 0) acc = solve_chunk_pure(vals, ctrl, x, acc);
+        else if (q < nfwd) acc = mF ? solve_chunk_flat<true, true>(vals, ctrl, x, acc) : solve_chunk_flat<true, false>(vals, ctrl, x, acc);
+        else acc = mF ? solve_chunk_flat<false, true>(vals, ctrl, x, acc) : solve_chunk_flat<false, false>(vals, ctrl, x, acc);
+        __syncthreads();                                   // both warps are done with this stage
+        if (threadIdx.x == 0 && q + nstages < nchunks) issue(q + nstages, slot);
+        if (++slot == nstages) { slot = 0; phase ^= 1; }
+    }
+}
+
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
                                 const db_slotcomb* rhs, void* stream)
 {
@@ -515,8 +622,22 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     // times over, without taking more shared memory than leaves the L1 useful for the x re-reads.
     static int impl = -1, st_env = 0;
     if (impl < 0) {
-        const char* e = getenv("DB_SOLVE_IMPL"); impl = (e && strcmp(e, "regs") == 0) ? 0 : 1;
+        const char* e = getenv("DB_SOLVE_IMPL");
+        impl = (e && strcmp(e, "regs") == 0) ? 0 : (e && strcmp(e, "ring") == 0) ? 1 : 2;
         const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
+    }
+    if (impl == 2) {
+        const int per_sm = (total_blocks + 147) / 148;
+        int nst = per_sm >= 7 ? 3 : per_sm >= 4 ? 4 : per_sm >= 2 ? 8 : 16;
+        if (st_env >= 2 && st_env <= 24) nst = st_env;
+        const size_t smem = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
+#define FLAT_GO(NV_) { static int attr_st = 0; \
+        if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_>)); attr_st = 1; } \
+        DB_LAUNCH((k_batches_solve_flat<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
+        if (nv <= 1) FLAT_GO(1) else if (nv == 2) FLAT_GO(2) else if (nv == 3) FLAT_GO(3) else if (nv == 4) FLAT_GO(4)
+        else if (nv == 5) FLAT_GO(5) else if (nv == 6) FLAT_GO(6) else if (nv <= 8) FLAT_GO(8) else if (nv <= 12) FLAT_GO(12) else FLAT_GO(16)
+#undef FLAT_GO
+        return db_check_launch("batches_solve");
     }
     if (impl == 1) {
         const int per_sm = (total_blocks + 147) / 148;

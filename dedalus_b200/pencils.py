@@ -445,6 +445,48 @@ def _permuted_templates(batch, name):
     return out
 
 
+SOLVE_CTRL_WORDS = 36
+
+
+def solve_control_blocks(plain, code, n_fwd, CH=16):
+    """Per-chunk control blocks of the branch-free solve kernel (csrc/pencil.cu k_batches_solve_flat), derived from the
+    flat instruction stream: for each chunk of 16 entries
+        goff[16]  element offset gathered before the chunk is consumed: the column of a multiply-accumulate entry, the
+                  NEXT row (its start value) of a row-boundary entry, 0 for padding (whose factor value is 0)
+        foff[16]  element offset of the row FINISHED at a row-boundary entry
+        maskE     entries that finish a row (store), maskB entries that start a row (take the gathered start value),
+        maskF     entries whose column was finished inside this chunk (re-read after the store instead of the gather)
+    Layout: int32 [nchunks][36] = goff, foff, maskE, maskB, maskF, 0."""
+    SKIP, FRESH = -2**31, (1 << 30) | (1 << 29)
+    MASK = (1 << 29) - 1
+    code = np.asarray(code, dtype=np.int64)           # stream with the hazard marks (DB_I_FRESH_*)
+    plain = np.asarray(plain, dtype=np.int64)         # same stream before marking: plain column offsets
+    nE = len(code)
+    assert nE % CH == 0 and n_fwd % CH == 0 and len(plain) == nE
+    out = np.zeros((nE // CH, SOLVE_CTRL_WORDS), dtype=np.int64)
+    cur = -1
+    for e in range(nE):
+        if e == n_fwd:
+            cur = -1
+        q, j = divmod(e, CH)
+        c = int(plain[e])
+        if c == SKIP:
+            continue
+        if c < 0:
+            nxt = -1 - c
+            out[q, j] = nxt
+            out[q, 33] |= 1 << j
+            if cur >= 0:
+                out[q, 16 + j] = cur
+                out[q, 32] |= 1 << j
+            cur = nxt
+        else:
+            out[q, j] = c
+            if int(code[e]) & FRESH:
+                out[q, 34] |= 1 << j
+    return out.astype(np.int32)
+
+
 def compile_batch(batch, a0, b0):
     """Build ordering (if needed), symbolic LU and all programs for the LHS  a0*M + b0*L."""
     if batch.cols is None:
@@ -507,6 +549,7 @@ def compile_batch(batch, a0, b0):
         sec.extend([SKIP] * pad); e += pad
         # hazard marking: the x values of a chunk are gathered in one burst right before the chunk is consumed
         sec = np.array(sec, dtype=np.int64)
+        plain_secs.append(sec.copy())
         done_at, completed, cur = {}, [], None
         for pos in range(len(sec)):
             c = sec[pos]
@@ -523,11 +566,13 @@ def compile_batch(batch, a0, b0):
                     k = len(completed) - completed.index(col)
                     sec[pos] = (FRESH_REG | k) if k <= 3 else (FRESH_MEM | int(c))
         return sec
+    plain_secs = []
     sec_f = emit_section(order_f, True)
     prog.n_fwd = len(sec_f)
     sec_b = emit_section(order_b, False)
     prog.nE = e
     prog.prog = np.concatenate([sec_f, sec_b]).astype(np.int32)
+    prog.ctrl = solve_control_blocks(np.concatenate(plain_secs), prog.prog, prog.n_fwd)
     assert len(prog.prog) == prog.nE
     prog.diag_eid = diag_eid
     # ---- factor program

@@ -54,7 +54,7 @@ class DeviceBatch:
         mono = np.zeros((len(prog.monos), ld)); mono[:, :prog.S] = prog.mono_vals
         f = lambda a: _i32(torch, a, dev)
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
-        self.t = dict(mono=d(mono), prog=f(prog.prog), diag_eid=f(prog.diag_eid), fl_ptr=f(prog.fl_ptr), fl_eid=f(prog.fl_eid),
+        self.t = dict(mono=d(mono), prog=f(prog.prog), ctrl=f(prog.ctrl.ravel()), diag_eid=f(prog.diag_eid), fl_ptr=f(prog.fl_ptr), fl_eid=f(prog.fl_eid),
                       fu_ptr=f(prog.fu_ptr), fu_eid=f(prog.fu_eid), fd_eid=f(prog.fd_eid))
         for name in ('M', 'L'):
             ptr, col, mono_i, val = prog.mv[name]
@@ -116,7 +116,7 @@ class BatchSet:
                 c.line_base[side], c.line_kind[side] = m['base'].data_ptr(), m['kind'].data_ptr()
                 c.line_ptr[side], c.line_pos[side], c.sys_off[side] = m['ptr'].data_ptr(), m['pos'].data_ptr(), m['sys_off'].data_ptr()
             t = db.t
-            c.prog, c.mono = t['prog'].data_ptr(), t['mono'].data_ptr()
+            c.prog, c.mono, c.ctrl = t['prog'].data_ptr(), t['mono'].data_ptr(), t['ctrl'].data_ptr()
             for j, v in enumerate(db.vecs):
                 c.vec[j] = v.data_ptr()
             for j in range(nlu):

@@ -182,6 +182,8 @@ typedef struct {
     const int32_t *m_ptr, *m_col, *m_mono; const double* m_val;
     const int32_t *l_ptr, *l_col, *l_mono; const double* l_val;
     const db_term *m_rec, *l_rec;      /* the same term lists packed 16 bytes per term (fused mat-vec kernel) */
+    const int32_t* ctrl;               /* [n_entries/16][36] per-chunk control blocks of the branch-free solve kernel:
+                                          gather offsets[16], finished-row offsets[16], masks end / begin / late, 0  */
     int32_t n_mono, pad_;
     const int64_t* line_base[2]; const int32_t* line_kind[2]; const int32_t* line_ptr[2]; const int32_t* line_pos[2];
     const int64_t* sys_off[2];

@@ -28,6 +28,7 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct double2 { double x, y; };
+struct int4 { int x, y, z, w; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 typedef void* cudaStream_t;
 typedef int cudaError_t;
