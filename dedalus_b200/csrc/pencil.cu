@@ -732,46 +732,59 @@ extern "C" int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_
     return db_check_launch("batches_matvec");
 }
 
+// 64 x 64 tiles: one side is a full 512-byte row of the tile-major pencil vectors (64 systems), the other a 512-byte
+// run of a z line; 16 independent loads per thread keep enough bytes in flight for a pure data-movement kernel.
+#define MOVE_T 64
 template <bool GATHER>
-__global__ void k_batches_move(const db_batch* __restrict__ batches, int nbatch, int side, int slot, double* __restrict__ arena)
+__global__ void __launch_bounds__(MOVE_T * 4)
+k_batches_move(const db_batch* __restrict__ batches, int nbatch, int side, int slot, double* __restrict__ arena)
 {
-    DB_SMEM(double, tile);
+    DB_SMEM(double, tile);                         // [MOVE_T][MOVE_T + 1]
     const int bi = find_batch(batches, nbatch, blockIdx.x, 2 + side);
     const db_batch& B = batches[bi];
     int local = blockIdx.x - B.blk_move[side];
-    const int sblocks = (B.S + 31) / 32;
-    const int mblocks = (B.max_len[side] + 31) / 32;
+    const int sblocks = (B.S + MOVE_T - 1) / MOVE_T;
+    const int mblocks = (B.max_len[side] + MOVE_T - 1) / MOVE_T;
     const int q = local / (sblocks * mblocks);
     local -= q * sblocks * mblocks;
-    const int m0 = (local / sblocks) * 32, s0 = (local % sblocks) * 32;
-    const int32_t* lp = B.line_ptr[side];
+    const int m0 = (local / sblocks) * MOVE_T, s0 = (local % sblocks) * MOVE_T;
+    const int32_t* __restrict__ lp = B.line_ptr[side];
     const int len = lp[q + 1] - lp[q];
     if (m0 >= len) return;
     const int S = B.S, ld = B.ld;
     const int64_t base = B.line_base[side][q];
-    const int64_t* so = B.sys_off[side] + (int64_t)B.line_kind[side][q] * ld;
-    const int32_t* pos = B.line_pos[side] + lp[q];
-    double* vec = B.vec[slot];
+    const int64_t* __restrict__ so = B.sys_off[side] + (int64_t)B.line_kind[side][q] * ld;
+    const int32_t* __restrict__ pos = B.line_pos[side] + lp[q];
+    double* __restrict__ vec = B.vec[slot];
     const int tx = threadIdx.x, ty = threadIdx.y;
+    constexpr int P = MOVE_T + 1;
     if (GATHER) {
-        for (int r = ty; r < 32; r += 8) {
-            int s = s0 + r, m = m0 + tx;
-            if (s < S && m < len) tile[r * 33 + tx] = arena[base + so[s] + m];
+#pragma unroll 4
+        for (int r = ty; r < MOVE_T; r += 4) {
+            const int s = s0 + r, m = m0 + tx;
+            if (s < S && m < len) tile[r * P + tx] = DB_LDCS(arena + base + so[s] + m);
         }
         __syncthreads();
-        for (int r = ty; r < 32; r += 8) {
-            int m = m0 + r, s = s0 + tx;
-            if (s < S && m < len) vec[db_tbase(s, B.n) + (int64_t)pos[m] * DB_TILE] = tile[tx * 33 + r];
+        const int s = s0 + tx;
+        const int64_t tb = db_tbase(s < S ? s : 0, B.n);
+#pragma unroll 4
+        for (int r = ty; r < MOVE_T; r += 4) {
+            const int m = m0 + r;
+            if (s < S && m < len) vec[tb + (int64_t)pos[m] * DB_TILE] = tile[tx * P + r];
         }
     } else {
-        for (int r = ty; r < 32; r += 8) {
-            int m = m0 + r, s = s0 + tx;
-            if (s < S && m < len) tile[tx * 33 + r] = vec[db_tbase(s, B.n) + (int64_t)pos[m] * DB_TILE];
+        const int s = s0 + tx;
+        const int64_t tb = db_tbase(s < S ? s : 0, B.n);
+#pragma unroll 4
+        for (int r = ty; r < MOVE_T; r += 4) {
+            const int m = m0 + r;
+            if (s < S && m < len) tile[tx * P + r] = DB_LDCS(vec + tb + (int64_t)pos[m] * DB_TILE);
         }
         __syncthreads();
-        for (int r = ty; r < 32; r += 8) {
-            int s = s0 + r, m = m0 + tx;
-            if (s < S && m < len) arena[base + so[s] + m] = tile[r * 33 + tx];
+#pragma unroll 4
+        for (int r = ty; r < MOVE_T; r += 4) {
+            const int sr = s0 + r, m = m0 + tx;
+            if (sr < S && m < len) arena[base + so[sr] + m] = tile[r * P + tx];
         }
     }
 }
@@ -781,8 +794,9 @@ extern "C" int db_batches_move(const db_batch* batches, int32_t nbatch, int32_t 
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
     if (side < 0 || side > 1 || slot < 0 || slot >= DB_MAX_VECS) { db_set_error("batches_move: bad arguments"); return 1; }
-    if (gather) DB_LAUNCH(k_batches_move<true>, dim3(total_blocks), dim3(32, 8), 32 * 33 * sizeof(double), stream, batches, nbatch, side, slot, arena);
-    else DB_LAUNCH(k_batches_move<false>, dim3(total_blocks), dim3(32, 8), 32 * 33 * sizeof(double), stream, batches, nbatch, side, slot, arena);
+    const size_t smem = (size_t)MOVE_T * (MOVE_T + 1) * sizeof(double);
+    if (gather) DB_LAUNCH(k_batches_move<true>, dim3(total_blocks), dim3(MOVE_T, 4), smem, stream, batches, nbatch, side, slot, arena);
+    else DB_LAUNCH(k_batches_move<false>, dim3(total_blocks), dim3(MOVE_T, 4), smem, stream, batches, nbatch, side, slot, arena);
     return db_check_launch("batches_move");
 }
 
