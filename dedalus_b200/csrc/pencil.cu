@@ -627,8 +627,11 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
         const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
     }
     if (impl == 2) {
+        // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
+        // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
+        // per step); with few CTAs per SM the ring is the only source of memory parallelism, so it gets deep
         const int per_sm = (total_blocks + 147) / 148;
-        int nst = per_sm >= 7 ? 3 : per_sm >= 4 ? 4 : per_sm >= 2 ? 8 : 16;
+        int nst = per_sm >= 5 ? 2 : per_sm >= 3 ? 4 : per_sm >= 2 ? 8 : 16;
         if (st_env >= 2 && st_env <= 24) nst = st_env;
         const size_t smem = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
 #define FLAT_GO(NV_) { static int attr_st = 0; \
@@ -677,50 +680,72 @@ __device__ __forceinline__ MvTerm mv_load(const db_term* __restrict__ rec, int t
     MvTerm r; r.val = __hiloint2double(raw.y, raw.x); r.col_off = raw.z; r.mono = raw.w; return r;
 #endif
 }
-__global__ void __launch_bounds__(PB_THREADS)
+#define MV_THREADS 64
+__global__ void __launch_bounds__(MV_THREADS)
 k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, int ym_slot, int yl_slot)
 {
-    // y = (sum_m mono_m T_m) x for the M and L templates: one thread per system, MV_ROWS_PER_BLOCK rows per CTA.
+    // y = (sum_m mono_m T_m) x for the M and L templates: one thread per system, one CTA = one 64-system tile x
+    // B.mv_rows consecutive rows.  Rows are walked in order, so the x rows a CTA touches form a window sliding down the
+    // (mode-major) band: with a handful of CTAs per SM those windows stay L1-resident, whereas 64-row blocks scattered
+    // over the matrix missed L1 three times out of four (ncu: 8.4 GB of L2 traffic for 2 GB of algorithmic bytes).
     // Terms are 16-byte records read with one warp-uniform load each; the system's monomial values (powers of its
     // wavenumbers) sit in shared memory, one private column per thread.
-    DB_SMEM(double, monos);                       // [MV_MAX_MONO][PB_THREADS]
+    DB_SMEM(double, monos);                       // [MV_MAX_MONO][MV_THREADS]
     const int bi = find_batch(batches, nbatch, blockIdx.x, 1);
     const db_batch& B = batches[bi];
     const int local = blockIdx.x - B.blk_matvec;
-    const int sblocks = (B.S + PB_THREADS - 1) / PB_THREADS;
-    const int s = (local % sblocks) * PB_THREADS + threadIdx.x;
+    const int sblocks = (B.S + MV_THREADS - 1) / MV_THREADS;
+    const int s = (local % sblocks) * MV_THREADS + threadIdx.x;
     if (s >= B.S) return;
-    const int r0 = (local / sblocks) * MV_ROWS_PER_BLOCK;
+    const int r0 = (local / sblocks) * B.mv_rows;
     const int n = B.n, ld = B.ld;
-    const int r1 = (r0 + MV_ROWS_PER_BLOCK < n) ? r0 + MV_ROWS_PER_BLOCK : n;
+    const int r1 = (r0 + B.mv_rows < n) ? r0 + B.mv_rows : n;
     const int64_t tb = db_tbase(s, n);
     const double* __restrict__ x = B.vec[x_slot] + tb;
     const int nm = B.n_mono < MV_MAX_MONO ? B.n_mono : MV_MAX_MONO;
     double* mine = monos + threadIdx.x;
-    for (int m = 0; m < nm; ++m) mine[m * PB_THREADS] = B.mono[(int64_t)m * ld + s];
-    for (int which = 0; which < 2; ++which) {
-        const int slot = which ? yl_slot : ym_slot;
-        if (slot < 0) continue;
-        const int32_t* __restrict__ ptr = which ? B.l_ptr : B.m_ptr;
-        const db_term* __restrict__ rec = which ? B.l_rec : B.m_rec;
-        double* __restrict__ y = B.vec[slot] + tb;
-        int t = ptr[r0];
-        for (int i = r0; i < r1; ++i) {
-            const int t1 = ptr[i + 1];
+    for (int m = 0; m < nm; ++m) mine[m * MV_THREADS] = B.mono[(int64_t)m * ld + s];
+    const bool do_m = ym_slot >= 0, do_l = yl_slot >= 0;
+    const int32_t* __restrict__ mptr = B.m_ptr;
+    const int32_t* __restrict__ lptr = B.l_ptr;
+    const db_term* __restrict__ mrec = B.m_rec;
+    const db_term* __restrict__ lrec = B.l_rec;
+    double* __restrict__ ym = do_m ? B.vec[ym_slot] + tb : nullptr;
+    double* __restrict__ yl = do_l ? B.vec[yl_slot] + tb : nullptr;
+    int tm = do_m ? mptr[r0] : 0, tl = do_l ? lptr[r0] : 0;
+    // M and L rows are interleaved (same row of both operators back to back) so both sweep the same x window
+    for (int i = r0; i < r1; ++i) {
+        if (do_m) {
+            const int t1 = mptr[i + 1];
             double acc0 = 0.0, acc1 = 0.0;
-            for (; t + 2 <= t1; t += 2) {
-                const MvTerm a = mv_load(rec, t), b = mv_load(rec, t + 1);
+            for (; tm + 2 <= t1; tm += 2) {
+                const MvTerm a = mv_load(mrec, tm), b = mv_load(mrec, tm + 1);
                 const double xa = x[a.col_off], xb = x[b.col_off];
-                const double ma = mine[a.mono * PB_THREADS], mb = mine[b.mono * PB_THREADS];
-                acc0 = fma(a.val * ma, xa, acc0);
-                acc1 = fma(b.val * mb, xb, acc1);
+                acc0 = fma(a.val * mine[a.mono * MV_THREADS], xa, acc0);
+                acc1 = fma(b.val * mine[b.mono * MV_THREADS], xb, acc1);
             }
-            if (t < t1) {
-                const MvTerm a = mv_load(rec, t);
-                acc0 = fma(a.val * mine[a.mono * PB_THREADS], x[a.col_off], acc0);
-                ++t;
+            if (tm < t1) {
+                const MvTerm a = mv_load(mrec, tm);
+                acc0 = fma(a.val * mine[a.mono * MV_THREADS], x[a.col_off], acc0);
+                ++tm;
             }
-            y[(int64_t)i * DB_TILE] = acc0 + acc1;
+            ym[(int64_t)i * DB_TILE] = acc0 + acc1;
+        }
+        if (do_l) {
+            const int t1 = lptr[i + 1];
+            double acc0 = 0.0, acc1 = 0.0;
+            for (; tl + 2 <= t1; tl += 2) {
+                const MvTerm a = mv_load(lrec, tl), b = mv_load(lrec, tl + 1);
+                const double xa = x[a.col_off], xb = x[b.col_off];
+                acc0 = fma(a.val * mine[a.mono * MV_THREADS], xa, acc0);
+                acc1 = fma(b.val * mine[b.mono * MV_THREADS], xb, acc1);
+            }
+            if (tl < t1) {
+                const MvTerm a = mv_load(lrec, tl);
+                acc0 = fma(a.val * mine[a.mono * MV_THREADS], x[a.col_off], acc0);
+                ++tl;
+            }
+            yl[(int64_t)i * DB_TILE] = acc0 + acc1;
         }
     }
 }
@@ -728,7 +753,7 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
 extern "C" int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t x_slot, int32_t ym_slot, int32_t yl_slot, void* stream)
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
-    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(PB_THREADS), MV_MAX_MONO * PB_THREADS * sizeof(double), stream, batches, nbatch, x_slot, ym_slot, yl_slot);
+    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(MV_THREADS), MV_MAX_MONO * MV_THREADS * sizeof(double), stream, batches, nbatch, x_slot, ym_slot, yl_slot);
     return db_check_launch("batches_matvec");
 }
 

@@ -115,6 +115,91 @@ k_pointwise_v3(const double* __restrict__ in, double* __restrict__ out, int64_t 
     db_cp_wait<0>();
 }
 
+// Products of at most two fields (every quadratic right-hand side: u.grad(u), u.grad(b), ...): terms are 16-byte records
+// {coef, a, b} read with one warp-uniform load, so a term costs two shared loads and four flops instead of the general
+// interpreter's pointer chasing (ncu: the interpreter issued ~1000 warp instructions per pair of points and kept the
+// kernel at 4 TB/s on instruction issue).  Same double-buffered asynchronous staging as k_pointwise_v3.
+struct PwPair { double coef; int a; int b; };
+__device__ __forceinline__ PwPair pw_load(const db_pair_term* __restrict__ rec, int t)
+{
+#ifdef DB_EMU
+    PwPair r; r.coef = rec[t].coef; r.a = rec[t].a; r.b = rec[t].b; return r;
+#else
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(rec) + t);
+    PwPair r; r.coef = __hiloint2double(raw.y, raw.x); r.a = raw.z; r.b = raw.w; return r;
+#endif
+}
+
+__global__ void __launch_bounds__(PW3_T)
+k_pointwise_pairs(const double* __restrict__ in, double* __restrict__ out, int64_t npoints, int n_in, int n_out,
+                  const int32_t* __restrict__ term_ptr, const db_pair_term* __restrict__ rec)
+{
+    DB_SMEM(double, tile);                         // 2 buffers of [n_in][PW3_T] double2
+    double2* tile2 = reinterpret_cast<double2*>(tile);
+    const int64_t np2 = npoints >> 1;
+    const int64_t stride = (int64_t)gridDim.x * PW3_T;
+    int64_t q = (int64_t)blockIdx.x * PW3_T + threadIdx.x;
+    auto stage = [&](int64_t qq, int buf) {
+        if (qq < np2) {
+            double2* dst = tile2 + (size_t)buf * n_in * PW3_T + threadIdx.x;
+            const double* src = in + 2 * qq;
+            for (int i = 0; i < n_in; ++i) db_cp_async16(dst + i * PW3_T, src + (int64_t)i * npoints);
+        }
+    };
+    int buf = 0;
+    stage(q, 0);
+    db_cp_commit();
+    for (; q - threadIdx.x < np2; q += stride, buf ^= 1) {        // block-uniform trip count
+        stage(q + stride, buf ^ 1);
+        db_cp_commit();
+        db_cp_wait<1>();
+        if (q < np2) {
+            const double2* mine = tile2 + (size_t)buf * n_in * PW3_T + threadIdx.x;
+            int t = term_ptr[0];
+            for (int o = 0; o < n_out; ++o) {
+                const int t1 = term_ptr[o + 1];
+                double a0 = 0.0, a1 = 0.0;
+                for (; t < t1; ++t) {
+                    const PwPair r = pw_load(rec, t);
+                    const double2 va = mine[r.a * PW3_T];
+                    double p0 = r.coef * va.x, p1 = r.coef * va.y;
+                    if (r.b >= 0) {
+                        const double2 vb = mine[r.b * PW3_T];
+                        a0 = fma(p0, vb.x, a0); a1 = fma(p1, vb.y, a1);
+                    } else { a0 += p0; a1 += p1; }
+                }
+                reinterpret_cast<double2*>(out + (int64_t)o * npoints)[q] = make_double2(a0, a1);
+            }
+        }
+    }
+    db_cp_wait<0>();
+}
+
+extern "C" int db_pointwise_pairs(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
+                                  const int32_t* term_ptr, const db_pair_term* terms, void* stream)
+{
+    if (npoints <= 0 || n_out <= 0) return 0;
+    const size_t smem3 = (size_t)2 * n_in * PW3_T * sizeof(double2);
+    if ((npoints & 1) || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) || smem3 > (size_t)DB_MAX_SMEM) {
+        db_set_error("pointwise_pairs: needs an even point count, 16-byte aligned arrays and at most %d inputs", (int)(DB_MAX_SMEM / (2 * PW3_T * sizeof(double2))));
+        return 1;
+    }
+    int per_sm = (int)((size_t)(226 * 1024) / (smem3 + 1024));
+    if (per_sm > 8) per_sm = 8;
+    int64_t blocks = (npoints / 2 + PW3_T - 1) / PW3_T;
+    if (blocks > (int64_t)148 * per_sm) blocks = (int64_t)148 * per_sm;
+#ifndef DB_EMU
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_pointwise_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_pointwise_pairs, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr = true;
+    }
+#endif
+    DB_LAUNCH(k_pointwise_pairs, dim3((unsigned)blocks), dim3(PW3_T), smem3, stream, in, out, npoints, n_in, n_out, term_ptr, terms);
+    return db_check_launch("pointwise_pairs");
+}
+
 extern "C" int db_pointwise(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
                             const int32_t* term_ptr, const double* coef, const int32_t* fac_ptr, const int32_t* fac, int32_t nfac_total,
                             void* stream)

@@ -215,6 +215,15 @@ class RHSPlan:
         self.fac_ptr = torch.tensor(fac_ptr, dtype=torch.int32, device=dev)
         self.fac = torch.tensor(fac, dtype=torch.int32, device=dev)
         self.nfac = len(fac)
+        # quadratic programs (every term a product of one or two inputs) take the packed-record kernel
+        self.pairs = None
+        nf = np.diff(fac_ptr)
+        if len(coef) and nf.min() >= 1 and nf.max() <= 2 and self.npoints % 2 == 0 and 2 * self.n_in * 128 * 16 <= 227 * 1024:
+            rec = np.zeros(len(coef), dtype=np.dtype([('coef', '<f8'), ('a', '<i4'), ('b', '<i4')]))      # db_pair_term
+            rec['coef'] = coef
+            rec['a'] = [fac[fac_ptr[t]] for t in range(len(coef))]
+            rec['b'] = [fac[fac_ptr[t] + 1] if nf[t] == 2 else -1 for t in range(len(coef))]
+            self.pairs = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()).to(dev)
         # ---- backward prefix tree: level order = axes from last to first
         self.axes_order = list(range(dim - 1, -1, -1))
         self._build_tree()
@@ -321,8 +330,12 @@ class RHSPlan:
                     plan.backward(src, dst, ax, deriv=nd['deriv'])
         # ---- phase 2: pointwise products
         with Timed(self.solver.prof, "pointwise", 8 * self.npoints * (self.n_in + self.n_out)):
-          get_lib().call("db_pointwise", _dptr(self.grid_in), _dptr(self.grid_out), self.npoints, self.n_in, self.n_out,
-                       _dptr(self.term_ptr), _dptr(self.coef), _dptr(self.fac_ptr), _dptr(self.fac), self.nfac, _stream())
+          if self.pairs is not None and self.grid_in.data_ptr() % 16 == 0 and self.grid_out.data_ptr() % 16 == 0:
+              get_lib().call("db_pointwise_pairs", _dptr(self.grid_in), _dptr(self.grid_out), self.npoints, self.n_in, self.n_out,
+                             _dptr(self.term_ptr), _dptr(self.pairs), _stream())
+          else:
+              get_lib().call("db_pointwise", _dptr(self.grid_in), _dptr(self.grid_out), self.npoints, self.n_in, self.n_out,
+                             _dptr(self.term_ptr), _dptr(self.coef), _dptr(self.fac_ptr), _dptr(self.fac), self.nfac, _stream())
         # ---- phase 3: forward transforms (axes first -> last), all outputs stacked
         cur = self.grid_out
         for ax in range(dim):

@@ -33,7 +33,7 @@ class Batch(C.Structure):
                 ("prog", vp), ("mono", vp), ("vec", vp * DB_MAX_VECS), ("lu", vp * DB_MAX_LU),
                 ("m_ptr", vp), ("m_col", vp), ("m_mono", vp), ("m_val", vp),
                 ("l_ptr", vp), ("l_col", vp), ("l_mono", vp), ("l_val", vp),
-                ("m_rec", vp), ("l_rec", vp), ("ctrl", vp), ("n_mono", i32), ("pad_", i32),
+                ("m_rec", vp), ("l_rec", vp), ("ctrl", vp), ("n_mono", i32), ("mv_rows", i32),
                 ("line_base", vp * 2), ("line_kind", vp * 2), ("line_ptr", vp * 2), ("line_pos", vp * 2), ("sys_off", vp * 2),
                 ("diag_eid", vp), ("fl_ptr", vp), ("fl_eid", vp), ("fu_ptr", vp), ("fu_eid", vp), ("fd_eid", vp),
                 ("asm_ptr", vp), ("asm_mono", vp), ("asm_val", vp), ("info", vp)]
@@ -60,6 +60,7 @@ SIGNATURES = {
     "db_band_lines": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i32, i32, vp]),
     "db_mmt_apply": (C.c_int, [vp, i32, i32, vp, vp, i64, i64, vp]),
     "db_pointwise": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp]),
+    "db_pointwise_pairs": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp]),
     "db_pencil_gather": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
     "db_pencil_scatter": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
     "db_pencil_matvec": (C.c_int, [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -94,6 +94,12 @@ int db_mmt_apply(const double* mat, int32_t m, int32_t n, const double* in, doub
 int db_pointwise(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
                  const int32_t* term_ptr, const double* coef, const int32_t* fac_ptr, const int32_t* fac, int32_t nfac_total,
                  void* stream);
+/* The same for programs whose terms have one or two factors (quadratic nonlinearities): term t of output o
+ * (term_ptr[o] <= t < term_ptr[o+1]) is coef * in[a] * in[b], or coef * in[a] when b < 0.  npoints even, arrays
+ * 16-byte aligned. */
+typedef struct { double coef; int32_t a; int32_t b; } db_pair_term;
+int db_pointwise_pairs(const double* in, double* out, int64_t npoints, int32_t n_in, int32_t n_out,
+                       const int32_t* term_ptr, const db_pair_term* terms, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Pencil systems (S1-S4).  A batch holds S structurally identical systems of size n; one thread owns one system.
@@ -184,7 +190,8 @@ typedef struct {
     const db_term *m_rec, *l_rec;      /* the same term lists packed 16 bytes per term (fused mat-vec kernel) */
     const int32_t* ctrl;               /* [n_entries/16][36] per-chunk control blocks of the branch-free solve kernel:
                                           gather offsets[16], finished-row offsets[16], masks end / begin / late, 0  */
-    int32_t n_mono, pad_;
+    int32_t n_mono;
+    int32_t mv_rows;                   /* rows per CTA of the fused mat-vec (multiple of 64; n rounded up = one CTA per tile) */
     const int64_t* line_base[2]; const int32_t* line_kind[2]; const int32_t* line_ptr[2]; const int32_t* line_pos[2];
     const int64_t* sys_off[2];
     /* factorisation programs */
