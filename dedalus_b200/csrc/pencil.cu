@@ -199,34 +199,34 @@ extern "C" int db_pencil_factor(double* lu, int32_t n, int32_t S, int32_t n_entr
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_pencil_solve(const double* __restrict__ lu, int n, int S, int ld,
                                const int32_t* __restrict__ prog, int n_fwd, int n_entries,
-                               db_lincomb rhs, double* __restrict__ xg)
+                               db_lincomb rhs, double* xg)
 {
-    // plain sequential interpreter of the solve stream (reference implementation; the pipelined fused kernel below
-    // must agree with it)
+    // plain sequential interpreter of the solve stream (reference implementation; the fused branch-free kernel below
+    // must agree with it): x <- right-hand-side combination, then every row starts from x[row]
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     (void)ld;
     const double* __restrict__ f = lu + db_tbase(s, n_entries);
     const int64_t tb = db_tbase(s, n);
-    double* __restrict__ x = xg + tb;
+    double* x = xg + tb;
+    for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][tb + (int64_t)i * DB_TILE], acc);
+        x[(int64_t)i * DB_TILE] = acc;
+    }
     for (int sec = 0; sec < 2; ++sec) {
         const int e0 = sec ? n_fwd : 0, e1 = sec ? n_entries : n_fwd;
         int cur = -1;
-        double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+        double acc = 0.0;
         for (int e = e0; e < e1; ++e) {
             const int c = prog[e];
             if (c == DB_I_SKIP) continue;
             if (c < 0) {
-                if (cur >= 0) {
-                    const double val = sec ? acc * f[(int64_t)e * DB_TILE] : acc;
-                    x[cur] = val; l3 = l2; l2 = l1; l1 = val;
-                }
+                if (cur >= 0) x[cur] = sec ? acc * f[(int64_t)e * DB_TILE] : acc;
                 cur = -1 - c;
-                if (sec) acc = x[cur];
-                else { acc = 0.0; for (int j = 0; j < rhs.nvec; ++j) acc = fma(rhs.coef[j], rhs.vec[j][tb + cur], acc); }
+                acc = x[cur];
             } else {
-                const double xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK];
-                acc = fma(-f[(int64_t)e * DB_TILE], xx, acc);
+                acc = fma(-f[(int64_t)e * DB_TILE], x[c], acc);
             }
         }
     }
@@ -278,8 +278,6 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 }
 
 #define SOLVE_THREADS 64
-template <int CH> struct SolveChunk { double v[CH]; int c[CH]; };
-
 // Right-hand side first: x <- sum_q cf[q] * rv[q] for every row, as one fully parallel streaming pass (many
 // independent loads in flight per thread).  The forward sweep then starts each row from x[row] like the backward sweep
 // does; folding the combination into the row starts instead puts NV dependent DRAM loads on the recurrence's critical
@@ -303,95 +301,14 @@ template <int CH> struct SolveChunk { double v[CH]; int c[CH]; };
         }                                                                                           \
     }
 
-// Triangular solves with the right-hand-side combination fused into the row starts.
-// NV = number of right-hand-side vectors (compile time: pointers and coefficients stay in registers).
-// Two-stage register pipeline over chunks of SOLVE_CH entries: the factor values + instructions of chunk q+1 are in
-// flight while chunk q is consumed; the x values / row-start values of chunk q are gathered in one burst right before
-// it is consumed (the host marks entries whose column completes inside the preload window, DB_I_FRESH_*).  Each CTA
-// streams one contiguous slab of the tile-major factor array.
-template <int NV, int SOLVE_CH>
-__global__ void __launch_bounds__(SOLVE_THREADS)
-k_batches_solve(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs)
-{
-    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
-    const db_batch& B = batches[bi];
-    const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
-    if (s >= B.S) return;
-    const int64_t tb = db_tbase(s, B.n);
-    const double* __restrict__ fp = B.lu[lu_slot] + db_tbase(s, B.n_entries);
-    const int32_t* __restrict__ pp = B.prog;
-    double* __restrict__ x = B.vec[x_slot] + tb;
-    const double* rv[NV];
-    double cf[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
-    SOLVE_PROLOGUE(NV, B.n)
-#define SOLVE_LOADA(K)                                                                              \
-    _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) { K.v[j] = DB_LDCS(fp + j * DB_TILE); K.c[j] = pp[j]; } \
-    fp += SOLVE_CH * DB_TILE; pp += SOLVE_CH;
-#define SOLVE_COMPUTE(K, FWD)                                                                       \
-    {                                                                                               \
-        double xv[SOLVE_CH];                                                                        \
-        _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) {                                      \
-            const int c = K.c[j];                                                                   \
-            double val = 0.0;                                                                       \
-            if (c >= 0) { if (c < DB_I_FRESH_MEM) val = x[c]; }                                     \
-            else if (c != DB_I_SKIP) {                                                              \
-                const int o = -1 - c;                                                               \
-                val = x[o];                                                                        \
-            }                                                                                       \
-            xv[j] = val;                                                                            \
-        }                                                                                           \
-        _Pragma("unroll") for (int j = 0; j < SOLVE_CH; ++j) {                                      \
-            const int c = K.c[j];                                                                   \
-            if (c >= 0) {                                                                           \
-                double xx = xv[j];                                                                  \
-                if (c >= DB_I_FRESH_MEM)                                                            \
-                    xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK]; \
-                acc = fma(-K.v[j], xx, acc);                                                        \
-            } else if (c != DB_I_SKIP) {                                                            \
-                if (cur >= 0) {                                                                     \
-                    const double val = (FWD) ? acc : acc * K.v[j];                                  \
-                    x[cur] = val; l3 = l2; l2 = l1; l1 = val;                                       \
-                }                                                                                   \
-                cur = -1 - c;                                                                       \
-                acc = xv[j];                                                                        \
-            }                                                                                       \
-        }                                                                                           \
-    }
-#define SOLVE_SECTION(NCH, FWD)                                                                     \
-    {                                                                                               \
-        const int nch = (NCH);                                                                      \
-        int cur = -1;                                                                               \
-        double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;                                             \
-        SolveChunk<SOLVE_CH> K0, K1;                                                                \
-        SOLVE_LOADA(K0)                                                                             \
-        for (int ch = 0; ch < nch; ch += 2) {                                                       \
-            if (ch + 1 < nch) { SOLVE_LOADA(K1) }                                                   \
-            SOLVE_COMPUTE(K0, FWD)                                                                  \
-            if (ch + 1 >= nch) break;                                                               \
-            if (ch + 2 < nch) { SOLVE_LOADA(K0) }                                                   \
-            SOLVE_COMPUTE(K1, FWD)                                                                  \
-        }                                                                                           \
-    }
-    SOLVE_SECTION(B.n_fwd / SOLVE_CH, true)
-    SOLVE_SECTION((B.n_entries - B.n_fwd) / SOLVE_CH, false)
-#undef SOLVE_SECTION
-#undef SOLVE_COMPUTE
-#undef SOLVE_LOADA
-}
-
-
 // ---------------------------------------------------------------------------------------------------------
-// Triangular solves, bulk-copy ring variant.  The tile-major factor array makes everything one CTA (64 systems) reads
-// a single contiguous stream of n_entries * 512 bytes, so one elected thread feeds it through a ring of shared-memory
-// stages with 1-D bulk async copies (cp.async.bulk -> UBLKCP) completing on mbarriers; the instruction words of each
-// chunk ride in the same stage.  The copy engine keeps `nstages` chunks in flight per CTA no matter how few warps are
-// resident, which is what a latency-bound, one-thread-per-system recurrence needs when there are only a few tiles
-// per SM (multi-GPU strong scaling); registers hold only the 16 gathered x values of the chunk being consumed.
+// Bulk-copy ring.  The tile-major factor array makes everything one CTA (64 systems) reads a single contiguous stream
+// of n_entries * 512 bytes, so one elected thread feeds it through a ring of shared-memory stages with 1-D bulk async
+// copies (cp.async.bulk -> UBLKCP) completing on mbarriers; the control block of each chunk rides in the same stage.
+// The copy engine keeps `nstages` chunks in flight per CTA no matter how few warps are resident, which is what a
+// one-thread-per-system recurrence needs when there are only a few tiles per SM (multi-GPU strong scaling).
 // ---------------------------------------------------------------------------------------------------------
 #define SOLVE_CE 16
-#define SOLVE_STAGE_BYTES (SOLVE_CE * DB_TILE * 8 + SOLVE_CE * 4)
 #ifdef DB_EMU
 typedef unsigned long long db_mbar_t;
 __device__ __forceinline__ void db_mbar_init(db_mbar_t*, int) {}
@@ -424,84 +341,6 @@ __device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
                  "}" ::"r"(db_smem_u32(bar)), "r"(parity) : "memory");
 }
 #endif
-
-template <int NV>
-__global__ void __launch_bounds__(SOLVE_THREADS)
-k_batches_solve_ring(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
-{
-    DB_SMEM(unsigned char, ring);
-    db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_STAGE_BYTES);
-    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
-    const db_batch& B = batches[bi];
-    const int tile = blockIdx.x - B.blk_solve;
-    const int s = tile * SOLVE_THREADS + threadIdx.x;          // padded lanes (s >= S) run on the zero padding
-    const int64_t tb = db_tbase(s, B.n);
-    const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
-    const int32_t* __restrict__ prog = B.prog;
-    const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
-    double* __restrict__ x = B.vec[x_slot] + tb;
-    const double* rv[NV];
-    double cf[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
-    auto issue = [&](int q, int slot) {
-        unsigned char* st = ring + (size_t)slot * SOLVE_STAGE_BYTES;
-        db_mbar_expect_tx(&bars[slot], SOLVE_STAGE_BYTES);
-        db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &bars[slot]);
-        db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, prog + (int64_t)q * SOLVE_CE, SOLVE_CE * 4, &bars[slot]);
-    };
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < nstages; ++i) db_mbar_init(&bars[i], 1);
-        db_mbar_fence_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-        for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
-    SOLVE_PROLOGUE(NV, B.n)
-    int slot = 0;
-    unsigned phase = 0;
-    int cur = -1;
-    double acc = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
-    for (int q = 0; q < nchunks; ++q) {
-        const bool fwd = q < nfwd;
-        if (q == nfwd) { cur = -1; acc = 0.0; l1 = l2 = l3 = 0.0; }
-        db_mbar_wait(&bars[slot], phase);
-        const unsigned char* st = ring + (size_t)slot * SOLVE_STAGE_BYTES;
-        const double* __restrict__ vals = reinterpret_cast<const double*>(st) + threadIdx.x;
-        const int* __restrict__ codes = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
-        double xv[SOLVE_CE];
-#pragma unroll
-        for (int j = 0; j < SOLVE_CE; ++j) {
-            const int c = codes[j];
-            double val = 0.0;
-            if (c >= 0) { if (c < DB_I_FRESH_MEM) val = x[c]; }
-            else if (c != DB_I_SKIP) {
-                val = x[-1 - c];
-            }
-            xv[j] = val;
-        }
-#pragma unroll
-        for (int j = 0; j < SOLVE_CE; ++j) {
-            const int c = codes[j];
-            if (c >= 0) {
-                double xx = xv[j];
-                if (c >= DB_I_FRESH_MEM)
-                    xx = (c & DB_I_FRESH_REG) ? (((c & 3) == 1) ? l1 : ((c & 3) == 2) ? l2 : l3) : x[c & DB_I_OFFMASK];
-                acc = fma(-vals[j * DB_TILE], xx, acc);
-            } else if (c != DB_I_SKIP) {
-                if (cur >= 0) {
-                    const double val = fwd ? acc : acc * vals[j * DB_TILE];
-                    x[cur] = val; l3 = l2; l2 = l1; l1 = val;
-                }
-                cur = -1 - c;
-                acc = xv[j];
-            }
-        }
-        __syncthreads();                                   // both warps are done with this stage
-        if (threadIdx.x == 0 && q + nstages < nchunks) issue(q + nstages, slot);
-        if (++slot == nstages) { slot = 0; phase ^= 1; }
-    }
-}
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -617,54 +456,21 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
     const dim3 g(total_blocks), b(SOLVE_THREADS);
     const int nv = rhs->nvec;
-    // DB_SOLVE_IMPL=regs selects the register-pipelined kernel; default is the bulk-copy ring.  Ring depth: enough
-    // stages that (CTAs per SM) x (stages) x 8 KB covers the HBM latency-bandwidth product (~40 KB per SM) several
-    // times over, without taking more shared memory than leaves the L1 useful for the x re-reads.
-    static int impl = -1, st_env = 0;
-    if (impl < 0) {
-        const char* e = getenv("DB_SOLVE_IMPL");
-        impl = (e && strcmp(e, "regs") == 0) ? 0 : (e && strcmp(e, "ring") == 0) ? 1 : 2;
-        const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
-    }
-    if (impl == 2) {
-        // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
-        // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
-        // per step); with few CTAs per SM the ring is the only source of memory parallelism, so it gets deep
-        const int per_sm = (total_blocks + 147) / 148;
-        int nst = per_sm >= 5 ? 2 : per_sm >= 3 ? 4 : per_sm >= 2 ? 8 : 16;
-        if (st_env >= 2 && st_env <= 24) nst = st_env;
-        const size_t smem = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
+    static int st_env = -1;
+    if (st_env < 0) { const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0; }
+    // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
+    // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
+    // per step); with few CTAs per SM the ring is the only source of memory parallelism, so it gets deep
+    const int per_sm = (total_blocks + 147) / 148;
+    int nst = per_sm >= 5 ? 2 : per_sm >= 3 ? 4 : per_sm >= 2 ? 8 : 16;
+    if (st_env >= 2 && st_env <= 24) nst = st_env;
+    const size_t smem = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
 #define FLAT_GO(NV_) { static int attr_st = 0; \
-        if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_>)); attr_st = 1; } \
-        DB_LAUNCH((k_batches_solve_flat<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
-        if (nv <= 1) FLAT_GO(1) else if (nv == 2) FLAT_GO(2) else if (nv == 3) FLAT_GO(3) else if (nv == 4) FLAT_GO(4)
-        else if (nv == 5) FLAT_GO(5) else if (nv == 6) FLAT_GO(6) else if (nv <= 8) FLAT_GO(8) else if (nv <= 12) FLAT_GO(12) else FLAT_GO(16)
+    if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_>)); attr_st = 1; } \
+    DB_LAUNCH((k_batches_solve_flat<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
+    if (nv <= 1) FLAT_GO(1) else if (nv == 2) FLAT_GO(2) else if (nv == 3) FLAT_GO(3) else if (nv == 4) FLAT_GO(4)
+    else if (nv == 5) FLAT_GO(5) else if (nv == 6) FLAT_GO(6) else if (nv <= 8) FLAT_GO(8) else if (nv <= 12) FLAT_GO(12) else FLAT_GO(16)
 #undef FLAT_GO
-        return db_check_launch("batches_solve");
-    }
-    if (impl == 1) {
-        const int per_sm = (total_blocks + 147) / 148;
-        int nst = per_sm >= 7 ? 3 : per_sm >= 4 ? 4 : per_sm >= 2 ? 8 : 16;
-        if (st_env >= 2 && st_env <= 24) nst = st_env;
-        const size_t smem = (size_t)nst * SOLVE_STAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
-#define RING_GO(NV_) { static int attr_st = 0; \
-        if (attr_st < nst) { DB_SET_SMEM_ATTR((k_batches_solve_ring<NV_>)); attr_st = 1 << 30; } \
-        DB_LAUNCH((k_batches_solve_ring<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
-        if (nv <= 1) RING_GO(1) else if (nv == 2) RING_GO(2) else if (nv == 3) RING_GO(3) else if (nv == 4) RING_GO(4)
-        else if (nv == 5) RING_GO(5) else if (nv == 6) RING_GO(6) else if (nv <= 8) RING_GO(8) else if (nv <= 12) RING_GO(12) else RING_GO(16)
-#undef RING_GO
-        return db_check_launch("batches_solve");
-    }
-    // chunk size: 8 keeps 7 CTAs / SM resident when there are many tiles; with few tiles per SM (multi-GPU strong
-    // scaling) occupancy is not the limit and the 16-entry chunk doubles each warp's loads in flight
-    static int ch_env = -1;
-    if (ch_env < 0) { const char* e = getenv("DB_SOLVE_CH"); ch_env = e ? atoi(e) : 0; }
-    const int ch = (ch_env == 8 || ch_env == 16) ? ch_env : (total_blocks < 148 * 3 ? 16 : 8);
-#define SOLVE_GO(NV_) { if (ch == 16) DB_LAUNCH((k_batches_solve<NV_, 16>), g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs); \
-                        else DB_LAUNCH((k_batches_solve<NV_, 8>), g, b, 0, stream, batches, nbatch, lu_slot, x_slot, *rhs); }
-    if (nv <= 1) SOLVE_GO(1) else if (nv == 2) SOLVE_GO(2) else if (nv == 3) SOLVE_GO(3) else if (nv == 4) SOLVE_GO(4)
-    else if (nv == 5) SOLVE_GO(5) else if (nv == 6) SOLVE_GO(6) else if (nv <= 8) SOLVE_GO(8) else if (nv <= 12) SOLVE_GO(12) else SOLVE_GO(16)
-#undef SOLVE_GO
     return db_check_launch("batches_solve");
 }
 
@@ -684,18 +490,17 @@ __device__ __forceinline__ MvTerm mv_load(const db_term* __restrict__ rec, int t
 __global__ void __launch_bounds__(MV_THREADS)
 k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, int ym_slot, int yl_slot)
 {
-    // y = (sum_m mono_m T_m) x for the M and L templates: one thread per system, one CTA = one 64-system tile x
-    // B.mv_rows consecutive rows.  Rows are walked in order, so the x rows a CTA touches form a window sliding down the
-    // (mode-major) band: with a handful of CTAs per SM those windows stay L1-resident, whereas 64-row blocks scattered
-    // over the matrix missed L1 three times out of four (ncu: 8.4 GB of L2 traffic for 2 GB of algorithmic bytes).
-    // Terms are 16-byte records read with one warp-uniform load each; the system's monomial values (powers of its
-    // wavenumbers) sit in shared memory, one private column per thread.
-    DB_SMEM(double, monos);                       // [MV_MAX_MONO][MV_THREADS]
+    // y = (sum_m mono_m T_m) x for the M and L templates.  One thread owns TWO adjacent systems (adjacent in memory in
+    // the tile-major vectors: one 16-byte load / store serves both), one CTA = 128 systems x B.mv_rows consecutive rows.
+    // Terms are 16-byte records read with one warp-uniform load each; the systems' monomial values (powers of their
+    // wavenumbers) sit in shared memory, one private column per thread.  Per term and pair of systems: one record load,
+    // one x load, one shared load, four flops.
+    DB_SMEM(double2, monos);                      // [MV_MAX_MONO][MV_THREADS]
     const int bi = find_batch(batches, nbatch, blockIdx.x, 1);
     const db_batch& B = batches[bi];
     const int local = blockIdx.x - B.blk_matvec;
-    const int sblocks = (B.S + MV_THREADS - 1) / MV_THREADS;
-    const int s = (local % sblocks) * MV_THREADS + threadIdx.x;
+    const int sblocks = (B.S + 2 * MV_THREADS - 1) / (2 * MV_THREADS);
+    const int s = (local % sblocks) * (2 * MV_THREADS) + 2 * threadIdx.x;        // even system of the pair
     if (s >= B.S) return;
     const int r0 = (local / sblocks) * B.mv_rows;
     const int n = B.n, ld = B.ld;
@@ -703,49 +508,33 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
     const int64_t tb = db_tbase(s, n);
     const double* __restrict__ x = B.vec[x_slot] + tb;
     const int nm = B.n_mono < MV_MAX_MONO ? B.n_mono : MV_MAX_MONO;
-    double* mine = monos + threadIdx.x;
-    for (int m = 0; m < nm; ++m) mine[m * MV_THREADS] = B.mono[(int64_t)m * ld + s];
-    const bool do_m = ym_slot >= 0, do_l = yl_slot >= 0;
-    const int32_t* __restrict__ mptr = B.m_ptr;
-    const int32_t* __restrict__ lptr = B.l_ptr;
-    const db_term* __restrict__ mrec = B.m_rec;
-    const db_term* __restrict__ lrec = B.l_rec;
-    double* __restrict__ ym = do_m ? B.vec[ym_slot] + tb : nullptr;
-    double* __restrict__ yl = do_l ? B.vec[yl_slot] + tb : nullptr;
-    int tm = do_m ? mptr[r0] : 0, tl = do_l ? lptr[r0] : 0;
-    // M and L rows are interleaved (same row of both operators back to back) so both sweep the same x window
-    for (int i = r0; i < r1; ++i) {
-        if (do_m) {
-            const int t1 = mptr[i + 1];
-            double acc0 = 0.0, acc1 = 0.0;
-            for (; tm + 2 <= t1; tm += 2) {
-                const MvTerm a = mv_load(mrec, tm), b = mv_load(mrec, tm + 1);
-                const double xa = x[a.col_off], xb = x[b.col_off];
-                acc0 = fma(a.val * mine[a.mono * MV_THREADS], xa, acc0);
-                acc1 = fma(b.val * mine[b.mono * MV_THREADS], xb, acc1);
+    double2* mine = monos + threadIdx.x;
+    for (int m = 0; m < nm; ++m) mine[m * MV_THREADS] = *reinterpret_cast<const double2*>(B.mono + (int64_t)m * ld + s);
+    for (int which = 0; which < 2; ++which) {
+        const int slot = which ? yl_slot : ym_slot;
+        if (slot < 0) continue;
+        const int32_t* __restrict__ ptr = which ? B.l_ptr : B.m_ptr;
+        const db_term* __restrict__ rec = which ? B.l_rec : B.m_rec;
+        double* __restrict__ y = B.vec[slot] + tb;
+        int t = ptr[r0];
+        for (int i = r0; i < r1; ++i) {
+            const int t1 = ptr[i + 1];
+            double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+            for (; t + 2 <= t1; t += 2) {
+                const MvTerm a = mv_load(rec, t), b = mv_load(rec, t + 1);
+                const double2 xa = *reinterpret_cast<const double2*>(x + a.col_off), xb = *reinterpret_cast<const double2*>(x + b.col_off);
+                const double2 ma = mine[a.mono * MV_THREADS], mb = mine[b.mono * MV_THREADS];
+                acc0.x = fma(a.val * ma.x, xa.x, acc0.x); acc0.y = fma(a.val * ma.y, xa.y, acc0.y);
+                acc1.x = fma(b.val * mb.x, xb.x, acc1.x); acc1.y = fma(b.val * mb.y, xb.y, acc1.y);
             }
-            if (tm < t1) {
-                const MvTerm a = mv_load(mrec, tm);
-                acc0 = fma(a.val * mine[a.mono * MV_THREADS], x[a.col_off], acc0);
-                ++tm;
+            if (t < t1) {
+                const MvTerm a = mv_load(rec, t);
+                const double2 xa = *reinterpret_cast<const double2*>(x + a.col_off);
+                const double2 ma = mine[a.mono * MV_THREADS];
+                acc0.x = fma(a.val * ma.x, xa.x, acc0.x); acc0.y = fma(a.val * ma.y, xa.y, acc0.y);
+                ++t;
             }
-            ym[(int64_t)i * DB_TILE] = acc0 + acc1;
-        }
-        if (do_l) {
-            const int t1 = lptr[i + 1];
-            double acc0 = 0.0, acc1 = 0.0;
-            for (; tl + 2 <= t1; tl += 2) {
-                const MvTerm a = mv_load(lrec, tl), b = mv_load(lrec, tl + 1);
-                const double xa = x[a.col_off], xb = x[b.col_off];
-                acc0 = fma(a.val * mine[a.mono * MV_THREADS], xa, acc0);
-                acc1 = fma(b.val * mine[b.mono * MV_THREADS], xb, acc1);
-            }
-            if (tl < t1) {
-                const MvTerm a = mv_load(lrec, tl);
-                acc0 = fma(a.val * mine[a.mono * MV_THREADS], x[a.col_off], acc0);
-                ++tl;
-            }
-            yl[(int64_t)i * DB_TILE] = acc0 + acc1;
+            *reinterpret_cast<double2*>(y + (int64_t)i * DB_TILE) = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
         }
     }
 }
@@ -753,7 +542,7 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
 extern "C" int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t x_slot, int32_t ym_slot, int32_t yl_slot, void* stream)
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
-    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(MV_THREADS), MV_MAX_MONO * MV_THREADS * sizeof(double), stream, batches, nbatch, x_slot, ym_slot, yl_slot);
+    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(MV_THREADS), MV_MAX_MONO * MV_THREADS * sizeof(double2), stream, batches, nbatch, x_slot, ym_slot, yl_slot);
     return db_check_launch("batches_matvec");
 }
 

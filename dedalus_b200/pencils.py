@@ -448,46 +448,48 @@ def _permuted_templates(batch, name):
 SOLVE_CTRL_WORDS = 36
 
 
-def solve_control_blocks(plain, code, n_fwd, CH=16):
+def solve_control_blocks(code, n_fwd, tile=64, CH=16):
     """Per-chunk control blocks of the branch-free solve kernel (csrc/pencil.cu k_batches_solve_flat), derived from the
     flat instruction stream: for each chunk of 16 entries
         goff[16]  element offset gathered before the chunk is consumed: the column of a multiply-accumulate entry, the
-                  NEXT row (its start value) of a row-boundary entry, 0 for padding (whose factor value is 0)
-        foff[16]  element offset of the row FINISHED at a row-boundary entry
-        maskE     entries that finish a row (store), maskB entries that start a row (take the gathered start value),
-        maskF     entries whose column was finished inside this chunk (re-read after the store instead of the gather)
+                  row ENTERED (its start value) at a row-boundary entry, 0 for padding (whose factor value is 0)
+        foff[16]  element offset of the row LEFT at a row-boundary entry
+        maskE     entries that leave a row (store), maskB entries that enter a row (take the gathered start value),
+        maskF     entries whose gathered value was stored inside this very chunk (re-read right before use)
     Layout: int32 [nchunks][36] = goff, foff, maskE, maskB, maskF, 0."""
-    SKIP, FRESH = -2**31, (1 << 30) | (1 << 29)
-    MASK = (1 << 29) - 1
-    code = np.asarray(code, dtype=np.int64)           # stream with the hazard marks (DB_I_FRESH_*)
-    plain = np.asarray(plain, dtype=np.int64)         # same stream before marking: plain column offsets
+    SKIP = -2**31
+    code = np.asarray(code, dtype=np.int64)
     nE = len(code)
-    assert nE % CH == 0 and n_fwd % CH == 0 and len(plain) == nE
+    assert nE % CH == 0 and n_fwd % CH == 0
     out = np.zeros((nE // CH, SOLVE_CTRL_WORDS), dtype=np.int64)
     cur = -1
+    stored_at = {}                         # element offset -> position of its most recent store
     for e in range(nE):
         if e == n_fwd:
             cur = -1
         q, j = divmod(e, CH)
-        c = int(plain[e])
+        c = int(code[e])
         if c == SKIP:
             continue
         if c < 0:
             nxt = -1 - c
             out[q, j] = nxt
             out[q, 33] |= 1 << j
+            if stored_at.get(nxt, -1) >= q * CH:
+                out[q, 34] |= 1 << j
             if cur >= 0:
                 out[q, 16 + j] = cur
                 out[q, 32] |= 1 << j
+                stored_at[cur] = e
             cur = nxt
         else:
             out[q, j] = c
-            if int(code[e]) & FRESH:
+            if stored_at.get(c, -1) >= q * CH:
                 out[q, 34] |= 1 << j
     return out.astype(np.int32)
 
 
-def compile_batch(batch, a0, b0):
+def compile_batch(batch, a0, b0, dense=None):
     """Build ordering (if needed), symbolic LU and all programs for the LHS  a0*M + b0*L."""
     if batch.cols is None:
         batch.compute_ordering(a0, b0)
@@ -499,18 +501,16 @@ def compile_batch(batch, a0, b0):
     # ---- solve stream (include/dedalus_b200.h).  Rows of each triangular solve are processed in LEVEL order of its
     #      dependency DAG (rows of one level are mutually independent), which keeps a row's inputs several rows behind it
     #      in the stream and lets the kernels preload x values two chunks ahead.  Codes:
-    #        c >= 0          : acc -= LU[e] * x_col ; plain: c = column*ld ; DB_I_FRESH_REG | k : k-th most recently
-    #                          completed row (registers) ; DB_I_FRESH_MEM | column*ld : re-read memory at compute time
-    #        c <  0, != SKIP : end of the current row (store; backward: multiply by LU[e] = reciprocal pivot) and start of
-    #                          row (-1 - c)/ld ; the first entry of a section only starts a row
+    #        c >= 0          : acc -= LU[e] * x[c] ; c = column * TILE
+    #        c <  0, != SKIP : leave the current row (store; backward: multiply by LU[e] = reciprocal pivot) and enter
+    #                          row (-1 - c) / TILE with acc = x[row] ; the first entry of a section only enters a row
     #        DB_I_SKIP       : padding to a multiple of the chunk size
-    SKIP, CH = -2**31, 16           # sections padded / hazards marked for 16-entry chunks (kernels use 8 or 16)
-    FRESH_REG, FRESH_MEM = 1 << 30, 1 << 29
+    SKIP, CH = -2**31, 16           # sections padded to the kernel's 16-entry chunks
     TILE = 64                        # DB_TILE: vectors / factors are stored tile-major, 64 systems per slab
     ld = ((batch.S + TILE - 1) // TILE) * TILE
     prog.ld, prog.tile = ld, TILE
-    if (n + 1) * TILE >= FRESH_MEM:
-        raise NotImplementedError("system too large for 29-bit vector offsets")
+    if (n + 1) * TILE >= 2**30:
+        raise NotImplementedError("system too large for 30-bit vector offsets")
     lev_f = np.zeros(n, dtype=np.int64)
     for i in range(n):
         js = np.nonzero(F[i, :i])[0]
@@ -531,48 +531,78 @@ def compile_batch(batch, a0, b0):
     code = []
     e = 0
 
+    import os
+    DENSE = int(dense if dense is not None else os.environ.get("DB_SOLVE_DENSE", 64))
+    SEG = 15                          # forward rows with >= DENSE entries are visited in segments of SEG entries
+
+    def visits_of(order, forward):
+        """Sequence of (row, columns) visits.  Normally one visit per row.  A run of consecutive DENSE forward rows (the
+        boundary rows, eliminated last: each sweeps the whole x vector) is interleaved segment by segment: every row
+        takes the next SEG of the columns finished before the run, so the 15 x rows of a segment are re-used by all rows
+        of the run while they are still cache-resident (one DRAM sweep of x for the run instead of one per row).  A row
+        that is left and re-entered keeps its partial sum in x[row]: leaving a row always stores the accumulator and
+        entering one loads x[row] (the forward sweep has no pivot scaling, so partial sums are exact)."""
+        cols_of = (lambda i: np.nonzero(F[i, :i])[0]) if forward else (lambda i: i + 1 + np.nonzero(F[i, i + 1:])[0])
+        out, idx = [], 0
+        while idx < len(order):
+            i = int(order[idx])
+            js = cols_of(i)
+            if not forward or js.size < DENSE:
+                out.append((i, js)); idx += 1
+                continue
+            run = [i]
+            while idx + len(run) < len(order) and cols_of(int(order[idx + len(run)])).size >= DENSE:
+                run.append(int(order[idx + len(run)]))
+            if len(run) < 2:
+                out.append((i, js)); idx += 1
+                continue
+            done_before = np.zeros(n, dtype=bool); done_before[np.asarray(order[:idx], dtype=np.int64)] = True
+            early = {r: cols_of(r)[done_before[cols_of(r)]] for r in run}
+            late = {r: cols_of(r)[~done_before[cols_of(r)]] for r in run}
+            nseg = max(-(-early[r].size // SEG) for r in run)
+            for k in range(nseg):
+                for r in run:
+                    seg = early[r][k * SEG:(k + 1) * SEG]
+                    if seg.size:
+                        out.append((r, seg))
+            for r in run:                       # in-run dependencies, in order: each row completes before the next needs it
+                out.append((r, late[r]))
+            idx += len(run)
+        merged = []                               # consecutive visits of one row are one visit
+        for i, js in out:
+            if merged and merged[-1][0] == i:
+                merged[-1] = (i, np.concatenate([merged[-1][1], js]))
+            else:
+                merged.append((i, js))
+        return merged
+
     def emit_section(order, forward):
         nonlocal e
-        sec = [-1 - int(order[0]) * TILE]               # start of the first row (its LU slot is unused)
+        visits = visits_of(order, forward)
+        sec = [-1 - int(visits[0][0]) * TILE]           # start of the first row (its LU slot is unused)
         e += 1
-        for idx, i in enumerate(order):
-            js = np.nonzero(F[i, :i])[0] if forward else i + 1 + np.nonzero(F[i, i + 1:])[0]
+        last_visit = {}
+        for v, (i, js) in enumerate(visits):
+            last_visit[i] = v
+        for v, (i, js) in enumerate(visits):
             eid[i, js] = e + np.arange(js.size)
             sec.extend((js.astype(np.int64) * TILE).tolist())
             e += js.size
             if not forward:
                 diag_eid[i] = e; eid[i, i] = e
-            nxt = order[idx + 1] if idx + 1 < len(order) else i
+            nxt = visits[v + 1][0] if v + 1 < len(visits) else i
             sec.append(-1 - int(nxt) * TILE)
             e += 1
         pad = (-len(sec)) % CH
         sec.extend([SKIP] * pad); e += pad
-        # hazard marking: the x values of a chunk are gathered in one burst right before the chunk is consumed
         sec = np.array(sec, dtype=np.int64)
-        plain_secs.append(sec.copy())
-        done_at, completed, cur = {}, [], None
-        for pos in range(len(sec)):
-            c = sec[pos]
-            if c == SKIP:
-                continue
-            if c < 0:
-                if cur is not None:
-                    done_at[cur] = pos; completed.append(cur)
-                cur = int((-1 - c) // TILE)
-            else:
-                col = int(c // TILE)
-                p_end = done_at.get(col)
-                if p_end is not None and p_end >= (pos // CH) * CH:
-                    k = len(completed) - completed.index(col)
-                    sec[pos] = (FRESH_REG | k) if k <= 3 else (FRESH_MEM | int(c))
         return sec
-    plain_secs = []
     sec_f = emit_section(order_f, True)
     prog.n_fwd = len(sec_f)
     sec_b = emit_section(order_b, False)
     prog.nE = e
     prog.prog = np.concatenate([sec_f, sec_b]).astype(np.int32)
-    prog.ctrl = solve_control_blocks(np.concatenate(plain_secs), prog.prog, prog.n_fwd)
+    prog.ctrl = solve_control_blocks(prog.prog, prog.n_fwd, TILE)
     assert len(prog.prog) == prog.nE
     prog.diag_eid = diag_eid
     # ---- factor program

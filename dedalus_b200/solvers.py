@@ -7,6 +7,7 @@ Here one step is a fixed sequence of kernel launches per *batch* of structurally
 -> fused RHS-combination + triangular solves -> scatter.  Factorisations are rebuilt only when the LHS
 coefficients (a0, b0) change, exactly as the reference drops its LHS_solvers (timesteppers.py:135-140, 577-583).
 """
+import os
 import time
 import ctypes as C
 from collections import deque
@@ -101,20 +102,15 @@ class BatchSet:
         self.nb = len(self.items)
         arr = (CBatch * max(self.nb, 1))()
         blk = dict(solve=0, matvec=0, move0=0, move1=0, asm=0)
-        tiles_total = sum((db.S + 63) // 64 for db in self.items)
         for i, db in enumerate(self.items):
             c = arr[i]
             c.n, c.S, c.ld, c.n_entries = db.n, db.S, db.ld, db.prog.nE
             c.n_fwd, c.n_bwd = db.prog.n_fwd, db.prog.nE - db.prog.n_fwd
             c.blk_solve = blk['solve']; blk['solve'] += (db.S + 63) // 64
-            # mat-vec CTAs: one 64-system tile x mv_rows consecutive rows; long row runs keep the x window in L1, but
-            # there must still be a few CTAs per SM in total (multi-GPU strong scaling: few tiles per rank)
-            tiles = (db.S + 63) // 64
-            want_chunks = max(1, -(-8 * 148 // max(tiles_total, 1)))
-            mv_rows = max(64, -(-db.n // want_chunks))
-            mv_rows = -(-mv_rows // 64) * 64
+            # mat-vec CTAs: 128 systems (two per thread) x mv_rows consecutive rows (csrc/pencil.cu k_batches_matvec)
+            mv_rows = int(os.environ.get("DB_MV_ROWS", 64))
             c.mv_rows = mv_rows
-            c.blk_matvec = blk['matvec']; blk['matvec'] += tiles * (-(-db.n // mv_rows))
+            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 127) // 128) * (-(-db.n // mv_rows))
             c.blk_assemble = blk['asm']; blk['asm'] += ((db.S + 127) // 128) * ((db.prog.nE + 63) // 64)
             for side in (0, 1):
                 m = db.maps[side]

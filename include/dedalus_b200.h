@@ -157,23 +157,19 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
  * batches (kx = 0 or ky = 0 pencils) run concurrently with the large ones instead of serialising on the stream.
  * `batches` is a DEVICE array of db_batch built once by the host; per-call arguments are slot indices.
  * The solve program is a flat instruction stream aligned one-to-one with the LU value stream: a forward section
- * then a backward section, each padded to a multiple of 8 entries.  Rows are visited in LEVEL order of the triangular
- * solve's dependency DAG (rows of one level are independent), so a row's inputs sit several rows upstream and the
- * kernel can preload x values two chunks ahead:
- *   c >= 0            : acc -= LU[e] * x_col.  Plain code = column * ld (element offset of that row in a vector).
- *                       DB_I_FRESH_REG | k: the column was completed too recently for the preload; it is the k-th most
- *                       recently completed row (k = 1..3), held in registers.  DB_I_FRESH_MEM | column*ld: re-read memory.
- *   c < 0, != DB_I_SKIP: end of the current row (forward: x[row] = acc; backward: x[row] = acc * LU[e], the reciprocal
- *                       pivot) and start of row (-1 - c) / ld, whose start value (RHS combination / forward result) is
- *                       preloaded like an x value.  The first entry of a section only starts a row.
- *   DB_I_SKIP         : padding
+ * then a backward section, each padded to a multiple of 16 entries.  First x <- right-hand-side combination; then
+ *   c >= 0            : acc -= LU[e] * x[c]            (c = column * DB_TILE, element offset of that row in a vector)
+ *   c < 0, != DB_I_SKIP: leave the current row (forward: x[row] = acc; backward: x[row] = acc * LU[e], the reciprocal
+ *                       pivot) and enter row (-1 - c) / DB_TILE with acc = x[row].  The first entry of a section only
+ *                       enters a row.  A forward row may be left and re-entered (its partial sum lives in x[row]).
+ *   DB_I_SKIP         : padding (factor value 0)
+ * Rows are visited in LEVEL order of the triangular solve's dependency DAG (rows of one level are independent); runs
+ * of dense forward rows (boundary rows) are interleaved in 15-entry segments so the run sweeps x once, not once per row.
+ * The fused kernel consumes the stream through per-chunk control blocks (`ctrl`, built by the host from the stream).
  * ------------------------------------------------------------------------------------------------------- */
 #define DB_MAX_VECS 24
 #define DB_MAX_LU 4
 #define DB_I_SKIP ((int32_t)0x80000000)
-#define DB_I_FRESH_REG 0x40000000
-#define DB_I_FRESH_MEM 0x20000000
-#define DB_I_OFFMASK   0x1FFFFFFF
 /* one term of a template mat-vec: y[row] += val * mono[mono][s] * x[col_off + s']; col_off = column * DB_TILE */
 typedef struct { double val; int32_t col_off; int32_t mono; } db_term;
 typedef struct {

@@ -32,52 +32,32 @@ def factor(prog, LU):
 
 
 def solve(prog, LU, rhs):
-    """Mirrors csrc/pencil.cu k_batches_solve: chunks of 8 entries; plain x values (and the start value of the next row)
-    of chunk q are preloaded BEFORE chunk q-1 is computed; FRESH entries come from the three most recently completed rows
-    or are re-read at compute time."""
-    SKIP, FRESH_REG, FRESH_MEM, MASK, CH = -2**31, 1 << 30, 1 << 29, (1 << 29) - 1, 16
-    n, ld = prog.n, prog.tile
+    """Mirrors csrc/pencil.cu k_batches_solve_flat: x <- rhs; per 16-entry chunk the control block's 16 offsets are
+    gathered in one burst, entries flagged in maskF are re-read right before use, row-boundary entries store the
+    accumulator into the row being left (backward: times the reciprocal pivot) and continue from the gathered start
+    value of the row being entered."""
+    CH = 16
+    ld = prog.tile
     y = np.array(rhs, dtype=float, copy=True)
-    for sec0, sec1, forward in ((0, prog.n_fwd, True), (prog.n_fwd, prog.nE, False)):
-        nch = (sec1 - sec0) // CH
-
-        def preload(q):
-            out = []
-            for e in range(sec0 + q * CH, sec0 + (q + 1) * CH):
-                c = int(prog.prog[e])
-                if c == SKIP:
-                    out.append(None)
-                elif c < 0:
-                    out.append(y[(-1 - c) // ld].copy())          # rhs (forward) / forward result (backward) of the next row
-                elif c & (FRESH_REG | FRESH_MEM):
-                    out.append(None)
-                else:
-                    out.append(y[c // ld].copy())
-            return out
-        cur, acc, last = None, None, [None, None, None]
-        DB = 0                                         # x values of chunk q are gathered right before chunk q is computed
-        for q in range(nch):
-            pre = preload(q)
-            for j in range(CH):
-                e = sec0 + q * CH + j
-                c = int(prog.prog[e])
-                if c == SKIP:
-                    continue
-                if c < 0:
-                    if cur is not None:
-                        val = acc if forward else acc * LU[e]
-                        y[cur] = val
-                        last = [val.copy(), last[0], last[1]]
-                    cur = (-1 - c) // ld
-                    acc = pre[j]
-                else:
-                    if c & FRESH_REG:
-                        xv = last[(c & 3) - 1]
-                    elif c & FRESH_MEM:
-                        xv = y[(c & MASK) // ld]
-                    else:
-                        xv = pre[j]
-                    acc = acc - LU[e] * xv
+    ctrl = prog.ctrl
+    nfwd = prog.n_fwd // CH
+    acc = None
+    for q in range(prog.nE // CH):
+        forward = q < nfwd
+        goff, foff = ctrl[q, :16], ctrl[q, 16:32]
+        maskE, maskB, maskF = (int(ctrl[q, 32]) & 0xFFFF, int(ctrl[q, 33]) & 0xFFFF, int(ctrl[q, 34]) & 0xFFFF)
+        xv = [y[g // ld].copy() for g in goff]
+        for j in range(CH):
+            e = q * CH + j
+            if maskF >> j & 1:
+                xv[j] = y[goff[j] // ld].copy()
+            if acc is None:
+                acc = np.zeros_like(xv[j])
+            acc_a = acc - LU[e] * xv[j]
+            val = acc if forward else acc * LU[e]
+            if maskE >> j & 1:
+                y[foff[j] // ld] = val
+            acc = xv[j] if (maskB >> j & 1) else acc_a
     return y
 
 

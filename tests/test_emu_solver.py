@@ -16,7 +16,12 @@ def emulation():
     E.uninstall()
 
 
-def test_rb3d_steps(golden):
+@pytest.mark.parametrize("dense", [None, "4"])
+def test_rb3d_steps(golden, dense, monkeypatch):
+    """dense="4": forward rows with >= 4 entries count as dense, so the segmented dense-run visits (partial sums kept in
+    x, re-entered rows, same-chunk re-reads) of the fused solve kernel are exercised at this tiny size."""
+    if dense:
+        monkeypatch.setenv("DB_SOLVE_DENSE", dense)
     g = golden("rb3d_8.npz")
     pb = examples.rayleigh_benard(dim=3, Nh=8, Nz=8, Rayleigh=1e6)
     solver = pb['problem'].build_solver(d3.RK222)

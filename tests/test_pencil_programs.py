@@ -10,8 +10,9 @@ import program_interp as pi
 GAMMA = (2 - np.sqrt(2)) / 2
 
 
+@pytest.mark.parametrize("dense", [64, 5])      # 5: the segmented dense-row runs are exercised at test sizes too
 @pytest.mark.parametrize("dim,Nh,Nz,dt", [(3, 8, 16, 1e-2), (2, 16, 24, 1e-3), (3, 6, 12, 1e2)])
-def test_rb_programs_solve(dim, Nh, Nz, dt):
+def test_rb_programs_solve(dim, Nh, Nz, dt, dense):
     pb = examples.rayleigh_benard(dim=dim, Nh=Nh, Nz=Nz)
     builder = PencilSystemBuilder(pb['problem'])
     batches = build_batches(builder)
@@ -19,7 +20,7 @@ def test_rb_programs_solve(dim, Nh, Nz, dt):
     rng = np.random.default_rng(0)
     total = 0
     for batch in batches:
-        prog = compile_batch(batch, a0, b0)
+        prog = compile_batch(batch, a0, b0, dense=dense)
         asm = assembly_program(batch, prog, a0, b0)
         LU = pi.factor(prog, pi.assemble(prog, asm))
         rhs = rng.standard_normal((prog.n, prog.S))
