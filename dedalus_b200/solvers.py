@@ -102,13 +102,17 @@ class BatchSet:
         self.nb = len(self.items)
         arr = (CBatch * max(self.nb, 1))()
         blk = dict(solve=0, matvec=0, move0=0, move1=0, asm=0)
+        pair_tiles_total = sum((db.S + 127) // 128 for db in self.items)
         for i, db in enumerate(self.items):
             c = arr[i]
             c.n, c.S, c.ld, c.n_entries = db.n, db.S, db.ld, db.prog.nE
             c.n_fwd, c.n_bwd = db.prog.n_fwd, db.prog.nE - db.prog.n_fwd
             c.blk_solve = blk['solve']; blk['solve'] += (db.S + 63) // 64
-            # mat-vec CTAs: 128 systems (two per thread) x mv_rows consecutive rows (csrc/pencil.cu k_batches_matvec)
-            mv_rows = int(os.environ.get("DB_MV_ROWS", 320))       # measured at 256^3: 64 -> 3.76, 128 -> 3.70, 320 -> 3.48 ms/step
+            # mat-vec CTAs: 128 systems (two per thread) x mv_rows consecutive rows (csrc/pencil.cu k_batches_matvec).
+            # Long row runs re-use the x window in L1 (measured at 256^3: 64 -> 3.76, 128 -> 3.70, 320 -> 3.48 ms/step) but
+            # need enough 128-system tiles to fill the GPU; with few tiles per rank (multi-GPU) fall back to 64-row CTAs.
+            mv_rows = 320 if pair_tiles_total * 4 >= 148 * 8 else 64
+            mv_rows = int(os.environ.get("DB_MV_ROWS", mv_rows))
             c.mv_rows = mv_rows
             c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 127) // 128) * (-(-db.n // mv_rows))
             c.blk_assemble = blk['asm']; blk['asm'] += ((db.S + 127) // 128) * ((db.prog.nE + 63) // 64)
