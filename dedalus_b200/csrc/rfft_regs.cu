@@ -118,14 +118,42 @@ __device__ __forceinline__ void stage_rows(double* buf, const double* __restrict
     }
 }
 
+// Thread layout.  Both register stages are split so that no thread holds more than max(Q, NB/2) complex values:
+//   stage A (size NA = 3Q): thread (c, n2, p) computes the Q outputs k1 = c + 3 kb of the radix-3 residue c
+//   stage B (size NB):      thread (h, k1, p) computes the NB/2 outputs k2 = 2 m + h (first radix-2 split, DIF)
+// (forward: the same two splits in the opposite order).  3 NB P threads work in stage A and 6 Q P in stage B: 384 = 384
+// at n = 384, at ~80 registers, so two CTAs (24 warps) are resident per SM and every warp works in both stages.
+template <int Q, int NB> struct RegGeom {
+    static constexpr int NA = 3 * Q, N = NA * NB, P = RR_P;
+    static constexpr int TA = 3 * NB * P, TB = 6 * Q * P;
+    static constexpr int THREADS = TA > TB ? TA : TB;
+    static constexpr int MINB = (2 * N * P * 16 + 1024) * 2 <= 226 * 1024 ? 2 : 1;
+};
+
+template <bool INV, int N, int... M>
+__device__ __forceinline__ void twiddle_odd_half(double2 (&o)[N], std::integer_sequence<int, M...>)
+{
+    ((void)(o[M] = mul_tw<M, 2 * N, INV>(o[M])), ...);
+}
+
+// u[b] = lo[b] + W3^(2c) hi[b], then * W_NA^(b c)      (backward stage A, residue C)
+template <int C, int Q, bool INV>
+__device__ __forceinline__ void residue_combine(double2 (&u)[Q], const double2 (&lo)[Q], const double2 (&hi)[Q])
+{
+#pragma unroll
+    for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<(2 * C) % 3, 3, INV>(hi[b]));
+    twiddle_row<C, 3 * Q, INV>(u, std::make_integer_sequence<int, Q>{});
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // backward: coefficients (M rows) -> grid (n rows)
 // ---------------------------------------------------------------------------------------------------------
 template <int Q, int NB, bool DERIV>
-__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P, (3 * Q * NB <= 384 ? 2 : 1))
+__global__ void __launch_bounds__(RegGeom<Q, NB>::THREADS, RegGeom<Q, NB>::MINB)
 k_rbwd_regs(RegArgs a, TileWalk tw_)
 {
-    constexpr int NA = 3 * Q, N = NA * NB, P = RR_P;
+    using G = RegGeom<Q, NB>;
+    constexpr int NA = G::NA, N = G::N, P = G::P, H = NB / 2;
     DB_SMEM(double2, sm);                                   // 2 buffers of [N][P] double2
     const int p = threadIdx.x & (P - 1), r = threadIdx.x >> 3;
     const int64_t inner = a.inner;
@@ -137,6 +165,9 @@ k_rbwd_regs(RegArgs a, TileWalk tw_)
     const double* __restrict__ tw = a.twn;
     auto tile_src = [&](int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
                                      return a.in + o * M * inner + xt * (2 * P); };
+    const bool in_a = r < 3 * NB, in_b = r < 2 * NA;
+    const int n2 = r % NB, c = r / NB;                       // stage A role
+    const int k1 = r % NA, h = r / NA;                       // stage B role
     int64_t t = blockIdx.x;
     int cur = 0;
     if (t < tw_.total) stage_rows(reinterpret_cast<double*>(sm), tile_src(t), M, inner);
@@ -148,9 +179,8 @@ k_rbwd_regs(RegArgs a, TileWalk tw_)
         db_cp_commit();
         db_cp_wait<1>();
         __syncthreads();
-        double2 lo[Q], hi[Q];
-        const int n2 = r;
-        if (r < NB) {
+        double2 u[Q];
+        if (in_a) {
             // Z_k = X1_k + i X2_k (k <= Kmax), Z_{n-k} = conj X1_k + i conj X2_k, X_k = (c_2k + i c_2k+1) / 2, X_0 = c_0
             auto spec = [&](int k, bool mirrored) -> double2 {
                 if (k > Kmax) return make_double2(0.0, 0.0);
@@ -167,80 +197,73 @@ k_rbwd_regs(RegArgs a, TileWalk tw_)
                 }
                 return mirrored ? make_double2(0.5 * (R.x + I.y), 0.5 * (R.y - I.x)) : make_double2(0.5 * (R.x - I.y), 0.5 * (I.x + R.y));
             };
+            double2 lo[Q], hi[Q];
 #pragma unroll
             for (int b = 0; b < Q; ++b) {
                 lo[b] = spec(NB * b + n2, false);                  // Z[NB b + n2]
                 hi[b] = spec(NB * (Q - b) - n2, true);             // Z[NB (2Q + b) + n2] = mirror of mode n - that
             }
+            // stage A: size-NA DFT over n1 = Q a + b with the a = 1 third identically zero; this thread's residue c
+            if (c == 0) residue_combine<0, Q, true>(u, lo, hi);
+            else if (c == 1) residue_combine<1, Q, true>(u, lo, hi);
+            else residue_combine<2, Q, true>(u, lo, hi);
         }
-        __syncthreads();                                           // every input value is in registers: reuse `in` as exchange
-        if (r < NB) {
-            // stage A: size-NA DFT over n1 = Q a + b with the a = 1 third identically zero; output k1 = c + 3 kb
+        __syncthreads();                                           // every input value is consumed: reuse `in` as exchange
+        if (in_a) {
+            DftP2<Q, true>::run(u);
             double2* dst = in + n2 * P + p;
-            {
-                double2 u[Q];
 #pragma unroll
-                for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], hi[b]);
-                DftP2<Q, true>::run(u);
-#pragma unroll
-                for (int kb = 0; kb < Q; ++kb) {
-                    const int k1 = 3 * kb;
-                    dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
-                }
-            }
-            {
-                double2 u[Q];
-#pragma unroll
-                for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<2, 3, true>(hi[b]));
-                twiddle_row<1, NA, true>(u, std::make_integer_sequence<int, Q>{});
-                DftP2<Q, true>::run(u);
-#pragma unroll
-                for (int kb = 0; kb < Q; ++kb) {
-                    const int k1 = 3 * kb + 1;
-                    dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
-                }
-            }
-            {
-                double2 u[Q];
-#pragma unroll
-                for (int b = 0; b < Q; ++b) u[b] = cadd2(lo[b], mul_tw<1, 3, true>(hi[b]));
-                twiddle_row<2, NA, true>(u, std::make_integer_sequence<int, Q>{});
-                DftP2<Q, true>::run(u);
-#pragma unroll
-                for (int kb = 0; kb < Q; ++kb) {
-                    const int k1 = 3 * kb + 2;
-                    dst[k1 * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * k1));
-                }
+            for (int kb = 0; kb < Q; ++kb) {
+                const int kk = 3 * kb + c;                         // output k1
+                dst[kk * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * kk));
             }
         }
         __syncthreads();
-        if (r < NA) {
-            // stage B: size-NB DFT over n2 for fixed k1 = r; grid index j = k1 + NA k2
-            const int k1 = r;
-            double2 v[NB];
+        if (in_b) {
+            // stage B: size-NB DFT over n2 for fixed k1, outputs k2 = 2 m + h; grid index j = k1 + NA k2
             const double2* src = in + (k1 * NB) * P + p;
+            double2 v[H];
+            if (h == 0) {
 #pragma unroll
-            for (int n2b = 0; n2b < NB; ++n2b) v[n2b] = src[n2b * P];
-            DftP2<NB, true>::run(v);
+                for (int m = 0; m < H; ++m) v[m] = cadd2(src[m * P], src[(m + H) * P]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < H; ++m) v[m] = csub2(src[m * P], src[(m + H) * P]);
+                twiddle_odd_half<true>(v, std::make_integer_sequence<int, H>{});
+            }
+            DftP2<H, true>::run(v);
             const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
-            double* __restrict__ gout = a.out + (o * N + k1) * inner + xt * (2 * P) + 2 * p;
+            double* __restrict__ gout = a.out + (o * N + k1 + NA * h) * inner + xt * (2 * P) + 2 * p;
 #pragma unroll
-            for (int k2 = 0; k2 < NB; ++k2)
-                *reinterpret_cast<double2*>(gout + (int64_t)(NA * k2) * inner) = v[k2];
+            for (int m = 0; m < H; ++m)
+                *reinterpret_cast<double2*>(gout + (int64_t)(2 * NA * m) * inner) = v[m];
         }
         __syncthreads();                                           // exchange reads done before the next prefetch lands here
     }
     db_cp_wait<0>();
 }
 
+// forward stage 2, residue C of the outputs: t[b] = sum_a' W3^(a' C) B[Q a' + b], times W_NA^(b C)
+template <int C, int Q>
+__device__ __forceinline__ void residue_gather(double2 (&u)[Q], const double2* src, int stride)
+{
+#pragma unroll
+    for (int b = 0; b < Q; ++b) {
+        const double2 b0 = src[b * stride], b1 = src[(Q + b) * stride], b2 = src[(2 * Q + b) * stride];
+        u[b] = cadd2(b0, cadd2(mul_tw<C % 3, 3, false>(b1), mul_tw<(2 * C) % 3, 3, false>(b2)));
+    }
+    twiddle_row<C, 3 * Q, false>(u, std::make_integer_sequence<int, Q>{});
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // forward: grid (n rows) -> coefficients (M rows)
 // ---------------------------------------------------------------------------------------------------------
 template <int Q, int NB>
-__global__ void __launch_bounds__((3 * Q > NB ? 3 * Q : NB) * RR_P, (3 * Q * NB <= 384 ? 2 : 1))
+__global__ void __launch_bounds__(RegGeom<Q, NB>::THREADS, RegGeom<Q, NB>::MINB)
 k_rfwd_regs(RegArgs a, TileWalk tw_)
 {
-    constexpr int NA = 3 * Q, N = NA * NB, P = RR_P;
+    using G = RegGeom<Q, NB>;
+    constexpr int NA = G::NA, N = G::N, P = G::P, H = NB / 2;
     DB_SMEM(double2, sm);                                   // 2 buffers of [N][P] double2
     const int p = threadIdx.x & (P - 1), r = threadIdx.x >> 3;
     const int64_t inner = a.inner;
@@ -248,6 +271,9 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
     const double* __restrict__ tw = a.twn;
     auto tile_src = [&](int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
                                      return a.in + o * N * inner + xt * (2 * P); };
+    const bool in_1 = r < 2 * NA, in_2 = r < 3 * NB;
+    const int j1 = r % NA, h = r / NA;                       // stage 1 role: outputs k2 = 2 m + h of the size-NB DFT
+    const int k2 = r % NB, c = r / NB;                       // stage 2 role: outputs k1 = c + 3 kb of the size-NA DFT
     int64_t t = blockIdx.x;
     int cur = 0;
     if (t < tw_.total) stage_rows(reinterpret_cast<double*>(sm), tile_src(t), N, inner);
@@ -259,53 +285,52 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
         db_cp_commit();
         db_cp_wait<1>();
         __syncthreads();
-        double2 v[NB];
-        if (r < NA) {
-            // stage 1: size-NB DFT over j2 for fixed j1 = r (grid index j = j1 + NA j2)
+        double2 v[H];
+        if (in_1) {
+            // stage 1: size-NB DFT over j2 for fixed j1 (grid index j = j1 + NA j2), first radix-2 split (DIF)
+            const double2* src = in + j1 * P + p;
+            if (h == 0) {
 #pragma unroll
-            for (int j2 = 0; j2 < NB; ++j2) v[j2] = in[(r + NA * j2) * P + p];
+                for (int m = 0; m < H; ++m) v[m] = cadd2(src[(NA * m) * P], src[(NA * (m + H)) * P]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < H; ++m) v[m] = csub2(src[(NA * m) * P], src[(NA * (m + H)) * P]);
+                twiddle_odd_half<false>(v, std::make_integer_sequence<int, H>{});
+            }
         }
-        __syncthreads();                                           // inputs are in registers: reuse `in` as exchange
-        if (r < NA) {
-            const int j1 = r;
-            DftP2<NB, false>::run(v);
-            double2* dst = in + (j1 * NB) * P + p;
+        __syncthreads();                                           // inputs are consumed: reuse `in` as exchange
+        if (in_1) {
+            DftP2<H, false>::run(v);
+            double2* dst = in + (j1 * NB + h) * P + p;
 #pragma unroll
-            for (int k2 = 0; k2 < NB; ++k2) dst[k2 * P] = (k2 == 0) ? v[0] : cmul2(v[k2], ldtwn(tw, j1 * k2));
+            for (int m = 0; m < H; ++m) {
+                const int kk = 2 * m + h;                          // output k2
+                dst[(2 * m) * P] = (kk == 0) ? v[m] : cmul2(v[m], ldtwn(tw, j1 * kk));
+            }
         }
         __syncthreads();
-        double2 zlo[Q], zhi[Q];
-        const int k2 = r;
-        if (r < NB) {
-            // stage 2: size-NA DFT over j1 = 3 jb + c for fixed k2, keeping only outputs k1 = kb (low third) and 2Q + kb
+        double2 z[Q];
+        if (in_2) {
+            // stage 2: size-NA DFT over j1 = Q a' + b for fixed k2; this thread's output residue c: k1 = c + 3 kb
             const double2* src = in + k2 * P + p;
-            double2 s0[Q], s1[Q], s2[Q];
-#pragma unroll
-            for (int jb = 0; jb < Q; ++jb) {
-                s0[jb] = src[(3 * jb) * NB * P];
-                s1[jb] = src[(3 * jb + 1) * NB * P];
-                s2[jb] = src[(3 * jb + 2) * NB * P];
-            }
-            DftP2<Q, false>::run(s0);
-            DftP2<Q, false>::run(s1);
-            DftP2<Q, false>::run(s2);
-            twiddle_row<1, NA, false>(s1, std::make_integer_sequence<int, Q>{});
-            twiddle_row<2, NA, false>(s2, std::make_integer_sequence<int, Q>{});
-#pragma unroll
-            for (int kb = 0; kb < Q; ++kb) {
-                zlo[kb] = cadd2(s0[kb], cadd2(s1[kb], s2[kb]));                                        // Z[NB kb + k2]
-                zhi[kb] = cadd2(s0[kb], cadd2(mul_tw<2, 3, false>(s1[kb]), mul_tw<1, 3, false>(s2[kb])));   // Z[NB (2Q + kb) + k2]
-            }
+            if (c == 0) residue_gather<0, Q>(z, src, NB * P);
+            else if (c == 1) residue_gather<1, Q>(z, src, NB * P);
+            else residue_gather<2, Q>(z, src, NB * P);
+            DftP2<Q, false>::run(z);
         }
         __syncthreads();
-        if (r < NB) {
+        if (in_2) {
+            // park the high third (k1 >= 2Q) as Zhi[k1 - 2Q][k2] for the mirror partners
             double2* dst = in + k2 * P + p;
 #pragma unroll
-            for (int kb = 0; kb < Q; ++kb) dst[kb * NB * P] = zhi[kb];
+            for (int kb = 0; kb < Q; ++kb) {
+                const int kk = 3 * kb + c;
+                if (kk >= 2 * Q) dst[(kk - 2 * Q) * NB * P] = z[kb];
+            }
         }
         __syncthreads();
-        if (r < NB) {
-            // Z_{n-k} for k = NB kb + k2 sits at (kb', k2') = (Q - 1 - kb, NB - k2) for k2 > 0, (Q - kb, 0) for k2 = 0
+        if (in_2) {
+            // Z_{n-k} for k = NB k1 + k2 sits at Zhi[(Q - 1 - k1), NB - k2] for k2 > 0, Zhi[Q - k1, 0] for k2 = 0
             const double sc = 1.0 / N;
             const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
             double* __restrict__ gout = a.out + o * M * inner + xt * (2 * P) + 2 * p;
@@ -313,15 +338,16 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
             const double2* src = in + k2p * P + p;
 #pragma unroll
             for (int kb = 0; kb < Q; ++kb) {
-                const int k = NB * kb + k2;
-                if (k > Kmax) continue;
+                const int kk = 3 * kb + c;                         // k1
+                const int k = NB * kk + k2;
+                if (kk >= Q || k > Kmax) continue;
                 double* row = gout + (int64_t)(2 * k) * inner;
-                const double2 za = zlo[kb];
+                const double2 za = z[kb];
                 if (k == 0) {
                     *reinterpret_cast<double2*>(row) = make_double2(za.x * sc, za.y * sc);
                     *reinterpret_cast<double2*>(row + inner) = make_double2(0.0, 0.0);
                 } else {
-                    const int kbp = (k2 == 0) ? Q - kb : Q - 1 - kb;
+                    const int kbp = (k2 == 0) ? Q - kk : Q - 1 - kk;
                     const double2 zb = src[kbp * NB * P];
                     *reinterpret_cast<double2*>(row) = make_double2((za.x + zb.x) * sc, (za.y + zb.y) * sc);
                     *reinterpret_cast<double2*>(row + inner) = make_double2((za.y - zb.y) * sc, (zb.x - za.x) * sc);
@@ -350,7 +376,7 @@ static int regs_num_sms()
 template <int Q, int NB>
 int launch_regs(bool fwd, const RegArgs& a, int64_t outer, void* stream)
 {
-    constexpr int NA = 3 * Q, THREADS = (NA > NB ? NA : NB) * RR_P;
+    constexpr int NA = 3 * Q, THREADS = RegGeom<Q, NB>::THREADS;
     const size_t bytes = (size_t)2 * NA * NB * RR_P * sizeof(double2);
     TileWalk w;
     w.tiles_per_outer = a.inner / (2 * RR_P);
