@@ -683,6 +683,8 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
 // ---------------------------------------------------------------------------------------------------------
 int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
                      int64_t inner, int32_t deriv, double kscale, void* stream);       // rfft_regs.cu
+int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t lines, int32_t n_coeff,
+                     const double* diags, int32_t nd, void* stream);
 
 template <int KIND>
 static int launch_fft(const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff, int64_t inner,
@@ -694,6 +696,10 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
     if (KIND == K_RFWD || KIND == K_RBWD) {
         // dealiased sizes on a strided axis: register-resident two-stage kernels (rfft_regs.cu)
         const int rc = db_rfft_regs_try(KIND == K_RFWD, plan, in, out, outer, n_coeff, inner, deriv, kscale, stream);
+        if (rc >= 0) return rc;
+    }
+    if ((KIND == K_CHFWD || (KIND == K_CHBWD && nda == 0 && ndb == 0)) && inner == 1) {
+        const int rc = db_cheb_regs_try(KIND == K_CHFWD, plan, in, out, outer, n_coeff, KIND == K_CHFWD ? da : nullptr, KIND == K_CHFWD ? nda : 0, stream);
         if (rc >= 0) return rc;
     }
     FftArgs a;

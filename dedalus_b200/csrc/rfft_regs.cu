@@ -359,6 +359,277 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
     db_cp_wait<0>();
 }
 
+// =========================================================================================================
+// Chebyshev (DCT-II / DCT-III) along CONTIGUOUS lines with the same two register stages (T2 on the benchmark path).
+// A tile is 16 adjacent lines = one contiguous block of global memory; lines are staged in shared memory as
+// X[line][n + 2] (the +2 spreads line pairs over the banks), two adjacent lines form one complex line, and the DCT runs
+// through the full-length complex FFT of the even/odd reordered sequence (Makhoul): v[m] = g[2m] (m < n/2),
+// v[m] = g[2(n-1-m)+1] otherwise;
+//   backward: Z_k = w_k ((a1 + b2) + i (a2 - b1)), a = c^_k, b = c^_{n-k}, w_k = exp(i pi k / 2n), c^ = scaled, sign-
+//             flipped coefficients (zero beyond the coefficient size);  v1 + i v2 = IDFT_n(Z)
+//   forward : Z = DFT_n(v1 + i v2);  C1_k = s_k Re(q^k (Z_k + conj Z_{n-k})),  C2_k = s_k Re(q^k (Z_k - conj Z_{n-k}) / i),
+//             q = conj w; truncation to the coefficient size and the banded ultraspherical conversion are applied while
+//             the coefficient lines are still in shared memory.
+// Conventions as fft.cu K_CHFWD / K_CHBWD (reference core/transforms.py:715-746, 771-902).
+// =========================================================================================================
+struct ChebArgs {
+    const double* in;
+    double* out;
+    const double* twn;      // exp(-2 pi i j / n)
+    const double* twq;      // exp(-i pi k / (2 n))
+    const double* diags;    // forward: conversion diagonals [nd][M]
+    int64_t lines;
+    int32_t M;              // coefficient size (even, <= n)
+    int32_t nd;
+};
+
+#define CH_LINES (2 * RR_P)
+
+template <int Q, int NB>
+__global__ void __launch_bounds__(RegGeom<Q, NB>::THREADS, RegGeom<Q, NB>::MINB)
+k_chbwd_regs(ChebArgs a)
+{
+    using G = RegGeom<Q, NB>;
+    constexpr int NA = G::NA, N = G::N, P = G::P, H = NB / 2, LX = N + 2;
+    DB_SMEM(double, X);                                      // [16][LX] doubles, then Y = [N][P] double2
+    double2* Y = reinterpret_cast<double2*>(X + CH_LINES * LX);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int M = a.M;
+    const int64_t l0 = (int64_t)blockIdx.x * CH_LINES;
+    const int nl = (a.lines - l0 < CH_LINES) ? (int)(a.lines - l0) : CH_LINES;
+    // ---- stage the coefficient lines (16-byte chunks); missing lines of a partial tile are zero
+    {
+        const int cpl = M / 2;                               // chunks per line
+        for (int idx = tid; idx < CH_LINES * cpl; idx += nthreads) {
+            const int l = idx / cpl, ch = idx - l * cpl;
+            if (l < nl) db_cp_async16(X + l * LX + 2 * ch, a.in + (l0 + l) * M + 2 * ch);
+            else { X[l * LX + 2 * ch] = 0.0; X[l * LX + 2 * ch + 1] = 0.0; }
+        }
+        db_cp_commit();
+        db_cp_wait<0>();
+    }
+    __syncthreads();
+    // ---- spectrum of the packed line pairs: Y[k][p] = Z_k
+    {
+        const double c0 = 0.56418958354775628694807945156077;     // 1/sqrt(pi)
+        const double c1 = 0.39894228040143267793994605993438;     // 1/sqrt(2 pi)
+        // warp task = (block of 8 modes, half of the line pairs); lanes = 4 pairs x 8 modes (bank-friendly on both sides)
+        const int lane = tid & 31, w = tid >> 5, nw = nthreads >> 5;
+        const int kk = lane >> 2;
+        for (int wt = w; wt < 2 * ((N + 7) / 8); wt += nw) {
+            const int k = (wt >> 1) * 8 + kk, pp = (lane & 3) + 4 * (wt & 1);
+            if (k >= N) continue;
+            const double* x1 = X + (2 * pp) * LX;
+            const double* x2 = x1 + LX;
+            const int kb = N - k;
+            const double sa = ((k == 0) ? c0 : c1) * ((k & 1) ? -1.0 : 1.0);
+            const double sb = c1 * ((kb & 1) ? -1.0 : 1.0);
+            const bool ha = k < M, hb = (k > 0) && (kb < M);
+            const double a1 = ha ? x1[k] * sa : 0.0, a2 = ha ? x2[k] * sa : 0.0;
+            const double b1 = hb ? x1[kb] * sb : 0.0, b2 = hb ? x2[kb] * sb : 0.0;
+            const double2 wq = ldtwn(a.twq, k);              // exp(-i pi k / 2n): conj of w_k
+            Y[k * P + pp] = cmulc2(make_double2(a1 + b2, a2 - b1), wq);
+        }
+    }
+    __syncthreads();
+    const int p = tid & (P - 1), r = tid >> 3;
+    const bool in_a = r < 3 * NB, in_b = r < 2 * NA;
+    const int n2 = r % NB, c = r / NB;
+    const int k1 = r % NA, h = r / NA;
+    const double* __restrict__ tw = a.twn;
+    double2 u[Q];
+    if (in_a) {
+        const double2* src = Y + n2 * P + p;
+        // stage A residue c: u[b] = sum_a W3^(a c) Z[NB (Q a + b) + n2], times W_NA^(b c)      (inverse signs)
+        auto gather = [&](auto CC) {
+            constexpr int C = decltype(CC)::value;
+#pragma unroll
+            for (int b = 0; b < Q; ++b) {
+                const double2 z0 = src[(NB * b) * P], z1 = src[(NB * (Q + b)) * P], z2 = src[(NB * (2 * Q + b)) * P];
+                u[b] = cadd2(z0, cadd2(mul_tw<C % 3, 3, true>(z1), mul_tw<(2 * C) % 3, 3, true>(z2)));
+            }
+            twiddle_row<C, NA, true>(u, std::make_integer_sequence<int, Q>{});
+        };
+        if (c == 0) gather(std::integral_constant<int, 0>{});
+        else if (c == 1) gather(std::integral_constant<int, 1>{});
+        else gather(std::integral_constant<int, 2>{});
+    }
+    __syncthreads();
+    if (in_a) {
+        DftP2<Q, true>::run(u);
+        double2* dst = Y + n2 * P + p;
+#pragma unroll
+        for (int kb = 0; kb < Q; ++kb) {
+            const int kq = 3 * kb + c;
+            dst[kq * NB * P] = cmulc2(u[kb], ldtwn(tw, n2 * kq));
+        }
+    }
+    __syncthreads();
+    if (in_b) {
+        const double2* src = Y + (k1 * NB) * P + p;
+        double2 v[H];
+        if (h == 0) {
+#pragma unroll
+            for (int m = 0; m < H; ++m) v[m] = cadd2(src[m * P], src[(m + H) * P]);
+        } else {
+#pragma unroll
+            for (int m = 0; m < H; ++m) v[m] = csub2(src[m * P], src[(m + H) * P]);
+            twiddle_odd_half<true>(v, std::make_integer_sequence<int, H>{});
+        }
+        DftP2<H, true>::run(v);
+        // v[m] = (v1, v2)[j], j = k1 + NA (2 m + h): scatter to grid positions of the two lines
+        double* o1 = X + (2 * p) * LX;
+        double* o2 = o1 + LX;
+#pragma unroll
+        for (int m = 0; m < H; ++m) {
+            const int j = k1 + NA * (2 * m + h);
+            const int pos = (2 * j < N) ? 2 * j : 2 * (N - 1 - j) + 1;
+            o1[pos] = v[m].x; o2[pos] = v[m].y;
+        }
+    }
+    __syncthreads();
+    // ---- store the grid lines (contiguous block)
+    {
+        const int cpl = N / 2;
+        for (int idx = tid; idx < nl * cpl; idx += nthreads) {
+            const int l = idx / cpl, ch = idx - l * cpl;
+            *reinterpret_cast<double2*>(a.out + (l0 + l) * N + 2 * ch) = *reinterpret_cast<const double2*>(X + l * LX + 2 * ch);
+        }
+    }
+}
+
+template <int Q, int NB>
+__global__ void __launch_bounds__(RegGeom<Q, NB>::THREADS, RegGeom<Q, NB>::MINB)
+k_chfwd_regs(ChebArgs a)
+{
+    using G = RegGeom<Q, NB>;
+    constexpr int NA = G::NA, N = G::N, P = G::P, H = NB / 2, LX = N + 2;
+    DB_SMEM(double, X);                                      // [16][LX] doubles, then Y = [N][P] double2
+    double2* Y = reinterpret_cast<double2*>(X + CH_LINES * LX);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int M = a.M;
+    const int64_t l0 = (int64_t)blockIdx.x * CH_LINES;
+    const int nl = (a.lines - l0 < CH_LINES) ? (int)(a.lines - l0) : CH_LINES;
+    {
+        const int cpl = N / 2;
+        for (int idx = tid; idx < CH_LINES * cpl; idx += nthreads) {
+            const int l = idx / cpl, ch = idx - l * cpl;
+            if (l < nl) db_cp_async16(X + l * LX + 2 * ch, a.in + (l0 + l) * N + 2 * ch);
+            else { X[l * LX + 2 * ch] = 0.0; X[l * LX + 2 * ch + 1] = 0.0; }
+        }
+        db_cp_commit();
+        db_cp_wait<0>();
+    }
+    __syncthreads();
+    const int p = tid & (P - 1), r = tid >> 3;
+    const bool in_1 = r < 2 * NA, in_2 = r < 3 * NB;
+    const int j1 = r % NA, h = r / NA;
+    const int k2 = r % NB, c = r / NB;
+    const double* __restrict__ tw = a.twn;
+    if (in_1) {
+        // stage 1: v[j] = (g1, g2)[pos(j)], j = j1 + NA j2; size-NB DFT over j2, outputs k2 = 2 m + h
+        const double* g1 = X + (2 * p) * LX;
+        const double* g2 = g1 + LX;
+        auto val = [&](int j2) -> double2 {
+            const int j = j1 + NA * j2;
+            const int pos = (2 * j < N) ? 2 * j : 2 * (N - 1 - j) + 1;
+            return make_double2(g1[pos], g2[pos]);
+        };
+        double2 v[H];
+        if (h == 0) {
+#pragma unroll
+            for (int m = 0; m < H; ++m) v[m] = cadd2(val(m), val(m + H));
+        } else {
+#pragma unroll
+            for (int m = 0; m < H; ++m) v[m] = csub2(val(m), val(m + H));
+            twiddle_odd_half<false>(v, std::make_integer_sequence<int, H>{});
+        }
+        DftP2<H, false>::run(v);
+        double2* dst = Y + (j1 * NB + h) * P + p;
+#pragma unroll
+        for (int m = 0; m < H; ++m) {
+            const int kq = 2 * m + h;
+            dst[(2 * m) * P] = (kq == 0) ? v[m] : cmul2(v[m], ldtwn(tw, j1 * kq));
+        }
+    }
+    __syncthreads();
+    double2 z[Q];
+    if (in_2) {
+        const double2* src = Y + k2 * P + p;
+        if (c == 0) residue_gather<0, Q>(z, src, NB * P);
+        else if (c == 1) residue_gather<1, Q>(z, src, NB * P);
+        else residue_gather<2, Q>(z, src, NB * P);
+        DftP2<Q, false>::run(z);
+    }
+    __syncthreads();
+    if (in_2) {
+        // full spectrum in natural order: Y[k][p] = Z_k, k = NB k1 + k2, k1 = c + 3 kb
+        double2* dst = Y + (k2 * P) + p;
+#pragma unroll
+        for (int kb = 0; kb < Q; ++kb) dst[(NB * (3 * kb + c)) * P] = z[kb];
+    }
+    __syncthreads();
+    // ---- coefficients of both lines of every pair into X[line][k] (k < Kin), scaled, odd modes negated
+    const int Kin = M < N ? M : N;
+    {
+        const double s0 = 0.5 / N * 1.7724538509055160272981674833411;      // sqrt(pi)/(2N)
+        const double s1 = 1.0 / N * 1.2533141373155002512078826424055;      // sqrt(pi/2)/N
+        const int lane = tid & 31, w = tid >> 5, nw = nthreads >> 5;
+        const int kk = lane >> 2;
+        for (int wt = w; wt < 2 * ((Kin + 7) / 8); wt += nw) {
+            const int k = (wt >> 1) * 8 + kk, pp = (lane & 3) + 4 * (wt & 1);
+            if (k >= Kin) continue;
+            double* x1 = X + (2 * pp) * LX;
+            double* x2 = x1 + LX;
+            const double2 za = Y[k * P + pp];
+            const double2 zb = Y[((k == 0) ? 0 : N - k) * P + pp];
+            const double2 S = make_double2(za.x + zb.x, za.y - zb.y);            // Z_k + conj Z_{n-k}
+            const double2 D = make_double2(za.y + zb.y, zb.x - za.x);            // (Z_k - conj Z_{n-k}) / i
+            const double2 q = ldtwn(a.twq, k);
+            const double sc = ((k == 0) ? s0 : s1) * ((k & 1) ? -1.0 : 1.0);
+            x1[k] = sc * (q.x * S.x - q.y * S.y);
+            x2[k] = sc * (q.x * D.x - q.y * D.y);
+        }
+    }
+    __syncthreads();
+    // ---- store with the banded conversion applied: out[i] = sum_d diag[d][i] cof[i + d]
+    {
+        const int nd = a.nd;
+        for (int idx = tid; idx < nl * M; idx += nthreads) {
+            const int l = idx / M, i = idx - l * M;
+            const double* cf = X + l * LX;
+            double acc = 0.0;
+            if (i < Kin) {
+                if (nd > 0) {
+                    for (int d = 0; d < nd && i + d < Kin; ++d) acc = fma(a.diags[(int64_t)d * M + i], cf[i + d], acc);
+                } else acc = cf[i];
+            }
+            a.out[(l0 + l) * M + i] = acc;
+        }
+    }
+}
+
+template <int Q, int NB>
+int launch_cheb(bool fwd, const ChebArgs& a, void* stream)
+{
+    constexpr int N = 3 * Q * NB, THREADS = RegGeom<Q, NB>::THREADS;
+    const size_t bytes = (size_t)CH_LINES * (N + 2) * sizeof(double) + (size_t)N * RR_P * sizeof(double2);
+    const int64_t blocks = (a.lines + CH_LINES - 1) / CH_LINES;
+#ifndef DB_EMU
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_chbwd_regs<Q, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_chfwd_regs<Q, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_chbwd_regs<Q, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_chfwd_regs<Q, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr = true;
+    }
+#endif
+    if (fwd) DB_LAUNCH((k_chfwd_regs<Q, NB>), dim3((unsigned)blocks), dim3(THREADS), bytes, stream, a);
+    else DB_LAUNCH((k_chbwd_regs<Q, NB>), dim3((unsigned)blocks), dim3(THREADS), bytes, stream, a);
+    return db_check_launch(fwd ? "cheb_forward(regs)" : "cheb_backward(regs)");
+}
+
 static int regs_num_sms()
 {
 #ifdef DB_EMU
@@ -434,6 +705,32 @@ int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double
         case 48:  return launch_regs<2, 8>(fwd, a, outer, stream);
         case 24:  return launch_regs<2, 4>(fwd, a, outer, stream);
         case 768: return launch_regs<8, 32>(fwd, a, outer, stream);
+        default: --g_regs_launches; return -1;
+    }
+}
+
+// Chebyshev on contiguous lines (inner == 1): returns -1 if not covered (generic kernel in fft.cu takes over).
+// backward: plain DCT-III only (derivative / back-conversion are applied beforehand by db_band_lines);
+// forward: conversion diagonals fused into the store.
+int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t lines, int32_t n_coeff,
+                     const double* diags, int32_t nd, void* stream)
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("DB_CHEB_REGS"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+    if (!enabled) return -1;
+    const int n = plan->n;
+    if (plan->twn == nullptr || plan->twq == nullptr) return -1;
+    if (n_coeff % 2 != 0 || n_coeff < 2 || n_coeff > n || lines > 2147483647LL * CH_LINES) return -1;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
+    ChebArgs a;
+    a.in = in; a.out = out; a.twn = plan->twn; a.twq = plan->twq; a.diags = diags; a.lines = lines; a.M = n_coeff; a.nd = nd;
+    ++g_regs_launches;
+    switch (n) {
+        case 384: return launch_cheb<8, 16>(fwd, a, stream);
+        case 192: return launch_cheb<4, 16>(fwd, a, stream);
+        case 96:  return launch_cheb<4, 8>(fwd, a, stream);
+        case 48:  return launch_cheb<2, 8>(fwd, a, stream);
+        case 24:  return launch_cheb<2, 4>(fwd, a, stream);
         default: --g_regs_launches; return -1;
     }
 }

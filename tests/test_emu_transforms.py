@@ -191,3 +191,35 @@ def test_band_lines_warp_scan_matches_serial_recurrence(M, npre):
     scale = np.abs(ref).max()
     assert np.allclose(out_serial, ref, rtol=0, atol=1e-12 * scale)
     assert np.allclose(out_scan, ref, rtol=0, atol=1e-12 * scale)
+
+
+@pytest.mark.parametrize("M,N", [(256, 384), (128, 192), (64, 96), (32, 48), (16, 24), (200, 384), (384, 384)])
+@pytest.mark.parametrize("alpha", [0, 2])
+def test_register_resident_chebyshev(M, N, alpha):
+    """csrc/rfft_regs.cu k_chbwd_regs / k_chfwd_regs (contiguous lines, two lines per complex FFT, conversion fused into
+    the forward store) against the oracle transforms; 21 lines = one full tile + a partial one."""
+    from oracle import transforms_oracle as T
+    lib = E.emu(); plan = E.EmuPlan(N, 'real')
+    rng = np.random.default_rng(3 + alpha)
+    lines = 21
+    a = -0.5 + alpha
+    c = rng.standard_normal((lines, M))
+    g = np.full((lines, N), np.nan)
+    served = lib.rfft_regs_launches()
+    lib.call("db_cheb_backward", plan.ref(), E.ptr(c), E.ptr(g), lines, M, 1, None, 0, None, 0, None)
+    assert lib.rfft_regs_launches() == served + 1
+    ref = T.cheb_backward_fft(c, N, 1)                       # plain DCT-III of (-1/2, -1/2) coefficients
+    assert np.allclose(g, ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))
+    gr = rng.standard_normal((lines, N))
+    out = np.full((lines, M), np.nan)
+    if alpha:
+        Cm = jacobi.conversion_matrix(max(M, N), -0.5, -0.5, a, a)
+        nd = 2 * alpha + 1
+        from dedalus_b200.transforms import banded_upper_diags
+        dg = banded_upper_diags(Cm, M, nd)
+        lib.call("db_cheb_forward", plan.ref(), E.ptr(gr), E.ptr(out), lines, M, 1, E.ptr(dg), nd, None)
+    else:
+        lib.call("db_cheb_forward", plan.ref(), E.ptr(gr), E.ptr(out), lines, M, 1, None, 0, None)
+    assert lib.rfft_regs_launches() == served + 2
+    ref = T.cheb_forward_fft(gr, M, 1, a, a)
+    assert np.allclose(out, ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))

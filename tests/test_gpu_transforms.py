@@ -150,3 +150,30 @@ def test_register_resident_real_fourier(M, N, deriv):
         out = torch.full((outer, M, inner), float('nan'), dtype=torch.float64, device='cuda')
         rf.forward(_t(gr), out, 1)
         assert np.allclose(out.cpu().numpy(), T.rf_forward_fft(gr, M, 1), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("M,N", [(256, 384), (128, 192), (64, 96), (32, 48), (16, 24), (200, 384)])
+@pytest.mark.parametrize("alpha", [0, 2])
+def test_register_resident_chebyshev(M, N, alpha):
+    """csrc/rfft_regs.cu k_chbwd_regs / k_chfwd_regs (the z passes of the 256^3 benchmark) against the CPU oracle."""
+    import torch
+    from dedalus_b200.transforms import FastChebyshevTransform
+    from dedalus_b200.lib import get_lib
+    from oracle import transforms_oracle as T
+    rng = np.random.default_rng(3 + alpha)
+    a = -0.5 + alpha
+    plan = FastChebyshevTransform(N, M, a, a, -0.5, -0.5)
+    plain = FastChebyshevTransform(N, M, -0.5, -0.5, -0.5, -0.5)
+    c = rng.standard_normal((7, 3, M))
+    g = torch.full((7, 3, N), float('nan'), dtype=torch.float64, device='cuda')
+    served = get_lib().rfft_regs_launches()
+    plain.backward(_t(c), g, 2)
+    assert get_lib().rfft_regs_launches() == served + 1
+    ref = T.cheb_backward_fft(c, N, 2)
+    assert np.allclose(g.cpu().numpy(), ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))
+    gr = rng.standard_normal((7, 3, N))
+    out = torch.full((7, 3, M), float('nan'), dtype=torch.float64, device='cuda')
+    plan.forward(_t(gr), out, 2)
+    assert get_lib().rfft_regs_launches() == served + 2
+    ref = T.cheb_forward_fft(gr, M, 2, a, a)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))
