@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
 int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
                      int64_t inner, int32_t deriv, double kscale, void* stream);       // rfft_regs.cu
 int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t lines, int32_t n_coeff,
-                     const double* diags, int32_t nd, void* stream);
+                     const double* diags, int32_t nd, const double* pre, int32_t npre, const double* sol2, void* stream);
 
 template <int KIND>
 static int launch_fft(const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff, int64_t inner,
@@ -699,7 +699,8 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
         if (rc >= 0) return rc;
     }
     if ((KIND == K_CHFWD || (KIND == K_CHBWD && nda == 0 && ndb == 0)) && inner == 1) {
-        const int rc = db_cheb_regs_try(KIND == K_CHFWD, plan, in, out, outer, n_coeff, KIND == K_CHFWD ? da : nullptr, KIND == K_CHFWD ? nda : 0, stream);
+        const int rc = db_cheb_regs_try(KIND == K_CHFWD, plan, in, out, outer, n_coeff, KIND == K_CHFWD ? da : nullptr, KIND == K_CHFWD ? nda : 0,
+                                        nullptr, 0, nullptr, stream);
         if (rc >= 0) return rc;
     }
     FftArgs a;
@@ -770,6 +771,14 @@ extern "C" int db_cfft_backward(const db_fft_plan* plan, const double* c, double
 extern "C" int db_cheb_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner,
                                const double* conv_diags, int32_t conv_ndiag, void* stream)
 { return launch_fft<K_CHFWD>(plan, g, c, outer, n_coeff, inner, 0, 0.0, conv_diags, conv_ndiag, nullptr, 0, stream, "cheb_forward"); }
+
+extern "C" int db_cheb_backward_scan(const db_fft_plan* plan, const double* c, double* g, int64_t lines, int32_t n_coeff,
+                                     const double* pre_diags, int32_t pre_ndiag, const double* solve2_diags, void* stream)
+{
+    if (lines <= 0) return 0;
+    const int rc = db_cheb_regs_try(false, plan, c, g, lines, n_coeff, nullptr, 0, pre_diags, pre_ndiag, solve2_diags, stream);
+    return rc < 0 ? 2 : rc;            // 2: this size / alignment is not covered (no error recorded): use db_band_lines + db_cheb_backward
+}
 
 extern "C" int db_cheb_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
                                 const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream)

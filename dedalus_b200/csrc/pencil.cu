@@ -310,12 +310,22 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 // ---------------------------------------------------------------------------------------------------------
 #define SOLVE_CE 16
 #ifdef DB_EMU
+// test emulation: low 32 bits = bytes still expected, high 32 bits = completed phases; copies complete at issue, and a
+// waiter yields to the other fibers until the phase it waits for is complete (threads may run ahead of the producer)
 typedef unsigned long long db_mbar_t;
-__device__ __forceinline__ void db_mbar_init(db_mbar_t*, int) {}
+__device__ __forceinline__ void db_mbar_init(db_mbar_t* bar, int) { *bar = 0; }
 __device__ __forceinline__ void db_mbar_fence_init() {}
-__device__ __forceinline__ void db_mbar_expect_tx(db_mbar_t*, unsigned) {}
-__device__ __forceinline__ void db_bulk_g2s(void* dst, const void* src, unsigned bytes, db_mbar_t*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void db_mbar_wait(db_mbar_t*, unsigned) {}
+__device__ __forceinline__ void db_mbar_expect_tx(db_mbar_t* bar, unsigned bytes) { *bar += bytes; }
+__device__ __forceinline__ void db_bulk_g2s(void* dst, const void* src, unsigned bytes, db_mbar_t* bar)
+{
+    memcpy(dst, src, bytes);
+    *bar -= bytes;
+    if ((*bar & 0xffffffffull) == 0) *bar += 1ull << 32;
+}
+__device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
+{
+    while ((((*bar) >> 32) & 1ull) == parity) emu_yield();
+}
 #else
 typedef unsigned long long db_mbar_t;
 __device__ __forceinline__ unsigned db_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

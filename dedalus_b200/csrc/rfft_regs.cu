@@ -378,9 +378,12 @@ struct ChebArgs {
     const double* twn;      // exp(-2 pi i j / n)
     const double* twq;      // exp(-i pi k / (2 n))
     const double* diags;    // forward: conversion diagonals [nd][M]
+    const double* pre;      // backward: derivative diagonals [npre][M] applied first (npre <= 3), or null
+    const double* sol2;     // backward: [2][M] reciprocal diagonal and second super-diagonal of the back-conversion, or null
     int64_t lines;
     int32_t M;              // coefficient size (even, <= n)
     int32_t nd;
+    int32_t npre;
 };
 
 #define CH_LINES (2 * RR_P)
@@ -409,6 +412,53 @@ k_chbwd_regs(ChebArgs a)
         db_cp_wait<0>();
     }
     __syncthreads();
+    if (a.sol2 != nullptr) {
+        // derivative + ultraspherical back-conversion in place on the staged lines (same suffix scan as k_band_scan2 in
+        // fft.cu: x_i = r_i (t_i - u_i x_{i+2}), t = banded pre-apply of the coefficients), one warp per line
+        const int lane = tid & 31, w = tid >> 5, nw = nthreads >> 5;
+        const double* __restrict__ pre = a.pre;
+        const double* __restrict__ sol = a.sol2;
+        const int npre = a.npre, rounds = (M + 63) / 64;
+        for (int l = w; l < CH_LINES; l += nw) {
+            double* xl = X + l * LX;
+            double carry0 = 0.0, carry1 = 0.0, nx0 = 0.0, nx1 = 0.0;     // nx: ORIGINAL c[i0+2], c[i0+3] of the round above
+            for (int q = rounds - 1; q >= 0; --q) {
+                const int i0 = 2 * (32 * q + lane);
+                const double c0 = (i0 < M) ? xl[i0] : 0.0, c1 = (i0 + 1 < M) ? xl[i0 + 1] : 0.0;
+                double c2 = __shfl_down_sync(0xffffffffu, c0, 1), c3 = __shfl_down_sync(0xffffffffu, c1, 1);
+                if (lane == 31) { c2 = nx0; c3 = nx1; }
+                nx0 = __shfl_sync(0xffffffffu, c0, 0); nx1 = __shfl_sync(0xffffffffu, c1, 0);
+                double t0 = c0, t1 = c1;
+                if (npre > 0) {
+                    t0 = 0.0; t1 = 0.0;
+                    if (i0 < M) {
+                        t0 = pre[i0] * c0;
+                        if (npre > 1) t0 = fma(pre[M + i0], c1, t0);
+                        if (npre > 2) t0 = fma(pre[2 * M + i0], c2, t0);
+                    }
+                    if (i0 + 1 < M) {
+                        t1 = pre[i0 + 1] * c1;
+                        if (npre > 1) t1 = fma(pre[M + i0 + 1], c2, t1);
+                        if (npre > 2) t1 = fma(pre[2 * M + i0 + 1], c3, t1);
+                    }
+                }
+                double A0 = 0.0, B0 = 0.0, A1 = 0.0, B1 = 0.0;
+                if (i0 < M) { const double rr = sol[i0]; B0 = rr * t0; A0 = (i0 + 2 < M) ? -rr * sol[M + i0] : 0.0; }
+                if (i0 + 1 < M) { const double rr = sol[i0 + 1]; B1 = rr * t1; A1 = (i0 + 3 < M) ? -rr * sol[M + i0 + 1] : 0.0; }
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double a0 = __shfl_down_sync(0xffffffffu, A0, off), b0 = __shfl_down_sync(0xffffffffu, B0, off);
+                    const double a1 = __shfl_down_sync(0xffffffffu, A1, off), b1 = __shfl_down_sync(0xffffffffu, B1, off);
+                    if (lane + off < 32) { B0 = fma(A0, b0, B0); A0 *= a0; B1 = fma(A1, b1, B1); A1 *= a1; }
+                }
+                const double x0 = fma(A0, carry0, B0), x1 = fma(A1, carry1, B1);
+                if (i0 < M) xl[i0] = x0;
+                if (i0 + 1 < M) xl[i0 + 1] = x1;
+                carry0 = __shfl_sync(0xffffffffu, x0, 0); carry1 = __shfl_sync(0xffffffffu, x1, 0);
+            }
+        }
+        __syncthreads();
+    }
     // ---- spectrum of the packed line pairs: Y[k][p] = Z_k
     {
         const double c0 = 0.56418958354775628694807945156077;     // 1/sqrt(pi)
@@ -710,10 +760,11 @@ int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double
 }
 
 // Chebyshev on contiguous lines (inner == 1): returns -1 if not covered (generic kernel in fft.cu takes over).
-// backward: plain DCT-III only (derivative / back-conversion are applied beforehand by db_band_lines);
+// backward: plain DCT-III, optionally preceded (in shared memory) by the derivative pre-apply + the back-substitution
+// of a conversion with only the main and the second super-diagonal (`sol2`, compact storage as db_band_lines stride 2);
 // forward: conversion diagonals fused into the store.
 int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t lines, int32_t n_coeff,
-                     const double* diags, int32_t nd, void* stream)
+                     const double* diags, int32_t nd, const double* pre, int32_t npre, const double* sol2, void* stream)
 {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("DB_CHEB_REGS"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
@@ -724,6 +775,8 @@ int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
     ChebArgs a;
     a.in = in; a.out = out; a.twn = plan->twn; a.twq = plan->twq; a.diags = diags; a.lines = lines; a.M = n_coeff; a.nd = nd;
+    a.pre = pre; a.npre = npre; a.sol2 = sol2;
+    if (npre > 3 || (npre > 0 && sol2 == nullptr)) return -1;
     ++g_regs_launches;
     switch (n) {
         case 384: return launch_cheb<8, 16>(fwd, a, stream);

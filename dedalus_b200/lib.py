@@ -57,6 +57,7 @@ SIGNATURES = {
     "db_cfft_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, vp]),
     "db_cheb_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp, i32, vp]),
     "db_cheb_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp, i32, vp, i32, vp]),
+    "db_cheb_backward_scan": (C.c_int, [PFFT, vp, vp, i64, i32, vp, i32, vp, vp]),
     "db_band_lines": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i32, i32, vp]),
     "db_mmt_apply": (C.c_int, [vp, i32, i32, vp, vp, i64, i64, vp]),
     "db_pointwise": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp]),
@@ -110,6 +111,17 @@ class BoundLib:
         if rc != 0:
             msg = self._raw_db_last_error()
             raise DedalusB200Error(f"{name} failed (code {rc}): {msg.decode() if msg else ''}")
+
+    def call_optional(self, name, *args):
+        """For entries that may decline a case: True if it ran, False if it returned 2 ("not covered")."""
+        rc = getattr(self, "_raw_" + name)(*args)
+        if rc == 2:
+            return False
+        self.launches += 1
+        if rc != 0:
+            msg = self._raw_db_last_error()
+            raise DedalusB200Error(f"{name} failed (code {rc}): {msg.decode() if msg else ''}")
+        return True
 
     def version(self):
         return self._raw_db_version()

@@ -206,8 +206,13 @@ class FastChebyshevTransform:
         if inner == 1 and (npre or nsol) and self.M <= self.N:
             # contiguous lines: run the serial banded recurrence in its own one-thread-per-line kernel, then the
             # plain transform (keeps the recurrence off the FFT kernel's critical path)
-            tmp = self._scratch(cdata)
             compact = self._dev.get((('solve2', deriv), str(gdata.device))) if (nsol and npre <= 3) else None
+            if compact is not None and cdata.data_ptr() % 16 == 0 and gdata.data_ptr() % 16 == 0:
+                # derivative + back-conversion + transform in one kernel (the scan runs on the lines staged in shared memory)
+                if get_lib().call_optional("db_cheb_backward_scan", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M,
+                                           _dptr(pre), npre, _dptr(compact[0]), _stream()):
+                    return
+            tmp = self._scratch(cdata)
             if compact is not None and cdata.data_ptr() % 16 == 0:
                 get_lib().call("db_band_lines", _dptr(cdata), _dptr(tmp), outer, self.M, _dptr(pre), npre, _dptr(compact[0]), 2, 2, _stream())
             else:

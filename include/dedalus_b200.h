@@ -72,6 +72,14 @@ int db_cheb_forward(const db_fft_plan* plan, const double* g, double* c, int64_t
 int db_cheb_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
                      const double* pre_diags, int32_t pre_ndiag, const double* solve_diags, int32_t solve_ndiag, void* stream);
 
+/* db_cheb_backward on contiguous lines with the derivative pre-apply (pre_ndiag <= 3) and the back-substitution of a
+ * conversion that has only its main and second super-diagonal fused in (solve2_diags: [2][n_coeff], row 0 = reciprocal
+ * diagonal, row 1 = second super-diagonal -- the stride-2 storage of db_band_lines).  Same result as db_band_lines followed
+ * by db_cheb_backward, without the intermediate array.  Returns 2 (and records no error) when the size / alignment is
+ * not covered by the fused kernel. */
+int db_cheb_backward_scan(const db_fft_plan* plan, const double* c, double* g, int64_t lines, int32_t n_coeff,
+                          const double* pre_diags, int32_t pre_ndiag, const double* solve2_diags, void* stream);
+
 /* Banded coefficient-space work along CONTIGUOUS lines (inner == 1), used ahead of db_cheb_backward when a spectral
  * derivative / ultraspherical back-conversion is fused in: out = solve_upper(solve_diags, apply(pre_diags, in)).
  * One thread per line with the line staged in shared memory: decouples the O(n) serial recurrence from the FFT

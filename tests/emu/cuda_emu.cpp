@@ -28,20 +28,34 @@ void fiber_entry() {
 }
 }  // namespace
 
-void emu_syncthreads() {
+// one scheduling step: give the other fibers of the block a turn
+void emu_yield() {
     Fiber* f = running;
     f->st = emu_cur;
     swapcontext(&f->ctx, &sched_ctx);
     emu_cur = f->st;
 }
 
+// block barrier: a real arrival count (threads that already exited count as arrived, as on the GPU), so that code
+// between two barriers may yield a different number of times in different warps (warp shuffles, see below)
+static thread_local size_t bar_arrived = 0, bar_generation = 0, bar_live = 0;
+static void bar_release_if_complete() {
+    if (bar_live > 0 && bar_arrived >= bar_live) { bar_arrived = 0; ++bar_generation; }
+}
+void emu_syncthreads() {
+    const size_t gen = bar_generation;
+    ++bar_arrived;
+    bar_release_if_complete();
+    while (bar_generation == gen) emu_yield();
+}
+
 static double shfl_slots[4096];
 double emu_shfl_exchange(double v, int src_lane) {
     const unsigned tid = emu_cur.tid.x;            // 1-D blocks only
     shfl_slots[tid] = v;
-    emu_syncthreads();
+    emu_yield();                                   // every lane of the warp has published (lanes run in lockstep)
     const double r = shfl_slots[(tid & ~31u) + (unsigned)src_lane];
-    emu_syncthreads();
+    emu_yield();                                   // every lane has read before any slot is overwritten
     return r;
 }
 
@@ -70,6 +84,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
             makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
         size_t remaining = nthreads;
+        bar_arrived = 0; bar_live = nthreads;
         while (remaining) {
             size_t finished_this_round = 0, waiting = 0;
             for (auto& f : fibers) {
@@ -77,7 +92,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
                 running = &f;
                 emu_cur = f.st;
                 swapcontext(&sched_ctx, &f.ctx);
-                if (f.done) { ++finished_this_round; } else { ++waiting; }
+                if (f.done) { ++finished_this_round; --bar_live; bar_release_if_complete(); } else { ++waiting; }
             }
             remaining -= finished_this_round;
             if (finished_this_round && waiting) {

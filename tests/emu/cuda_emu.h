@@ -47,6 +47,7 @@ extern thread_local EmuState emu_cur;           // state of the running fiber
 #define gridDim (emu_cur.gdim)
 
 void emu_syncthreads();
+void emu_yield();          // one scheduling step (used by the emulated mbarrier wait and warp shuffles)
 #define __syncthreads() emu_syncthreads()
 #define __syncwarp(...) ((void)0)
 // warp shuffles: every lane of the warp publishes its value, yields once (all live fibers advance one step per

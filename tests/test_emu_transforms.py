@@ -223,3 +223,24 @@ def test_register_resident_chebyshev(M, N, alpha):
     assert lib.rfft_regs_launches() == served + 2
     ref = T.cheb_forward_fft(gr, M, 1, a, a)
     assert np.allclose(out, ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("M,N", [(256, 384), (64, 96), (16, 24), (50, 96)])
+@pytest.mark.parametrize("npre", [0, 2])
+def test_chebyshev_backward_with_fused_derivative_scan(M, N, npre):
+    """db_cheb_backward_scan == db_band_lines (stride-2 scan) followed by db_cheb_backward, bit for bit up to rounding."""
+    lib = E.emu(); plan = E.EmuPlan(N, 'real')
+    rng = np.random.default_rng(M + npre)
+    lines = 19
+    c = rng.standard_normal((lines, M))
+    Cm = jacobi.conversion_matrix(M, -0.5, -0.5, 0.5, 0.5).toarray()
+    sol2 = np.zeros((2, M)); sol2[0] = 1.0 / np.diag(Cm); sol2[1, :M - 2] = np.diag(Cm, 2)
+    pre = np.zeros((max(npre, 1), M))
+    for d in range(npre):
+        pre[d, :M - d] = rng.standard_normal(M - d)
+    pre_ptr = E.ptr(pre) if npre else None
+    tmp = np.full_like(c, np.nan); ref = np.full((lines, N), np.nan); out = np.full((lines, N), np.nan)
+    lib.call("db_band_lines", E.ptr(c), E.ptr(tmp), lines, M, pre_ptr, npre, E.ptr(sol2), 2, 2, None)
+    lib.call("db_cheb_backward", plan.ref(), E.ptr(tmp), E.ptr(ref), lines, M, 1, None, 0, None, 0, None)
+    assert lib.call_optional("db_cheb_backward_scan", plan.ref(), E.ptr(c), E.ptr(out), lines, M, pre_ptr, npre, E.ptr(sol2), None)
+    assert np.allclose(out, ref, rtol=0, atol=1e-12 * np.abs(ref).max())

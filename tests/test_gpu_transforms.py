@@ -177,3 +177,22 @@ def test_register_resident_chebyshev(M, N, alpha):
     assert get_lib().rfft_regs_launches() == served + 2
     ref = T.cheb_forward_fft(gr, M, 2, a, a)
     assert np.allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("M,N", [(256, 384), (64, 96), (16, 24)])
+def test_chebyshev_derivative_fused_scan_matches_matrices(M, N):
+    """backward(deriv=1) on contiguous lines takes db_cheb_backward_scan (derivative + back-conversion by a warp scan on
+    the staged lines + DCT-III in one kernel); reference: differentiation matrix then the plain oracle transform."""
+    import torch
+    from dedalus_b200.transforms import FastChebyshevTransform
+    from dedalus_b200 import jacobi
+    rng = np.random.default_rng(M)
+    stretch = 0.5
+    plan = FastChebyshevTransform(N, M, -0.5, -0.5, -0.5, -0.5, stretch=stretch)
+    c = rng.standard_normal((37, M))
+    out = torch.full((37, N), float('nan'), dtype=torch.float64, device='cuda')
+    plan.backward(_t(c), out, 1, deriv=1)
+    dc = (jacobi.differentiation_matrix(M, -0.5, -0.5) / stretch @ c.T).T
+    z = jacobi.gauss_grid(N, -0.5, -0.5)[0]
+    ref = dc @ jacobi.polynomials(M, 0.5, 0.5, z)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
