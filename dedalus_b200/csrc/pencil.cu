@@ -496,55 +496,73 @@ __device__ __forceinline__ MvTerm mv_load(const db_term* __restrict__ rec, int t
     MvTerm r; r.val = __hiloint2double(raw.y, raw.x); r.col_off = raw.z; r.mono = raw.w; return r;
 #endif
 }
-#define MV_THREADS 64
+// y = (sum_m mono_m T_m) x for the M and L templates of all batches.  One CTA = one 64-system tile x MV_R consecutive rows,
+// 256 threads = 4 row groups x 64 systems.  The operators are banded in the mode-major row / column order, so the x rows
+// a row block needs form a window of ~2 MV_R rows: it is staged ONCE in shared memory (16-byte cp.async) together with the
+// block's term records and the tile's monomial values, and the term loop then runs entirely out of shared memory (ncu on
+// the previous version: x re-read through L2 with a 25 % L1 hit rate, 20 long-scoreboard stalls per issue).  The few terms
+// outside the window (dense boundary rows) read x from global memory.
+#define MV_R 32
+#define MV_GROUPS 4
+#define MV_THREADS (64 * MV_GROUPS)
+#define MV_WMAX 80
+#define MV_RECMAX 768
+#define MV_SMEM_BYTES ((MV_WMAX * 64 + MV_MAX_MONO * 64) * 8 + MV_RECMAX * 16)
 __global__ void __launch_bounds__(MV_THREADS)
 k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, int ym_slot, int yl_slot)
 {
-    // y = (sum_m mono_m T_m) x for the M and L templates.  One thread owns TWO adjacent systems (adjacent in memory in
-    // the tile-major vectors: one 16-byte load / store serves both), one CTA = 128 systems x B.mv_rows consecutive rows.
-    // Terms are 16-byte records read with one warp-uniform load each; the systems' monomial values (powers of their
-    // wavenumbers) sit in shared memory, one private column per thread.  Per term and pair of systems: one record load,
-    // one x load, one shared load, four flops.
-    DB_SMEM(double2, monos);                      // [MV_MAX_MONO][MV_THREADS]
+    DB_SMEM(double, win);                                   // [MV_WMAX][64] x window, then monomials [MV_MAX_MONO][64], then records
+    double* monos = win + MV_WMAX * 64;
+    db_term* recs = reinterpret_cast<db_term*>(monos + MV_MAX_MONO * 64);
     const int bi = find_batch(batches, nbatch, blockIdx.x, 1);
     const db_batch& B = batches[bi];
     const int local = blockIdx.x - B.blk_matvec;
-    const int sblocks = (B.S + 2 * MV_THREADS - 1) / (2 * MV_THREADS);
-    const int s = (local % sblocks) * (2 * MV_THREADS) + 2 * threadIdx.x;        // even system of the pair
-    if (s >= B.S) return;
-    const int r0 = (local / sblocks) * B.mv_rows;
+    const int tiles = (B.S + 63) / 64;
+    const int tile = local % tiles, rb = local / tiles;
     const int n = B.n, ld = B.ld;
-    const int r1 = (r0 + B.mv_rows < n) ? r0 + B.mv_rows : n;
-    const int64_t tb = db_tbase(s, n);
-    const double* __restrict__ x = B.vec[x_slot] + tb;
+    const int r0 = rb * MV_R, r1 = (r0 + MV_R < n) ? r0 + MV_R : n;
+    const int tid = threadIdx.x, sl = tid & 63, g = tid >> 6;
+    const int64_t tile_base = (int64_t)tile * n * DB_TILE;
+    const double* __restrict__ xt = B.vec[x_slot] + tile_base;
+    const int w0 = B.mv_win[2 * rb], wl = B.mv_win[2 * rb + 1];
+    const bool do_m = ym_slot >= 0, do_l = yl_slot >= 0;
+    const int m0 = B.m_ptr[r0], m1 = B.m_ptr[r1], l0 = B.l_ptr[r0], l1 = B.l_ptr[r1];
+    const int nm_rec = do_m ? m1 - m0 : 0, nl_rec = do_l ? l1 - l0 : 0;
+    const bool staged = nm_rec + nl_rec <= MV_RECMAX;
+    // ---- stage: x window (16-byte chunks), monomials of this tile, term records
+    for (int idx = tid; idx < wl * 32; idx += MV_THREADS)
+        db_cp_async16(win + 2 * idx, xt + (int64_t)w0 * DB_TILE + 2 * idx);
     const int nm = B.n_mono < MV_MAX_MONO ? B.n_mono : MV_MAX_MONO;
-    double2* mine = monos + threadIdx.x;
-    for (int m = 0; m < nm; ++m) mine[m * MV_THREADS] = *reinterpret_cast<const double2*>(B.mono + (int64_t)m * ld + s);
+    for (int idx = tid; idx < nm * 32; idx += MV_THREADS)
+        db_cp_async16(monos + 2 * idx, B.mono + (int64_t)(idx >> 5) * ld + tile * 64 + 2 * (idx & 31));
+    if (staged) {
+        for (int idx = tid; idx < nm_rec; idx += MV_THREADS) db_cp_async16(recs + idx, B.m_rec + m0 + idx);
+        for (int idx = tid; idx < nl_rec; idx += MV_THREADS) db_cp_async16(recs + nm_rec + idx, B.l_rec + l0 + idx);
+    }
+    db_cp_commit();
+    db_cp_wait<0>();
+    __syncthreads();
+    const double* xs = win + sl;
+    const double* ms = monos + sl;
+    const double* __restrict__ xg = xt + sl;
     for (int which = 0; which < 2; ++which) {
         const int slot = which ? yl_slot : ym_slot;
         if (slot < 0) continue;
         const int32_t* __restrict__ ptr = which ? B.l_ptr : B.m_ptr;
-        const db_term* __restrict__ rec = which ? B.l_rec : B.m_rec;
-        double* __restrict__ y = B.vec[slot] + tb;
-        int t = ptr[r0];
-        for (int i = r0; i < r1; ++i) {
+        const db_term* rec = staged ? (recs + (which ? nm_rec - l0 : -m0)) : (which ? B.l_rec : B.m_rec);
+        double* __restrict__ y = B.vec[slot] + tile_base + sl;
+        for (int i = r0 + g; i < r1; i += MV_GROUPS) {
+            int t = ptr[i];
             const int t1 = ptr[i + 1];
-            double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-            for (; t + 2 <= t1; t += 2) {
-                const MvTerm a = mv_load(rec, t), b = mv_load(rec, t + 1);
-                const double2 xa = *reinterpret_cast<const double2*>(x + a.col_off), xb = *reinterpret_cast<const double2*>(x + b.col_off);
-                const double2 ma = mine[a.mono * MV_THREADS], mb = mine[b.mono * MV_THREADS];
-                acc0.x = fma(a.val * ma.x, xa.x, acc0.x); acc0.y = fma(a.val * ma.y, xa.y, acc0.y);
-                acc1.x = fma(b.val * mb.x, xb.x, acc1.x); acc1.y = fma(b.val * mb.y, xb.y, acc1.y);
+            double acc0 = 0.0, acc1 = 0.0;
+            for (; t < t1; ++t) {
+                const db_term a = rec[t];
+                const int c = a.col_off >> 6;                 // column = col_off / DB_TILE
+                const double xv = ((unsigned)(c - w0) < (unsigned)wl) ? xs[(c - w0) * 64] : xg[a.col_off];
+                const double p = a.val * ms[a.mono * 64];
+                if (t & 1) acc1 = fma(p, xv, acc1); else acc0 = fma(p, xv, acc0);
             }
-            if (t < t1) {
-                const MvTerm a = mv_load(rec, t);
-                const double2 xa = *reinterpret_cast<const double2*>(x + a.col_off);
-                const double2 ma = mine[a.mono * MV_THREADS];
-                acc0.x = fma(a.val * ma.x, xa.x, acc0.x); acc0.y = fma(a.val * ma.y, xa.y, acc0.y);
-                ++t;
-            }
-            *reinterpret_cast<double2*>(y + (int64_t)i * DB_TILE) = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
+            y[(int64_t)i * DB_TILE] = acc0 + acc1;
         }
     }
 }
@@ -552,7 +570,15 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
 extern "C" int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t x_slot, int32_t ym_slot, int32_t yl_slot, void* stream)
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
-    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(MV_THREADS), MV_MAX_MONO * MV_THREADS * sizeof(double2), stream, batches, nbatch, x_slot, ym_slot, yl_slot);
+#ifndef DB_EMU
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_batches_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_batches_matvec, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr = true;
+    }
+#endif
+    DB_LAUNCH(k_batches_matvec, dim3(total_blocks), dim3(MV_THREADS), MV_SMEM_BYTES, stream, batches, nbatch, x_slot, ym_slot, yl_slot);
     return db_check_launch("batches_matvec");
 }
 

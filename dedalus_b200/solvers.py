@@ -41,6 +41,27 @@ class Timed:
         return False
 
 
+def matvec_windows(prog, R, wmax):
+    """Per block of R rows: [first column, count] of the x window staged in shared memory by k_batches_matvec -- the
+    densest run of at most `wmax` columns among the terms of the block's rows (both operators); columns of the dense
+    boundary rows mostly fall outside and are read from global memory."""
+    n = prog.n
+    out = np.zeros((-(-n // R), 2), dtype=np.int32)
+    for rb in range(out.shape[0]):
+        r0, r1 = rb * R, min(n, (rb + 1) * R)
+        cols = np.concatenate([np.asarray(prog.mv[k][1][prog.mv[k][0][r0]:prog.mv[k][0][r1]], dtype=np.int64) for k in ('M', 'L')])
+        if cols.size == 0:
+            continue
+        cols.sort()
+        # window start maximising the number of terms covered
+        hi = np.searchsorted(cols, cols + wmax, side='left')
+        best = int(np.argmax(hi - np.arange(cols.size)))
+        w0 = int(cols[best]); w1 = min(n, w0 + wmax)
+        w1 = min(w1, int(cols[-1]) + 1)
+        out[rb] = (w0, w1 - w0)
+    return out
+
+
 class DeviceBatch:
     """Device copies of one batch's programs and work vectors (kept alive for the fused descriptors)."""
 
@@ -64,6 +85,7 @@ class DeviceBatch:
             rec = np.zeros(len(col), dtype=np.dtype([('val', '<f8'), ('col_off', '<i4'), ('mono', '<i4')]))     # db_term
             rec['val'], rec['col_off'], rec['mono'] = val, np.asarray(col, dtype=np.int64) * prog.tile, mono_i
             self.t[k + '_rec'] = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()).to(dev)
+        self.t['mv_win'] = f(matvec_windows(prog, 32, 80).ravel())
         self.maps = []
         for side, arena in (('cols', solver.var_arena), ('rows', solver.eq_arena)):
             m = line_maps(batch, arena, side)
@@ -102,19 +124,16 @@ class BatchSet:
         self.nb = len(self.items)
         arr = (CBatch * max(self.nb, 1))()
         blk = dict(solve=0, matvec=0, move0=0, move1=0, asm=0)
-        pair_tiles_total = sum((db.S + 127) // 128 for db in self.items)
         for i, db in enumerate(self.items):
             c = arr[i]
+            t_ = db.t
             c.n, c.S, c.ld, c.n_entries = db.n, db.S, db.ld, db.prog.nE
             c.n_fwd, c.n_bwd = db.prog.n_fwd, db.prog.nE - db.prog.n_fwd
             c.blk_solve = blk['solve']; blk['solve'] += (db.S + 63) // 64
-            # mat-vec CTAs: 128 systems (two per thread) x mv_rows consecutive rows (csrc/pencil.cu k_batches_matvec).
-            # Long row runs re-use the x window in L1 (measured at 256^3: 64 -> 3.76, 128 -> 3.70, 320 -> 3.48 ms/step) but
-            # need enough 128-system tiles to fill the GPU; with few tiles per rank (multi-GPU) fall back to 64-row CTAs.
-            mv_rows = 320 if pair_tiles_total * 4 >= 148 * 8 else 64
-            mv_rows = int(os.environ.get("DB_MV_ROWS", mv_rows))
-            c.mv_rows = mv_rows
-            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 127) // 128) * (-(-db.n // mv_rows))
+            # mat-vec CTAs: one 64-system tile x 32 consecutive rows, x window in shared memory (csrc/pencil.cu k_batches_matvec)
+            c.mv_rows = 32
+            c.mv_win = t_['mv_win'].data_ptr()
+            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 63) // 64) * (-(-db.n // 32))
             c.blk_assemble = blk['asm']; blk['asm'] += ((db.S + 127) // 128) * ((db.prog.nE + 63) // 64)
             for side in (0, 1):
                 m = db.maps[side]

@@ -7,6 +7,7 @@ torch CUDA tensors (float64, or complex128 for ComplexFourier) and the work is o
 (csrc/fft.cu) per call; results are written into the output tensor, which must not alias the input.
 """
 import ctypes as C
+import os
 import numpy as np
 from . import jacobi
 from .lib import get_lib, FftPlan, DedalusB200Error
@@ -120,6 +121,9 @@ class ComplexFourierTransform:
         get_lib().call("db_cfft_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner, int(deriv), float(self.kscale), _stream())
 
 
+_FUSED_SCAN = os.environ.get("DB_CHEB_FUSED_SCAN", "0") == "1"
+
+
 def banded_upper_diags(mat, M, ndiag):
     """Diagonals 0..ndiag-1 of a sparse upper-triangular matrix, rows < M, as (ndiag, M) float64."""
     A = mat.tocsr()
@@ -207,8 +211,10 @@ class FastChebyshevTransform:
             # contiguous lines: run the serial banded recurrence in its own one-thread-per-line kernel, then the
             # plain transform (keeps the recurrence off the FFT kernel's critical path)
             compact = self._dev.get((('solve2', deriv), str(gdata.device))) if (nsol and npre <= 3) else None
-            if compact is not None and cdata.data_ptr() % 16 == 0 and gdata.data_ptr() % 16 == 0:
-                # derivative + back-conversion + transform in one kernel (the scan runs on the lines staged in shared memory)
+            if _FUSED_SCAN and compact is not None and cdata.data_ptr() % 16 == 0 and gdata.data_ptr() % 16 == 0:
+                # derivative + back-conversion + transform in one kernel (the scan runs on the lines staged in shared
+                # memory).  Opt-in (DB_CHEB_FUSED_SCAN=1): measured at 256^3 it is not faster than the separate scan
+                # kernel -- 16 lines per CTA leave most warps idle during the scan (z backward 3.11 vs 2.98 ms per step)
                 if get_lib().call_optional("db_cheb_backward_scan", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M,
                                            _dptr(pre), npre, _dptr(compact[0]), _stream()):
                     return

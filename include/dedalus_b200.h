@@ -195,7 +195,8 @@ typedef struct {
     const int32_t* ctrl;               /* [n_entries/16][36] per-chunk control blocks of the branch-free solve kernel:
                                           gather offsets[16], finished-row offsets[16], masks end / begin / late, 0  */
     int32_t n_mono;
-    int32_t mv_rows;                   /* rows per CTA of the fused mat-vec (multiple of 64; n rounded up = one CTA per tile) */
+    int32_t mv_rows;                   /* rows per CTA of the fused mat-vec (= 32, MV_R in csrc/pencil.cu) */
+    const int32_t* mv_win;             /* [ceil(n / mv_rows)][2]: first x row and row count (<= 80) of the shared-memory window of each row block */
     const int64_t* line_base[2]; const int32_t* line_kind[2]; const int32_t* line_ptr[2]; const int32_t* line_pos[2];
     const int64_t* sys_off[2];
     /* factorisation programs */
