@@ -682,7 +682,8 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
 // host side
 // ---------------------------------------------------------------------------------------------------------
 int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
-                     int64_t inner, int32_t deriv, double kscale, void* stream);       // rfft_regs.cu
+                     int64_t inner, int32_t deriv, double kscale, void* stream,
+                     int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride);       // rfft_regs.cu
 int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t lines, int32_t n_coeff,
                      const double* diags, int32_t nd, const double* pre, int32_t npre, const double* sol2, void* stream);
 
@@ -695,7 +696,7 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
     if (plan->n <= 0 || plan->nc <= 0 || n_coeff <= 0) { db_set_error("%s: bad sizes", name); return 1; }
     if (KIND == K_RFWD || KIND == K_RBWD) {
         // dealiased sizes on a strided axis: register-resident two-stage kernels (rfft_regs.cu)
-        const int rc = db_rfft_regs_try(KIND == K_RFWD, plan, in, out, outer, n_coeff, inner, deriv, kscale, stream);
+        const int rc = db_rfft_regs_try(KIND == K_RFWD, plan, in, out, outer, n_coeff, inner, deriv, kscale, stream, 0, 0, 0, 0);
         if (rc >= 0) return rc;
     }
     if ((KIND == K_CHFWD || (KIND == K_CHBWD && nda == 0 && ndb == 0)) && inner == 1) {
@@ -760,6 +761,24 @@ extern "C" int db_rfft_forward(const db_fft_plan* plan, const double* g, double*
 extern "C" int db_rfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
                                 int32_t deriv, double kscale, void* stream)
 { return launch_fft<K_RBWD>(plan, c, g, outer, n_coeff, inner, deriv, kscale, nullptr, 0, nullptr, 0, stream, "rfft_backward"); }
+
+// Blocked variants (X1): see include/dedalus_b200.h.  Only the register-resident kernels implement them; 2 = not covered.
+extern "C" int db_rfft_forward_blocked(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner,
+                                       int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride, void* stream)
+{
+    if (outer <= 0 || inner <= 0) return 0;
+    const int rc = db_rfft_regs_try(true, plan, g, c, outer, n_coeff, inner, 0, 0.0, stream, in_rpb, in_blk_stride, out_rpb, out_blk_stride);
+    return rc < 0 ? 2 : rc;
+}
+
+extern "C" int db_rfft_backward_blocked(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                                        int32_t deriv, double kscale,
+                                        int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride, void* stream)
+{
+    if (outer <= 0 || inner <= 0) return 0;
+    const int rc = db_rfft_regs_try(false, plan, c, g, outer, n_coeff, inner, deriv, kscale, stream, in_rpb, in_blk_stride, out_rpb, out_blk_stride);
+    return rc < 0 ? 2 : rc;
+}
 
 extern "C" int db_cfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream)
 { return launch_fft<K_CFWD>(plan, g, c, outer, n_coeff, inner, 0, 0.0, nullptr, 0, nullptr, 0, stream, "cfft_forward"); }

@@ -28,7 +28,19 @@ struct RegArgs {
     int32_t M;              // coefficient rows (even, <= 2n/3)
     int32_t deriv;
     double kscale;
+    // Blocked row addressing (pencil transposes without pack / unpack kernels, X1): with rpb > 0 row r of outer index o
+    // lives at (r / rpb) * blk_stride + (o * rpb + r % rpb) * inner, i.e. the rows are grouped into the per-peer blocks
+    // of an all-to-all send buffer (output side) or receive buffer (input side).  rpb = 0: plain (o * rows + r) * inner.
+    int32_t in_rpb, out_rpb;
+    int64_t in_blk_stride, out_blk_stride;
 };
+
+__device__ __forceinline__ int64_t row_offset(int64_t o, int r, int rows, int rpb, int64_t blk_stride, int64_t inner)
+{
+    if (rpb == 0) return (o * rows + r) * inner;
+    const int blk = r / rpb;
+    return (int64_t)blk * blk_stride + (o * rpb + (r - blk * rpb)) * inner;
+}
 
 __device__ __forceinline__ double2 cadd2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub2(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -110,11 +122,13 @@ struct TileWalk {
 };
 
 // stage `rows` rows of 16 doubles (row stride `inner`) into buf[row][16]
-__device__ __forceinline__ void stage_rows(double* buf, const double* __restrict__ src, int rows, int64_t inner)
+__device__ __forceinline__ void stage_rows(double* buf, const double* __restrict__ src, int64_t o, int rows, int rpb,
+                                           int64_t blk_stride, int64_t inner)
 {
+    // src already points at the tile's first column; row r of outer index o is at row_offset(...)
     for (int idx = threadIdx.x; idx < rows * 8; idx += blockDim.x) {
         const int row = idx >> 3, seg = idx & 7;
-        db_cp_async16(buf + row * 16 + seg * 2, src + (int64_t)row * inner + seg * 2);
+        db_cp_async16(buf + row * 16 + seg * 2, src + row_offset(o, row, rows, rpb, blk_stride, inner) + seg * 2);
     }
 }
 
@@ -163,19 +177,19 @@ k_rbwd_regs(RegArgs a, TileWalk tw_)
     const double ur = ((deriv & 3) == 0) ? 1.0 : ((deriv & 3) == 2) ? -1.0 : 0.0;
     const double ui = ((deriv & 3) == 1) ? 1.0 : ((deriv & 3) == 3) ? -1.0 : 0.0;
     const double* __restrict__ tw = a.twn;
-    auto tile_src = [&](int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
-                                     return a.in + o * M * inner + xt * (2 * P); };
+    auto stage_tile = [&](double2* buf, int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
+        stage_rows(reinterpret_cast<double*>(buf), a.in + xt * (2 * P), o, M, a.in_rpb, a.in_blk_stride, inner); };
     const bool in_a = r < 3 * NB, in_b = r < 2 * NA;
     const int n2 = r % NB, c = r / NB;                       // stage A role
     const int k1 = r % NA, h = r / NA;                       // stage B role
     int64_t t = blockIdx.x;
     int cur = 0;
-    if (t < tw_.total) stage_rows(reinterpret_cast<double*>(sm), tile_src(t), M, inner);
+    if (t < tw_.total) stage_tile(sm, t);
     db_cp_commit();
     for (; t < tw_.total; t += gridDim.x, cur ^= 1) {
         double2* in = sm + cur * (N * P);
         const int64_t tn = t + gridDim.x;
-        if (tn < tw_.total) stage_rows(reinterpret_cast<double*>(sm + (cur ^ 1) * (N * P)), tile_src(tn), M, inner);
+        if (tn < tw_.total) stage_tile(sm + (cur ^ 1) * (N * P), tn);
         db_cp_commit();
         db_cp_wait<1>();
         __syncthreads();
@@ -233,10 +247,10 @@ k_rbwd_regs(RegArgs a, TileWalk tw_)
             }
             DftP2<H, true>::run(v);
             const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
-            double* __restrict__ gout = a.out + (o * N + k1 + NA * h) * inner + xt * (2 * P) + 2 * p;
+            double* __restrict__ gout = a.out + xt * (2 * P) + 2 * p;
 #pragma unroll
             for (int m = 0; m < H; ++m)
-                *reinterpret_cast<double2*>(gout + (int64_t)(2 * NA * m) * inner) = v[m];
+                *reinterpret_cast<double2*>(gout + row_offset(o, k1 + NA * (2 * m + h), N, a.out_rpb, a.out_blk_stride, inner)) = v[m];
         }
         __syncthreads();                                           // exchange reads done before the next prefetch lands here
     }
@@ -269,19 +283,19 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
     const int64_t inner = a.inner;
     const int M = a.M, Kmax = (a.M - 1) / 2;
     const double* __restrict__ tw = a.twn;
-    auto tile_src = [&](int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
-                                     return a.in + o * N * inner + xt * (2 * P); };
+    auto stage_tile = [&](double2* buf, int64_t t) { const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
+        stage_rows(reinterpret_cast<double*>(buf), a.in + xt * (2 * P), o, N, a.in_rpb, a.in_blk_stride, inner); };
     const bool in_1 = r < 2 * NA, in_2 = r < 3 * NB;
     const int j1 = r % NA, h = r / NA;                       // stage 1 role: outputs k2 = 2 m + h of the size-NB DFT
     const int k2 = r % NB, c = r / NB;                       // stage 2 role: outputs k1 = c + 3 kb of the size-NA DFT
     int64_t t = blockIdx.x;
     int cur = 0;
-    if (t < tw_.total) stage_rows(reinterpret_cast<double*>(sm), tile_src(t), N, inner);
+    if (t < tw_.total) stage_tile(sm, t);
     db_cp_commit();
     for (; t < tw_.total; t += gridDim.x, cur ^= 1) {
         double2* in = sm + cur * (N * P);
         const int64_t tn = t + gridDim.x;
-        if (tn < tw_.total) stage_rows(reinterpret_cast<double*>(sm + (cur ^ 1) * (N * P)), tile_src(tn), N, inner);
+        if (tn < tw_.total) stage_tile(sm + (cur ^ 1) * (N * P), tn);
         db_cp_commit();
         db_cp_wait<1>();
         __syncthreads();
@@ -333,7 +347,7 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
             // Z_{n-k} for k = NB k1 + k2 sits at Zhi[(Q - 1 - k1), NB - k2] for k2 > 0, Zhi[Q - k1, 0] for k2 = 0
             const double sc = 1.0 / N;
             const int64_t o = t / tw_.tiles_per_outer, xt = t - o * tw_.tiles_per_outer;
-            double* __restrict__ gout = a.out + o * M * inner + xt * (2 * P) + 2 * p;
+            double* __restrict__ gout = a.out + xt * (2 * P) + 2 * p;
             const int k2p = (k2 == 0) ? 0 : NB - k2;
             const double2* src = in + k2p * P + p;
 #pragma unroll
@@ -341,16 +355,17 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
                 const int kk = 3 * kb + c;                         // k1
                 const int k = NB * kk + k2;
                 if (kk >= Q || k > Kmax) continue;
-                double* row = gout + (int64_t)(2 * k) * inner;
+                double* row = gout + row_offset(o, 2 * k, M, a.out_rpb, a.out_blk_stride, inner);
+                double* row1 = gout + row_offset(o, 2 * k + 1, M, a.out_rpb, a.out_blk_stride, inner);
                 const double2 za = z[kb];
                 if (k == 0) {
                     *reinterpret_cast<double2*>(row) = make_double2(za.x * sc, za.y * sc);
-                    *reinterpret_cast<double2*>(row + inner) = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2*>(row1) = make_double2(0.0, 0.0);
                 } else {
                     const int kbp = (k2 == 0) ? Q - kk : Q - 1 - kk;
                     const double2 zb = src[kbp * NB * P];
                     *reinterpret_cast<double2*>(row) = make_double2((za.x + zb.x) * sc, (za.y + zb.y) * sc);
-                    *reinterpret_cast<double2*>(row + inner) = make_double2((za.y - zb.y) * sc, (zb.x - za.x) * sc);
+                    *reinterpret_cast<double2*>(row1) = make_double2((za.y - zb.y) * sc, (zb.x - za.x) * sc);
                 }
             }
         }
@@ -735,7 +750,8 @@ extern "C" long long db_rfft_regs_launches(void) { return g_regs_launches; }
 // Returns -1 if the register kernels do not cover this case (the caller falls back to the generic shared-memory
 // kernel), otherwise the launch status.
 int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
-                     int64_t inner, int32_t deriv, double kscale, void* stream)
+                     int64_t inner, int32_t deriv, double kscale, void* stream,
+                     int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride)
 {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("DB_FFT_REGS"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
@@ -747,6 +763,8 @@ int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
     RegArgs a;
     a.in = in; a.out = out; a.twn = plan->twn; a.inner = inner; a.M = n_coeff; a.deriv = deriv; a.kscale = kscale;
+    a.in_rpb = in_rpb; a.in_blk_stride = in_blk_stride; a.out_rpb = out_rpb; a.out_blk_stride = out_blk_stride;
+    if (((in_rpb ? in_blk_stride : 0) | (out_rpb ? out_blk_stride : 0)) & 1) return -1;          // 16-byte alignment of every block
     ++g_regs_launches;
     switch (n) {
         case 384: return launch_regs<8, 16>(fwd, a, outer, stream);

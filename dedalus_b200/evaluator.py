@@ -301,9 +301,13 @@ class RHSPlan:
         for lvl, ax in enumerate(self.axes_order):
             nodes = self.levels[lvl]
             final = (lvl == dim - 1)
+            prev = bufs[lvl - 1] if lvl > 0 else None
+            if self.P > 1 and dim >= 3 and lvl == dim - 2 and self._blocked_bwd_ok():
+                # the y pass writes the all-to-all send buffer directly and the x pass reads the receive buffer directly
+                self._backward_blocked_levels(prev, lvl)
+                break
             if not final:
                 bufs[lvl] = self._scratch(('bwd', lvl), (len(nodes),) + self.level_shapes[lvl])
-            prev = bufs[lvl - 1] if lvl > 0 else None
             if final and self.P > 1:
                 # transpose hop (axis 0 <-> axis 1) for the whole stack of level-(dim-2) arrays in ONE all-to-all
                 nn = prev.shape[0]
@@ -338,8 +342,14 @@ class RHSPlan:
                              _dptr(self.term_ptr), _dptr(self.coef), _dptr(self.fac_ptr), _dptr(self.fac), self.nfac, _stream())
         # ---- phase 3: forward transforms (axes first -> last), all outputs stacked
         cur = self.grid_out
+        blocked_fwd = self.P > 1 and dim >= 3 and self._blocked_fwd_ok()
         for ax in range(dim):
             basis = self.bases[ax]
+            if blocked_fwd and ax == 0:
+                cur = self._forward_blocked_xy(cur)
+                continue
+            if blocked_fwd and ax == 1:
+                continue
             if ax < last:
                 plan = cached_plan(basis, self.dealias[ax])
                 shp = list(cur.shape); shp[1 + ax] = plan.M
@@ -383,6 +393,90 @@ class RHSPlan:
                 from .transforms import JacobiMatrixTransform
                 self._plans[key] = JacobiMatrixTransform(N, prod_basis.size, target_basis.a, target_basis.b, prod_basis.a0, prod_basis.b0)
         return self._plans[key]
+
+    # ---- distributed path without pack / unpack kernels (X1): blocked row addressing in the real-Fourier kernels
+    def _xy_plans(self):
+        from .transforms import cached_plan, RealFourierTransform
+        px, py = cached_plan(self.bases[0], self.dealias[0]), cached_plan(self.bases[1], self.dealias[1])
+        if not (isinstance(px, RealFourierTransform) and isinstance(py, RealFourierTransform)):
+            return None
+        return px, py
+
+    def _blocked_bwd_ok(self):
+        if not hasattr(self, '_blk_bwd'):
+            ok = False
+            plans = self._xy_plans()
+            if plans is not None:
+                px, py = plans
+                n1loc, n2, n3 = self.level_shapes[self.dist.dim - 2][0], self.gshape_full[1], int(np.prod(self.gshape_full[2:], dtype=int))
+                n2loc = n2 // self.P
+                ok = (py.blocked_supported(n3) and px.blocked_supported(n2loc * n3) and (n1loc * n2loc * n3) % 2 == 0
+                      and px.M == n1loc * self.P)
+            self._blk_bwd = ok
+        return self._blk_bwd
+
+    def _blocked_fwd_ok(self):
+        if not hasattr(self, '_blk_fwd'):
+            ok = False
+            plans = self._xy_plans()
+            if plans is not None:
+                px, py = plans
+                n2loc, n3 = self.gshape[1], int(np.prod(self.gshape[2:], dtype=int))
+                ok = (px.blocked_supported(n2loc * n3) and py.blocked_supported(n3) and px.M % self.P == 0
+                      and ((px.M // self.P) * n2loc * n3) % 2 == 0 and py.N == n2loc * self.P)
+            self._blk_fwd = ok
+        return self._blk_fwd
+
+    def _backward_blocked_levels(self, prev, lvl):
+        """Levels dim-2 (y pass) and dim-1 (x pass) of the backward tree with the all-to-all in between."""
+        from .transforms import cached_plan, _dptr
+        from .solvers import Timed
+        px, py = self._xy_plans()
+        dim = self.dist.dim
+        nodes = self.levels[lvl]
+        nn = len(nodes)
+        n1loc = self.level_shapes[lvl][0]
+        n2 = self.gshape_full[1]; n2loc = n2 // self.P
+        n3 = int(np.prod(self.gshape_full[2:], dtype=int))
+        per_field = n1loc * n2loc * n3
+        send = self._scratch(('blk_send_bwd',), (self.P * nn * per_field,))
+        recv = self._scratch(('blk_recv_bwd',), (self.P * nn * per_field,))
+        for key, nd in nodes.items():
+            f = nd['field']
+            src = (f.device_data()[self._comp_index(f, nd['comp'])] if lvl == 0 else prev[self.levels[lvl - 1][nd['parent']]['index']])
+            with Timed(self.solver.prof, "transform_bwd_axis1", 8 * (src.numel() + n1loc * n2 * n3)):
+                py.backward_blocked(src.data_ptr(), send.data_ptr() + 8 * nd['index'] * per_field, n1loc, n3, self.device,
+                                    deriv=nd['deriv'], out_block=(n2loc, nn * per_field))
+        with Timed(self.solver.prof, "transpose_bwd", 8 * 2 * send.numel()):
+            self.planner._alltoall(recv, send)
+        inner = n2loc * n3
+        for key, nd in self.levels[lvl + 1].items():
+            dst = self.grid_in[self._input_slot(key)]
+            pidx = nodes[nd['parent']]['index']
+            with Timed(self.solver.prof, "transform_bwd_axis0", 8 * (n1loc * self.P * inner + dst.numel())):
+                px.backward_blocked(recv.data_ptr() + 8 * pidx * per_field, dst.data_ptr(), 1, inner, self.device,
+                                    deriv=nd['deriv'], in_block=(n1loc, nn * per_field))
+
+    def _forward_blocked_xy(self, cur):
+        """x pass into the send buffer, all-to-all, y pass out of the receive buffer; returns the (n_out, n1loc, My, ...) stack."""
+        from .solvers import Timed
+        px, py = self._xy_plans()
+        n_out = cur.shape[0]
+        n2loc = cur.shape[2]
+        n3 = int(np.prod(cur.shape[3:], dtype=int))
+        inner = n2loc * n3
+        n1loc = px.M // self.P
+        send = self._scratch(('blk_send_fwd',), (n_out * px.M * inner,))
+        recv = self._scratch(('blk_recv_fwd',), (n_out * px.M * inner,))
+        with Timed(self.solver.prof, "transform_fwd_axis0", 8 * (cur.numel() + send.numel())):
+            px.forward_blocked(cur.data_ptr(), send.data_ptr(), n_out, inner, self.device, out_block=(n1loc, n_out * n1loc * inner))
+        with Timed(self.solver.prof, "transpose_fwd", 8 * 2 * send.numel()):
+            self.planner._alltoall(recv, send)
+        outer = n_out * n1loc
+        out = self._scratch(('fwd', 1), (n_out, n1loc, py.M) + tuple(cur.shape[3:]))
+        with Timed(self.solver.prof, "transform_fwd_axis1", 8 * (recv.numel() + out.numel())):
+            py.forward_blocked(recv.data_ptr(), out.data_ptr(), outer, n3, self.device, in_block=(n2loc, outer * n2loc * n3))
+        return out
 
     def _scratch(self, key, shape):
         import torch

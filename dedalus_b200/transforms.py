@@ -99,6 +99,28 @@ class RealFourierTransform:
         outer, inner = _split(gdata.shape, axis)
         get_lib().call("db_rfft_backward", plan.ref(), _dptr(cdata), _dptr(gdata), outer, self.M, inner, int(deriv), float(self.kscale), _stream())
 
+    # ---- blocked row addressing: the transform writes / reads the per-peer blocks of an all-to-all buffer directly
+    #      (include/dedalus_b200.h db_rfft_*_blocked); pointers are raw device addresses, block = (rows per peer, stride)
+    def blocked_supported(self, inner):
+        """Mirror of the coverage test in csrc/rfft_regs.cu db_rfft_regs_try."""
+        return (self.N in (24, 48, 96, 192, 384, 768) and self.M % 2 == 0 and self.M >= 2 and 3 * self.M <= 2 * self.N
+                and inner >= 16 and inner % 16 == 0 and os.environ.get("DB_FFT_REGS", "1") != "0"
+                and os.environ.get("DB_BLOCKED_TRANSPOSE", "1") != "0")
+
+    def backward_blocked(self, c_ptr, g_ptr, outer, inner, device, deriv=0, in_block=(0, 0), out_block=(0, 0)):
+        plan = DevicePlan(self.N, 'real', device)
+        ok = get_lib().call_optional("db_rfft_backward_blocked", plan.ref(), C.c_void_p(c_ptr), C.c_void_p(g_ptr), outer, self.M, inner,
+                                     int(deriv), float(self.kscale), int(in_block[0]), int(in_block[1]), int(out_block[0]), int(out_block[1]), _stream())
+        if not ok:
+            raise RuntimeError("blocked real-Fourier transform not covered (blocked_supported() out of sync with the kernels)")
+
+    def forward_blocked(self, g_ptr, c_ptr, outer, inner, device, in_block=(0, 0), out_block=(0, 0)):
+        plan = DevicePlan(self.N, 'real', device)
+        ok = get_lib().call_optional("db_rfft_forward_blocked", plan.ref(), C.c_void_p(g_ptr), C.c_void_p(c_ptr), outer, self.M, inner,
+                                     int(in_block[0]), int(in_block[1]), int(out_block[0]), int(out_block[1]), _stream())
+        if not ok:
+            raise RuntimeError("blocked real-Fourier transform not covered (blocked_supported() out of sync with the kernels)")
+
 
 @register_transform(ComplexFourier, 'b200')
 class ComplexFourierTransform:

@@ -53,6 +53,19 @@ int db_rfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t
 int db_rfft_backward(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
                      int32_t deriv, double kscale, void* stream);
 
+/* The same transforms with BLOCKED row addressing on either side, so that the pencil transposes (X1) need no pack /
+ * unpack kernels: with rpb > 0 row r of outer index o lives at (r / rpb) * blk_stride + (o * rpb + r % rpb) * inner
+ * (elements) -- the rows are grouped into the per-peer blocks of an all-to-all buffer: the transform before the exchange
+ * writes the send buffer directly (out_rpb = rows per peer), the transform after it reads the receive buffer directly
+ * (in_rpb).  Replaces the copies in and out of the transpose buffers of FFTWTranspose (core/transposes.pyx:146-246).
+ * rpb = 0: plain layout on that side.  Returns 2 (no error recorded) when the size / layout is not covered by the
+ * register-resident kernels (dealiased sizes, inner % 16 == 0): the caller then uses db_transpose_* + the plain entries. */
+int db_rfft_forward_blocked(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner,
+                            int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride, void* stream);
+int db_rfft_backward_blocked(const db_fft_plan* plan, const double* c, double* g, int64_t outer, int32_t n_coeff, int64_t inner,
+                             int32_t deriv, double kscale,
+                             int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride, void* stream);
+
 /* Complex Fourier, ordering [0..KM,(Nyq),-KM..-1], forward scaled by 1/N.
  * Replaces FFTWComplexFFT (core/transforms.py:243-267, 302-330).  Arrays are interleaved complex. */
 int db_cfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream);

@@ -244,3 +244,40 @@ def test_chebyshev_backward_with_fused_derivative_scan(M, N, npre):
     lib.call("db_cheb_backward", plan.ref(), E.ptr(tmp), E.ptr(ref), lines, M, 1, None, 0, None, 0, None)
     assert lib.call_optional("db_cheb_backward_scan", plan.ref(), E.ptr(c), E.ptr(out), lines, M, pre_ptr, npre, E.ptr(sol2), None)
     assert np.allclose(out, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("M,N,P", [(16, 24, 2), (64, 96, 4), (256, 384, 8)])
+def test_blocked_row_addressing_equals_pack_transform_unpack(M, N, P):
+    """db_rfft_*_blocked: writing / reading the per-peer blocks of an all-to-all buffer directly gives what the plain
+    transform gives after / before the pack and unpack copies (reference: FFTWTranspose buffer copies,
+    core/transposes.pyx:146-246).  Two fields share the buffers (blk_stride spans both)."""
+    lib = E.emu(); plan = E.EmuPlan(N, 'real')
+    rng = np.random.default_rng(P)
+    outer, inner, nf = 3, 32, 2
+    kscale = 1.3
+
+    def blocked(a, rows, rpb):
+        # a: (nf, outer, rows, inner) -> (rows // rpb, nf, outer, rpb, inner)
+        return np.ascontiguousarray(a.reshape(nf, outer, rows // rpb, rpb, inner).transpose(2, 0, 1, 3, 4))
+
+    c = rng.standard_normal((nf, outer, M, inner)); c[:, :, 1, :] = 0
+    g_ref = np.zeros((nf, outer, N, inner))
+    for f in range(nf):
+        lib.call("db_rfft_backward", plan.ref(), E.ptr(np.ascontiguousarray(c[f])), E.ptr(g_ref[f]), outer, M, inner, 1, kscale, None)
+    # backward: blocked input (receive buffer of M / P rows per peer) and blocked output (send buffer of N / P rows per peer)
+    cin = blocked(c, M, M // P); gout = np.full((P, nf, outer, N // P, inner), np.nan)
+    per_field_in, per_field_out = outer * (M // P) * inner, outer * (N // P) * inner
+    for f in range(nf):
+        assert lib.call_optional("db_rfft_backward_blocked", plan.ref(), E.ptr(cin.reshape(-1)[f * per_field_in:]), E.ptr(gout.reshape(-1)[f * per_field_out:]),
+                                 outer, M, inner, 1, kscale, M // P, nf * per_field_in, N // P, nf * per_field_out, None)
+    assert np.array_equal(gout, blocked(g_ref, N, N // P))
+    # forward likewise
+    g = rng.standard_normal((nf, outer, N, inner))
+    c_ref = np.zeros((nf, outer, M, inner))
+    for f in range(nf):
+        lib.call("db_rfft_forward", plan.ref(), E.ptr(np.ascontiguousarray(g[f])), E.ptr(c_ref[f]), outer, M, inner, None)
+    gin = blocked(g, N, N // P); cout = np.full((P, nf, outer, M // P, inner), np.nan)
+    for f in range(nf):
+        assert lib.call_optional("db_rfft_forward_blocked", plan.ref(), E.ptr(gin.reshape(-1)[f * per_field_out:]), E.ptr(cout.reshape(-1)[f * per_field_in:]),
+                                 outer, M, inner, N // P, nf * per_field_out, M // P, nf * per_field_in, None)
+    assert np.array_equal(cout, blocked(c_ref, M, M // P))
