@@ -503,14 +503,16 @@ __device__ __forceinline__ MvTerm mv_load(const db_term* __restrict__ rec, int t
 // the previous version: x re-read through L2 with a 25 % L1 hit rate, 20 long-scoreboard stalls per issue).  The few terms
 // outside the window (dense boundary rows) read x from global memory.
 #define MV_R 32
-#define MV_GROUPS 4
-#define MV_THREADS (64 * MV_GROUPS)
+#define MV_GROUPS 8
+#define MV_THREADS (32 * MV_GROUPS)
 #define MV_WMAX 80
 #define MV_RECMAX 768
 #define MV_SMEM_BYTES ((MV_WMAX * 64 + MV_MAX_MONO * 64) * 8 + MV_RECMAX * 16)
 __global__ void __launch_bounds__(MV_THREADS)
 k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, int ym_slot, int yl_slot)
 {
+    // thread = (row group g, system pair sp): the two systems 2 sp, 2 sp + 1 of the tile are adjacent in every array,
+    // so each term costs one 16-byte record load, one 16-byte x load and one 16-byte monomial load for two systems
     DB_SMEM(double, win);                                   // [MV_WMAX][64] x window, then monomials [MV_MAX_MONO][64], then records
     double* monos = win + MV_WMAX * 64;
     db_term* recs = reinterpret_cast<db_term*>(monos + MV_MAX_MONO * 64);
@@ -521,7 +523,7 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
     const int tile = local % tiles, rb = local / tiles;
     const int n = B.n, ld = B.ld;
     const int r0 = rb * MV_R, r1 = (r0 + MV_R < n) ? r0 + MV_R : n;
-    const int tid = threadIdx.x, sl = tid & 63, g = tid >> 6;
+    const int tid = threadIdx.x, sp = tid & 31, g = tid >> 5;
     const int64_t tile_base = (int64_t)tile * n * DB_TILE;
     const double* __restrict__ xt = B.vec[x_slot] + tile_base;
     const int w0 = B.mv_win[2 * rb], wl = B.mv_win[2 * rb + 1];
@@ -542,27 +544,28 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
     db_cp_commit();
     db_cp_wait<0>();
     __syncthreads();
-    const double* xs = win + sl;
-    const double* ms = monos + sl;
-    const double* __restrict__ xg = xt + sl;
+    const double2* xs = reinterpret_cast<const double2*>(win) + sp;           // row stride 32 double2
+    const double2* ms = reinterpret_cast<const double2*>(monos) + sp;
+    const double* __restrict__ xg = xt + 2 * sp;
     for (int which = 0; which < 2; ++which) {
         const int slot = which ? yl_slot : ym_slot;
         if (slot < 0) continue;
         const int32_t* __restrict__ ptr = which ? B.l_ptr : B.m_ptr;
         const db_term* rec = staged ? (recs + (which ? nm_rec - l0 : -m0)) : (which ? B.l_rec : B.m_rec);
-        double* __restrict__ y = B.vec[slot] + tile_base + sl;
+        double* __restrict__ y = B.vec[slot] + tile_base + 2 * sp;
         for (int i = r0 + g; i < r1; i += MV_GROUPS) {
-            int t = ptr[i];
             const int t1 = ptr[i + 1];
-            double acc0 = 0.0, acc1 = 0.0;
-            for (; t < t1; ++t) {
+            double2 acc = make_double2(0.0, 0.0);
+            for (int t = ptr[i]; t < t1; ++t) {
                 const db_term a = rec[t];
                 const int c = a.col_off >> 6;                 // column = col_off / DB_TILE
-                const double xv = ((unsigned)(c - w0) < (unsigned)wl) ? xs[(c - w0) * 64] : xg[a.col_off];
-                const double p = a.val * ms[a.mono * 64];
-                if (t & 1) acc1 = fma(p, xv, acc1); else acc0 = fma(p, xv, acc0);
+                const double2 xv = ((unsigned)(c - w0) < (unsigned)wl) ? xs[(c - w0) * 32]
+                                                                       : *reinterpret_cast<const double2*>(xg + a.col_off);
+                const double2 mv = ms[a.mono * 32];
+                acc.x = fma(a.val * mv.x, xv.x, acc.x);
+                acc.y = fma(a.val * mv.y, xv.y, acc.y);
             }
-            y[(int64_t)i * DB_TILE] = acc0 + acc1;
+            *reinterpret_cast<double2*>(y + (int64_t)i * DB_TILE) = acc;
         }
     }
 }

@@ -427,38 +427,62 @@ class RHSPlan:
             self._blk_fwd = ok
         return self._blk_fwd
 
+    @staticmethod
+    def _groups(n, want):
+        g = max(1, min(want, n))
+        cuts = [round(i * n / g) for i in range(g + 1)]
+        return [(cuts[i], cuts[i + 1]) for i in range(g) if cuts[i + 1] > cuts[i]]
+
     def _backward_blocked_levels(self, prev, lvl):
-        """Levels dim-2 (y pass) and dim-1 (x pass) of the backward tree with the all-to-all in between."""
-        from .transforms import cached_plan, _dptr
+        """Levels dim-2 (y pass) and dim-1 (x pass) of the backward tree with the all-to-all in between.  The stack of y-level
+        arrays is exchanged in groups: the all-to-all of one group runs (on the communicator's stream) while the y passes of
+        the next group and the x passes of the previous one occupy the SMs."""
         from .solvers import Timed
         px, py = self._xy_plans()
-        dim = self.dist.dim
         nodes = self.levels[lvl]
-        nn = len(nodes)
+        order = sorted(nodes.items(), key=lambda kv: kv[1]['index'])
+        nn = len(order)
         n1loc = self.level_shapes[lvl][0]
         n2 = self.gshape_full[1]; n2loc = n2 // self.P
         n3 = int(np.prod(self.gshape_full[2:], dtype=int))
         per_field = n1loc * n2loc * n3
         send = self._scratch(('blk_send_bwd',), (self.P * nn * per_field,))
         recv = self._scratch(('blk_recv_bwd',), (self.P * nn * per_field,))
-        for key, nd in nodes.items():
-            f = nd['field']
-            src = (f.device_data()[self._comp_index(f, nd['comp'])] if lvl == 0 else prev[self.levels[lvl - 1][nd['parent']]['index']])
-            with Timed(self.solver.prof, "transform_bwd_axis1", 8 * (src.numel() + n1loc * n2 * n3)):
-                py.backward_blocked(src.data_ptr(), send.data_ptr() + 8 * nd['index'] * per_field, n1loc, n3, self.device,
-                                    deriv=nd['deriv'], out_block=(n2loc, nn * per_field))
-        with Timed(self.solver.prof, "transpose_bwd", 8 * 2 * send.numel()):
-            self.planner._alltoall(recv, send)
+        groups = self._groups(nn, 3)
+        handles, group_of, base_of = [], {}, {}
+        for gi, (g0, g1) in enumerate(groups):
+            ng = g1 - g0
+            off = self.P * g0 * per_field                        # groups are laid out one after the other
+            for key, nd in order[g0:g1]:
+                f = nd['field']
+                src = (f.device_data()[self._comp_index(f, nd['comp'])] if lvl == 0 else prev[self.levels[lvl - 1][nd['parent']]['index']])
+                local = nd['index'] - g0
+                group_of[key] = gi; base_of[key] = (off + local * per_field, ng * per_field)
+                with Timed(self.solver.prof, "transform_bwd_axis1", 8 * (src.numel() + n1loc * n2 * n3)):
+                    py.backward_blocked(src.data_ptr(), send.data_ptr() + 8 * (off + local * per_field), n1loc, n3, self.device,
+                                        deriv=nd['deriv'], out_block=(n2loc, ng * per_field))
+            sl = slice(off, off + self.P * ng * per_field)
+            with Timed(self.solver.prof, "transpose_bwd", 8 * 2 * self.P * ng * per_field):
+                handles.append(self.planner.alltoall_async(recv[sl], send[sl]))
         inner = n2loc * n3
-        for key, nd in self.levels[lvl + 1].items():
+        waited = set()
+        children = sorted(self.levels[lvl + 1].items(), key=lambda kv: group_of[kv[1]['parent']])
+        for key, nd in children:
+            gi = group_of[nd['parent']]
+            if gi not in waited:
+                waited.add(gi)
+                if handles[gi] is not None:
+                    with Timed(self.solver.prof, "transpose_bwd", 0):
+                        handles[gi].wait()
             dst = self.grid_in[self._input_slot(key)]
-            pidx = nodes[nd['parent']]['index']
+            base, stride = base_of[nd['parent']]
             with Timed(self.solver.prof, "transform_bwd_axis0", 8 * (n1loc * self.P * inner + dst.numel())):
-                px.backward_blocked(recv.data_ptr() + 8 * pidx * per_field, dst.data_ptr(), 1, inner, self.device,
-                                    deriv=nd['deriv'], in_block=(n1loc, nn * per_field))
+                px.backward_blocked(recv.data_ptr() + 8 * base, dst.data_ptr(), 1, inner, self.device,
+                                    deriv=nd['deriv'], in_block=(n1loc, stride))
 
     def _forward_blocked_xy(self, cur):
-        """x pass into the send buffer, all-to-all, y pass out of the receive buffer; returns the (n_out, n1loc, My, ...) stack."""
+        """x pass into the send buffer, all-to-all, y pass out of the receive buffer (in two groups of outputs so that the
+        exchange of one overlaps the passes of the other); returns the (n_out, n1loc, My, ...) stack."""
         from .solvers import Timed
         px, py = self._xy_plans()
         n_out = cur.shape[0]
@@ -466,16 +490,32 @@ class RHSPlan:
         n3 = int(np.prod(cur.shape[3:], dtype=int))
         inner = n2loc * n3
         n1loc = px.M // self.P
-        send = self._scratch(('blk_send_fwd',), (n_out * px.M * inner,))
-        recv = self._scratch(('blk_recv_fwd',), (n_out * px.M * inner,))
-        with Timed(self.solver.prof, "transform_fwd_axis0", 8 * (cur.numel() + send.numel())):
-            px.forward_blocked(cur.data_ptr(), send.data_ptr(), n_out, inner, self.device, out_block=(n1loc, n_out * n1loc * inner))
-        with Timed(self.solver.prof, "transpose_fwd", 8 * 2 * send.numel()):
-            self.planner._alltoall(recv, send)
-        outer = n_out * n1loc
+        per_out_g = px.N * inner                                  # grid elements per output
+        per_out_c = px.M * inner                                  # coefficient elements per output (all peers' blocks)
+        send = self._scratch(('blk_send_fwd',), (n_out * per_out_c,))
+        recv = self._scratch(('blk_recv_fwd',), (n_out * per_out_c,))
         out = self._scratch(('fwd', 1), (n_out, n1loc, py.M) + tuple(cur.shape[3:]))
-        with Timed(self.solver.prof, "transform_fwd_axis1", 8 * (recv.numel() + out.numel())):
-            py.forward_blocked(recv.data_ptr(), out.data_ptr(), outer, n3, self.device, in_block=(n2loc, outer * n2loc * n3))
+        flat_in = cur.reshape(-1)
+        groups = self._groups(n_out, 2)
+        handles = []
+        for g0, g1 in groups:
+            ng = g1 - g0
+            sl = slice(g0 * per_out_c, g1 * per_out_c)
+            with Timed(self.solver.prof, "transform_fwd_axis0", 8 * ng * (per_out_g + per_out_c)):
+                px.forward_blocked(flat_in.data_ptr() + 8 * g0 * per_out_g, send.data_ptr() + 8 * g0 * per_out_c, ng, inner, self.device,
+                                   out_block=(n1loc, ng * n1loc * inner))
+            with Timed(self.solver.prof, "transpose_fwd", 8 * 2 * ng * per_out_c):
+                handles.append(self.planner.alltoall_async(recv[sl], send[sl]))
+        per_out_y = n1loc * py.M * n3
+        for (g0, g1), h in zip(groups, handles):
+            ng = g1 - g0
+            if h is not None:
+                with Timed(self.solver.prof, "transpose_fwd", 0):
+                    h.wait()
+            outer = ng * n1loc
+            with Timed(self.solver.prof, "transform_fwd_axis1", 8 * ng * (per_out_c + per_out_y)):
+                py.forward_blocked(recv.data_ptr() + 8 * g0 * per_out_c, out.reshape(-1).data_ptr() + 8 * g0 * per_out_y, outer, n3, self.device,
+                                   in_block=(n2loc, outer * n2loc * n3))
         return out
 
     def _scratch(self, key, shape):

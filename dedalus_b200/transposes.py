@@ -45,6 +45,15 @@ class TransposePlanner:
         else:
             td.all_to_all_single(recv, send)
 
+    def alltoall_async(self, recv, send):
+        """Start the exchange and return a handle whose wait() orders the current stream after it (NCCL: the collective
+        runs on the communicator's stream, so kernels launched meanwhile overlap it); gloo: synchronous, returns None."""
+        td = self.td
+        if td.get_backend() == "gloo":
+            self._alltoall(recv, send)
+            return None
+        return td.all_to_all_single(recv, send, async_op=True)
+
     def localize_columns(self, a, out):
         """(B, n1_local, n2, n3) distributed along axis 1  ->  (B, n1, n2_local, n3) distributed along axis 2."""
         B, n1loc, n2, n3 = a.shape
