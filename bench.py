@@ -194,6 +194,14 @@ def main():
                         peak_source="MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                         algorithmic_bytes_per_launch=d['bytes'] / d['launches'], avg_launch_ms=d['ms'] / d['launches'],
                         traffic=None)
+        # measured DRAM bytes per launch of this kernel class from the committed ncu capture of the same workload
+        try:
+            tr = json.load(open(ROOT / "profiles" / "ncu_traffic.json"))
+            if world == 1 and N == 256 and args.dim == 3 and dom in tr.get("classes", {}):
+                roofline['traffic'] = tr["classes"][dom]["dram_bytes_per_launch"]
+                roofline['traffic_source'] = tr["classes"][dom]["capture"] + " (" + tr["how"] + ")"
+        except Exception:
+            pass
     # ---- end-to-end: state uploaded from pinned host memory and read back every step, through solver.step()
     e2e = None
     if not args.no_e2e:
