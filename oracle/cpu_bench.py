@@ -20,6 +20,13 @@ from . import imex
 
 def _pencil_worker(args):
     dim, Nh, Nz, Ra, groups, dt, reps = args
+    # one thread per worker process: the pool already uses every core, and 128 processes x 128 BLAS / OpenMP threads
+    # made a single sample take minutes on the GPU box's host
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     orc = rb_oracle.RBOracle(dim, Nh, Nz, Ra)
     tab = imex.RK["RK222"]; A, H = tab['A'], tab['H']
     rng = np.random.default_rng(0)
@@ -31,8 +38,9 @@ def _pencil_worker(args):
         orc._solve(grp, (dt, H[1, 1]), 1.0, dt * H[1, 1], np.zeros(M.shape[0]))      # factorise (untimed)
         data.append((grp, x, rng.standard_normal(M.shape[0]) * vr, rng.standard_normal(M.shape[0]) * vr))
     st = orc.new_state(np.zeros(orc.cshape))
-    t0 = time.perf_counter()
+    rep_times = []
     for _ in range(reps):
+        t0 = time.perf_counter()
         for grp, x, f1, f2 in data:
             M, L, vr, vc, voff, eoff = orc.pencils[grp]
             # stage 1
@@ -47,11 +55,16 @@ def _pencil_worker(args):
             rhs = mx0 + dt * (A[2, 0] * f1 + A[2, 1] * f2) - dt * (H[2, 0] * lx0 + H[2, 1] * lx1)
             x2 = orc._solve(grp, (dt, H[2, 2]), 1.0, dt * H[2, 2], rhs)
             orc.scatter_state(grp, x2, st, voff)
-    return (time.perf_counter() - t0) / reps
+        rep_times.append(time.perf_counter() - t0)
+    return rep_times
 
 
-def sampled_step(dim=3, N=256, Ra=1e6, dt=0.0025, cores=None, n_pencils=None, slab=None):
-    """Estimated wall time of ONE RK222 step of dim-D RB at N^dim on this host, from a bounded sample."""
+def sampled_step(dim=3, N=256, Ra=1e6, dt=0.0025, cores=None, n_pencils=None, slab=None, reps=1, pool_timeout=150.0):
+    """Estimated wall time of ONE RK222 step of dim-D RB at N^dim on this host, from a bounded sample.  `reps` repeats
+    the timed pencil work on the same (untimed) setup -- matrices and factorisations are built once -- and the result
+    carries one estimate per repetition in `steps_per_sec_list`; `steps_per_sec` is their median.  If the process pool
+    does not finish within `pool_timeout` seconds it is abandoned and a small in-process sample is used instead, so a
+    call always returns within a few minutes."""
     cores = cores or os.cpu_count() or 1
     Nh = Nz = N
     G = int(1.5 * N)
@@ -113,13 +126,27 @@ def sampled_step(dim=3, N=256, Ra=1e6, dt=0.0025, cores=None, n_pencils=None, sl
     chunks = [sample[i::cores] for i in range(cores) if sample[i::cores]]
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    with ctx.Pool(len(chunks)) as pool:
-        times = pool.map(_pencil_worker, [(dim, Nh, Nz, Ra, ch, dt, 1) for ch in chunks])
-    t_pencil_sample = max(times)                     # wall time of the slowest worker for its share
-    t_pencil_step = t_pencil_sample * len(groups_all) / n_pencils
-    t_step = 2 * t_rhs_stage + t_pencil_step
-    return dict(step_seconds=t_step, steps_per_sec=1.0 / t_step, cores=cores,
+    used_procs = len(chunks)
+    pool = ctx.Pool(len(chunks))
+    try:
+        times = pool.map_async(_pencil_worker, [(dim, Nh, Nz, Ra, ch, dt, reps) for ch in chunks]).get(timeout=pool_timeout)
+        pool.close()
+    except mp.TimeoutError:
+        pool.terminate()
+        n_pencils = min(4, len(groups_all)); used_procs = 1
+        idx = np.linspace(0, len(groups_all) - 1, n_pencils).astype(int)
+        times = [_pencil_worker((dim, Nh, Nz, Ra, [groups_all[i] for i in idx], dt, reps))]
+        cores_eff = 1
+        # one process handled the whole sample: scale as if `cores` such processes shared the pencils
+        times = [[t / cores for t in times[0]]]
+    finally:
+        pool.join()
+    # per repetition: wall time of the slowest worker for its share
+    t_pencil_reps = [max(w[r] for w in times) * len(groups_all) / n_pencils for r in range(reps)]
+    t_steps = [2 * t_rhs_stage + tp for tp in t_pencil_reps]
+    t_step = float(np.median(t_steps)); t_pencil_step = float(np.median(t_pencil_reps))
+    return dict(step_seconds=t_step, steps_per_sec=1.0 / t_step, steps_per_sec_list=[1.0 / t for t in t_steps], cores=cores,
                 rhs_seconds=2 * t_rhs_stage, pencil_seconds=t_pencil_step,
                 sample=(f"transform passes on {slab}-plane slabs (1/{N // slab} of z/y lines, 1/{G // slab} of x lines), "
-                        f"products on a {slab}-plane slab, {n_pencils} of {len(groups_all)} pencils over {len(chunks)} processes; "
+                        f"products on a {slab}-plane slab, {n_pencils} of {len(groups_all)} pencils over {used_procs} processes; "
                         f"scaled to the full {N}^{dim} step; SuperLU factorisations excluded (constant dt)"))
