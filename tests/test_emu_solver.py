@@ -84,3 +84,22 @@ def test_heat_periodic_every_timestepper(timestepper):
     amp = 1 - np.exp(-solver.sim_time)
     u.change_scales(1)
     assert np.allclose(u['g'], amp * np.sin(x))
+
+
+def test_rb3d_16_register_kernels_match_oracle():
+    """16^3 (24-point dealiased lines): the x passes and the z passes run through csrc/rfft_regs.cu inside the solver; two
+    RK222 steps against the oracle (oracle/rb_oracle.py, itself pinned to the reference fixtures in test_oracle.py)."""
+    from oracle import rb_oracle
+    from dedalus_b200.lib import get_lib
+    Nh, Nz, steps, dt = 16, 16, 2, 0.01
+    pb = examples.rayleigh_benard(dim=3, Nh=Nh, Nz=Nz, Rayleigh=1e6)
+    solver = pb['problem'].build_solver(d3.RK222)
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    b0 = pb['b']['c'].copy()
+    served = get_lib().rfft_regs_launches()
+    for _ in range(steps):
+        solver.step(dt)
+    assert get_lib().rfft_regs_launches() > served
+    ref = rb_oracle.run(dim=3, Nh=Nh, Nz=Nz, Ra=1e6, b0_c=b0, steps=steps, dt=dt, scheme="RK222")
+    for name in ("p", "b", "u"):
+        assert np.allclose(pb[name]['c'], ref[name], rtol=1e-8, atol=1e-12), name
