@@ -486,6 +486,16 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
 
 #define MV_MAX_MONO 16
 struct MvTerm { double val; int col_off; int mono; };
+__device__ __forceinline__ MvTerm mv_load_shared(const db_term* rec, int t)
+{
+    // staged records: one 16-byte shared-memory load (broadcast: every lane reads the same record)
+#ifdef DB_EMU
+    MvTerm r; r.val = rec[t].val; r.col_off = rec[t].col_off; r.mono = rec[t].mono; return r;
+#else
+    const int4 raw = *reinterpret_cast<const int4*>(rec + t);
+    MvTerm r; r.val = __hiloint2double(raw.y, raw.x); r.col_off = raw.z; r.mono = raw.w; return r;
+#endif
+}
 __device__ __forceinline__ MvTerm mv_load(const db_term* __restrict__ rec, int t)
 {
     // one 16-byte load (the records are 16-byte aligned: the array comes from its own allocation)
@@ -551,19 +561,41 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
         const int slot = which ? yl_slot : ym_slot;
         if (slot < 0) continue;
         const int32_t* __restrict__ ptr = which ? B.l_ptr : B.m_ptr;
-        const db_term* rec = staged ? (recs + (which ? nm_rec - l0 : -m0)) : (which ? B.l_rec : B.m_rec);
+        const int32_t* __restrict__ split = which ? B.l_split : B.m_split;
+        const db_term* __restrict__ grec = which ? B.l_rec : B.m_rec;
+        const db_term* srec = recs + (which ? nm_rec - l0 : -m0);               // staged copy, indexed like the global array
         double* __restrict__ y = B.vec[slot] + tile_base + 2 * sp;
         for (int i = r0 + g; i < r1; i += MV_GROUPS) {
-            const int t1 = ptr[i + 1];
+            const int ta = ptr[i], tb = split[i], tc = ptr[i + 1];
             double2 acc = make_double2(0.0, 0.0);
-            for (int t = ptr[i]; t < t1; ++t) {
-                const db_term a = rec[t];
-                const int c = a.col_off >> 6;                 // column = col_off / DB_TILE
-                const double2 xv = ((unsigned)(c - w0) < (unsigned)wl) ? xs[(c - w0) * 32]
-                                                                       : *reinterpret_cast<const double2*>(xg + a.col_off);
-                const double2 mv = ms[a.mono * 32];
-                acc.x = fma(a.val * mv.x, xv.x, acc.x);
-                acc.y = fma(a.val * mv.y, xv.y, acc.y);
+            if (staged) {
+                // terms inside the window: record, x and monomial all come from shared memory
+#pragma unroll 4
+                for (int t = ta; t < tb; ++t) {
+                    const MvTerm a = mv_load_shared(srec, t);
+                    const double2 xv = xs[a.col_off * 32], mv = ms[a.mono * 32];
+                    acc.x = fma(a.val * mv.x, xv.x, acc.x);
+                    acc.y = fma(a.val * mv.y, xv.y, acc.y);
+                }
+                for (int t = tb; t < tc; ++t) {
+                    const MvTerm a = mv_load_shared(srec, t);
+                    const double2 xv = *reinterpret_cast<const double2*>(xg + a.col_off), mv = ms[a.mono * 32];
+                    acc.x = fma(a.val * mv.x, xv.x, acc.x);
+                    acc.y = fma(a.val * mv.y, xv.y, acc.y);
+                }
+            } else {
+                for (int t = ta; t < tb; ++t) {
+                    const MvTerm a = mv_load(grec, t);
+                    const double2 xv = xs[a.col_off * 32], mv = ms[a.mono * 32];
+                    acc.x = fma(a.val * mv.x, xv.x, acc.x);
+                    acc.y = fma(a.val * mv.y, xv.y, acc.y);
+                }
+                for (int t = tb; t < tc; ++t) {
+                    const MvTerm a = mv_load(grec, t);
+                    const double2 xv = *reinterpret_cast<const double2*>(xg + a.col_off), mv = ms[a.mono * 32];
+                    acc.x = fma(a.val * mv.x, xv.x, acc.x);
+                    acc.y = fma(a.val * mv.y, xv.y, acc.y);
+                }
             }
             *reinterpret_cast<double2*>(y + (int64_t)i * DB_TILE) = acc;
         }

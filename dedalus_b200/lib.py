@@ -33,7 +33,7 @@ class Batch(C.Structure):
                 ("prog", vp), ("mono", vp), ("vec", vp * DB_MAX_VECS), ("lu", vp * DB_MAX_LU),
                 ("m_ptr", vp), ("m_col", vp), ("m_mono", vp), ("m_val", vp),
                 ("l_ptr", vp), ("l_col", vp), ("l_mono", vp), ("l_val", vp),
-                ("m_rec", vp), ("l_rec", vp), ("ctrl", vp), ("n_mono", i32), ("mv_rows", i32), ("mv_win", vp),
+                ("m_rec", vp), ("l_rec", vp), ("ctrl", vp), ("n_mono", i32), ("mv_rows", i32), ("mv_win", vp), ("m_split", vp), ("l_split", vp),
                 ("line_base", vp * 2), ("line_kind", vp * 2), ("line_ptr", vp * 2), ("line_pos", vp * 2), ("sys_off", vp * 2),
                 ("diag_eid", vp), ("fl_ptr", vp), ("fl_eid", vp), ("fu_ptr", vp), ("fu_eid", vp), ("fd_eid", vp),
                 ("asm_ptr", vp), ("asm_mono", vp), ("asm_val", vp), ("info", vp)]

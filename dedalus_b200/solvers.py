@@ -78,14 +78,31 @@ class DeviceBatch:
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
         self.t = dict(mono=d(mono), prog=f(prog.prog), ctrl=f(prog.ctrl.ravel()), diag_eid=f(prog.diag_eid), fl_ptr=f(prog.fl_ptr), fl_eid=f(prog.fl_eid),
                       fu_ptr=f(prog.fu_ptr), fu_eid=f(prog.fu_eid), fd_eid=f(prog.fd_eid))
+        win = matvec_windows(prog, 32, 80)
         for name in ('M', 'L'):
             ptr, col, mono_i, val = prog.mv[name]
             k = name.lower()
             self.t[k + '_ptr'], self.t[k + '_col'], self.t[k + '_mono'], self.t[k + '_val'] = f(ptr), f(col), f(mono_i), d(val)
-            rec = np.zeros(len(col), dtype=np.dtype([('val', '<f8'), ('col_off', '<i4'), ('mono', '<i4')]))     # db_term
-            rec['val'], rec['col_off'], rec['mono'] = val, np.asarray(col, dtype=np.int64) * prog.tile, mono_i
+            # fused kernel: 16-byte records, each row's terms reordered so that those inside the row block's shared-memory
+            # window come first (col_off = window row) and the others (col_off = column * tile, read from global memory) last
+            ptr_a, col_a, mono_a, val_a = (np.asarray(a) for a in (ptr, col, mono_i, val))
+            rec = np.zeros(len(col_a), dtype=np.dtype([('val', '<f8'), ('col_off', '<i4'), ('mono', '<i4')]))     # db_term
+            split = np.zeros(prog.n, dtype=np.int32)
+            for i in range(prog.n):
+                t0, t1 = int(ptr_a[i]), int(ptr_a[i + 1])
+                w0, wl = win[i // 32]
+                cols = col_a[t0:t1].astype(np.int64)
+                inside = (cols >= w0) & (cols < w0 + wl)
+                order = np.concatenate([np.nonzero(inside)[0], np.nonzero(~inside)[0]])
+                n_in = int(inside.sum())
+                rec['val'][t0:t1] = val_a[t0:t1][order]
+                rec['mono'][t0:t1] = mono_a[t0:t1][order]
+                rec['col_off'][t0:t0 + n_in] = cols[order[:n_in]] - w0
+                rec['col_off'][t0 + n_in:t1] = cols[order[n_in:]] * prog.tile
+                split[i] = t0 + n_in
             self.t[k + '_rec'] = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()).to(dev)
-        self.t['mv_win'] = f(matvec_windows(prog, 32, 80).ravel())
+            self.t[k + '_split'] = f(split)
+        self.t['mv_win'] = f(win.ravel())
         self.maps = []
         for side, arena in (('cols', solver.var_arena), ('rows', solver.eq_arena)):
             m = line_maps(batch, arena, side)
@@ -151,6 +168,7 @@ class BatchSet:
             c.m_ptr, c.m_col, c.m_mono, c.m_val = (t[k].data_ptr() for k in ('m_ptr', 'm_col', 'm_mono', 'm_val'))
             c.l_ptr, c.l_col, c.l_mono, c.l_val = (t[k].data_ptr() for k in ('l_ptr', 'l_col', 'l_mono', 'l_val'))
             c.m_rec, c.l_rec, c.n_mono = t['m_rec'].data_ptr(), t['l_rec'].data_ptr(), len(db.prog.monos)
+            c.m_split, c.l_split = t['m_split'].data_ptr(), t['l_split'].data_ptr()
             if len(db.prog.monos) > 16:
                 raise NotImplementedError("more than 16 wavenumber monomials in one class (MV_MAX_MONO in csrc/pencil.cu)")
             c.diag_eid, c.fl_ptr, c.fl_eid = t['diag_eid'].data_ptr(), t['fl_ptr'].data_ptr(), t['fl_eid'].data_ptr()

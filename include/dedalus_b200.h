@@ -191,7 +191,8 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
 #define DB_MAX_VECS 24
 #define DB_MAX_LU 4
 #define DB_I_SKIP ((int32_t)0x80000000)
-/* one term of a template mat-vec: y[row] += val * mono[mono][s] * x[col_off + s']; col_off = column * DB_TILE */
+/* one term of a template mat-vec: y[row] += val * mono[mono][s] * x[column][s]; in the fused kernel's record arrays col_off is
+ * the row inside the block's shared-memory window or column * DB_TILE (see db_batch.m_split) */
 typedef struct { double val; int32_t col_off; int32_t mono; } db_term;
 typedef struct {
     int32_t n, S, ld, n_entries;
@@ -210,6 +211,8 @@ typedef struct {
     int32_t n_mono;
     int32_t mv_rows;                   /* rows per CTA of the fused mat-vec (= 32, MV_R in csrc/pencil.cu) */
     const int32_t* mv_win;             /* [ceil(n / mv_rows)][2]: first x row and row count (<= 80) of the shared-memory window of each row block */
+    const int32_t *m_split, *l_split;  /* [n]: within row i, records m_ptr[i]..split[i] lie inside the window (col_off = window row),
+                                          records split[i]..m_ptr[i+1] outside (col_off = column * DB_TILE)                       */
     const int64_t* line_base[2]; const int32_t* line_kind[2]; const int32_t* line_ptr[2]; const int32_t* line_pos[2];
     const int64_t* sys_off[2];
     /* factorisation programs */
