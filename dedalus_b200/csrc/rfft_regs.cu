@@ -417,11 +417,16 @@ k_chbwd_regs(ChebArgs a)
     const int nl = (a.lines - l0 < CH_LINES) ? (int)(a.lines - l0) : CH_LINES;
     // ---- stage the coefficient lines (16-byte chunks); missing lines of a partial tile are zero
     {
-        const int cpl = M / 2;                               // chunks per line
-        for (int idx = tid; idx < CH_LINES * cpl; idx += nthreads) {
-            const int l = idx / cpl, ch = idx - l * cpl;
-            if (l < nl) db_cp_async16(X + l * LX + 2 * ch, a.in + (l0 + l) * M + 2 * ch);
-            else { X[l * LX + 2 * ch] = 0.0; X[l * LX + 2 * ch + 1] = 0.0; }
+        // one warp per line at a time, lanes along the line (16-byte chunks): no index division
+        const int cpl = M / 2, lane = tid & 31, nw = nthreads >> 5;
+        for (int l = tid >> 5; l < CH_LINES; l += nw) {
+            double* dst = X + l * LX;
+            if (l < nl) {
+                const double* src = a.in + (l0 + l) * M;
+                for (int ch = lane; ch < cpl; ch += 32) db_cp_async16(dst + 2 * ch, src + 2 * ch);
+            } else {
+                for (int ch = lane; ch < cpl; ch += 32) { dst[2 * ch] = 0.0; dst[2 * ch + 1] = 0.0; }
+            }
         }
         db_cp_commit();
         db_cp_wait<0>();
@@ -555,10 +560,12 @@ k_chbwd_regs(ChebArgs a)
     __syncthreads();
     // ---- store the grid lines (contiguous block)
     {
-        const int cpl = N / 2;
-        for (int idx = tid; idx < nl * cpl; idx += nthreads) {
-            const int l = idx / cpl, ch = idx - l * cpl;
-            *reinterpret_cast<double2*>(a.out + (l0 + l) * N + 2 * ch) = *reinterpret_cast<const double2*>(X + l * LX + 2 * ch);
+        const int cpl = N / 2, lane = tid & 31, nw = nthreads >> 5;
+        for (int l = tid >> 5; l < nl; l += nw) {
+            const double* src = X + l * LX;
+            double* dst = a.out + (l0 + l) * N;
+            for (int ch = lane; ch < cpl; ch += 32)
+                *reinterpret_cast<double2*>(dst + 2 * ch) = *reinterpret_cast<const double2*>(src + 2 * ch);
         }
     }
 }
@@ -576,11 +583,15 @@ k_chfwd_regs(ChebArgs a)
     const int64_t l0 = (int64_t)blockIdx.x * CH_LINES;
     const int nl = (a.lines - l0 < CH_LINES) ? (int)(a.lines - l0) : CH_LINES;
     {
-        const int cpl = N / 2;
-        for (int idx = tid; idx < CH_LINES * cpl; idx += nthreads) {
-            const int l = idx / cpl, ch = idx - l * cpl;
-            if (l < nl) db_cp_async16(X + l * LX + 2 * ch, a.in + (l0 + l) * N + 2 * ch);
-            else { X[l * LX + 2 * ch] = 0.0; X[l * LX + 2 * ch + 1] = 0.0; }
+        const int cpl = N / 2, lane = tid & 31, nw = nthreads >> 5;
+        for (int l = tid >> 5; l < CH_LINES; l += nw) {
+            double* dst = X + l * LX;
+            if (l < nl) {
+                const double* src = a.in + (l0 + l) * N;
+                for (int ch = lane; ch < cpl; ch += 32) db_cp_async16(dst + 2 * ch, src + 2 * ch);
+            } else {
+                for (int ch = lane; ch < cpl; ch += 32) { dst[2 * ch] = 0.0; dst[2 * ch + 1] = 0.0; }
+            }
         }
         db_cp_commit();
         db_cp_wait<0>();
@@ -659,17 +670,21 @@ k_chfwd_regs(ChebArgs a)
     __syncthreads();
     // ---- store with the banded conversion applied: out[i] = sum_d diag[d][i] cof[i + d]
     {
-        const int nd = a.nd;
-        for (int idx = tid; idx < nl * M; idx += nthreads) {
-            const int l = idx / M, i = idx - l * M;
+        // one warp per line at a time, lanes along the line: coalesced diagonal loads and stores, conflict-free cf[i + d]
+        const int nd = a.nd, lane = tid & 31, nw = nthreads >> 5;
+        const double* __restrict__ dg = a.diags;
+        for (int l = tid >> 5; l < nl; l += nw) {
             const double* cf = X + l * LX;
-            double acc = 0.0;
-            if (i < Kin) {
-                if (nd > 0) {
-                    for (int d = 0; d < nd && i + d < Kin; ++d) acc = fma(a.diags[(int64_t)d * M + i], cf[i + d], acc);
-                } else acc = cf[i];
+            double* dst = a.out + (l0 + l) * M;
+            for (int i = lane; i < M; i += 32) {
+                double acc = 0.0;
+                if (i < Kin) {
+                    if (nd > 0) {
+                        for (int d = 0; d < nd && i + d < Kin; ++d) acc = fma(dg[(int64_t)d * M + i], cf[i + d], acc);
+                    } else acc = cf[i];
+                }
+                dst[i] = acc;
             }
-            a.out[(l0 + l) * M + i] = acc;
         }
     }
 }
