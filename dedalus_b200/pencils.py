@@ -500,7 +500,7 @@ def compile_batch(batch, a0, b0, dense=None):
     prog.n, prog.S = n, batch.S
     # ---- solve stream (include/dedalus_b200.h).  Rows of each triangular solve are processed in LEVEL order of its
     #      dependency DAG (rows of one level are mutually independent), which keeps a row's inputs several rows behind it
-    #      in the stream and lets the kernels preload x values two chunks ahead.  Codes:
+    #      in the stream, so the 16 values a chunk needs can be gathered in one burst before it is consumed.  Codes:
     #        c >= 0          : acc -= LU[e] * x[c] ; c = column * TILE
     #        c <  0, != SKIP : leave the current row (store; backward: multiply by LU[e] = reciprocal pivot) and enter
     #                          row (-1 - c) / TILE with acc = x[row] ; the first entry of a section only enters a row
