@@ -103,3 +103,13 @@ def test_rb3d_16_register_kernels_match_oracle():
     ref = rb_oracle.run(dim=3, Nh=Nh, Nz=Nz, Ra=1e6, b0_c=b0, steps=steps, dt=dt, scheme="RK222")
     for name in ("p", "b", "u"):
         assert np.allclose(pb[name]['c'], ref[name], rtol=1e-8, atol=1e-12), name
+
+
+def test_solve_then_multiply_back_residual():
+    """(M + b0 L) solve(b) == b through the fused solve and mat-vec kernels, every system of every batch."""
+    from residual_check import solve_residual
+    pb = examples.rayleigh_benard(dim=3, Nh=8, Nz=16, Rayleigh=1e6)
+    solver = pb['problem'].build_solver(d3.RK222)
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    solver.step(0.01)
+    assert solve_residual(solver, 0.01) < 1e-11
