@@ -618,7 +618,10 @@ extern "C" int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_
 }
 
 // 64 x 64 tiles: one side is a full 512-byte row of the tile-major pencil vectors (64 systems), the other a 512-byte
-// run of a z line; 16 independent loads per thread keep enough bytes in flight for a pure data-movement kernel.
+// run of a z line; 16 independent loads per thread keep enough bytes in flight for a pure data-movement kernel.  One CTA
+// owns (line kind, 64 systems) and walks the whole line in 64-element steps, so the descriptor / batch look-up in front of
+// the copies is paid once per line instead of once per tile (ncu on the one-tile-per-CTA version: ~70 instructions per
+// element moved, issue-bound at 2.8 TB/s).
 #define MOVE_T 64
 template <bool GATHER>
 __global__ void __launch_bounds__(MOVE_T * 4)
@@ -627,49 +630,56 @@ k_batches_move(const db_batch* __restrict__ batches, int nbatch, int side, int s
     DB_SMEM(double, tile);                         // [MOVE_T][MOVE_T + 1]
     const int bi = find_batch(batches, nbatch, blockIdx.x, 2 + side);
     const db_batch& B = batches[bi];
-    int local = blockIdx.x - B.blk_move[side];
+    const int local = blockIdx.x - B.blk_move[side];
     const int sblocks = (B.S + MOVE_T - 1) / MOVE_T;
-    const int mblocks = (B.max_len[side] + MOVE_T - 1) / MOVE_T;
-    const int q = local / (sblocks * mblocks);
-    local -= q * sblocks * mblocks;
-    const int m0 = (local / sblocks) * MOVE_T, s0 = (local % sblocks) * MOVE_T;
+    const int q = local / sblocks;
+    const int s0 = (local - q * sblocks) * MOVE_T;
     const int32_t* __restrict__ lp = B.line_ptr[side];
-    const int len = lp[q + 1] - lp[q];
-    if (m0 >= len) return;
+    const int lq = lp[q];
+    const int len = lp[q + 1] - lq;
     const int S = B.S, ld = B.ld;
     const int64_t base = B.line_base[side][q];
     const int64_t* __restrict__ so = B.sys_off[side] + (int64_t)B.line_kind[side][q] * ld;
-    const int32_t* __restrict__ pos = B.line_pos[side] + lp[q];
+    const int32_t* __restrict__ pos = B.line_pos[side] + lq;
     double* __restrict__ vec = B.vec[slot];
     const int tx = threadIdx.x, ty = threadIdx.y;
     constexpr int P = MOVE_T + 1;
-    if (GATHER) {
+    const int s = s0 + tx;                                     // system on the tile-major side
+    const bool s_ok = s < S;
+    double* __restrict__ vcol = vec + db_tbase(s_ok ? s : 0, B.n);
+    // arena row bases of the (up to) 16 systems this thread touches on the line side
+    int64_t rowb[MOVE_T / 4];
+#pragma unroll
+    for (int i = 0; i < MOVE_T / 4; ++i) {
+        const int sr = s0 + ty + 4 * i;
+        rowb[i] = (sr < S) ? base + so[sr] : -1;
+    }
+    for (int m0 = 0; m0 < len; m0 += MOVE_T) {
+        if (m0 > 0) __syncthreads();                           // previous tile fully consumed
+        if (GATHER) {
+#pragma unroll
+            for (int i = 0; i < MOVE_T / 4; ++i) {
+                const int m = m0 + tx;
+                if (rowb[i] >= 0 && m < len) tile[(ty + 4 * i) * P + tx] = DB_LDCS(arena + rowb[i] + m);
+            }
+            __syncthreads();
 #pragma unroll 4
-        for (int r = ty; r < MOVE_T; r += 4) {
-            const int s = s0 + r, m = m0 + tx;
-            if (s < S && m < len) tile[r * P + tx] = DB_LDCS(arena + base + so[s] + m);
-        }
-        __syncthreads();
-        const int s = s0 + tx;
-        const int64_t tb = db_tbase(s < S ? s : 0, B.n);
+            for (int r = ty; r < MOVE_T; r += 4) {
+                const int m = m0 + r;
+                if (s_ok && m < len) vcol[(int64_t)pos[m] * DB_TILE] = tile[tx * P + r];
+            }
+        } else {
 #pragma unroll 4
-        for (int r = ty; r < MOVE_T; r += 4) {
-            const int m = m0 + r;
-            if (s < S && m < len) vec[tb + (int64_t)pos[m] * DB_TILE] = tile[tx * P + r];
-        }
-    } else {
-        const int s = s0 + tx;
-        const int64_t tb = db_tbase(s < S ? s : 0, B.n);
-#pragma unroll 4
-        for (int r = ty; r < MOVE_T; r += 4) {
-            const int m = m0 + r;
-            if (s < S && m < len) tile[tx * P + r] = DB_LDCS(vec + tb + (int64_t)pos[m] * DB_TILE);
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int r = ty; r < MOVE_T; r += 4) {
-            const int sr = s0 + r, m = m0 + tx;
-            if (sr < S && m < len) arena[base + so[sr] + m] = tile[r * P + tx];
+            for (int r = ty; r < MOVE_T; r += 4) {
+                const int m = m0 + r;
+                if (s_ok && m < len) tile[tx * P + r] = DB_LDCS(vcol + (int64_t)pos[m] * DB_TILE);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < MOVE_T / 4; ++i) {
+                const int m = m0 + tx;
+                if (rowb[i] >= 0 && m < len) arena[rowb[i] + m] = tile[(ty + 4 * i) * P + tx];
+            }
         }
     }
 }

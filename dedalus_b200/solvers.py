@@ -156,7 +156,7 @@ class BatchSet:
                 m = db.maps[side]
                 c.nlines[side], c.max_len[side] = m['nlines'], m['max_len']
                 c.blk_move[side] = blk[f'move{side}']
-                blk[f'move{side}'] += m['nlines'] * ((db.S + 63) // 64) * ((m['max_len'] + 63) // 64)     # MOVE_T in csrc/pencil.cu
+                blk[f'move{side}'] += m['nlines'] * ((db.S + 63) // 64)     # one CTA per (line, 64 systems): MOVE_T in csrc/pencil.cu
                 c.line_base[side], c.line_kind[side] = m['base'].data_ptr(), m['kind'].data_ptr()
                 c.line_ptr[side], c.line_pos[side], c.sys_off[side] = m['ptr'].data_ptr(), m['pos'].data_ptr(), m['sys_off'].data_ptr()
             t = db.t
