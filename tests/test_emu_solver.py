@@ -113,3 +113,20 @@ def test_solve_then_multiply_back_residual():
     examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
     solver.step(0.01)
     assert solve_residual(solver, 0.01) < 1e-11
+
+
+@pytest.mark.parametrize("dim,Nh,Nz,scheme,steps", [(2, 16, 16, "RK443", 2), (2, 16, 16, "RK111", 3), (3, 8, 8, "RK443", 2), (2, 16, 24, "SBDF2", 4)])
+def test_rayleigh_benard_schemes_match_oracle(dim, Nh, Nz, scheme, steps):
+    """More tableaux on the pencil path (several implicit stages sharing / not sharing a factorisation, multistep history
+    rotation) against the oracle's own IMEX loops (oracle/imex.py restates core/timesteppers.py:205-495, 647-740)."""
+    from oracle import rb_oracle
+    dt = 0.004
+    pb = examples.rayleigh_benard(dim=dim, Nh=Nh, Nz=Nz, Rayleigh=1e5)
+    solver = pb['problem'].build_solver(getattr(d3, scheme))
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    b0 = pb['b']['c'].copy()
+    for _ in range(steps):
+        solver.step(dt)
+    ref = rb_oracle.run(dim=dim, Nh=Nh, Nz=Nz, Ra=1e5, b0_c=b0, steps=steps, dt=dt, scheme=scheme)
+    for name in ("p", "b", "u"):
+        assert np.allclose(pb[name]['c'], ref[name], rtol=1e-8, atol=1e-12), name
