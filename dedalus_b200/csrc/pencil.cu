@@ -459,6 +459,115 @@ k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_sl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Software-pipelined variant (opt-in, DB_SOLVE_PIPE=1; not yet measured): the 16 gathers of chunk q+1 are issued BEFORE
+// chunk q is consumed, so a CTA that is alone on its SM (multi-GPU strong scaling: one or two tiles per SM) overlaps the
+// L2 / DRAM latency of the gathers with the dependent FMA chain of the previous chunk.  The hazard window grows by one
+// chunk: control word 35 (maskF2) marks the entries whose source row is stored in this or the previous chunk.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void solve_gather(const int* __restrict__ ctrl, const double* x, double (&xv)[SOLVE_CE])
+{
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; j += 4) {
+        const int4 g = *reinterpret_cast<const int4*>(ctrl + j);
+        xv[j] = x[g.x]; xv[j + 1] = x[g.y]; xv[j + 2] = x[g.z]; xv[j + 3] = x[g.w];
+    }
+}
+
+template <bool FWD>
+__device__ __forceinline__ double solve_chunk_pipe(const double* __restrict__ vals, const int* __restrict__ ctrl, double* x,
+                                                   double (&xv)[SOLVE_CE], double acc)
+{
+    const unsigned maskE = (unsigned)ctrl[2 * SOLVE_CE], maskB = (unsigned)ctrl[2 * SOLVE_CE + 1], maskL = (unsigned)ctrl[2 * SOLVE_CE + 3];
+    if ((maskB | maskL) == 0) {
+#pragma unroll
+        for (int j = 0; j < SOLVE_CE; ++j) acc = fma(-vals[j * DB_TILE], xv[j], acc);
+        return acc;
+    }
+    int goff[SOLVE_CE], foff[SOLVE_CE];
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; j += 4) {
+        const int4 g = *reinterpret_cast<const int4*>(ctrl + j);
+        goff[j] = g.x; goff[j + 1] = g.y; goff[j + 2] = g.z; goff[j + 3] = g.w;
+        const int4 f = *reinterpret_cast<const int4*>(ctrl + SOLVE_CE + j);
+        foff[j] = f.x; foff[j + 1] = f.y; foff[j + 2] = f.z; foff[j + 3] = f.w;
+    }
+#pragma unroll
+    for (int j = 0; j < SOLVE_CE; ++j) {
+        const double v = vals[j * DB_TILE];
+        if (maskL & (1u << j)) xv[j] = x[goff[j]];
+        const double acc_a = fma(-v, xv[j], acc);
+        const double val = FWD ? acc : acc * v;
+        if (maskE & (1u << j)) x[foff[j]] = val;
+        acc = (maskB & (1u << j)) ? xv[j] : acc_a;
+    }
+    return acc;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_batches_solve_pipe(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
+{
+    DB_SMEM(unsigned char, ring);
+    db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int tile = blockIdx.x - B.blk_solve;
+    const int s = tile * SOLVE_THREADS + threadIdx.x;
+    const int64_t tb = db_tbase(s, B.n);
+    const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
+    const int32_t* __restrict__ ctrl_g = B.ctrl;
+    const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
+    double* x = B.vec[x_slot] + tb;
+    const double* rv[NV];
+    double cf[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+    auto issue = [&](int q, int slot) {
+        unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+        db_mbar_expect_tx(&bars[slot], SOLVE_FSTAGE_BYTES);
+        db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &bars[slot]);
+        db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, ctrl_g + (int64_t)q * SOLVE_CTRL_WORDS, SOLVE_CTRL_WORDS * 4, &bars[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) db_mbar_init(&bars[i], 1);
+        db_mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
+    SOLVE_PROLOGUE(NV, B.n)
+    auto stage_ctrl = [&](int slot) { return reinterpret_cast<const int*>(ring + (size_t)slot * SOLVE_FSTAGE_BYTES + SOLVE_CE * DB_TILE * 8); };
+    int slot = 0;
+    unsigned phase = 0;
+    double acc = 0.0;
+    double xa[SOLVE_CE], xb[SOLVE_CE];
+    if (nchunks > 0) { db_mbar_wait(&bars[0], 0); solve_gather(stage_ctrl(0), x, xa); }
+    // two chunks per iteration so that the two gather buffers alternate without register copies
+    for (int q = 0; q < nchunks; q += 2) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int qq = q + half;
+            if (qq >= nchunks) break;
+            int nslot = slot + 1; unsigned nphase = phase;
+            if (nslot == nstages) { nslot = 0; nphase ^= 1; }
+            if (qq + 1 < nchunks) {                              // gather of the NEXT chunk goes out first
+                db_mbar_wait(&bars[nslot], nphase);
+                if (half == 0) solve_gather(stage_ctrl(nslot), x, xb); else solve_gather(stage_ctrl(nslot), x, xa);
+            }
+            const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+            const double* __restrict__ vals = reinterpret_cast<const double*>(st) + threadIdx.x;
+            const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+            if (qq < nfwd) acc = (half == 0) ? solve_chunk_pipe<true>(vals, ctrl, x, xa, acc) : solve_chunk_pipe<true>(vals, ctrl, x, xb, acc);
+            else acc = (half == 0) ? solve_chunk_pipe<false>(vals, ctrl, x, xa, acc) : solve_chunk_pipe<false>(vals, ctrl, x, xb, acc);
+            __syncthreads();                                   // both warps are done with this stage
+            if (threadIdx.x == 0 && qq + nstages < nchunks) issue(qq + nstages, slot);
+            slot = nslot; phase = nphase;
+        }
+    }
+}
+
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
                                 const db_slotcomb* rhs, void* stream)
 {
@@ -466,8 +575,11 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
     const dim3 g(total_blocks), b(SOLVE_THREADS);
     const int nv = rhs->nvec;
-    static int st_env = -1;
-    if (st_env < 0) { const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0; }
+    static int st_env = -1, pipe_env = 0;
+    if (st_env < 0) {
+        const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
+        const char* p = getenv("DB_SOLVE_PIPE"); pipe_env = p ? atoi(p) : 0;
+    }
     // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
     // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
     // per step); with few CTAs per SM the ring is the only source of memory parallelism, so it gets deep
@@ -476,8 +588,9 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (st_env >= 2 && st_env <= 24) nst = st_env;
     const size_t smem = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
 #define FLAT_GO(NV_) { static int attr_st = 0; \
-    if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_>)); attr_st = 1; } \
-    DB_LAUNCH((k_batches_solve_flat<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
+    if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_>)); DB_SET_SMEM_ATTR((k_batches_solve_pipe<NV_>)); attr_st = 1; } \
+    if (pipe_env && nst >= 2) DB_LAUNCH((k_batches_solve_pipe<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
+    else DB_LAUNCH((k_batches_solve_flat<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
     if (nv <= 1) FLAT_GO(1) else if (nv == 2) FLAT_GO(2) else if (nv == 3) FLAT_GO(3) else if (nv == 4) FLAT_GO(4)
     else if (nv == 5) FLAT_GO(5) else if (nv == 6) FLAT_GO(6) else if (nv <= 8) FLAT_GO(8) else if (nv <= 12) FLAT_GO(12) else FLAT_GO(16)
 #undef FLAT_GO

@@ -456,7 +456,9 @@ def solve_control_blocks(code, n_fwd, tile=64, CH=16):
         foff[16]  element offset of the row LEFT at a row-boundary entry
         maskE     entries that leave a row (store), maskB entries that enter a row (take the gathered start value),
         maskF     entries whose gathered value was stored inside this very chunk (re-read right before use)
-    Layout: int32 [nchunks][36] = goff, foff, maskE, maskB, maskF, 0."""
+        maskF2    the same for a gather issued ONE CHUNK EARLIER (software-pipelined kernel variant): stored inside this
+                  or the previous chunk
+    Layout: int32 [nchunks][36] = goff, foff, maskE, maskB, maskF, maskF2."""
     SKIP = -2**31
     code = np.asarray(code, dtype=np.int64)
     nE = len(code)
@@ -477,6 +479,8 @@ def solve_control_blocks(code, n_fwd, tile=64, CH=16):
             out[q, 33] |= 1 << j
             if stored_at.get(nxt, -1) >= q * CH:
                 out[q, 34] |= 1 << j
+            if stored_at.get(nxt, -1) >= (q - 1) * CH:
+                out[q, 35] |= 1 << j
             if cur >= 0:
                 out[q, 16 + j] = cur
                 out[q, 32] |= 1 << j
@@ -486,6 +490,8 @@ def solve_control_blocks(code, n_fwd, tile=64, CH=16):
             out[q, j] = c
             if stored_at.get(c, -1) >= q * CH:
                 out[q, 34] |= 1 << j
+            if stored_at.get(c, -1) >= (q - 1) * CH:
+                out[q, 35] |= 1 << j
     return out.astype(np.int32)
 
 

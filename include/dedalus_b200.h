@@ -207,7 +207,7 @@ typedef struct {
     const int32_t *l_ptr, *l_col, *l_mono; const double* l_val;
     const db_term *m_rec, *l_rec;      /* the same term lists packed 16 bytes per term (fused mat-vec kernel) */
     const int32_t* ctrl;               /* [n_entries/16][36] per-chunk control blocks of the branch-free solve kernel:
-                                          gather offsets[16], finished-row offsets[16], masks end / begin / late, 0  */
+                                          gather offsets[16], finished-row offsets[16], masks end / begin / late / late for a one-chunk-early gather */
     int32_t n_mono;
     int32_t mv_rows;                   /* rows per CTA of the fused mat-vec (= 32, MV_R in csrc/pencil.cu) */
     const int32_t* mv_win;             /* [ceil(n / mv_rows)][2]: first x row and row count (<= 80) of the shared-memory window of each row block */

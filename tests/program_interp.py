@@ -31,8 +31,9 @@ def factor(prog, LU):
     return LU
 
 
-def solve(prog, LU, rhs):
-    """Mirrors csrc/pencil.cu k_batches_solve_flat: x <- rhs; per 16-entry chunk the control block's 16 offsets are
+def solve(prog, LU, rhs, pipelined=False):
+    """Mirrors csrc/pencil.cu k_batches_solve_flat (pipelined=True: k_batches_solve_pipe, whose gathers are issued one chunk
+    early and which re-reads the entries of control word 35 instead of 34): x <- rhs; per 16-entry chunk the control block's 16 offsets are
     gathered in one burst, entries flagged in maskF are re-read right before use, row-boundary entries store the
     accumulator into the row being left (backward: times the reciprocal pivot) and continue from the gathered start
     value of the row being entered."""
@@ -42,11 +43,18 @@ def solve(prog, LU, rhs):
     ctrl = prog.ctrl
     nfwd = prog.n_fwd // CH
     acc = None
-    for q in range(prog.nE // CH):
+    nchunks = prog.nE // CH
+    gather = lambda q: [y[g // ld].copy() for g in ctrl[q, :16]]
+    nxt = gather(0) if pipelined else None
+    for q in range(nchunks):
         forward = q < nfwd
         goff, foff = ctrl[q, :16], ctrl[q, 16:32]
-        maskE, maskB, maskF = (int(ctrl[q, 32]) & 0xFFFF, int(ctrl[q, 33]) & 0xFFFF, int(ctrl[q, 34]) & 0xFFFF)
-        xv = [y[g // ld].copy() for g in goff]
+        maskE, maskB, maskF = (int(ctrl[q, 32]) & 0xFFFF, int(ctrl[q, 33]) & 0xFFFF, int(ctrl[q, 35 if pipelined else 34]) & 0xFFFF)
+        if pipelined:
+            xv = nxt
+            nxt = gather(q + 1) if q + 1 < nchunks else None          # issued before chunk q is consumed
+        else:
+            xv = gather(q)
         for j in range(CH):
             e = q * CH + j
             if maskF >> j & 1:

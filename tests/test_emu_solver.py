@@ -130,3 +130,33 @@ def test_rayleigh_benard_schemes_match_oracle(dim, Nh, Nz, scheme, steps):
     ref = rb_oracle.run(dim=dim, Nh=Nh, Nz=Nz, Ra=1e5, b0_c=b0, steps=steps, dt=dt, scheme=scheme)
     for name in ("p", "b", "u"):
         assert np.allclose(pb[name]['c'], ref[name], rtol=1e-8, atol=1e-12), name
+
+
+def test_software_pipelined_solve_variant_matches_oracle():
+    """DB_SOLVE_PIPE=1 (opt-in kernel k_batches_solve_pipe: gathers issued one chunk early) in a fresh process, because the
+    switch is read once per process; 3-D RB 8x8x16, dense threshold lowered so segmented rows and late re-reads occur."""
+    import subprocess, sys, os, pathlib
+    root = pathlib.Path(__file__).resolve().parents[1]
+    script = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from emu import emu_lib as E
+E.install()
+import numpy as np
+import dedalus_b200 as d3
+from dedalus_b200 import examples
+from oracle import rb_oracle
+pb = examples.rayleigh_benard(dim=3, Nh=8, Nz=16, Rayleigh=1e6)
+solver = pb['problem'].build_solver(d3.RK222)
+examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+b0 = pb['b']['c'].copy()
+for _ in range(2):
+    solver.step(0.01)
+ref = rb_oracle.run(dim=3, Nh=8, Nz=16, Ra=1e6, b0_c=b0, steps=2, dt=0.01, scheme="RK222")
+ok = all(np.allclose(pb[n]['c'], ref[n], rtol=1e-8, atol=1e-12) for n in ("p", "b", "u"))
+print("PIPE_OK" if ok else "PIPE_FAIL")
+""" % (str(root), str(root / "tests"))
+    for dense in ("64", "5"):
+        out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600,
+                             env=dict(os.environ, DB_SOLVE_PIPE="1", DB_SOLVE_DENSE=dense))
+        assert "PIPE_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]

@@ -25,6 +25,7 @@ def test_rb_programs_solve(dim, Nh, Nz, dt, dense):
         LU = pi.factor(prog, pi.assemble(prog, asm))
         rhs = rng.standard_normal((prog.n, prog.S))
         x = pi.solve(prog, LU, rhs)
+        assert np.allclose(pi.solve(prog, LU, rhs, pipelined=True), x, rtol=0, atol=0)      # one-chunk-early gathers + word-35 re-reads
         xm = rng.standard_normal((prog.n, prog.S))
         Mx = pi.matvec(prog, 'M', xm); Lx = pi.matvec(prog, 'L', xm)
         for s in range(0, prog.S, max(1, prog.S // 5)):
