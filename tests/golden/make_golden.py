@@ -219,6 +219,39 @@ def gen_ivps():
     print({k: v for k, v in chk.items()})
 
 
+def gen_transforms_bench():
+    """Reference transform outputs AT THE BENCHMARK LINE LENGTHS (256 -> 384 and 128 -> 192, dealias 3/2) in layouts the
+    register-resident kernels take: real Fourier on a strided axis with 16 lines, Chebyshev on contiguous lines (alpha 0 and 2)."""
+    rng = np.random.default_rng(4321)
+    out = {}
+    for (M, N) in [(256, 384), (128, 192)]:
+        plan = rbasis.RealFourier.transforms["scipy"](N, M)
+        c = rng.standard_normal((1, M, 16)); c[:, 1, :] = 0
+        g = np.zeros((1, N, 16)); plan.backward(c.copy(), g, 1)
+        gg = rng.standard_normal((1, N, 16)); cc = np.zeros((1, M, 16)); plan.forward(gg.copy(), cc, 1)
+        out[f"rf_{M}_{N}_cin"] = c; out[f"rf_{M}_{N}_gout"] = g; out[f"rf_{M}_{N}_gin"] = gg; out[f"rf_{M}_{N}_cout"] = cc
+        for alpha in ((0, 2) if M == 256 else (2,)):
+            a = alpha - 0.5
+            plan = rbasis.Jacobi.transforms["scipy_dct"](N, M, a, a, -0.5, -0.5)
+            c = rng.standard_normal((17, M)); g = np.zeros((17, N)); plan.backward(c.copy(), g, 1)
+            gg = rng.standard_normal((17, N)); cc = np.zeros((17, M)); plan.forward(gg.copy(), cc, 1)
+            key = f"ch_{M}_{N}_{alpha}"
+            out[key + "_cin"] = c; out[key + "_gout"] = g; out[key + "_gin"] = gg; out[key + "_cout"] = cc
+    np.savez_compressed(HERE / "transforms_bench.npz", **out)
+    print("transforms_bench.npz", len(out), "arrays")
+
+
+def gen_rb3d_16():
+    """16^3 (24-point dealiased lines: the smallest size at which the register-resident FFT / Chebyshev kernels run)."""
+    r = rb(3, 16, 16, steps=3, tstep=0.01, Ra=1e6)
+    np.savez_compressed(HERE / "rb3d_16.npz", **{k: v for k, v in r.items() if not k.startswith('pen_')})
+
+
+if __name__ == "__main__" and ("rb3d_16" in sys.argv[1:] or "transforms_bench" in sys.argv[1:]):
+    if "rb3d_16" in sys.argv[1:]: gen_rb3d_16()
+    if "transforms_bench" in sys.argv[1:]: gen_transforms_bench()
+    sys.exit(0)
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["transforms", "ivps"]
     if "transforms" in which: gen_transforms()

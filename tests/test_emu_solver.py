@@ -160,3 +160,20 @@ print("PIPE_OK" if ok else "PIPE_FAIL")
         out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600,
                              env=dict(os.environ, DB_SOLVE_PIPE="1", DB_SOLVE_DENSE=dense))
         assert "PIPE_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
+
+
+def test_rb3d_16_matches_reference_fixture(golden):
+    """16^3 against the UNMODIFIED reference's states (tests/golden/rb3d_16.npz): the smallest size at which the
+    register-resident Fourier / Chebyshev kernels sit on the solver's path."""
+    g = golden("rb3d_16.npz")
+    pb = examples.rayleigh_benard(dim=3, Nh=16, Nz=16, Rayleigh=float(g['Ra']))
+    solver = pb['problem'].build_solver(getattr(d3, str(g['scheme'])))
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    assert np.allclose(pb['b']['c'], g['b0_c'], rtol=1e-12, atol=1e-14)
+    for i in range(int(g['steps'])):
+        solver.step(float(g['dt']))
+        if i == 0:
+            for name in ('p', 'b', 'u'):
+                assert np.allclose(pb[name]['c'], g[f"{name}_c_step1"], **TOL), name
+    for name in ('p', 'b', 'u'):
+        assert np.allclose(pb[name]['c'], g[f"{name}_c"], **TOL), name

@@ -281,3 +281,46 @@ def test_blocked_row_addressing_equals_pack_transform_unpack(M, N, P):
         assert lib.call_optional("db_rfft_forward_blocked", plan.ref(), E.ptr(gin.reshape(-1)[f * per_field_out:]), E.ptr(cout.reshape(-1)[f * per_field_in:]),
                                  outer, M, inner, N // P, nf * per_field_out, M // P, nf * per_field_in, None)
     assert np.array_equal(cout, blocked(c_ref, M, M // P))
+
+
+def test_register_kernels_match_reference_at_benchmark_lengths(golden):
+    """The UNMODIFIED reference's own transforms (ScipyRealFFT, ScipyFastChebyshev; tests/golden/transforms_bench.npz) at the
+    256 -> 384 and 128 -> 192 line lengths, in the layouts the register-resident kernels take."""
+    from dedalus_b200.transforms import banded_upper_diags
+    g = golden("transforms_bench.npz"); lib = E.emu()
+    for (M, N) in [(256, 384), (128, 192)]:
+        plan = E.EmuPlan(N, 'real')
+        cin, gout = g[f"rf_{M}_{N}_cin"], g[f"rf_{M}_{N}_gout"]
+        served = lib.rfft_regs_launches()
+        out = np.full_like(gout, np.nan)
+        lib.call("db_rfft_backward", plan.ref(), E.ptr(np.ascontiguousarray(cin)), E.ptr(out), cin.shape[0], M, cin.shape[2], 0, 0.0, None)
+        assert np.allclose(out, gout, rtol=1e-12, atol=1e-12)
+        gin, cout = g[f"rf_{M}_{N}_gin"], g[f"rf_{M}_{N}_cout"]
+        out = np.full_like(cout, np.nan)
+        lib.call("db_rfft_forward", plan.ref(), E.ptr(np.ascontiguousarray(gin)), E.ptr(out), gin.shape[0], M, gin.shape[2], None)
+        assert np.allclose(out, cout, rtol=1e-12, atol=1e-12)
+        assert lib.rfft_regs_launches() == served + 2
+        for alpha in ((0, 2) if M == 256 else (2,)):
+            key = f"ch_{M}_{N}_{alpha}"
+            a = alpha - 0.5
+            cin, gout, gin, cout = (g[key + s] for s in ("_cin", "_gout", "_gin", "_cout"))
+            lines = cin.shape[0]
+            # backward from the (a, a) basis = back-conversion to Chebyshev-T coefficients (host, exact banded solve), then DCT-III
+            served = lib.rfft_regs_launches()
+            if alpha:
+                Cm = jacobi.conversion_matrix(M, -0.5, -0.5, a, a).toarray()
+                c0 = np.linalg.solve(Cm, cin.T).T
+            else:
+                c0 = cin
+            out = np.full_like(gout, np.nan)
+            lib.call("db_cheb_backward", plan.ref(), E.ptr(np.ascontiguousarray(c0)), E.ptr(out), lines, M, 1, None, 0, None, 0, None)
+            assert np.allclose(out, gout, rtol=1e-10, atol=1e-10 * np.abs(gout).max())
+            out = np.full_like(cout, np.nan)
+            if alpha:
+                nd = 2 * alpha + 1
+                dg = banded_upper_diags(jacobi.conversion_matrix(max(M, N), -0.5, -0.5, a, a), M, nd)
+                lib.call("db_cheb_forward", plan.ref(), E.ptr(np.ascontiguousarray(gin)), E.ptr(out), lines, M, 1, E.ptr(dg), nd, None)
+            else:
+                lib.call("db_cheb_forward", plan.ref(), E.ptr(np.ascontiguousarray(gin)), E.ptr(out), lines, M, 1, None, 0, None)
+            assert np.allclose(out, cout, rtol=1e-11, atol=1e-11 * np.abs(cout).max())
+            assert lib.rfft_regs_launches() == served + 2

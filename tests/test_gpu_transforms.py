@@ -196,3 +196,36 @@ def test_chebyshev_derivative_fused_scan_matches_matrices(M, N):
     z = jacobi.gauss_grid(N, -0.5, -0.5)[0]
     ref = dc @ jacobi.polynomials(M, 0.5, 0.5, z)
     assert np.allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+
+
+def test_register_kernels_match_reference_at_benchmark_lengths(golden):
+    """The UNMODIFIED reference's own transforms (ScipyRealFFT, ScipyFastChebyshev; tests/golden/transforms_bench.npz) at the
+    256 -> 384 and 128 -> 192 line lengths through the plugins, in the layouts the register-resident kernels take."""
+    import torch
+    from dedalus_b200.transforms import RealFourierTransform, FastChebyshevTransform
+    from dedalus_b200.lib import get_lib
+    g = golden("transforms_bench.npz")
+    for (M, N) in [(256, 384), (128, 192)]:
+        rf = RealFourierTransform(N, M)
+        served = get_lib().rfft_regs_launches()
+        out = torch.full(g[f"rf_{M}_{N}_gout"].shape, float('nan'), dtype=torch.float64, device='cuda')
+        rf.backward(_t(g[f"rf_{M}_{N}_cin"]), out, 1)
+        assert np.allclose(out.cpu().numpy(), g[f"rf_{M}_{N}_gout"], **TOL)
+        out = torch.full(g[f"rf_{M}_{N}_cout"].shape, float('nan'), dtype=torch.float64, device='cuda')
+        rf.forward(_t(g[f"rf_{M}_{N}_gin"]), out, 1)
+        assert np.allclose(out.cpu().numpy(), g[f"rf_{M}_{N}_cout"], **TOL)
+        assert get_lib().rfft_regs_launches() == served + 2
+        for alpha in ((0, 2) if M == 256 else (2,)):
+            key = f"ch_{M}_{N}_{alpha}"
+            a = alpha - 0.5
+            plan = FastChebyshevTransform(N, M, a, a, -0.5, -0.5)
+            served = get_lib().rfft_regs_launches()
+            gout = g[key + "_gout"]
+            out = torch.full(gout.shape, float('nan'), dtype=torch.float64, device='cuda')
+            plan.backward(_t(g[key + "_cin"]), out, 1)
+            assert np.allclose(out.cpu().numpy(), gout, rtol=1e-10, atol=1e-10 * np.abs(gout).max())
+            cout = g[key + "_cout"]
+            out = torch.full(cout.shape, float('nan'), dtype=torch.float64, device='cuda')
+            plan.forward(_t(g[key + "_gin"]), out, 1)
+            assert np.allclose(out.cpu().numpy(), cout, rtol=1e-11, atol=1e-11 * np.abs(cout).max())
+            assert get_lib().rfft_regs_launches() == served + 2

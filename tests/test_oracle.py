@@ -58,7 +58,7 @@ def test_rb_pencil_matrices(golden, fname, groups):
 
 
 @pytest.mark.parametrize("fname,transforms", [("rb3d_8.npz", "fft"), ("rb3d_8.npz", "matrix"), ("rb2d_16x16.npz", "fft"),
-                                              ("rb3d_8x8x12_sbdf2.npz", "fft")])
+                                              ("rb3d_8x8x12_sbdf2.npz", "fft"), ("rb3d_16.npz", "fft")])
 def test_rb_states(golden, fname, transforms):
     g = golden(fname)
     st = rb_oracle.run(int(g['dim']), int(g['Nh']), int(g['Nz']), float(g['Ra']), g['b0_c'], int(g['steps']), float(g['dt']),
