@@ -177,3 +177,19 @@ def test_rb3d_16_matches_reference_fixture(golden):
                 assert np.allclose(pb[name]['c'], g[f"{name}_c_step1"], **TOL), name
     for name in ('p', 'b', 'u'):
         assert np.allclose(pb[name]['c'], g[f"{name}_c"], **TOL), name
+
+
+def test_global_flow_property_reductions():
+    """GlobalFlowProperty.max / min (reference extras/flow_tools.py:64-130: reductions of the grid data of a field) equal the
+    same reductions of the field's grid values read back through the host mirror."""
+    from dedalus_b200.extras import flow_tools
+    pb = examples.rayleigh_benard(dim=2, Nh=16, Nz=16, Rayleigh=1e5)
+    solver = pb['problem'].build_solver(d3.RK222)
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    for _ in range(2):
+        solver.step(0.01)
+    flow = flow_tools.GlobalFlowProperty(solver, cadence=1)
+    flow.add_property(pb['b'], name='b')
+    vmax, vmin = flow.max('b'), flow.min('b')
+    bg = np.array(pb['b']['g'])
+    assert np.isclose(vmax, bg.max(), rtol=1e-13, atol=0) and np.isclose(vmin, bg.min(), rtol=1e-13, atol=1e-15)
