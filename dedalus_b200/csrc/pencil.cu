@@ -875,3 +875,49 @@ extern "C" int db_batches_factor(const db_batch* batches, int32_t nbatch, int32_
     DB_LAUNCH(k_batches_factor, dim3(total_blocks), dim3(SOLVE_THREADS), 0, stream, batches, nbatch, lu_slot);
     return db_check_launch("batches_factor");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Verification of a factorisation (no reference counterpart: SuperLU pivots every pencil separately,
+// libraries/matsolvers.py:179-183; a pivot order shared by a batch has to be CHECKED for every member).  After
+// x = LU^{-1} b (db_batches_solve) and Mx, Lx (db_batches_matvec) of a probe right-hand side b:
+//     out[system] = max_i |a0 (Mx)_i + b0 (Lx)_i - b_i| / (max_i |b_i| + max_i |a0 (Mx)_i| + max_i |b0 (Lx)_i|)
+// i.e. the normwise backward error of the solve; non-finite values give +inf.  One thread per system (coalesced
+// rows), same block map as the solve.  out has total_blocks * 64 entries (padding lanes: 0).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_batches_residual(const db_batch* __restrict__ batches, int nbatch, int b_slot, int m_slot, int l_slot, double a0, double b0,
+                   double* __restrict__ out)
+{
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
+    double res = 0.0;
+    if (s < B.S) {
+        const int64_t tb = db_tbase(s, B.n);
+        const double* __restrict__ b = B.vec[b_slot] + tb;
+        const double* __restrict__ m = B.vec[m_slot] + tb;
+        const double* __restrict__ l = B.vec[l_slot] + tb;
+        double rmax = 0.0, bmax = 0.0, mmax = 0.0, lmax = 0.0;
+        bool finite = true;
+        for (int i = 0; i < B.n; ++i) {
+            const double bv = b[(int64_t)i * DB_TILE], mv = a0 * m[(int64_t)i * DB_TILE], lv = b0 * l[(int64_t)i * DB_TILE];
+            const double r = (mv + lv) - bv;
+            if (!(fabs(r) < 1e300)) finite = false;
+            rmax = fmax(rmax, fabs(r)); bmax = fmax(bmax, fabs(bv)); mmax = fmax(mmax, fabs(mv)); lmax = fmax(lmax, fabs(lv));
+        }
+        const double den = bmax + mmax + lmax;
+        res = !finite ? 1e300 * 1e300 : (den > 0.0 ? rmax / den : 0.0);
+    }
+    out[(int64_t)blockIdx.x * SOLVE_THREADS + threadIdx.x] = res;
+}
+
+extern "C" int db_batches_residual(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t b_slot, int32_t m_slot,
+                                   int32_t l_slot, double a0, double b0, double* out, void* stream)
+{
+    if (nbatch <= 0 || total_blocks <= 0) return 0;
+    if (b_slot < 0 || m_slot < 0 || l_slot < 0 || b_slot >= DB_MAX_VECS || m_slot >= DB_MAX_VECS || l_slot >= DB_MAX_VECS) {
+        db_set_error("batches_residual: bad slots"); return 1;
+    }
+    DB_LAUNCH(k_batches_residual, dim3(total_blocks), dim3(SOLVE_THREADS), 0, stream, batches, nbatch, b_slot, m_slot, l_slot, a0, b0, out);
+    return db_check_launch("batches_residual");
+}

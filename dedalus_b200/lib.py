@@ -75,6 +75,7 @@ SIGNATURES = {
     "db_batches_solve": (C.c_int, [vp, i32, i32, i32, i32, C.c_void_p, vp]),
     "db_batches_assemble": (C.c_int, [vp, i32, i32, i32, vp]),
     "db_batches_factor": (C.c_int, [vp, i32, i32, i32, vp]),
+    "db_batches_residual": (C.c_int, [vp, i32, i32, i32, i32, i32, f64, f64, vp, vp]),
     "db_lincomb_apply": (C.c_int, [PLIN, vp, i64, vp]),
     "db_transpose_pack": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
     "db_transpose_unpack": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),

@@ -65,7 +65,7 @@ def matvec_windows(prog, R, wmax):
 class DeviceBatch:
     """Device copies of one batch's programs and work vectors (kept alive for the fused descriptors)."""
 
-    def __init__(self, solver, batch, a0, b0, nslots):
+    def __init__(self, solver, batch, a0, b0, nslots, vecs=None):
         import torch
         self.batch, self.solver = batch, solver
         dev = solver.device
@@ -113,7 +113,8 @@ class DeviceBatch:
         ptr, mono_i, val = assembly_program(batch, prog, a0, b0)
         self.t['asm_ptr'], self.t['asm_mono'], self.t['asm_val'] = f(ptr), f(mono_i), d(val)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.vecs = [torch.zeros(self.n * ld, dtype=torch.float64, device=dev) for _ in range(nslots)]
+        # work vectors survive a re-ordering of the batch (row-space vectors are unaffected by a new pivot column order)
+        self.vecs = vecs if vecs is not None else [torch.zeros(self.n * ld, dtype=torch.float64, device=dev) for _ in range(nslots)]
         self.lu = {}
 
     def lu_tensor(self, slot):
@@ -131,14 +132,26 @@ class DeviceBatch:
 class BatchSet:
     """All batches of a solver behind ONE device descriptor array (include/dedalus_b200.h: db_batch)."""
 
+    # relative backward error above which a factorisation is rejected (a healthy static order gives 1e-16 .. 1e-13; the
+    # unstable orders of round 1 gave 1e-4 .. 1)
+    VERIFY_TOL = 1e-10
+
     def __init__(self, solver, a0, b0, nslots, nlu):
-        import torch
-        from .lib import Batch as CBatch, DB_MAX_VECS, DB_MAX_LU
+        from .lib import DB_MAX_VECS, DB_MAX_LU
         if nslots > DB_MAX_VECS or nlu > DB_MAX_LU:
             raise NotImplementedError("too many work vectors / factor sets for the fused batch descriptor")
         self.solver = solver
+        self.nslots, self.nlu = nslots, nlu
         self.items = [DeviceBatch(solver, b, a0, b0, nslots) for b in solver.batches]
         self.nb = len(self.items)
+        self.reorders = 0            # number of batches whose pivot order had to be recomputed after a failed verification
+        self.last_verify = None
+        self._build_descriptors()
+
+    def _build_descriptors(self):
+        import torch
+        from .lib import Batch as CBatch
+        solver, nlu = self.solver, self.nlu
         arr = (CBatch * max(self.nb, 1))()
         blk = dict(solve=0, matvec=0, move0=0, move1=0, asm=0)
         for i, db in enumerate(self.items):
@@ -216,6 +229,69 @@ class BatchSet:
         bad = sum(int(db.info.item()) for db in self.items)
         if bad:
             raise DedalusB200Error(f"{bad} pencil systems hit a zero / non-finite pivot during factorisation.")
+
+    # ---- verification of the shared pivot order (every system, after every factorisation) -------------------
+    def probe(self, lu_slot, a0, b0, slots, seed=1234):
+        """Relative backward error of  x = LU^{-1} b  for a random b, per system: list over batches of numpy arrays.
+        slots = (b, x, Mx, Lx) work-vector slots that may be overwritten."""
+        import torch
+        s_b, s_x, s_m, s_l = slots
+        dev = self.solver.device
+        gen = torch.Generator(device=dev); gen.manual_seed(seed)
+        for db in self.items:
+            db.vecs[s_b].normal_(generator=gen)
+        self.solve(lu_slot, s_x, [(s_b, 1.0)])
+        self.matvec(s_x, s_m, s_l)
+        nblk = self.blocks['solve']
+        out = torch.zeros(nblk * 64, dtype=torch.float64, device=dev)
+        self._call("db_batches_residual", nblk, s_b, s_m, s_l, float(a0), float(b0), out.data_ptr())
+        host = out.cpu().numpy()
+        res, start = [], 0
+        for db in self.items:
+            res.append(host[start:start + db.S].copy())
+            start += ((db.S + 63) // 64) * 64
+        return res
+
+    def factor_verified(self, lhs, slots):
+        """lhs: list of (lu_slot, a0, b0).  Factorise every a0 M + b0 L into its slot and verify every system of every batch
+        (probe()).  Batches with a member above VERIFY_TOL get a new pivot order -- true partial pivoting on the
+        representatives plus the offending members, jointly at every LHS seen so far -- and all sets are factorised again;
+        raises if that does not help.  Returns the worst backward error (also kept in `last_verify`)."""
+        lhs_seen = self.__dict__.setdefault('_lhs_seen', [])
+        for _, a0, b0 in lhs:
+            if (float(a0), float(b0)) not in lhs_seen:
+                lhs_seen.append((float(a0), float(b0)))
+        del lhs_seen[:-6]
+        for attempt in range(3):
+            worst, failing = 0.0, {}
+            for lu_slot, a0, b0 in lhs:
+                self.factor(lu_slot, a0, b0)
+                self.check_info()
+                for i, r in enumerate(self.probe(lu_slot, a0, b0, slots)):
+                    if not r.size:
+                        continue
+                    r = np.nan_to_num(r, nan=np.inf)
+                    worst = max(worst, float(r.max()))
+                    if not r.max() <= self.VERIFY_TOL:
+                        bad = [int(j) for j in np.argsort(-r)[:4] if r[int(j)] > self.VERIFY_TOL]
+                        failing.setdefault(i, []).extend(bad)
+            self.last_verify = worst
+            if not failing:
+                return worst
+            if attempt == 2:
+                break
+            a0, b0 = lhs[0][1], lhs[0][2]
+            for i, members in failing.items():
+                db = self.items[i]
+                extra = getattr(db.batch, 'extra_groups', []) + [db.batch.groups[j] for j in sorted(set(members))]
+                db.batch.extra_groups = extra[-8:]
+                db.batch.compute_ordering(a0, b0, threshold=1.0, extra_groups=db.batch.extra_groups,
+                                          extra_lhs=[ab for ab in lhs_seen if ab != (float(a0), float(b0))])
+                self.items[i] = DeviceBatch(self.solver, db.batch, a0, b0, self.nslots, vecs=db.vecs)
+                self.reorders += 1
+            self._build_descriptors()
+        raise DedalusB200Error(f"pencil factorisation failed verification: backward error {worst:.2e} > {self.VERIFY_TOL:.0e} "
+                               f"in batches {sorted(failing)} after re-ordering.")
 
 
 class InitialValueSolver:
@@ -396,16 +472,17 @@ class InitialValueSolver:
         sim_time_0 = self.sim_time
         bs = self.bset
         if update:
-            # one factorisation per distinct H_ii (RK222 and RK443 share a single one across stages)
+            # one factorisation per distinct H_ii (RK222 and RK443 share a single one across stages), each verified on the
+            # device for every system; the probe overwrites X, MX0, LX[0], F[0], all of which are rebuilt below
             self._stage_lu = []
             done = {}
             for i in range(1, cls.stages + 1):
                 hii = float(H[i, i])
                 if hii not in done:
                     done[hii] = len(done)
-                    bs.factor(done[hii], 1.0, k * hii)
                 self._stage_lu.append(done[hii])
-            self._check_factor_info()
+            bs.factor_verified([(slot, 1.0, k * hii) for hii, slot in done.items()],
+                               (self.slot_F[0], self.slot_X, self.slot_MX0, self.slot_LX[0]))
         bs.move(0, True, self.slot_X, self.state_t)
         bs.matvec(self.slot_X, self.slot_MX0, self.slot_LX[0])
         for i in range(1, cls.stages + 1):
@@ -437,10 +514,10 @@ class InitialValueSolver:
         update = (key != self._lhs_key)
         self._lhs_key = key
         bs = self.bset
-        if update:
-            bs.factor(0, float(a[0]), float(b[0]))
-            self._check_factor_info()
         self.slot_MX.rotate(); self.slot_LX.rotate(); self.slot_F.rotate()
+        if update:
+            # the probe overwrites X and the oldest history vectors, which this step overwrites anyway
+            bs.factor_verified([(0, float(a[0]), float(b[0]))], (self.slot_F[0], self.slot_X, self.slot_MX[0], self.slot_LX[0]))
         bs.move(0, True, self.slot_X, self.state_t)
         bs.matvec(self.slot_X, self.slot_MX[0], self.slot_LX[0])
         self.rhs_plan.evaluate(self.eq_t)

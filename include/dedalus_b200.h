@@ -239,6 +239,14 @@ int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_bloc
 int db_batches_assemble(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, void* stream);
 int db_batches_factor(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, void* stream);
 
+/* Verification of a factorisation with a probe right-hand side: given b = vec[b_slot], x = LU^{-1} b (db_batches_solve) and
+ * vec[m_slot] = M x, vec[l_slot] = L x (db_batches_matvec), writes per system (index = solve block * 64 + lane, padding lanes 0)
+ *     max_i |a0 (Mx)_i + b0 (Lx)_i - b_i| / (max|b| + max|a0 Mx| + max|b0 Lx|)       (+inf if anything is non-finite)
+ * No reference counterpart: the reference's SuperLU pivots each pencil on its own (libraries/matsolvers.py:126-183); a pivot
+ * order shared by a whole batch must be checked for every member after each factorisation (core/timesteppers.py:632-639). */
+int db_batches_residual(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t b_slot, int32_t m_slot,
+                        int32_t l_slot, double a0, double b0, double* out, void* stream);
+
 /* out = sum_j coef[j]*vecs[j] over `count` doubles (explicit RHS build, used by tests and diagnostics). */
 int db_lincomb_apply(const db_lincomb* terms, double* out, int64_t count, void* stream);
 

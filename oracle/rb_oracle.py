@@ -355,13 +355,20 @@ class RBOracle:
         return st
 
 
-def run(dim, Nh, Nz, Ra, b0_c, steps, dt, scheme="RK222", transforms="fft"):
+def run(dim, Nh, Nz, Ra, b0_c, steps, dt, scheme="RK222", transforms="fft", u0_c=None):
+    """`dt` may be a sequence (one value per step: every change drops the factorisations like the reference,
+    core/timesteppers.py:577-583); `u0_c` an initial velocity (default 0, the stock scripts' initial condition)."""
     orc = RBOracle(dim, Nh, Nz, Ra, transforms=transforms)
     st = orc.new_state(b0_c)
+    if u0_c is not None:
+        st['u'] = np.array(u0_c, dtype=float, copy=True)
     hist = dict(it=0, dts=[], MX=[], LX=[], F=[])
-    for _ in range(steps):
+    dts = list(dt) if np.ndim(dt) else [dt] * steps
+    for i in range(steps):
+        if i and dts[i] != dts[i - 1]:
+            orc.lu_cache.clear()
         if scheme == "SBDF2":
-            orc.step_sbdf2(st, dt, hist)
+            orc.step_sbdf2(st, dts[i], hist)
         else:
-            orc.step_rk(st, dt, scheme)
+            orc.step_rk(st, dts[i], scheme)
     return st

@@ -1,6 +1,6 @@
 """Kernel logic of csrc/fft.cu executed under the test-only CPU emulation (tests/emu) against the reference
 outputs in tests/golden/transforms.npz (ScipyRealFFT / RealFourierMMT / ScipyComplexFFT / ScipyFastChebyshev /
-JacobiMMT dumped by make_golden.py).  The same comparisons run on the real GPU in test_gpu_transforms.py."""
+JacobiMMT dumped by make_golden.py).  The same comparisons run on the real GPU in test_gpu_0_transforms.py."""
 import numpy as np, pytest, ctypes as C
 from dedalus_b200 import jacobi
 from emu import emu_lib as E
