@@ -8,8 +8,9 @@ A "step" is one full solver.step(dt): 2 IMEX stages, each = RHS evaluation (15 b
 transforms and the fused products), template mat-vecs, RHS combination + per-pencil LU solves, scatter.
 `value` times K steps with the state resident in HBM (CUDA events, barrier + synchronize both sides, max over
 ranks); `e2e` times the same K steps through the public API with the state uploaded from pinned host memory and
-read back every step.  `--impl reference` times the oracle's CPU restatement of the reference algorithm
-(oracle/cpu_bench.py) on a bounded sample with all host cores.
+read back every step.  Before anything is timed a parity gate steps a tall (16 x 16 x N) problem on the same ranks against
+the CPU oracle.  `--impl reference` times the UNMODIFIED reference (baseline/_ref, oracle/ref_bench.py) on a bounded sample
+of the workload with all host cores (the oracle port, oracle/cpu_bench.py, if the reference did not travel).
 """
 import argparse, json, os, subprocess, sys, threading, time, pathlib
 import numpy as np
@@ -30,6 +31,7 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -88,30 +90,94 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def cpu_arm(args, cfg, warmup, steps):
+    """CPU arm on this host: the UNMODIFIED reference (baseline/_ref, oracle/ref_bench.py) when it travelled with the
+    snapshot, else the oracle port (oracle/cpu_bench.py).  Returns (value, cpu_baseline dict, extra)."""
+    from oracle import ref_bench
+    if args.dim == 3 and ref_bench.available() and not os.environ.get("DB_BENCH_PORT"):
+        r = ref_bench.run(N=args.size, dt=cfg['dt'], warmup=warmup, steps=steps)
+        cb = dict(value=r['steps_per_sec'], unit="steps/s", cores=r['cores'], kind="reference", sample=r['sample'],
+                  spread=r['spread'], per_step=r['steps_per_sec_list'], sample_step_seconds=r['sample_step_seconds'],
+                  setup_seconds=r['setup_seconds'])
+        return r['steps_per_sec'], cb
+    from oracle import cpu_bench
+    cores = os.cpu_count() or 1
+    slab = 16 if args.size >= 128 else 8
+    info = cpu_bench.sampled_step(dim=args.dim, N=args.size, dt=cfg['dt'], cores=cores, slab=min(slab, args.size),
+                                  n_pencils=2 * cores, reps=warmup + steps)
+    vals = info['steps_per_sec_list'][warmup:]
+    v = float(np.median(vals))
+    return v, dict(value=v, unit="steps/s", cores=info['cores'], kind="port", sample=info['sample'])
+
+
 def run_reference(args):
-    """CPU arm: oracle restatement of the reference algorithm, bounded sample, all host cores (rank 0 only)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cpu_bench
     cfg = workload(args)
-    cores = os.cpu_count() or 1
-    # ONE sample set-up (slabs, pencil matrices, factorisations: untimed, as the reference reuses them at constant dt), then
-    # warm-up + timed repetitions of the sampled step on it; bounded so the whole arm ends within a few minutes
-    n_warm = min(args.warmup, 1)
-    n_runs = max(1, min(args.steps, 3))
-    slab = 16 if args.size >= 128 else 8
-    info = cpu_bench.sampled_step(dim=args.dim, N=args.size, dt=cfg['dt'], cores=cores, slab=min(slab, args.size),
-                                  n_pencils=2 * cores, reps=n_warm + n_runs)
-    vals = info['steps_per_sec_list'][n_warm:]
-    v = float(np.median(vals))
+    # bounded: the sample's set-up (per-pencil matrix assembly + SuperLU factorisations, untimed as in the reference's own
+    # warm-up) dominates the wall time; at most 2 warm-up and 12 timed sample steps keep the arm within a few minutes
+    n_warm = max(1, min(args.warmup, 2))
+    n_runs = max(3, min(args.steps, 12))
+    v, cb = cpu_arm(args, cfg, n_warm, n_runs)
     line = dict(impl="reference", metric=METRIC, value=v, unit="steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 / v, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                config=cfg,
-                cpu_baseline=dict(value=v, unit="steps/s", cores=info['cores'], kind="port", sample=info['sample']),
-                e2e=dict(value=v, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                note="oracle port of the reference CPU path (scipy pocketfft + SuperLU); the Python reference itself cannot travel to the GPU box")
+                config=dict(cfg, timed_sample_steps=n_runs, sample_warmup=n_warm), cpu_baseline=cb,
+                e2e=dict(value=v, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                note=("value = whole-256^3-step throughput of the host derived from a bounded sample (see cpu_baseline.sample): "
+                      "ms_per_step is 1000 / value, not the wall time of a sample step (cpu_baseline.sample_step_seconds)"))
     print(json.dumps(line))
+
+
+def parity_gate(args, world, rank):
+    """Correctness gate in front of the timing: a TALL problem -- the benchmark's Nz, 16 x 16 horizontal
+    modes (the benchmark's pencil systems, 1/256 of them), distributed over the same ranks -- stepped 2 RK222 steps on the
+    GPU(s) against the CPU oracle on rank 0.  Returns dict(max_rel, ok, ...)."""
+    import torch
+    import torch.distributed as dist
+    import dedalus_b200 as d3
+    from dedalus_b200 import examples
+    N = args.size
+    Nh = max(16, 2 * world)
+    dt = 1e-2 * 64.0 / N
+    t0 = time.time()
+    pb = examples.rayleigh_benard(dim=args.dim, Nh=Nh, Nz=N, Rayleigh=1e6, mesh=(world,) if world > 1 else None)
+    solver = pb['problem'].build_solver(d3.RK222)
+    examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+    u = pb['u']
+    u.fill_random('g', seed=7, distribution='normal', scale=1.0)
+    uc = np.array(u['c']); uc[..., N // 2:] = 0; u['c'] = uc
+    b0, u0 = np.array(pb['b']['c']), np.array(pb['u']['c'])
+    steps = 2
+    for _ in range(steps):
+        solver.step(dt)
+    got = {n: np.array(pb[n]['c']) for n in ("p", "b", "u")}
+    verify = float(solver.bset.last_verify)
+    blocked = world > 1 and solver.rhs_plan._blocked_bwd_ok() and solver.rhs_plan._blocked_fwd_ok()
+    if world > 1:
+        # local coefficient blocks (axis 0 of the horizontal modes is block-distributed) -> rank 0
+        def gather(a, axis):
+            t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            return np.concatenate([x.cpu().numpy() for x in parts], axis=axis)
+        b0 = gather(b0, 0); u0 = gather(u0, 1)
+        got = {n: gather(a, 1 if n == "u" else 0) for n, a in got.items()}
+    res = None
+    if rank == 0:
+        from oracle import rb_oracle
+        ref = rb_oracle.run(dim=args.dim, Nh=Nh, Nz=N, Ra=1e6, b0_c=b0, steps=steps, dt=dt, u0_c=u0)
+        rel = {n: float(np.abs(got[n] - ref[n]).max() / np.abs(ref[n]).max()) for n in got}
+        ok = all(np.allclose(got[n], ref[n], rtol=1e-8, atol=(1e-10 * np.abs(ref[n]).max() if n == "p" else 1e-12)) for n in got)
+        res = dict(ok=bool(ok), max_rel=max(rel.values()), rel=rel, shape=[Nh, Nh, N], steps=steps, ranks=world,
+                   blocked_transposes=bool(blocked),
+                   factor_backward_error=verify, seconds=time.time() - t0,
+                   what="GPU state vs CPU oracle (oracle/rb_oracle.py, pinned to the reference fixtures) after 2 RK222 steps, O(1) velocity; "
+                        "np.allclose(rtol=1e-8, atol=1e-12; p: atol=1e-10 max|p|)")
+    del solver, pb
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -131,6 +197,13 @@ def main():
     from dedalus_b200.lib import get_lib
     cfg = workload(args)
     N, dt = args.size, cfg['dt']
+    parity = None if args.no_parity else parity_gate(args, world, rank)
+    if rank == 0 and parity is not None and not parity['ok']:
+        print(json.dumps(dict(metric=METRIC, value=None, unit="steps/s", n_gpus=world, parity=parity,
+                              error="parity gate failed: the GPU path does not reproduce the oracle; nothing was timed")))
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(3)
     t_setup = time.time()
     pb = examples.rayleigh_benard(dim=args.dim, Nh=N, Nz=N, Rayleigh=1e6, mesh=(world,) if world > 1 else None)
     solver = pb['problem'].build_solver(d3.RK222)
@@ -169,6 +242,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = args.steps / (ms * 1e-3)
+    # ---- state checksum after the timed steps (identical problem and step count at every N: the values must agree across
+    #      --gpus 1/2/4/8 runs with the same --steps/--warmup; the transposes are pure permutations)
+    chk = torch.stack([(v.double() ** 2).sum() for v in solver.state_views[:3]])
+    if world > 1:
+        dist.all_reduce(chk)
+    checksum = dict(sum_sq=dict(zip(("p", "b", "u"), [float(x) for x in chk.cpu()])), steps_taken=int(solver.iteration))
+    try:
+        gold = json.load(open(ROOT / "tests" / "golden" / "bench_checksums.json"))
+        key = f"{args.dim}d_{N}_{solver.iteration}"
+        if key in gold:
+            ref = gold[key]
+            checksum['golden'] = ref
+            checksum['matches_single_gpu'] = bool(all(abs(checksum['sum_sq'][k] - ref[k]) <= 1e-9 * abs(ref[k]) + 1e-300 for k in ref))
+    except Exception:
+        pass
     # ---- per-kernel accounting
     agg = {}
     for name, a, b, nbytes in prof:
@@ -258,18 +346,17 @@ def main():
         e2e = dict(value=ksteps / (ms2 * 1e-3), unit="steps/s", h2d_bytes_per_step=int(nst * 8 * world), d2h_bytes_per_step=int(nst * 8 * world),
                    path="solver.step(dt) with the coefficient state copied host->device from pinned memory before and device->host after every step; "
                         "the copies run on two copy streams and overlap the neighbouring steps' kernels (all inside the timed region)")
-    # ---- CPU baseline (rank 0, N=1 only)
+    # ---- CPU baseline (rank 0, N=1 only): the reference itself on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_bench
-        r = cpu_bench.sampled_step(dim=args.dim, N=N, dt=dt, cores=os.cpu_count() or 1, slab=min(16, N), n_pencils=2 * (os.cpu_count() or 1))
-        cpu = dict(value=r['steps_per_sec'], unit="steps/s", cores=r['cores'], kind="port", sample=r['sample'])
+        _, cpu = cpu_arm(args, cfg, 2, 5)
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                     data="synthetic", config=dict(cfg, parallelism=f"pencil{world}" if world > 1 else "single", setup_seconds=setup_s,
                                                   pencil_systems=sum(b.S for b in solver.batches), total_modes=solver.total_modes),
-                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
+                    parity=parity, state_checksum=checksum, factor_backward_error=float(solver.bset.last_verify))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
