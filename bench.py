@@ -90,12 +90,12 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_arm(args, cfg, warmup, steps):
+def cpu_arm(args, cfg, warmup, steps, max_pencils=256):
     """CPU arm on this host: the UNMODIFIED reference (baseline/_ref, oracle/ref_bench.py) when it travelled with the
     snapshot, else the oracle port (oracle/cpu_bench.py).  Returns (value, cpu_baseline dict, extra)."""
     from oracle import ref_bench
     if args.dim == 3 and ref_bench.available() and not os.environ.get("DB_BENCH_PORT"):
-        r = ref_bench.run(N=args.size, dt=cfg['dt'], warmup=warmup, steps=steps)
+        r = ref_bench.run(N=args.size, dt=cfg['dt'], warmup=warmup, steps=steps, max_pencils=max_pencils)
         cb = dict(value=r['steps_per_sec'], unit="steps/s", cores=r['cores'], kind="reference", sample=r['sample'],
                   spread=r['spread'], per_step=r['steps_per_sec_list'], sample_step_seconds=r['sample_step_seconds'],
                   setup_seconds=r['setup_seconds'])
@@ -349,12 +349,12 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): the reference itself on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, cpu = cpu_arm(args, cfg, 2, 5)
+        _, cpu = cpu_arm(args, cfg, 1, 4, max_pencils=64)      # short: the driver times the full arm separately (--impl reference)
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                     data="synthetic", config=dict(cfg, parallelism=f"pencil{world}" if world > 1 else "single", setup_seconds=setup_s,
-                                                  pencil_systems=sum(b.S for b in solver.batches), total_modes=solver.total_modes),
+                                                  pencil_systems=sum(b.S * b.R for b in solver.batches), factorisations=sum(b.S for b in solver.batches), total_modes=solver.total_modes),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
                     parity=parity, state_checksum=checksum, factor_backward_error=float(solver.bset.last_verify))
         print(json.dumps(line))

@@ -277,7 +277,8 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
     return lo;
 }
 
-#define SOLVE_THREADS 64
+#define SOLVE_THREADS 64              // lanes per member group = systems per tile
+#define SOLVE_MAX_RHS 4               // members (right-hand sides per factorisation) one CTA can carry
 // Right-hand side first: x <- sum_q cf[q] * rv[q] for every row, as one fully parallel streaming pass (many
 // independent loads in flight per thread).  The forward sweep then starts each row from x[row] like the backward sweep
 // does; folding the combination into the row starts instead puts NV dependent DRAM loads on the recurrence's critical
@@ -409,15 +410,20 @@ __device__ __forceinline__ double solve_chunk_pure(const double* __restrict__ va
 }
 
 template <int NV>
-__global__ void __launch_bounds__(SOLVE_THREADS)
+__global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS)
 k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
 {
+    // blockDim.x = 64 * (largest nrhs of the launch).  Thread group g = threadIdx.x / 64 owns member g of the tile's 64
+    // pencils: all groups consume the SAME factor stage of the ring (one DRAM read of the factors for nrhs solves); groups
+    // beyond the batch's nrhs only take part in the barriers.
     DB_SMEM(unsigned char, ring);
     db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
     const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
     const db_batch& B = batches[bi];
     const int tile = blockIdx.x - B.blk_solve;
-    const int s = tile * SOLVE_THREADS + threadIdx.x;          // padded lanes (s >= S) run on the zero padding
+    const int grp = threadIdx.x / SOLVE_THREADS, lane = threadIdx.x % SOLVE_THREADS;
+    const bool active = grp < B.nrhs;
+    const int s = (active ? grp : 0) * B.ld + tile * SOLVE_THREADS + lane;   // padded lanes run on the zero padding
     const int64_t tb = db_tbase(s, B.n);
     const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
     const int32_t* __restrict__ ctrl_g = B.ctrl;
@@ -440,20 +446,22 @@ k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_sl
     __syncthreads();
     if (threadIdx.x == 0)
         for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
-    SOLVE_PROLOGUE(NV, B.n)
+    if (active) SOLVE_PROLOGUE(NV, B.n)
     int slot = 0;
     unsigned phase = 0;
     double acc = 0.0;
     for (int q = 0; q < nchunks; ++q) {
-        db_mbar_wait(&bars[slot], phase);
-        const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
-        const double* __restrict__ vals = reinterpret_cast<const double*>(st) + threadIdx.x;
-        const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
-        const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
-        if ((mB | mF) == 0) acc = solve_chunk_pure(vals, ctrl, x, acc);
-        else if (q < nfwd) acc = mF ? solve_chunk_flat<true, true>(vals, ctrl, x, acc) : solve_chunk_flat<true, false>(vals, ctrl, x, acc);
-        else acc = mF ? solve_chunk_flat<false, true>(vals, ctrl, x, acc) : solve_chunk_flat<false, false>(vals, ctrl, x, acc);
-        __syncthreads();                                   // both warps are done with this stage
+        if (active) {
+            db_mbar_wait(&bars[slot], phase);
+            const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+            const double* __restrict__ vals = reinterpret_cast<const double*>(st) + lane;
+            const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+            const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+            if ((mB | mF) == 0) acc = solve_chunk_pure(vals, ctrl, x, acc);
+            else if (q < nfwd) acc = mF ? solve_chunk_flat<true, true>(vals, ctrl, x, acc) : solve_chunk_flat<true, false>(vals, ctrl, x, acc);
+            else acc = mF ? solve_chunk_flat<false, true>(vals, ctrl, x, acc) : solve_chunk_flat<false, false>(vals, ctrl, x, acc);
+        }
+        __syncthreads();                                   // every warp is done with this stage
         if (threadIdx.x == 0 && q + nstages < nchunks) issue(q + nstages, slot);
         if (++slot == nstages) { slot = 0; phase ^= 1; }
     }
@@ -506,15 +514,20 @@ __device__ __forceinline__ double solve_chunk_pipe(const double* __restrict__ va
 }
 
 template <int NV>
-__global__ void __launch_bounds__(SOLVE_THREADS)
+__global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS)
 k_batches_solve_pipe(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
 {
+    // blockDim.x = 64 * (largest nrhs of the launch).  Thread group g = threadIdx.x / 64 owns member g of the tile's 64
+    // pencils: all groups consume the SAME factor stage of the ring (one DRAM read of the factors for nrhs solves); groups
+    // beyond the batch's nrhs only take part in the barriers.
     DB_SMEM(unsigned char, ring);
     db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
     const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
     const db_batch& B = batches[bi];
     const int tile = blockIdx.x - B.blk_solve;
-    const int s = tile * SOLVE_THREADS + threadIdx.x;
+    const int grp = threadIdx.x / SOLVE_THREADS, lane = threadIdx.x % SOLVE_THREADS;
+    const bool active = grp < B.nrhs;
+    const int s = (active ? grp : 0) * B.ld + tile * SOLVE_THREADS + lane;
     const int64_t tb = db_tbase(s, B.n);
     const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
     const int32_t* __restrict__ ctrl_g = B.ctrl;
@@ -537,13 +550,13 @@ k_batches_solve_pipe(const db_batch* __restrict__ batches, int nbatch, int lu_sl
     __syncthreads();
     if (threadIdx.x == 0)
         for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
-    SOLVE_PROLOGUE(NV, B.n)
+    if (active) SOLVE_PROLOGUE(NV, B.n)
     auto stage_ctrl = [&](int slot) { return reinterpret_cast<const int*>(ring + (size_t)slot * SOLVE_FSTAGE_BYTES + SOLVE_CE * DB_TILE * 8); };
     int slot = 0;
     unsigned phase = 0;
     double acc = 0.0;
     double xa[SOLVE_CE], xb[SOLVE_CE];
-    if (nchunks > 0) { db_mbar_wait(&bars[0], 0); solve_gather(stage_ctrl(0), x, xa); }
+    if (nchunks > 0 && active) { db_mbar_wait(&bars[0], 0); solve_gather(stage_ctrl(0), x, xa); }
     // two chunks per iteration so that the two gather buffers alternate without register copies
     for (int q = 0; q < nchunks; q += 2) {
 #pragma unroll
@@ -552,28 +565,32 @@ k_batches_solve_pipe(const db_batch* __restrict__ batches, int nbatch, int lu_sl
             if (qq >= nchunks) break;
             int nslot = slot + 1; unsigned nphase = phase;
             if (nslot == nstages) { nslot = 0; nphase ^= 1; }
-            if (qq + 1 < nchunks) {                              // gather of the NEXT chunk goes out first
-                db_mbar_wait(&bars[nslot], nphase);
-                if (half == 0) solve_gather(stage_ctrl(nslot), x, xb); else solve_gather(stage_ctrl(nslot), x, xa);
+            if (active) {
+                if (qq + 1 < nchunks) {                              // gather of the NEXT chunk goes out first
+                    db_mbar_wait(&bars[nslot], nphase);
+                    if (half == 0) solve_gather(stage_ctrl(nslot), x, xb); else solve_gather(stage_ctrl(nslot), x, xa);
+                }
+                const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+                const double* __restrict__ vals = reinterpret_cast<const double*>(st) + lane;
+                const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+                if (qq < nfwd) acc = (half == 0) ? solve_chunk_pipe<true>(vals, ctrl, x, xa, acc) : solve_chunk_pipe<true>(vals, ctrl, x, xb, acc);
+                else acc = (half == 0) ? solve_chunk_pipe<false>(vals, ctrl, x, xa, acc) : solve_chunk_pipe<false>(vals, ctrl, x, xb, acc);
             }
-            const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
-            const double* __restrict__ vals = reinterpret_cast<const double*>(st) + threadIdx.x;
-            const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
-            if (qq < nfwd) acc = (half == 0) ? solve_chunk_pipe<true>(vals, ctrl, x, xa, acc) : solve_chunk_pipe<true>(vals, ctrl, x, xb, acc);
-            else acc = (half == 0) ? solve_chunk_pipe<false>(vals, ctrl, x, xa, acc) : solve_chunk_pipe<false>(vals, ctrl, x, xb, acc);
-            __syncthreads();                                   // both warps are done with this stage
+            __syncthreads();                                   // every warp is done with this stage
             if (threadIdx.x == 0 && qq + nstages < nchunks) issue(qq + nstages, slot);
             slot = nslot; phase = nphase;
         }
     }
 }
 
-extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
+extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t max_nrhs, int32_t lu_slot, int32_t x_slot,
                                 const db_slotcomb* rhs, void* stream)
 {
     if (nbatch <= 0 || total_blocks <= 0) return 0;
-    if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU) { db_set_error("batches_solve: bad arguments"); return 1; }
-    const dim3 g(total_blocks), b(SOLVE_THREADS);
+    if (rhs->nvec < 0 || rhs->nvec > 16 || lu_slot < 0 || lu_slot >= DB_MAX_LU || max_nrhs < 1 || max_nrhs > SOLVE_MAX_RHS) {
+        db_set_error("batches_solve: bad arguments"); return 1;
+    }
+    const dim3 g(total_blocks), b(SOLVE_THREADS * max_nrhs);
     const int nv = rhs->nvec;
     static int st_env = -1, pipe_env = 0;
     if (st_env < 0) {
@@ -642,8 +659,10 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
     const int bi = find_batch(batches, nbatch, blockIdx.x, 1);
     const db_batch& B = batches[bi];
     const int local = blockIdx.x - B.blk_matvec;
-    const int tiles = (B.S + 63) / 64;
+    const int ptiles = (B.S + 63) / 64;                       // tiles of pencils; tiles of vector columns = nrhs * ptiles
+    const int tiles = ptiles * B.nrhs;
     const int tile = local % tiles, rb = local / tiles;
+    const int ptile = tile % ptiles;                          // pencil tile (monomials are per pencil)
     const int n = B.n, ld = B.ld;
     const int r0 = rb * MV_R, r1 = (r0 + MV_R < n) ? r0 + MV_R : n;
     const int tid = threadIdx.x, sp = tid & 31, g = tid >> 5;
@@ -659,7 +678,7 @@ k_batches_matvec(const db_batch* __restrict__ batches, int nbatch, int x_slot, i
         db_cp_async16(win + 2 * idx, xt + (int64_t)w0 * DB_TILE + 2 * idx);
     const int nm = B.n_mono < MV_MAX_MONO ? B.n_mono : MV_MAX_MONO;
     for (int idx = tid; idx < nm * 32; idx += MV_THREADS)
-        db_cp_async16(monos + 2 * idx, B.mono + (int64_t)(idx >> 5) * ld + tile * 64 + 2 * (idx & 31));
+        db_cp_async16(monos + 2 * idx, B.mono + (int64_t)(idx >> 5) * ld + ptile * 64 + 2 * (idx & 31));
     if (staged) {
         for (int idx = tid; idx < nm_rec; idx += MV_THREADS) db_cp_async16(recs + idx, B.m_rec + m0 + idx);
         for (int idx = tid; idx < nl_rec; idx += MV_THREADS) db_cp_async16(recs + nm_rec + idx, B.l_rec + l0 + idx);
@@ -744,14 +763,18 @@ k_batches_move(const db_batch* __restrict__ batches, int nbatch, int side, int s
     const int bi = find_batch(batches, nbatch, blockIdx.x, 2 + side);
     const db_batch& B = batches[bi];
     const int local = blockIdx.x - B.blk_move[side];
-    const int sblocks = (B.S + MOVE_T - 1) / MOVE_T;
+    const int ptiles = (B.S + MOVE_T - 1) / MOVE_T;
+    const int sblocks = ptiles * B.nrhs;                       // (member, pencil tile) pairs per line
     const int q = local / sblocks;
-    const int s0 = (local - q * sblocks) * MOVE_T;
+    const int mt = local - q * sblocks;
+    const int member = mt / ptiles;
+    const int s0 = (mt - member * ptiles) * MOVE_T;
     const int32_t* __restrict__ lp = B.line_ptr[side];
     const int lq = lp[q];
     const int len = lp[q + 1] - lq;
     const int S = B.S, ld = B.ld;
-    const int64_t base = B.line_base[side][q];
+    const int64_t base = B.line_base[side][member * B.nlines[side] + q];
+    const double sgn = B.line_sign[side][member * B.nlines[side] + q];   // +-1: D2 (variables) / D1 (equations) of this member
     const int64_t* __restrict__ so = B.sys_off[side] + (int64_t)B.line_kind[side][q] * ld;
     const int32_t* __restrict__ pos = B.line_pos[side] + lq;
     double* __restrict__ vec = B.vec[slot];
@@ -759,7 +782,7 @@ k_batches_move(const db_batch* __restrict__ batches, int nbatch, int side, int s
     constexpr int P = MOVE_T + 1;
     const int s = s0 + tx;                                     // system on the tile-major side
     const bool s_ok = s < S;
-    double* __restrict__ vcol = vec + db_tbase(s_ok ? s : 0, B.n);
+    double* __restrict__ vcol = vec + db_tbase(member * ld + (s_ok ? s : 0), B.n);
     // arena row bases of the (up to) 16 systems this thread touches on the line side
     int64_t rowb[MOVE_T / 4];
 #pragma unroll
@@ -779,13 +802,13 @@ k_batches_move(const db_batch* __restrict__ batches, int nbatch, int side, int s
 #pragma unroll 4
             for (int r = ty; r < MOVE_T; r += 4) {
                 const int m = m0 + r;
-                if (s_ok && m < len) vcol[(int64_t)pos[m] * DB_TILE] = tile[tx * P + r];
+                if (s_ok && m < len) vcol[(int64_t)pos[m] * DB_TILE] = sgn * tile[tx * P + r];
             }
         } else {
 #pragma unroll 4
             for (int r = ty; r < MOVE_T; r += 4) {
                 const int m = m0 + r;
-                if (s_ok && m < len) tile[tx * P + r] = DB_LDCS(vcol + (int64_t)pos[m] * DB_TILE);
+                if (s_ok && m < len) tile[tx * P + r] = sgn * DB_LDCS(vcol + (int64_t)pos[m] * DB_TILE);
             }
             __syncthreads();
 #pragma unroll
@@ -881,7 +904,7 @@ extern "C" int db_batches_factor(const db_batch* batches, int32_t nbatch, int32_
 // libraries/matsolvers.py:179-183; a pivot order shared by a batch has to be CHECKED for every member).  After
 // x = LU^{-1} b (db_batches_solve) and Mx, Lx (db_batches_matvec) of a probe right-hand side b:
 //     out[system] = max_i |a0 (Mx)_i + b0 (Lx)_i - b_i| / (max_i |b_i| + max_i |a0 (Mx)_i| + max_i |b0 (Lx)_i|)
-// i.e. the normwise backward error of the solve; non-finite values give +inf.  One thread per system (coalesced
+// i.e. the normwise backward error of the solve (worst member of the pencil); non-finite values give +inf.  One thread per pencil (coalesced
 // rows), same block map as the solve.  out has total_blocks * 64 entries (padding lanes: 0).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SOLVE_THREADS)
@@ -893,20 +916,22 @@ k_batches_residual(const db_batch* __restrict__ batches, int nbatch, int b_slot,
     const int s = (blockIdx.x - B.blk_solve) * SOLVE_THREADS + threadIdx.x;
     double res = 0.0;
     if (s < B.S) {
-        const int64_t tb = db_tbase(s, B.n);
-        const double* __restrict__ b = B.vec[b_slot] + tb;
-        const double* __restrict__ m = B.vec[m_slot] + tb;
-        const double* __restrict__ l = B.vec[l_slot] + tb;
-        double rmax = 0.0, bmax = 0.0, mmax = 0.0, lmax = 0.0;
-        bool finite = true;
-        for (int i = 0; i < B.n; ++i) {
-            const double bv = b[(int64_t)i * DB_TILE], mv = a0 * m[(int64_t)i * DB_TILE], lv = b0 * l[(int64_t)i * DB_TILE];
-            const double r = (mv + lv) - bv;
-            if (!(fabs(r) < 1e300)) finite = false;
-            rmax = fmax(rmax, fabs(r)); bmax = fmax(bmax, fabs(bv)); mmax = fmax(mmax, fabs(mv)); lmax = fmax(lmax, fabs(lv));
+        for (int member = 0; member < B.nrhs; ++member) {
+            const int64_t tb = db_tbase(member * B.ld + s, B.n);
+            const double* __restrict__ b = B.vec[b_slot] + tb;
+            const double* __restrict__ m = B.vec[m_slot] + tb;
+            const double* __restrict__ l = B.vec[l_slot] + tb;
+            double rmax = 0.0, bmax = 0.0, mmax = 0.0, lmax = 0.0;
+            bool finite = true;
+            for (int i = 0; i < B.n; ++i) {
+                const double bv = b[(int64_t)i * DB_TILE], mv = a0 * m[(int64_t)i * DB_TILE], lv = b0 * l[(int64_t)i * DB_TILE];
+                const double r = (mv + lv) - bv;
+                if (!(fabs(r) < 1e300)) finite = false;
+                rmax = fmax(rmax, fabs(r)); bmax = fmax(bmax, fabs(bv)); mmax = fmax(mmax, fabs(mv)); lmax = fmax(lmax, fabs(lv));
+            }
+            const double den = bmax + mmax + lmax;
+            res = fmax(res, !finite ? 1e300 * 1e300 : (den > 0.0 ? rmax / den : 0.0));
         }
-        const double den = bmax + mmax + lmax;
-        res = !finite ? 1e300 * 1e300 : (den > 0.0 ? rmax / den : 0.0);
     }
     out[(int64_t)blockIdx.x * SOLVE_THREADS + threadIdx.x] = res;
 }

@@ -401,14 +401,24 @@ struct ChebArgs {
     int32_t npre;
 };
 
-#define CH_LINES (2 * RR_P)
+// Tile height.  The z kernels are one tile per CTA with full-CTA barriers between their phases, i.e. latency-bound (ncu,
+// round 1: 2 CTAs / SM, long-scoreboard stalls, 1.1 - 1.9 TB/s): P = line pairs per tile is a template parameter so that
+// smaller tiles (P = 4: 8 lines, 192 threads, 49 KB at n = 384 -> 4 CTAs / SM in different phases) can hide it.
+template <int Q, int NB, int P> struct ChGeom {
+    static constexpr int NA = 3 * Q, N = NA * NB, LINES = 2 * P;
+    static constexpr int TA = 3 * NB * P, TB = 6 * Q * P;
+    static constexpr int THREADS = TA > TB ? TA : TB;
+    static constexpr int LOGP = P == 8 ? 3 : P == 4 ? 2 : P == 2 ? 1 : 0;
+    static constexpr size_t SMEM = (size_t)LINES * (N + 2) * sizeof(double) + (size_t)N * P * sizeof(double2);
+    static constexpr int MINB = (int)((226 * 1024) / (SMEM + 1024)) > 8 ? 8 : ((int)((226 * 1024) / (SMEM + 1024)) < 1 ? 1 : (int)((226 * 1024) / (SMEM + 1024)));
+};
 
-template <int Q, int NB>
-__global__ void __launch_bounds__(RegGeom<Q, NB>::THREADS, RegGeom<Q, NB>::MINB)
+template <int Q, int NB, int P>
+__global__ void __launch_bounds__((ChGeom<Q, NB, P>::THREADS), (ChGeom<Q, NB, P>::MINB))
 k_chbwd_regs(ChebArgs a)
 {
-    using G = RegGeom<Q, NB>;
-    constexpr int NA = G::NA, N = G::N, P = G::P, H = NB / 2, LX = N + 2;
+    using G = ChGeom<Q, NB, P>;
+    constexpr int NA = G::NA, N = G::N, H = NB / 2, LX = N + 2, CH_LINES = G::LINES;
     DB_SMEM(double, X);                                      // [16][LX] doubles, then Y = [N][P] double2
     double2* Y = reinterpret_cast<double2*>(X + CH_LINES * LX);
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -485,9 +495,10 @@ k_chbwd_regs(ChebArgs a)
         const double c1 = 0.39894228040143267793994605993438;     // 1/sqrt(2 pi)
         // warp task = (block of 8 modes, half of the line pairs); lanes = 4 pairs x 8 modes (bank-friendly on both sides)
         const int lane = tid & 31, w = tid >> 5, nw = nthreads >> 5;
-        const int kk = lane >> 2;
-        for (int wt = w; wt < 2 * ((N + 7) / 8); wt += nw) {
-            const int k = (wt >> 1) * 8 + kk, pp = (lane & 3) + 4 * (wt & 1);
+        constexpr int PL = P < 4 ? P : 4, KL = 32 / PL, PH = P / PL;       // lanes = PL pairs x KL modes; PH warp tasks per mode block
+        const int kk = lane / PL;
+        for (int wt = w; wt < PH * ((N + KL - 1) / KL); wt += nw) {
+            const int k = (wt / PH) * KL + kk, pp = (lane % PL) + PL * (wt % PH);
             if (k >= N) continue;
             const double* x1 = X + (2 * pp) * LX;
             const double* x2 = x1 + LX;
@@ -502,7 +513,7 @@ k_chbwd_regs(ChebArgs a)
         }
     }
     __syncthreads();
-    const int p = tid & (P - 1), r = tid >> 3;
+    const int p = tid & (P - 1), r = tid >> G::LOGP;
     const bool in_a = r < 3 * NB, in_b = r < 2 * NA;
     const int n2 = r % NB, c = r / NB;
     const int k1 = r % NA, h = r / NA;
@@ -570,12 +581,12 @@ k_chbwd_regs(ChebArgs a)
     }
 }
 
-template <int Q, int NB>
-__global__ void __launch_bounds__(RegGeom<Q, NB>::THREADS, RegGeom<Q, NB>::MINB)
+template <int Q, int NB, int P>
+__global__ void __launch_bounds__((ChGeom<Q, NB, P>::THREADS), (ChGeom<Q, NB, P>::MINB))
 k_chfwd_regs(ChebArgs a)
 {
-    using G = RegGeom<Q, NB>;
-    constexpr int NA = G::NA, N = G::N, P = G::P, H = NB / 2, LX = N + 2;
+    using G = ChGeom<Q, NB, P>;
+    constexpr int NA = G::NA, N = G::N, H = NB / 2, LX = N + 2, CH_LINES = G::LINES;
     DB_SMEM(double, X);                                      // [16][LX] doubles, then Y = [N][P] double2
     double2* Y = reinterpret_cast<double2*>(X + CH_LINES * LX);
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -597,7 +608,7 @@ k_chfwd_regs(ChebArgs a)
         db_cp_wait<0>();
     }
     __syncthreads();
-    const int p = tid & (P - 1), r = tid >> 3;
+    const int p = tid & (P - 1), r = tid >> G::LOGP;
     const bool in_1 = r < 2 * NA, in_2 = r < 3 * NB;
     const int j1 = r % NA, h = r / NA;
     const int k2 = r % NB, c = r / NB;
@@ -651,9 +662,10 @@ k_chfwd_regs(ChebArgs a)
         const double s0 = 0.5 / N * 1.7724538509055160272981674833411;      // sqrt(pi)/(2N)
         const double s1 = 1.0 / N * 1.2533141373155002512078826424055;      // sqrt(pi/2)/N
         const int lane = tid & 31, w = tid >> 5, nw = nthreads >> 5;
-        const int kk = lane >> 2;
-        for (int wt = w; wt < 2 * ((Kin + 7) / 8); wt += nw) {
-            const int k = (wt >> 1) * 8 + kk, pp = (lane & 3) + 4 * (wt & 1);
+        constexpr int PL = P < 4 ? P : 4, KL = 32 / PL, PH = P / PL;
+        const int kk = lane / PL;
+        for (int wt = w; wt < PH * ((Kin + KL - 1) / KL); wt += nw) {
+            const int k = (wt / PH) * KL + kk, pp = (lane % PL) + PL * (wt % PH);
             if (k >= Kin) continue;
             double* x1 = X + (2 * pp) * LX;
             double* x2 = x1 + LX;
@@ -689,25 +701,43 @@ k_chfwd_regs(ChebArgs a)
     }
 }
 
-template <int Q, int NB>
-int launch_cheb(bool fwd, const ChebArgs& a, void* stream)
+template <int Q, int NB, int P>
+int launch_cheb_p(bool fwd, const ChebArgs& a, void* stream)
 {
-    constexpr int N = 3 * Q * NB, THREADS = RegGeom<Q, NB>::THREADS;
-    const size_t bytes = (size_t)CH_LINES * (N + 2) * sizeof(double) + (size_t)N * RR_P * sizeof(double2);
-    const int64_t blocks = (a.lines + CH_LINES - 1) / CH_LINES;
+    using G = ChGeom<Q, NB, P>;
+    const int64_t blocks = (a.lines + G::LINES - 1) / G::LINES;
 #ifndef DB_EMU
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_chbwd_regs<Q, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
-        cudaFuncSetAttribute(k_chfwd_regs<Q, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
-        cudaFuncSetAttribute(k_chbwd_regs<Q, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(k_chfwd_regs<Q, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_chbwd_regs<Q, NB, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_chfwd_regs<Q, NB, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_MAX_SMEM);
+        cudaFuncSetAttribute(k_chbwd_regs<Q, NB, P>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_chfwd_regs<Q, NB, P>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr = true;
     }
 #endif
-    if (fwd) DB_LAUNCH((k_chfwd_regs<Q, NB>), dim3((unsigned)blocks), dim3(THREADS), bytes, stream, a);
-    else DB_LAUNCH((k_chbwd_regs<Q, NB>), dim3((unsigned)blocks), dim3(THREADS), bytes, stream, a);
+    if (fwd) DB_LAUNCH((k_chfwd_regs<Q, NB, P>), dim3((unsigned)blocks), dim3(G::THREADS), G::SMEM, stream, a);
+    else DB_LAUNCH((k_chbwd_regs<Q, NB, P>), dim3((unsigned)blocks), dim3(G::THREADS), G::SMEM, stream, a);
     return db_check_launch(fwd ? "cheb_forward(regs)" : "cheb_backward(regs)");
+}
+
+static int cheb_tile_pairs()
+{
+    static int p = 0;
+    if (p == 0) { const char* e = getenv("DB_CHEB_P"); p = e ? atoi(e) : 4; if (p != 8 && p != 4 && p != 2) p = 4; }
+    return p;
+}
+
+template <int Q, int NB>
+int launch_cheb(bool fwd, const ChebArgs& a, void* stream)
+{
+    // small transforms keep the tall tile (their CTAs are small anyway); the tile height of the long ones is tunable
+    if (3 * Q * NB < 192) return launch_cheb_p<Q, NB, 8>(fwd, a, stream);
+    switch (cheb_tile_pairs()) {
+        case 8: return launch_cheb_p<Q, NB, 8>(fwd, a, stream);
+        case 2: return launch_cheb_p<Q, NB, 2>(fwd, a, stream);
+        default: return launch_cheb_p<Q, NB, 4>(fwd, a, stream);
+    }
 }
 
 static int regs_num_sms()
@@ -804,7 +834,7 @@ int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double
     if (!enabled) return -1;
     const int n = plan->n;
     if (plan->twn == nullptr || plan->twq == nullptr) return -1;
-    if (n_coeff % 2 != 0 || n_coeff < 2 || n_coeff > n || lines > 2147483647LL * CH_LINES) return -1;
+    if (n_coeff % 2 != 0 || n_coeff < 2 || n_coeff > n || lines > 2147483647LL * 4) return -1;
     if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) return -1;
     ChebArgs a;
     a.in = in; a.out = out; a.twn = plan->twn; a.twq = plan->twq; a.diags = diags; a.lines = lines; a.M = n_coeff; a.nd = nd;

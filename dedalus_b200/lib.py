@@ -35,6 +35,7 @@ class Batch(C.Structure):
                 ("l_ptr", vp), ("l_col", vp), ("l_mono", vp), ("l_val", vp),
                 ("m_rec", vp), ("l_rec", vp), ("ctrl", vp), ("n_mono", i32), ("mv_rows", i32), ("mv_win", vp), ("m_split", vp), ("l_split", vp),
                 ("line_base", vp * 2), ("line_kind", vp * 2), ("line_ptr", vp * 2), ("line_pos", vp * 2), ("sys_off", vp * 2),
+                ("nrhs", i32), ("line_sign", vp * 2),
                 ("diag_eid", vp), ("fl_ptr", vp), ("fl_eid", vp), ("fu_ptr", vp), ("fu_eid", vp), ("fd_eid", vp),
                 ("asm_ptr", vp), ("asm_mono", vp), ("asm_val", vp), ("info", vp)]
 
@@ -72,7 +73,7 @@ SIGNATURES = {
     "db_pencil_solve": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, PLIN, vp, vp]),
     "db_batches_move": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "db_batches_matvec": (C.c_int, [vp, i32, i32, i32, i32, i32, vp]),
-    "db_batches_solve": (C.c_int, [vp, i32, i32, i32, i32, C.c_void_p, vp]),
+    "db_batches_solve": (C.c_int, [vp, i32, i32, i32, i32, i32, C.c_void_p, vp]),
     "db_batches_assemble": (C.c_int, [vp, i32, i32, i32, vp]),
     "db_batches_factor": (C.c_int, [vp, i32, i32, i32, vp]),
     "db_batches_residual": (C.c_int, [vp, i32, i32, i32, i32, i32, f64, f64, vp, vp]),
@@ -140,47 +141,54 @@ def bind(path):
     return BoundLib(C.CDLL(str(path)))
 
 
-_LIB = None
-_TEST_EMULATION = None      # set ONLY by tests/emu/emu_lib.install(): kernels compiled for the host, CPU tensors
+class CudaBackend:
+    """Where data lives and which library executes: the current CUDA device, torch's current stream and
+    dedalus_b200/libdedalus_b200.so.  There is no other backend in the product and no CPU fallback: every method raises if
+    CUDA or the library is missing.  (`_BACKEND` below is the single indirection point; the GPU-less build container's
+    tests replace it with their own object defined in tests/emu/emu_lib.py -- the product contains no emulation code.)"""
+
+    _lib = None
+
+    def device(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise DedalusB200Error("dedalus_b200 requires a CUDA device (sm_100a); there is no CPU fallback.")
+        return torch.device('cuda', torch.cuda.current_device())
+
+    def stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def lib(self):
+        if CudaBackend._lib is None:
+            if not LIB_PATH.exists():
+                raise DedalusB200Error(
+                    f"{LIB_PATH} not found: build it with `python -m dedalus_b200.build` (nvcc, sm_100a). "
+                    "dedalus_b200 has no CPU fallback.")
+            CudaBackend._lib = bind(LIB_PATH)
+        return CudaBackend._lib
+
+    def accepts(self, tensor):
+        return tensor.is_cuda
 
 
-def install_test_emulation(bound):
-    """TEST HOOK (tests/emu only): route C-ABI calls to the CPU emulation build of the same kernels so the
-    Python orchestration can be exercised on the GPU-less build container.  Never called by the product."""
-    global _TEST_EMULATION
-    _TEST_EMULATION = bound
-
-
-def emulation_active():
-    return _TEST_EMULATION is not None
+_BACKEND = CudaBackend()
 
 
 def compute_device():
-    """torch device for all data: the current CUDA device (required), or 'cpu' under the test emulation."""
-    import torch
-    if _TEST_EMULATION is not None:
-        return torch.device('cpu')
-    if not torch.cuda.is_available():
-        raise DedalusB200Error("dedalus_b200 requires a CUDA device (sm_100a); there is no CPU fallback.")
-    return torch.device('cuda', torch.cuda.current_device())
+    """torch device for all data: the current CUDA device (required)."""
+    return _BACKEND.device()
 
 
 def current_stream():
-    import torch
-    if _TEST_EMULATION is not None:
-        return None
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _BACKEND.stream()
 
 
 def get_lib():
-    """Load the CUDA library (built in-tree by dedalus_b200/build.py). Fails loudly if it is absent."""
-    global _LIB
-    if _TEST_EMULATION is not None:
-        return _TEST_EMULATION
-    if _LIB is None:
-        if not LIB_PATH.exists():
-            raise DedalusB200Error(
-                f"{LIB_PATH} not found: build it with `python -m dedalus_b200.build` (nvcc, sm_100a). "
-                "dedalus_b200 has no CPU fallback.")
-        _LIB = bind(LIB_PATH)
-    return _LIB
+    """The CUDA library (built in-tree by dedalus_b200/build.py). Fails loudly if it is absent."""
+    return _BACKEND.lib()
+
+
+def device_tensor_ok(tensor):
+    """True if `tensor` lives where the kernels can reach it (a CUDA tensor)."""
+    return _BACKEND.accepts(tensor)

@@ -319,7 +319,25 @@ class Batch:
         self.rows = rows[rorder]          # natural (class) row index of solver row i
         self.cols0 = cols[corder]         # natural column index in preliminary order
         self.cols = None                  # after matching
+        self.seq = None                   # pivot sequence: cols = cols0[seq]
         self.n_border_rows = int((~rint).sum())
+        # sign-equivalent components merged into this batch (merge_sign_equivalent): member c has the matrices
+        #   A_c = D1_c A_0 D2_c   (D = diag(+-1)),  A_0 = this batch's own (canonical) component,
+        # so with the vectors of member c stored as  D2_c x_c  (column space) and  D1_c b_c  (row space) every member is
+        # solved / multiplied with the SAME matrix: one LU factorisation per pencil serves all members.
+        self.members = [dict(rows=self.rows, cols0=self.cols0, d1=np.ones(self.n), d2=np.ones(self.n))]
+
+    @property
+    def R(self):
+        return len(self.members)
+
+    def describe(self, side, member=0):
+        """(owner, tensor component, mode index, has_last) of every row / preliminary column position of a member."""
+        cls = self.cls
+        m = self.members[member]
+        idx, offs, slots = (m['rows'], cls.row_off, cls.row_slots) if side == 'rows' else (m['cols0'], cls.col_off, cls.col_slots)
+        sl = _slot_of(idx, offs)
+        return np.array([(slots[q].owner, slots[q].comp, int(i - offs[q]), int(slots[q].has_last)) for q, i in zip(sl, idx)], dtype=np.int64)
 
     # -- numeric matrix of one member in the current ordering
     def matrix(self, name_or_coefs, group, cols=None):
@@ -420,6 +438,7 @@ class Batch:
                 mats[:, i + 1 + rows, :] -= f[:, :, None] * mats[:, i, :][:, None, :]
                 mats[:, i + 1 + rows, j] = 0
         self.cols = self.cols0[seq]
+        self.seq = seq
         self.order_threshold = threshold
         return self.cols
 
@@ -717,13 +736,31 @@ class Arena:
 
 def line_maps(batch, arena, side):
     """For every coefficient line (slot) of the batch: arena base offset, system-offset kind, length and the
-    solver positions of its modes.  side = 'cols' (variables/state) or 'rows' (equations/F)."""
+    solver positions of its modes.  side = 'cols' (variables/state) or 'rows' (equations/F).
+    Members of a merged batch share everything but the base offset (their parity slot) and the sign of each line:
+    line_base / line_sign have shape (R, nlines)."""
+    per = [_line_maps_member(batch, arena, side, c) for c in range(batch.R)]
+    m = per[0]
+    for c, o in enumerate(per[1:], 1):
+        same = (np.array_equal(m.line_kind_key, o.line_kind_key) and np.array_equal(m.line_len, o.line_len)
+                and np.array_equal(m.line_pos, o.line_pos) and np.array_equal(m.sys_off, o.sys_off))
+        if not same:
+            raise RuntimeError("merged pencil components do not have aligned coefficient lines")
+    m.line_base = np.stack([o.line_base for o in per], axis=0)
+    m.line_sign = np.stack([o.line_sign for o in per], axis=0)
+    return m
+
+
+def _line_maps_member(batch, arena, side, member):
     b, cls = batch.builder, batch.cls
     dist = b.dist
+    mem = batch.members[member]
     if side == 'cols':
-        nat, slots, offs = batch.cols, cls.col_slots, cls.col_off
+        nat = mem['cols0'][batch.seq] if batch.seq is not None else mem['cols0']
+        sign_pos = mem['d2'][batch.seq] if batch.seq is not None else mem['d2']
+        slots, offs = cls.col_slots, cls.col_off
     else:
-        nat, slots, offs = batch.rows, cls.row_slots, cls.row_off
+        nat, sign_pos, slots, offs = mem['rows'], mem['d1'], cls.row_slots, cls.row_off
     pos_of_nat = {int(v): i for i, v in enumerate(nat)}
     kinds, kind_tables = {}, []
     lines = []
@@ -767,11 +804,16 @@ def line_maps(batch, arena, side):
             m1 = m
             while m1 < slot.size and members[m1] >= 0:
                 m1 += 1
-            lines.append((base + m, kinds[key], m1 - m, members[m:m1]))
+            sg = sign_pos[members[m:m1]]
+            if np.unique(sg).size != 1:
+                raise RuntimeError("sign of a merged pencil component varies along a coefficient line")
+            lines.append((base + m, kinds[key], m1 - m, members[m:m1], float(sg[0]), key))
             m = m1
     m = BatchProgram()
     m.line_base = np.array([l[0] for l in lines], dtype=np.int64)
+    m.line_sign = np.array([l[4] for l in lines], dtype=np.float64)
     m.line_kind = np.array([l[1] for l in lines], dtype=np.int32)
+    m.line_kind_key = np.array([hash(l[5]) for l in lines], dtype=np.int64)
     m.line_len = np.array([l[2] for l in lines], dtype=np.int32)
     m.line_ptr = np.concatenate([[0], np.cumsum(m.line_len)]).astype(np.int32)
     m.line_pos = np.concatenate([np.asarray(l[3], dtype=np.int32) for l in lines]) if lines else np.zeros(0, np.int32)
@@ -779,11 +821,97 @@ def line_maps(batch, arena, side):
     return m
 
 
-def build_batches(builder):
+def sign_relation(canon, other, rtol=1e-12):
+    """If every template of `other` equals D1 T D2 of the canonical component's template (position by position in the
+    mode-major orderings, D1 / D2 diagonal +-1), return (d1, d2); else None.  For real-Fourier directions the cos / -sin parity
+    blocks of a pencil are related this way: d/dx maps cos -> sin with one sign and sin -> cos with the other
+    (reference core/basis.py:1217-1224 group matrix [[0, -k], [k, 0]])."""
+    if other.n != canon.n or other.n_border_rows != canon.n_border_rows or other.S != canon.S:
+        return None
+    for side in ('rows', 'cols'):
+        if not np.array_equal(canon.describe(side), other.describe(side)):
+            return None
+    cls = canon.cls
+    n = canon.n
+    ii, jj, ss = [], [], []
+    for name in ('M', 'L'):
+        for mono, T in cls.templates[name].items():
+            T = T.tocsr()
+            P0 = T[canon.rows][:, canon.cols0].tocsr(); Pc = T[other.rows][:, other.cols0].tocsr()
+            P0.sort_indices(); Pc.sort_indices()
+            if P0.nnz != Pc.nnz or not np.array_equal(P0.indptr, Pc.indptr) or not np.array_equal(P0.indices, Pc.indices):
+                return None
+            if P0.nnz == 0:
+                continue
+            a, b = P0.data, Pc.data
+            if np.iscomplexobj(a) or np.iscomplexobj(b):
+                return None
+            if not np.allclose(np.abs(a), np.abs(b), rtol=rtol, atol=0):
+                return None
+            coo = P0.tocoo()
+            ii.append(coo.row); jj.append(coo.col); ss.append(np.sign(a) * np.sign(b))
+    if not ii:
+        return None
+    ii, jj, ss = np.concatenate(ii), np.concatenate(jj), np.concatenate(ss)
+    # breadth-first propagation of  s_ij = d1_i d2_j  over the bipartite pattern (connected: it is one component)
+    adj_r = [[] for _ in range(n)]; adj_c = [[] for _ in range(n)]
+    for i, j, sg in zip(ii.tolist(), jj.tolist(), ss.tolist()):
+        adj_r[i].append((j, sg)); adj_c[j].append((i, sg))
+    d1 = np.zeros(n); d2 = np.zeros(n)
+    d1[0] = 1.0
+    stack = [('r', 0)]
+    while stack:
+        kind, i = stack.pop()
+        if kind == 'r':
+            for j, sg in adj_r[i]:
+                v = sg * d1[i]
+                if d2[j] == 0:
+                    d2[j] = v; stack.append(('c', j))
+                elif d2[j] != v:
+                    return None
+        else:
+            for r, sg in adj_c[i]:
+                v = sg * d2[i]
+                if d1[r] == 0:
+                    d1[r] = v; stack.append(('r', r))
+                elif d1[r] != v:
+                    return None
+    if np.any(d1 == 0) or np.any(d2 == 0):
+        return None
+    # the gather / scatter kernels apply ONE sign per coefficient line: the signs must be constant along every line
+    for side, d in (('rows', d1), ('cols', d2)):
+        desc = canon.describe(side)
+        key = desc[:, 0] * 1000003 + desc[:, 1]
+        for k in np.unique(key):
+            if np.unique(d[key == k]).size != 1:
+                return None
+    return d1, d2
+
+
+def merge_sign_equivalent(comps):
+    """Greedy grouping of a class's independent components into batches of sign-equivalent members."""
+    out = []
+    for comp in comps:
+        for canon in out:
+            rel = sign_relation(canon, comp)
+            if rel is not None:
+                canon.members.append(dict(rows=comp.rows, cols0=comp.cols0, d1=rel[0], d2=rel[1]))
+                break
+        else:
+            out.append(comp)
+    return out
+
+
+def build_batches(builder, merge=None):
+    """One batch per (class, group of sign-equivalent independent components).  merge=False (or DB_MERGE_COMPONENTS=0) keeps
+    every component a batch of its own (one factorisation per component, as in round 1)."""
+    import os
+    if merge is None:
+        merge = os.environ.get("DB_MERGE_COMPONENTS", "1") != "0"
     batches = []
     for cls in builder.classes.values():
         if len(cls.groups) == 0 or cls.shape[0] == 0:
             continue
-        for rows, cols in split_components(cls):
-            batches.append(Batch(builder, cls, rows, cols))
+        comps = [Batch(builder, cls, rows, cols) for rows, cols in split_components(cls)]
+        batches.extend(merge_sign_equivalent(comps) if merge else comps)
     return batches

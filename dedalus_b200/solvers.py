@@ -72,7 +72,8 @@ class DeviceBatch:
         prog = compile_batch(batch, a0, b0)
         self.prog = prog
         self.n, self.S = prog.n, prog.S
-        self.ld = ld = prog.ld          # systems padded to whole tiles of 64 (tile-major storage, see include/dedalus_b200.h)
+        self.R = batch.R                # sign-equivalent members sharing each pencil's factorisation (pencils.merge_sign_equivalent)
+        self.ld = ld = prog.ld          # pencils padded to whole tiles of 64 (tile-major storage, see include/dedalus_b200.h)
         mono = np.zeros((len(prog.monos), ld)); mono[:, :prog.S] = prog.mono_vals
         f = lambda a: _i32(torch, a, dev)
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
@@ -107,14 +108,14 @@ class DeviceBatch:
         for side, arena in (('cols', solver.var_arena), ('rows', solver.eq_arena)):
             m = line_maps(batch, arena, side)
             so = np.zeros((m.sys_off.shape[0], ld), dtype=np.int64); so[:, :prog.S] = m.sys_off
-            self.maps.append(dict(nlines=len(m.line_base), max_len=int(m.line_len.max()) if len(m.line_len) else 0,
-                                  base=torch.from_numpy(m.line_base).to(dev), kind=f(m.line_kind), ptr=f(m.line_ptr),
-                                  pos=f(m.line_pos), sys_off=torch.from_numpy(so).to(dev)))
+            self.maps.append(dict(nlines=m.line_base.shape[1], max_len=int(m.line_len.max()) if len(m.line_len) else 0,
+                                  base=torch.from_numpy(np.ascontiguousarray(m.line_base)).to(dev), sign=d(m.line_sign),
+                                  kind=f(m.line_kind), ptr=f(m.line_ptr), pos=f(m.line_pos), sys_off=torch.from_numpy(so).to(dev)))
         ptr, mono_i, val = assembly_program(batch, prog, a0, b0)
         self.t['asm_ptr'], self.t['asm_mono'], self.t['asm_val'] = f(ptr), f(mono_i), d(val)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
         # work vectors survive a re-ordering of the batch (row-space vectors are unaffected by a new pivot column order)
-        self.vecs = vecs if vecs is not None else [torch.zeros(self.n * ld, dtype=torch.float64, device=dev) for _ in range(nslots)]
+        self.vecs = vecs if vecs is not None else [torch.zeros(self.n * ld * self.R, dtype=torch.float64, device=dev) for _ in range(nslots)]
         self.lu = {}
 
     def lu_tensor(self, slot):
@@ -158,19 +159,21 @@ class BatchSet:
             c = arr[i]
             t_ = db.t
             c.n, c.S, c.ld, c.n_entries = db.n, db.S, db.ld, db.prog.nE
+            c.nrhs = db.R
             c.n_fwd, c.n_bwd = db.prog.n_fwd, db.prog.nE - db.prog.n_fwd
             c.blk_solve = blk['solve']; blk['solve'] += (db.S + 63) // 64
             # mat-vec CTAs: one 64-system tile x 32 consecutive rows, x window in shared memory (csrc/pencil.cu k_batches_matvec)
             c.mv_rows = 32
             c.mv_win = t_['mv_win'].data_ptr()
-            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 63) // 64) * (-(-db.n // 32))
+            c.blk_matvec = blk['matvec']; blk['matvec'] += ((db.S + 63) // 64) * db.R * (-(-db.n // 32))
             c.blk_assemble = blk['asm']; blk['asm'] += ((db.S + 127) // 128) * ((db.prog.nE + 63) // 64)
             for side in (0, 1):
                 m = db.maps[side]
                 c.nlines[side], c.max_len[side] = m['nlines'], m['max_len']
                 c.blk_move[side] = blk[f'move{side}']
-                blk[f'move{side}'] += m['nlines'] * ((db.S + 63) // 64)     # one CTA per (line, 64 systems): MOVE_T in csrc/pencil.cu
+                blk[f'move{side}'] += m['nlines'] * ((db.S + 63) // 64) * db.R     # one CTA per (line, member, 64 pencils): MOVE_T in csrc/pencil.cu
                 c.line_base[side], c.line_kind[side] = m['base'].data_ptr(), m['kind'].data_ptr()
+                c.line_sign[side] = m['sign'].data_ptr()
                 c.line_ptr[side], c.line_pos[side], c.sys_off[side] = m['ptr'].data_ptr(), m['pos'].data_ptr(), m['sys_off'].data_ptr()
             t = db.t
             c.prog, c.mono, c.ctrl = t['prog'].data_ptr(), t['mono'].data_ptr(), t['ctrl'].data_ptr()
@@ -193,8 +196,9 @@ class BatchSet:
         self.desc = torch.from_numpy(raw).to(solver.device)
         self.host_desc = arr
         # byte counts for the roofline accounting
-        self.sum_nS = sum(db.n * db.S for db in self.items)
-        self.sum_ES = sum(db.prog.nE * db.S for db in self.items)
+        self.sum_nS = sum(db.n * db.S * db.R for db in self.items)      # unknowns of all systems
+        self.sum_ES = sum(db.prog.nE * db.S for db in self.items)        # stored factor entries (one set per pencil)
+        self.max_nrhs = max((db.R for db in self.items), default=1)
 
     def _call(self, name, *args):
         self.solver.lib.call(name, self.desc.data_ptr(), self.nb, *args, self.solver.stream())
@@ -216,7 +220,7 @@ class BatchSet:
             sc.slot[j] = slot; sc.coef[j] = coef
         # algorithmic bytes: every stored LU entry once + each RHS vector once + the solution written once
         with Timed(self.solver.prof, "pencil_solve", 8 * (self.sum_ES + self.sum_nS * (len(terms) + 1))):
-            self._call("db_batches_solve", self.blocks['solve'], lu_slot, x_slot, C.byref(sc))
+            self._call("db_batches_solve", self.blocks['solve'], self.max_nrhs, lu_slot, x_slot, C.byref(sc))
 
     def factor(self, lu_slot, a0, b0):
         for db in self.items:

@@ -70,8 +70,8 @@ class DevicePlan:
 
 
 def _check(x, name):
-    from .lib import emulation_active
-    if not (x.is_cuda or emulation_active()) or not x.is_contiguous():
+    from .lib import device_tensor_ok
+    if not device_tensor_ok(x) or not x.is_contiguous():
         raise ValueError(f"{name} must be a contiguous CUDA tensor.")
 
 

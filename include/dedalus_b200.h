@@ -195,7 +195,7 @@ int db_pencil_solve(const double* lu, int32_t n, int32_t S, int32_t ld,
  * the row inside the block's shared-memory window or column * DB_TILE (see db_batch.m_split) */
 typedef struct { double val; int32_t col_off; int32_t mono; } db_term;
 typedef struct {
-    int32_t n, S, ld, n_entries;
+    int32_t n, S, ld, n_entries;       /* S pencils; every pencil carries `nrhs` systems sharing ONE factorisation (see nrhs) */
     int32_t n_fwd, n_bwd;
     int32_t blk_solve, blk_matvec, blk_move[2], blk_assemble;   /* first block of this batch in each fused launch */
     int32_t nlines[2], max_len[2];
@@ -215,6 +215,13 @@ typedef struct {
                                           records split[i]..m_ptr[i+1] outside (col_off = column * DB_TILE)                       */
     const int64_t* line_base[2]; const int32_t* line_kind[2]; const int32_t* line_ptr[2]; const int32_t* line_pos[2];
     const int64_t* sys_off[2];
+    /* Merged sign-equivalent components.  The real-Fourier parity blocks of a pencil (cos/cos, cos/sin, ... : the reference
+     * keeps them inside one SuperLU system per pencil, core/subsystems.py:497-602) have matrices A_c = D1_c A_0 D2_c with
+     * D = diag(+-1); stored as D2_c x_c / D1_c b_c they are `nrhs` right-hand sides of the SAME matrix A_0.  Work vectors
+     * then hold nrhs * ld columns, member c of pencil s in column c * ld + s (tile-major over that column index); the
+     * factors hold ld columns.  line_base and line_sign are [nrhs][nlines]: arena offset and sign of member c's line q. */
+    int32_t nrhs;
+    const double* line_sign[2];
     /* factorisation programs */
     const int32_t *diag_eid, *fl_ptr, *fl_eid, *fu_ptr, *fu_eid, *fd_eid;
     const int32_t *asm_ptr, *asm_mono; const double* asm_val;
@@ -233,7 +240,8 @@ int db_batches_move(const db_batch* batches, int32_t nbatch, int32_t total_block
 /* vec[ym_slot] = M vec[x_slot], vec[yl_slot] = L vec[x_slot]; a negative slot skips that product */
 int db_batches_matvec(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t x_slot, int32_t ym_slot, int32_t yl_slot, void* stream);
 /* vec[x_slot] = LU[lu_slot]^{-1} (sum_j coef[j] vec[slot[j]]) */
-int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, int32_t x_slot,
+/* max_nrhs: largest db_batch.nrhs of the set (the CTAs have 64 * max_nrhs threads) */
+int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t max_nrhs, int32_t lu_slot, int32_t x_slot,
                      const db_slotcomb* rhs, void* stream);
 /* LU[lu_slot] = assembled LHS (asm_* programs), then in-place factorisation */
 int db_batches_assemble(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t lu_slot, void* stream);

@@ -88,16 +88,17 @@ def _instance(args):
                 check=chk)
 
 
-def sample_shape(N, instances):
-    """(nx_s, ny_s) of one instance: 32 x 32 (256 pencils) unless that would make instances * fraction exceed the whole."""
+def sample_shape(N, instances, max_pencils=256):
+    """(nx_s, ny_s) of one instance: 32 x 32 (256 pencils) unless that would make instances * fraction exceed the whole
+    (or max_pencils asks for a cheaper set-up: the per-pencil matrix assembly dominates the arm's wall time)."""
     nx = ny = min(32, N)
-    while instances * nx * ny > N * N and ny > 4:
+    while (instances * nx * ny > N * N or (nx // 2) * (ny // 2) > max_pencils) and ny > 4:
         if nx >= ny and nx > 4: nx //= 2
         else: ny //= 2
     return nx, ny
 
 
-def run(N=256, dt=0.0025, warmup=1, steps=5, instances=None):
+def run(N=256, dt=0.0025, warmup=1, steps=5, instances=None, max_pencils=256):
     """Returns dict(steps_per_sec (median, scaled to N^3), list, spread, cores, sample, ...)."""
     import multiprocessing as mp
     import numpy as np
@@ -105,7 +106,7 @@ def run(N=256, dt=0.0025, warmup=1, steps=5, instances=None):
         raise RuntimeError("baseline/_ref is missing: run `python -m oracle.build_ref` where /root/reference exists")
     cores = os.cpu_count() or 1
     C = instances or cores
-    nx, ny = sample_shape(N, C)
+    nx, ny = sample_shape(N, C, max_pencils)
     f = (N * N) / (nx * ny)
     C = int(min(C, f))
     ctx = mp.get_context("fork")

@@ -43,10 +43,36 @@ class EmuPlan:
         return C.byref(self.struct)
 
 
+class EmuBackend:
+    """TEST-ONLY stand-in for dedalus_b200.lib.CudaBackend: CPU tensors, no stream, the host build of the kernels."""
+
+    def device(self):
+        import torch
+        return torch.device('cpu')
+
+    def stream(self):
+        return None
+
+    def lib(self):
+        return emu()
+
+    def accepts(self, tensor):
+        return True
+
+
+_saved = None
+
+
 def install():
-    """Route the product's C-ABI calls to the emulated kernels (CPU tensors). Test-only."""
-    dlib.install_test_emulation(emu())
+    """Route the product's C-ABI calls to the emulated kernels (CPU tensors). Test-only: swaps the backend object."""
+    global _saved
+    if _saved is None:
+        _saved = dlib._BACKEND
+    dlib._BACKEND = EmuBackend()
 
 
 def uninstall():
-    dlib.install_test_emulation(None)
+    global _saved
+    if _saved is not None:
+        dlib._BACKEND = _saved
+        _saved = None

@@ -78,20 +78,23 @@ def matvec(prog, name, x):
     return y
 
 
-def gather(maps, arena, n, S):
+def gather(maps, arena, n, S, member=0):
+    """Member `member` of a (possibly merged) batch: line_base / line_sign are (R, nlines)."""
     X = np.zeros((n, S))
-    for q in range(len(maps.line_base)):
+    base, sign = np.atleast_2d(maps.line_base)[member], np.atleast_2d(maps.line_sign)[member]
+    for q in range(len(base)):
         for m in range(maps.line_len[q]):
             pos = maps.line_pos[maps.line_ptr[q] + m]
-            X[pos] = arena[maps.line_base[q] + maps.sys_off[maps.line_kind[q]] + m]
+            X[pos] = sign[q] * arena[base[q] + maps.sys_off[maps.line_kind[q]] + m]
     return X
 
 
-def scatter(maps, X, arena):
-    for q in range(len(maps.line_base)):
+def scatter(maps, X, arena, member=0):
+    base, sign = np.atleast_2d(maps.line_base)[member], np.atleast_2d(maps.line_sign)[member]
+    for q in range(len(base)):
         for m in range(maps.line_len[q]):
             pos = maps.line_pos[maps.line_ptr[q] + m]
-            arena[maps.line_base[q] + maps.sys_off[maps.line_kind[q]] + m] = X[pos]
+            arena[base[q] + maps.sys_off[maps.line_kind[q]] + m] = sign[q] * X[pos]
 
 
 def to_tiles(a, tile=64):

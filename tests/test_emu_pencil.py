@@ -1,6 +1,7 @@
 """csrc/pencil.cu + pointwise.cu logic under the test-only CPU emulation vs the numpy program interpreters /
 direct numpy evaluation."""
 import numpy as np, pytest, ctypes as C
+from scipy import sparse
 from scipy.sparse.linalg import spsolve
 from dedalus_b200 import examples
 from dedalus_b200 import lib as dlib
@@ -18,7 +19,7 @@ def test_pencil_kernels_match_interpreters():
     lib = E.emu()
     pb = examples.rayleigh_benard(dim=3, Nh=6, Nz=10)
     builder = PencilSystemBuilder(pb['problem'])
-    batches = build_batches(builder)
+    batches = build_batches(builder, merge=False)      # single-component batches: the per-batch kernels and interpreters
     a0, b0 = 1.0, 0.02 * GAMMA
     rng = np.random.default_rng(1)
     var_arena = Arena(builder.dist, [(v.tshape, v.bases) for v in builder.variables])
@@ -48,7 +49,7 @@ def test_pencil_kernels_match_interpreters():
         kind_ext = _i32(maps.line_kind)
         sys_off = np.zeros((maps.sys_off.shape[0], ld), dtype=np.int64); sys_off[:, :S] = maps.sys_off
         max_len = int(maps.line_len.max())
-        lib.call("db_pencil_gather", E.ptr(state), E.ptr(Xt), S, n, len(maps.line_base), max_len, E.ptr(maps.line_base), E.ptr(kind_ext),
+        lib.call("db_pencil_gather", E.ptr(state), E.ptr(Xt), S, n, maps.line_base.shape[1], max_len, E.ptr(np.ascontiguousarray(maps.line_base[0])), E.ptr(kind_ext),
                  E.ptr(_i32(maps.line_ptr)), E.ptr(_i32(maps.line_pos)), E.ptr(sys_off), ld, None)
         Xref = pi.gather(maps, state, n, S)
         X = pi.from_tiles(Xt, n, ld)
@@ -73,7 +74,7 @@ def test_pencil_kernels_match_interpreters():
             A = batch.matrix((a0, b0), batch.groups[s]).tocsc()
             ref = spsolve(A, rhs[:, s])
             assert np.abs(xs[:, s] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
-        lib.call("db_pencil_scatter", E.ptr(Xt), E.ptr(state_out), S, n, len(maps.line_base), max_len, E.ptr(maps.line_base), E.ptr(kind_ext),
+        lib.call("db_pencil_scatter", E.ptr(Xt), E.ptr(state_out), S, n, maps.line_base.shape[1], max_len, E.ptr(np.ascontiguousarray(maps.line_base[0])), E.ptr(kind_ext),
                  E.ptr(_i32(maps.line_ptr)), E.ptr(_i32(maps.line_pos)), E.ptr(sys_off), ld, None)
         tmp = np.zeros(var_arena.size); pi.scatter(maps, np.ones((n, S)), tmp); covered |= tmp > 0
     # scatter(gather(state)) reproduces every valid state entry; invalid (sin 0) slots are never touched
@@ -133,3 +134,54 @@ def test_mmt_and_transposes(golden):
     v = rng.standard_normal(5000); v[1234] = -9.5; res = np.zeros(1)
     lib.call("db_absmax", E.ptr(v), v.size, E.ptr(res), None)
     assert res[0] == 9.5
+
+
+def test_merged_sign_equivalent_components_share_one_factorisation():
+    """pencils.merge_sign_equivalent: the cos / -sin parity blocks of a pencil are D1 A D2 images of one another (D = +-1), so
+    they are stored sign-transformed and solved as several right-hand sides of ONE factorisation.  Check (a) the claimed
+    relation A_c = D1_c A_0 D2_c entry by entry on numerical pencil matrices, (b) the fused kernels (gather with signs ->
+    mat-vec -> solve on 64 * nrhs-thread CTAs -> scatter) against a sparse solve of every member's OWN matrix."""
+    from dedalus_b200.solvers import BatchSet
+    E.install()
+    try:
+        pb = examples.rayleigh_benard(dim=3, Nh=8, Nz=12)
+        import dedalus_b200 as d3
+        solver = pb['problem'].build_solver(d3.RK222)
+        a0, b0 = 1.0, 0.01 * GAMMA
+        solver._init_device()
+        solver._prepare_batches(a0, b0)
+        bs = solver.bset
+        assert max(db.R for db in bs.items) == 4 and sum(db.R for db in bs.items) == 15      # 15 components, 8 factorisation sets
+        bs.factor(0, a0, b0)
+        import torch
+        rng = np.random.default_rng(3)
+        state = torch.from_numpy(rng.standard_normal(solver.var_arena.size))
+        feq = torch.from_numpy(rng.standard_normal(solver.eq_arena.size))
+        bs.move(0, True, solver.slot_X, state)                 # X   <- D2 state
+        bs.move(1, True, solver.slot_F[0], feq)                # F   <- D1 f
+        bs.matvec(solver.slot_X, solver.slot_MX0, solver.slot_LX[0])
+        bs.solve(0, solver.slot_LX[1], [(solver.slot_F[0], 1.0), (solver.slot_MX0, 0.5)])
+        out = torch.zeros_like(state)
+        bs.move(0, False, solver.slot_LX[1], out)              # out <- D2 x
+        out = out.numpy(); st = state.numpy(); fe = feq.numpy()
+        for db in bs.items:
+            batch = db.batch
+            for c, mem in enumerate(batch.members):
+                cols = mem['cols0'][batch.seq]
+                for s in range(0, batch.S, max(1, batch.S // 2)):
+                    g = batch.groups[s]
+                    full = lambda name: batch.builder.class_matrix(batch.cls, name, g, restrict=False).tocsr()
+                    Mc, Lc = (full(nm)[mem['rows']][:, cols] for nm in ('M', 'L'))
+                    M0, L0 = batch.matrix('M', g), batch.matrix('L', g)
+                    D1 = sparse.diags(mem['d1']); D2 = sparse.diags(mem['d2'][batch.seq])
+                    assert abs(Mc - D1 @ M0 @ D2).max() < 1e-14 and abs(Lc - D1 @ L0 @ D2).max() < 1e-12
+                    # this member's own unknowns / right-hand side picked from the arenas in natural order
+                    maps_c = line_maps(batch, solver.var_arena, 'cols'); maps_r = line_maps(batch, solver.eq_arena, 'rows')
+                    x_own = pi.gather(maps_c, st, batch.n, batch.S, member=c)[:, s] * mem['d2'][batch.seq]
+                    f_own = pi.gather(maps_r, fe, batch.n, batch.S, member=c)[:, s] * mem['d1']
+                    rhs = f_own + 0.5 * (Mc @ x_own)
+                    ref = spsolve((a0 * Mc + b0 * Lc).tocsc(), rhs)
+                    got = pi.gather(maps_c, out, batch.n, batch.S, member=c)[:, s] * mem['d2'][batch.seq]
+                    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), (batch.cls.zero_axes, c, s)
+    finally:
+        E.uninstall()

@@ -15,7 +15,7 @@ GAMMA = (2 - np.sqrt(2)) / 2
 def test_rb_programs_solve(dim, Nh, Nz, dt, dense):
     pb = examples.rayleigh_benard(dim=dim, Nh=Nh, Nz=Nz)
     builder = PencilSystemBuilder(pb['problem'])
-    batches = build_batches(builder)
+    batches = build_batches(builder, merge=False)      # single-component batches: the per-batch kernels and interpreters
     a0, b0 = 1.0, dt * GAMMA
     rng = np.random.default_rng(0)
     total = 0
