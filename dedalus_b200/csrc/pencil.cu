@@ -369,28 +369,24 @@ __device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
 template <bool FWD, bool LATE>
 __device__ __forceinline__ double solve_chunk_flat(const double* __restrict__ vals, const int* __restrict__ ctrl, double* x, double acc)
 {
-    int goff[SOLVE_CE], foff[SOLVE_CE];
+    // register diet (ncu, round 2: the sweep is bound by the number of gathers in flight per SM, i.e. by resident warps x 16;
+    // 102 registers allowed two 256-thread CTAs per SM): the gather offsets are consumed straight from the control block and
+    // the finished-row / late offsets are re-read from shared memory at the few entries that need them, so that only the 16
+    // gathered values stay live -> three CTAs per SM
+    double xv[SOLVE_CE];
 #pragma unroll
     for (int j = 0; j < SOLVE_CE; j += 4) {
         const int4 g = *reinterpret_cast<const int4*>(ctrl + j);
-        goff[j] = g.x; goff[j + 1] = g.y; goff[j + 2] = g.z; goff[j + 3] = g.w;
-    }
-    double xv[SOLVE_CE];
-#pragma unroll
-    for (int j = 0; j < SOLVE_CE; ++j) xv[j] = x[goff[j]];
-#pragma unroll
-    for (int j = 0; j < SOLVE_CE; j += 4) {
-        const int4 f = *reinterpret_cast<const int4*>(ctrl + SOLVE_CE + j);
-        foff[j] = f.x; foff[j + 1] = f.y; foff[j + 2] = f.z; foff[j + 3] = f.w;
+        xv[j] = x[g.x]; xv[j + 1] = x[g.y]; xv[j + 2] = x[g.z]; xv[j + 3] = x[g.w];
     }
     const unsigned maskE = (unsigned)ctrl[2 * SOLVE_CE], maskB = (unsigned)ctrl[2 * SOLVE_CE + 1], maskF = (unsigned)ctrl[2 * SOLVE_CE + 2];
 #pragma unroll
     for (int j = 0; j < SOLVE_CE; ++j) {
         const double v = vals[j * DB_TILE];
-        if (LATE) { if (maskF & (1u << j)) xv[j] = x[goff[j]]; }
+        if (LATE) { if (maskF & (1u << j)) xv[j] = x[ctrl[j]]; }
         const double acc_a = fma(-v, xv[j], acc);
         const double val = FWD ? acc : acc * v;
-        if (maskE & (1u << j)) x[foff[j]] = val;
+        if (maskE & (1u << j)) x[ctrl[SOLVE_CE + j]] = val;
         acc = (maskB & (1u << j)) ? xv[j] : acc_a;
     }
     return acc;
@@ -409,8 +405,8 @@ __device__ __forceinline__ double solve_chunk_pure(const double* __restrict__ va
     return acc;
 }
 
-template <int NV>
-__global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS)
+template <int NV, int MINB>
+__global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS, MINB)
 k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
 {
     // blockDim.x = 64 * (largest nrhs of the launch).  Thread group g = threadIdx.x / 64 owns member g of the tile's 64
@@ -583,6 +579,152 @@ k_batches_solve_pipe(const db_batch* __restrict__ batches, int nbatch, int lu_sl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Members in registers (DB_SOLVE_RT = 2 / 4): one thread carries RT members of its pencil -- RT independent recurrences
+// driven by the same factor values and the same control block.  The sweep is latency-bound (one dependent chain per
+// thread: mbarrier -> control words -> 16 gathers from L2 -> 16 dependent FMAs; ncu on the one-member kernel: 22 %
+// occupancy, 6 long-scoreboard stalls per issue, and with few tiles per GPU -- 8-GPU strong scaling -- the time per launch
+// stops shrinking at the length of that chain).  RT chains per thread put RT x the loads in flight per warp and amortise
+// the shared-memory reads of the factor values and of the control block over RT systems.  Gathers are issued per half
+// chunk (8 entries x RT members) to bound the register count.  Work vectors are allocated for SOLVE_MAX_RHS members per
+// batch (missing members are all-zero columns: they are solved along, never read), so there is no per-member predicate.
+// ---------------------------------------------------------------------------------------------------------
+template <bool FWD, bool LATE, int RT>
+__device__ __forceinline__ void solve_chunk_mr(const double* __restrict__ vals, const int* __restrict__ ctrl, double* const (&x)[RT], double (&acc)[RT])
+{
+    const unsigned maskE = (unsigned)ctrl[2 * SOLVE_CE], maskB = (unsigned)ctrl[2 * SOLVE_CE + 1], maskF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+#pragma unroll
+    for (int h = 0; h < SOLVE_CE; h += 8) {
+        int goff[8], foff[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+            const int4 g = *reinterpret_cast<const int4*>(ctrl + h + j);
+            goff[j] = g.x; goff[j + 1] = g.y; goff[j + 2] = g.z; goff[j + 3] = g.w;
+        }
+        double xv[8][RT];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int r = 0; r < RT; ++r) xv[j][r] = x[r][goff[j]];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+            const int4 f = *reinterpret_cast<const int4*>(ctrl + SOLVE_CE + h + j);
+            foff[j] = f.x; foff[j + 1] = f.y; foff[j + 2] = f.z; foff[j + 3] = f.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double v = vals[(h + j) * DB_TILE];
+            const unsigned bit = 1u << (h + j);
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                if (LATE) { if (maskF & bit) xv[j][r] = x[r][goff[j]]; }
+                const double acc_a = fma(-v, xv[j][r], acc[r]);
+                const double val = FWD ? acc[r] : acc[r] * v;
+                if (maskE & bit) x[r][foff[j]] = val;
+                acc[r] = (maskB & bit) ? xv[j][r] : acc_a;
+            }
+        }
+    }
+}
+
+template <int RT>
+__device__ __forceinline__ void solve_chunk_mr_pure(const double* __restrict__ vals, const int* __restrict__ ctrl, double* const (&x)[RT], double (&acc)[RT])
+{
+#pragma unroll
+    for (int h = 0; h < SOLVE_CE; h += 8) {
+        double xv[8][RT];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+            const int4 g = *reinterpret_cast<const int4*>(ctrl + h + j);
+#pragma unroll
+            for (int r = 0; r < RT; ++r) { xv[j][r] = x[r][g.x]; xv[j + 1][r] = x[r][g.y]; xv[j + 2][r] = x[r][g.z]; xv[j + 3][r] = x[r][g.w]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double v = vals[(h + j) * DB_TILE];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) acc[r] = fma(-v, xv[j][r], acc[r]);
+        }
+    }
+}
+
+template <int NV, int RT>
+__global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS / RT)
+k_batches_solve_mr(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
+{
+    DB_SMEM(unsigned char, ring);
+    db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int tile = blockIdx.x - B.blk_solve;
+    const int grp = threadIdx.x / SOLVE_THREADS, lane = threadIdx.x % SOLVE_THREADS;
+    const bool active = grp * RT < B.nrhs;                      // groups beyond the batch's members only take part in the barriers
+    const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
+    const int32_t* __restrict__ ctrl_g = B.ctrl;
+    const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
+    int64_t tb[RT];
+    double* x[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        tb[r] = db_tbase(((active ? grp : 0) * RT + r) * B.ld + tile * SOLVE_THREADS + lane, B.n);
+        x[r] = B.vec[x_slot] + tb[r];
+    }
+    auto issue = [&](int q, int slot) {
+        unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+        db_mbar_expect_tx(&bars[slot], SOLVE_FSTAGE_BYTES);
+        db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &bars[slot]);
+        db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, ctrl_g + (int64_t)q * SOLVE_CTRL_WORDS, SOLVE_CTRL_WORDS * 4, &bars[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) db_mbar_init(&bars[i], 1);
+        db_mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
+    if (active) {
+        // right-hand side: x <- sum_q coef[q] vec[q], RT * NV independent loads in flight per row
+        const int nv = rhs.nvec < NV ? rhs.nvec : NV;
+        for (int i = 0; i < B.n; ++i) {
+            double a_[RT];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) a_[r] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                if (q < nv) {
+                    const double* __restrict__ v = B.vec[rhs.slot[q]];
+                    const double c = rhs.coef[q];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) a_[r] = fma(c, DB_LDCS(v + tb[r] + (int64_t)i * DB_TILE), a_[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RT; ++r) x[r][(int64_t)i * DB_TILE] = a_[r];
+        }
+    }
+    int slot = 0;
+    unsigned phase = 0;
+    double acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    for (int q = 0; q < nchunks; ++q) {
+        if (active) {
+            db_mbar_wait(&bars[slot], phase);
+            const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+            const double* __restrict__ vals = reinterpret_cast<const double*>(st) + lane;
+            const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+            const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+            if ((mB | mF) == 0) solve_chunk_mr_pure<RT>(vals, ctrl, x, acc);
+            else if (q < nfwd) { if (mF) solve_chunk_mr<true, true, RT>(vals, ctrl, x, acc); else solve_chunk_mr<true, false, RT>(vals, ctrl, x, acc); }
+            else { if (mF) solve_chunk_mr<false, true, RT>(vals, ctrl, x, acc); else solve_chunk_mr<false, false, RT>(vals, ctrl, x, acc); }
+        }
+        if (blockDim.x > 32) __syncthreads(); else __syncwarp();        // every warp is done with this stage
+        if (threadIdx.x == 0 && q + nstages < nchunks) issue(q + nstages, slot);
+        if (++slot == nstages) { slot = 0; phase ^= 1; }
+    }
+}
+
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t max_nrhs, int32_t lu_slot, int32_t x_slot,
                                 const db_slotcomb* rhs, void* stream)
 {
@@ -592,10 +734,12 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     }
     const dim3 g(total_blocks), b(SOLVE_THREADS * max_nrhs);
     const int nv = rhs->nvec;
-    static int st_env = -1, pipe_env = 0;
+    static int st_env = -1, pipe_env = 0, rt_env = 0, minb_env = 3;
     if (st_env < 0) {
         const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
         const char* p = getenv("DB_SOLVE_PIPE"); pipe_env = p ? atoi(p) : 0;
+        const char* r = getenv("DB_SOLVE_RT"); rt_env = r ? atoi(r) : 0;
+        const char* m = getenv("DB_SOLVE_MINB"); minb_env = m ? atoi(m) : 3;
     }
     // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
     // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
@@ -604,10 +748,21 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     int nst = per_sm >= 5 ? 2 : per_sm >= 3 ? 4 : per_sm >= 2 ? 8 : 16;
     if (st_env >= 2 && st_env <= 24) nst = st_env;
     const size_t smem = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)nst * sizeof(db_mbar_t);
+    // members per thread: 1 = k_batches_solve_flat; 2 / 4 = k_batches_solve_mr (RT chains per thread; opt-in, DB_SOLVE_RT)
+    int rt = rt_env ? rt_env : 1;       // measured at 256^3 on one GPU: 1 -> 5.1 ms / step, 2 -> 8.6, 4 -> 11.8 (fewer resident warps)
+    if (rt != 1 && rt != 2 && rt != 4) rt = 1;
+    if (rt > max_nrhs) rt = max_nrhs >= 2 ? 2 : 1;
+    const dim3 bmr(SOLVE_THREADS * ((max_nrhs + rt - 1) / rt));
 #define FLAT_GO(NV_) { static int attr_st = 0; \
-    if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_>)); DB_SET_SMEM_ATTR((k_batches_solve_pipe<NV_>)); attr_st = 1; } \
-    if (pipe_env && nst >= 2) DB_LAUNCH((k_batches_solve_pipe<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
-    else DB_LAUNCH((k_batches_solve_flat<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
+    if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 3>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 4>)); \
+                    DB_SET_SMEM_ATTR((k_batches_solve_pipe<NV_>)); \
+                    DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 4>)); attr_st = 1; } \
+    if (rt == 4 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 4>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
+    else if (rt == 2 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 2>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
+    else if (pipe_env && nst >= 2) DB_LAUNCH((k_batches_solve_pipe<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
+    else if (minb_env == 4) DB_LAUNCH((k_batches_solve_flat<NV_, 4>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
+    else if (minb_env == 2) DB_LAUNCH((k_batches_solve_flat<NV_, 2>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
+    else DB_LAUNCH((k_batches_solve_flat<NV_, 3>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
     if (nv <= 1) FLAT_GO(1) else if (nv == 2) FLAT_GO(2) else if (nv == 3) FLAT_GO(3) else if (nv == 4) FLAT_GO(4)
     else if (nv == 5) FLAT_GO(5) else if (nv == 6) FLAT_GO(6) else if (nv <= 8) FLAT_GO(8) else if (nv <= 12) FLAT_GO(12) else FLAT_GO(16)
 #undef FLAT_GO

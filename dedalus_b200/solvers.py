@@ -115,7 +115,10 @@ class DeviceBatch:
         self.t['asm_ptr'], self.t['asm_mono'], self.t['asm_val'] = f(ptr), f(mono_i), d(val)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
         # work vectors survive a re-ordering of the batch (row-space vectors are unaffected by a new pivot column order)
-        self.vecs = vecs if vecs is not None else [torch.zeros(self.n * ld * self.R, dtype=torch.float64, device=dev) for _ in range(nslots)]
+        # allocated for a whole number of member groups of 4 (SOLVE_MAX_RHS): the members-in-registers solve kernel carries 2 or
+        # 4 members per thread without per-member predicates; missing members are all-zero columns nobody reads
+        self.R_alloc = -(-self.R // 4) * 4
+        self.vecs = vecs if vecs is not None else [torch.zeros(self.n * ld * self.R_alloc, dtype=torch.float64, device=dev) for _ in range(nslots)]
         self.lu = {}
 
     def lu_tensor(self, slot):

@@ -19,7 +19,7 @@ def solve_residual(solver, dt, seed=0):
     check = 0.0
     for db in bs.items:
         n, S, ld, R = db.n, db.S, db.ld, db.R
-        view = lambda t: t.view(R * ld // 64, n, 64)
+        view = lambda t: t[:R * ld * n].view(R * ld // 64, n, 64)      # (allocated for 4 members; the first R are real)
         b, x, mx, lx = (view(db.vecs[s]) for s in (s_b, s_x, s_m, s_l))
         col = torch.arange(R * ld, device=b.device).view(R * ld // 64, 1, 64) % ld
         valid = col < S
