@@ -363,7 +363,7 @@ __device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
 // FMA, a predicated store and a select; chunks made only of multiply-accumulates (the dense boundary rows: a third of
 // all entries) take a shorter path.
 // ---------------------------------------------------------------------------------------------------------
-#define SOLVE_CTRL_WORDS 36
+#define SOLVE_CTRL_WORDS 44
 #define SOLVE_FSTAGE_BYTES (SOLVE_CE * DB_TILE * 8 + SOLVE_CTRL_WORDS * 4)
 
 template <bool FWD, bool LATE>
@@ -725,6 +725,119 @@ k_batches_solve_mr(const db_batch* __restrict__ batches, int nbatch, int lu_slot
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Deep-prefetch variant for the latency-bound regime (few tiles per GPU: 8-GPU strong scaling, where the time of the
+// kernels above stops shrinking at the length of ONE thread's dependent chain: per 16-entry chunk an L2 round trip for the
+// gathers, ~1 us, then 16 dependent FMAs).  Here the 16 gathers of chunk q + D are issued while chunk q is consumed -- as
+// 8-byte cp.async (LDGSTS) copies into a per-thread column of a shared-memory ring, so they cost no registers and D chunks
+// of gathers are in flight per thread.  Values whose source row is finished AFTER the gather was issued (15 % of the
+// entries at D = 3 with the level-ordered stream) come from a second shared-memory ring holding the last SOLVE_DEEP_RRN
+// finished rows of every thread (control words 36..40, pencils.py solve_control_blocks); the rare older ones are re-read
+// from global memory.  One 256-thread CTA per SM (194 KB of shared memory).
+// ---------------------------------------------------------------------------------------------------------
+#define SOLVE_DEEP_D 3
+#define SOLVE_DEEP_RRN 16
+template <int NV>
+__global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS, 1)
+k_batches_solve_deep(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
+{
+    constexpr int D = SOLVE_DEEP_D, GS = D + 1, RRN = SOLVE_DEEP_RRN;
+    DB_SMEM(unsigned char, ring);
+    const int NT = blockDim.x;
+    db_mbar_t* bars = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
+    double* G = reinterpret_cast<double*>(ring + (((size_t)nstages * SOLVE_FSTAGE_BYTES + (size_t)nstages * sizeof(db_mbar_t) + 15) & ~(size_t)15));
+    double* RR = G + (size_t)GS * SOLVE_CE * NT;                 // [RRN][NT]
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int tile = blockIdx.x - B.blk_solve;
+    // blockDim.x = 64 * (members per CTA); blockIdx.y selects the member group (the members of a tile may be spread over
+    // several CTAs, each with its own factor ring, so that more SMs work when there are few tiles)
+    const int grp = blockIdx.y * (blockDim.x / SOLVE_THREADS) + threadIdx.x / SOLVE_THREADS, lane = threadIdx.x % SOLVE_THREADS;
+    if (blockIdx.y * (blockDim.x / SOLVE_THREADS) >= B.nrhs) return;      // whole CTA without members
+    const bool active = grp < B.nrhs;
+    const int s = (active ? grp : 0) * B.ld + tile * SOLVE_THREADS + lane;
+    const int64_t tb = db_tbase(s, B.n);
+    const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
+    const int32_t* __restrict__ ctrl_g = B.ctrl;
+    const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
+    double* x = B.vec[x_slot] + tb;
+    const double* rv[NV];
+    double cf[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+    auto issue = [&](int q, int slot) {
+        unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+        db_mbar_expect_tx(&bars[slot], SOLVE_FSTAGE_BYTES);
+        db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &bars[slot]);
+        db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, ctrl_g + (int64_t)q * SOLVE_CTRL_WORDS, SOLVE_CTRL_WORDS * 4, &bars[slot]);
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) db_mbar_init(&bars[i], 1);
+        db_mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int q = 0; q < nstages && q < nchunks; ++q) issue(q, q);
+    if (active) SOLVE_PROLOGUE(NV, B.n)
+    auto stage_ctrl = [&](int slot) { return reinterpret_cast<const int*>(ring + (size_t)slot * SOLVE_FSTAGE_BYTES + SOLVE_CE * DB_TILE * 8); };
+    // gathers of chunk q -> G[q % GS][j][thread]; the stage of chunk q is slot q % nstages, its first phase parity (q / nstages) & 1
+    auto gather = [&](int q) {
+        const int slot = q % nstages;
+        db_mbar_wait(&bars[slot], (unsigned)((q / nstages) & 1));
+        const int* __restrict__ ctrl = stage_ctrl(slot);
+        double* g = G + ((size_t)(q % GS) * SOLVE_CE) * NT + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < SOLVE_CE; j += 4) {
+            const int4 o = *reinterpret_cast<const int4*>(ctrl + j);
+            db_cp_async8(g + (size_t)(j + 0) * NT, x + o.x); db_cp_async8(g + (size_t)(j + 1) * NT, x + o.y);
+            db_cp_async8(g + (size_t)(j + 2) * NT, x + o.z); db_cp_async8(g + (size_t)(j + 3) * NT, x + o.w);
+        }
+    };
+    if (active)
+        for (int q = 0; q < D; ++q) { if (q < nchunks) gather(q); db_cp_commit(); }
+    unsigned cnt = 0;                                           // row ends so far (uniform): next slot of the recent-rows ring
+    double acc = 0.0;
+    double* rr = RR + threadIdx.x;
+    for (int q = 0; q < nchunks; ++q) {
+        const int slot = q % nstages;
+        if (active) {
+            if (q + D < nchunks) gather(q + D);
+            db_cp_commit();
+            db_cp_wait<D>();                                     // the group of chunk q (and everything older) has landed
+            const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+            const double* __restrict__ vals = reinterpret_cast<const double*>(st) + lane;
+            const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+            const double* g = G + ((size_t)(q % GS) * SOLVE_CE) * NT + threadIdx.x;
+            const unsigned maskE = (unsigned)ctrl[32], maskB = (unsigned)ctrl[33], maskR = (unsigned)ctrl[36], maskG = (unsigned)ctrl[37];
+            const bool fwd = q < nfwd;
+            if ((maskE | maskB | maskR | maskG) == 0) {
+#pragma unroll
+                for (int j = 0; j < SOLVE_CE; ++j) acc = fma(-vals[j * DB_TILE], g[(size_t)j * NT], acc);
+            } else {
+                const unsigned rs0 = (unsigned)ctrl[38], rs1 = (unsigned)ctrl[39], rs2 = (unsigned)ctrl[40];
+#pragma unroll
+                for (int j = 0; j < SOLVE_CE; ++j) {
+                    const unsigned bit = 1u << j;
+                    const double v = vals[j * DB_TILE];
+                    double xv = g[(size_t)j * NT];
+                    if (maskR & bit) {
+                        const unsigned w = (j < 6) ? rs0 : (j < 12) ? rs1 : rs2;
+                        xv = rr[(size_t)((w >> (5 * (j % 6))) & 31u) * NT];
+                    }
+                    if (maskG & bit) xv = x[ctrl[j]];
+                    const double acc_a = fma(-v, xv, acc);
+                    const double val = fwd ? acc : acc * v;
+                    if (maskE & bit) { x[ctrl[SOLVE_CE + j]] = val; rr[(size_t)(cnt & (RRN - 1)) * NT] = val; ++cnt; }
+                    acc = (maskB & bit) ? xv : acc_a;
+                }
+            }
+        }
+        if (blockDim.x > 32) __syncthreads(); else __syncwarp();     // every warp is done with this stage
+        if (threadIdx.x == 0 && q + nstages < nchunks) issue(q + nstages, slot);
+    }
+}
+
 extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t total_blocks, int32_t max_nrhs, int32_t lu_slot, int32_t x_slot,
                                 const db_slotcomb* rhs, void* stream)
 {
@@ -734,12 +847,13 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     }
     const dim3 g(total_blocks), b(SOLVE_THREADS * max_nrhs);
     const int nv = rhs->nvec;
-    static int st_env = -1, pipe_env = 0, rt_env = 0, minb_env = 3;
+    static int st_env = -1, pipe_env = 0, rt_env = 0, minb_env = 3, deep_env = -1;
     if (st_env < 0) {
         const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
         const char* p = getenv("DB_SOLVE_PIPE"); pipe_env = p ? atoi(p) : 0;
         const char* r = getenv("DB_SOLVE_RT"); rt_env = r ? atoi(r) : 0;
         const char* m = getenv("DB_SOLVE_MINB"); minb_env = m ? atoi(m) : 3;
+        const char* d = getenv("DB_SOLVE_DEEP"); deep_env = d ? atoi(d) : -1;
     }
     // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
     // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
@@ -753,11 +867,29 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (rt != 1 && rt != 2 && rt != 4) rt = 1;
     if (rt > max_nrhs) rt = max_nrhs >= 2 ? 2 : 1;
     const dim3 bmr(SOLVE_THREADS * ((max_nrhs + rt - 1) / rt));
+    // deep-prefetch kernel: by default when there is at most one tile per SM (the launch is then bound by one thread's
+    // dependent chain, not by bandwidth); DB_SOLVE_DEEP = 0 / 1 forces it off / on.  Members per CTA: as few as still give
+    // at most one CTA per SM (more SMs at work, deeper factor ring per CTA); DB_SOLVE_DEEP_MPC overrides.
+    const bool deep = deep_env >= 0 ? deep_env != 0 : total_blocks <= 148;
+    static int mpc_env = -1;
+    if (mpc_env < 0) { const char* e = getenv("DB_SOLVE_DEEP_MPC"); mpc_env = e ? atoi(e) : 0; }
+    int mpc = 1;
+    while (mpc < max_nrhs && total_blocks * ((max_nrhs + mpc - 1) / mpc) > 148) mpc *= 2;
+    if (mpc_env == 1 || mpc_env == 2 || mpc_env == 4) mpc = mpc_env;
+    if (mpc > max_nrhs) mpc = max_nrhs;
+    const dim3 g_deep(total_blocks, (max_nrhs + mpc - 1) / mpc), b_deep(SOLVE_THREADS * mpc);
+    const size_t deep_fixed = (size_t)((SOLVE_DEEP_D + 1) * SOLVE_CE + SOLVE_DEEP_RRN) * b_deep.x * sizeof(double) + 64;
+    int nst_deep = (int)(((size_t)220 * 1024 - deep_fixed) / (SOLVE_FSTAGE_BYTES + sizeof(db_mbar_t)));
+    if (nst_deep > 24) nst_deep = 24;
+    if (st_env >= SOLVE_DEEP_D + 2 && st_env <= 24 && st_env < nst_deep) nst_deep = st_env;
+    const size_t smem_deep = (((size_t)nst_deep * SOLVE_FSTAGE_BYTES + (size_t)nst_deep * sizeof(db_mbar_t) + 15) & ~(size_t)15) + deep_fixed;
 #define FLAT_GO(NV_) { static int attr_st = 0; \
     if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 3>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 4>)); \
                     DB_SET_SMEM_ATTR((k_batches_solve_pipe<NV_>)); \
-                    DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 4>)); attr_st = 1; } \
-    if (rt == 4 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 4>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
+                    DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 4>)); \
+                    DB_SET_SMEM_ATTR((k_batches_solve_deep<NV_>)); attr_st = 1; } \
+    if (deep) DB_LAUNCH((k_batches_solve_deep<NV_>), g_deep, b_deep, smem_deep, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst_deep); \
+    else if (rt == 4 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 4>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
     else if (rt == 2 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 2>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
     else if (pipe_env && nst >= 2) DB_LAUNCH((k_batches_solve_pipe<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
     else if (minb_env == 4) DB_LAUNCH((k_batches_solve_flat<NV_, 4>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \

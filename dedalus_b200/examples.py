@@ -21,11 +21,12 @@ def kdv_initial_condition(u, xbasis, Lx, n=20):
     u['g'] = np.log(1 + np.cosh(n)**2 / np.cosh(n * (x - 0.2 * Lx))**2) / (2 * n)
 
 
-def rayleigh_benard(dim=3, Nh=256, Nz=256, Rayleigh=1e6, Prandtl=1, Lx=4, Lz=1, dealias=3/2, mesh=None, dtype=np.float64):
+def rayleigh_benard(dim=3, Nh=256, Nz=256, Rayleigh=1e6, Prandtl=1, Lx=4, Lz=1, dealias=3/2, mesh=None, dtype=np.float64, Nx=None):
     names = ('x', 'z') if dim == 2 else ('x', 'y', 'z')
     coords = d3.CartesianCoordinates(*names)
     dist = d3.Distributor(coords, dtype=dtype, mesh=mesh)
-    hb = tuple(d3.RealFourier(coords[n], size=Nh, bounds=(0, Lx), dealias=dealias) for n in names[:-1])
+    # Nx: size of the FIRST horizontal axis if different from Nh (slab-shaped problems: one rank's share of a distributed run)
+    hb = tuple(d3.RealFourier(coords[n], size=(Nx if (Nx and i == 0) else Nh), bounds=(0, Lx), dealias=dealias) for i, n in enumerate(names[:-1]))
     zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, Lz), dealias=dealias)
     bases = hb + (zb,)
     p = dist.Field(name='p', bases=bases)

@@ -482,12 +482,14 @@ def _permuted_templates(batch, name):
     return out
 
 
-SOLVE_CTRL_WORDS = 36
+SOLVE_CTRL_WORDS = 44
+SOLVE_DEEP_D = 3          # k_batches_solve_deep: gathers are issued this many chunks ahead (csrc/pencil.cu SOLVE_DEEP_D)
+SOLVE_DEEP_RING = 16      # ... and the last 16 finished rows are kept in a shared-memory ring (SOLVE_DEEP_RRN)
 
 
 def solve_control_blocks(code, n_fwd, tile=64, CH=16):
-    """Per-chunk control blocks of the branch-free solve kernel (csrc/pencil.cu k_batches_solve_flat), derived from the
-    flat instruction stream: for each chunk of 16 entries
+    """Per-chunk control blocks of the branch-free solve kernels (csrc/pencil.cu), derived from the flat instruction stream:
+    for each chunk of 16 entries
         goff[16]  element offset gathered before the chunk is consumed: the column of a multiply-accumulate entry, the
                   row ENTERED (its start value) at a row-boundary entry, 0 for padding (whose factor value is 0)
         foff[16]  element offset of the row LEFT at a row-boundary entry
@@ -495,14 +497,23 @@ def solve_control_blocks(code, n_fwd, tile=64, CH=16):
         maskF     entries whose gathered value was stored inside this very chunk (re-read right before use)
         maskF2    the same for a gather issued ONE CHUNK EARLIER (software-pipelined kernel variant): stored inside this
                   or the previous chunk
-    Layout: int32 [nchunks][36] = goff, foff, maskE, maskB, maskF, maskF2."""
+      deep-prefetch kernel (gathers issued SOLVE_DEEP_D chunks ahead, landing in shared memory):
+        maskR     entries whose source row was finished after their gather was issued AND is still among the last
+                  SOLVE_DEEP_RING finished rows: taken from the shared-memory ring of recent rows, slot rslot[j]
+                  (= index of that row's store modulo the ring size; the kernel counts row ends the same way)
+        maskG     such entries whose source is older than the ring: re-read from global memory right before use
+        rslot     16 x 5 bits packed 6 per word
+    Layout: int32 [nchunks][44] = goff, foff, maskE, maskB, maskF, maskF2, maskR, maskG, rslot[3], spare[3]."""
     SKIP = -2**31
+    D, RRN = SOLVE_DEEP_D, SOLVE_DEEP_RING
     code = np.asarray(code, dtype=np.int64)
     nE = len(code)
     assert nE % CH == 0 and n_fwd % CH == 0
     out = np.zeros((nE // CH, SOLVE_CTRL_WORDS), dtype=np.int64)
     cur = -1
     stored_at = {}                         # element offset -> position of its most recent store
+    store_idx = {}                         # element offset -> running index (count of row ends before it) of that store
+    nstores = 0
     for e in range(nE):
         if e == n_fwd:
             cur = -1
@@ -510,25 +521,35 @@ def solve_control_blocks(code, n_fwd, tile=64, CH=16):
         c = int(code[e])
         if c == SKIP:
             continue
+
+        def mark(src):
+            pos = stored_at.get(src, -1)
+            if pos >= q * CH:
+                out[q, 34] |= 1 << j
+            if pos >= (q - 1) * CH:
+                out[q, 35] |= 1 << j
+            if pos >= 0 and pos >= (q - D) * CH:          # stored after the deep kernel issued this entry's gather
+                k = store_idx[src]
+                if nstores - k <= RRN:                    # still in the ring (nstores = row ends before this entry)
+                    out[q, 36] |= 1 << j
+                    out[q, 38 + j // 6] |= (k % RRN) << (5 * (j % 6))
+                else:
+                    out[q, 37] |= 1 << j
         if c < 0:
             nxt = -1 - c
             out[q, j] = nxt
             out[q, 33] |= 1 << j
-            if stored_at.get(nxt, -1) >= q * CH:
-                out[q, 34] |= 1 << j
-            if stored_at.get(nxt, -1) >= (q - 1) * CH:
-                out[q, 35] |= 1 << j
+            mark(nxt)
             if cur >= 0:
                 out[q, 16 + j] = cur
                 out[q, 32] |= 1 << j
                 stored_at[cur] = e
+                store_idx[cur] = nstores
+                nstores += 1
             cur = nxt
         else:
             out[q, j] = c
-            if stored_at.get(c, -1) >= q * CH:
-                out[q, 34] |= 1 << j
-            if stored_at.get(c, -1) >= (q - 1) * CH:
-                out[q, 35] |= 1 << j
+            mark(c)
     return out.astype(np.int32)
 
 

@@ -69,6 +69,46 @@ def solve(prog, LU, rhs, pipelined=False):
     return y
 
 
+def solve_deep(prog, LU, rhs, D=None, RRN=None):
+    """Mirrors csrc/pencil.cu k_batches_solve_deep: the 16 gathers of chunk q are issued D chunks ahead (they see x as it
+    was before chunk q - D was consumed); entries in maskR take their value from the ring of the last RRN finished rows
+    (slot from the packed rslot words), entries in maskG re-read global memory right before use."""
+    from dedalus_b200.pencils import SOLVE_DEEP_D, SOLVE_DEEP_RING
+    D = SOLVE_DEEP_D if D is None else D
+    RRN = SOLVE_DEEP_RING if RRN is None else RRN
+    CH, ld = 16, prog.tile
+    y = np.array(rhs, dtype=float, copy=True)
+    ctrl = prog.ctrl
+    nchunks, nfwd = prog.nE // CH, prog.n_fwd // CH
+    gather = lambda q: [y[g // ld].copy() for g in ctrl[q, :16]]
+    inflight = {q: gather(q) for q in range(min(D, nchunks))}          # issued before chunk 0 is consumed
+    ring = [None] * RRN
+    cnt = 0
+    acc = np.zeros_like(y[0])
+    for q in range(nchunks):
+        if q + D < nchunks:
+            inflight[q + D] = gather(q + D)                              # top of iteration q
+        xv = inflight.pop(q)
+        forward = q < nfwd
+        goff, foff = ctrl[q, :16], ctrl[q, 16:32]
+        maskE, maskB, maskR, maskG = (int(ctrl[q, w]) & 0xFFFF for w in (32, 33, 36, 37))
+        for j in range(CH):
+            e = q * CH + j
+            if maskR >> j & 1:
+                slot = (int(ctrl[q, 38 + j // 6]) >> (5 * (j % 6))) & 31
+                xv[j] = ring[slot].copy()
+            if maskG >> j & 1:
+                xv[j] = y[goff[j] // ld].copy()
+            acc_a = acc - LU[e] * xv[j]
+            val = acc if forward else acc * LU[e]
+            if maskE >> j & 1:
+                y[foff[j] // ld] = val
+                ring[cnt % RRN] = val.copy()
+                cnt += 1
+            acc = xv[j] if (maskB >> j & 1) else acc_a
+    return y
+
+
 def matvec(prog, name, x):
     ptr, col, mono, val = prog.mv[name]
     y = np.zeros_like(x)

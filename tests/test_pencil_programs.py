@@ -26,6 +26,7 @@ def test_rb_programs_solve(dim, Nh, Nz, dt, dense):
         rhs = rng.standard_normal((prog.n, prog.S))
         x = pi.solve(prog, LU, rhs)
         assert np.allclose(pi.solve(prog, LU, rhs, pipelined=True), x, rtol=0, atol=0)      # one-chunk-early gathers + word-35 re-reads
+        assert np.allclose(pi.solve_deep(prog, LU, rhs), x, rtol=0, atol=0)                 # deep prefetch + ring of recent rows
         xm = rng.standard_normal((prog.n, prog.S))
         Mx = pi.matvec(prog, 'M', xm); Lx = pi.matvec(prog, 'L', xm)
         for s in range(0, prog.S, max(1, prog.S // 5)):
