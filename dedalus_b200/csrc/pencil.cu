@@ -283,17 +283,20 @@ __device__ __forceinline__ int find_batch(const db_batch* __restrict__ b, int nb
 // independent loads in flight per thread).  The forward sweep then starts each row from x[row] like the backward sweep
 // does; folding the combination into the row starts instead puts NV dependent DRAM loads on the recurrence's critical
 // path two or three times per 16-entry chunk (rows are short), which is what the sweep's time was made of.
+#define SOLVE_PRO_U 8      /* rows per iteration: NV * 8 independent streaming loads in flight per thread (the prologue was 18 % of the
+                              solve's stall samples at 4 rows: it is a pure DRAM stream, bound by loads in flight) */
 #define SOLVE_PROLOGUE(NV_, NROWS)                                                                  \
     {                                                                                               \
         const int nrows_ = (NROWS);                                                                 \
         int i_ = 0;                                                                                 \
-        for (; i_ + 4 <= nrows_; i_ += 4) {                                                         \
-            double a_[4] = {0.0, 0.0, 0.0, 0.0};                                                    \
+        for (; i_ + SOLVE_PRO_U <= nrows_; i_ += SOLVE_PRO_U) {                                     \
+            double a_[SOLVE_PRO_U];                                                                 \
+            _Pragma("unroll") for (int u_ = 0; u_ < SOLVE_PRO_U; ++u_) a_[u_] = 0.0;                \
             _Pragma("unroll") for (int q_ = 0; q_ < NV_; ++q_) {                                    \
-                _Pragma("unroll") for (int u_ = 0; u_ < 4; ++u_)                                    \
+                _Pragma("unroll") for (int u_ = 0; u_ < SOLVE_PRO_U; ++u_)                          \
                     a_[u_] = fma(cf[q_], DB_LDCS(rv[q_] + (int64_t)(i_ + u_) * DB_TILE), a_[u_]);   \
             }                                                                                       \
-            _Pragma("unroll") for (int u_ = 0; u_ < 4; ++u_) x[(int64_t)(i_ + u_) * DB_TILE] = a_[u_]; \
+            _Pragma("unroll") for (int u_ = 0; u_ < SOLVE_PRO_U; ++u_) x[(int64_t)(i_ + u_) * DB_TILE] = a_[u_]; \
         }                                                                                           \
         for (; i_ < nrows_; ++i_) {                                                                 \
             double a_ = 0.0;                                                                        \
@@ -327,6 +330,14 @@ __device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
 {
     while ((((*bar) >> 32) & 1ull) == parity) emu_yield();
 }
+// arrival-count barrier (emulation): bits 0-15 pending arrivals, bits 16-31 arrivals per phase, bits 32.. completed phases
+__device__ __forceinline__ void db_cbar_init(db_mbar_t* bar, int count) { *bar = (unsigned long long)count | ((unsigned long long)count << 16); }
+__device__ __forceinline__ void db_cbar_arrive(db_mbar_t* bar)
+{
+    *bar -= 1;
+    if ((*bar & 0xffffull) == 0) *bar += (1ull << 32) + ((*bar >> 16) & 0xffffull);
+}
+#define DB_CBAR_PER_THREAD 1        // every consumer thread arrives (fibers are not warp-synchronous)
 #else
 typedef unsigned long long db_mbar_t;
 __device__ __forceinline__ unsigned db_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -340,6 +351,10 @@ __device__ __forceinline__ void db_bulk_g2s(void* dst, const void* src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(db_smem_u32(dst)), "l"(src), "r"(bytes), "r"(db_smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void db_cbar_init(db_mbar_t* bar, int count) { db_mbar_init(bar, count); }
+__device__ __forceinline__ void db_cbar_arrive(db_mbar_t* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(db_smem_u32(bar)) : "memory"); }
+#define DB_CBAR_PER_THREAD 0        // one elected lane per consumer warp arrives after __syncwarp()
 __device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
 {
     asm volatile("{\n"
@@ -364,6 +379,22 @@ __device__ __forceinline__ void db_mbar_wait(db_mbar_t* bar, unsigned parity)
 // all entries) take a shorter path.
 // ---------------------------------------------------------------------------------------------------------
 #define SOLVE_CTRL_WORDS 44
+// Start values of the rows entered SOLVE_PF_AHEAD chunks from now (control words 41, 42): pulled towards the SM early, so
+// that the gather at the row's first entry hits a cache instead of paying a DRAM round trip on the thread's critical path
+#ifdef DB_EMU
+#define DB_PREFETCH_L2(p) ((void)0)
+#define DB_PREFETCH_L1(p) ((void)0)
+#else
+#define DB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define DB_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#endif
+__device__ __forceinline__ void solve_prefetch(const int* __restrict__ ctrl, const double* x, int mode)
+{
+    if (mode == 0) return;
+    const int p0 = ctrl[41], p1 = ctrl[42];
+    if (mode == 1) { if (p0 >= 0) DB_PREFETCH_L2(x + p0); if (p1 >= 0) DB_PREFETCH_L2(x + p1); }
+    else { if (p0 >= 0) DB_PREFETCH_L1(x + p0); if (p1 >= 0) DB_PREFETCH_L1(x + p1); }
+}
 #define SOLVE_FSTAGE_BYTES (SOLVE_CE * DB_TILE * 8 + SOLVE_CTRL_WORDS * 4)
 
 template <bool FWD, bool LATE>
@@ -407,8 +438,9 @@ __device__ __forceinline__ double solve_chunk_pure(const double* __restrict__ va
 
 template <int NV, int MINB>
 __global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS, MINB)
-k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
+k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages_pf)
 {
+    const int nstages = nstages_pf & 255, pfmode = nstages_pf >> 8;       // ring depth | row-start prefetch mode << 8
     // blockDim.x = 64 * (largest nrhs of the launch).  Thread group g = threadIdx.x / 64 owns member g of the tile's 64
     // pencils: all groups consume the SAME factor stage of the ring (one DRAM read of the factors for nrhs solves); groups
     // beyond the batch's nrhs only take part in the barriers.
@@ -453,6 +485,7 @@ k_batches_solve_flat(const db_batch* __restrict__ batches, int nbatch, int lu_sl
             const double* __restrict__ vals = reinterpret_cast<const double*>(st) + lane;
             const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
             const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+            solve_prefetch(ctrl, x, pfmode);
             if ((mB | mF) == 0) acc = solve_chunk_pure(vals, ctrl, x, acc);
             else if (q < nfwd) acc = mF ? solve_chunk_flat<true, true>(vals, ctrl, x, acc) : solve_chunk_flat<true, false>(vals, ctrl, x, acc);
             else acc = mF ? solve_chunk_flat<false, true>(vals, ctrl, x, acc) : solve_chunk_flat<false, false>(vals, ctrl, x, acc);
@@ -579,6 +612,89 @@ k_batches_solve_pipe(const db_batch* __restrict__ batches, int nbatch, int lu_sl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-specialised variant of k_batches_solve_flat: a PRODUCER warp feeds the factor ring, the consumer warps never meet
+// at a CTA barrier.  In the kernel above every chunk ends with __syncthreads() + thread 0 issuing the next stage
+// (mbarrier.arrive.expect_tx + two cp.async.bulk), so all eight warps advance at the pace of warp 0 and pay the issue
+// latency of the bulk copies once per chunk: the time per launch hardly depends on the number of tiles (2.1 ms at 39
+// tiles, 2.6 ms at 264: one thread's chain of 1600 chunks at ~1.3 us each), i.e. the chain, not the bandwidth, sets the time.
+// Here stage release is an arrival-count mbarrier per stage (one arrival per consumer warp), the producer lane waits on
+// it before refilling, and consumers only ever wait for "stage full".
+// ---------------------------------------------------------------------------------------------------------
+template <int NV, int MINB>
+__global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS + 32, MINB)
+k_batches_solve_ws(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages_pf)
+{
+    const int nstages = nstages_pf & 255, pfmode = nstages_pf >> 8;       // ring depth | row-start prefetch mode << 8
+    DB_SMEM(unsigned char, ring);
+    db_mbar_t* full = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
+    db_mbar_t* empty = full + nstages;
+    const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
+    const db_batch& B = batches[bi];
+    const int tile = blockIdx.x - B.blk_solve;
+    const int ncons = blockDim.x - 32;                          // consumer threads: 64 per member group
+    const int ngroups = ncons / SOLVE_THREADS;
+    const int act_groups = B.nrhs < ngroups ? B.nrhs : ngroups;
+    const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstages; ++i) {
+            db_mbar_init(&full[i], 1);
+            db_cbar_init(&empty[i], DB_CBAR_PER_THREAD ? act_groups * SOLVE_THREADS : act_groups * (SOLVE_THREADS / 32));
+        }
+        db_mbar_fence_init();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= ncons) {
+        // ---- producer warp: one lane streams the tile's factors + control blocks through the ring
+        if (threadIdx.x == ncons) {
+            const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
+            const int32_t* __restrict__ ctrl_g = B.ctrl;
+            int slot = 0;
+            unsigned par = 0;                                   // parity of the "empty" phase to wait for: (q / nstages - 1) & 1
+            for (int q = 0; q < nchunks; ++q) {
+                if (q >= nstages) db_mbar_wait(&empty[slot], par);
+                unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+                db_mbar_expect_tx(&full[slot], SOLVE_FSTAGE_BYTES);
+                db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &full[slot]);
+                db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, ctrl_g + (int64_t)q * SOLVE_CTRL_WORDS, SOLVE_CTRL_WORDS * 4, &full[slot]);
+                if (++slot == nstages) { slot = 0; if (q >= nstages) par ^= 1; }      // flips at the end of every wrap after the first
+            }
+        }
+        return;
+    }
+    const int grp = threadIdx.x / SOLVE_THREADS, lane = threadIdx.x % SOLVE_THREADS;
+    if (grp >= B.nrhs) return;                                  // member groups this batch does not have
+    const int s = grp * B.ld + tile * SOLVE_THREADS + lane;      // padded lanes run on the zero padding
+    const int64_t tb = db_tbase(s, B.n);
+    double* x = B.vec[x_slot] + tb;
+    const double* rv[NV];
+    double cf[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { rv[j] = B.vec[rhs.slot[j < rhs.nvec ? j : 0]] + tb; cf[j] = (j < rhs.nvec) ? rhs.coef[j] : 0.0; }
+    SOLVE_PROLOGUE(NV, B.n)
+    double acc = 0.0;
+    int slot = 0;
+    unsigned phase = 0;
+    for (int q = 0; q < nchunks; ++q) {
+        db_mbar_wait(&full[slot], phase);
+        const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
+        const double* __restrict__ vals = reinterpret_cast<const double*>(st) + lane;
+        const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
+        const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+        solve_prefetch(ctrl, x, pfmode);
+        if ((mB | mF) == 0) acc = solve_chunk_pure(vals, ctrl, x, acc);
+        else if (q < nfwd) acc = mF ? solve_chunk_flat<true, true>(vals, ctrl, x, acc) : solve_chunk_flat<true, false>(vals, ctrl, x, acc);
+        else acc = mF ? solve_chunk_flat<false, true>(vals, ctrl, x, acc) : solve_chunk_flat<false, false>(vals, ctrl, x, acc);
+#if DB_CBAR_PER_THREAD
+        db_cbar_arrive(&empty[slot]);
+#else
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) db_cbar_arrive(&empty[slot]);
+#endif
+        if (++slot == nstages) { slot = 0; phase ^= 1; }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Members in registers (DB_SOLVE_RT = 2 / 4): one thread carries RT members of its pencil -- RT independent recurrences
@@ -740,8 +856,9 @@ k_batches_solve_mr(const db_batch* __restrict__ batches, int nbatch, int lu_slot
 #define SOLVE_DEEP_RRN 16
 template <int NV>
 __global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS, 1)
-k_batches_solve_deep(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages)
+k_batches_solve_deep(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages_pf)
 {
+    const int nstages = nstages_pf & 255, pfmode = nstages_pf >> 8;
     constexpr int D = SOLVE_DEEP_D, GS = D + 1, RRN = SOLVE_DEEP_RRN;
     DB_SMEM(unsigned char, ring);
     const int NT = blockDim.x;
@@ -811,6 +928,7 @@ k_batches_solve_deep(const db_batch* __restrict__ batches, int nbatch, int lu_sl
             const double* g = G + ((size_t)(q % GS) * SOLVE_CE) * NT + threadIdx.x;
             const unsigned maskE = (unsigned)ctrl[32], maskB = (unsigned)ctrl[33], maskR = (unsigned)ctrl[36], maskG = (unsigned)ctrl[37];
             const bool fwd = q < nfwd;
+            solve_prefetch(ctrl, x, pfmode);
             if ((maskE | maskB | maskR | maskG) == 0) {
 #pragma unroll
                 for (int j = 0; j < SOLVE_CE; ++j) acc = fma(-vals[j * DB_TILE], g[(size_t)j * NT], acc);
@@ -847,13 +965,15 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     }
     const dim3 g(total_blocks), b(SOLVE_THREADS * max_nrhs);
     const int nv = rhs->nvec;
-    static int st_env = -1, pipe_env = 0, rt_env = 0, minb_env = 3, deep_env = -1;
+    static int st_env = -1, pipe_env = 0, rt_env = 0, minb_env = 3, deep_env = -1, ws_env = 1, pf_env = 2;
     if (st_env < 0) {
         const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
         const char* p = getenv("DB_SOLVE_PIPE"); pipe_env = p ? atoi(p) : 0;
         const char* r = getenv("DB_SOLVE_RT"); rt_env = r ? atoi(r) : 0;
         const char* m = getenv("DB_SOLVE_MINB"); minb_env = m ? atoi(m) : 3;
         const char* d = getenv("DB_SOLVE_DEEP"); deep_env = d ? atoi(d) : -1;
+        const char* w = getenv("DB_SOLVE_WS"); ws_env = w ? atoi(w) : 1;
+        const char* f = getenv("DB_SOLVE_PF"); pf_env = f ? atoi(f) : 2;
     }
     // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
     // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
@@ -870,7 +990,7 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     // deep-prefetch kernel: by default when there is at most one tile per SM (the launch is then bound by one thread's
     // dependent chain, not by bandwidth); DB_SOLVE_DEEP = 0 / 1 forces it off / on.  Members per CTA: as few as still give
     // at most one CTA per SM (more SMs at work, deeper factor ring per CTA); DB_SOLVE_DEEP_MPC overrides.
-    const bool deep = deep_env >= 0 ? deep_env != 0 : total_blocks <= 148;
+    const bool deep = deep_env > 0;          // opt-in (DB_SOLVE_DEEP=1): measured no faster than the one-chunk-early variant
     static int mpc_env = -1;
     if (mpc_env < 0) { const char* e = getenv("DB_SOLVE_DEEP_MPC"); mpc_env = e ? atoi(e) : 0; }
     int mpc = 1;
@@ -887,14 +1007,19 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 3>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 4>)); \
                     DB_SET_SMEM_ATTR((k_batches_solve_pipe<NV_>)); \
                     DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 4>)); \
+                    DB_SET_SMEM_ATTR((k_batches_solve_ws<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_ws<NV_, 3>)); \
                     DB_SET_SMEM_ATTR((k_batches_solve_deep<NV_>)); attr_st = 1; } \
-    if (deep) DB_LAUNCH((k_batches_solve_deep<NV_>), g_deep, b_deep, smem_deep, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst_deep); \
+    if (ws_env && !deep && rt == 1 && !pipe_env) { \
+        const size_t smem_ws = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)2 * nst * sizeof(db_mbar_t); \
+        if (minb_env == 4) DB_LAUNCH((k_batches_solve_ws<NV_, 3>), g, dim3(b.x + 32), smem_ws, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst | (pf_env << 8)); \
+        else DB_LAUNCH((k_batches_solve_ws<NV_, 2>), g, dim3(b.x + 32), smem_ws, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst | (pf_env << 8)); } \
+    else if (deep) DB_LAUNCH((k_batches_solve_deep<NV_>), g_deep, b_deep, smem_deep, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst_deep | (pf_env << 8)); \
     else if (rt == 4 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 4>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
     else if (rt == 2 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 2>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
     else if (pipe_env && nst >= 2) DB_LAUNCH((k_batches_solve_pipe<NV_>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
-    else if (minb_env == 4) DB_LAUNCH((k_batches_solve_flat<NV_, 4>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
-    else if (minb_env == 2) DB_LAUNCH((k_batches_solve_flat<NV_, 2>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
-    else DB_LAUNCH((k_batches_solve_flat<NV_, 3>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); }
+    else if (minb_env == 4) DB_LAUNCH((k_batches_solve_flat<NV_, 4>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst | (pf_env << 8)); \
+    else if (minb_env == 2) DB_LAUNCH((k_batches_solve_flat<NV_, 2>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst | (pf_env << 8)); \
+    else DB_LAUNCH((k_batches_solve_flat<NV_, 3>), g, b, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst | (pf_env << 8)); }
     if (nv <= 1) FLAT_GO(1) else if (nv == 2) FLAT_GO(2) else if (nv == 3) FLAT_GO(3) else if (nv == 4) FLAT_GO(4)
     else if (nv == 5) FLAT_GO(5) else if (nv == 6) FLAT_GO(6) else if (nv <= 8) FLAT_GO(8) else if (nv <= 12) FLAT_GO(12) else FLAT_GO(16)
 #undef FLAT_GO

@@ -485,6 +485,7 @@ def _permuted_templates(batch, name):
 SOLVE_CTRL_WORDS = 44
 SOLVE_DEEP_D = 3          # k_batches_solve_deep: gathers are issued this many chunks ahead (csrc/pencil.cu SOLVE_DEEP_D)
 SOLVE_DEEP_RING = 16      # ... and the last 16 finished rows are kept in a shared-memory ring (SOLVE_DEEP_RRN)
+SOLVE_PF_AHEAD = 12       # chunks between the prefetch of a row's start value and the chunk that enters the row
 
 
 def solve_control_blocks(code, n_fwd, tile=64, CH=16):
@@ -503,7 +504,12 @@ def solve_control_blocks(code, n_fwd, tile=64, CH=16):
                   (= index of that row's store modulo the ring size; the kernel counts row ends the same way)
         maskG     such entries whose source is older than the ring: re-read from global memory right before use
         rslot     16 x 5 bits packed 6 per word
-    Layout: int32 [nchunks][44] = goff, foff, maskE, maskB, maskF, maskF2, maskR, maskG, rslot[3], spare[3]."""
+      prefetch (all kernels): pf[2] = element offsets of the first two rows ENTERED FOR THE FIRST TIME in chunk
+        q + SOLVE_PF_AHEAD (-1: none).  A row's start value (the right-hand side in the forward sweep, the forward result
+        in the backward sweep) was written long before it is needed and has left the L2 by then: without the prefetch every
+        row costs one DRAM round trip on the critical path of its thread (ncu, round 2: that is what the time of the sweep
+        was made of when there are few tiles per SM).
+    Layout: int32 [nchunks][44] = goff, foff, maskE, maskB, maskF, maskF2, maskR, maskG, rslot[3], pf[2], spare."""
     SKIP = -2**31
     D, RRN = SOLVE_DEEP_D, SOLVE_DEEP_RING
     code = np.asarray(code, dtype=np.int64)
@@ -550,6 +556,25 @@ def solve_control_blocks(code, n_fwd, tile=64, CH=16):
         else:
             out[q, j] = c
             mark(c)
+    # prefetch words: first entries into rows, per chunk
+    out[:, 41] = -1; out[:, 42] = -1
+    first_entries = [[] for _ in range(nE // CH)]
+    seen = set()
+    for e in range(nE):
+        if e == n_fwd:
+            seen = set()
+        c = int(code[e])
+        if c != SKIP and c < 0:
+            row = -1 - c
+            if row not in seen:
+                seen.add(row)
+                first_entries[e // CH].append(row)
+    for q in range(nE // CH):
+        tgt = q + SOLVE_PF_AHEAD
+        if tgt < nE // CH:
+            for k, row in enumerate(first_entries[tgt][:2]):
+                out[q, 41 + k] = row
+    # (rows first entered in chunks 0 .. SOLVE_PF_AHEAD-1 are not prefetched; the kernel's prologue has just written them)
     return out.astype(np.int32)
 
 
