@@ -400,10 +400,10 @@ __device__ __forceinline__ void solve_prefetch(const int* __restrict__ ctrl, con
 template <bool FWD, bool LATE>
 __device__ __forceinline__ double solve_chunk_flat(const double* __restrict__ vals, const int* __restrict__ ctrl, double* x, double acc)
 {
-    // register diet (ncu, round 2: the sweep is bound by the number of gathers in flight per SM, i.e. by resident warps x 16;
-    // 102 registers allowed two 256-thread CTAs per SM): the gather offsets are consumed straight from the control block and
-    // the finished-row / late offsets are re-read from shared memory at the few entries that need them, so that only the 16
-    // gathered values stay live -> three CTAs per SM
+    // register diet: the gather offsets are consumed straight from the control block and the finished-row / late offsets are
+    // re-read from shared memory at the few entries that need them, so that only the 16 gathered values stay live.
+    // (Measured, round 2: also holding the 16 factor values in registers -- to take their shared-memory loads off the
+    // dependent chain -- costs more in occupancy / spills than it gains: 2.32 -> 2.8 ms per launch at 256^3.)
     double xv[SOLVE_CE];
 #pragma unroll
     for (int j = 0; j < SOLVE_CE; j += 4) {
@@ -626,9 +626,13 @@ template <int NV, int MINB>
 __global__ void __launch_bounds__(SOLVE_THREADS * SOLVE_MAX_RHS + 32, MINB)
 k_batches_solve_ws(const db_batch* __restrict__ batches, int nbatch, int lu_slot, int x_slot, db_slotcomb rhs, int nstages_pf)
 {
-    const int nstages = nstages_pf & 255, pfmode = nstages_pf >> 8;       // ring depth | row-start prefetch mode << 8
+    // nstages_pf = ring depth | row-start prefetch mode << 8 | chunks per stage << 16.  A stage carries `cps` consecutive
+    // 16-entry chunks (their factor values, then their control blocks): a single thread can only issue a bulk copy every few
+    // hundred cycles, so with one chunk per stage the producer lane, not the consumers, paces the sweep.
+    const int nstages = nstages_pf & 255, pfmode = (nstages_pf >> 8) & 255, cps = (nstages_pf >> 16) & 255;
+    const size_t stage_bytes = (size_t)cps * SOLVE_FSTAGE_BYTES;
     DB_SMEM(unsigned char, ring);
-    db_mbar_t* full = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * SOLVE_FSTAGE_BYTES);
+    db_mbar_t* full = reinterpret_cast<db_mbar_t*>(ring + (size_t)nstages * stage_bytes);
     db_mbar_t* empty = full + nstages;
     const int bi = find_batch(batches, nbatch, blockIdx.x, 0);
     const db_batch& B = batches[bi];
@@ -637,6 +641,7 @@ k_batches_solve_ws(const db_batch* __restrict__ batches, int nbatch, int lu_slot
     const int ngroups = ncons / SOLVE_THREADS;
     const int act_groups = B.nrhs < ngroups ? B.nrhs : ngroups;
     const int nchunks = B.n_entries / SOLVE_CE, nfwd = B.n_fwd / SOLVE_CE;
+    const int nst_total = (nchunks + cps - 1) / cps;            // stages to stream
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstages; ++i) {
             db_mbar_init(&full[i], 1);
@@ -651,14 +656,15 @@ k_batches_solve_ws(const db_batch* __restrict__ batches, int nbatch, int lu_slot
             const double* __restrict__ lu_tile = B.lu[lu_slot] + (int64_t)tile * B.n_entries * DB_TILE;
             const int32_t* __restrict__ ctrl_g = B.ctrl;
             int slot = 0;
-            unsigned par = 0;                                   // parity of the "empty" phase to wait for: (q / nstages - 1) & 1
-            for (int q = 0; q < nchunks; ++q) {
-                if (q >= nstages) db_mbar_wait(&empty[slot], par);
-                unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
-                db_mbar_expect_tx(&full[slot], SOLVE_FSTAGE_BYTES);
-                db_bulk_g2s(st, lu_tile + (int64_t)q * SOLVE_CE * DB_TILE, SOLVE_CE * DB_TILE * 8, &full[slot]);
-                db_bulk_g2s(st + SOLVE_CE * DB_TILE * 8, ctrl_g + (int64_t)q * SOLVE_CTRL_WORDS, SOLVE_CTRL_WORDS * 4, &full[slot]);
-                if (++slot == nstages) { slot = 0; if (q >= nstages) par ^= 1; }      // flips at the end of every wrap after the first
+            unsigned par = 0;                                   // parity of the "empty" phase to wait for: (t / nstages - 1) & 1
+            for (int t = 0; t < nst_total; ++t) {
+                if (t >= nstages) db_mbar_wait(&empty[slot], par);
+                const int q0 = t * cps, cs = (nchunks - q0 < cps) ? nchunks - q0 : cps;
+                unsigned char* st = ring + (size_t)slot * stage_bytes;
+                db_mbar_expect_tx(&full[slot], (unsigned)(cs * SOLVE_FSTAGE_BYTES));
+                db_bulk_g2s(st, lu_tile + (int64_t)q0 * SOLVE_CE * DB_TILE, (unsigned)(cs * SOLVE_CE * DB_TILE * 8), &full[slot]);
+                db_bulk_g2s(st + (size_t)cps * SOLVE_CE * DB_TILE * 8, ctrl_g + (int64_t)q0 * SOLVE_CTRL_WORDS, (unsigned)(cs * SOLVE_CTRL_WORDS * 4), &full[slot]);
+                if (++slot == nstages) { slot = 0; if (t >= nstages) par ^= 1; }      // flips at the end of every wrap after the first
             }
         }
         return;
@@ -676,16 +682,20 @@ k_batches_solve_ws(const db_batch* __restrict__ batches, int nbatch, int lu_slot
     double acc = 0.0;
     int slot = 0;
     unsigned phase = 0;
-    for (int q = 0; q < nchunks; ++q) {
+    for (int t = 0; t < nst_total; ++t) {
         db_mbar_wait(&full[slot], phase);
-        const unsigned char* st = ring + (size_t)slot * SOLVE_FSTAGE_BYTES;
-        const double* __restrict__ vals = reinterpret_cast<const double*>(st) + lane;
-        const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + SOLVE_CE * DB_TILE * 8);
-        const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
-        solve_prefetch(ctrl, x, pfmode);
-        if ((mB | mF) == 0) acc = solve_chunk_pure(vals, ctrl, x, acc);
-        else if (q < nfwd) acc = mF ? solve_chunk_flat<true, true>(vals, ctrl, x, acc) : solve_chunk_flat<true, false>(vals, ctrl, x, acc);
-        else acc = mF ? solve_chunk_flat<false, true>(vals, ctrl, x, acc) : solve_chunk_flat<false, false>(vals, ctrl, x, acc);
+        const unsigned char* st = ring + (size_t)slot * stage_bytes;
+        const int q0 = t * cps, cs = (nchunks - q0 < cps) ? nchunks - q0 : cps;
+        for (int c = 0; c < cs; ++c) {
+            const int q = q0 + c;
+            const double* __restrict__ vals = reinterpret_cast<const double*>(st + (size_t)c * SOLVE_CE * DB_TILE * 8) + lane;
+            const int* __restrict__ ctrl = reinterpret_cast<const int*>(st + (size_t)cps * SOLVE_CE * DB_TILE * 8) + c * SOLVE_CTRL_WORDS;
+            const unsigned mB = (unsigned)ctrl[2 * SOLVE_CE + 1], mF = (unsigned)ctrl[2 * SOLVE_CE + 2];
+            solve_prefetch(ctrl, x, pfmode & 3);
+            if ((mB | mF) == 0) acc = solve_chunk_pure(vals, ctrl, x, acc);
+            else if (q < nfwd) acc = mF ? solve_chunk_flat<true, true>(vals, ctrl, x, acc) : solve_chunk_flat<true, false>(vals, ctrl, x, acc);
+            else acc = mF ? solve_chunk_flat<false, true>(vals, ctrl, x, acc) : solve_chunk_flat<false, false>(vals, ctrl, x, acc);
+        }
 #if DB_CBAR_PER_THREAD
         db_cbar_arrive(&empty[slot]);
 #else
@@ -965,7 +975,7 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     }
     const dim3 g(total_blocks), b(SOLVE_THREADS * max_nrhs);
     const int nv = rhs->nvec;
-    static int st_env = -1, pipe_env = 0, rt_env = 0, minb_env = 3, deep_env = -1, ws_env = 1, pf_env = 2;
+    static int st_env = -1, pipe_env = 0, rt_env = 0, minb_env = 3, deep_env = -1, ws_env = 1, pf_env = 2, cps_env = 2;
     if (st_env < 0) {
         const char* t = getenv("DB_SOLVE_STAGES"); st_env = t ? atoi(t) : 0;
         const char* p = getenv("DB_SOLVE_PIPE"); pipe_env = p ? atoi(p) : 0;
@@ -974,6 +984,8 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
         const char* d = getenv("DB_SOLVE_DEEP"); deep_env = d ? atoi(d) : -1;
         const char* w = getenv("DB_SOLVE_WS"); ws_env = w ? atoi(w) : 1;
         const char* f = getenv("DB_SOLVE_PF"); pf_env = f ? atoi(f) : 2;
+        const char* c = getenv("DB_SOLVE_CPS"); cps_env = c ? atoi(c) : 2;
+        if (cps_env < 1 || cps_env > 8) cps_env = 2;
     }
     // ring depth: with ~7 CTAs per SM two stages already keep 100+ KB of factor bytes in flight per SM and every
     // further stage only shrinks the L1 the x gathers live in (measured at 256^3: 2 stages 6.1 ms, 3: 6.4, 4: 9.4
@@ -1007,12 +1019,16 @@ extern "C" int db_batches_solve(const db_batch* batches, int32_t nbatch, int32_t
     if (!attr_st) { DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 3>)); DB_SET_SMEM_ATTR((k_batches_solve_flat<NV_, 4>)); \
                     DB_SET_SMEM_ATTR((k_batches_solve_pipe<NV_>)); \
                     DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_mr<NV_, 4>)); \
-                    DB_SET_SMEM_ATTR((k_batches_solve_ws<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_ws<NV_, 3>)); \
+                    DB_SET_SMEM_ATTR((k_batches_solve_ws<NV_, 1>)); DB_SET_SMEM_ATTR((k_batches_solve_ws<NV_, 2>)); DB_SET_SMEM_ATTR((k_batches_solve_ws<NV_, 3>)); \
                     DB_SET_SMEM_ATTR((k_batches_solve_deep<NV_>)); attr_st = 1; } \
     if (ws_env && !deep && rt == 1 && !pipe_env) { \
-        const size_t smem_ws = (size_t)nst * SOLVE_FSTAGE_BYTES + (size_t)2 * nst * sizeof(db_mbar_t); \
-        if (minb_env == 4) DB_LAUNCH((k_batches_solve_ws<NV_, 3>), g, dim3(b.x + 32), smem_ws, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst | (pf_env << 8)); \
-        else DB_LAUNCH((k_batches_solve_ws<NV_, 2>), g, dim3(b.x + 32), smem_ws, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst | (pf_env << 8)); } \
+        int nst_ws = (nst * 1 + cps_env - 1) / cps_env; if (nst_ws < 3) nst_ws = 3; \
+        if (st_env >= 2 && st_env <= 24) nst_ws = st_env; \
+        const size_t smem_ws = (size_t)nst_ws * cps_env * SOLVE_FSTAGE_BYTES + (size_t)2 * nst_ws * sizeof(db_mbar_t); \
+        const int code = nst_ws | (pf_env << 8) | (cps_env << 16); \
+        if (minb_env == 4) DB_LAUNCH((k_batches_solve_ws<NV_, 3>), g, dim3(b.x + 32), smem_ws, stream, batches, nbatch, lu_slot, x_slot, *rhs, code); \
+        else if (minb_env == 1) DB_LAUNCH((k_batches_solve_ws<NV_, 1>), g, dim3(b.x + 32), smem_ws, stream, batches, nbatch, lu_slot, x_slot, *rhs, code); \
+        else DB_LAUNCH((k_batches_solve_ws<NV_, 2>), g, dim3(b.x + 32), smem_ws, stream, batches, nbatch, lu_slot, x_slot, *rhs, code); } \
     else if (deep) DB_LAUNCH((k_batches_solve_deep<NV_>), g_deep, b_deep, smem_deep, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst_deep | (pf_env << 8)); \
     else if (rt == 4 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 4>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \
     else if (rt == 2 && !pipe_env) DB_LAUNCH((k_batches_solve_mr<NV_, 2>), g, bmr, smem, stream, batches, nbatch, lu_slot, x_slot, *rhs, nst); \

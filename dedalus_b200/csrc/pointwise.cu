@@ -6,6 +6,8 @@
 // tile of all inputs in shared memory (every input element read from HBM exactly once, coalesced), evaluates
 // all outputs from it and writes each output once.
 #include "db_common.cuh"
+#include <cstdlib>
+#include <cstdint>
 #include <cstdint>
 
 #define PW_TILE 256
@@ -294,10 +296,113 @@ k_mmt(const double* __restrict__ mat, int m, int n, const double* __restrict__ i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same contraction on the FP64 tensor cores (DMMA.8x8x4 via mma.sync.m8n8k4.f64: tcgen05 has no FP64 path, so this is the
+// tensor pipe for double precision on sm_100a).  CTA tile 64 (rows of mat) x 64 (inner), 4 warps of 32 x 32 = 4 x 4 DMMA
+// tiles each (32 accumulator registers per thread); k in blocks of 16, double-buffered with 16-byte cp.async (LDGSTS,
+// zero-filled outside the matrix), shared-memory rows padded (+4 doubles) so that both fragment loads are conflict-free:
+//   A fragment: lane t holds mat[m0 + t/4][k + t%4]       -> As[row][k], row stride 20 doubles
+//   B fragment: lane t holds in[k + t%4][r0 + t/4]        -> Bs[k][col], row stride 68 doubles
+//   C fragment: lane t holds out[m0 + t/4][r0 + 2 (t%4) + {0, 1}]
+// Requirements of this path: n and inner even, 16-byte aligned pointers (else the FMA-pipe kernel above runs).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef DB_EMU
+#define DM_BM 64
+#define DM_BN 64
+#define DM_BK 16
+#define DM_AS (DM_BK + 4)
+#define DM_BS (DM_BN + 4)
+__device__ __forceinline__ void db_cp_async16_zfill(void* dst, const void* src, bool valid)
+{
+    const unsigned sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(sz) : "memory");
+}
+__global__ void __launch_bounds__(128)
+k_mmt_dmma(const double* __restrict__ mat, int m, int n, const double* __restrict__ in, double* __restrict__ out, int64_t inner)
+{
+    __shared__ __align__(16) double As[2][DM_BM * DM_AS];
+    __shared__ __align__(16) double Bs[2][DM_BK * DM_BS];
+    const int64_t o = blockIdx.z;
+    const int i0 = blockIdx.y * DM_BM;
+    const int64_t r0 = (int64_t)blockIdx.x * DM_BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const double* __restrict__ inb = in + o * (int64_t)n * inner;
+    auto stage = [&](int buf, int k0) {
+        // A: 64 rows x 8 chunks of 2 doubles;  B: 16 rows x 32 chunks
+#pragma unroll
+        for (int e = tid; e < DM_BM * (DM_BK / 2); e += 128) {
+            const int row = e >> 3, c = e & 7;
+            const int gi = i0 + row, gk = k0 + 2 * c;
+            const bool ok = gi < m && gk < n;
+            db_cp_async16_zfill(&As[buf][row * DM_AS + 2 * c], ok ? mat + (int64_t)gi * n + gk : mat, ok);
+        }
+#pragma unroll
+        for (int e = tid; e < DM_BK * (DM_BN / 2); e += 128) {
+            const int kk = e >> 5, c = e & 31;
+            const int gk = k0 + kk; const int64_t gr = r0 + 2 * c;
+            const bool ok = gk < n && gr < inner;
+            db_cp_async16_zfill(&Bs[buf][kk * DM_BS + 2 * c], ok ? inb + (int64_t)gk * inner + gr : inb, ok);
+        }
+        db_cp_commit();
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+    const int nk = (n + DM_BK - 1) / DM_BK;
+    stage(0, 0);
+    for (int kb = 0; kb < nk; ++kb) {
+        const int buf = kb & 1;
+        if (kb + 1 < nk) { stage(buf ^ 1, (kb + 1) * DM_BK); db_cp_wait<1>(); } else db_cp_wait<0>();
+        __syncthreads();
+        const double* __restrict__ A = As[buf] + (wm + (lane >> 2)) * DM_AS + (lane & 3);
+        const double* __restrict__ B = Bs[buf] + (lane & 3) * DM_BS + wn + (lane >> 2);
+#pragma unroll
+        for (int k4 = 0; k4 < DM_BK; k4 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = A[a * 8 * DM_AS + k4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = B[k4 * DM_BS + b * 8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[a][b][0]), "+d"(acc[a][b][1]) : "d"(af[a]), "d"(bf[b]));
+        }
+        __syncthreads();
+    }
+    double* outb = out + o * (int64_t)m * inner;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int gi = i0 + wm + a * 8 + (lane >> 2);
+        if (gi >= m) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t gr = r0 + wn + b * 8 + 2 * (lane & 3);
+            if (gr < inner) *reinterpret_cast<double2*>(outb + (int64_t)gi * inner + gr) = make_double2(acc[a][b][0], acc[a][b][1]);
+        }
+    }
+}
+#endif
+
 extern "C" int db_mmt_apply(const double* mat, int32_t m, int32_t n, const double* in, double* out, int64_t outer, int64_t inner, void* stream)
 {
     if (outer <= 0 || inner <= 0 || m <= 0 || n <= 0) return 0;
     if (outer > 65535) { db_set_error("mmt_apply: outer too large (%lld)", (long long)outer); return 1; }
+#ifndef DB_EMU
+    static int dmma = -1;
+    if (dmma < 0) { const char* e = getenv("DB_MMT_DMMA"); dmma = (e && atoi(e) == 0) ? 0 : 1; }
+    const bool aligned = (((uintptr_t)mat | (uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    if (dmma && aligned && n % 2 == 0 && inner % 2 == 0) {
+        dim3 grid((unsigned)((inner + DM_BN - 1) / DM_BN), (unsigned)((m + DM_BM - 1) / DM_BM), (unsigned)outer);
+        DB_LAUNCH(k_mmt_dmma, grid, dim3(128), 0, stream, mat, m, n, in, out, inner);
+        return db_check_launch("mmt_apply(dmma)");
+    }
+#endif
     dim3 grid((unsigned)((inner + MM_BN - 1) / MM_BN), (unsigned)((m + MM_BM - 1) / MM_BM), (unsigned)outer);
     DB_LAUNCH(k_mmt, grid, dim3(256), (MM_BK * MM_BM + MM_BK * MM_BN) * sizeof(double), stream, mat, m, n, in, out, outer, inner);
     return db_check_launch("mmt_apply");

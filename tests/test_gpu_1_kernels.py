@@ -93,8 +93,10 @@ def test_transpose_pack_unpack_is_the_global_permutation(P, B, n1, n2, n3):
         assert np.array_equal(out.cpu().numpy(), G[:, r * n1b:(r + 1) * n1b])
 
 
-@pytest.mark.parametrize("m,n,outer,inner", [(70, 45, 3, 67), (384, 255, 2, 130), (5, 3, 1, 1)])
+@pytest.mark.parametrize("m,n,outer,inner", [(70, 45, 3, 67), (384, 255, 2, 130), (5, 3, 1, 1),
+                                             (70, 46, 3, 66), (384, 256, 2, 130), (255, 384, 2, 64), (8, 4, 1, 2), (200, 128, 1, 1000)])
 def test_dense_matrix_transform_matches_numpy(m, n, outer, inner):
+    """Odd n / inner: FMA-pipe tiles (k_mmt); even: FP64 tensor-core tiles (k_mmt_dmma, DMMA.8x8x4), including partial tiles."""
     import torch
     from dedalus_b200.lib import get_lib, current_stream
     rng = np.random.default_rng(9)
