@@ -409,6 +409,70 @@ extern "C" int db_mmt_apply(const double* mat, int32_t m, int32_t n, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Ragged batch of small dense matrix-vector products (T5): the spin-weighted spherical harmonic colatitude transform
+// (reference core/transforms.py:1251-1340) applies a DIFFERENT matrix per azimuthal wavenumber m to the few lines that carry
+// that m (cos / -sin pair x tensor components), with the coefficient lines addressed through the folded triangular packing
+// (forward or reversed l order).  On the 2-D sphere the work is streaming the matrices (~100 MB per spin weight at Lmax = 254)
+// against a handful of right-hand sides, i.e. HBM-bound, not tensor-bound: one warp per output row, lanes along the
+// contraction index (coalesced matrix reads), up to RG_C right-hand sides accumulated per pass, shuffle reduction.
+//   entry e:  out[o, out_i0 + i, out_row0 + k * out_step, r] = sum_j mat_e[k][j] * in[o, in_i0 + i, in_row0 + j * in_step, r]
+//             for k < nrow, j < ncol, i < nm, all o < N0, r < N3;  zero != 0: the output lines are set to zero instead.
+// ---------------------------------------------------------------------------------------------------------
+#define RG_C 8
+#define RG_ROWS 8
+__global__ void __launch_bounds__(32 * RG_ROWS)
+k_ragged_matvec(const double* __restrict__ mats, const db_ragged_entry* __restrict__ entries, const double* __restrict__ in,
+                double* __restrict__ out, int64_t N0, int N1i, int N2i, int N1o, int N2o, int64_t N3)
+{
+    const db_ragged_entry E = entries[blockIdx.x];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ncols_total = N0 * E.nm * N3;                  // right-hand sides of this entry
+    const double* __restrict__ mat = mats + E.mat_off;
+    for (int k = blockIdx.y * RG_ROWS + w; k < E.nrow; k += gridDim.y * RG_ROWS) {
+        for (int64_t c0 = 0; c0 < ncols_total; c0 += RG_C) {
+            double acc[RG_C];
+            int64_t ibase[RG_C], obase[RG_C];
+#pragma unroll
+            for (int cc = 0; cc < RG_C; ++cc) {
+                acc[cc] = 0.0;
+                const int64_t c = c0 + cc < ncols_total ? c0 + cc : ncols_total - 1;
+                const int64_t r = c % N3; const int64_t t = c / N3; const int i = (int)(t % E.nm); const int64_t o = t / E.nm;
+                ibase[cc] = ((o * N1i + E.in_i0 + i) * N2i + E.in_row0) * N3 + r;
+                obase[cc] = ((o * N1o + E.out_i0 + i) * N2o + E.out_row0 + (int64_t)k * E.out_step) * N3 + r;
+            }
+            if (!E.zero) {
+                for (int j = lane; j < E.ncol; j += 32) {
+                    const double mv = mat[(int64_t)k * E.ncol + j];
+                    const int64_t joff = (int64_t)j * E.in_step * N3;
+#pragma unroll
+                    for (int cc = 0; cc < RG_C; ++cc) acc[cc] = fma(mv, in[ibase[cc] + joff], acc[cc]);
+                }
+#pragma unroll
+                for (int cc = 0; cc < RG_C; ++cc)
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) acc[cc] += __shfl_down_sync(0xffffffffu, acc[cc], off);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int cc = 0; cc < RG_C; ++cc)
+                    if (c0 + cc < ncols_total) out[obase[cc]] = acc[cc];
+            }
+        }
+    }
+}
+
+extern "C" int db_ragged_matvec(const double* mats, const db_ragged_entry* entries, int32_t nentries, int32_t max_nrow,
+                                const double* in, double* out, int64_t N0, int32_t N1i, int32_t N2i, int32_t N1o, int32_t N2o, int64_t N3,
+                                void* stream)
+{
+    if (nentries <= 0 || N0 <= 0 || N3 <= 0 || max_nrow <= 0) return 0;
+    int yb = (max_nrow + RG_ROWS - 1) / RG_ROWS;
+    if (yb > 64) yb = 64;
+    DB_LAUNCH(k_ragged_matvec, dim3((unsigned)nentries, (unsigned)yb), dim3(32 * RG_ROWS), 0, stream, mats, entries, in, out, N0, N1i, N2i, N1o, N2o, N3);
+    return db_check_launch("ragged_matvec");
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Distributed-transpose pack / unpack (X1)
 // forward hop (towards grid space): local A (B, n1loc, n2, n3), n2 split in P blocks of n2blk:
 //   send[p][b][i][j][r] = A[b][i][p*n2blk + j][r]                       (contiguous per destination rank)

@@ -40,6 +40,12 @@ class Batch(C.Structure):
                 ("asm_ptr", vp), ("asm_mono", vp), ("asm_val", vp), ("info", vp)]
 
 
+class RaggedEntry(C.Structure):
+    """include/dedalus_b200.h: db_ragged_entry"""
+    _fields_ = [("mat_off", i64), ("nrow", i32), ("ncol", i32), ("in_i0", i32), ("in_row0", i32), ("in_step", i32),
+                ("out_i0", i32), ("out_row0", i32), ("out_step", i32), ("nm", i32), ("zero", i32)]
+
+
 class SlotComb(C.Structure):
     _fields_ = [("nvec", i32), ("slot", i32 * 16), ("coef", f64 * 16)]
 
@@ -63,6 +69,7 @@ SIGNATURES = {
     "db_cheb_backward_scan": (C.c_int, [PFFT, vp, vp, i64, i32, vp, i32, vp, vp]),
     "db_band_lines": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i32, i32, vp]),
     "db_mmt_apply": (C.c_int, [vp, i32, i32, vp, vp, i64, i64, vp]),
+    "db_ragged_matvec": (C.c_int, [vp, vp, i32, i32, vp, vp, i64, i32, i32, i32, i32, i64, vp]),
     "db_pointwise": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp]),
     "db_pointwise_pairs": (C.c_int, [vp, vp, i64, i32, i32, vp, vp, vp]),
     "db_pencil_gather": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),

@@ -300,6 +300,125 @@ class JacobiMatrixTransform:
         get_lib().call("db_mmt_apply", _dptr(self._mat('b', gdata.device)), self.N, self.M, _dptr(cdata), _dptr(gdata), outer, inner, _stream())
 
 
+class SWSHColatitudeTransform:
+    """Spin-weighted spherical harmonic colatitude transform (reference SWSHColatitudeTransform, core/transforms.py:1251-1340).
+
+    Same constructor contract as the reference plugin -- `cls(Ntheta, Lmax, m_maps, s)` with `m_maps` the tuple of
+    (m, mg_slice, mc_slice, ell_slice) produced by SphereBasis.m_maps (core/basis.py:2940-2970; rows of 8 integers
+    (m, mg0, mg1, mc0, mc1, ell_start, ell_stop or -1, ell_step) are accepted as well) -- and the same
+    `forward(gdata, cdata, axis)` / `backward(cdata, gdata, axis)` on arrays whose axis - 1 carries the azimuthal
+    coefficients and whose `axis` carries colatitude / degree.  The harmonics are built on the host from the unit-normalised
+    Jacobi polynomials (dedalus_b200/jacobi.py):  Y_{l,m,s}(z) = (-1)^max(m,-s) sqrt((1-z)^a (1+z)^b) p_k^(a,b)(z), a = |m+s|,
+    b = |m-s|, k = l - max(|m|,|s|) (reference libraries/dedalus_sphere/sphere.py:43-64), on the Ntheta Gauss-Legendre nodes;
+    all per-m matrices live in one device buffer and one kernel launch (db_ragged_matvec) serves every local m."""
+
+    def __init__(self, Ntheta, Lmax, m_maps, s):
+        self.Ntheta, self.Lmax, self.s = int(Ntheta), int(Lmax), int(s)
+        rows = []
+        for e in m_maps:
+            if len(e) == 4:
+                m, mg, mc, ell = e
+                rows.append((int(m), int(mg.start), int(mg.stop), int(mc.start), int(mc.stop), int(ell.start),
+                             -1 if ell.stop is None else int(ell.stop), -1 if ell.step == -1 else 1))
+            else:
+                rows.append(tuple(int(v) for v in e))
+        self.m_maps = rows
+        self._dev = {}
+
+    @staticmethod
+    def quadrature(Ntheta):
+        from scipy.special import roots_jacobi
+        return roots_jacobi(Ntheta, 0.0, 0.0)
+
+    def matrices(self, m):
+        """(forward (Lmax+1-|m|, Ntheta), backward (Ntheta, Lmax+1-|m|)), zero rows for l < |s| and l >= Ntheta."""
+        Nt, Lmax, s = self.Ntheta, self.Lmax, self.s
+        z, w = self.quadrature(Nt)
+        n = Lmax + 1 - max(abs(m), abs(s))
+        a, b = abs(m + s), abs(m - s)
+        F = np.zeros((Lmax + 1 - abs(m), Nt)); B = np.zeros((Nt, Lmax + 1 - abs(m)))
+        if n > 0:
+            env = np.sqrt((1 - z) ** a * (1 + z) ** b) * ((-1.0) ** max(m, -s))
+            Y = jacobi.polynomials(n, a, b, z) * env[None, :]
+            Lmin = max(abs(m), abs(s))
+            F[Lmin - abs(m):, :] = Y * w[None, :]
+            B[:, Lmin - abs(m):] = Y.T
+        F[max(Nt - abs(m), 0):, :] = 0
+        B[:, max(Nt - abs(m), 0):] = 0
+        return F, B
+
+    def _program(self, device, nell):
+        """Device buffers: concatenated matrices + the two entry tables (forward / backward)."""
+        key = (str(device), nell)
+        if key in self._dev:
+            return self._dev[key]
+        from .lib import RaggedEntry
+        torch = _torch()
+        mats, off = [], 0
+        fwd = (RaggedEntry * len(self.m_maps))(); bwd = (RaggedEntry * len(self.m_maps))()
+        cache = {}
+        maxf = maxb = 1
+        for q, (m, mg0, mg1, mc0, mc1, e0, e1, estep) in enumerate(self.m_maps):
+            nm = mg1 - mg0
+            ells = np.arange(nell)[slice(e0, None if e1 < 0 else e1, estep)]
+            if abs(m) > self.Lmax:
+                # nothing to do forward; zeros written backward (they feed the inverse azimuthal transform)
+                f, b = fwd[q], bwd[q]
+                f.nrow = 0; f.ncol = 0; f.nm = nm; f.zero = 0
+                b.mat_off = 0; b.nrow = self.Ntheta; b.ncol = 0; b.in_i0 = mc0; b.in_row0 = 0; b.in_step = 1
+                b.out_i0 = mg0; b.out_row0 = 0; b.out_step = 1; b.nm = nm; b.zero = 1
+                maxb = max(maxb, self.Ntheta)
+                continue
+            if m not in cache:
+                F, B = self.matrices(m)
+                cache[m] = (off, off + F.size)
+                mats += [F.ravel(), B.ravel()]
+                off += F.size + B.size
+            nl = self.Lmax + 1 - abs(m)
+            if len(ells) != nl:
+                raise ValueError("m_maps degree slice does not have Lmax + 1 - |m| entries")
+            f, b = fwd[q], bwd[q]
+            f.mat_off = cache[m][0]; f.nrow = nl; f.ncol = self.Ntheta
+            f.in_i0 = mg0; f.in_row0 = 0; f.in_step = 1
+            f.out_i0 = mc0; f.out_row0 = int(ells[0]); f.out_step = int(estep); f.nm = nm; f.zero = 0
+            b.mat_off = cache[m][1]; b.nrow = self.Ntheta; b.ncol = nl
+            b.in_i0 = mc0; b.in_row0 = int(ells[0]); b.in_step = int(estep)
+            b.out_i0 = mg0; b.out_row0 = 0; b.out_step = 1; b.nm = nm; b.zero = 0
+            maxf = max(maxf, nl); maxb = max(maxb, self.Ntheta)
+        mats_t = torch.from_numpy(np.concatenate(mats) if mats else np.zeros(1)).to(device)
+        tab = lambda arr: torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
+        prog = dict(mats=mats_t, fwd=tab(fwd), bwd=tab(bwd), n=len(self.m_maps), maxf=maxf, maxb=maxb)
+        self._dev[key] = prog
+        return prog
+
+    @staticmethod
+    def _reduced(t, axis):
+        """(N0, N1, N2, N3) view with N1 = axis - 1, N2 = axis (reference reduced_view_4, tools/array.py)."""
+        shp = t.shape
+        n0 = int(np.prod(shp[:axis - 1], dtype=np.int64)); n3 = int(np.prod(shp[axis + 1:], dtype=np.int64))
+        return n0, int(shp[axis - 1]), int(shp[axis]), n3
+
+    def forward(self, gdata, cdata, axis):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        n0, n1g, n2g, n3 = self._reduced(gdata, axis)
+        _, n1c, n2c, _ = self._reduced(cdata, axis)
+        if n2g != self.Ntheta:
+            raise ValueError("Array shapes do not match the transform plan.")
+        p = self._program(gdata.device, n2c)
+        get_lib().call("db_ragged_matvec", _dptr(p['mats']), _dptr(p['fwd']), p['n'], p['maxf'], _dptr(gdata), _dptr(cdata),
+                       n0, n1g, n2g, n1c, n2c, n3, _stream())
+
+    def backward(self, cdata, gdata, axis):
+        _check(gdata, "gdata"); _check(cdata, "cdata")
+        n0, n1g, n2g, n3 = self._reduced(gdata, axis)
+        _, n1c, n2c, _ = self._reduced(cdata, axis)
+        if n2g != self.Ntheta:
+            raise ValueError("Array shapes do not match the transform plan.")
+        p = self._program(gdata.device, n2c)
+        get_lib().call("db_ragged_matvec", _dptr(p['mats']), _dptr(p['bwd']), p['n'], p['maxb'], _dptr(cdata), _dptr(gdata),
+                       n0, n1c, n2c, n1g, n2g, n3, _stream())
+
+
 def transform_plan(basis, scale):
     """Plan for one basis at one scale (reference basis.transform_plan, basis.py:506-509, 915-922)."""
     N = basis.grid_size(scale)

@@ -106,6 +106,25 @@ int db_band_lines(const double* in, double* out, int64_t lines, int32_t n,
  * Replaces SeparableMatrixTransform -> apply_dense (core/transforms.py:54-75, tools/array.py:104-129). */
 int db_mmt_apply(const double* mat, int32_t m, int32_t n, const double* in, double* out, int64_t outer, int64_t inner, void* stream);
 
+/* Ragged batch of dense matrix-vector products: the spin-weighted spherical harmonic colatitude transform.
+ * Replaces SWSHColatitudeTransform.forward_reduced / backward_reduced (core/transforms.py:1263-1290): for every local
+ * azimuthal wavenumber m (one entry; m_maps of core/basis.py:2940-2970) the matrix of that m (`mats + mat_off`, row-major
+ * nrow x ncol; built by the host as core/transforms.py:1296-1340) is applied along axis 2 of the reduced 4-D views
+ *   in (N0, N1i, N2i, N3),  out (N0, N1o, N2o, N3)
+ * to the nm lines in_i0 .. in_i0 + nm of axis 1 (cos / -sin pair), reading input row in_row0 + j * in_step and writing
+ * output row out_row0 + k * out_step (steps of -1 address the folded, reversed-l halves of the triangular packing);
+ * zero != 0: the nm output lines (rows out_row0 + k * out_step, k < nrow) are set to zero (|m| > Lmax on the way back). */
+typedef struct {
+    int64_t mat_off;
+    int32_t nrow, ncol;
+    int32_t in_i0, in_row0, in_step;
+    int32_t out_i0, out_row0, out_step;
+    int32_t nm, zero;
+} db_ragged_entry;
+int db_ragged_matvec(const double* mats, const db_ragged_entry* entries, int32_t nentries, int32_t max_nrow,
+                     const double* in, double* out, int64_t N0, int32_t N1i, int32_t N2i, int32_t N1o, int32_t N2o, int64_t N3,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Grid-space products (P1): every output is a sum of coef * product of inputs, evaluated pointwise.
  * Replaces DotProduct.operate / MultiplyFields.operate / AddFields.operate chains

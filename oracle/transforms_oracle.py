@@ -207,3 +207,67 @@ def cheb_backward_fft(c, N, axis, a=-0.5, b=-0.5):
     temp[axslice(axis, 0, 1)] = data[axslice(axis, 0, 1)] / np.sqrt(np.pi)
     temp[axslice(axis, 1, Kmax + 1)] = data[axslice(axis, 1, Kmax + 1)] * (0.5 / np.sqrt(np.pi / 2))
     return scipy.fft.dct(temp, type=3, axis=axis)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Spin-weighted spherical harmonic colatitude transform (reference core/transforms.py:1251-1340).
+# Harmonics restated from libraries/dedalus_sphere/sphere.py:43-64 + jacobi.py:28-80, 147-172:
+#   Y_{l,m,s}(z) = (-1)^max(m,-s) sqrt((1-z)^a (1+z)^b) p_k^(a,b)(z),  a = |m+s|, b = |m-s|, k = l - max(|m|,|s|),
+# p_k the unit-weight-normalised Jacobi polynomials; Gauss-Legendre quadrature in z = cos(theta) with Ntheta nodes.
+# ---------------------------------------------------------------------------------------------------------
+def swsh_quadrature(Ntheta):
+    z, w = roots_jacobi(Ntheta, 0.0, 0.0)
+    return z, w
+
+
+def swsh_harmonics(Lmax, m, s, z):
+    n = Lmax + 1 - max(abs(m), abs(s))
+    a, b = abs(m + s), abs(m - s)
+    if n <= 0:
+        return np.zeros((0, len(z)))
+    env = np.sqrt((1 - z) ** a * (1 + z) ** b) * ((-1.0) ** max(m, -s))
+    return jacobi_polynomials(n, a, b, z) * env[None, :]
+
+
+@functools.lru_cache(maxsize=None)
+def swsh_matrices(Ntheta, Lmax, m, s):
+    """(forward (Lmax+1-|m|, Ntheta), backward (Ntheta, Lmax+1-|m|)) padded with zero rows for l < |s| and zeroed for
+    l >= Ntheta (core/transforms.py:1291-1340)."""
+    z, w = swsh_quadrature(Ntheta)
+    Y = swsh_harmonics(Lmax, m, s, z)
+    Lmin = max(abs(m), abs(s))
+    F = np.zeros((Lmax + 1 - abs(m), Ntheta)); B = np.zeros((Ntheta, Lmax + 1 - abs(m)))
+    F[Lmin - abs(m):, :] = Y * w[None, :]
+    B[:, Lmin - abs(m):] = Y.T
+    F[max(Ntheta - abs(m), 0):, :] = 0
+    B[:, max(Ntheta - abs(m), 0):] = 0
+    return F, B
+
+
+def _ell_index(row, nell):
+    start, stop, step = int(row[5]), int(row[6]), int(row[7])
+    return np.arange(nell)[slice(start, None if stop < 0 else stop, step)]
+
+
+def swsh_forward(g, c, m_maps, Ntheta, Lmax, s):
+    """g: (..., Nphi_cg, Ntheta) -> c: (..., Nphi_c, Nell) in place; m_maps rows (m, mg0, mg1, mc0, mc1, ell start/stop/step)."""
+    for row in np.asarray(m_maps):
+        m = int(row[0])
+        if abs(m) > Lmax:
+            continue
+        F, _ = swsh_matrices(Ntheta, Lmax, m, s)
+        ell = _ell_index(row, c.shape[-1])
+        c[..., row[3]:row[4], ell] = np.einsum('kt,...it->...ik', F, g[..., row[1]:row[2], :])
+    return c
+
+
+def swsh_backward(c, g, m_maps, Ntheta, Lmax, s):
+    for row in np.asarray(m_maps):
+        m = int(row[0])
+        if abs(m) > Lmax:
+            g[..., row[1]:row[2], :] = 0
+            continue
+        _, B = swsh_matrices(Ntheta, Lmax, m, s)
+        ell = _ell_index(row, c.shape[-1])
+        g[..., row[1]:row[2], :] = np.einsum('tk,...ik->...it', B, c[..., row[3]:row[4], ell])
+    return g

@@ -298,3 +298,49 @@ def gen_cfl():
 
 if __name__ == "__main__" and "cfl" in sys.argv[1:]:
     gen_cfl()
+
+
+def gen_swsh():
+    """SWSH colatitude transform (reference core/transforms.py:1251-1340, matrices from libraries/dedalus_sphere/sphere.py:43-64
+    x Gauss weights): the reference's own plan objects on its own m_maps (real dtype: cos / -sin pairs per m, folded
+    triangular coefficient packing, core/basis.py:2800-2809, 2940-2970), forward and backward, spin weights -2 .. 2, with and
+    without 3/2 dealiasing.  Stored: the m_maps as integer rows (m, mg0, mg1, mc0, mc1, ell_start, ell_stop_or_-1, ell_step),
+    inputs, outputs and two of the matrices."""
+    rng = np.random.default_rng(77)
+    out = {}
+    for tag, (Nphi, Ntheta, dealias) in dict(a=(16, 12, 1), b=(32, 16, 1.5)).items():
+        coords = d3.S2Coordinates('phi', 'theta')
+        dist = d3.Distributor(coords, dtype=np.float64)
+        basis = d3.SphereBasis(coords, (Nphi, Ntheta), radius=1, dealias=(dealias, dealias), dtype=np.float64)
+        f = dist.Field(bases=basis)
+        f.preset_scales(dealias)
+        gshape = tuple(int(n) for n in basis.grid_shape((dealias, dealias)))
+        mm = basis.m_maps(dist)
+        rows = []
+        for m, mg, mc, ell in mm:
+            rows.append((int(m), int(mg.start), int(mg.stop), int(mc.start), int(mc.stop), int(ell.start),
+                         -1 if ell.stop is None else int(ell.stop), -1 if ell.step == -1 else 1))
+        cshape = tuple(int(n) for n in f['c'].shape)
+        out[f"{tag}_m_maps"] = np.array(rows, dtype=np.int64)
+        out[f"{tag}_meta"] = np.array([Nphi, Ntheta, basis.Lmax, gshape[0], gshape[1], cshape[0], cshape[1]], dtype=np.int64)
+        for s in (0, 1, -1, 2, -2):
+            plan = basis.transform_plan(dist, gshape[1], s)
+            # arrays as the reference passes them for a rank-|s| component: (1, Nphi_cg, Ntheta_g) <-> (1, Nphi_c, Nell)
+            g = rng.standard_normal((2, gshape[0], gshape[1]))
+            c = np.zeros((2,) + cshape)
+            plan.forward(g.copy(), c, 2)
+            cc = rng.standard_normal((2,) + cshape)
+            gg = np.full((2, gshape[0], gshape[1]), np.nan)
+            plan.backward(cc.copy(), gg, 2)
+            out[f"{tag}_s{s}_gin"] = g; out[f"{tag}_s{s}_cout"] = c
+            out[f"{tag}_s{s}_cin"] = cc; out[f"{tag}_s{s}_gout"] = gg
+            if s in (0, 2):
+                for m in (0, 3):
+                    out[f"{tag}_s{s}_m{m}_fwdmat"] = np.array(plan._forward_SWSH_matrices[m])
+                    out[f"{tag}_s{s}_m{m}_bwdmat"] = np.array(plan._backward_SWSH_matrices[m])
+    np.savez_compressed(HERE / "swsh.npz", **out)
+    print({k: v.shape for k, v in out.items() if k.endswith("m_maps") or k.endswith("meta")})
+
+
+if __name__ == "__main__" and "swsh" in sys.argv[1:]:
+    gen_swsh()

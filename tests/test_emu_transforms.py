@@ -324,3 +324,32 @@ def test_register_kernels_match_reference_at_benchmark_lengths(golden):
                 lib.call("db_cheb_forward", plan.ref(), E.ptr(np.ascontiguousarray(gin)), E.ptr(out), lines, M, 1, None, 0, None)
             assert np.allclose(out, cout, rtol=1e-11, atol=1e-11 * np.abs(cout).max())
             assert lib.rfft_regs_launches() == served + 2
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("s", [0, 1, -1, 2, -2])
+def test_swsh_colatitude_transform_matches_reference(golden, tag, s):
+    """T5: SWSHColatitudeTransform plugin (ragged per-m matrices, folded triangular packing) vs the UNMODIFIED reference's own
+    plan on its own m_maps (tests/golden/swsh.npz), forward and backward, and the per-m matrices vs the reference's."""
+    import torch
+    from dedalus_b200.transforms import SWSHColatitudeTransform
+    E.install()
+    try:
+        g = golden("swsh.npz")
+        Nphi, Ntheta, Lmax, Gp, Gt, Cp, Ce = (int(v) for v in g[tag + "_meta"])
+        plan = SWSHColatitudeTransform(Gt, Lmax, [tuple(r) for r in g[tag + "_m_maps"]], s)
+        if s in (0, 2):
+            for m in (0, 3):
+                F, B = plan.matrices(m)
+                assert np.allclose(F, g[f"{tag}_s{s}_m{m}_fwdmat"], rtol=1e-12, atol=1e-13)
+                assert np.allclose(B, g[f"{tag}_s{s}_m{m}_bwdmat"], rtol=1e-12, atol=1e-13)
+        gin = torch.from_numpy(np.ascontiguousarray(g[f"{tag}_s{s}_gin"]))
+        c = torch.zeros(g[f"{tag}_s{s}_cout"].shape, dtype=torch.float64)
+        plan.forward(gin, c, 2)
+        assert np.allclose(c.numpy(), g[f"{tag}_s{s}_cout"], rtol=1e-12, atol=1e-13)
+        cin = torch.from_numpy(np.ascontiguousarray(g[f"{tag}_s{s}_cin"]))
+        gg = torch.full(g[f"{tag}_s{s}_gout"].shape, float('nan'), dtype=torch.float64)
+        plan.backward(cin, gg, 2)
+        assert np.allclose(gg.numpy(), g[f"{tag}_s{s}_gout"], rtol=1e-12, atol=1e-12, equal_nan=True)
+    finally:
+        E.uninstall()

@@ -229,3 +229,45 @@ def test_register_kernels_match_reference_at_benchmark_lengths(golden):
             plan.forward(_t(g[key + "_gin"]), out, 1)
             assert np.allclose(out.cpu().numpy(), cout, rtol=1e-11, atol=1e-11 * np.abs(cout).max())
             assert get_lib().rfft_regs_launches() == served + 2
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("s", [0, 1, -2])
+def test_swsh_colatitude_transform_matches_reference(golden, tag, s):
+    """T5 on the GPU: SWSHColatitudeTransform plugin vs the UNMODIFIED reference's plan on its own m_maps (swsh.npz)."""
+    import torch
+    from dedalus_b200.transforms import SWSHColatitudeTransform
+    g = golden("swsh.npz")
+    Nphi, Ntheta, Lmax, Gp, Gt, Cp, Ce = (int(v) for v in g[tag + "_meta"])
+    plan = SWSHColatitudeTransform(Gt, Lmax, [tuple(r) for r in g[tag + "_m_maps"]], s)
+    c = torch.zeros(g[f"{tag}_s{s}_cout"].shape, dtype=torch.float64, device='cuda')
+    plan.forward(_t(g[f"{tag}_s{s}_gin"]), c, 2)
+    assert np.allclose(c.cpu().numpy(), g[f"{tag}_s{s}_cout"], rtol=1e-12, atol=1e-13)
+    gg = torch.full(g[f"{tag}_s{s}_gout"].shape, float('nan'), dtype=torch.float64, device='cuda')
+    plan.backward(_t(g[f"{tag}_s{s}_cin"]), gg, 2)
+    assert np.allclose(gg.cpu().numpy(), g[f"{tag}_s{s}_gout"], rtol=1e-12, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("s", [0, 2])
+def test_swsh_round_trip_at_config4_size(s):
+    """BASELINE config 4's resolution (Nphi = 512, Ntheta = 256 -> Lmax = 254, 3/2 dealiasing: 384 colatitude points): backward
+    then forward is the identity on band-limited coefficients (l >= max(|m|, |s|)), and matches the CPU oracle for one m."""
+    import torch
+    from dedalus_b200.transforms import SWSHColatitudeTransform
+    from oracle import transforms_oracle as T
+    Lmax, Nt = 254, 384
+    maps = [(m, 2 * m, 2 * m + 2, 2 * m, 2 * m + 2, m, Lmax + 1, 1) for m in range(Lmax + 1)]
+    plan = SWSHColatitudeTransform(Nt, Lmax, maps, s)
+    rng = np.random.default_rng(s)
+    c = rng.standard_normal((3, 2 * (Lmax + 1), Lmax + 1))
+    for m in range(Lmax + 1):
+        c[:, 2 * m:2 * m + 2, :max(m, abs(s))] = 0
+    g = torch.full((3, 2 * (Lmax + 1), Nt), float('nan'), dtype=torch.float64, device='cuda')
+    plan.backward(_t(c), g, 2)
+    back = torch.zeros(c.shape, dtype=torch.float64, device='cuda')
+    plan.forward(g, back, 2)
+    assert np.allclose(back.cpu().numpy(), c, rtol=1e-10, atol=1e-11)
+    m = 37
+    _, B = T.swsh_matrices(Nt, Lmax, m, s)
+    ref = np.einsum('tk,oik->oit', B, c[:, 2 * m:2 * m + 2, m:])
+    assert np.allclose(g.cpu().numpy()[:, 2 * m:2 * m + 2], ref, rtol=1e-11, atol=1e-12)

@@ -75,3 +75,22 @@ def test_kdv(golden, prefix):
     orc = kdv_oracle.KdVOracle(int(g[prefix + "N"]))
     u = orc.run(g[prefix + "u0_c"], int(g[prefix + "steps"]), float(g[prefix + "dt"]), scheme=str(g[prefix + "scheme"]))
     assert np.allclose(u, g[prefix + "u_c"], rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_swsh_oracle_matches_reference(golden, tag):
+    """oracle/transforms_oracle.py swsh_* pinned to the reference's SWSHColatitudeTransform (tests/golden/swsh.npz)."""
+    from oracle import transforms_oracle as T
+    g = golden("swsh.npz")
+    Nphi, Ntheta, Lmax, Gp, Gt, Cp, Ce = (int(v) for v in g[tag + "_meta"])
+    mm = g[tag + "_m_maps"]
+    for s in (0, 1, -1, 2, -2):
+        c = np.zeros_like(g[f"{tag}_s{s}_cout"]); T.swsh_forward(g[f"{tag}_s{s}_gin"], c, mm, Gt, Lmax, s)
+        assert np.allclose(c, g[f"{tag}_s{s}_cout"], rtol=1e-12, atol=1e-13)
+        gg = np.full_like(g[f"{tag}_s{s}_gout"], np.nan); T.swsh_backward(g[f"{tag}_s{s}_cin"], gg, mm, Gt, Lmax, s)
+        assert np.allclose(gg, g[f"{tag}_s{s}_gout"], rtol=1e-12, atol=1e-12, equal_nan=True)
+    for s in (0, 2):
+        for m in (0, 3):
+            F, B = T.swsh_matrices(Gt, Lmax, m, s)
+            assert np.allclose(F, g[f"{tag}_s{s}_m{m}_fwdmat"], rtol=1e-12, atol=1e-13)
+            assert np.allclose(B, g[f"{tag}_s{s}_m{m}_bwdmat"], rtol=1e-12, atol=1e-13)
