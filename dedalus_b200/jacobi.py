@@ -84,8 +84,12 @@ def differentiation_matrix(N, a, b):
     return sparse.diags([s[1:]], [1], shape=(N, N), format='csr')
 
 
-def polynomials(N, a, b, z):
-    """Unit-normalised p_n^(a,b)(z), n < N, as an (N, len(z)) float64 array (long-double recurrence)."""
+def polynomials(N, a, b, z, half_log_weight=False):
+    """Unit-normalised p_n^(a,b)(z), n < N, as an (N, len(z)) float64 array (long-double recurrence).
+    half_log_weight=True multiplies by sqrt((1-z)^a (1+z)^b), applied in log space inside the long-double scaling: for large
+    a, b (spherical harmonics of high order) the envelope underflows and the polynomial values overflow double range
+    separately, while their product is O(1) (the reference starts its recurrence from the envelope for the same reason,
+    libraries/dedalus_sphere/sphere.py:59-64)."""
     z = np.atleast_1d(np.asarray(z, dtype=LD))
     P = np.zeros((max(N, 2), z.size), dtype=LD)
     P[0] = 1
@@ -98,7 +102,13 @@ def polynomials(N, a, b, z):
         a4 = 2 * (n + a) * (n + b) * (c + 2)
         P[n + 1] = ((a2 + a3 * z) * P[n] - a4 * P[n - 1]) / a1
     ln = log_norm(np.arange(max(N, 2)), a, b)
-    P = P * np.exp(-0.5 * ln).astype(LD)[:, None]
+    if half_log_weight:
+        zl = z.astype(LD)
+        with np.errstate(divide='ignore'):
+            lw = 0.5 * (a * np.log1p(-zl) + b * np.log1p(zl))
+        P = P * np.exp(-0.5 * ln.astype(LD)[:, None] + lw[None, :])
+    else:
+        P = P * np.exp(-0.5 * ln).astype(LD)[:, None]
     return np.asarray(P[:N], dtype=np.float64)
 
 

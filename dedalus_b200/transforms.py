@@ -338,8 +338,7 @@ class SWSHColatitudeTransform:
         a, b = abs(m + s), abs(m - s)
         F = np.zeros((Lmax + 1 - abs(m), Nt)); B = np.zeros((Nt, Lmax + 1 - abs(m)))
         if n > 0:
-            env = np.sqrt((1 - z) ** a * (1 + z) ** b) * ((-1.0) ** max(m, -s))
-            Y = jacobi.polynomials(n, a, b, z) * env[None, :]
+            Y = jacobi.polynomials(n, a, b, z, half_log_weight=True) * ((-1.0) ** max(m, -s))
             Lmin = max(abs(m), abs(s))
             F[Lmin - abs(m):, :] = Y * w[None, :]
             B[:, Lmin - abs(m):] = Y.T

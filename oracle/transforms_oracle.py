@@ -225,8 +225,15 @@ def swsh_harmonics(Lmax, m, s, z):
     a, b = abs(m + s), abs(m - s)
     if n <= 0:
         return np.zeros((0, len(z)))
-    env = np.sqrt((1 - z) ** a * (1 + z) ** b) * ((-1.0) ** max(m, -s))
-    return jacobi_polynomials(n, a, b, z) * env[None, :]
+    # envelope and normalisation combined in log space (long double): separately they under- / overflow for large m
+    zl = np.asarray(z, dtype=np.longdouble)
+    k = np.arange(n)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ln = log_norm(k, a, b)
+    ln[0] = (a + b + 1) * np.log(2.0) + gammaln(a + 1) + gammaln(b + 1) - gammaln(a + b + 2)
+    P = np.stack([eval_jacobi(int(q), a, b, z) for q in k], axis=0).astype(np.longdouble)
+    scale = np.exp(-0.5 * ln.astype(np.longdouble)[:, None] + 0.5 * (a * np.log1p(-zl) + b * np.log1p(zl))[None, :])
+    return np.asarray(P * scale, dtype=float) * ((-1.0) ** max(m, -s))
 
 
 @functools.lru_cache(maxsize=None)
