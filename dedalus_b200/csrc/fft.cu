@@ -683,7 +683,8 @@ __global__ void __launch_bounds__(FFT_THREADS, DIRECT ? 3 : 2) k_fft(FftArgs a)
 // ---------------------------------------------------------------------------------------------------------
 int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
                      int64_t inner, int32_t deriv, double kscale, void* stream,
-                     int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride);       // rfft_regs.cu
+                     int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride,
+                     int32_t out_peers, double* const* out_blk_ptr);       // rfft_regs.cu
 int db_cheb_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t lines, int32_t n_coeff,
                      const double* diags, int32_t nd, const double* pre, int32_t npre, const double* sol2, void* stream);
 
@@ -696,7 +697,7 @@ static int launch_fft(const db_fft_plan* plan, const double* in, double* out, in
     if (plan->n <= 0 || plan->nc <= 0 || n_coeff <= 0) { db_set_error("%s: bad sizes", name); return 1; }
     if (KIND == K_RFWD || KIND == K_RBWD) {
         // dealiased sizes on a strided axis: register-resident two-stage kernels (rfft_regs.cu)
-        const int rc = db_rfft_regs_try(KIND == K_RFWD, plan, in, out, outer, n_coeff, inner, deriv, kscale, stream, 0, 0, 0, 0);
+        const int rc = db_rfft_regs_try(KIND == K_RFWD, plan, in, out, outer, n_coeff, inner, deriv, kscale, stream, 0, 0, 0, 0, 0, nullptr);
         if (rc >= 0) return rc;
     }
     if ((KIND == K_CHFWD || (KIND == K_CHBWD && nda == 0 && ndb == 0)) && inner == 1) {
@@ -767,7 +768,7 @@ extern "C" int db_rfft_forward_blocked(const db_fft_plan* plan, const double* g,
                                        int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride, void* stream)
 {
     if (outer <= 0 || inner <= 0) return 0;
-    const int rc = db_rfft_regs_try(true, plan, g, c, outer, n_coeff, inner, 0, 0.0, stream, in_rpb, in_blk_stride, out_rpb, out_blk_stride);
+    const int rc = db_rfft_regs_try(true, plan, g, c, outer, n_coeff, inner, 0, 0.0, stream, in_rpb, in_blk_stride, out_rpb, out_blk_stride, 0, nullptr);
     return rc < 0 ? 2 : rc;
 }
 
@@ -776,7 +777,26 @@ extern "C" int db_rfft_backward_blocked(const db_fft_plan* plan, const double* c
                                         int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride, void* stream)
 {
     if (outer <= 0 || inner <= 0) return 0;
-    const int rc = db_rfft_regs_try(false, plan, c, g, outer, n_coeff, inner, deriv, kscale, stream, in_rpb, in_blk_stride, out_rpb, out_blk_stride);
+    const int rc = db_rfft_regs_try(false, plan, c, g, outer, n_coeff, inner, deriv, kscale, stream, in_rpb, in_blk_stride, out_rpb, out_blk_stride, 0, nullptr);
+    return rc < 0 ? 2 : rc;
+}
+
+// Peer variants (X1 as the transform's own stores): output block b goes to out_blocks[b] (a peer GPU's receive buffer mapped
+// into this process) instead of out + b * blk_stride.  `local_out` is only the 16-byte-aligned origin of the column offsets.
+extern "C" int db_rfft_forward_peer(const db_fft_plan* plan, const double* g, double* local_out, int64_t outer, int32_t n_coeff, int64_t inner,
+                                    int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int32_t n_peers, double* const* out_blocks, void* stream)
+{
+    if (outer <= 0 || inner <= 0) return 0;
+    const int rc = db_rfft_regs_try(true, plan, g, local_out, outer, n_coeff, inner, 0, 0.0, stream, in_rpb, in_blk_stride, out_rpb, 0, n_peers, out_blocks);
+    return rc < 0 ? 2 : rc;
+}
+
+extern "C" int db_rfft_backward_peer(const db_fft_plan* plan, const double* c, double* local_out, int64_t outer, int32_t n_coeff, int64_t inner,
+                                     int32_t deriv, double kscale, int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb,
+                                     int32_t n_peers, double* const* out_blocks, void* stream)
+{
+    if (outer <= 0 || inner <= 0) return 0;
+    const int rc = db_rfft_regs_try(false, plan, c, local_out, outer, n_coeff, inner, deriv, kscale, stream, in_rpb, in_blk_stride, out_rpb, 0, n_peers, out_blocks);
     return rc < 0 ? 2 : rc;
 }
 

@@ -33,6 +33,11 @@ struct RegArgs {
     // of an all-to-all send buffer (output side) or receive buffer (input side).  rpb = 0: plain (o * rows + r) * inner.
     int32_t in_rpb, out_rpb;
     int64_t in_blk_stride, out_blk_stride;
+    // Peer exchange (X1 without a library collective): with out_peers > 0 output block b is not at out + b * out_blk_stride
+    // but at out_blk_ptr[b] -- the receive buffer of GPU b, mapped into this process (NVLink peer memory): the transform's
+    // own 16-byte stores ARE the all-to-all, overlapped tile by tile with its arithmetic.
+    int32_t out_peers;
+    double* out_blk_ptr[8];
 };
 
 __device__ __forceinline__ int64_t row_offset(int64_t o, int r, int rows, int rpb, int64_t blk_stride, int64_t inner)
@@ -40,6 +45,16 @@ __device__ __forceinline__ int64_t row_offset(int64_t o, int r, int rows, int rp
     if (rpb == 0) return (o * rows + r) * inner;
     const int blk = r / rpb;
     return (int64_t)blk * blk_stride + (o * rpb + (r - blk * rpb)) * inner;
+}
+
+// address of output row r of outer index o (plain / blocked / blocked into peer memory)
+__device__ __forceinline__ double* out_row_ptr(const RegArgs& a, double* gout, int64_t o, int r, int rows, int64_t inner)
+{
+    if (a.out_peers > 0) {
+        const int blk = r / a.out_rpb;
+        return a.out_blk_ptr[blk] + (gout - a.out) + (o * a.out_rpb + (r - blk * a.out_rpb)) * inner;
+    }
+    return gout + row_offset(o, r, rows, a.out_rpb, a.out_blk_stride, inner);
 }
 
 __device__ __forceinline__ double2 cadd2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -250,7 +265,7 @@ k_rbwd_regs(RegArgs a, TileWalk tw_)
             double* __restrict__ gout = a.out + xt * (2 * P) + 2 * p;
 #pragma unroll
             for (int m = 0; m < H; ++m)
-                *reinterpret_cast<double2*>(gout + row_offset(o, k1 + NA * (2 * m + h), N, a.out_rpb, a.out_blk_stride, inner)) = v[m];
+                *reinterpret_cast<double2*>(out_row_ptr(a, gout, o, k1 + NA * (2 * m + h), N, inner)) = v[m];
         }
         __syncthreads();                                           // exchange reads done before the next prefetch lands here
     }
@@ -355,8 +370,8 @@ k_rfwd_regs(RegArgs a, TileWalk tw_)
                 const int kk = 3 * kb + c;                         // k1
                 const int k = NB * kk + k2;
                 if (kk >= Q || k > Kmax) continue;
-                double* row = gout + row_offset(o, 2 * k, M, a.out_rpb, a.out_blk_stride, inner);
-                double* row1 = gout + row_offset(o, 2 * k + 1, M, a.out_rpb, a.out_blk_stride, inner);
+                double* row = out_row_ptr(a, gout, o, 2 * k, M, inner);
+                double* row1 = out_row_ptr(a, gout, o, 2 * k + 1, M, inner);
                 const double2 za = z[kb];
                 if (k == 0) {
                     *reinterpret_cast<double2*>(row) = make_double2(za.x * sc, za.y * sc);
@@ -812,7 +827,8 @@ extern "C" long long db_rfft_regs_launches(void) { return g_regs_launches; }
 // kernel), otherwise the launch status.
 int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double* out, int64_t outer, int32_t n_coeff,
                      int64_t inner, int32_t deriv, double kscale, void* stream,
-                     int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride)
+                     int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride,
+                     int32_t out_peers, double* const* out_blk_ptr)
 {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("DB_FFT_REGS"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
@@ -825,6 +841,16 @@ int db_rfft_regs_try(bool fwd, const db_fft_plan* plan, const double* in, double
     RegArgs a;
     a.in = in; a.out = out; a.twn = plan->twn; a.inner = inner; a.M = n_coeff; a.deriv = deriv; a.kscale = kscale;
     a.in_rpb = in_rpb; a.in_blk_stride = in_blk_stride; a.out_rpb = out_rpb; a.out_blk_stride = out_blk_stride;
+    a.out_peers = 0;
+    for (int i = 0; i < 8; ++i) a.out_blk_ptr[i] = nullptr;
+    if (out_peers > 0) {
+        if (out_peers > 8 || out_rpb <= 0 || out_blk_ptr == nullptr) return -1;
+        a.out_peers = out_peers;
+        for (int i = 0; i < out_peers; ++i) {
+            if (reinterpret_cast<uintptr_t>(out_blk_ptr[i]) & 15) return -1;
+            a.out_blk_ptr[i] = out_blk_ptr[i];
+        }
+    }
     if (((in_rpb ? in_blk_stride : 0) | (out_rpb ? out_blk_stride : 0)) & 1) return -1;          // 16-byte alignment of every block
     ++g_regs_launches;
     switch (n) {

@@ -427,6 +427,13 @@ class RHSPlan:
             self._blk_fwd = ok
         return self._blk_fwd
 
+    def _peer(self):
+        """PeerExchange of this plan's process mesh (None: NCCL all-to-all path).  Created collectively on first use."""
+        if not hasattr(self, '_peer_x'):
+            from .transposes import PeerExchange
+            self._peer_x = PeerExchange.create(self.dist) if self.P > 1 else None
+        return self._peer_x
+
     @staticmethod
     def _groups(n, want):
         g = max(1, min(want, n))
@@ -446,9 +453,17 @@ class RHSPlan:
         n2 = self.gshape_full[1]; n2loc = n2 // self.P
         n3 = int(np.prod(self.gshape_full[2:], dtype=int))
         per_field = n1loc * n2loc * n3
-        send = self._scratch(('blk_send_bwd',), (self.P * nn * per_field,))
-        recv = self._scratch(('blk_recv_bwd',), (self.P * nn * per_field,))
-        groups = self._groups(nn, 3)
+        peer = self._peer()
+        if peer is not None:
+            # the y passes store every peer's rows straight into that peer's receive buffer (NVLink peer memory): no send
+            # buffer, no communication kernel; ONE device-side barrier orders the x passes after all writers
+            recv, peer_ptrs, peer_h = peer.buffers('bwd', self.P * nn * per_field)
+            rank = self.dist.rank
+            groups = [(0, nn)]
+        else:
+            send = self._scratch(('blk_send_bwd',), (self.P * nn * per_field,))
+            recv = self._scratch(('blk_recv_bwd',), (self.P * nn * per_field,))
+            groups = self._groups(nn, 3)
         handles, group_of, base_of = [], {}, {}
         for gi, (g0, g1) in enumerate(groups):
             ng = g1 - g0
@@ -459,11 +474,20 @@ class RHSPlan:
                 local = nd['index'] - g0
                 group_of[key] = gi; base_of[key] = (off + local * per_field, ng * per_field)
                 with Timed(self.solver.prof, "transform_bwd_axis1", 8 * (src.numel() + n1loc * n2 * n3)):
-                    py.backward_blocked(src.data_ptr(), send.data_ptr() + 8 * (off + local * per_field), n1loc, n3, self.device,
-                                        deriv=nd['deriv'], out_block=(n2loc, ng * per_field))
+                    if peer is not None:
+                        # block for peer p lands where the all-to-all would have put it: slot `rank` of p's group region
+                        dst = [peer_ptrs[p] + 8 * (off + rank * ng * per_field + local * per_field) for p in range(self.P)]
+                        py.backward_peer(src.data_ptr(), recv.data_ptr(), n1loc, n3, self.device, n2loc, dst, deriv=nd['deriv'])
+                    else:
+                        py.backward_blocked(src.data_ptr(), send.data_ptr() + 8 * (off + local * per_field), n1loc, n3, self.device,
+                                            deriv=nd['deriv'], out_block=(n2loc, ng * per_field))
             sl = slice(off, off + self.P * ng * per_field)
             with Timed(self.solver.prof, "transpose_bwd", 8 * 2 * self.P * ng * per_field):
-                handles.append(self.planner.alltoall_async(recv[sl], send[sl]))
+                if peer is not None:
+                    peer.barrier(peer_h)
+                    handles.append(None)
+                else:
+                    handles.append(self.planner.alltoall_async(recv[sl], send[sl]))
         inner = n2loc * n3
         waited = set()
         children = sorted(self.levels[lvl + 1].items(), key=lambda kv: group_of[kv[1]['parent']])
@@ -492,20 +516,35 @@ class RHSPlan:
         n1loc = px.M // self.P
         per_out_g = px.N * inner                                  # grid elements per output
         per_out_c = px.M * inner                                  # coefficient elements per output (all peers' blocks)
-        send = self._scratch(('blk_send_fwd',), (n_out * per_out_c,))
-        recv = self._scratch(('blk_recv_fwd',), (n_out * per_out_c,))
+        peer = self._peer()
+        if peer is not None:
+            recv, peer_ptrs, peer_h = peer.buffers('fwd', n_out * per_out_c)
+            rank = self.dist.rank
+            groups = [(0, n_out)]
+        else:
+            send = self._scratch(('blk_send_fwd',), (n_out * per_out_c,))
+            recv = self._scratch(('blk_recv_fwd',), (n_out * per_out_c,))
+            groups = self._groups(n_out, 2)
         out = self._scratch(('fwd', 1), (n_out, n1loc, py.M) + tuple(cur.shape[3:]))
         flat_in = cur.reshape(-1)
-        groups = self._groups(n_out, 2)
         handles = []
         for g0, g1 in groups:
             ng = g1 - g0
             sl = slice(g0 * per_out_c, g1 * per_out_c)
             with Timed(self.solver.prof, "transform_fwd_axis0", 8 * ng * (per_out_g + per_out_c)):
-                px.forward_blocked(flat_in.data_ptr() + 8 * g0 * per_out_g, send.data_ptr() + 8 * g0 * per_out_c, ng, inner, self.device,
-                                   out_block=(n1loc, ng * n1loc * inner))
+                if peer is not None:
+                    # peer p's block (its n1loc coefficient rows of all ng outputs) -> slot `rank` of p's receive buffer
+                    dst = [peer_ptrs[p] + 8 * (g0 * per_out_c + rank * ng * n1loc * inner) for p in range(self.P)]
+                    px.forward_peer(flat_in.data_ptr() + 8 * g0 * per_out_g, recv.data_ptr(), ng, inner, self.device, n1loc, dst)
+                else:
+                    px.forward_blocked(flat_in.data_ptr() + 8 * g0 * per_out_g, send.data_ptr() + 8 * g0 * per_out_c, ng, inner, self.device,
+                                       out_block=(n1loc, ng * n1loc * inner))
             with Timed(self.solver.prof, "transpose_fwd", 8 * 2 * ng * per_out_c):
-                handles.append(self.planner.alltoall_async(recv[sl], send[sl]))
+                if peer is not None:
+                    peer.barrier(peer_h)
+                    handles.append(None)
+                else:
+                    handles.append(self.planner.alltoall_async(recv[sl], send[sl]))
         per_out_y = n1loc * py.M * n3
         for (g0, g1), h in zip(groups, handles):
             ng = g1 - g0

@@ -61,6 +61,8 @@ SIGNATURES = {
     "db_rfft_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp]),
     "db_rfft_forward_blocked": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, i64, i32, i64, vp]),
     "db_rfft_backward_blocked": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, i32, i64, i32, i64, vp]),
+    "db_rfft_forward_peer": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, i64, i32, i32, C.POINTER(vp), vp]),
+    "db_rfft_backward_peer": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, i32, i64, i32, i32, C.POINTER(vp), vp]),
     "db_rfft_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, vp]),
     "db_cfft_forward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, vp]),
     "db_cfft_backward": (C.c_int, [PFFT, vp, vp, i64, i32, i64, i32, f64, vp]),

@@ -114,6 +114,23 @@ class RealFourierTransform:
         if not ok:
             raise RuntimeError("blocked real-Fourier transform not covered (blocked_supported() out of sync with the kernels)")
 
+    # ---- peer variants: output block b goes to out_ptrs[b] (another GPU's receive buffer), see db_rfft_*_peer
+    def backward_peer(self, c_ptr, origin_ptr, outer, inner, device, out_rpb, out_ptrs, deriv=0, in_block=(0, 0)):
+        plan = DevicePlan(self.N, 'real', device)
+        arr = (C.c_void_p * len(out_ptrs))(*[C.c_void_p(int(p)) for p in out_ptrs])
+        ok = get_lib().call_optional("db_rfft_backward_peer", plan.ref(), C.c_void_p(c_ptr), C.c_void_p(origin_ptr), outer, self.M, inner,
+                                     int(deriv), float(self.kscale), int(in_block[0]), int(in_block[1]), int(out_rpb), len(out_ptrs), arr, _stream())
+        if not ok:
+            raise RuntimeError("peer real-Fourier transform not covered (blocked_supported() out of sync with the kernels)")
+
+    def forward_peer(self, g_ptr, origin_ptr, outer, inner, device, out_rpb, out_ptrs, in_block=(0, 0)):
+        plan = DevicePlan(self.N, 'real', device)
+        arr = (C.c_void_p * len(out_ptrs))(*[C.c_void_p(int(p)) for p in out_ptrs])
+        ok = get_lib().call_optional("db_rfft_forward_peer", plan.ref(), C.c_void_p(g_ptr), C.c_void_p(origin_ptr), outer, self.M, inner,
+                                     int(in_block[0]), int(in_block[1]), int(out_rpb), len(out_ptrs), arr, _stream())
+        if not ok:
+            raise RuntimeError("peer real-Fourier transform not covered (blocked_supported() out of sync with the kernels)")
+
     def forward_blocked(self, g_ptr, c_ptr, outer, inner, device, in_block=(0, 0), out_block=(0, 0)):
         plan = DevicePlan(self.N, 'real', device)
         ok = get_lib().call_optional("db_rfft_forward_blocked", plan.ref(), C.c_void_p(g_ptr), C.c_void_p(c_ptr), outer, self.M, inner,

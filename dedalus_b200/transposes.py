@@ -12,6 +12,75 @@ import numpy as np
 from .lib import get_lib, current_stream
 
 
+class PeerExchange:
+    """Receive buffers of a pencil transpose that every GPU of the box can STORE into (NVLink peer memory): the Fourier pass in
+    front of a hop writes each peer's rows straight into that peer's buffer (db_rfft_*_peer), so the all-to-all is the
+    transform's own stores and no communication kernel runs; `barrier()` (signal pads, device side, stream ordered) then orders
+    the consumers after all writers.  Buffers come in pairs used alternately: a rank reaches the barrier of use k + 1 only
+    after its own reads of use k (same stream), so nobody overwrites a buffer that is still being read.
+    Built on torch's symmetric-memory allocator (plumbing: allocation + handle exchange + signal pads); unavailable -> None
+    and the NCCL all-to-all path is used.  Replaces the FFTW-MPI exchange of core/transposes.pyx:173-192."""
+
+    def __init__(self, dist):
+        import torch
+        import torch.distributed as td
+        import torch.distributed._symmetric_memory as symm
+        self.symm, self.td, self.torch = symm, td, torch
+        self.P, self.rank = dist.size, td.get_rank()
+        self.group = td.group.WORLD
+        if hasattr(symm, "enable_symm_mem_for_group"):
+            try:
+                symm.enable_symm_mem_for_group(self.group.group_name)
+            except Exception:
+                pass
+        self._bufs = {}
+        self._use = {}
+
+    @staticmethod
+    def create(dist):
+        import os
+        if os.environ.get("DB_PEER_TRANSPOSE", "1") == "0" or dist.size > 8:
+            return None
+        try:
+            import torch.distributed as td
+            if td.get_backend() != "nccl":
+                return None
+            px = PeerExchange(dist)
+            px.buffers('probe', 256)               # allocation + rendezvous must work on this box
+            ok = px.torch.ones(1, device='cuda')
+            td.all_reduce(ok, op=td.ReduceOp.MIN)
+            return px if float(ok.item()) == 1.0 else None
+        except Exception as exc:                   # e.g. no P2P / handle exchange not permitted in this container
+            import warnings
+            warnings.warn(f"peer-memory transposes unavailable ({type(exc).__name__}: {exc}); using the NCCL all-to-all")
+            try:
+                bad = td.get_rank() * 0.0
+                t = __import__('torch').zeros(1, device='cuda'); td.all_reduce(t, op=td.ReduceOp.MIN)
+            except Exception:
+                pass
+            return None
+
+    def buffers(self, key, numel):
+        """(local tensor, [base pointer on every rank]) of the next buffer of pair `key` (symmetric: same size on all ranks)."""
+        pair = self._bufs.get(key)
+        if pair is None or pair[0][0].numel() < numel:
+            pair = []
+            for _ in range(2):
+                t = self.symm.empty(int(numel), dtype=self.torch.float64, device=self.torch.device('cuda', self.torch.cuda.current_device()))
+                h = self.symm.rendezvous(t, self.group)
+                pair.append((t, h, [int(p) for p in h.buffer_ptrs]))
+            self._bufs[key] = pair
+            self._use[key] = 0
+        k = self._use[key] & 1
+        self._use[key] += 1
+        t, h, ptrs = pair[k]
+        self._last = h
+        return t, ptrs, h
+
+    def barrier(self, handle):
+        handle.barrier(channel=0)
+
+
 class TransposePlanner:
     def __init__(self, dist):
         import torch.distributed as td

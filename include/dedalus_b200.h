@@ -66,6 +66,19 @@ int db_rfft_backward_blocked(const db_fft_plan* plan, const double* c, double* g
                              int32_t deriv, double kscale,
                              int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int64_t out_blk_stride, void* stream);
 
+/* The all-to-all of a pencil transpose as the transform's OWN stores into peer memory (X1 without a library collective;
+ * replaces fftw_mpi_execute_r2r on the transposed plan, core/transposes.pyx:173-192, 209, 223): as the _blocked entries, but
+ * output block b (the rows destined for GPU b) is written to out_blocks[b] -- GPU b's receive buffer mapped into this process
+ * (NVLink peer memory, e.g. the buffer_ptrs of a torch symmetric-memory allocation) -- instead of the local send buffer, so
+ * the exchange overlaps the arithmetic tile by tile and no communication kernel is launched.  out_blocks is a HOST array of
+ * n_peers (<= 8) device pointers (copied into the launch); local_out is only the 16-byte aligned origin of the column offsets.
+ * The caller orders the consumers after all writers with a device-side barrier (signal pads).  Returns 2 if not covered. */
+int db_rfft_forward_peer(const db_fft_plan* plan, const double* g, double* local_out, int64_t outer, int32_t n_coeff, int64_t inner,
+                         int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb, int32_t n_peers, double* const* out_blocks, void* stream);
+int db_rfft_backward_peer(const db_fft_plan* plan, const double* c, double* local_out, int64_t outer, int32_t n_coeff, int64_t inner,
+                          int32_t deriv, double kscale, int32_t in_rpb, int64_t in_blk_stride, int32_t out_rpb,
+                          int32_t n_peers, double* const* out_blocks, void* stream);
+
 /* Complex Fourier, ordering [0..KM,(Nyq),-KM..-1], forward scaled by 1/N.
  * Replaces FFTWComplexFFT (core/transforms.py:243-267, 302-330).  Arrays are interleaved complex. */
 int db_cfft_forward(const db_fft_plan* plan, const double* g, double* c, int64_t outer, int32_t n_coeff, int64_t inner, void* stream);
