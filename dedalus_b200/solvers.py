@@ -335,7 +335,9 @@ class InitialValueSolver:
         self.total_modes = sum(int(c.valid_cols.sum()) * len(c.groups) for c in self.builder.classes.values())
         self.setup_time = time.time() - t0
         self._device_ready = False
-        self.step_hooks = []        # callables(solver) run at the start of each step (CFL, flow properties)
+        self.step_hooks = []        # callables(solver) run at the start of each step (CFL, flow properties, output handlers)
+        from .handlers import Evaluator
+        self.evaluator = Evaluator(self)      # solver.evaluator.add_file_handler(...).add_task(...) as in the reference
         self.prof = None            # set to a list to collect (name, start_event, end_event, bytes) per launch
         self._lhs_key = None
         self._ts_iteration = 0
@@ -545,6 +547,11 @@ class InitialValueSolver:
         self.sim_time += dt
 
     # ------------------------------------------------------------------------------------------------
+    def load_state(self, path, index=-1, allow_missing=False):
+        """Restore iteration, sim_time and the state from a FileHandler set (reference core/solvers.py:632-673)."""
+        from .handlers import load_state
+        return load_state(self, path, index=index, allow_missing=allow_missing)
+
     def evolve(self, timestep_function, log_cadence=100):
         try:
             while self.proceed:

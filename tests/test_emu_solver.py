@@ -219,3 +219,36 @@ def test_global_flow_property_reductions():
     vmax, vmin = flow.max('b'), flow.min('b')
     bg = np.array(pb['b']['g'])
     assert np.isclose(vmax, bg.max(), rtol=1e-13, atol=0) and np.isclose(vmin, bg.min(), rtol=1e-13, atol=1e-15)
+
+
+def test_file_handler_checkpoint_and_restart(tmp_path):
+    """Analysis output / checkpoint from the device state and restart (reference core/evaluator.py:208-300, 366-865;
+    core/solvers.py:632-673): snapshots fire on the iteration cadence, a run restarted from a checkpoint with load_state
+    reproduces the uninterrupted run, and the scales / tasks bookkeeping matches the reference's layout."""
+    def make():
+        pb = examples.rayleigh_benard(dim=2, Nh=16, Nz=16, Rayleigh=1e5)
+        solver = pb['problem'].build_solver(d3.RK222)
+        examples.rayleigh_benard_initial_condition(pb['b'], pb['bases'], pb['Lz'])
+        return pb, solver
+    dt = 0.01
+    pb, solver = make()
+    snaps = solver.evaluator.add_file_handler(tmp_path / "snapshots", iter=2, max_writes=2)
+    snaps.add_task(pb['b'], name='buoyancy', layout='g')
+    chk = solver.evaluator.add_file_handler(tmp_path / "checkpoints", iter=3)
+    chk.add_tasks(solver.state, layout='g')
+    for _ in range(6):
+        solver.step(dt)
+    final = {n: np.array(pb[n]['c']) for n in ('p', 'b', 'u')}
+    # snapshots at iterations 0, 2, 4 -> sets of 2 writes
+    s1 = np.load(tmp_path / "snapshots" / "snapshots_s1.npz"); s2 = np.load(tmp_path / "snapshots" / "snapshots_s2.npz")
+    assert list(s1['scales/iteration']) == [0, 2] and list(s2['scales/iteration']) == [4]
+    assert list(s1['scales/write_number']) == [1, 2] and list(s2['scales/write_number']) == [3]
+    assert s1['tasks/buoyancy'].shape == (2, 16, 16) and np.isclose(s1['scales/sim_time'][1], 2 * dt)
+    # restart from the checkpoint written at iteration 3 and run to iteration 6
+    pb2, solver2 = make()
+    write, dt_loaded = solver2.load_state(tmp_path / "checkpoints" / "checkpoints_s1.npz", index=1)
+    assert (write, solver2.iteration) == (2, 3) and np.isclose(solver2.sim_time, 3 * dt) and np.isclose(dt_loaded, dt)
+    for _ in range(3):
+        solver2.step(dt)
+    for n in ('p', 'b', 'u'):
+        assert np.allclose(pb2[n]['c'], final[n], rtol=1e-9, atol=1e-12), n
