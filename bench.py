@@ -18,7 +18,7 @@ import numpy as np
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "timesteps/sec 3D Rayleigh-Benard 256^3 fp64"
+METRIC = "timesteps/sec 3D Rayleigh-Benard 256^3 fp64"      # --size N replaces 256 (north_star: 256^3 and 512^3)
 
 
 def parse():
@@ -181,7 +181,9 @@ def parity_gate(args, world, rank):
 
 
 def main():
+    global METRIC
     args = parse()
+    METRIC = METRIC.replace("256^3", f"{args.size}^3")
     if args.impl == "reference":
         return run_reference(args)
     import torch

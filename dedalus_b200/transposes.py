@@ -28,11 +28,6 @@ class PeerExchange:
         self.symm, self.td, self.torch = symm, td, torch
         self.P, self.rank = dist.size, td.get_rank()
         self.group = td.group.WORLD
-        if hasattr(symm, "enable_symm_mem_for_group"):
-            try:
-                symm.enable_symm_mem_for_group(self.group.group_name)
-            except Exception:
-                pass
         self._bufs = {}
         self._use = {}
 
