@@ -460,8 +460,14 @@ class InitialValueSolver:
                 f.change_scales(f.dealias)
                 f.change_layout('g')
                 f.change_layout('c')
-            except NotImplementedError:
-                continue     # partially-based fields on a distributed mesh: not supported yet
+            except NotImplementedError as exc:
+                # partially-based fields (e.g. tau fields on (x, y)) on a distributed mesh have no grid round trip yet: the
+                # reference enforces them too (core/solvers.py:675-681), so say so once instead of skipping silently
+                if not getattr(self, "_warned_hermitian", False):
+                    import warnings
+                    warnings.warn(f"Hermitian-symmetry enforcement skipped for field {f.name!r} ({exc}); "
+                                  "the reference applies it to every state field")
+                    self._warned_hermitian = True
 
     def _sync_clock(self):
         import torch

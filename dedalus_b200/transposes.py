@@ -3,9 +3,13 @@
 Reference: Transpose (core/distributor.py:696-924) driving FFTWTranspose (core/transposes.pyx:22-246): every rank
 copies its slab into a (N1, n2_local, N0, N3) buffer, FFTW-MPI exchanges blocks (MPI alltoall inside FFTW) and the
 result is copied out again; with GROUP_TRANSPOSES all fields sharing a shape travel together (842-871).
-Here one hop is: pack kernel (per-destination contiguous blocks) -> one NCCL all-to-all over NVLink/NVSwitch for
-the whole stack of fields -> unpack kernel (csrc/pointwise.cu: db_transpose_*).  The planner keeps the reference's
-method names: localize_columns (towards grid space) / localize_rows (towards coefficient space).
+Three realisations, fastest first:
+  * PeerExchange (this file) + db_rfft_*_peer: the Fourier pass in front of the hop stores every peer's rows straight into that
+    peer's receive buffer over NVLink (no pack / unpack, no communication kernel; evaluator._backward_blocked_levels);
+  * blocked row addressing + NCCL all-to-all (no pack / unpack; the all-to-all overlaps the neighbouring passes);
+  * general fallback, any sizes: pack kernel (per-destination contiguous blocks) -> one NCCL all-to-all for the whole stack of
+    fields -> unpack kernel (csrc/pointwise.cu: db_transpose_*).  The planner keeps the reference's method names:
+    localize_columns (towards grid space) / localize_rows (towards coefficient space).
 """
 import ctypes as C
 import numpy as np
@@ -48,8 +52,7 @@ class PeerExchange:
         except Exception as exc:                   # e.g. no P2P / handle exchange not permitted in this container
             import warnings
             warnings.warn(f"peer-memory transposes unavailable ({type(exc).__name__}: {exc}); using the NCCL all-to-all")
-            try:
-                bad = td.get_rank() * 0.0
+            try:       # keep the ranks' collectives matched: everybody learns that somebody failed
                 t = __import__('torch').zeros(1, device='cuda'); td.all_reduce(t, op=td.ReduceOp.MIN)
             except Exception:
                 pass
@@ -139,13 +142,13 @@ class TransposePlanner:
         lib.call("db_transpose_unpack_rev", recv.data_ptr(), out.data_ptr(), B, n1 // P, n2loc * P, n3, P, current_stream())
 
 
-_planners = {}
-
-
 def get_planner(dist):
-    if id(dist) not in _planners:
-        _planners[id(dist)] = TransposePlanner(dist)
-    return _planners[id(dist)]
+    """One planner per Distributor, stored ON the distributor (a cache keyed by id(dist) could hand a stale planner to a new
+    distributor that reuses the id of a garbage-collected one)."""
+    planner = getattr(dist, "_transpose_planner", None)
+    if planner is None:
+        planner = dist._transpose_planner = TransposePlanner(dist)
+    return planner
 
 
 def check_divisible(dist, bases, scales):
