@@ -2,16 +2,22 @@
 
     python -m dedalus_b200.build            # product library (needs nvcc; cross-compiles without a GPU)
     python -m dedalus_b200.build --emu      # TEST-ONLY CPU emulation of the same kernels (tests/emu/)
+
+Every source is compiled to its own object (dedalus_b200/csrc/_obj/, git-ignored) and only stale objects are rebuilt;
+the objects are compiled concurrently and linked into the shared library through a temporary file + rename, so that
+concurrent test workers never load a half-written library.
 """
 import os, subprocess, sys, pathlib, shutil
 
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-SOURCES = ["core.cu", "fft.cu", "rfft_regs.cu", "pencil.cu", "pointwise.cu"]
+SOURCES = ["core.cu", "fft.cu", "rfft_regs.cu", "pencil.cu", "pointwise.cu", "banded.cu"]
 LIB = PKG / "libdedalus_b200.so"
+OBJ = CSRC / "_obj"
 EMU_DIR = ROOT / "tests" / "emu"
 EMU_LIB = EMU_DIR / "libdedalus_b200_emu.so"
+HEADERS = [CSRC / "db_common.cuh", CSRC / "tw96.inc", ROOT / "include" / "dedalus_b200.h"]
 
 
 def _newer(target, deps):
@@ -21,34 +27,60 @@ def _newer(target, deps):
     return any(pathlib.Path(d).stat().st_mtime > t for d in deps)
 
 
+def _compile_all(jobs):
+    """jobs: list of (command, object path); run the stale ones concurrently."""
+    procs = [(subprocess.Popen(cmd), obj) for cmd, obj in jobs]
+    failed = [str(obj) for p, obj in procs if p.wait() != 0]
+    if failed:
+        raise RuntimeError(f"compilation failed: {failed}")
+
+
+def _link(cmd, target):
+    tmp = target.with_suffix(f".tmp{os.getpid()}.so")
+    subprocess.run(cmd + ["-o", str(tmp)], check=True)
+    os.replace(tmp, target)
+
+
 def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    srcs = [str(CSRC / s) for s in SOURCES]
-    deps = srcs + [str(CSRC / "db_common.cuh"), str(CSRC / "tw96.inc"), str(ROOT / "include" / "dedalus_b200.h")]
-    if not force and not _newer(LIB, deps):
+    OBJ.mkdir(exist_ok=True)
+    jobs, objs = [], []
+    for s in SOURCES:
+        obj = OBJ / (s + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [CSRC / s] + HEADERS):
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                   "-Xcompiler", "-fPIC", "-c", str(CSRC / s), "-o", str(obj)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append((cmd, obj))
+    if not jobs and not _newer(LIB, objs):
         return LIB
     if not pathlib.Path(nvcc).exists():
         raise RuntimeError("nvcc not found: cannot build libdedalus_b200.so")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", str(LIB)] + srcs
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
+    _compile_all(jobs)
+    _link([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [str(o) for o in objs], LIB)
     return LIB
 
 
 def build_emu(force=False):
-    srcs = [str(CSRC / s) for s in SOURCES] + [str(EMU_DIR / "cuda_emu.cpp")]
-    deps = srcs + [str(CSRC / "db_common.cuh"), str(ROOT / "include" / "dedalus_b200.h"), str(EMU_DIR / "cuda_emu.h")]
-    if not force and not _newer(EMU_LIB, deps):
+    OBJ.mkdir(exist_ok=True)
+    jobs, objs = [], []
+    for src in [CSRC / s for s in SOURCES] + [EMU_DIR / "cuda_emu.cpp"]:
+        obj = OBJ / (src.name + ".emu.o")
+        objs.append(obj)
+        if force or _newer(obj, [src, EMU_DIR / "cuda_emu.h"] + HEADERS):
+            jobs.append((["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-DDB_EMU", "-I", str(EMU_DIR), "-x", "c++", "-c", str(src),
+                          "-o", str(obj)], obj))
+    if not jobs and not _newer(EMU_LIB, objs):
         return EMU_LIB
-    cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DDB_EMU", "-I", str(EMU_DIR), "-x", "c++"] + srcs + ["-o", str(EMU_LIB)]
-    subprocess.run(cmd, check=True)
+    _compile_all(jobs)
+    _link(["g++", "-shared", "-fPIC"] + [str(o) for o in objs], EMU_LIB)
     return EMU_LIB
 
 
 if __name__ == "__main__":
     if "--emu" in sys.argv:
-        print(build_emu(force=True))
+        print(build_emu(force="--force" in sys.argv))
     else:
-        print(build(force=True, verbose="-v" in sys.argv))
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

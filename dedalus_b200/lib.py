@@ -50,6 +50,21 @@ class SlotComb(C.Structure):
     _fields_ = [("nvec", i32), ("slot", i32 * 16), ("coef", f64 * 16)]
 
 
+class BandedSys(C.Structure):
+    """include/dedalus_b200.h: db_banded_sys"""
+    _fields_ = [("n", i32), ("nrhs", i32), ("op_off", i64), ("lu_off", i64), ("piv_off", i64), ("vec_off", i64)]
+
+
+class VecComb(C.Structure):
+    """include/dedalus_b200.h: db_veccomb"""
+    _fields_ = [("nvec", i32), ("vec", vp * 16), ("coef", f64 * 16)]
+
+
+class PairLinTerm(C.Structure):
+    """include/dedalus_b200.h: db_pair_lin_term"""
+    _fields_ = [("re", f64), ("im", f64), ("sym_off", i64), ("src", i32), ("pad", i32)]
+
+
 PFFT = C.POINTER(FftPlan)
 PLIN = C.POINTER(LinComb)
 
@@ -91,6 +106,12 @@ SIGNATURES = {
     "db_transpose_unpack": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
     "db_transpose_pack_rev": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
     "db_transpose_unpack_rev": (C.c_int, [vp, vp, i64, i64, i64, i64, i32, vp]),
+    "db_banded_combine": (C.c_int, [vp, i32, i32, i32, f64, vp, f64, vp, vp, vp]),
+    "db_banded_factor": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp]),
+    "db_banded_solve": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, C.POINTER(VecComb), vp, vp]),
+    "db_banded_matvec": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "db_index_move": (C.c_int, [vp, i64, vp, vp, i32, vp]),
+    "db_pair_lincomb": (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, vp]),
     "db_absmax": (C.c_int, [vp, i64, vp, vp]),
     "db_cfl_max": (C.c_int, [C.POINTER(vp), C.POINTER(vp), i32, i64, i64, i64, vp, vp]),
 }

@@ -299,6 +299,52 @@ int db_transpose_unpack(const double* recvbuf, double* out, int64_t B, int64_t n
 int db_transpose_pack_rev(const double* a, double* sendbuf, int64_t B, int64_t n1, int64_t n2loc, int64_t n3, int32_t P, void* stream);
 int db_transpose_unpack_rev(const double* recvbuf, double* out, int64_t B, int64_t n1loc, int64_t n2, int64_t n3, int32_t P, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Curvilinear pencil path (sphere / shell problems).  On the sphere the pencils are one system
+ * per azimuthal wavenumber m, coupled along the degree l (core/basis.py:2780-2786 matrix_dependence; operators
+ * core/basis.py:3299-3420, core/operators.py:2995-3050 MulCosine, 2125-2160 SpinSkew): RAGGED sizes, narrow bands.
+ * They are stored in LAPACK's general-band layout, column-major,
+ *     operator storage (ld0 = kl + ku + 1):    A(i, j) at ab0[op_off + (ku + i - j) + j * ld0]
+ *     factor storage   (ldf = 2 kl + ku + 1):  A(i, j) at ab [lu_off + (kl + ku + i - j) + j * ldf]
+ * and factorised with row interchanges by one warp per system (replaces the per-pencil SuperLU of
+ * libraries/matsolvers.py:126-183 driven from core/timesteppers.py:577-583, 632-639).  Vectors of system s hold nrhs
+ * right-hand-side columns: element (i, r) at vec_off + i * nrhs + r.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n, nrhs;
+    int64_t op_off;       /* offset (doubles) of this system's band in the operator-storage buffers (M, L)      */
+    int64_t lu_off;       /* offset (doubles) in the factor-storage buffer                                        */
+    int64_t piv_off;      /* offset (int32) of its pivot rows                                                      */
+    int64_t vec_off;      /* offset (doubles) of its rows in every work vector                                     */
+} db_banded_sys;
+typedef struct { int32_t nvec; const double* vec[16]; double coef[16]; } db_veccomb;
+/* lu = a0 * M + b0 * L (fill-in rows zeroed): the LHS of an IMEX stage, core/timesteppers.py:632-639 */
+int db_banded_combine(const db_banded_sys* sys, int32_t nsys, int32_t kl, int32_t ku, double a0, const double* m_ab,
+                      double b0, const double* l_ab, double* lu, void* stream);
+/* in-place band LU with partial pivoting of every system; info[s] = zero / non-finite pivots met */
+int db_banded_factor(const db_banded_sys* sys, int32_t nsys, int32_t kl, int32_t ku, double* lu, int32_t* ipiv, int32_t* info, void* stream);
+/* x = A^{-1} (sum_k coef_k vec_k) for all columns (the RHS combination of core/timesteppers.py:617-623 fused in);
+ * x may be one of the vec_k.  max_n / max_nrhs: largest n / nrhs over the systems. */
+int db_banded_solve(const db_banded_sys* sys, int32_t nsys, int32_t kl, int32_t ku, int32_t max_n, int32_t max_nrhs,
+                    const double* lu, const int32_t* ipiv, const db_veccomb* rhs, double* x, void* stream);
+/* ya = A x and / or yb = B x (operator storage; either output may be NULL): M.X, L.X of core/timesteppers.py:590-591 */
+int db_banded_matvec(const db_banded_sys* sys, int32_t nsys, int32_t kl, int32_t ku, const double* a_ab, const double* b_ab,
+                     const double* x, double* ya, double* yb, void* stream);
+/* gather (vec[e] = idx[e] >= 0 ? arena[idx[e]] : 0) / scatter (arena[idx[e]] = vec[e] where idx[e] >= 0) through an index
+ * table: pencil vectors <-> coefficient arrays in the folded triangular (m, l) packing (core/subsystems.py:340-371) */
+int db_index_move(const int64_t* idx, int64_t count, double* arena, double* vec, int32_t gather, void* stream);
+
+/* Complex linear combinations on (cos, -sin) pairs.  in / out: (ncomp, 2 * npair, ncol), rows 2j and 2j + 1 = real and
+ * imaginary part of the exp(i m phi) coefficient (core/basis.py:1108-1134).  Output o = sum over its terms
+ * term_ptr[o] <= t < term_ptr[o + 1] of (re + i im) * sym * in[src], sym = syms[sym_off + j * ncol + c] or 1 (sym_off < 0).
+ * Replaces (a) SeparableSphereOperator.operate -- SphereGradient / Divergence / Laplacian symbols k(l, s, mu) / R
+ * (core/operators.py:2725-2866, core/basis.py:3299-3420) and SpinSkew (core/operators.py:2125-2160) in coefficient space,
+ * (b) the component <-> spin recombination (libraries/spin_recombination.pyx:9-56 with U of core/coords.py:219-232) in
+ * (azimuthal coefficient, colatitude grid) space.  in and out must not overlap. */
+typedef struct { double re, im; int64_t sym_off; int32_t src; int32_t pad; } db_pair_lin_term;
+int db_pair_lincomb(const double* in, double* out, int64_t npair, int64_t ncol, int32_t n_out,
+                    const int32_t* term_ptr, const db_pair_lin_term* terms, const double* syms, void* stream);
+
 /* max |x| reduction (CFL / flow properties; extras/flow_tools.py:33-37 before the Allreduce) */
 int db_absmax(const double* x, int64_t count, double* out, void* stream);
 
