@@ -2,14 +2,15 @@
 
 Public surface mirrors `dedalus.public` (reference dedalus/public.py:4-15) for the Cartesian IVP path.
 """
-from .coords import Coordinate, CartesianCoordinates
+from .coords import Coordinate, CartesianCoordinates, S2Coordinates
 from .distributor import Distributor
 from .basis import (RealFourier, ComplexFourier, Jacobi, Legendre, Ultraspherical,
                     ChebyshevT, ChebyshevU, ChebyshevV, Chebyshev)
+from .sphere import SphereBasis
 from .field import Field
 from .operators import (Differentiate, Gradient, Divergence, Laplacian, Trace, TransposeComponents,
-                        Interpolate, Integrate, Lift, Convert, TimeDerivative, DotProduct, Multiply,
-                        grad, div, lap, trace, transpose, integ, ave, dot, interp)
+                        Interpolate, Integrate, Lift, Convert, TimeDerivative, DotProduct, Multiply, Skew, MulCosine,
+                        grad, div, lap, skew, trace, transpose, integ, ave, dot, interp)
 from .problems import IVP
 InitialValueProblem = IVP
 from .timesteppers import (schemes, CNAB1, SBDF1, CNAB2, MCNAB2, SBDF2, CNLF2, SBDF3, SBDF4,

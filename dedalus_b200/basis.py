@@ -14,6 +14,19 @@ from .coords import Coordinate, AffineCOV
 class Basis:
     dim = 1
 
+    # per-axis accessors (sub = axis index inside a multi-dimensional basis, always 0 here; dedalus_b200/sphere.py overrides)
+    def axis_size(self, sub=0):
+        return self.size
+
+    def axis_grid_size(self, scale, sub=0):
+        return self.grid_size(scale)
+
+    def axis_dealias(self, sub=0):
+        return self.dealias[0]
+
+    def axis_group_size(self, sub=0):
+        return self.group_size
+
     def grid_size(self, scale):
         g = float(scale) * self.size
         if not g.is_integer():

@@ -71,3 +71,43 @@ class AffineCOV:
             return {'left': self.native_left, 'right': self.native_right, 'center': self.native_center}[problem_coord]
         neutral = (np.asarray(problem_coord) - self.problem_left) / self.problem_length
         return self.native_left + neutral * self.native_length
+
+
+class AzimuthalCoordinate(Coordinate):
+    pass
+
+
+class S2Coordinates:
+    """S2 coordinate system (azimuth, colatitude); spin component ordering (-, +) (reference coords.py:201-252)."""
+    spin_ordering = (-1, +1)
+    dim = 2
+    curvilinear = True
+
+    def __init__(self, azimuth, colatitude):
+        self.names = (azimuth, colatitude)
+        self.azimuth = AzimuthalCoordinate(azimuth, cs=self)
+        self.colatitude = Coordinate(colatitude, cs=self)
+        self.coords = (self.azimuth, self.colatitude)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.coords[self.names.index(key)]
+        return self.coords[key]
+
+    def __repr__(self):
+        return "{" + ",".join(self.names) + "}"
+
+    @classmethod
+    def U_forward(cls, order=1):
+        """Unitary map from coordinate (phi, theta) to spin (-, +) components: u[+-] = (u[theta] +- 1j u[phi]) / sqrt(2)
+        (reference coords.py:219-227)."""
+        Ui = {+1: np.array([+1j, 1]) / np.sqrt(2), -1: np.array([-1j, 1]) / np.sqrt(2)}
+        U = np.array([Ui[s] for s in cls.spin_ordering])
+        out = U
+        for _ in range(order - 1):
+            out = np.kron(out, U)
+        return out
+
+    @classmethod
+    def U_backward(cls, order=1):
+        return cls.U_forward(order).T.conj()

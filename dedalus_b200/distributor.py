@@ -72,10 +72,15 @@ class Distributor:
             if b is None:
                 continue
             ax = self.get_basis_axis(b)
-            if out[ax] is not None:
-                raise ValueError("Overlapping bases specified.")
-            out[ax] = b
+            for sub in range(b.dim):            # a multi-dimensional basis (sphere) occupies dim consecutive axes
+                if out[ax + sub] is not None:
+                    raise ValueError("Overlapping bases specified.")
+                out[ax + sub] = b
         return tuple(out)
+
+    def basis_subaxis(self, basis, axis):
+        """Index of `axis` inside `basis` (0 for one-dimensional bases)."""
+        return axis - self.get_basis_axis(basis)
 
     # ---- field factories (reference distributor.py:213-235) ----------------------------------------
     def Field(self, *args, **kw):
@@ -103,18 +108,22 @@ class Distributor:
 
     def coeff_local_slice(self, axis, basis):
         """Local slice along `axis` in coefficient layout (axis 0 distributed in whole groups)."""
-        size = 1 if basis is None else basis.size
+        size = 1 if basis is None else basis.axis_size(self.basis_subaxis(basis, axis))
         if axis != 0 or self.size == 1 or basis is None:
             return slice(0, size)
+        if basis.dim > 1:
+            raise NotImplementedError("curvilinear bases are single-GPU in this build")
         g = basis.group_size
         s, e = self.block_range(size // g, self.size, self.rank)
         return slice(s * g, e * g)
 
     def grid_local_slice(self, axis, basis, scale):
         """Local slice along `axis` in full grid layout (axis 1 distributed after the transpose hop)."""
-        size = 1 if basis is None else basis.grid_size(scale)
+        size = 1 if basis is None else basis.axis_grid_size(scale, self.basis_subaxis(basis, axis))
         if axis != 1 or self.size == 1 or basis is None:
             return slice(0, size)
+        if basis.dim > 1:
+            raise NotImplementedError("curvilinear bases are single-GPU in this build")
         s, e = self.block_range(size, self.size, self.rank)
         return slice(s, e)
 
@@ -130,7 +139,14 @@ class Distributor:
 
     def local_grids(self, *bases, scales=None):
         scales = self.remedy_scales(scales)
-        return tuple(self.local_grid(b, scales[self.get_basis_axis(b)]) for b in bases)
+        out = []
+        for b in bases:
+            ax = self.get_basis_axis(b)
+            if b.dim > 1:       # one grid per axis of the basis (reference distributor.py:291-301)
+                out.extend(b.local_grids(self, scales[ax:ax + b.dim]))
+            else:
+                out.append(self.local_grid(b, scales[ax]))
+        return tuple(out)
 
     def remedy_scales(self, scales):
         if scales is None:

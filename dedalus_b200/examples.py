@@ -63,3 +63,46 @@ def rayleigh_benard_initial_condition(b, bases, Lz, seed=42):
     b.fill_random('g', seed=seed, distribution='normal', scale=1e-3)
     b['g'] *= z * (Lz - z)
     b['g'] += Lz - z
+
+
+def shallow_water(Nphi=512, Ntheta=256, dealias=3/2, dtype=np.float64):
+    """Spherical shallow water, BASELINE config 4 (examples/ivp_sphere_shallow_water/shallow_water.py:25-86)."""
+    meter = 1 / 6.37122e6
+    hour = 1
+    second = hour / 3600
+    R = 6.37122e6 * meter
+    Omega = 7.292e-5 / second
+    nu = 1e5 * meter**2 / second / 32**2
+    g = 9.80616 * meter / second**2
+    H = 1e4 * meter
+    timestep = 600 * second * min(1.0, 128 / Ntheta)
+    coords = d3.S2Coordinates('phi', 'theta')
+    dist = d3.Distributor(coords, dtype=dtype)
+    basis = d3.SphereBasis(coords, (Nphi, Ntheta), radius=R, dealias=dealias, dtype=dtype)
+    u = dist.VectorField(coords, name='u', bases=basis)
+    h = dist.Field(name='h', bases=basis)
+    zcross = lambda A: d3.MulCosine(d3.skew(A))
+    problem = d3.IVP([u, h], namespace=locals())
+    problem.add_equation("dt(u) + nu*lap(lap(u)) + g*grad(h) + 2*Omega*zcross(u) = - u@grad(u)")
+    problem.add_equation("dt(h) + nu*lap(lap(h)) + H*div(u) = - div(h*u)")
+    return dict(problem=problem, dist=dist, coords=coords, basis=basis, u=u, h=h, timestep=timestep,
+                units=dict(meter=meter, hour=hour, second=second))
+
+
+def shallow_water_initial_condition(u, h, basis, units):
+    """Zonal jet and height perturbation of the stock script (lines 48-57, 68-73), without the balancing LBVP."""
+    meter, second = units['meter'], units['second']
+    phi, theta = u.dist.local_grids(basis)
+    lat = np.pi / 2 - theta + 0 * phi
+    umax = 80 * meter / second
+    lat0 = np.pi / 7
+    lat1 = np.pi / 2 - lat0
+    en = np.exp(-4 / (lat1 - lat0)**2)
+    jet = (lat0 <= lat) * (lat <= lat1)
+    u_jet = umax / en * np.exp(1 / (lat[jet] - lat0) / (lat[jet] - lat1))
+    u['g'][0][jet] = u_jet
+    lat2 = np.pi / 4
+    hpert = 120 * meter
+    alpha = 1 / 3
+    beta = 1 / 15
+    h['g'] += hpert * np.cos(lat) * np.exp(-(phi / alpha)**2) * np.exp(-((lat2 - lat) / beta)**2)

@@ -33,10 +33,17 @@ class Field(Operand):
     def atoms(self):
         return [self]
 
+    def unique_bases(self):
+        out = []
+        for b in self.bases:
+            if b is not None and not any(b is o for o in out):
+                out.append(b)
+        return tuple(out)
+
     # ---- shapes --------------------------------------------------------------------------------------
     @property
     def dealias(self):
-        return tuple(1 if b is None else b.dealias[0] for b in self.bases)
+        return tuple(1 if b is None else b.axis_dealias(self.dist.basis_subaxis(b, ax)) for ax, b in enumerate(self.bases))
 
     @property
     def is_real(self):
@@ -48,9 +55,9 @@ class Field(Operand):
             if b is None:
                 shp.append(1)
             elif layout == 'c':
-                shp.append(b.size)
+                shp.append(b.axis_size(self.dist.basis_subaxis(b, ax)))
             else:
-                shp.append(b.grid_size(scales[ax]))
+                shp.append(b.axis_grid_size(scales[ax], self.dist.basis_subaxis(b, ax)))
         return tuple(shp)
 
     def local_slices(self, layout, scales):
@@ -167,7 +174,7 @@ class Field(Operand):
 
     def copy_device_to_grid(self):
         """Grid values (dealias scales) of this field as a NEW device tensor; the field itself is left untouched."""
-        tmp = Field(self.dist, bases=tuple(b for b in self.bases if b is not None), tensorsig=self.tensorsig, dtype=self.dtype)
+        tmp = Field(self.dist, bases=self.unique_bases(), tensorsig=self.tensorsig, dtype=self.dtype)
         self.dist._fields.pop()
         if self.layout != 'c':
             self.change_layout('c')
@@ -177,7 +184,7 @@ class Field(Operand):
         return tmp.device_data()
 
     def copy(self):
-        out = Field(self.dist, bases=tuple(b for b in self.bases if b is not None), tensorsig=self.tensorsig, dtype=self.dtype)
+        out = Field(self.dist, bases=self.unique_bases(), tensorsig=self.tensorsig, dtype=self.dtype)
         out.preset_scales(self.scales)
         out.preset_layout(self.layout)
         np.copyto(out.data, self.data)

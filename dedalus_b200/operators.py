@@ -282,6 +282,30 @@ class TransposeComponents(LinearOperator):
         self.tensorsig = (ts[1], ts[0]) + ts[2:]
 
 
+class Skew(LinearOperator):
+    """90-degree positive rotation of a 2-D vector index (reference operators.py:2049-2160; on S2 the spin components are
+    multiplied by -+1j, SpinSkew)."""
+    def __init__(self, A, index=0):
+        if not A.tensorsig:
+            raise ValueError("Skew requires a tensor operand.")
+        if A.tensorsig[index].dim != 2:
+            raise ValueError("Skew is only defined for 2-D vector indices.")
+        self.args = [A]
+        self.index = index
+        self.cs = A.tensorsig[index]
+        self.dist, self.dtype, self.tensorsig, self.bases = A.dist, A.dtype, A.tensorsig, A.bases
+
+
+class MulCosine(LinearOperator):
+    """Multiplication by cos(colatitude) on S2 (reference operators.py:2995-3050)."""
+    def __init__(self, A, coordsys=None):
+        self.args = [A]
+        self.cs = coordsys if coordsys is not None else A.dist.coordsys
+        if not getattr(self.cs, 'curvilinear', False):
+            raise ValueError("MulCosine needs an S2 coordinate system.")
+        self.dist, self.dtype, self.tensorsig, self.bases = A.dist, A.dtype, A.tensorsig, A.bases
+
+
 class Interpolate(LinearOperator):
     def __init__(self, A, coord, position):
         self.args = [A]
@@ -338,6 +362,7 @@ class Convert(LinearOperator):
 def grad(A, cs=None): return Gradient(A, cs)
 def div(A, index=0): return Divergence(A, index)
 def lap(A, cs=None): return Laplacian(A, cs)
+def skew(A, index=0): return Skew(A, index)
 def trace(A): return Trace(A)
 def transpose(A): return TransposeComponents(A)
 def dt(A): return TimeDerivative(A)

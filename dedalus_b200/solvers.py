@@ -328,11 +328,18 @@ class InitialValueSolver:
         self.start_time = time.time()
         # ---- host setup: templates and batches (replaces Subproblem.build_matrices loops, subsystems.py:72-81)
         t0 = time.time()
-        self.builder = PencilSystemBuilder(problem, entry_cutoff=entry_cutoff)
-        self.batches = build_batches(self.builder)
+        from .sphere import sphere_basis_of
+        self.entry_cutoff = entry_cutoff
+        # curvilinear problems (S2 sphere): per-m banded systems, dedalus_b200/sphere.py SphereSystems, built on the device side
+        self.curvilinear = any(sphere_basis_of(v) is not None for v in problem.variables)
+        if self.curvilinear:
+            self.builder, self.batches = None, []
+        else:
+            self.builder = PencilSystemBuilder(problem, entry_cutoff=entry_cutoff)
+            self.batches = build_batches(self.builder)
         self.var_arena = Arena(self.dist, [(v.tshape, v.bases) for v in problem.variables])
         self.eq_arena = Arena(self.dist, [(tuple(cs.dim for cs in eq['tensorsig']), eq['bases']) for eq in problem.equations])
-        self.total_modes = sum(int(c.valid_cols.sum()) * len(c.groups) for c in self.builder.classes.values())
+        self.total_modes = 0 if self.curvilinear else sum(int(c.valid_cols.sum()) * len(c.groups) for c in self.builder.classes.values())
         self.setup_time = time.time() - t0
         self._device_ready = False
         self.step_hooks = []        # callables(solver) run at the start of each step (CFL, flow properties, output handlers)
@@ -364,8 +371,12 @@ class InitialValueSolver:
         for v, off, (tsh, shp) in zip(self.state, self.var_arena.offsets, self.var_arena.shapes):
             n = int(np.prod(tsh, dtype=int)) * int(np.prod(shp, dtype=int))
             self.state_views.append(self.state_t[off:off + n].view(tuple(tsh) + tuple(shp)))
-        from .evaluator import RHSPlan
-        self.rhs_plan = RHSPlan(self)
+        if self.curvilinear:
+            from .sphere import SphereRHSPlan
+            self.rhs_plan = SphereRHSPlan(self)
+        else:
+            from .evaluator import RHSPlan
+            self.rhs_plan = RHSPlan(self)
         self.rhs_plan.set_static(self.eq_t)
         self.bset = None
         self._device_ready = True
@@ -389,7 +400,12 @@ class InitialValueSolver:
             self.slot_F = deque(1 + cls.amax + cls.bmax + j for j in range(cls.cmax))
             nslots = 1 + cls.amax + cls.bmax + cls.cmax
             nlu = 1
-        self.bset = BatchSet(self, a0, b0, nslots, nlu)
+        if self.curvilinear:
+            from .sphere import SphereSystems
+            self.bset = SphereSystems(self, nslots, nlu)
+            self.total_modes = self.bset.total_modes
+        else:
+            self.bset = BatchSet(self, a0, b0, nslots, nlu)
 
     def _sync_state_to_device(self):
         """Make the state arena hold the current coefficient data of every variable (uploads host edits)."""

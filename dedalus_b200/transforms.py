@@ -407,6 +407,10 @@ class SWSHColatitudeTransform:
         self._dev[key] = prog
         return prog
 
+    def matrix_bytes(self):
+        """Bytes of the per-m matrices one application streams (one direction): sum over m of Ntheta * (Lmax + 1 - m) * 8."""
+        return 8 * sum(self.Ntheta * (self.Lmax + 1 - abs(r[0])) for r in self.m_maps if abs(r[0]) <= self.Lmax)
+
     @staticmethod
     def _reduced(t, axis):
         """(N0, N1, N2, N3) view with N1 = axis - 1, N2 = axis (reference reduced_view_4, tools/array.py)."""
@@ -466,6 +470,9 @@ def transform_field(field, layout):
     distributor.py:131-175, with an empty mesh); the multi-GPU chain with its transpose hop is handled by
     dedalus_b200/transposes.py."""
     torch = _torch()
+    from .sphere import sphere_basis_of, transform_sphere_field
+    if sphere_basis_of(field) is not None:
+        return transform_sphere_field(field, layout)
     if field.dist.size > 1:
         from .transposes import transform_field_distributed
         return transform_field_distributed(field, layout)

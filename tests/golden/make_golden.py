@@ -344,3 +344,86 @@ def gen_swsh():
 
 if __name__ == "__main__" and "swsh" in sys.argv[1:]:
     gen_swsh()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Sphere (S2) fields and the shallow-water IVP of examples/ivp_sphere_shallow_water (config 4)
+# ----------------------------------------------------------------------------------------------------------
+def shallow_water(Nphi, Ntheta, steps, scheme="RK222", dump_mats=(), dealias=3/2):
+    """The stock script's problem (examples/ivp_sphere_shallow_water/shallow_water.py:25-86) with the zonal-jet + height
+    perturbation initial condition evaluated analytically (the LBVP for the balanced height is not part of the IVP path)."""
+    meter = 1 / 6.37122e6; hour = 1; second = hour / 3600
+    R = 6.37122e6 * meter; Omega = 7.292e-5 / second; nu = 1e5 * meter**2 / second / 32**2
+    g = 9.80616 * meter / second**2; H = 1e4 * meter; timestep = 600 * second * min(1.0, 128 / Ntheta)
+    coords = d3.S2Coordinates('phi', 'theta')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    basis = d3.SphereBasis(coords, (Nphi, Ntheta), radius=R, dealias=dealias, dtype=np.float64)
+    u = dist.VectorField(coords, name='u', bases=basis)
+    h = dist.Field(name='h', bases=basis)
+    zcross = lambda A: d3.MulCosine(d3.skew(A))
+    phi, theta = dist.local_grids(basis)
+    lat = np.pi / 2 - theta + 0*phi
+    umax = 80 * meter / second
+    lat0 = np.pi / 7; lat1 = np.pi / 2 - lat0
+    en = np.exp(-4 / (lat1 - lat0)**2)
+    jet = (lat0 <= lat) * (lat <= lat1)
+    u_jet = umax / en * np.exp(1 / (lat[jet] - lat0) / (lat[jet] - lat1))
+    u['g'][0][jet] = u_jet
+    lat2 = np.pi / 4; hpert = 120 * meter; alpha = 1 / 3; beta = 1 / 15
+    h['g'] += hpert * np.cos(lat) * np.exp(-(phi/alpha)**2) * np.exp(-((lat2-lat)/beta)**2)
+    out = dict(u0=u['c'].copy(), h0=h['c'].copy(), meta=np.array([Nphi, Ntheta, dealias, steps, timestep]))
+    problem = d3.IVP([u, h], namespace=locals())
+    problem.add_equation("dt(u) + nu*lap(lap(u)) + g*grad(h) + 2*Omega*zcross(u) = - u@grad(u)")
+    problem.add_equation("dt(h) + nu*lap(lap(h)) + H*div(u) = - div(h*u)")
+    solver = problem.build_solver(getattr(d3, scheme))
+    for sp in solver.subproblems:
+        m = sp.group[0]
+        if m in dump_mats:
+            nat = natural_matrices(sp)
+            for name in ("M", "L"):
+                out[f"m{m}_{name}"] = nat[name].toarray()
+    for i in range(steps):
+        solver.step(timestep)
+    out.update(u1=u['c'].copy(), h1=h['c'].copy())
+    return out
+
+
+def gen_sphere():
+    """(1) random grid data of scalar / vector / rank-2 fields -> coefficients -> grid through the reference's own transform
+    chain (azimuthal FFT, spin recombination, SWSH colatitude transform) incl. the folded triangular packing with shift > 0;
+    (2) shallow-water states after K steps at 16 x 8 (RK222, with three pencil matrices), 32 x 16 (RK222 and SBDF2);
+    (3) config 4's size (512 x 256, Lmax = 254): checksums and one m-line of the state after 3 RK222 steps."""
+    out = {}
+    for tag, (Nphi, Ntheta, dealias) in dict(a=(16, 8, 1.5), b=(32, 24, 1.0)).items():
+        coords = d3.S2Coordinates('phi', 'theta')
+        dist = d3.Distributor(coords, dtype=np.float64)
+        basis = d3.SphereBasis(coords, (Nphi, Ntheta), radius=1.7, dealias=dealias, dtype=np.float64)
+        phi, theta = dist.local_grids(basis, scales=(dealias, dealias))
+        out[f"f{tag}_meta"] = np.array([Nphi, Ntheta, dealias])
+        out[f"f{tag}_phi"] = phi.ravel(); out[f"f{tag}_theta"] = theta.ravel()
+        rng = np.random.default_rng(5)
+        for name, f in (("s", dist.Field(bases=basis)), ("v", dist.VectorField(coords, bases=basis)),
+                        ("t", dist.TensorField((coords, coords), bases=basis))):
+            f.preset_scales(dealias)
+            g = rng.standard_normal(f['g'].shape)
+            f['g'] = g
+            c = f['c'].copy()
+            g2 = f['g'].copy()
+            out[f"f{tag}_{name}_gin"] = g; out[f"f{tag}_{name}_c"] = c; out[f"f{tag}_{name}_g2"] = g2
+    for tag, kw in dict(sw16=dict(Nphi=16, Ntheta=8, steps=3, dump_mats=(0, 1, 5)), sw32=dict(Nphi=32, Ntheta=16, steps=5),
+                        sw32sbdf2=dict(Nphi=32, Ntheta=16, steps=6, scheme="SBDF2")).items():
+        for k, v in shallow_water(**kw).items():
+            out[f"{tag}_{k}"] = v
+    big = shallow_water(512, 256, 3)
+    out["sw512_meta"] = big["meta"]
+    for name in ("u", "h"):
+        a = big[name + "1"]
+        out[f"sw512_{name}1_sumsq"] = np.array(np.sum(a.astype(np.longdouble)**2), dtype=np.float64)
+        out[f"sw512_{name}1_absmax"] = np.abs(a).max()
+        out[f"sw512_{name}1_rows"] = a[..., 20:24, :].copy()        # m = 10, 11 (and the folded partners 245, 244)
+    np.savez_compressed(HERE / "sphere.npz", **out)
+    print({k: getattr(v, 'shape', v) for k, v in out.items() if 'meta' in k or 'sumsq' in k})
+
+
+if __name__ == "__main__" and "sphere" in sys.argv[1:]:
+    gen_sphere()

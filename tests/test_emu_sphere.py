@@ -1,0 +1,51 @@
+"""Sphere (S2) path -- SphereBasis, spin recombination, SWSH transforms, per-m banded pencil systems, RHS plan -- executed
+on the CPU through the test-only kernel emulation against reference data; GPU versions: tests/test_gpu_2_sphere.py."""
+import ctypes as C
+import numpy as np, pytest
+from emu import emu_lib as E
+import sphere_cases as S
+
+
+@pytest.fixture(autouse=True)
+def emulation():
+    E.install()
+    yield
+    E.uninstall()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_sphere_field_transforms(golden, tag):
+    S.check_field_transforms(golden("sphere.npz"), tag)
+
+
+def test_sphere_pencil_matrices(golden):
+    S.check_pencil_matrices(golden("sphere.npz"))
+
+
+@pytest.mark.parametrize("tag,scheme", [("sw16", "RK222"), ("sw32", "RK222"), ("sw32sbdf2", "SBDF2")])
+def test_shallow_water_matches_reference(golden, tag, scheme):
+    sw, solver = S.check_shallow_water(golden("sphere.npz"), tag, scheme)
+    assert solver.bset.last_verify < 1e-12
+
+
+class _EmuArrays:
+    """numpy arrays + the emulated library, behind the small interface sphere_cases.check_banded_* use."""
+    lib = property(lambda self: E.emu())
+    stream = None
+
+    def dev(self, a):
+        return np.ascontiguousarray(a)
+
+    def ptr(self, a):
+        return E.ptr(a)
+
+    def host(self, a):
+        return a
+
+
+def test_banded_kernels_against_dense_solves():
+    S.check_banded_kernels(_EmuArrays())
+
+
+def test_banded_factor_flags_singular_system():
+    S.check_banded_singular(_EmuArrays())
