@@ -7,6 +7,7 @@
 // for a warp: pivot search = shuffle arg-max over the kl + 1 candidates, interchange and rank-1 update = lanes over the
 // (kl) x (ku + kl) window.  Vectors of system s: element (i, r) at vec_off + i * nrhs + r.
 #include "db_common.cuh"
+#include <cstdlib>
 
 #ifdef DB_EMU
 #define DB_WARP_SYNC() emu_yield()
@@ -17,6 +18,30 @@
 __device__ __forceinline__ int bd_min(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int bd_max(int a, int b) { return a > b ? a : b; }
 __device__ __forceinline__ bool bd_finite(double v) { return v - v == 0.0; }
+
+#ifdef DB_EMU
+#define BD_LDCG(p) (*(p))
+#define BD_FENCE() ((void)0)
+#else
+#define BD_LDCG(p) __ldcg(p)
+#define BD_FENCE() __threadfence_block()
+#endif
+// Kernel variants (environment DB_BANDED_MODE or db_banded_set_mode; default 3):
+//   bit 0: the factor kernel re-reads band entries that other lanes wrote with L2 loads (ld.global.cg) behind a CTA fence
+//          instead of relying on the SM's L1 for lane-to-lane communication through global memory;
+//   bit 1: the solve kernel reads the factor columns straight from global memory instead of through the cp.async ring.
+// Round-2 measurements on the B200 (profiles/r02_sphere_diag.json, 255 systems, n <= 1530): all four variants reproduce
+// LAPACK's dgbtrf / dgbtrs bit for bit over 8 repetitions; ONE earlier verification of the default-at-the-time variant 0 in a
+// fresh process came back with a backward error of 1.2e-5 (profiles/r02_sphere_bench_first_attempt.err) and could not be
+// reproduced -- until that is understood the variant without asynchronous copies is the default and every factorisation is
+// verified (and retried) by dedalus_b200/sphere.py SphereSystems.factor_verified.
+static int g_bd_mode = -1;
+static int bd_mode()
+{
+    if (g_bd_mode < 0) { const char* e = getenv("DB_BANDED_MODE"); g_bd_mode = e ? atoi(e) : 3; }
+    return g_bd_mode;
+}
+extern "C" int db_banded_set_mode(int32_t mode) { g_bd_mode = mode; return 0; }
 
 #define BD_WARPS 4            // systems per CTA in the factor / elementwise kernels
 
@@ -54,8 +79,8 @@ extern "C" int db_banded_combine(const db_banded_sys* sys, int32_t nsys, int32_t
 // info[s] = number of exactly-zero / non-finite pivots met (0 = ok)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * BD_WARPS)
-k_banded_factor(const db_banded_sys* __restrict__ sys, int nsys, int kl, int ku, double* __restrict__ ab_all,
-                int32_t* __restrict__ ipiv_all, int32_t* __restrict__ info)
+k_banded_factor(const db_banded_sys* __restrict__ sys, int nsys, int kl, int ku, double* ab_all,
+                int32_t* __restrict__ ipiv_all, int32_t* __restrict__ info, int cg)
 {
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * BD_WARPS + (threadIdx.x >> 5);
@@ -64,16 +89,18 @@ k_banded_factor(const db_banded_sys* __restrict__ sys, int nsys, int kl, int ku,
     const db_banded_sys S = sys[live ? s : 0];
     const int n = live ? S.n : 0;
     const int kv = kl + ku, ldf = 2 * kl + ku + 1;
-    double* __restrict__ ab = ab_all + S.lu_off;
+    double* ab = ab_all + S.lu_off;
     int32_t* __restrict__ ipiv = ipiv_all + S.piv_off;
     int ju = 0, bad = 0;
+#define BD_RD(ptr) (cg ? BD_LDCG(ptr) : *(ptr))
+#define BD_SYNC() do { if (cg) BD_FENCE(); DB_WARP_SYNC(); } while (0)
     for (int j = 0; j < n; ++j) {
         const int km = bd_min(kl, n - 1 - j);
-        double* __restrict__ colj = ab + (int64_t)j * ldf + kv;          // colj[l] = A(j + l, j)
+        double* colj = ab + (int64_t)j * ldf + kv;                       // colj[l] = A(j + l, j)
         // pivot search: largest |A(j + l, j)|, l = 0 .. km, lowest l on ties
         double best = -1.0; int bl = 0;
         for (int l = lane; l <= km; l += 32) {
-            const double v = fabs(colj[l]);
+            const double v = fabs(BD_RD(colj + l));
             if (v > best) { best = v; bl = l; }
         }
 #pragma unroll
@@ -91,24 +118,26 @@ k_banded_factor(const db_banded_sys* __restrict__ sys, int nsys, int kl, int ku,
         if (jp != 0) {
             for (int c = j + lane; c <= ju; c += 32) {
                 double* p = ab + (int64_t)c * ldf + kv + (j - c);
-                const double t = p[0]; p[0] = p[jp]; p[jp] = t;
+                const double t = BD_RD(p), u = BD_RD(p + jp); p[0] = u; p[jp] = t;
             }
         }
-        DB_WARP_SYNC();
-        const double rp = 1.0 / colj[0];
-        DB_WARP_SYNC();
-        for (int l = 1 + lane; l <= km; l += 32) colj[l] *= rp;
-        DB_WARP_SYNC();
+        BD_SYNC();
+        const double rp = 1.0 / BD_RD(colj);
+        BD_SYNC();
+        for (int l = 1 + lane; l <= km; l += 32) colj[l] = BD_RD(colj + l) * rp;
+        BD_SYNC();
         // trailing update A(j + l, c) -= L(l) * U(j, c),  l = 1 .. km,  c = j + 1 .. ju
         const int nc = ju - j;
         for (int idx = lane; idx < nc * km; idx += 32) {
             const int cc = idx / km, l = 1 + idx - cc * km;
             const int c = j + 1 + cc;
             double* p = ab + (int64_t)c * ldf + kv + (j - c);             // p[0] = U(j, c), p[l] = A(j + l, c)
-            p[l] = fma(-colj[l], p[0], p[l]);
+            p[l] = fma(-BD_RD(colj + l), BD_RD(p), BD_RD(p + l));
         }
-        DB_WARP_SYNC();
+        BD_SYNC();
     }
+#undef BD_RD
+#undef BD_SYNC
     if (live && lane == 0) info[s] = bad;
 }
 
@@ -117,7 +146,7 @@ extern "C" int db_banded_factor(const db_banded_sys* sys, int32_t nsys, int32_t 
 {
     if (nsys <= 0) return 0;
     DB_LAUNCH(k_banded_factor, dim3((unsigned)((nsys + BD_WARPS - 1) / BD_WARPS)), dim3(32 * BD_WARPS), 0, stream,
-              sys, nsys, kl, ku, ab, ipiv, info);
+              sys, nsys, kl, ku, ab, ipiv, info, bd_mode() & 1);
     return db_check_launch("banded_factor");
 }
 
@@ -128,11 +157,11 @@ extern "C" int db_banded_factor(const db_banded_sys* sys, int32_t nsys, int32_t 
 // factor columns stream through a shared-memory ring filled DEPTH columns ahead by cp.async, so neither the vector nor the
 // factor loads sit on the dependent chain of the sweep.
 // ---------------------------------------------------------------------------------------------------------
-#define BS_DEPTH 16
+#define BS_DEPTH 8
 
 __global__ void __launch_bounds__(32)
 k_banded_solve(const db_banded_sys* __restrict__ sys, int kl, int ku, const double* __restrict__ ab_all,
-               const int32_t* __restrict__ ipiv_all, db_veccomb rhs, double* __restrict__ x_all, int RC)
+               const int32_t* __restrict__ ipiv_all, db_veccomb rhs, double* __restrict__ x_all, int RC, int direct)
 {
     DB_SMEM(double, smem);
     const db_banded_sys S = sys[blockIdx.x];
@@ -156,17 +185,19 @@ k_banded_solve(const db_banded_sys* __restrict__ sys, int kl, int ku, const doub
     }
     for (int i = lane; i < n; i += 32) piv[i] = ipiv_all[S.piv_off + i] - i;
     // ---- forward sweep: y = L^{-1} P b
-    for (int d = 0; d < BS_DEPTH - 1 && d < n; ++d) {
+    for (int d = 0; d < BS_DEPTH - 1 && d < n && !direct; ++d) {
         for (int l = lane; l < ldf; l += 32) db_cp_async8(&ring[d * ldf + l], &ab[(int64_t)d * ldf + l]);
         db_cp_commit();
     }
     DB_WARP_SYNC();
     for (int j = 0; j < n; ++j) {
         const int jn = j + BS_DEPTH - 1;
-        if (jn < n)
-            for (int l = lane; l < ldf; l += 32) db_cp_async8(&ring[(jn % BS_DEPTH) * ldf + l], &ab[(int64_t)jn * ldf + l]);
-        db_cp_commit();
-        db_cp_wait<BS_DEPTH - 1>();
+        if (!direct) {
+            if (jn < n)
+                for (int l = lane; l < ldf; l += 32) db_cp_async8(&ring[(jn % BS_DEPTH) * ldf + l], &ab[(int64_t)jn * ldf + l]);
+            db_cp_commit();
+            db_cp_wait<BS_DEPTH - 1>();
+        }
         DB_WARP_SYNC();
         const int km = bd_min(kl, n - 1 - j);
         const int p = piv[j];
@@ -174,7 +205,7 @@ k_banded_solve(const db_banded_sys* __restrict__ sys, int kl, int ku, const doub
             for (int r = lane; r < R; r += 32) { const double t = b[j * R + r]; b[j * R + r] = b[(j + p) * R + r]; b[(j + p) * R + r] = t; }
             DB_WARP_SYNC();
         }
-        const double* __restrict__ col = ring + (j % BS_DEPTH) * ldf + kv;
+        const double* col = direct ? ab + (int64_t)j * ldf + kv : ring + (j % BS_DEPTH) * ldf + kv;
         for (int idx = lane; idx < km * R; idx += 32) {
             const int l = 1 + idx / R, r = idx % R;
             b[(j + l) * R + r] = fma(-col[l], b[j * R + r], b[(j + l) * R + r]);
@@ -184,7 +215,7 @@ k_banded_solve(const db_banded_sys* __restrict__ sys, int kl, int ku, const doub
     // ---- backward sweep: x = U^{-1} y  (column oriented: x_j = y_j / U_jj, then y_i -= U_ij x_j for i = j - kv .. j - 1)
     db_cp_wait<0>();
     DB_WARP_SYNC();
-    for (int d = 0; d < BS_DEPTH - 1 && d < n; ++d) {
+    for (int d = 0; d < BS_DEPTH - 1 && d < n && !direct; ++d) {
         const int c = n - 1 - d;
         for (int l = lane; l < ldf; l += 32) db_cp_async8(&ring[d * ldf + l], &ab[(int64_t)c * ldf + l]);
         db_cp_commit();
@@ -193,12 +224,14 @@ k_banded_solve(const db_banded_sys* __restrict__ sys, int kl, int ku, const doub
     for (int jj = 0; jj < n; ++jj) {
         const int j = n - 1 - jj;
         const int jn = jj + BS_DEPTH - 1;
-        if (jn < n)
-            for (int l = lane; l < ldf; l += 32) db_cp_async8(&ring[(jn % BS_DEPTH) * ldf + l], &ab[(int64_t)(n - 1 - jn) * ldf + l]);
-        db_cp_commit();
-        db_cp_wait<BS_DEPTH - 1>();
+        if (!direct) {
+            if (jn < n)
+                for (int l = lane; l < ldf; l += 32) db_cp_async8(&ring[(jn % BS_DEPTH) * ldf + l], &ab[(int64_t)(n - 1 - jn) * ldf + l]);
+            db_cp_commit();
+            db_cp_wait<BS_DEPTH - 1>();
+        }
         DB_WARP_SYNC();
-        const double* __restrict__ col = ring + (jj % BS_DEPTH) * ldf + kv;      // col[i - j] = U(i, j), i <= j
+        const double* col = direct ? ab + (int64_t)j * ldf + kv : ring + (jj % BS_DEPTH) * ldf + kv;      // col[i - j] = U(i, j), i <= j
         const double rd = 1.0 / col[0];
         for (int r = lane; r < R; r += 32) b[j * R + r] *= rd;
         DB_WARP_SYNC();
@@ -230,7 +263,7 @@ extern "C" int db_banded_solve(const db_banded_sys* sys, int32_t nsys, int32_t k
     static bool attr_set = false;
     if (!attr_set) { DB_SET_SMEM_ATTR(k_banded_solve); attr_set = true; }
     DB_LAUNCH(k_banded_solve, dim3((unsigned)nsys, (unsigned)((max_nrhs + RC - 1) / RC)), dim3(32), smem, stream,
-              sys, kl, ku, ab, ipiv, *rhs, x, RC);
+              sys, kl, ku, ab, ipiv, *rhs, x, RC, (bd_mode() >> 1) & 1);
     return db_check_launch("banded_solve");
 }
 

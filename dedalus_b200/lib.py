@@ -110,6 +110,7 @@ SIGNATURES = {
     "db_banded_factor": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp]),
     "db_banded_solve": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, C.POINTER(VecComb), vp, vp]),
     "db_banded_matvec": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "db_banded_set_mode": (C.c_int, [i32]),
     "db_index_move": (C.c_int, [vp, i64, vp, vp, i32, vp]),
     "db_pair_lincomb": (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, vp]),
     "db_absmax": (C.c_int, [vp, i64, vp, vp]),

@@ -664,15 +664,21 @@ class SphereSystems:
         s_b, s_x, s_m, s_l = slots
         worst = 0.0
         for lu_slot, a0, b0 in lhs:
-            self.factor(lu_slot, a0, b0)
-            self.check_info()
-            gen = torch.Generator(device=self.solver.device); gen.manual_seed(1234)
-            self.vecs[s_b].normal_(generator=gen)
-            self.solve(lu_slot, s_x, [(s_b, 1.0)])
-            self.matvec(s_x, s_m, s_l)
-            b, mx, lx = self.vecs[s_b], self.vecs[s_m], self.vecs[s_l]
-            r = (a0 * mx + b0 * lx - b).abs().max() / (b.abs().max() + (a0 * mx).abs().max() + (b0 * lx).abs().max())
-            worst = max(worst, float(r))
+            for attempt in range(3):
+                self.factor(lu_slot, a0, b0)
+                self.check_info()
+                gen = torch.Generator(device=self.solver.device); gen.manual_seed(1234)
+                self.vecs[s_b].normal_(generator=gen)
+                self.solve(lu_slot, s_x, [(s_b, 1.0)])
+                self.matvec(s_x, s_m, s_l)
+                b, mx, lx = self.vecs[s_b], self.vecs[s_m], self.vecs[s_l]
+                r = float((a0 * mx + b0 * lx - b).abs().max() / (b.abs().max() + (a0 * mx).abs().max() + (b0 * lx).abs().max()))
+                if r <= self.VERIFY_TOL:
+                    break
+                import warnings
+                warnings.warn(f"sphere pencil factorisation: backward error {r:.2e} on attempt {attempt + 1}; factorising again")
+                self.reorders += 1
+            worst = max(worst, r)
         self.last_verify = worst
         if not worst <= self.VERIFY_TOL:
             raise DedalusB200Error(f"sphere pencil factorisation failed verification: backward error {worst:.2e}")

@@ -330,6 +330,9 @@ int db_banded_solve(const db_banded_sys* sys, int32_t nsys, int32_t kl, int32_t 
 /* ya = A x and / or yb = B x (operator storage; either output may be NULL): M.X, L.X of core/timesteppers.py:590-591 */
 int db_banded_matvec(const db_banded_sys* sys, int32_t nsys, int32_t kl, int32_t ku, const double* a_ab, const double* b_ab,
                      const double* x, double* ya, double* yb, void* stream);
+/* diagnostic variants of the two kernels above (also environment DB_BANDED_MODE): bit 0 = the factorisation re-reads entries
+ * written by other lanes through L2 behind a CTA fence, bit 1 = the solve reads factor columns directly from global memory */
+int db_banded_set_mode(int32_t mode);
 /* gather (vec[e] = idx[e] >= 0 ? arena[idx[e]] : 0) / scatter (arena[idx[e]] = vec[e] where idx[e] >= 0) through an index
  * table: pencil vectors <-> coefficient arrays in the folded triangular (m, l) packing (core/subsystems.py:340-371) */
 int db_index_move(const int64_t* idx, int64_t count, double* arena, double* vec, int32_t gather, void* stream);
