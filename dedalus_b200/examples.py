@@ -106,3 +106,30 @@ def shallow_water_initial_condition(u, h, basis, units):
     alpha = 1 / 3
     beta = 1 / 15
     h['g'] += hpert * np.cos(lat) * np.exp(-(phi / alpha)**2) * np.exp(-((lat2 - lat) / beta)**2)
+
+
+def complex_ginzburg_landau(Nx=16, Nz=12, dealias=3/2):
+    """Complex-dtype test problem (T3): ComplexFourier x ChebyshevT in complex128 with complex LHS coefficients, an advective and a
+    cubic term (tests/golden/make_golden.py complex_cgl runs the same script through the reference)."""
+    coords = d3.CartesianCoordinates('x', 'z')
+    dist = d3.Distributor(coords, dtype=np.complex128)
+    xb = d3.ComplexFourier(coords['x'], size=Nx, bounds=(0, 2 * np.pi), dealias=dealias)
+    zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, 1), dealias=dealias)
+    u = dist.Field(name='u', bases=(xb, zb))
+    tau1 = dist.Field(name='tau1', bases=xb)
+    tau2 = dist.Field(name='tau2', bases=xb)
+    lift_basis = zb.derivative_basis(2)
+    lift = lambda A, n: d3.Lift(A, lift_basis, n)
+    dx = lambda A: d3.Differentiate(A, coords['x'])
+    c1, c2 = 0.3 + 0.2j, 1.0 - 0.5j
+    problem = d3.IVP([u, tau1, tau2], namespace=locals())
+    problem.add_equation("dt(u) - c1*lap(u) + (0.5j)*dx(u) + lift(tau1,-1) + lift(tau2,-2) = - c2*u*dx(u) + u*u*u")
+    problem.add_equation("u(z=0) = 0")
+    problem.add_equation("u(z=1) = 0")
+    return dict(problem=problem, dist=dist, u=u, tau1=tau1, tau2=tau2, bases=(xb, zb))
+
+
+def complex_ginzburg_landau_initial_condition(u, bases):
+    x, z = u.dist.local_grids(*bases)
+    u.fill_random('g', seed=3, distribution='normal', scale=0.1)
+    u['g'] *= z * (1 - z)

@@ -88,6 +88,11 @@ class PencilSystemBuilder:
         self.entry_cutoff = entry_cutoff
         self.variables = problem.variables
         self.equations = problem.equations
+        # complex-dtype problems (T3): every complex unknown is carried as two real ones.  The real / imaginary PLANES of a
+        # field are the leading tensor index of its arena entry, so all kernels see ordinary real coefficient arrays, and a
+        # complex operator block B becomes [[Re B, -Im B], [Im B, Re B]] (the reference solves complex pencils in complex
+        # arithmetic, libraries/matsolvers.py:126-183 on complex128 matrices).
+        self.complex = bool(np.issubdtype(problem.dtype, np.complexfloating))
         # separable bases (one per separable axis), taken from the variables
         self.sep_bases = []
         for ax in self.sep_axes:
@@ -153,8 +158,7 @@ class PencilSystemBuilder:
 
     # ---------------------------------------------------------------------------------------------
     def _assemble_class(self, cls):
-        var_items = [(v.tshape, v.bases) for v in self.variables]
-        eq_items = [(tuple(cs.dim for cs in eq['tensorsig']), eq['bases']) for eq in self.equations]
+        var_items, eq_items = self.arena_items()
         cls.col_slots, cls.col_off, ncols = _enumerate_slots(var_items, self.sep_axes, cls.zero_axes, self.last_axis)
         cls.row_slots, cls.row_off, nrows = _enumerate_slots(eq_items, self.sep_axes, cls.zero_axes, self.last_axis)
         cls.shape = (nrows, ncols)
@@ -209,7 +213,10 @@ class PencilSystemBuilder:
                         K = sparse.csr_matrix(t.comp)
                         for _, A in combo:
                             K = sparse.kron(K, sparse.csr_matrix(A), format='csr')
-                        blk = (t.coef * sparse.kron(K, Z, format='csr')).tocoo()
+                        blk = (t.coef * sparse.kron(K, Z, format='csr'))
+                        if self.complex:
+                            blk = sparse.bmat([[blk.real, -blk.imag], [blk.imag, blk.real]], format='csr')
+                        blk = blk.tocoo()
                         if blk.shape != (r1 - r0, c1 - c0):
                             raise RuntimeError(f"Template block shape mismatch: {blk.shape} vs {(r1 - r0, c1 - c0)}")
                         full = sparse.coo_matrix((blk.data, (blk.row + r0, blk.col + c0)), shape=cls.shape).tocsr()
@@ -235,10 +242,17 @@ class PencilSystemBuilder:
             raise ValueError(f"Non-square pencil system for class zero_axes={cls.zero_axes}: "
                              f"{int(cls.valid_rows.sum())} equations vs {int(cls.valid_cols.sum())} unknowns.")
 
+    def arena_items(self):
+        """(tensor shape, bases) of every variable / equation as stored in the solver's arenas (complex: leading re / im index)."""
+        lead = (2,) if self.complex else ()
+        var_items = [(lead + tuple(v.tshape), v.bases) for v in self.variables]
+        eq_items = [(lead + tuple(cs.dim for cs in eq['tensorsig']), eq['bases']) for eq in self.equations]
+        return var_items, eq_items
+
     # ---------------------------------------------------------------------------------------------
     def monomial_values(self, cls, mono, groups=None):
         groups = cls.groups if groups is None else groups
-        val = np.ones(len(groups), dtype=self.problem.dtype if np.issubdtype(self.problem.dtype, np.complexfloating) else np.float64)
+        val = np.ones(len(groups), dtype=np.float64)
         for i, ax in enumerate(self.sep_axes):
             if mono[i]:
                 val = val * self.group_wavenumber(ax, groups[:, i]) ** mono[i]

@@ -337,8 +337,10 @@ class InitialValueSolver:
         else:
             self.builder = PencilSystemBuilder(problem, entry_cutoff=entry_cutoff)
             self.batches = build_batches(self.builder)
-        self.var_arena = Arena(self.dist, [(v.tshape, v.bases) for v in problem.variables])
-        self.eq_arena = Arena(self.dist, [(tuple(cs.dim for cs in eq['tensorsig']), eq['bases']) for eq in problem.equations])
+        self.complex = bool(np.issubdtype(self.dtype, np.complexfloating))
+        lead = (2,) if self.complex else ()      # complex fields live in the arenas as a real and an imaginary plane (pencils.py)
+        self.var_arena = Arena(self.dist, [(lead + tuple(v.tshape), v.bases) for v in problem.variables])
+        self.eq_arena = Arena(self.dist, [(lead + tuple(cs.dim for cs in eq['tensorsig']), eq['bases']) for eq in problem.equations])
         self.total_modes = 0 if self.curvilinear else sum(int(c.valid_cols.sum()) * len(c.groups) for c in self.builder.classes.values())
         self.setup_time = time.time() - t0
         self._device_ready = False
@@ -363,8 +365,8 @@ class InitialValueSolver:
         self.device = compute_device()        # raises without a CUDA device: no CPU fallback
         self.lib = get_lib()
         self.dist.device = self.device
-        if np.issubdtype(self.dtype, np.complexfloating):
-            raise NotImplementedError("complex-dtype IVPs run through the complex pencil path (not in this build)")
+        if self.complex and (self.curvilinear or self.dist.size > 1):
+            raise NotImplementedError("complex-dtype problems are single-GPU Cartesian in this build")
         self.state_t = torch.zeros(self.var_arena.size, dtype=torch.float64, device=self.device)
         self.eq_t = torch.zeros(self.eq_arena.size, dtype=torch.float64, device=self.device)
         self.state_views = []
@@ -374,6 +376,9 @@ class InitialValueSolver:
         if self.curvilinear:
             from .sphere import SphereRHSPlan
             self.rhs_plan = SphereRHSPlan(self)
+        elif self.complex:
+            from .complex_path import ComplexRHSPlan
+            self.rhs_plan = ComplexRHSPlan(self)
         else:
             from .evaluator import RHSPlan
             self.rhs_plan = RHSPlan(self)
@@ -409,9 +414,13 @@ class InitialValueSolver:
 
     def _sync_state_to_device(self):
         """Make the state arena hold the current coefficient data of every variable (uploads host edits)."""
+        import torch
         for v, view in zip(self.state, self.state_views):
             v.change_layout('c')
             dev = v.device_data()
+            if self.complex:
+                view.copy_(torch.view_as_real(dev).movedim(-1, 0))      # interleaved complex field -> re / im planes
+                continue
             if dev.data_ptr() != view.data_ptr():
                 view.copy_(dev.reshape(view.shape))
                 v.set_device_data(view, 'c')
@@ -421,7 +430,11 @@ class InitialValueSolver:
         # RHS evaluation (core/evaluator.py:116-133), so e.g. u['g'] returns the dealiased grid unless the user
         # calls change_scales(1) first (as the stock scripts do)
         for v, view in zip(self.state, self.state_views):
-            v.set_device_data(view, 'c', scales=v.dealias)
+            if self.complex:
+                import torch
+                v.set_device_data(torch.complex(view[0], view[1]), 'c', scales=v.dealias)
+            else:
+                v.set_device_data(view, 'c', scales=v.dealias)
 
     def _check_factor_info(self):
         self.bset.check_info()

@@ -427,3 +427,46 @@ def gen_sphere():
 
 if __name__ == "__main__" and "sphere" in sys.argv[1:]:
     gen_sphere()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Complex-dtype pencil path (T3): ComplexFourier x ChebyshevT in complex128, complex LHS coefficients, cubic RHS
+# ----------------------------------------------------------------------------------------------------------
+def complex_cgl(scheme, steps, tstep=1e-3, Nx=16, Nz=12):
+    coords = d3.CartesianCoordinates('x', 'z')
+    dist = d3.Distributor(coords, dtype=np.complex128)
+    xb = d3.ComplexFourier(coords['x'], size=Nx, bounds=(0, 2 * np.pi), dealias=3/2)
+    zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, 1), dealias=3/2)
+    u = dist.Field(name='u', bases=(xb, zb))
+    tau1 = dist.Field(name='tau1', bases=xb)
+    tau2 = dist.Field(name='tau2', bases=xb)
+    lift_basis = zb.derivative_basis(2)
+    lift = lambda A, n: d3.Lift(A, lift_basis, n)
+    dx = lambda A: d3.Differentiate(A, coords['x'])
+    c1, c2 = 0.3 + 0.2j, 1.0 - 0.5j
+    x, z = dist.local_grids(xb, zb)
+    u.fill_random('g', seed=3, distribution='normal', scale=0.1)
+    u['g'] *= z * (1 - z)
+    out = dict(u0=u['c'].copy(), meta=np.array([Nx, Nz, steps, tstep]))
+    problem = d3.IVP([u, tau1, tau2], namespace=locals())
+    problem.add_equation("dt(u) - c1*lap(u) + (0.5j)*dx(u) + lift(tau1,-1) + lift(tau2,-2) = - c2*u*dx(u) + u*u*u")
+    problem.add_equation("u(z=0) = 0")
+    problem.add_equation("u(z=1) = 0")
+    solver = problem.build_solver(getattr(d3, scheme))
+    for i in range(steps):
+        solver.step(tstep)
+    out.update(u1=u['c'].copy(), tau1=tau1['c'].copy(), tau2=tau2['c'].copy())
+    return out
+
+
+def gen_complex():
+    out = {}
+    for tag, (scheme, steps) in dict(rk222=("RK222", 5), sbdf2=("SBDF2", 6)).items():
+        for k, v in complex_cgl(scheme, steps).items():
+            out[f"{tag}_{k}"] = v
+    np.savez_compressed(HERE / "complex_cgl.npz", **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__" and "complex" in sys.argv[1:]:
+    gen_complex()
