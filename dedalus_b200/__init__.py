@@ -2,11 +2,12 @@
 
 Public surface mirrors `dedalus.public` (reference dedalus/public.py:4-15) for the Cartesian IVP path.
 """
-from .coords import Coordinate, CartesianCoordinates, S2Coordinates
+from .coords import Coordinate, CartesianCoordinates, S2Coordinates, SphericalCoordinates
 from .distributor import Distributor
 from .basis import (RealFourier, ComplexFourier, Jacobi, Legendre, Ultraspherical,
                     ChebyshevT, ChebyshevU, ChebyshevV, Chebyshev)
 from .sphere import SphereBasis
+from .shell import ShellBasis
 from .field import Field
 from .operators import (Differentiate, Gradient, Divergence, Laplacian, Trace, TransposeComponents,
                         Interpolate, Integrate, Lift, Convert, TimeDerivative, DotProduct, Multiply, Skew, MulCosine,

@@ -111,3 +111,46 @@ class S2Coordinates:
     @classmethod
     def U_backward(cls, order=1):
         return cls.U_forward(order).T.conj()
+
+
+class SphericalCoordinates:
+    """Spherical coordinate system (azimuth, colatitude, radius); spin and regularity component ordering (-, +, 0)
+    (reference coords.py:313-385)."""
+    spin_ordering = (-1, +1, 0)
+    reg_ordering = (-1, +1, 0)
+    dim = 3
+    curvilinear = True
+
+    def __init__(self, azimuth, colatitude, radius):
+        self.names = (azimuth, colatitude, radius)
+        self.azimuth = AzimuthalCoordinate(azimuth, cs=self)
+        self.colatitude = Coordinate(colatitude, cs=self)
+        self.radius = Coordinate(radius, cs=self)
+        self.S2coordsys = S2Coordinates(azimuth, colatitude)
+        self.coords = (self.azimuth, self.colatitude, self.radius)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.coords[self.names.index(key)]
+        return self.coords[key]
+
+    def __repr__(self):
+        return "{" + ",".join(self.names) + "}"
+
+    @classmethod
+    def U_forward(cls, order=1):
+        """Unitary map from coordinate (phi, theta, r) to spin (-, +, 0) components (reference coords.py:336-345)."""
+        Ui = {+1: np.array([+1j, 1, 0]) / np.sqrt(2), -1: np.array([-1j, 1, 0]) / np.sqrt(2), 0: np.array([0, 0, 1])}
+        U = np.array([Ui[s] for s in cls.spin_ordering])
+        out = U
+        for _ in range(order - 1):
+            out = np.kron(out, U)
+        return out
+
+    @classmethod
+    def U_backward(cls, order=1):
+        return cls.U_forward(order).T.conj()
+
+    @staticmethod
+    def cartesian(phi, theta, r):
+        return r * np.sin(theta) * np.cos(phi), r * np.sin(theta) * np.sin(phi), r * np.cos(theta)

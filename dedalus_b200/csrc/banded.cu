@@ -329,7 +329,8 @@ extern "C" int db_index_move(const int64_t* idx, int64_t count, double* arena, d
 // Complex linear combinations on (cos, -sin) pairs: arrays (ncomp, 2 * npair, ncol), a pair = two adjacent rows holding the
 // real and imaginary part of the coefficient of exp(i m phi) (core/basis.py:1108-1134).  For output component o
 //     out[o] = sum_{t in terms of o} (re_t + i im_t) * in[src_t]
-// where re_t / im_t are either constants or per-element symbol arrays of shape (npair, ncol) (sym_off >= 0).
+// where re_t / im_t are constants, optionally times a per-element symbol: syms[sym_off + (j * ncol + c) / sym_div] (sym_off >= 0;
+// sym_div > 1 when the symbol does not depend on the trailing sym_div entries of a row, e.g. the radial index of shell data).
 // Serves (a) the separable sphere operators in coefficient space -- gradient, divergence, Laplacian, skew: symbols
 // k(l, s, mu) per degree, core/basis.py:3299-3420, core/operators.py:2125-2160 -- and (b) the component <-> spin
 // recombination in (azimuthal coefficient, colatitude grid) space (libraries/spin_recombination.pyx:9-56,
@@ -337,7 +338,8 @@ extern "C" int db_index_move(const int64_t* idx, int64_t count, double* arena, d
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_pair_lincomb(const double* __restrict__ in, double* __restrict__ out, int64_t npair, int64_t ncol, int n_out,
-               const int32_t* __restrict__ term_ptr, const db_pair_lin_term* __restrict__ terms, const double* __restrict__ syms)
+               const int32_t* __restrict__ term_ptr, const db_pair_lin_term* __restrict__ terms, const double* __restrict__ syms,
+               int64_t sym_div)
 {
     const int64_t plane = 2 * npair * ncol;
     const int64_t total = npair * ncol;
@@ -349,7 +351,7 @@ k_pair_lincomb(const double* __restrict__ in, double* __restrict__ out, int64_t 
             for (int t = term_ptr[o]; t < term_ptr[o + 1]; ++t) {
                 const db_pair_lin_term T = terms[t];
                 double sr = T.re, si = T.im;
-                if (T.sym_off >= 0) { sr *= syms[T.sym_off + e]; si *= syms[T.sym_off + e]; }
+                if (T.sym_off >= 0) { const double sv = syms[T.sym_off + e / sym_div]; sr *= sv; si *= sv; }
                 const double xr = in[T.src * plane + o_re], xi = in[T.src * plane + o_im];
                 ar += sr * xr - si * xi;
                 ai += sr * xi + si * xr;
@@ -361,12 +363,13 @@ k_pair_lincomb(const double* __restrict__ in, double* __restrict__ out, int64_t 
 }
 
 extern "C" int db_pair_lincomb(const double* in, double* out, int64_t npair, int64_t ncol, int32_t n_out,
-                               const int32_t* term_ptr, const db_pair_lin_term* terms, const double* syms, void* stream)
+                               const int32_t* term_ptr, const db_pair_lin_term* terms, const double* syms, int64_t sym_div, void* stream)
 {
     const int64_t total = npair * ncol;
     if (total <= 0 || n_out <= 0) return 0;
+    if (sym_div < 1) sym_div = 1;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    DB_LAUNCH(k_pair_lincomb, dim3((unsigned)blocks), dim3(256), 0, stream, in, out, npair, ncol, n_out, term_ptr, terms, syms);
+    DB_LAUNCH(k_pair_lincomb, dim3((unsigned)blocks), dim3(256), 0, stream, in, out, npair, ncol, n_out, term_ptr, terms, syms, sym_div);
     return db_check_launch("pair_lincomb");
 }

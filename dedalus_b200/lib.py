@@ -112,7 +112,7 @@ SIGNATURES = {
     "db_banded_matvec": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "db_banded_set_mode": (C.c_int, [i32]),
     "db_index_move": (C.c_int, [vp, i64, vp, vp, i32, vp]),
-    "db_pair_lincomb": (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, vp]),
+    "db_pair_lincomb": (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, i64, vp]),
     "db_absmax": (C.c_int, [vp, i64, vp, vp]),
     "db_cfl_max": (C.c_int, [C.POINTER(vp), C.POINTER(vp), i32, i64, i64, i64, vp, vp]),
 }

@@ -258,10 +258,10 @@ class PairProgram:
         rows = [[(j, U[i, j], -1) for j in range(U.shape[1]) if U[i, j] != 0] for i in range(U.shape[0])]
         return cls(rows, device)
 
-    def apply(self, inp, out, npair, ncol):
+    def apply(self, inp, out, npair, ncol, sym_div=1):
         from .lib import get_lib, current_stream
         get_lib().call("db_pair_lincomb", inp.data_ptr(), out.data_ptr(), int(npair), int(ncol), self.n_out,
-                       self.ptr.data_ptr(), self.terms.data_ptr(), self.syms.data_ptr(), current_stream())
+                       self.ptr.data_ptr(), self.terms.data_ptr(), self.syms.data_ptr(), int(sym_div), current_stream())
 
 
 def sphere_basis_of(field_or_bases):

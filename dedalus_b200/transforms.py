@@ -473,6 +473,9 @@ def transform_field(field, layout):
     from .sphere import sphere_basis_of, transform_sphere_field
     if sphere_basis_of(field) is not None:
         return transform_sphere_field(field, layout)
+    from .shell import shell_basis_of, transform_shell_field
+    if shell_basis_of(field) is not None:
+        return transform_shell_field(field, layout)
     if field.dist.size > 1:
         from .transposes import transform_field_distributed
         return transform_field_distributed(field, layout)

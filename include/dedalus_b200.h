@@ -339,14 +339,16 @@ int db_index_move(const int64_t* idx, int64_t count, double* arena, double* vec,
 
 /* Complex linear combinations on (cos, -sin) pairs.  in / out: (ncomp, 2 * npair, ncol), rows 2j and 2j + 1 = real and
  * imaginary part of the exp(i m phi) coefficient (core/basis.py:1108-1134).  Output o = sum over its terms
- * term_ptr[o] <= t < term_ptr[o + 1] of (re + i im) * sym * in[src], sym = syms[sym_off + j * ncol + c] or 1 (sym_off < 0).
+ * term_ptr[o] <= t < term_ptr[o + 1] of (re + i im) * sym * in[src], sym = syms[sym_off + (j * ncol + c) / sym_div] or 1 (sym_off < 0);
+ * sym_div > 1 when the symbol is constant along the trailing sym_div entries of a row (the radial index of shell data: the
+ * regularity recombination Q(l) of core/basis.py:3590-3627).
  * Replaces (a) SeparableSphereOperator.operate -- SphereGradient / Divergence / Laplacian symbols k(l, s, mu) / R
  * (core/operators.py:2725-2866, core/basis.py:3299-3420) and SpinSkew (core/operators.py:2125-2160) in coefficient space,
  * (b) the component <-> spin recombination (libraries/spin_recombination.pyx:9-56 with U of core/coords.py:219-232) in
  * (azimuthal coefficient, colatitude grid) space.  in and out must not overlap. */
 typedef struct { double re, im; int64_t sym_off; int32_t src; int32_t pad; } db_pair_lin_term;
 int db_pair_lincomb(const double* in, double* out, int64_t npair, int64_t ncol, int32_t n_out,
-                    const int32_t* term_ptr, const db_pair_lin_term* terms, const double* syms, void* stream);
+                    const int32_t* term_ptr, const db_pair_lin_term* terms, const double* syms, int64_t sym_div, void* stream);
 
 /* max |x| reduction (CFL / flow properties; extras/flow_tools.py:33-37 before the Allreduce) */
 int db_absmax(const double* x, int64_t count, double* out, void* stream);

@@ -470,3 +470,36 @@ def gen_complex():
 
 if __name__ == "__main__" and "complex" in sys.argv[1:]:
     gen_complex()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Spherical-shell field transforms (T6: core/basis.py:4474-4508 on top of the sphere chain)
+# ----------------------------------------------------------------------------------------------------------
+def gen_shell():
+    """Random grid data of scalar / vector / rank-2 fields on a ShellBasis -> coefficients -> grid through the reference.
+    Case b has the folded (m, l) packing with shift > 0 and an ODD Lmax: for even Lmax and shift > 0 the reference's ell_maps merge
+    the m = 0 row and the folded rows of l = Lmax / 2 into one slice that also covers the rows of another degree, which then get
+    two regularity recombinations (a reference oddity, not reproduced).  Case c: a k = 1 (derivative) basis."""
+    out = {}
+    for tag, (shape, dealias, k) in dict(a=((16, 8, 6), 1.5, 0), b=((32, 23, 8), 1.0, 0), c=((16, 8, 6), 1.5, 1)).items():
+        coords = d3.SphericalCoordinates('phi', 'theta', 'r')
+        dist = d3.Distributor(coords, dtype=np.float64)
+        shell = d3.ShellBasis(coords, shape=shape, radii=(1.2, 2.7), dealias=dealias, dtype=np.float64, k=k)
+        phi, theta, r = dist.local_grids(shell, scales=(dealias,) * 3)
+        out[f"{tag}_meta"] = np.array(list(shape) + [dealias, k])
+        out[f"{tag}_phi"] = phi.ravel(); out[f"{tag}_theta"] = theta.ravel(); out[f"{tag}_r"] = r.ravel()
+        rng = np.random.default_rng(11)
+        for name, f in (("s", dist.Field(bases=shell)), ("v", dist.VectorField(coords, bases=shell)),
+                        ("t", dist.TensorField((coords, coords), bases=shell))):
+            f.preset_scales(dealias)
+            g = rng.standard_normal(f['g'].shape)
+            f['g'] = g
+            c = f['c'].copy()
+            g2 = f['g'].copy()
+            out[f"{tag}_{name}_gin"] = g; out[f"{tag}_{name}_c"] = c; out[f"{tag}_{name}_g2"] = g2
+    np.savez_compressed(HERE / "shell.npz", **out)
+    print({k: v.shape for k, v in out.items() if k.endswith("_c")})
+
+
+if __name__ == "__main__" and "shell" in sys.argv[1:]:
+    gen_shell()
