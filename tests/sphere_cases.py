@@ -187,3 +187,23 @@ def check_banded_singular(B):
     lu, ipiv, info = B.dev(np.zeros(16)), B.dev(np.zeros(4, dtype=np.int32)), B.dev(np.zeros(1, dtype=np.int32))
     B.lib.call("db_banded_factor", B.ptr(sysb), 1, 1, 1, B.ptr(lu), B.ptr(ipiv), B.ptr(info), B.stream)
     assert B.host(info)[0] == 4
+
+
+def check_against_oracle(Nphi, Ntheta, scheme, dts, seed=7):
+    """Random (smooth) initial state, a time-step sequence with changes (every change refactorises all per-m systems), against
+    oracle/sphere_oracle.py -- an independent complex, dense formulation pinned to the reference in tests/test_oracle.py."""
+    from oracle import sphere_oracle
+    sw = examples.shallow_water(Nphi, Ntheta)
+    solver = sw['problem'].build_solver(getattr(d3, scheme))
+    examples.shallow_water_initial_condition(sw['u'], sw['h'], sw['basis'], sw['units'])
+    rng = np.random.default_rng(seed)
+    phi, theta = sw['dist'].local_grids(sw['basis'])
+    sw['h']['g'] += 1e-5 * np.cos(3 * phi) * np.sin(theta)**3 * rng.standard_normal()
+    u0, h0 = sw['u']['c'].copy(), sw['h']['c'].copy()
+    for dt in dts:
+        solver.step(dt)
+    ref = sphere_oracle.run(Nphi, Ntheta, u0, h0, len(dts), dts, scheme)
+    for name in ('u', 'h'):
+        got = sw[name]['c']
+        assert np.allclose(got, ref[name], rtol=1e-8, atol=1e-12 * np.abs(ref[name]).max()), (name, np.abs(got - ref[name]).max())
+    return solver

@@ -28,6 +28,11 @@ def test_shallow_water_matches_reference(golden, tag, scheme):
     assert solver.bset.last_verify < 1e-12
 
 
+def test_shallow_water_rk443_with_timestep_changes_matches_oracle():
+    dt = 1 / 12
+    S.check_against_oracle(16, 8, "RK443", [dt, dt, dt / 2, dt / 2, dt])
+
+
 class _EmuArrays:
     """numpy arrays + the emulated library, behind the small interface sphere_cases.check_banded_* use."""
     lib = property(lambda self: E.emu())

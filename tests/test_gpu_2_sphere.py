@@ -57,3 +57,12 @@ def test_shallow_water_config4_size(golden):
     """BASELINE config 4 at its stated size: Nphi, Ntheta = 512, 256 (Lmax = 254), 3 RK222 steps."""
     solver = S.check_config4_size(golden("sphere.npz"))
     assert solver.bset.last_verify < 1e-12
+
+
+@pytest.mark.parametrize("Nphi,Ntheta,scheme", [(64, 32, "RK443"), (128, 64, "RK222"), (64, 32, "SBDF2")])
+def test_shallow_water_with_timestep_changes_matches_oracle(Nphi, Ntheta, scheme):
+    """Sizes without reference fixtures, other schemes, and time-step changes (each one refactorises all per-m systems), against
+    the oracle (pinned to the reference by tests/test_oracle.py)."""
+    dt = 600 / 3600 * min(1.0, 128 / Ntheta)
+    solver = S.check_against_oracle(Nphi, Ntheta, scheme, [dt, dt, dt / 2, dt / 2, dt])
+    assert solver.bset.last_verify < 1e-12

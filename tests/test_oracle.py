@@ -94,3 +94,15 @@ def test_swsh_oracle_matches_reference(golden, tag):
             F, B = T.swsh_matrices(Gt, Lmax, m, s)
             assert np.allclose(F, g[f"{tag}_s{s}_m{m}_fwdmat"], rtol=1e-12, atol=1e-13)
             assert np.allclose(B, g[f"{tag}_s{s}_m{m}_bwdmat"], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("tag,scheme", [("sw16", "RK222"), ("sw32", "RK222"), ("sw32sbdf2", "SBDF2")])
+def test_sphere_oracle_matches_reference(golden, tag, scheme):
+    """oracle/sphere_oracle.py (complex per-m formulation, dense solves) vs the reference's shallow-water states."""
+    from oracle import sphere_oracle
+    g = golden("sphere.npz")
+    Nphi, Ntheta, dealias, steps, dt = g[f"{tag}_meta"]
+    out = sphere_oracle.run(int(Nphi), int(Ntheta), g[f"{tag}_u0"], g[f"{tag}_h0"], int(steps), float(dt), scheme, dealias=float(dealias))
+    for name in ("u", "h"):
+        ref = g[f"{tag}_{name}1"]
+        assert np.allclose(out[name], ref, rtol=1e-9, atol=1e-13 * np.abs(ref).max()), name
