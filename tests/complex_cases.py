@@ -1,5 +1,5 @@
 """Shared bodies of the complex-dtype (T3) tests: run under the CPU emulation (tests/test_emu_complex.py) and on the GPU
-(tests/test_gpu_3_complex.py)."""
+(tests/test_gpu_t3_complex.py)."""
 import numpy as np
 import dedalus_b200 as d3
 from dedalus_b200 import examples

@@ -1,4 +1,4 @@
-"""Shared body of the spherical-shell transform tests (emulation: tests/test_emu_shell.py, GPU: tests/test_gpu_4_shell.py)."""
+"""Shared body of the spherical-shell transform tests (emulation: tests/test_emu_shell.py, GPU: tests/test_gpu_t6_shell.py)."""
 import numpy as np
 import dedalus_b200 as d3
 

@@ -1,5 +1,5 @@
 """Complex-dtype pencil path (T3: complex128 IVPs on ComplexFourier^n x Jacobi; dedalus_b200/complex_path.py and the real / imaginary
-plane embedding of dedalus_b200/pencils.py) through the CPU emulation of the kernels; GPU versions: tests/test_gpu_3_complex.py."""
+plane embedding of dedalus_b200/pencils.py) through the CPU emulation of the kernels; GPU versions: tests/test_gpu_t3_complex.py."""
 import numpy as np, pytest
 import dedalus_b200 as d3
 from emu import emu_lib as E

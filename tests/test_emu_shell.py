@@ -1,5 +1,5 @@
 """Spherical-shell field transforms (T6) through the CPU emulation of the kernels, against reference vectors
-(tests/golden/shell.npz); GPU version: tests/test_gpu_4_shell.py."""
+(tests/golden/shell.npz); GPU version: tests/test_gpu_t6_shell.py."""
 import pytest
 from emu import emu_lib as E
 import shell_cases as SC
