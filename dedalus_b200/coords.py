@@ -127,6 +127,9 @@ class SphericalCoordinates:
         self.colatitude = Coordinate(colatitude, cs=self)
         self.radius = Coordinate(radius, cs=self)
         self.S2coordsys = S2Coordinates(azimuth, colatitude)
+        # the sphere's coordinate system shares the coordinate OBJECTS (a sphere basis inside a 3-D distributor sits on them)
+        self.S2coordsys.azimuth, self.S2coordsys.colatitude = self.azimuth, self.colatitude
+        self.S2coordsys.coords = (self.azimuth, self.colatitude)
         self.coords = (self.azimuth, self.colatitude, self.radius)
 
     def __getitem__(self, key):

@@ -338,16 +338,18 @@ class Integrate(LinearOperator):
 
 
 class Lift(LinearOperator):
-    """Tau lift: operand * P_n of `basis` (reference LiftJacobi basis.py:790-814)."""
+    """Tau lift: operand * P_n of `basis` (reference LiftJacobi basis.py:790-814; LiftShell basis.py:5155-5199: the operand
+    lives on the sphere and is lifted along the radius of a shell basis)."""
     def __init__(self, A, basis, n):
         self.args = [A]
         self.basis, self.n = basis, n
-        self.axis = A.dist.get_axis(basis.coord)
+        self.axis = A.dist.get_axis(basis.coord) + (basis.dim - 1)          # the last axis of a multi-dimensional (shell) basis
         if A.bases[self.axis] is not None:
             raise ValueError("Lift operand must be constant along the lift basis axis.")
         self.dist, self.dtype, self.tensorsig = A.dist, A.dtype, A.tensorsig
         b = list(A.bases)
-        b[self.axis] = basis
+        for sub in range(basis.dim):
+            b[self.axis - (basis.dim - 1) + sub] = basis
         self.bases = tuple(b)
 
 

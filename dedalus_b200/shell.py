@@ -123,6 +123,30 @@ class ShellBasis(Basis):
         self._key = (coordsys, shape, radii, self.k, alpha, dealias)
         self._ctor_args = dict(coordsys=coordsys, shape=shape, dtype=np.float64, radii=radii, k=self.k, alpha=alpha, dealias=dealias)
         self._plans = {}
+        self.grid_params = (coordsys, radii, alpha, dealias)
+
+    # ---- related bases (reference basis.py:4401-4413, 4236-4245)
+    @property
+    def radial_basis(self):
+        if 'radial' not in self._plans:
+            self._plans['radial'] = ShellRadialBasis(self.coordsys, self.shape[2], radii=self.radii, alpha=self.alpha,
+                                                     dealias=(self.dealias[2],), k=self.k)
+        return self._plans['radial']
+
+    def S2_basis(self, radius=None):
+        radius = max(self.radii) if radius is None else radius
+        key = ('S2', radius)
+        if key not in self._plans:
+            self._plans[key] = SphereBasis(self.coordsys, self.shape[:2], radius=radius, dealias=self.dealias[:2])
+        return self._plans[key]
+
+    @property
+    def outer_surface(self):
+        return self.S2_basis(self.radii[1])
+
+    @property
+    def inner_surface(self):
+        return self.S2_basis(self.radii[0])
 
     @classmethod
     def _make(cls, **kw):
@@ -146,13 +170,28 @@ class ShellBasis(Basis):
     def grid_shape(self, scales):
         return tuple(self.axis_grid_size(s, i) for i, s in enumerate(scales))
 
+    # ---- basis algebra (reference basis.py:4423-4462, 3718-3762): sums take the larger k, products add them
     def __add__(self, other):
         if other is None or other == self:
             return self
+        if isinstance(other, ShellBasis) and self.grid_params == other.grid_params and self.shape == other.shape:
+            return self.clone_with(k=max(self.k, other.k))
+        if isinstance(other, ShellRadialBasis) and self.grid_params[:3] == other.grid_params[:3]:
+            return self.clone_with(k=max(self.k, other.k))
+        if isinstance(other, SphereBasis):
+            return self
         return NotImplemented
     __radd__ = __add__
-    __mul__ = __add__
-    __rmul__ = __add__
+
+    def __mul__(self, other):
+        if other is None:
+            return self
+        if isinstance(other, (ShellBasis, ShellRadialBasis)) and self.grid_params[:3] == other.grid_params[:3]:
+            return self.clone_with(k=self.k + other.k)
+        if isinstance(other, SphereBasis):
+            return self
+        return NotImplemented
+    __rmul__ = __mul__
 
     def derivative_basis(self, order=1):
         return self.clone_with(k=self.k + order)
@@ -225,6 +264,65 @@ class ShellBasis(Basis):
                 rows.append(row)
             self._plans[key] = PairProgram(rows, device, torch.from_numpy(np.concatenate(syms)).to(device))
         return self._plans[key]
+
+
+class ShellRadialBasis(Basis):
+    """Radial part of a shell basis as a 1-D basis on the radius coordinate: (dR / r)^k P_n^(alpha + k)(z) (reference
+    basis.py:3684-3850).  Fields on it (er, rvec, ...) are the radial non-constant coefficients of shell problems; their
+    transforms (regularity components at l = 0) are tiny host-side setup work (dedalus_b200/shell_ivp.py)."""
+    dim = 1
+    kind = "ShellRadial"
+    group_size = 1
+
+    def __init__(self, coordsys, radial_size, dtype=np.float64, radii=(1, 2), alpha=(-0.5, -0.5), dealias=(1,), k=0, radius_library=None):
+        self.coordsys, self.coord = coordsys, coordsys.radius
+        self.size = int(radial_size)
+        self.radii, self.alpha, self.k = tuple(radii), tuple(alpha), int(k)
+        self.dealias = (dealias,) if isinstance(dealias, (int, float)) else tuple(dealias)
+        self.dtype = np.float64
+        self.dR = radii[1] - radii[0]
+        self.rho = (radii[1] + radii[0]) / self.dR
+        self.grid_params = (coordsys, self.radii, self.alpha)
+        self._key = (coordsys, self.size, self.radii, self.alpha, self.dealias, self.k)
+        self._ctor_args = dict(coordsys=coordsys, radial_size=self.size, radii=self.radii, alpha=self.alpha, dealias=self.dealias, k=self.k)
+
+    @classmethod
+    def _make(cls, **kw):
+        return cls(**kw)
+
+    def grid_size(self, scale):
+        return int(np.ceil(scale * self.size))
+
+    def _native_grid(self, scale):
+        from . import jacobi
+        return jacobi.gauss_grid(self.grid_size(scale), self.alpha[0], self.alpha[1])[0]
+
+    def global_grid(self, scale=None):
+        scale = self.dealias[0] if scale is None else scale
+        return self.dR / 2 * (self._native_grid(scale) + self.rho)
+
+    def derivative_basis(self, order=1):
+        return self.clone_with(k=self.k + order)
+
+    def __add__(self, other):
+        if other is None or other == self:
+            return self
+        if isinstance(other, ShellRadialBasis) and self.grid_params == other.grid_params:
+            return self.clone_with(k=max(self.k, other.k))
+        if isinstance(other, ShellBasis):
+            return other + self
+        return NotImplemented
+    __radd__ = __add__
+
+    def __mul__(self, other):
+        if other is None:
+            return self
+        if isinstance(other, ShellRadialBasis) and self.grid_params == other.grid_params:
+            return self.clone_with(k=self.k + other.k)
+        if isinstance(other, ShellBasis):
+            return other * self
+        return NotImplemented
+    __rmul__ = __mul__
 
 
 def shell_basis_of(field_or_bases):
@@ -302,3 +400,44 @@ def transform_shell_field(field, layout):
         c = torch.empty((ncomp, Nc0, Nc1, Nr), dtype=dt, device=dev)
         basis.radial_plan(Ngr).forward(cr.contiguous(), c, 3)
         field.set_device_data(c.reshape(field.tshape + basis.coeff_shape), 'c')
+
+
+def transform_radial_field(field, layout):
+    """Fields on a ShellRadialBasis alone (er, rvec: the radial coefficients of shell problems): coordinate components on the
+    radial grid <-> regularity components (at l = 0) in Jacobi coefficients.  Host-side numpy: these are a few 1-D arrays used
+    while the pencil matrices are assembled, never inside a time step (reference: RegularityBasis transforms with the azimuthal
+    and colatitude axes constant, core/basis.py:3629-3660, 3814-3846)."""
+    from . import jacobi
+    basis = field.bases[-1]
+    rank = len(field.tensorsig)
+    ncomp = max(field.ncomp, 1)
+    data = np.asarray(field.data).reshape(ncomp, -1)
+    a, b = basis.alpha[0] + basis.k, basis.alpha[1] + basis.k
+    N = basis.grid_size(field.scales[-1])
+    z, w = jacobi.gauss_grid(N, basis.alpha[0], basis.alpha[1])
+    r = basis.dR / 2 * (z + basis.rho)
+    if rank:
+        cs = field.tensorsig[0]
+        U, Q = cs.U_forward(rank), Intertwiner(0).matrix(rank)
+    if layout == 'g':
+        P = jacobi.polynomials(basis.size, a, b, z)                         # (Nr, N)
+        reg = (data @ P) * (basis.dR / r) ** basis.k
+        out = reg if not rank else (U.conj().T @ (Q @ reg)).real
+        shape = field.tshape + (1,) * (field.dist.dim - 1) + (N,)
+    else:
+        spin = data if not rank else (U @ data)
+        if rank and np.abs(spin.imag).max() > 1e-14 * max(np.abs(spin).max(), 1e-300):
+            raise NotImplementedError("radial fields with angular components")
+        reg = np.real(spin) if not rank else Q.T @ np.real(spin)
+        reg = reg * (basis.dR / r) ** (-basis.k)
+        # grid (alpha0 weight) -> coefficients of the (alpha + k) polynomials: project in the alpha0 basis, then convert
+        P0 = jacobi.polynomials(max(basis.size, N), basis.alpha[0], basis.alpha[1], z)[:, :] * w[None, :]
+        c0 = reg @ P0.T
+        c0[:, N:] = 0
+        C = jacobi.conversion_matrix(c0.shape[1], basis.alpha[0], basis.alpha[1], a, b)
+        out = (C @ c0.T).T[:, :basis.size]
+        shape = field.tshape + (1,) * (field.dist.dim - 1) + (basis.size,)
+    field.layout = layout
+    field._host = np.ascontiguousarray(out.reshape(shape))
+    field._dev = None
+    field._fresh = 'host'

@@ -27,7 +27,8 @@ class SphereBasis(Basis):
     constant_mode_value = 1 / np.sqrt(2)
 
     def __init__(self, coordsys, shape, dtype=np.float64, radius=1, dealias=(1, 1), azimuth_library=None, colatitude_library=None):
-        if not isinstance(coordsys, S2Coordinates):
+        from .coords import SphericalCoordinates
+        if not isinstance(coordsys, (S2Coordinates, SphericalCoordinates)):
             raise ValueError("Sphere coordsys must be S2Coordinates.")
         shape = tuple(int(n) for n in shape)
         if len(shape) != 2:
@@ -83,6 +84,8 @@ class SphereBasis(Basis):
             return self
         if isinstance(other, SphereBasis) and (self.coordsys, self.radius, self.dealias) == (other.coordsys, other.radius, other.dealias):
             return self.clone_with(shape=tuple(np.maximum(self.shape, other.shape)))
+        if getattr(other, 'kind', None) == "Shell":        # a sphere basis met on the angular axes of a shell expression
+            return other
         return NotImplemented
     __radd__ = __add__
     __mul__ = __add__
@@ -145,9 +148,9 @@ class SphereBasis(Basis):
         """Spin total of every tensor component, shape (2,) * rank (spin ordering -, +)."""
         S = np.zeros(tuple(cs.dim for cs in tensorsig), dtype=int)
         for i, cs in enumerate(tensorsig):
-            if cs is not self.coordsys:
-                raise NotImplementedError("tensor indices over other coordinate systems on a sphere basis")
-            shp = [1] * len(tensorsig); shp[i] = 2
+            if not hasattr(cs, 'spin_ordering'):
+                raise NotImplementedError("tensor indices over non-curvilinear coordinate systems on a sphere basis")
+            shp = [1] * len(tensorsig); shp[i] = cs.dim           # S2: (-, +); spherical: (-, +, 0)
             S = S + np.array(cs.spin_ordering).reshape(shp)
         return S
 
@@ -223,11 +226,11 @@ class SphereBasis(Basis):
             self._plans[key] = RealFourierTransform(Nphi_g, self.shape[0], kscale=1.0)
         return self._plans[key]
 
-    def recombination_table(self, rank, forward, device):
-        """Device program of db_pair_lincomb for the component <-> spin recombination of a rank-`rank` tensor."""
-        key = ('rec', rank, bool(forward), str(device))
+    def recombination_table(self, rank, forward, device, cs=S2Coordinates):
+        """Device program of db_pair_lincomb for the component <-> spin recombination of a rank-`rank` tensor over `cs`."""
+        key = ('rec', rank, bool(forward), str(device), cs.dim)
         if key not in self._plans:
-            U = S2Coordinates.U_forward(rank) if forward else S2Coordinates.U_backward(rank)
+            U = cs.U_forward(rank) if forward else cs.U_backward(rank)
             self._plans[key] = PairProgram.from_matrix(U, device)
         return self._plans[key]
 
@@ -272,7 +275,7 @@ def sphere_basis_of(field_or_bases):
     return None
 
 
-def components_to_grid(basis, cdata, spins, rank, scales):
+def components_to_grid(basis, cdata, spins, rank, scales, cs=S2Coordinates):
     """Coefficient data (ncomp, Nphi/2, Nl) of spin components -> grid data (ncomp, Nphi_g, Ntheta_g) of coordinate
     components; components of a rank-`rank` tensor in C order.  Components of equal spin weight that are ADJACENT share one
     launch of the colatitude transform (one pass over that spin weight's matrices)."""
@@ -289,14 +292,14 @@ def components_to_grid(basis, cdata, spins, rank, scales):
         c = c1
     if rank > 0:
         cg2 = torch.empty_like(cg)
-        basis.recombination_table(rank, False, cdata.device).apply(cg, cg2, basis.shape[0] // 2, Ng_theta)
+        basis.recombination_table(rank, False, cdata.device, cs).apply(cg, cg2, basis.shape[0] // 2, Ng_theta)
         cg = cg2
     g = torch.empty((ncomp, Ng_phi, Ng_theta), dtype=cdata.dtype, device=cdata.device)
     basis.azimuth_plan(Ng_phi).backward(cg, g, 1)
     return g
 
 
-def grid_to_components(basis, gdata, spins, rank, out=None):
+def grid_to_components(basis, gdata, spins, rank, out=None, cs=S2Coordinates):
     """Inverse chain of components_to_grid."""
     import torch
     ncomp, Ng_phi, Ng_theta = gdata.shape
@@ -304,7 +307,7 @@ def grid_to_components(basis, gdata, spins, rank, out=None):
     basis.azimuth_plan(Ng_phi).forward(gdata, cg, 1)
     if rank > 0:
         cg2 = torch.empty_like(cg)
-        basis.recombination_table(rank, True, gdata.device).apply(cg, cg2, basis.shape[0] // 2, Ng_theta)
+        basis.recombination_table(rank, True, gdata.device, cs).apply(cg, cg2, basis.shape[0] // 2, Ng_theta)
         cg = cg2
     if out is None:
         out = torch.zeros((ncomp,) + basis.coeff_shape, dtype=gdata.dtype, device=gdata.device)
@@ -326,18 +329,20 @@ def transform_sphere_field(field, layout):
     ax = field.dist.get_basis_axis(basis)
     scales = field.scales[ax:ax + 2]
     rank = len(field.tensorsig)
+    cs = type(field.tensorsig[0]) if rank else S2Coordinates
+    trail = (1,) * (field.dist.dim - ax - 2)             # a sphere inside a 3-D distributor: trailing constant axis
     spins = [int(s) for s in basis.spin_weights(field.tensorsig).reshape(-1)]
     data = field.device_data()
     ncomp = max(1, len(spins))
     if layout == 'g':
         cdata = data.reshape((ncomp,) + basis.coeff_shape).contiguous()
-        g = components_to_grid(basis, cdata, spins, rank, scales)
-        field.set_device_data(g.reshape(field.tshape + tuple(g.shape[1:])), 'g')
+        g = components_to_grid(basis, cdata, spins, rank, scales, cs)
+        field.set_device_data(g.reshape(field.tshape + tuple(g.shape[1:]) + trail), 'g')
     else:
         gshape = basis.grid_shape(scales)
         gdata = data.reshape((ncomp,) + gshape).contiguous()
-        c = grid_to_components(basis, gdata, spins, rank)
-        field.set_device_data(c.reshape(field.tshape + basis.coeff_shape), 'c')
+        c = grid_to_components(basis, gdata, spins, rank, cs=cs)
+        field.set_device_data(c.reshape(field.tshape + basis.coeff_shape + trail), 'c')
 
 
 # ------------------------------------------------------------------------------------------------------------

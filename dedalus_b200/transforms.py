@@ -476,6 +476,9 @@ def transform_field(field, layout):
     from .shell import shell_basis_of, transform_shell_field
     if shell_basis_of(field) is not None:
         return transform_shell_field(field, layout)
+    from .shell import ShellRadialBasis, transform_radial_field
+    if any(isinstance(b, ShellRadialBasis) for b in field.bases):
+        return transform_radial_field(field, layout)
     if field.dist.size > 1:
         from .transposes import transform_field_distributed
         return transform_field_distributed(field, layout)
