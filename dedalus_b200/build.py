@@ -12,7 +12,7 @@ import os, subprocess, sys, pathlib, shutil
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-SOURCES = ["core.cu", "fft.cu", "rfft_regs.cu", "pencil.cu", "pointwise.cu", "banded.cu"]
+SOURCES = ["core.cu", "fft.cu", "rfft_regs.cu", "pencil.cu", "pointwise.cu", "banded.cu", "dense.cu"]
 LIB = PKG / "libdedalus_b200.so"
 OBJ = CSRC / "_obj"
 EMU_DIR = ROOT / "tests" / "emu"

@@ -133,3 +133,49 @@ def complex_ginzburg_landau_initial_condition(u, bases):
     x, z = u.dist.local_grids(*bases)
     u.fill_random('g', seed=3, distribution='normal', scale=0.1)
     u['g'] *= z * (1 - z)
+
+
+def shell_convection(Nphi=256, Ntheta=128, Nr=128, Ri=14, Ro=15, Rayleigh=3500, Prandtl=1, dealias=3/2, dtype=np.float64):
+    """Boussinesq convection in a spherical shell, BASELINE config 5 (examples/ivp_shell_convection/shell_convection.py:33-83)."""
+    coords = d3.SphericalCoordinates('phi', 'theta', 'r')
+    dist = d3.Distributor(coords, dtype=dtype)
+    shell = d3.ShellBasis(coords, shape=(Nphi, Ntheta, Nr), radii=(Ri, Ro), dealias=dealias, dtype=dtype)
+    sphere = shell.outer_surface
+    p = dist.Field(name='p', bases=shell)
+    b = dist.Field(name='b', bases=shell)
+    u = dist.VectorField(coords, name='u', bases=shell)
+    tau_p = dist.Field(name='tau_p')
+    tau_b1 = dist.Field(name='tau_b1', bases=sphere)
+    tau_b2 = dist.Field(name='tau_b2', bases=sphere)
+    tau_u1 = dist.VectorField(coords, name='tau_u1', bases=sphere)
+    tau_u2 = dist.VectorField(coords, name='tau_u2', bases=sphere)
+    kappa = (Rayleigh * Prandtl)**(-1/2)
+    nu = (Rayleigh / Prandtl)**(-1/2)
+    phi, theta, r = dist.local_grids(shell)
+    er = dist.VectorField(coords, bases=shell.radial_basis)
+    er['g'][2] = 1
+    rvec = dist.VectorField(coords, bases=shell.radial_basis)
+    rvec['g'][2] = r
+    lift_basis = shell.derivative_basis(1)
+    lift = lambda A: d3.Lift(A, lift_basis, -1)
+    grad_u = d3.grad(u) + rvec*lift(tau_u1)
+    grad_b = d3.grad(b) + rvec*lift(tau_b1)
+    problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
+    problem.add_equation("trace(grad_u) + tau_p = 0")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*er + lift(tau_u2) = - u@grad(u)")
+    problem.add_equation("b(r=Ri) = 1")
+    problem.add_equation("u(r=Ri) = 0")
+    problem.add_equation("b(r=Ro) = 0")
+    problem.add_equation("u(r=Ro) = 0")
+    problem.add_equation("integ(p) = 0")
+    return dict(problem=problem, dist=dist, coords=coords, shell=shell, p=p, b=b, u=u, Ri=Ri, Ro=Ro,
+                taus=dict(tau_p=tau_p, tau_b1=tau_b1, tau_b2=tau_b2, tau_u1=tau_u1, tau_u2=tau_u2))
+
+
+def shell_convection_initial_condition(b, shell, Ri, Ro, seed=42):
+    """Random noise damped at the walls on top of the conductive profile (stock script lines 86-88)."""
+    phi, theta, r = b.dist.local_grids(shell)
+    b.fill_random('g', seed=seed, distribution='normal', scale=1e-3)
+    b['g'] *= (r - Ri) * (Ro - r)
+    b['g'] += (Ri - Ri * Ro / r) / (Ri - Ro)

@@ -60,6 +60,11 @@ class VecComb(C.Structure):
     _fields_ = [("nvec", i32), ("vec", vp * 16), ("coef", f64 * 16)]
 
 
+class DenseSys(C.Structure):
+    """include/dedalus_b200.h: db_dense_sys"""
+    _fields_ = [("ncols", i32), ("pad", i32), ("vec_off", i64)]
+
+
 class PairLinTerm(C.Structure):
     """include/dedalus_b200.h: db_pair_lin_term"""
     _fields_ = [("re", f64), ("im", f64), ("sym_off", i64), ("src", i32), ("pad", i32)]
@@ -111,6 +116,10 @@ SIGNATURES = {
     "db_banded_solve": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, C.POINTER(VecComb), vp, vp]),
     "db_banded_matvec": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "db_banded_set_mode": (C.c_int, [i32]),
+    "db_dense_combine": (C.c_int, [i32, i32, f64, vp, f64, vp, vp, vp]),
+    "db_dense_factor": (C.c_int, [i32, i32, vp, vp, vp, vp]),
+    "db_dense_solve": (C.c_int, [vp, i32, i32, i32, vp, vp, C.POINTER(VecComb), vp, vp]),
+    "db_dense_matvec": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "db_index_move": (C.c_int, [vp, i64, vp, vp, i32, vp]),
     "db_pair_lincomb": (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, i64, vp]),
     "db_absmax": (C.c_int, [vp, i64, vp, vp]),

@@ -343,62 +343,81 @@ def _spin_groups(spins):
         c = c1
 
 
+def shell_components_to_grid(basis, c, rank, scales):
+    """Regularity components (ncomp, Nphi/2, Nl, Nr) in basis `basis` (its k) -> coordinate components on the grid."""
+    import torch
+    sb = basis.sphere_basis
+    ncomp = c.shape[0]
+    spins = ([int(s) for s in basis.spin_weights((basis.coordsys,) * rank).reshape(-1)] if rank else [0])
+    Ngp, Ngt, Ngr = basis.grid_shape(scales)
+    Nc0, Nc1, Nr = basis.coeff_shape
+    Nphi = basis.shape[0]
+    dev, dt = c.device, c.dtype
+    cr = torch.empty((ncomp, Nc0, Nc1, Ngr), dtype=dt, device=dev)
+    basis.radial_plan(Ngr).backward(c, cr, 3)
+    if rank > 0:
+        tmp = torch.empty_like(cr)
+        basis.regularity_table(rank, False, dev).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
+        cr = tmp
+    if basis.k > 0:
+        cr = cr * torch.from_numpy((basis.dR / basis.global_grid_radius(scales[2])) ** basis.k).to(dev)
+    cg = torch.empty((ncomp, Nphi, Ngt, Ngr), dtype=dt, device=dev)
+    for s, c0, c1 in _spin_groups(spins):
+        sb.colatitude_plan(Ngt, s).backward(cr[c0:c1], cg[c0:c1], 2)
+    if rank > 0:
+        tmp = torch.empty_like(cg)
+        basis.spin_table(rank, False, dev).apply(cg, tmp, Nphi // 2, Ngt * Ngr)
+        cg = tmp
+    g = torch.empty((ncomp, Ngp, Ngt, Ngr), dtype=dt, device=dev)
+    sb.azimuth_plan(Ngp).backward(cg, g, 1)
+    return g
+
+
+def shell_grid_to_components(basis, g, rank):
+    """Coordinate components on the grid (ncomp, Ngp, Ngt, Ngr) -> regularity components in basis `basis`."""
+    import torch
+    sb = basis.sphere_basis
+    ncomp, Ngp, Ngt, Ngr = g.shape
+    spins = ([int(s) for s in basis.spin_weights((basis.coordsys,) * rank).reshape(-1)] if rank else [0])
+    Nc0, Nc1, Nr = basis.coeff_shape
+    Nphi = basis.shape[0]
+    dev, dt = g.device, g.dtype
+    cg = torch.empty((ncomp, Nphi, Ngt, Ngr), dtype=dt, device=dev)
+    sb.azimuth_plan(Ngp).forward(g, cg, 1)
+    if rank > 0:
+        tmp = torch.empty_like(cg)
+        basis.spin_table(rank, True, dev).apply(cg, tmp, Nphi // 2, Ngt * Ngr)
+        cg = tmp
+    cr = torch.zeros((ncomp, Nc0, Nc1, Ngr), dtype=dt, device=dev)
+    for s, c0, c1 in _spin_groups(spins):
+        sb.colatitude_plan(Ngt, s).forward(cg[c0:c1], cr[c0:c1], 2)
+    if basis.k > 0:
+        scale = Ngr / basis.shape[2]
+        cr = cr * torch.from_numpy((basis.dR / basis.global_grid_radius(scale)) ** (-basis.k)).to(dev)
+    if rank > 0:
+        tmp = torch.empty_like(cr)
+        basis.regularity_table(rank, True, dev).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
+        cr = tmp
+    c = torch.empty((ncomp, Nc0, Nc1, Nr), dtype=dt, device=dev)
+    basis.radial_plan(Ngr).forward(cr.contiguous(), c, 3)
+    return c
+
+
 def transform_shell_field(field, layout):
     """field['c'] <-> field['g'] for fields on a ShellBasis (single GPU; reference basis.py:4474-4508 + the sphere chain)."""
-    import torch
     basis = shell_basis_of(field)
-    sb = basis.sphere_basis
     if any(b is not None and b is not basis for b in field.bases):
         raise NotImplementedError("shell basis combined with other bases")
     ax = field.dist.get_basis_axis(basis)
     scales = field.scales[ax:ax + 3]
     rank = len(field.tensorsig)
-    spins = [int(s) for s in basis.spin_weights(field.tensorsig).reshape(-1)] or [0]
-    ncomp = len(spins)
-    Ngp, Ngt, Ngr = basis.grid_shape(scales)
-    Nc0, Nc1, Nr = basis.coeff_shape
-    Nphi = basis.shape[0]
+    ncomp = max(field.ncomp, 1)
     data = field.device_data()
-    dev, dt = data.device, data.dtype
     if layout == 'g':
-        c = data.reshape(ncomp, Nc0, Nc1, Nr).contiguous()
-        cr = torch.empty((ncomp, Nc0, Nc1, Ngr), dtype=dt, device=dev)
-        basis.radial_plan(Ngr).backward(c, cr, 3)
-        if rank > 0:
-            tmp = torch.empty_like(cr)
-            basis.regularity_table(rank, False, dev).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
-            cr = tmp
-        if basis.k > 0:
-            cr = cr * torch.from_numpy((basis.dR / basis.global_grid_radius(scales[2])) ** basis.k).to(dev)
-        cg = torch.empty((ncomp, Nphi, Ngt, Ngr), dtype=dt, device=dev)
-        for s, c0, c1 in _spin_groups(spins):
-            sb.colatitude_plan(Ngt, s).backward(cr[c0:c1], cg[c0:c1], 2)
-        if rank > 0:
-            tmp = torch.empty_like(cg)
-            basis.spin_table(rank, False, dev).apply(cg, tmp, Nphi // 2, Ngt * Ngr)
-            cg = tmp
-        g = torch.empty((ncomp, Ngp, Ngt, Ngr), dtype=dt, device=dev)
-        sb.azimuth_plan(Ngp).backward(cg, g, 1)
-        field.set_device_data(g.reshape(field.tshape + (Ngp, Ngt, Ngr)), 'g')
+        g = shell_components_to_grid(basis, data.reshape((ncomp,) + basis.coeff_shape).contiguous(), rank, scales)
+        field.set_device_data(g.reshape(field.tshape + tuple(g.shape[1:])), 'g')
     else:
-        g = data.reshape(ncomp, Ngp, Ngt, Ngr).contiguous()
-        cg = torch.empty((ncomp, Nphi, Ngt, Ngr), dtype=dt, device=dev)
-        sb.azimuth_plan(Ngp).forward(g, cg, 1)
-        if rank > 0:
-            tmp = torch.empty_like(cg)
-            basis.spin_table(rank, True, dev).apply(cg, tmp, Nphi // 2, Ngt * Ngr)
-            cg = tmp
-        cr = torch.zeros((ncomp, Nc0, Nc1, Ngr), dtype=dt, device=dev)
-        for s, c0, c1 in _spin_groups(spins):
-            sb.colatitude_plan(Ngt, s).forward(cg[c0:c1], cr[c0:c1], 2)
-        if basis.k > 0:
-            cr = cr * torch.from_numpy((basis.dR / basis.global_grid_radius(scales[2])) ** (-basis.k)).to(dev)
-        if rank > 0:
-            tmp = torch.empty_like(cr)
-            basis.regularity_table(rank, True, dev).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
-            cr = tmp
-        c = torch.empty((ncomp, Nc0, Nc1, Nr), dtype=dt, device=dev)
-        basis.radial_plan(Ngr).forward(cr.contiguous(), c, 3)
+        c = shell_grid_to_components(basis, data.reshape((ncomp,) + basis.grid_shape(scales)).contiguous(), rank)
         field.set_device_data(c.reshape(field.tshape + basis.coeff_shape), 'c')
 
 

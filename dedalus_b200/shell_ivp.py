@@ -379,3 +379,380 @@ def assemble(low, ell):
                 B = B.toarray() if sparse.issparse(B) else np.asarray(B)
                 mats[t][row_off[ri]:row_off[ri + 1], col_off[cj]:col_off[cj + 1]] += B
     return mats[1], mats[0], rows, cols
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Device side: per-l dense systems with one right-hand-side column per (m <= l, cos | -sin)
+# ------------------------------------------------------------------------------------------------------------
+class ShellSystems:
+    """Per-degree pencil systems of a shell IVP on the device, behind the interface of the IMEX loops in solvers.py
+    (move / matvec / solve / factor_verified), served by csrc/dense.cu.
+
+    System l: the valid unknowns of degree l in natural order (variable, component, radial mode), padded to the common size
+    n with identity rows; its right-hand-side columns are r = 2 m + part for m <= l (reference: one Subproblem per l with one
+    subsystem per m, core/subsystems.py:272-274; real dtype: the cos and -sin parts see the same real matrix)."""
+
+    VERIFY_TOL = 1e-9
+
+    def __init__(self, solver, nslots, nlu):
+        import torch
+        from .lib import DenseSys
+        self.solver = solver
+        dev = solver.device
+        problem = solver.problem
+        low = self.low = ShellLowering(problem)
+        basis = low.basis
+        sb = basis.sphere_basis
+        Lmax, Nphi = basis.Lmax, basis.shape[0]
+        Nc0, Nc1, Nr = basis.coeff_shape
+        per_l = []
+        for ell in range(Lmax + 1):
+            M, L, rows, cols = assemble(low, ell)
+            vr = np.array([r['valid'] for r in rows for _ in range(r['n'])], dtype=bool)
+            vc = np.array([c['valid'] for c in cols for _ in range(c['n'])], dtype=bool)
+            if vr.sum() != vc.sum():
+                raise ValueError(f"shell problem: {int(vr.sum())} equations for {int(vc.sum())} unknowns at l = {ell}")
+            per_l.append(dict(M=M[np.ix_(vr, vc)], L=L[np.ix_(vr, vc)], rows=rows, cols=cols, vr=vr, vc=vc))
+        n = max(p['M'].shape[0] for p in per_l)
+        self.n, self.nsys = n, Lmax + 1
+        Mall, Lall = np.zeros((self.nsys, n, n)), np.zeros((self.nsys, n, n))
+        for ell, p in enumerate(per_l):
+            k = p['M'].shape[0]
+            Mall[ell, :k, :k], Lall[ell, :k, :k] = p['M'], p['L']
+            Lall[ell, np.arange(k, n), np.arange(k, n)] = 1.0                   # padding unknowns: identity
+        Mall[np.abs(Mall) < solver.entry_cutoff] = 0
+        Lall[np.abs(Lall) < solver.entry_cutoff] = 0
+        # ---- right-hand-side columns and index tables
+        arr = (DenseSys * self.nsys)()
+        vec_off, xi_all, fi_all = 0, [], []
+        mode = {m: sb.mode_columns(m) for m in range(Nphi // 2)}
+        var_items = [(low.kind_of(v)[0], len(v.tensorsig)) for v in low.variables]
+        eq_items = [(low.kind_of(eq['LHS'])[0], len(eq['tensorsig'])) for eq in problem.equations]
+        self.total_modes = 0
+        for ell, p in enumerate(per_l):
+            mmax = min(ell, Nphi // 2 - 1)
+            ncols = 2 * (mmax + 1)
+            arr[ell].ncols, arr[ell].vec_off = ncols, vec_off
+            for side, layout, valid, arena, items in ((0, p['cols'], p['vc'], solver.var_arena, var_items),
+                                                      (1, p['rows'], p['vr'], solver.eq_arena, eq_items)):
+                idx = np.full((n, ncols), -1, dtype=np.int64)
+                i = 0
+                ms = np.array([m for m in range(mmax + 1) if mode[m][0] is not None], dtype=np.int64)
+                js = np.array([mode[m][0] for m in ms], dtype=np.int64)
+                slots = np.array([mode[m][1][ell - m] for m in ms], dtype=np.int64)
+                for comp in layout:
+                    if not comp['valid']:
+                        continue
+                    kind = items[comp['item']][0]
+                    nrad = comp['n']
+                    base = arena.offsets[comp['item']]
+                    if kind == 'const':
+                        idx[i, 0] = base
+                        i += 1
+                        continue
+                    plane = Nc0 * Nc1 * nrad
+                    nr = np.arange(nrad)[:, None]
+                    for part in (0, 1):
+                        idx[i:i + nrad, 2 * ms + part] = (base + comp['comp'] * plane + ((2 * js + part) * Nc1 + slots)[None, :] * nrad + nr)
+                    i += nrad
+                (xi_all if side == 0 else fi_all).append(idx.ravel())
+            self.total_modes += int(p['vc'].sum()) * ncols
+            vec_off += n * ncols
+        self.nvec = vec_off
+        self.max_ncols = max(a.ncols for a in arr)
+        t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.M_t, self.L_t = t64(Mall), t64(Lall)
+        self.desc = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(dev)
+        self.idx = [t64(np.concatenate(xi_all)), t64(np.concatenate(fi_all))]
+        self.vecs = [torch.zeros(self.nvec, dtype=torch.float64, device=dev) for _ in range(nslots)]
+        self.lu = [torch.zeros((self.nsys, n, n), dtype=torch.float64, device=dev) for _ in range(nlu)]
+        self.ipiv = [torch.zeros((self.nsys, n), dtype=torch.int32, device=dev) for _ in range(nlu)]
+        self.info = torch.zeros(self.nsys, dtype=torch.int32, device=dev)
+        self.reorders, self.last_verify = 0, None
+
+    def _call(self, name, *args):
+        self.solver.lib.call(name, *args, self.solver.stream())
+
+    def move(self, side, gather, slot, arena_t):
+        from .solvers import Timed
+        with Timed(self.solver.prof, "pencil_gather" if gather else "pencil_scatter", 24 * self.nvec):
+            self._call("db_index_move", self.idx[side].data_ptr(), self.nvec, arena_t.data_ptr(), self.vecs[slot].data_ptr(), 1 if gather else 0)
+
+    def matvec(self, x_slot, ym_slot=-1, yl_slot=-1):
+        from .solvers import Timed
+        ym = self.vecs[ym_slot].data_ptr() if ym_slot >= 0 else None
+        yl = self.vecs[yl_slot].data_ptr() if yl_slot >= 0 else None
+        nout = (ym_slot >= 0) + (yl_slot >= 0)
+        with Timed(self.solver.prof, "pencil_matvec", 8 * (self.nsys * self.n * self.n * nout + (1 + nout) * self.nvec)):
+            self._call("db_dense_matvec", self.desc.data_ptr(), self.nsys, self.n, self.M_t.data_ptr(), self.L_t.data_ptr(),
+                       self.vecs[x_slot].data_ptr(), ym, yl)
+
+    def solve(self, lu_slot, x_slot, terms):
+        import ctypes as C
+        from .lib import VecComb
+        from .solvers import Timed
+        vc = VecComb()
+        vc.nvec = len(terms)
+        for k, (slot, coef) in enumerate(terms):
+            if slot == x_slot:
+                raise ValueError("the solution slot must not be one of the right-hand-side slots")
+            vc.vec[k] = self.vecs[slot].data_ptr(); vc.coef[k] = coef
+        with Timed(self.solver.prof, "pencil_solve", 8 * (self.nsys * self.n * self.n + self.nvec * (len(terms) + 1))):
+            self._call("db_dense_solve", self.desc.data_ptr(), self.nsys, self.n, self.max_ncols, self.lu[lu_slot].data_ptr(),
+                       self.ipiv[lu_slot].data_ptr(), C.byref(vc), self.vecs[x_slot].data_ptr())
+
+    def factor(self, lu_slot, a0, b0):
+        self._call("db_dense_combine", self.nsys, self.n, float(a0), self.M_t.data_ptr(), float(b0), self.L_t.data_ptr(), self.lu[lu_slot].data_ptr())
+        self._call("db_dense_factor", self.nsys, self.n, self.lu[lu_slot].data_ptr(), self.ipiv[lu_slot].data_ptr(), self.info.data_ptr())
+
+    def check_info(self):
+        from .lib import DedalusB200Error
+        bad = int((self.info != 0).sum().item())
+        if bad:
+            raise DedalusB200Error(f"{bad} shell pencil systems hit a zero / non-finite pivot during factorisation.")
+
+    def factor_verified(self, lhs, slots):
+        """Factorise a0 M + b0 L into each slot and check the backward error of a probe solve."""
+        import torch
+        from .lib import DedalusB200Error
+        s_b, s_x, s_m, s_l = slots
+        worst = 0.0
+        for lu_slot, a0, b0 in lhs:
+            self.factor(lu_slot, a0, b0)
+            self.check_info()
+            gen = torch.Generator(device=self.solver.device); gen.manual_seed(1234)
+            self.vecs[s_b].normal_(generator=gen)
+            self.solve(lu_slot, s_x, [(s_b, 1.0)])
+            self.matvec(s_x, s_m, s_l)
+            b, mx, lx = self.vecs[s_b], self.vecs[s_m], self.vecs[s_l]
+            r = float((a0 * mx + b0 * lx - b).abs().max() / (b.abs().max() + (a0 * mx).abs().max() + (b0 * lx).abs().max()))
+            worst = max(worst, r)
+        self.last_verify = worst
+        if not worst <= self.VERIFY_TOL:
+            raise DedalusB200Error(f"shell pencil factorisation failed verification: backward error {worst:.2e}")
+        return worst
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Right-hand sides:  sum coef * (state field | grad(state field)) products, evaluated on the dealiased grid
+# ------------------------------------------------------------------------------------------------------------
+class ShellRHSPlan:
+    """Explicit terms of a shell IVP (reference: Evaluator walking the RHS trees, core/evaluator.py:95-146).
+      1. gradients of state fields in coefficient space: two l-independent radial matrices per sign (db_mmt_apply along r) and
+         ONE db_pair_lincomb with the per-(m, l) symbols xi(mu, l + R), xi(mu, l + R) (l + R) (core/operators.py:3280-3310)
+      2. every operand to the grid (dedalus_b200/shell.py shell_components_to_grid), one pointwise launch for all products
+      3. products back to coefficients in the product basis k = k_A + k_B, converted to the equation's basis with E^dk and
+         written into the equation arena (db_mmt_apply with -E^dk folded in).
+    Supported: sums of numeric multiples of dot / tensor products whose factors are state fields or gradients of state fields."""
+
+    def __init__(self, solver):
+        import torch
+        self.solver = solver
+        problem = solver.problem
+        dev = self.device = solver.device
+        low = ShellLowering(problem)
+        basis = self.basis = low.basis
+        self.rops = low.rops
+        sb = basis.sphere_basis
+        Nc0, Nc1, Nr = basis.coeff_shape
+        self.scales = tuple(basis.dealias)
+        self.gshape = basis.grid_shape(self.scales)
+        self.npoints = int(np.prod(self.gshape))
+        variables = problem.variables
+        plane = Nc0 * Nc1 * Nr
+        self.static = []
+        operands, op_ids = [], {}
+
+        def operand(e):
+            """Grid operand: a state field on the shell or the gradient of one."""
+            if id(e) in op_ids:
+                return operands[op_ids[id(e)]]
+            if isinstance(e, Field) and any(e is v for v in variables) and low.kind_of(e)[0] == 'shell':
+                rec = dict(kind='field', field=e, rank=len(e.tensorsig), k=0, g0=sum(3 ** o['rank'] for o in operands))
+            elif isinstance(e, ops.Gradient) and isinstance(e.args[0], Field) and any(e.args[0] is v for v in variables):
+                f = e.args[0]
+                rec = dict(kind='grad', field=f, rank=len(f.tensorsig) + 1, k=1, g0=sum(3 ** o['rank'] for o in operands))
+            else:
+                raise NotImplementedError(f"RHS factor {type(e).__name__} of a shell problem (state fields and their gradients only)")
+            op_ids[id(e)] = len(operands)
+            operands.append(rec)
+            return rec
+
+        def poly(e):
+            if isinstance(e, ops.DotProduct):
+                A, B = e.args
+                ra, ka, na = poly(A); rb, kb, nb = poly(B)
+                d = 3
+                nA, nB = na // d, nb // d
+                out = {ia * nB + ib: [(x * y, fx + fy) for i in range(d) for x, fx in ra[ia * d + i] for y, fy in rb[i * nB + ib]]
+                       for ia in range(nA) for ib in range(nB)}
+                return out, ka + kb, nA * nB
+            if isinstance(e, ops.Multiply):
+                A, B = e.args
+                ra, ka, na = poly(A); rb, kb, nb = poly(B)
+                return ({ca * nb + cb: [(x * y, fx + fy) for x, fx in ra[ca] for y, fy in rb[cb]] for ca in range(na) for cb in range(nb)},
+                        ka + kb, na * nb)
+            if isinstance(e, ops.ScalarMul):
+                r, k, n = poly(e.args[0])
+                return {c: [(x * e.c, f) for x, f in t] for c, t in r.items()}, k, n
+            o = operand(e)
+            n = 3 ** o['rank']
+            return {c: [(1.0, (o['g0'] + c,))] for c in range(n)}, o['k'], n
+
+        self.products = []            # (eq index, rank, k of the product basis, terms per component)
+        for ie, eq in enumerate(problem.equations):
+            rhs = eq['RHS']
+            if not isinstance(rhs, ops.Operand):
+                if rhs != 0:
+                    self._add_constant(ie, eq, float(rhs), low)
+                continue
+            terms = rhs.args if isinstance(rhs, ops.Add) else [rhs]
+            acc, kprod, ncomp = None, None, None
+            for t in terms:
+                r, k, n = poly(t)
+                if acc is None:
+                    acc, kprod, ncomp = r, k, n
+                else:
+                    if k != kprod:
+                        raise NotImplementedError("RHS terms in different radial bases")
+                    for c, tl in r.items():
+                        acc[c] = acc.get(c, []) + tl
+            self.products.append(dict(eq=ie, rank=len(eq['tensorsig']), k=kprod, poly=acc, ncomp=ncomp, k_eq=low.kind_of(eq['LHS'])[1]))
+        self.operands = operands
+        self.n_g = sum(3 ** o['rank'] for o in operands)
+        self.n_p = sum(p['ncomp'] for p in self.products)
+        if self.n_p == 0:
+            return
+        # ---- gradient programs: stacked input [D0_- x, D0_+ x, AB x / dR] per field
+        _, ell_map = sb.elements_to_groups()
+        ell_pairs = ell_map[0::2]
+        in_range = ell_pairs <= sb.Lmax
+        lidx = np.minimum(ell_pairs, sb.Lmax)
+        self.grads = {}
+        ro = self.rops
+        q = ro._parts(0)
+        dense = lambda M: torch.from_numpy(np.ascontiguousarray(M.toarray())).to(dev)
+        self.D0 = {mu: dense((q['DZ'] - (1 - (1 if mu == -1 else 0)) * q['AB']) / ro.dR) for mu in (-1, +1)}
+        self.ABm = dense(q['AB'] / ro.dR)
+        for o in operands:
+            if o['kind'] != 'grad' or id(o['field']) in self.grads:
+                continue
+            f = o['field']
+            rin_rank = len(f.tensorsig)
+            nin = 3 ** rin_rank
+            syms, rows = [], []
+            for a, mu in ((0, -1), (1, +1), (2, 0)):
+                for ci in range(nin):
+                    rin = tuple(np.unravel_index(ci, (3,) * rin_rank)) if rin_rank else ()
+                    R = regtotal(rin)
+                    if mu == 0:
+                        rows.append([])
+                        continue
+                    rout = (a,) + rin
+                    tab = np.zeros(sb.Lmax + 1); tab2 = np.zeros(sb.Lmax + 1)
+                    for ell in range(sb.Lmax + 1):
+                        if regularity_allowed(ell, rin) and regularity_allowed(ell, rout):
+                            tab[ell] = xi(mu, ell + R)
+                            tab2[ell] = xi(mu, ell + R) * (ell + R)
+                    off1 = len(syms) * ell_pairs.size; syms.append(np.where(in_range, tab[lidx], 0.0).ravel())
+                    off2 = len(syms) * ell_pairs.size; syms.append(np.where(in_range, tab2[lidx], 0.0).ravel())
+                    src_D = (0 if mu == -1 else 1) * nin + ci
+                    rows.append([(src_D, 1.0, off1), (2 * nin + ci, -float(mu), off2)])
+            from .sphere import PairProgram
+            self.grads[id(f)] = dict(nin=nin, prog=PairProgram(rows, dev, torch.from_numpy(np.concatenate(syms)).to(dev)))
+        # ---- pointwise program (general kernel)
+        coef, fac_ptr, fac, term_ptr = [], [0], [], [0]
+        for p in self.products:
+            for c in range(p['ncomp']):
+                for x, f in p['poly'].get(c, []):
+                    if x != 0:
+                        coef.append(float(x)); fac.extend(f); fac_ptr.append(len(fac))
+                term_ptr.append(len(coef))
+        i32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.int32)).to(dev)
+        self.term_ptr, self.fac_ptr, self.fac = i32(term_ptr), i32(fac_ptr), i32(fac if fac else [0])
+        self.coef = torch.from_numpy(np.asarray(coef if coef else [0.0])).to(dev)
+        self.nfac = len(fac)
+        self.g_in = torch.zeros((self.n_g,) + self.gshape, dtype=torch.float64, device=dev)
+        self.g_out = torch.zeros((self.n_p,) + self.gshape, dtype=torch.float64, device=dev)
+        # ---- conversions product basis -> equation basis (sign folded in: F enters as +F, the minus signs sit in the polynomial)
+        self.convert = {}
+        for p in self.products:
+            key = (p['k'], p['k_eq'])
+            if key not in self.convert and p['k_eq'] != p['k']:
+                if p['k_eq'] < p['k']:
+                    raise NotImplementedError("RHS in a higher radial basis than its equation")
+                self.convert[key] = dense(ro.E(p['k'], p['k_eq'] - p['k']))
+        self.bases_k = {}
+
+    def _basis_k(self, k):
+        if k not in self.bases_k:
+            self.bases_k[k] = self.basis.clone_with(k=k)
+        return self.bases_k[k]
+
+    def _add_constant(self, ie, eq, value, low):
+        """Constant right-hand side of a scalar equation: its l = 0, m = 0 cosine mode (sphere: value / (1 / sqrt 2))."""
+        kind, _ = low.kind_of(eq['LHS'])
+        if eq['tensorsig']:
+            raise NotImplementedError("nonzero constant right-hand side of a tensor equation")
+        off = self.solver.eq_arena.offsets[ie]
+        if kind == 'sphere':
+            self.static.append((off, value * np.sqrt(2)))
+        elif kind == 'const':
+            self.static.append((off, value))
+        else:
+            raise NotImplementedError("nonzero constant right-hand side of a shell-interior equation")
+
+    def set_static(self, eq_t):
+        eq_t.zero_()
+        for off, val in self.static:
+            eq_t[off] = val
+
+    def _mmt(self, mat, inp, out):
+        from .lib import get_lib, current_stream
+        n_out, n_in = mat.shape
+        outer = inp.numel() // n_in
+        get_lib().call("db_mmt_apply", mat.data_ptr(), n_out, n_in, inp.data_ptr(), out.data_ptr(), outer, 1, current_stream())
+
+    def evaluate(self, eq_t):
+        import torch
+        from .lib import get_lib, current_stream
+        from .shell import shell_components_to_grid, shell_grid_to_components
+        from .solvers import Timed
+        if self.n_p == 0:
+            return
+        solver, basis = self.solver, self.basis
+        prof = solver.prof
+        Nc0, Nc1, Nr = basis.coeff_shape
+        views = {id(v): view for v, view in zip(solver.state, solver.state_views)}
+        grads = {}
+        for o in self.operands:
+            f = o['field']
+            c = views[id(f)].reshape((-1, Nc0, Nc1, Nr))
+            if o['kind'] == 'grad':
+                if id(f) not in grads:
+                    G = self.grads[id(f)]
+                    nin = G['nin']
+                    stack = torch.empty((3 * nin, Nc0, Nc1, Nr), dtype=torch.float64, device=self.device)
+                    with Timed(prof, "shell_gradient", 8 * 4 * c.numel()):
+                        self._mmt(self.D0[-1], c, stack[0:nin]); self._mmt(self.D0[+1], c, stack[nin:2 * nin]); self._mmt(self.ABm, c, stack[2 * nin:])
+                        out = torch.empty((3 * nin, Nc0, Nc1, Nr), dtype=torch.float64, device=self.device)
+                        G['prog'].apply(stack, out, Nc0 // 2, Nc1 * Nr, sym_div=Nr)
+                    grads[id(f)] = out
+                c = grads[id(f)]
+            with Timed(prof, "shell_backward", 8 * (c.numel() + 3 ** o['rank'] * self.npoints)):
+                g = shell_components_to_grid(self._basis_k(o['k']), c.contiguous(), o['rank'], self.scales)
+            self.g_in[o['g0']:o['g0'] + 3 ** o['rank']].copy_(g)
+        with Timed(prof, "pointwise", 8 * self.npoints * (self.n_g + self.n_p)):
+            get_lib().call("db_pointwise", self.g_in.data_ptr(), self.g_out.data_ptr(), self.npoints, self.n_g, self.n_p,
+                           self.term_ptr.data_ptr(), self.coef.data_ptr(), self.fac_ptr.data_ptr(), self.fac.data_ptr(), self.nfac, current_stream())
+        p0 = 0
+        for p in self.products:
+            with Timed(prof, "shell_forward", 8 * p['ncomp'] * (self.npoints + Nc0 * Nc1 * Nr)):
+                c = shell_grid_to_components(self._basis_k(p['k']), self.g_out[p0:p0 + p['ncomp']].contiguous(), p['rank'])
+            off = solver.eq_arena.offsets[p['eq']]
+            dst = eq_t[off:off + c.numel()].view(c.shape)
+            if p['k_eq'] != p['k']:
+                self._mmt(self.convert[(p['k'], p['k_eq'])], c, dst)
+            else:
+                dst.copy_(c)
+            p0 += p['ncomp']

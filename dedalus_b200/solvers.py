@@ -331,7 +331,9 @@ class InitialValueSolver:
         from .sphere import sphere_basis_of
         self.entry_cutoff = entry_cutoff
         # curvilinear problems (S2 sphere): per-m banded systems, dedalus_b200/sphere.py SphereSystems, built on the device side
-        self.curvilinear = any(sphere_basis_of(v) is not None for v in problem.variables)
+        from .shell import shell_basis_of
+        self.shell = any(shell_basis_of(v) is not None for v in problem.variables)
+        self.curvilinear = self.shell or any(sphere_basis_of(v) is not None for v in problem.variables)
         if self.curvilinear:
             self.builder, self.batches = None, []
         else:
@@ -373,7 +375,10 @@ class InitialValueSolver:
         for v, off, (tsh, shp) in zip(self.state, self.var_arena.offsets, self.var_arena.shapes):
             n = int(np.prod(tsh, dtype=int)) * int(np.prod(shp, dtype=int))
             self.state_views.append(self.state_t[off:off + n].view(tuple(tsh) + tuple(shp)))
-        if self.curvilinear:
+        if self.shell:
+            from .shell_ivp import ShellRHSPlan
+            self.rhs_plan = ShellRHSPlan(self)
+        elif self.curvilinear:
             from .sphere import SphereRHSPlan
             self.rhs_plan = SphereRHSPlan(self)
         elif self.complex:
@@ -405,7 +410,11 @@ class InitialValueSolver:
             self.slot_F = deque(1 + cls.amax + cls.bmax + j for j in range(cls.cmax))
             nslots = 1 + cls.amax + cls.bmax + cls.cmax
             nlu = 1
-        if self.curvilinear:
+        if self.shell:
+            from .shell_ivp import ShellSystems
+            self.bset = ShellSystems(self, nslots, nlu)
+            self.total_modes = self.bset.total_modes
+        elif self.curvilinear:
             from .sphere import SphereSystems
             self.bset = SphereSystems(self, nslots, nlu)
             self.total_modes = self.bset.total_modes

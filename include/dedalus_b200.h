@@ -337,6 +337,20 @@ int db_banded_set_mode(int32_t mode);
  * table: pencil vectors <-> coefficient arrays in the folded triangular (m, l) packing (core/subsystems.py:340-371) */
 int db_index_move(const int64_t* idx, int64_t count, double* arena, double* vec, int32_t gather, void* stream);
 
+/* Dense batches with many right-hand sides: the per-degree pencil systems of spherical-shell problems -- ONE matrix per l for all
+ * m <= l (core/subsystems.py:272-274: Subproblem.shape = (n, n_subsystems); libraries/matsolvers.py:126-183 per matrix).  Matrices
+ * [nsys][n][n] row-major, every system padded to the same n; vectors of system s: element (i, r) at vec_off + i * ncols + r. */
+typedef struct { int32_t ncols; int32_t pad; int64_t vec_off; } db_dense_sys;
+int db_dense_combine(int32_t nsys, int32_t n, double a0, const double* m, double b0, const double* l, double* out, void* stream);
+/* in-place LU with partial pivoting, one CTA per system; ipiv [nsys][n], info[s] = zero / non-finite pivots met */
+int db_dense_factor(int32_t nsys, int32_t n, double* a, int32_t* ipiv, int32_t* info, void* stream);
+/* x = A^{-1} (sum_k coef_k vec_k) for every column of every system (x must not be one of the vec_k) */
+int db_dense_solve(const db_dense_sys* sys, int32_t nsys, int32_t n, int32_t max_ncols, const double* lu, const int32_t* ipiv,
+                   const db_veccomb* rhs, double* x, void* stream);
+/* ya = A x and / or yb = B x (either output may be NULL) */
+int db_dense_matvec(const db_dense_sys* sys, int32_t nsys, int32_t n, const double* a, const double* b, const double* x,
+                    double* ya, double* yb, void* stream);
+
 /* Complex linear combinations on (cos, -sin) pairs.  in / out: (ncomp, 2 * npair, ncol), rows 2j and 2j + 1 = real and
  * imaginary part of the exp(i m phi) coefficient (core/basis.py:1108-1134).  Output o = sum over its terms
  * term_ptr[o] <= t < term_ptr[o + 1] of (re + i im) * sym * in[src], sym = syms[sym_off + (j * ncol + c) / sym_div] or 1 (sym_off < 0);

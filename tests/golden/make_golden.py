@@ -503,3 +503,68 @@ def gen_shell():
 
 if __name__ == "__main__" and "shell" in sys.argv[1:]:
     gen_shell()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Shell convection IVP (BASELINE config 5: examples/ivp_shell_convection/shell_convection.py)
+# ----------------------------------------------------------------------------------------------------------
+def shell_convection(shape, steps, scheme="SBDF2", tstep=0.05, dump=()):
+    Ri, Ro = 14, 15
+    Nphi, Ntheta, Nr = shape
+    Rayleigh = 3500; Prandtl = 1; dealias = 3/2
+    coords = d3.SphericalCoordinates('phi', 'theta', 'r')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    shell = d3.ShellBasis(coords, shape=(Nphi, Ntheta, Nr), radii=(Ri, Ro), dealias=dealias, dtype=np.float64)
+    sphere = shell.outer_surface
+    p = dist.Field(name='p', bases=shell); b = dist.Field(name='b', bases=shell)
+    u = dist.VectorField(coords, name='u', bases=shell)
+    tau_p = dist.Field(name='tau_p')
+    tau_b1 = dist.Field(name='tau_b1', bases=sphere); tau_b2 = dist.Field(name='tau_b2', bases=sphere)
+    tau_u1 = dist.VectorField(coords, name='tau_u1', bases=sphere); tau_u2 = dist.VectorField(coords, name='tau_u2', bases=sphere)
+    kappa = (Rayleigh * Prandtl)**(-1/2); nu = (Rayleigh / Prandtl)**(-1/2)
+    phi, theta, r = dist.local_grids(shell)
+    er = dist.VectorField(coords, bases=shell.radial_basis); er['g'][2] = 1
+    rvec = dist.VectorField(coords, bases=shell.radial_basis); rvec['g'][2] = r
+    lift_basis = shell.derivative_basis(1)
+    lift = lambda A: d3.Lift(A, lift_basis, -1)
+    grad_u = d3.grad(u) + rvec*lift(tau_u1)
+    grad_b = d3.grad(b) + rvec*lift(tau_b1)
+    problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
+    problem.add_equation("trace(grad_u) + tau_p = 0")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*er + lift(tau_u2) = - u@grad(u)")
+    problem.add_equation("b(r=Ri) = 1"); problem.add_equation("u(r=Ri) = 0")
+    problem.add_equation("b(r=Ro) = 0"); problem.add_equation("u(r=Ro) = 0")
+    problem.add_equation("integ(p) = 0")
+    solver = problem.build_solver(getattr(d3, scheme))
+    b.fill_random('g', seed=42, distribution='normal', scale=1e-3)
+    b['g'] *= (r - Ri) * (Ro - r)
+    b['g'] += (Ri - Ri*Ro/r) / (Ri - Ro)
+    out = dict(b0=b['c'].copy(), meta=np.array(list(shape) + [steps, tstep]))
+    for sp in solver.subproblems:
+        ell = sp.group[1]
+        if ell in dump:
+            nat = natural_matrices(sp)
+            for name in ("M", "L"):
+                out[f"l{ell}_{name}"] = nat[name].toarray()
+    for i in range(steps):
+        solver.step(tstep)
+    for f in (p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2):
+        out[f.name + "1"] = f['c'].copy()
+    return out
+
+
+def gen_shell_ivp():
+    """Shell convection: three per-l pencil matrices (natural ordering) and states after K steps, 16 x 8 x 6 (SBDF2, RK222) and
+    32 x 16 x 12 (SBDF2)."""
+    out = {}
+    for tag, kw in dict(a_sbdf2=dict(shape=(16, 8, 6), steps=3, dump=(0, 1, 3)), a_rk222=dict(shape=(16, 8, 6), steps=3, scheme="RK222"),
+                        b_sbdf2=dict(shape=(32, 16, 12), steps=3)).items():
+        for k, v in shell_convection(**kw).items():
+            out[f"{tag}_{k}"] = v
+    np.savez_compressed(HERE / "shell_ivp.npz", **out)
+    print({k: v.shape for k, v in out.items() if k.endswith("b1") or "_l" in k})
+
+
+if __name__ == "__main__" and "shell_ivp" in sys.argv[1:]:
+    gen_shell_ivp()

@@ -37,3 +37,104 @@ def check_intertwiner_orthogonal():
             assert np.all((np.abs(d - 1) < 1e-13) | (np.abs(d) < 1e-13))
             if ell >= rank:
                 assert np.allclose(d, 1)
+
+
+def _shell_problem(g, tag):
+    from dedalus_b200 import examples
+    Nphi, Ntheta, Nr, steps, dt = g[f"{tag}_meta"]
+    sc = examples.shell_convection(int(Nphi), int(Ntheta), int(Nr))
+    return sc, int(steps), float(dt)
+
+
+def check_shell_pencil_matrices(g, tag="a_sbdf2"):
+    """M and L of the shell-convection pencils of degree l = 0, 1, 3 against the reference's subproblem matrices in natural
+    ordering (variable, component, (cos | -sin), radial mode; core/subsystems.py:497-602): every operator of the problem --
+    gradient, divergence, trace, radial-NCC products, lift, interpolation, integration, conversions."""
+    from dedalus_b200 import shell_ivp
+    sc, steps, dt = _shell_problem(g, tag)
+    problem = sc['problem']
+    low = shell_ivp.ShellLowering(problem)
+    for ell in (0, 1, 3):
+        M, L, rows, cols = shell_ivp.assemble(low, ell)
+
+        def ref_index(layout, kinds):
+            idx, off = [], 0
+            for c, kd in zip(layout, kinds):
+                if kd == 'const' and ell > 0:            # constants only exist in the l = 0 subproblem
+                    idx += [-1]
+                    continue
+                idx += list(range(off, off + c['n']))    # the cos part; the -sin part follows it in the reference ordering
+                off += c['n'] * (1 if kd == 'const' else 2)
+            return np.array(idx)
+        ci = ref_index(cols, [low.kind_of(low.variables[c['item']])[0] for c in cols])
+        ri = ref_index(rows, [low.kind_of(problem.equations[r['item']]['LHS'])[0] for r in rows])
+        vr = np.array([r['valid'] for r in rows for _ in range(r['n'])])
+        vc = np.array([c['valid'] for c in cols for _ in range(c['n'])])
+        for name, mine in (("M", M), ("L", L)):
+            R = g[f"{tag}_l{ell}_{name}"]
+            Rp = np.zeros((R.shape[0] + 1, R.shape[1] + 1)); Rp[:-1, :-1] = R
+            ref = Rp[np.ix_(ri, ci)]
+            got = mine * np.outer(vr, vc)
+            assert np.allclose(got, ref, rtol=1e-11, atol=1e-12 * np.abs(ref).max()), (ell, name, np.abs(got - ref).max())
+
+
+def check_shell_convection(g, tag, scheme):
+    """K steps of shell convection vs the reference.  b, p, u: rtol 1e-8 with atol 1e-10 max|field| + 1e-13 max|b| (after a
+    few steps from noise the velocity is 1e-6 of the buoyancy it is coupled to in the same pencil systems, so its error floor is
+    rounding relative to b); the tau fields (the unknowns most sensitive to the conditioning of the tau systems, which the
+    reference solves with another pivot order): atol 1e-4 max|tau|."""
+    from dedalus_b200 import examples
+    sc, steps, dt = _shell_problem(g, tag)
+    solver = sc['problem'].build_solver(getattr(d3, scheme))
+    examples.shell_convection_initial_condition(sc['b'], sc['shell'], sc['Ri'], sc['Ro'])
+    assert np.allclose(sc['b']['c'], g[f"{tag}_b0"], rtol=1e-11, atol=1e-13)
+    for _ in range(steps):
+        solver.step(dt)
+    floor = 1e-13 * np.abs(g[f"{tag}_b1"]).max()
+    for name in ('p', 'b', 'u'):
+        ref = g[f"{tag}_{name}1"]
+        got = sc[name]['c']
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max() + floor), (name, np.abs(got - ref).max(), np.abs(ref).max())
+    for name, f in sc['taus'].items():
+        ref = g[f"{tag}_{name}1"]
+        got = f['c']
+        assert np.allclose(got, ref, rtol=1e-6, atol=1e-4 * max(np.abs(ref).max(), 1e-300) + 1e-20), (name, np.abs(got - ref).max(), np.abs(ref).max())
+    return solver
+
+
+def check_dense_kernels(B):
+    """db_dense_combine / factor / solve / matvec (ragged column counts, pivoting forced) against numpy; B: array backend."""
+    import ctypes as C
+    from dedalus_b200 import lib as dlib
+    rng = np.random.default_rng(1)
+    n, nsys = 23, 4
+    ncols = [1, 5, 40, 33]
+    A = rng.standard_normal((nsys, n, n)); Bm = rng.standard_normal((nsys, n, n))
+    A[2, 0, 0] = 0
+    sysarr = (dlib.DenseSys * nsys)(); off = 0
+    for i, nc in enumerate(ncols):
+        sysarr[i].ncols = nc; sysarr[i].vec_off = off; off += n * nc
+    a0, b0 = 1.0, 0.3
+    P = B.ptr
+    sysb = B.dev(np.frombuffer(bytes(sysarr), dtype=np.uint8).copy())
+    Ad, Bd = B.dev(A), B.dev(Bm)
+    lu, ipiv, info = B.dev(np.zeros_like(A)), B.dev(np.zeros((nsys, n), dtype=np.int32)), B.dev(np.full(nsys, -1, dtype=np.int32))
+    B.lib.call("db_dense_combine", nsys, n, a0, P(Ad), b0, P(Bd), P(lu), B.stream)
+    B.lib.call("db_dense_factor", nsys, n, P(lu), P(ipiv), P(info), B.stream)
+    assert not B.host(info).any()
+    v1h, v2h = rng.standard_normal(off), rng.standard_normal(off)
+    v1, v2, x, ya, yb = B.dev(v1h), B.dev(v2h), B.dev(np.zeros(off)), B.dev(np.zeros(off)), B.dev(np.zeros(off))
+    vc = dlib.VecComb(); vc.nvec = 2
+    vc.vec[0], vc.vec[1] = P(v1).value, P(v2).value
+    vc.coef[0], vc.coef[1] = 2.0, -0.5
+    B.lib.call("db_dense_solve", P(sysb), nsys, n, max(ncols), P(lu), P(ipiv), C.byref(vc), P(x), B.stream)
+    B.lib.call("db_dense_matvec", P(sysb), nsys, n, P(Ad), P(Bd), P(x), P(ya), P(yb), B.stream)
+    xh, yah, ybh = B.host(x), B.host(ya), B.host(yb)
+    for i, nc in enumerate(ncols):
+        o = sysarr[i].vec_off
+        b = (2 * v1h[o:o + n * nc] - 0.5 * v2h[o:o + n * nc]).reshape(n, nc)
+        xr = np.linalg.solve(a0 * A[i] + b0 * Bm[i], b)
+        xg = xh[o:o + n * nc].reshape(n, nc)
+        assert np.abs(xg - xr).max() <= 1e-10 * np.abs(xr).max(), (i, np.abs(xg - xr).max())
+        assert np.allclose(yah[o:o + n * nc].reshape(n, nc), A[i] @ xg, rtol=1e-12, atol=1e-12)
+        assert np.allclose(ybh[o:o + n * nc].reshape(n, nc), Bm[i] @ xg, rtol=1e-12, atol=1e-12)

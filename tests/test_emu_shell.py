@@ -19,3 +19,18 @@ def test_shell_field_transforms(golden, tag):
 
 def test_intertwiner_orthogonal():
     SC.check_intertwiner_orthogonal()
+
+
+def test_shell_pencil_matrices(golden):
+    SC.check_shell_pencil_matrices(golden("shell_ivp.npz"))
+
+
+@pytest.mark.parametrize("tag,scheme", [("a_sbdf2", "SBDF2"), ("a_rk222", "RK222")])
+def test_shell_convection_matches_reference(golden, tag, scheme):
+    solver = SC.check_shell_convection(golden("shell_ivp.npz"), tag, scheme)
+    assert solver.bset.last_verify < 1e-12
+
+
+def test_dense_kernels_against_numpy():
+    from test_emu_sphere import _EmuArrays
+    SC.check_dense_kernels(_EmuArrays())
