@@ -199,10 +199,27 @@ def main():
     from dedalus_b200.lib import get_lib
     cfg = workload(args)
     N, dt = args.size, cfg['dt']
-    parity = None if args.no_parity else parity_gate(args, world, rank)
-    if rank == 0 and parity is not None and not parity['ok']:
-        print(json.dumps(dict(metric=METRIC, value=None, unit="steps/s", n_gpus=world, parity=parity,
-                              error="parity gate failed: the GPU path does not reproduce the oracle; nothing was timed")))
+    def gate():
+        """Parity gate on all ranks; every rank learns the verdict (rank 0 holds the comparison)."""
+        res = parity_gate(args, world, rank)
+        flag = torch.tensor([1.0 if (res is None or res['ok']) else 0.0], device='cuda')
+        if world > 1:
+            dist.broadcast(flag, src=0)
+        return res, bool(flag.item() == 1.0)
+
+    parity, parity_ok = (None, True) if args.no_parity else gate()
+    if not parity_ok and world > 1 and os.environ.get("DB_PEER_TRANSPOSE", "1") != "0":
+        # safety net: the transposes-as-peer-stores path is measured at 2 and 4 GPUs; if it ever fails the gate, time the NCCL
+        # all-to-all path instead (and say so in the JSON line) rather than time nothing
+        os.environ["DB_PEER_TRANSPOSE"] = "0"
+        first = parity
+        parity, parity_ok = gate()
+        if rank == 0 and parity is not None:
+            parity['peer_transposes_failed_gate'] = first
+    if not parity_ok:
+        if rank == 0:
+            print(json.dumps(dict(metric=METRIC, value=None, unit="steps/s", n_gpus=world, parity=parity,
+                                  error="parity gate failed: the GPU path does not reproduce the oracle; nothing was timed")))
         if world > 1:
             dist.destroy_process_group()
         sys.exit(3)
