@@ -325,6 +325,33 @@ extern "C" int db_index_move(const int64_t* idx, int64_t count, double* arena, d
     return db_check_launch("index_move");
 }
 
+// the same for contiguous RUNS of `run` doubles per index entry (row permutations of the curvilinear transposes: one entry per
+// coefficient row): gather: vec[e * run + x] = arena[idx[e] + x];  scatter: arena[idx[e] + x] = vec[e * run + x]
+__global__ void __launch_bounds__(256)
+k_index_move_runs(const int64_t* __restrict__ idx, int64_t run, double* __restrict__ arena, double* __restrict__ vec, int gather)
+{
+    const int64_t e = blockIdx.x;
+    const int64_t a = idx[e];
+    if (a < 0) {
+        if (gather) for (int64_t x = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; x < run; x += (int64_t)gridDim.y * blockDim.x) vec[e * run + x] = 0.0;
+        return;
+    }
+    for (int64_t x = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; x < run; x += (int64_t)gridDim.y * blockDim.x) {
+        if (gather) vec[e * run + x] = arena[a + x];
+        else arena[a + x] = vec[e * run + x];
+    }
+}
+
+extern "C" int db_index_move_runs(const int64_t* idx, int64_t count, int64_t run, double* arena, double* vec, int32_t gather, void* stream)
+{
+    if (count <= 0 || run <= 0) return 0;
+    if (count > 2147483647LL) { db_set_error("index_move_runs: too many entries"); return 1; }
+    int yb = (int)((run + 255) / 256);
+    if (yb > 64) yb = 64;
+    DB_LAUNCH(k_index_move_runs, dim3((unsigned)count, (unsigned)yb), dim3(256), 0, stream, idx, run, arena, vec, gather);
+    return db_check_launch("index_move_runs");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Complex linear combinations on (cos, -sin) pairs: arrays (ncomp, 2 * npair, ncol), a pair = two adjacent rows holding the
 // real and imaginary part of the coefficient of exp(i m phi) (core/basis.py:1108-1134).  For output component o

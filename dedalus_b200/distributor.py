@@ -111,9 +111,9 @@ class Distributor:
         size = 1 if basis is None else basis.axis_size(self.basis_subaxis(basis, axis))
         if axis != 0 or self.size == 1 or basis is None:
             return slice(0, size)
-        if basis.dim > 1:
-            raise NotImplementedError("curvilinear bases are single-GPU in this build")
-        g = basis.group_size
+        g = basis.axis_group_size(0) if basis.dim > 1 else basis.group_size
+        if basis.dim > 1 and (size // g) % self.size:
+            raise ValueError(f"curvilinear bases need the {size // g} azimuthal pairs of the coefficient packing to divide evenly over {self.size} ranks")
         s, e = self.block_range(size // g, self.size, self.rank)
         return slice(s * g, e * g)
 
@@ -122,8 +122,8 @@ class Distributor:
         size = 1 if basis is None else basis.axis_grid_size(scale, self.basis_subaxis(basis, axis))
         if axis != 1 or self.size == 1 or basis is None:
             return slice(0, size)
-        if basis.dim > 1:
-            raise NotImplementedError("curvilinear bases are single-GPU in this build")
+        if basis.dim > 1 and size % self.size:
+            raise ValueError(f"curvilinear bases need the {size} colatitude grid points to divide evenly over {self.size} ranks")
         s, e = self.block_range(size, self.size, self.rank)
         return slice(s, e)
 

@@ -114,6 +114,7 @@ class SphereBasis(Basis):
         ax = dist.get_basis_axis(self)
         out = []
         for sub, g in enumerate((self.global_grid_azimuth(scales[0]), self.global_grid_colatitude(scales[1]))):
+            g = g[dist.grid_local_slice(ax + sub, self, scales[sub])]          # colatitude (axis 1) is distributed on the grid
             shp = [1] * dist.dim
             shp[ax + sub] = g.size
             out.append(g.reshape(shp))
@@ -179,20 +180,41 @@ class SphereBasis(Basis):
         assert np.array_equal(ells[2 * j, cols], np.arange(m, self.Lmax + 1))
         return j, cols
 
-    def m_maps(self):
+    def local_pairs(self, dist=None):
+        """Block [j0, j1) of the azimuthal pairs of the coefficient packing owned by this rank (all of them on one GPU).  Pair
+        j carries m = j and its folded partner Nphi/2 - 1 - j: the reference's load-balanced layout, core/basis.py:2757-2777."""
+        npairs = self.shape[0] // 4
+        if dist is None or dist.size == 1:
+            return 0, npairs
+        return dist.block_range(npairs, dist.size, dist.rank)
+
+    def local_wavenumbers(self, dist=None):
+        """[(m, row of its cos part in the rank's (azimuthal coefficient, colatitude grid) array)]: single GPU: natural FFT order
+        (row 2 m); distributed: the unfolded wavenumbers of the rank's pairs ascending, then their folded partners ascending."""
+        N2 = self.shape[0] // 2
+        if dist is None or dist.size == 1:
+            return [(m, 2 * m) for m in range(N2)]
+        j0, j1 = self.local_pairs(dist)
+        npl = j1 - j0
+        out = [(j, 2 * (j - j0)) for j in range(j0, j1)]
+        out += [(N2 - 1 - j, 2 * npl + 2 * (j1 - 1 - j)) for j in range(j1 - 1, j0 - 1, -1)]
+        return out
+
+    def m_maps(self, dist=None):
         """Rows (m, mg0, mg1, mc0, mc1, ell_start, ell_stop or -1, ell_step) for SWSHColatitudeTransform: the reference's
-        m_maps (basis.py:2940-2970) with the azimuthal positions of the NATURAL FFT order (mg = 2m, 2m + 2)."""
+        m_maps (basis.py:2940-2970) for the wavenumbers of this rank, positions as in local_wavenumbers()."""
+        j0, _ = self.local_pairs(dist)
         rows = []
-        for m in range(self.shape[0] // 2):
+        for m, row in self.local_wavenumbers(dist):
             j, cols = self.mode_columns(m)
             if j is None:
                 # |m| > Lmax: no coefficients; the transform zero-fills these grid lines on the way back
-                rows.append((m, 2 * m, 2 * m + 2, 0, 2, 0, 0, 1))
+                rows.append((m, row, row + 2, 0, 2, 0, 0, 1))
                 continue
             step = 1 if (cols.size < 2 or cols[1] > cols[0]) else -1
             assert np.all(np.diff(cols) == step)
             stop = int(cols[-1]) + step
-            rows.append((m, 2 * m, 2 * m + 2, 2 * j, 2 * j + 2, int(cols[0]), -1 if stop < 0 else stop, step))
+            rows.append((m, row, row + 2, 2 * (j - j0), 2 * (j - j0) + 2, int(cols[0]), -1 if stop < 0 else stop, step))
         return rows
 
     # ---- operator symbols (reference basis.py:3150-3152, libraries/dedalus_sphere/sphere.py k_element)
@@ -212,11 +234,18 @@ class SphereBasis(Basis):
         return jacobi.jacobi_matrix(n, abs(m + s), abs(m - s)), Lmin
 
     # ---- device transforms
-    def colatitude_plan(self, Ntheta_g, s):
-        key = (int(Ntheta_g), int(s))
+    def colatitude_plan(self, Ntheta_g, s, dist=None):
+        P, rank = (1, 0) if (dist is None or dist.size == 1) else (dist.size, dist.rank)
+        key = (int(Ntheta_g), int(s), P, rank)
         if key not in self._plans:
             from .transforms import SWSHColatitudeTransform
-            self._plans[key] = SWSHColatitudeTransform(Ntheta_g, self.Lmax, self.m_maps(), s)
+            self._plans[key] = SWSHColatitudeTransform(Ntheta_g, self.Lmax, self.m_maps(dist), s)
+        return self._plans[key]
+
+    def hop(self, dist):
+        key = ('hop', dist.size, dist.rank)
+        if key not in self._plans:
+            self._plans[key] = SphereHop(self, dist)
         return self._plans[key]
 
     def azimuth_plan(self, Nphi_g):
@@ -233,6 +262,70 @@ class SphereBasis(Basis):
             U = cs.U_forward(rank) if forward else cs.U_backward(rank)
             self._plans[key] = PairProgram.from_matrix(U, device)
         return self._plans[key]
+
+
+class SphereHop:
+    """Transpose between the two distributed intermediate layouts of a sphere transform chain (P GPUs):
+        A  (comps, rows of the rank's wavenumbers, ALL colatitude points, trailing)    after / before the colatitude transform
+        B  (comps, ALL azimuthal rows in natural FFT order, the rank's colatitude block, trailing)   before / after the FFT
+    = pack -> all-to-all -> unpack (dedalus_b200/transposes.py TransposePlanner, csrc/pointwise.cu k_tr_chunks) plus a row
+    permutation (db_index_move_runs) between the rank-major row order the exchange delivers and the FFT's natural order.
+    Replaces the reference's azimuth <-> colatitude Transpose of a curvilinear layout chain (core/distributor.py:696-924)."""
+
+    def __init__(self, basis, dist):
+        import torch
+        from .transposes import get_planner
+        self.basis, self.dist = basis, dist
+        self.P = dist.size
+        self.planner = get_planner(dist)
+        Nphi = basis.shape[0]
+        N2 = Nphi // 2
+        npairs = Nphi // 4
+        npl = npairs // self.P
+        # natural row of each row of the rank-major order delivered by the exchange
+        nat = np.zeros(Nphi, dtype=np.int64)
+        for p in range(self.P):
+            j0, j1 = p * npl, (p + 1) * npl
+            rows = [(j, 2 * (j - j0)) for j in range(j0, j1)] + [(N2 - 1 - j, 2 * npl + 2 * (j1 - 1 - j)) for j in range(j1 - 1, j0 - 1, -1)]
+            for m, r in rows:
+                nat[p * 4 * npl + r], nat[p * 4 * npl + r + 1] = 2 * m, 2 * m + 1
+        self.nat = nat
+        self._idx = {}
+
+    def _table(self, ncomp, run, device):
+        import torch
+        key = (ncomp, run, str(device))
+        if key not in self._idx:
+            Nphi = self.basis.shape[0]
+            idx = (np.arange(ncomp)[:, None] * Nphi + self.nat[None, :]) * run          # entry (c, rank-major row) -> natural row offset
+            self._idx[key] = torch.from_numpy(np.ascontiguousarray(idx.ravel())).to(device)
+        return self._idx[key]
+
+    def to_grid_side(self, A):
+        """A (ncomp, 4 npl, Ntheta_g, trail) -> B (ncomp, Nphi, Ntheta_g / P, trail)."""
+        import torch
+        from .lib import get_lib, current_stream
+        ncomp, rows, Nt, trail = A.shape
+        tb = Nt // self.P
+        rm = torch.empty((ncomp, rows * self.P, tb, trail), dtype=A.dtype, device=A.device)
+        self.planner.localize_columns(A, rm)
+        B = torch.empty_like(rm)
+        run = tb * trail
+        get_lib().call("db_index_move_runs", self._table(ncomp, run, A.device).data_ptr(), ncomp * rows * self.P, run,
+                       B.data_ptr(), rm.data_ptr(), 0, current_stream())                # scatter: B[natural row] = rank-major row
+        return B
+
+    def to_coeff_side(self, B):
+        import torch
+        from .lib import get_lib, current_stream
+        ncomp, Nphi, tb, trail = B.shape
+        rm = torch.empty_like(B)
+        run = tb * trail
+        get_lib().call("db_index_move_runs", self._table(ncomp, run, B.device).data_ptr(), ncomp * Nphi, run,
+                       B.data_ptr(), rm.data_ptr(), 1, current_stream())                # gather: rank-major row = B[natural row]
+        A = torch.empty((ncomp, Nphi // self.P, tb * self.P, trail), dtype=B.dtype, device=B.device)
+        self.planner.localize_rows(rm, A)
+        return A
 
 
 class PairProgram:
@@ -275,48 +368,60 @@ def sphere_basis_of(field_or_bases):
     return None
 
 
-def components_to_grid(basis, cdata, spins, rank, scales, cs=S2Coordinates):
-    """Coefficient data (ncomp, Nphi/2, Nl) of spin components -> grid data (ncomp, Nphi_g, Ntheta_g) of coordinate
-    components; components of a rank-`rank` tensor in C order.  Components of equal spin weight that are ADJACENT share one
-    launch of the colatitude transform (one pass over that spin weight's matrices)."""
+def _distributed(dist):
+    return dist is not None and dist.size > 1
+
+
+def components_to_grid(basis, cdata, spins, rank, scales, cs=S2Coordinates, dist=None):
+    """Coefficient data (ncomp, local Nphi/2 rows, Nl) of spin components -> grid data (ncomp, Nphi_g, local Ntheta_g) of
+    coordinate components; components of a rank-`rank` tensor in C order.  Components of equal spin weight that are ADJACENT
+    share one launch of the colatitude transform (one pass over that spin weight's matrices).  On P GPUs the azimuth <->
+    colatitude transpose (SphereHop) sits between the spin recombination and the azimuthal FFT."""
     import torch
     ncomp = cdata.shape[0]
     Ng_phi, Ng_theta = basis.grid_shape(scales)
-    cg = torch.empty((ncomp, basis.shape[0], Ng_theta), dtype=cdata.dtype, device=cdata.device)
+    rows = 2 * len(basis.local_wavenumbers(dist))
+    cg = torch.empty((ncomp, rows, Ng_theta), dtype=cdata.dtype, device=cdata.device)
     c = 0
     while c < ncomp:
         c1 = c
         while c1 < ncomp and spins[c1] == spins[c]:
             c1 += 1
-        basis.colatitude_plan(Ng_theta, spins[c]).backward(cdata[c:c1], cg[c:c1], 2)
+        basis.colatitude_plan(Ng_theta, spins[c], dist).backward(cdata[c:c1], cg[c:c1], 2)
         c = c1
     if rank > 0:
         cg2 = torch.empty_like(cg)
-        basis.recombination_table(rank, False, cdata.device, cs).apply(cg, cg2, basis.shape[0] // 2, Ng_theta)
+        basis.recombination_table(rank, False, cdata.device, cs).apply(cg, cg2, rows // 2, Ng_theta)
         cg = cg2
-    g = torch.empty((ncomp, Ng_phi, Ng_theta), dtype=cdata.dtype, device=cdata.device)
-    basis.azimuth_plan(Ng_phi).backward(cg, g, 1)
+    if _distributed(dist):
+        cg = basis.hop(dist).to_grid_side(cg.unsqueeze(-1)).squeeze(-1)
+    g = torch.empty((ncomp, Ng_phi, cg.shape[2]), dtype=cdata.dtype, device=cdata.device)
+    basis.azimuth_plan(Ng_phi).backward(cg.contiguous(), g, 1)
     return g
 
 
-def grid_to_components(basis, gdata, spins, rank, out=None, cs=S2Coordinates):
+def grid_to_components(basis, gdata, spins, rank, out=None, cs=S2Coordinates, dist=None):
     """Inverse chain of components_to_grid."""
     import torch
-    ncomp, Ng_phi, Ng_theta = gdata.shape
-    cg = torch.empty((ncomp, basis.shape[0], Ng_theta), dtype=gdata.dtype, device=gdata.device)
+    ncomp, Ng_phi, tb = gdata.shape
+    cg = torch.empty((ncomp, basis.shape[0], tb), dtype=gdata.dtype, device=gdata.device)
     basis.azimuth_plan(Ng_phi).forward(gdata, cg, 1)
+    if _distributed(dist):
+        cg = basis.hop(dist).to_coeff_side(cg.unsqueeze(-1)).squeeze(-1).contiguous()
+    rows, Ng_theta = cg.shape[1], cg.shape[2]
     if rank > 0:
         cg2 = torch.empty_like(cg)
-        basis.recombination_table(rank, True, gdata.device, cs).apply(cg, cg2, basis.shape[0] // 2, Ng_theta)
+        basis.recombination_table(rank, True, gdata.device, cs).apply(cg, cg2, rows // 2, Ng_theta)
         cg = cg2
     if out is None:
-        out = torch.zeros((ncomp,) + basis.coeff_shape, dtype=gdata.dtype, device=gdata.device)
+        j0, j1 = basis.local_pairs(dist)
+        out = torch.zeros((ncomp, 2 * (j1 - j0), basis.coeff_shape[1]), dtype=gdata.dtype, device=gdata.device)
     c = 0
     while c < ncomp:
         c1 = c
         while c1 < ncomp and spins[c1] == spins[c]:
             c1 += 1
-        basis.colatitude_plan(Ng_theta, spins[c]).forward(cg[c:c1], out[c:c1], 2)
+        basis.colatitude_plan(Ng_theta, spins[c], dist).forward(cg[c:c1], out[c:c1], 2)
         c = c1
     return out
 
@@ -334,15 +439,15 @@ def transform_sphere_field(field, layout):
     spins = [int(s) for s in basis.spin_weights(field.tensorsig).reshape(-1)]
     data = field.device_data()
     ncomp = max(1, len(spins))
+    dist = field.dist
     if layout == 'g':
-        cdata = data.reshape((ncomp,) + basis.coeff_shape).contiguous()
-        g = components_to_grid(basis, cdata, spins, rank, scales, cs)
+        cdata = data.reshape((ncomp,) + tuple(data.shape[len(field.tshape):len(field.tshape) + 2])).contiguous()
+        g = components_to_grid(basis, cdata, spins, rank, scales, cs, dist)
         field.set_device_data(g.reshape(field.tshape + tuple(g.shape[1:]) + trail), 'g')
     else:
-        gshape = basis.grid_shape(scales)
-        gdata = data.reshape((ncomp,) + gshape).contiguous()
-        c = grid_to_components(basis, gdata, spins, rank, cs=cs)
-        field.set_device_data(c.reshape(field.tshape + basis.coeff_shape + trail), 'c')
+        gdata = data.reshape((ncomp,) + tuple(data.shape[len(field.tshape):len(field.tshape) + 2])).contiguous()
+        c = grid_to_components(basis, gdata, spins, rank, cs=cs, dist=dist)
+        field.set_device_data(c.reshape(field.tshape + tuple(c.shape[1:]) + trail), 'c')
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -533,10 +638,12 @@ class SphereSystems:
         eq_rank = [len(eq['tensorsig']) for eq in problem.equations
                    for _ in range(max(int(np.prod([cs.dim for cs in eq['tensorsig']], dtype=int)), 1))]
         var_base = np.cumsum([0] + [max(v.ncomp, 1) for v in variables])
-        plane = int(np.prod(basis.coeff_shape))
+        dist = solver.dist
+        j0, j1 = basis.local_pairs(dist)
+        plane = 2 * (j1 - j0) * basis.coeff_shape[1]                 # the rank's block of the coefficient packing
         var_off = [solver.var_arena.offsets[iv] + c * plane for iv, c in var_comps]
         eq_off = [solver.eq_arena.offsets[ie] + c * plane for ie, c in eq_comps]
-        ms = [m for m in range(basis.shape[0] // 2) if m <= Lmax]
+        ms = sorted(m for m, _ in basis.local_wavenumbers(dist) if m <= Lmax)       # the wavenumbers of this rank's pairs
         systems = []
         kband = 0
         total_valid = 0
@@ -585,7 +692,7 @@ class SphereSystems:
             # arena positions of the unknowns / equation rows
             j, cols = basis.mode_columns(m)
             col_of = cols[lidx - m]
-            pos = (2 * j + part) * basis.coeff_shape[1] + col_of
+            pos = (2 * (j - j0) + part) * basis.coeff_shape[1] + col_of
             xi = np.where(vcol, np.asarray(var_off)[comp] + pos, -1)
             fi = np.where(vrow, np.asarray(eq_off)[comp] + pos, -1)
             systems.append(dict(m=m, n=n, L=mats[0], M=mats[1], xi=xi, fi=fi))
@@ -714,10 +821,17 @@ class SphereRHSPlan:
         dev = solver.device
         basis = self.basis = sphere_basis_of(problem.variables[0])
         variables = problem.variables
-        ax = solver.dist.get_basis_axis(basis)
+        dist = self.dist = solver.dist
+        ax = dist.get_basis_axis(basis)
         self.scales = tuple(basis.dealias)
-        self.gshape = basis.grid_shape(self.scales)
-        plane_c = int(np.prod(basis.coeff_shape))
+        gfull = basis.grid_shape(self.scales)
+        P = dist.size
+        self.gshape = (gfull[0], gfull[1] // P)                      # colatitude is distributed on the grid
+        self.Ngt_full = gfull[1]
+        j0, j1 = basis.local_pairs(dist)
+        self.Nc0 = 2 * (j1 - j0)
+        self.rowsA = 2 * len(basis.local_wavenumbers(dist))
+        plane_c = self.Nc0 * basis.coeff_shape[1]
         state_comp0 = {}
         for iv, v in enumerate(variables):
             assert solver.var_arena.offsets[iv] % plane_c == 0
@@ -802,7 +916,7 @@ class SphereRHSPlan:
         self.trivial = False
         # ---- symbol table on the coefficient packing: sym[l] -> (npair, ncol) array
         _, ell_map = basis.elements_to_groups()
-        ell_pairs = ell_map[0::2]
+        ell_pairs = ell_map[0::2][j0:j1]
         in_range = ell_pairs <= basis.Lmax
         sym_arrays, sym_index = [], {}
 
@@ -867,12 +981,13 @@ class SphereRHSPlan:
         remap = {pr['p0'] + c: fslot[(p, c)] for p, pr in enumerate(products) for c in range(len(pr['spins']))}
         self.post = PairProgram([[(remap[src], coef, so) for src, coef, so in terms] for terms in post_rows], dev, syms)
         # ---- buffers
-        Nc0, Nc1 = basis.coeff_shape
-        Ngp, Ngt = self.gshape
+        Nc0, Nc1 = self.Nc0, basis.coeff_shape[1]
+        Ngp, tb = self.gshape
+        Ngt, rowsA = self.Ngt_full, self.rowsA
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
-        self.c_pre, self.cg_a, self.cg_b = z(self.n_g, Nc0, Nc1), z(self.n_g, basis.shape[0], Ngt), z(self.n_g, basis.shape[0], Ngt)
-        self.g_in, self.g_out = z(self.n_g, Ngp, Ngt), z(self.n_p, Ngp, Ngt)
-        self.pg_a, self.pg_b, self.c_post = z(self.n_p, basis.shape[0], Ngt), z(self.n_p, basis.shape[0], Ngt), z(self.n_p, Nc0, Nc1)
+        self.c_pre, self.cg_a, self.cg_b = z(self.n_g, Nc0, Nc1), z(self.n_g, rowsA, Ngt), z(self.n_g, rowsA, Ngt)
+        self.g_in, self.g_out = z(self.n_g, Ngp, tb), z(self.n_p, Ngp, tb)
+        self.pg_a, self.pg_b, self.c_post = z(self.n_p, basis.shape[0], tb), z(self.n_p, rowsA, Ngt), z(self.n_p, Nc0, Nc1)
 
     def set_static(self, eq_t):
         eq_t.zero_()
@@ -893,21 +1008,27 @@ class SphereRHSPlan:
         if self.trivial:
             eq_t.zero_()
             return
-        basis, solver = self.basis, self.solver
+        basis, solver, dist = self.basis, self.solver, self.dist
         prof = solver.prof
-        Nc0, Nc1 = basis.coeff_shape
-        Ngp, Ngt = self.gshape
-        npair_c, npair_g = Nc0 // 2, basis.shape[0] // 2
+        Nc0, Nc1 = self.Nc0, basis.coeff_shape[1]
+        Ngp, tb = self.gshape
+        Ngt, rowsA = self.Ngt_full, self.rowsA
+        multi = dist.size > 1
+        npair_c, npair_a = Nc0 // 2, rowsA // 2
         with Timed(prof, "sphere_symbols", 8 * Nc0 * Nc1 * (self.n_g + len(solver.state_t) // (Nc0 * Nc1))):
             self.pre.apply(solver.state_t, self.c_pre, npair_c, Nc1)
         for s, c0, c1 in self._groups(self.pre_spins):
-            plan = basis.colatitude_plan(Ngt, s)
-            with Timed(prof, "swsh_backward", plan.matrix_bytes() + 8 * (c1 - c0) * (Nc0 * Nc1 + basis.shape[0] * Ngt)):
+            plan = basis.colatitude_plan(Ngt, s, dist)
+            with Timed(prof, "swsh_backward", plan.matrix_bytes() + 8 * (c1 - c0) * (Nc0 * Nc1 + rowsA * Ngt)):
                 plan.backward(self.c_pre[c0:c1], self.cg_a[c0:c1], 2)
         with Timed(prof, "spin_recombine", 16 * self.cg_a.numel()):
-            self.rec_b.apply(self.cg_a, self.cg_b, npair_g, Ngt)
-        with Timed(prof, "azimuth_backward", 8 * (self.cg_b.numel() + self.g_in.numel())):
-            basis.azimuth_plan(Ngp).backward(self.cg_b, self.g_in, 1)
+            self.rec_b.apply(self.cg_a, self.cg_b, npair_a, Ngt)
+        cgB = self.cg_b
+        if multi:
+            with Timed(prof, "sphere_transpose", 16 * self.cg_b.numel()):
+                cgB = basis.hop(dist).to_grid_side(self.cg_b.unsqueeze(-1)).squeeze(-1).contiguous()
+        with Timed(prof, "azimuth_backward", 8 * (cgB.numel() + self.g_in.numel())):
+            basis.azimuth_plan(Ngp).backward(cgB, self.g_in, 1)
         with Timed(prof, "pointwise", 8 * self.npoints * (self.n_g + self.n_p)):
             if self.pairs is not None and self.g_in.data_ptr() % 16 == 0 and self.g_out.data_ptr() % 16 == 0:
                 get_lib().call("db_pointwise_pairs", self.g_in.data_ptr(), self.g_out.data_ptr(), self.npoints, self.n_g, self.n_p,
@@ -917,11 +1038,15 @@ class SphereRHSPlan:
                                self.term_ptr.data_ptr(), self.coef.data_ptr(), self.fac_ptr.data_ptr(), self.fac.data_ptr(), self.nfac, current_stream())
         with Timed(prof, "azimuth_forward", 8 * (self.g_out.numel() + self.pg_a.numel())):
             basis.azimuth_plan(Ngp).forward(self.g_out, self.pg_a, 1)
-        with Timed(prof, "spin_recombine", 16 * self.pg_a.numel()):
-            self.rec_f.apply(self.pg_a, self.pg_b, npair_g, Ngt)
+        pgA = self.pg_a
+        if multi:
+            with Timed(prof, "sphere_transpose", 16 * self.pg_a.numel()):
+                pgA = basis.hop(dist).to_coeff_side(self.pg_a.unsqueeze(-1)).squeeze(-1).contiguous()
+        with Timed(prof, "spin_recombine", 16 * pgA.numel()):
+            self.rec_f.apply(pgA, self.pg_b, npair_a, Ngt)
         for s, c0, c1 in self._groups(self.post_spins):
-            plan = basis.colatitude_plan(Ngt, s)
-            with Timed(prof, "swsh_forward", plan.matrix_bytes() + 8 * (c1 - c0) * (Nc0 * Nc1 + basis.shape[0] * Ngt)):
+            plan = basis.colatitude_plan(Ngt, s, dist)
+            with Timed(prof, "swsh_forward", plan.matrix_bytes() + 8 * (c1 - c0) * (Nc0 * Nc1 + rowsA * Ngt)):
                 plan.forward(self.pg_b[c0:c1], self.c_post[c0:c1], 2)
         n_eq = len(self.post_rows)
         with Timed(prof, "sphere_symbols", 8 * Nc0 * Nc1 * (self.n_p + n_eq)):

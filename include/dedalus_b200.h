@@ -337,6 +337,9 @@ int db_banded_set_mode(int32_t mode);
  * table: pencil vectors <-> coefficient arrays in the folded triangular (m, l) packing (core/subsystems.py:340-371) */
 int db_index_move(const int64_t* idx, int64_t count, double* arena, double* vec, int32_t gather, void* stream);
 
+/* the same for runs of `run` contiguous doubles per index entry (row permutations around the curvilinear transposes) */
+int db_index_move_runs(const int64_t* idx, int64_t count, int64_t run, double* arena, double* vec, int32_t gather, void* stream);
+
 /* Dense batches with many right-hand sides: the per-degree pencil systems of spherical-shell problems -- ONE matrix per l for all
  * m <= l (core/subsystems.py:272-274: Subproblem.shape = (n, n_subsystems); libraries/matsolvers.py:126-183 per matrix).  Matrices
  * [nsys][n][n] row-major, every system padded to the same n; vectors of system s: element (i, r) at vec_off + i * ncols + r. */
