@@ -207,6 +207,7 @@ class ShellBasis(Basis):
         sb = self.sphere_basis
         out = []
         for sub, g in enumerate((sb.global_grid_azimuth(scales[0]), sb.global_grid_colatitude(scales[1]), self.global_grid_radius(scales[2]))):
+            g = g[dist.grid_local_slice(ax + sub, self, scales[sub])]
             shp = [1] * dist.dim
             shp[ax + sub] = g.size
             out.append(g.reshape(shp))
@@ -237,15 +238,16 @@ class ShellBasis(Basis):
             self._plans[key] = PairProgram.from_matrix(U, device)
         return self._plans[key]
 
-    def regularity_table(self, rank, forward, device):
+    def regularity_table(self, rank, forward, device, dist=None):
         """db_pair_lincomb program of the regularity recombination: out = Q(l)^T in (forward, spin -> regularity) or Q(l) in
         (backward), one real symbol table over the (m, l) packing per nonzero (out, in) pair (reference basis.py:3590-3627)."""
-        key = ('reg', rank, bool(forward), str(device))
+        j0, j1 = self.sphere_basis.local_pairs(dist)
+        key = ('reg', rank, bool(forward), str(device), j0, j1)
         if key not in self._plans:
             import torch
             sb = self.sphere_basis
             _, ell_map = sb.elements_to_groups()
-            ell_pairs = ell_map[0::2]                                   # (npair, Nl)
+            ell_pairs = ell_map[0::2][j0:j1]                            # (local pairs, Nl)
             n = 3 ** rank
             Q = np.zeros((sb.Lmax + 1, n, n))
             for ell in range(sb.Lmax + 1):
@@ -343,60 +345,68 @@ def _spin_groups(spins):
         c = c1
 
 
-def shell_components_to_grid(basis, c, rank, scales):
-    """Regularity components (ncomp, Nphi/2, Nl, Nr) in basis `basis` (its k) -> coordinate components on the grid."""
+def shell_components_to_grid(basis, c, rank, scales, dist=None):
+    """Regularity components (ncomp, local Nphi/2 rows, Nl, Nr) in basis `basis` (its k) -> coordinate components on the
+    (colatitude-distributed) grid."""
     import torch
     sb = basis.sphere_basis
-    ncomp = c.shape[0]
+    ncomp, Nc0 = c.shape[0], c.shape[1]
     spins = ([int(s) for s in basis.spin_weights((basis.coordsys,) * rank).reshape(-1)] if rank else [0])
     Ngp, Ngt, Ngr = basis.grid_shape(scales)
-    Nc0, Nc1, Nr = basis.coeff_shape
-    Nphi = basis.shape[0]
+    Nc1, Nr = basis.coeff_shape[1:]
+    rows = 2 * len(sb.local_wavenumbers(dist))
     dev, dt = c.device, c.dtype
     cr = torch.empty((ncomp, Nc0, Nc1, Ngr), dtype=dt, device=dev)
     basis.radial_plan(Ngr).backward(c, cr, 3)
     if rank > 0:
         tmp = torch.empty_like(cr)
-        basis.regularity_table(rank, False, dev).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
+        basis.regularity_table(rank, False, dev, dist).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
         cr = tmp
     if basis.k > 0:
         cr = cr * torch.from_numpy((basis.dR / basis.global_grid_radius(scales[2])) ** basis.k).to(dev)
-    cg = torch.empty((ncomp, Nphi, Ngt, Ngr), dtype=dt, device=dev)
+    cg = torch.empty((ncomp, rows, Ngt, Ngr), dtype=dt, device=dev)
     for s, c0, c1 in _spin_groups(spins):
-        sb.colatitude_plan(Ngt, s).backward(cr[c0:c1], cg[c0:c1], 2)
+        sb.colatitude_plan(Ngt, s, dist).backward(cr[c0:c1], cg[c0:c1], 2)
     if rank > 0:
         tmp = torch.empty_like(cg)
-        basis.spin_table(rank, False, dev).apply(cg, tmp, Nphi // 2, Ngt * Ngr)
+        basis.spin_table(rank, False, dev).apply(cg, tmp, rows // 2, Ngt * Ngr)
         cg = tmp
-    g = torch.empty((ncomp, Ngp, Ngt, Ngr), dtype=dt, device=dev)
+    if dist is not None and dist.size > 1:
+        cg = sb.hop(dist).to_grid_side(cg).contiguous()
+    g = torch.empty((ncomp, Ngp, cg.shape[2], Ngr), dtype=dt, device=dev)
     sb.azimuth_plan(Ngp).backward(cg, g, 1)
     return g
 
 
-def shell_grid_to_components(basis, g, rank):
-    """Coordinate components on the grid (ncomp, Ngp, Ngt, Ngr) -> regularity components in basis `basis`."""
+def shell_grid_to_components(basis, g, rank, dist=None):
+    """Coordinate components on the grid (ncomp, Ngp, local Ngt, Ngr) -> regularity components in basis `basis`."""
     import torch
     sb = basis.sphere_basis
-    ncomp, Ngp, Ngt, Ngr = g.shape
+    ncomp, Ngp, tb, Ngr = g.shape
     spins = ([int(s) for s in basis.spin_weights((basis.coordsys,) * rank).reshape(-1)] if rank else [0])
-    Nc0, Nc1, Nr = basis.coeff_shape
+    Nc1, Nr = basis.coeff_shape[1:]
+    j0, j1 = sb.local_pairs(dist)
+    Nc0 = 2 * (j1 - j0)
     Nphi = basis.shape[0]
     dev, dt = g.device, g.dtype
-    cg = torch.empty((ncomp, Nphi, Ngt, Ngr), dtype=dt, device=dev)
+    cg = torch.empty((ncomp, Nphi, tb, Ngr), dtype=dt, device=dev)
     sb.azimuth_plan(Ngp).forward(g, cg, 1)
+    if dist is not None and dist.size > 1:
+        cg = sb.hop(dist).to_coeff_side(cg).contiguous()
+    rows, Ngt = cg.shape[1], cg.shape[2]
     if rank > 0:
         tmp = torch.empty_like(cg)
-        basis.spin_table(rank, True, dev).apply(cg, tmp, Nphi // 2, Ngt * Ngr)
+        basis.spin_table(rank, True, dev).apply(cg, tmp, rows // 2, Ngt * Ngr)
         cg = tmp
     cr = torch.zeros((ncomp, Nc0, Nc1, Ngr), dtype=dt, device=dev)
     for s, c0, c1 in _spin_groups(spins):
-        sb.colatitude_plan(Ngt, s).forward(cg[c0:c1], cr[c0:c1], 2)
+        sb.colatitude_plan(Ngt, s, dist).forward(cg[c0:c1], cr[c0:c1], 2)
     if basis.k > 0:
         scale = Ngr / basis.shape[2]
         cr = cr * torch.from_numpy((basis.dR / basis.global_grid_radius(scale)) ** (-basis.k)).to(dev)
     if rank > 0:
         tmp = torch.empty_like(cr)
-        basis.regularity_table(rank, True, dev).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
+        basis.regularity_table(rank, True, dev, dist).apply(cr, tmp, Nc0 // 2, Nc1 * Ngr, sym_div=Ngr)
         cr = tmp
     c = torch.empty((ncomp, Nc0, Nc1, Nr), dtype=dt, device=dev)
     basis.radial_plan(Ngr).forward(cr.contiguous(), c, 3)
@@ -413,12 +423,13 @@ def transform_shell_field(field, layout):
     rank = len(field.tensorsig)
     ncomp = max(field.ncomp, 1)
     data = field.device_data()
+    nt = len(field.tshape)
     if layout == 'g':
-        g = shell_components_to_grid(basis, data.reshape((ncomp,) + basis.coeff_shape).contiguous(), rank, scales)
+        g = shell_components_to_grid(basis, data.reshape((ncomp,) + tuple(data.shape[nt:])).contiguous(), rank, scales, field.dist)
         field.set_device_data(g.reshape(field.tshape + tuple(g.shape[1:])), 'g')
     else:
-        c = shell_grid_to_components(basis, data.reshape((ncomp,) + basis.grid_shape(scales)).contiguous(), rank)
-        field.set_device_data(c.reshape(field.tshape + basis.coeff_shape), 'c')
+        c = shell_grid_to_components(basis, data.reshape((ncomp,) + tuple(data.shape[nt:])).contiguous(), rank, field.dist)
+        field.set_device_data(c.reshape(field.tshape + tuple(c.shape[1:])), 'c')
 
 
 def transform_radial_field(field, layout):

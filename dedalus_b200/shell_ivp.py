@@ -404,7 +404,10 @@ class ShellSystems:
         basis = low.basis
         sb = basis.sphere_basis
         Lmax, Nphi = basis.Lmax, basis.shape[0]
-        Nc0, Nc1, Nr = basis.coeff_shape
+        dist = solver.dist
+        j0, j1 = sb.local_pairs(dist)
+        Nc0, Nc1, Nr = 2 * (j1 - j0), basis.coeff_shape[1], basis.coeff_shape[2]
+        local_ms = sorted(m for m, _ in sb.local_wavenumbers(dist))
         per_l = []
         for ell in range(Lmax + 1):
             M, L, rows, cols = assemble(low, ell)
@@ -430,16 +433,17 @@ class ShellSystems:
         eq_items = [(low.kind_of(eq['LHS'])[0], len(eq['tensorsig'])) for eq in problem.equations]
         self.total_modes = 0
         for ell, p in enumerate(per_l):
-            mmax = min(ell, Nphi // 2 - 1)
-            ncols = 2 * (mmax + 1)
+            ms_l = [m for m in local_ms if m <= ell and mode[m][0] is not None]       # this rank's columns of degree l
+            ncols = 2 * len(ms_l)
             arr[ell].ncols, arr[ell].vec_off = ncols, vec_off
             for side, layout, valid, arena, items in ((0, p['cols'], p['vc'], solver.var_arena, var_items),
                                                       (1, p['rows'], p['vr'], solver.eq_arena, eq_items)):
                 idx = np.full((n, ncols), -1, dtype=np.int64)
                 i = 0
-                ms = np.array([m for m in range(mmax + 1) if mode[m][0] is not None], dtype=np.int64)
-                js = np.array([mode[m][0] for m in ms], dtype=np.int64)
-                slots = np.array([mode[m][1][ell - m] for m in ms], dtype=np.int64)
+                ms = np.array(ms_l, dtype=np.int64)
+                cpos = np.arange(len(ms_l), dtype=np.int64)                               # column pair of each local m
+                js = np.array([mode[m][0] - j0 for m in ms_l], dtype=np.int64)
+                slots = np.array([mode[m][1][ell - m] for m in ms_l], dtype=np.int64)
                 for comp in layout:
                     if not comp['valid']:
                         continue
@@ -447,19 +451,21 @@ class ShellSystems:
                     nrad = comp['n']
                     base = arena.offsets[comp['item']]
                     if kind == 'const':
-                        idx[i, 0] = base
+                        if ncols and ms_l[0] == 0:
+                            idx[i, 0] = base
                         i += 1
                         continue
                     plane = Nc0 * Nc1 * nrad
                     nr = np.arange(nrad)[:, None]
                     for part in (0, 1):
-                        idx[i:i + nrad, 2 * ms + part] = (base + comp['comp'] * plane + ((2 * js + part) * Nc1 + slots)[None, :] * nrad + nr)
+                        if ncols:
+                            idx[i:i + nrad, 2 * cpos + part] = (base + comp['comp'] * plane + ((2 * js + part) * Nc1 + slots)[None, :] * nrad + nr)
                     i += nrad
                 (xi_all if side == 0 else fi_all).append(idx.ravel())
             self.total_modes += int(p['vc'].sum()) * ncols
             vec_off += n * ncols
-        self.nvec = vec_off
-        self.max_ncols = max(a.ncols for a in arr)
+        self.nvec = max(vec_off, 1)
+        self.max_ncols = max(max(a.ncols for a in arr), 1)
         t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         self.M_t, self.L_t = t64(Mall), t64(Lall)
         self.desc = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(dev)
@@ -554,9 +560,13 @@ class ShellRHSPlan:
         basis = self.basis = low.basis
         self.rops = low.rops
         sb = basis.sphere_basis
-        Nc0, Nc1, Nr = basis.coeff_shape
+        dist = self.dist = solver.dist
+        j0, j1 = sb.local_pairs(dist)
+        Nc0, Nc1, Nr = 2 * (j1 - j0), basis.coeff_shape[1], basis.coeff_shape[2]
+        self.cshape = (Nc0, Nc1, Nr)
         self.scales = tuple(basis.dealias)
-        self.gshape = basis.grid_shape(self.scales)
+        gfull = basis.grid_shape(self.scales)
+        self.gshape = (gfull[0], gfull[1] // dist.size, gfull[2])
         self.npoints = int(np.prod(self.gshape))
         variables = problem.variables
         plane = Nc0 * Nc1 * Nr
@@ -625,7 +635,7 @@ class ShellRHSPlan:
             return
         # ---- gradient programs: stacked input [D0_- x, D0_+ x, AB x / dR] per field
         _, ell_map = sb.elements_to_groups()
-        ell_pairs = ell_map[0::2]
+        ell_pairs = ell_map[0::2][j0:j1]
         in_range = ell_pairs <= sb.Lmax
         lidx = np.minimum(ell_pairs, sb.Lmax)
         self.grads = {}
@@ -695,6 +705,8 @@ class ShellRHSPlan:
         if eq['tensorsig']:
             raise NotImplementedError("nonzero constant right-hand side of a tensor equation")
         off = self.solver.eq_arena.offsets[ie]
+        if low.basis.sphere_basis.local_pairs(self.solver.dist)[0] != 0:
+            return                                             # the l = 0, m = 0 mode lives on the rank that owns pair 0
         if kind == 'sphere':
             self.static.append((off, value * np.sqrt(2)))
         elif kind == 'const':
@@ -722,7 +734,7 @@ class ShellRHSPlan:
             return
         solver, basis = self.solver, self.basis
         prof = solver.prof
-        Nc0, Nc1, Nr = basis.coeff_shape
+        Nc0, Nc1, Nr = self.cshape
         views = {id(v): view for v, view in zip(solver.state, solver.state_views)}
         grads = {}
         for o in self.operands:
@@ -740,7 +752,7 @@ class ShellRHSPlan:
                     grads[id(f)] = out
                 c = grads[id(f)]
             with Timed(prof, "shell_backward", 8 * (c.numel() + 3 ** o['rank'] * self.npoints)):
-                g = shell_components_to_grid(self._basis_k(o['k']), c.contiguous(), o['rank'], self.scales)
+                g = shell_components_to_grid(self._basis_k(o['k']), c.contiguous(), o['rank'], self.scales, self.dist)
             self.g_in[o['g0']:o['g0'] + 3 ** o['rank']].copy_(g)
         with Timed(prof, "pointwise", 8 * self.npoints * (self.n_g + self.n_p)):
             get_lib().call("db_pointwise", self.g_in.data_ptr(), self.g_out.data_ptr(), self.npoints, self.n_g, self.n_p,
@@ -748,7 +760,7 @@ class ShellRHSPlan:
         p0 = 0
         for p in self.products:
             with Timed(prof, "shell_forward", 8 * p['ncomp'] * (self.npoints + Nc0 * Nc1 * Nr)):
-                c = shell_grid_to_components(self._basis_k(p['k']), self.g_out[p0:p0 + p['ncomp']].contiguous(), p['rank'])
+                c = shell_grid_to_components(self._basis_k(p['k']), self.g_out[p0:p0 + p['ncomp']].contiguous(), p['rank'], self.dist)
             off = solver.eq_arena.offsets[p['eq']]
             dst = eq_t[off:off + c.numel()].view(c.shape)
             if p['k_eq'] != p['k']:

@@ -71,6 +71,31 @@ def main():
             print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
         dist.destroy_process_group()
         return
+    if which.startswith("shell:"):
+        # shell convection (config 5's problem) distributed over the azimuthal pairs / colatitude against the reference state
+        tag = which.split(":")[1]
+        g = np.load(ROOT / "tests" / "golden" / "shell_ivp.npz")
+        Nphi, Ntheta, Nr, steps, dt = g[f"{tag}_meta"]
+        sc = examples.shell_convection(int(Nphi), int(Ntheta), int(Nr))
+        solver = sc['problem'].build_solver(d3.SBDF2 if "sbdf2" in tag else d3.RK222)
+        examples.shell_convection_initial_condition(sc['b'], sc['shell'], sc['Ri'], sc['Ro'])
+        rows = sc['dist'].coeff_local_slice(0, sc['shell'])
+        ok = bool(np.allclose(sc['b']['c'], g[f"{tag}_b0"][rows], rtol=1e-11, atol=1e-13))
+        for _ in range(int(steps)):
+            solver.step(float(dt))
+        floor = 1e-13 * np.abs(g[f"{tag}_b1"]).max()
+        for name in ('p', 'b', 'u'):
+            full = g[f"{tag}_{name}1"]
+            ok = ok and bool(np.allclose(sc[name]['c'], full[..., rows, :, :], rtol=1e-8, atol=1e-10 * np.abs(full).max() + floor))
+        for name in ('tau_b1', 'tau_b2', 'tau_u1', 'tau_u2'):
+            full = g[f"{tag}_{name}1"]
+            ok = ok and bool(np.allclose(sc['taus'][name]['c'], full[..., rows, :, :], rtol=1e-6, atol=1e-4 * np.abs(full).max() + 1e-20))
+        flag = torch.tensor([1 if ok else 0], device='cuda' if backend == "nccl" else 'cpu')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
+        dist.destroy_process_group()
+        return
     g = np.load(ROOT / "tests" / "golden" / which)
     dim, Nh, Nz = int(g['dim']), int(g['Nh']), int(g['Nz'])
     pb = examples.rayleigh_benard(dim=dim, Nh=Nh, Nz=Nz, Rayleigh=float(g['Ra']), mesh=(world,))
