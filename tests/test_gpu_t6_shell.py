@@ -26,3 +26,18 @@ def test_shell_convection_matches_reference(golden, tag, scheme):
     """BASELINE config 5's problem (shell convection) at 16 x 8 x 6 and 32 x 16 x 12 against the reference."""
     solver = SC.check_shell_convection(golden("shell_ivp.npz"), tag, scheme)
     assert solver.bset.last_verify < 1e-12
+
+
+@pytest.mark.parametrize("which", ["sphere:sw16", "sphere:sw32", "shell:a_sbdf2", "shell:b_sbdf2"])
+def test_two_gpu_curvilinear_matches_reference(which):
+    """Sphere / shell problems on 2 GPUs over NCCL (coefficients distributed over the azimuthal pairs, grid over colatitude)
+    against the single-rank reference states."""
+    import torch, subprocess, sys, os, socket, pathlib
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = pathlib.Path(__file__).resolve().parents[1]
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(root / "tests" / "dist_worker.py"), which]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, DB_DIST_BACKEND="nccl"))
+    assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
