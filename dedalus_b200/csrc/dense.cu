@@ -174,3 +174,42 @@ extern "C" int db_dense_matvec(const db_dense_sys* sys, int32_t nsys, int32_t n,
     DB_LAUNCH(k_dense_matvec, dim3((unsigned)nsys, 16), dim3(256), 0, stream, sys, n, a, b, x, ya, yb);
     return db_check_launch("dense_matvec");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Sparse form of the same products: the pencil OPERATORS M, L of a shell problem are 3-4 % dense (banded blocks + boundary rows
+// + tau columns; only their LU factors fill in), so M.X and L.X use CSR: ptr [nsys][n + 1] with offsets into col / val that are
+// global over the batch.  Thread = (row, column) of one system; either matrix may be absent (ptr == NULL).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_csr_matvec(const db_dense_sys* __restrict__ sys, int n, const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_col,
+             const double* __restrict__ a_val, const int64_t* __restrict__ b_ptr, const int32_t* __restrict__ b_col,
+             const double* __restrict__ b_val, const double* __restrict__ x, double* __restrict__ ya, double* __restrict__ yb)
+{
+    const db_dense_sys S = sys[blockIdx.x];
+    const int64_t total = (int64_t)n * S.ncols;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.y * blockDim.x) {
+        const int i = (int)(e / S.ncols); const int r = (int)(e - (int64_t)i * S.ncols);
+        const double* __restrict__ xr = x + S.vec_off + r;
+        if (ya) {
+            double s = 0.0;
+            const int64_t p0 = a_ptr[(int64_t)blockIdx.x * (n + 1) + i], p1 = a_ptr[(int64_t)blockIdx.x * (n + 1) + i + 1];
+            for (int64_t p = p0; p < p1; ++p) s = fma(a_val[p], xr[(int64_t)a_col[p] * S.ncols], s);
+            ya[S.vec_off + e] = s;
+        }
+        if (yb) {
+            double s = 0.0;
+            const int64_t p0 = b_ptr[(int64_t)blockIdx.x * (n + 1) + i], p1 = b_ptr[(int64_t)blockIdx.x * (n + 1) + i + 1];
+            for (int64_t p = p0; p < p1; ++p) s = fma(b_val[p], xr[(int64_t)b_col[p] * S.ncols], s);
+            yb[S.vec_off + e] = s;
+        }
+    }
+}
+
+extern "C" int db_csr_matvec(const db_dense_sys* sys, int32_t nsys, int32_t n, const int64_t* a_ptr, const int32_t* a_col, const double* a_val,
+                             const int64_t* b_ptr, const int32_t* b_col, const double* b_val, const double* x, double* ya, double* yb,
+                             void* stream)
+{
+    if (nsys <= 0 || n <= 0) return 0;
+    DB_LAUNCH(k_csr_matvec, dim3((unsigned)nsys, 16), dim3(256), 0, stream, sys, n, a_ptr, a_col, a_val, b_ptr, b_col, b_val, x, ya, yb);
+    return db_check_launch("csr_matvec");
+}

@@ -120,6 +120,7 @@ SIGNATURES = {
     "db_dense_factor": (C.c_int, [i32, i32, vp, vp, vp, vp]),
     "db_dense_solve": (C.c_int, [vp, i32, i32, i32, vp, vp, C.POINTER(VecComb), vp, vp]),
     "db_dense_matvec": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "db_csr_matvec": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "db_index_move": (C.c_int, [vp, i64, vp, vp, i32, vp]),
     "db_index_move_runs": (C.c_int, [vp, i64, i64, vp, vp, i32, vp]),
     "db_pair_lincomb": (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, i64, vp]),

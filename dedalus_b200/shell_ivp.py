@@ -467,7 +467,16 @@ class ShellSystems:
         self.nvec = max(vec_off, 1)
         self.max_ncols = max(max(a.ncols for a in arr), 1)
         t64 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        self.M_t, self.L_t = t64(Mall), t64(Lall)
+        self.M_t, self.L_t = t64(Mall), t64(Lall)                       # dense: the LHS a0 M + b0 L is factorised in this form
+        self.csr = {}
+        for name, A in (('M', Mall), ('L', Lall)):                       # CSR: the operators are a few percent dense (mat-vecs)
+            nz = A != 0
+            counts = nz.sum(axis=2)                                       # (nsys, n)
+            ptr = np.zeros((self.nsys, n + 1), dtype=np.int64)
+            ptr[:, 1:] = np.cumsum(counts, axis=1)
+            ptr += np.concatenate([[0], np.cumsum(counts.sum(axis=1))[:-1]])[:, None]
+            s_, r_, c_ = np.nonzero(nz)
+            self.csr[name] = (t64(ptr), t64(c_.astype(np.int32)), t64(A[s_, r_, c_]))
         self.desc = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(dev)
         self.idx = [t64(np.concatenate(xi_all)), t64(np.concatenate(fi_all))]
         self.vecs = [torch.zeros(self.nvec, dtype=torch.float64, device=dev) for _ in range(nslots)]
@@ -489,9 +498,10 @@ class ShellSystems:
         ym = self.vecs[ym_slot].data_ptr() if ym_slot >= 0 else None
         yl = self.vecs[yl_slot].data_ptr() if yl_slot >= 0 else None
         nout = (ym_slot >= 0) + (yl_slot >= 0)
-        with Timed(self.solver.prof, "pencil_matvec", 8 * (self.nsys * self.n * self.n * nout + (1 + nout) * self.nvec)):
-            self._call("db_dense_matvec", self.desc.data_ptr(), self.nsys, self.n, self.M_t.data_ptr(), self.L_t.data_ptr(),
-                       self.vecs[x_slot].data_ptr(), ym, yl)
+        (mp, mc, mv), (lp, lc, lv) = self.csr['M'], self.csr['L']
+        with Timed(self.solver.prof, "pencil_matvec", 12 * (mv.numel() * (ym_slot >= 0) + lv.numel() * (yl_slot >= 0)) + 8 * (1 + nout) * self.nvec):
+            self._call("db_csr_matvec", self.desc.data_ptr(), self.nsys, self.n, mp.data_ptr(), mc.data_ptr(), mv.data_ptr(),
+                       lp.data_ptr(), lc.data_ptr(), lv.data_ptr(), self.vecs[x_slot].data_ptr(), ym, yl)
 
     def solve(self, lu_slot, x_slot, terms):
         import ctypes as C

@@ -354,6 +354,11 @@ int db_dense_solve(const db_dense_sys* sys, int32_t nsys, int32_t n, int32_t max
 int db_dense_matvec(const db_dense_sys* sys, int32_t nsys, int32_t n, const double* a, const double* b, const double* x,
                     double* ya, double* yb, void* stream);
 
+/* the same products with the operators in CSR (ptr [nsys][n + 1], offsets into col / val global over the batch): the pencil
+ * operators M, L of shell problems are a few percent dense, only their factors fill in */
+int db_csr_matvec(const db_dense_sys* sys, int32_t nsys, int32_t n, const int64_t* a_ptr, const int32_t* a_col, const double* a_val,
+                  const int64_t* b_ptr, const int32_t* b_col, const double* b_val, const double* x, double* ya, double* yb, void* stream);
+
 /* Complex linear combinations on (cos, -sin) pairs.  in / out: (ncomp, 2 * npair, ncol), rows 2j and 2j + 1 = real and
  * imaginary part of the exp(i m phi) coefficient (core/basis.py:1108-1134).  Output o = sum over its terms
  * term_ptr[o] <= t < term_ptr[o + 1] of (re + i im) * sym * in[src], sym = syms[sym_off + (j * ncol + c) / sym_div] or 1 (sym_off < 0);

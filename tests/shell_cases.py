@@ -129,9 +129,24 @@ def check_dense_kernels(B):
     vc.coef[0], vc.coef[1] = 2.0, -0.5
     B.lib.call("db_dense_solve", P(sysb), nsys, n, max(ncols), P(lu), P(ipiv), C.byref(vc), P(x), B.stream)
     B.lib.call("db_dense_matvec", P(sysb), nsys, n, P(Ad), P(Bd), P(x), P(ya), P(yb), B.stream)
+    # the same products with the operators in CSR (one of them made sparse)
+    As = A * (rng.random(A.shape) < 0.2)
+    def csr(Mx):
+        nz = Mx != 0
+        counts = nz.sum(axis=2)
+        ptr = np.zeros((nsys, n + 1), dtype=np.int64); ptr[:, 1:] = np.cumsum(counts, axis=1)
+        ptr += np.concatenate([[0], np.cumsum(counts.sum(axis=1))[:-1]])[:, None]
+        s_, r_, c_ = np.nonzero(nz)
+        return B.dev(ptr), B.dev(c_.astype(np.int32)), B.dev(Mx[s_, r_, c_])
+    (ap, ac, av), (bp, bc, bv) = csr(As), csr(Bm)
+    za, zb = B.dev(np.zeros(off)), B.dev(np.zeros(off))
+    B.lib.call("db_csr_matvec", P(sysb), nsys, n, P(ap), P(ac), P(av), P(bp), P(bc), P(bv), P(x), P(za), P(zb), B.stream)
+    zah, zbh = B.host(za), B.host(zb)
     xh, yah, ybh = B.host(x), B.host(ya), B.host(yb)
     for i, nc in enumerate(ncols):
         o = sysarr[i].vec_off
+        assert np.allclose(zah[o:o + n * nc].reshape(n, nc), As[i] @ xh[o:o + n * nc].reshape(n, nc), rtol=1e-12, atol=1e-12)
+        assert np.allclose(zbh[o:o + n * nc].reshape(n, nc), Bm[i] @ xh[o:o + n * nc].reshape(n, nc), rtol=1e-12, atol=1e-12)
         b = (2 * v1h[o:o + n * nc] - 0.5 * v2h[o:o + n * nc]).reshape(n, nc)
         xr = np.linalg.solve(a0 * A[i] + b0 * Bm[i], b)
         xg = xh[o:o + n * nc].reshape(n, nc)
