@@ -9,8 +9,10 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--problem", default="shallow_water", choices=["shallow_water", "shell_convection"])
     ap.add_argument("--nphi", type=int, default=512)
     ap.add_argument("--ntheta", type=int, default=256)
+    ap.add_argument("--nr", type=int, default=128)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -20,9 +22,15 @@ def main():
     from dedalus_b200.lib import get_lib
     torch.cuda.set_device(0)
     t0 = time.time()
-    sw = examples.shallow_water(args.nphi, args.ntheta)
-    solver = sw['problem'].build_solver(d3.RK222)
-    examples.shallow_water_initial_condition(sw['u'], sw['h'], sw['basis'], sw['units'])
+    if args.problem == "shell_convection":          # config 5's problem (single GPU): python scripts/sphere_bench.py --problem shell_convection --nphi 256 --ntheta 128
+        sw = examples.shell_convection(args.nphi, args.ntheta, args.nr)
+        solver = sw['problem'].build_solver(d3.SBDF2)
+        examples.shell_convection_initial_condition(sw['b'], sw['shell'], sw['Ri'], sw['Ro'])
+        sw.update(h=sw['b'], basis=sw['shell'].sphere_basis, timestep=0.05)
+    else:
+        sw = examples.shallow_water(args.nphi, args.ntheta)
+        solver = sw['problem'].build_solver(d3.RK222)
+        examples.shallow_water_initial_condition(sw['u'], sw['h'], sw['basis'], sw['units'])
     dt = sw['timestep']
     for _ in range(max(args.warmup, 3)):
         solver.step(dt)
@@ -52,10 +60,12 @@ def main():
                        gbps=d['bytes'] / (d['ms'] * 1e-3) / 1e9 if d['ms'] > 0 else None)
                for k, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])}
     u, h = sw['u']['c'], sw['h']['c']
-    print(json.dumps(dict(metric=f"timesteps/sec spherical shallow water {args.nphi}x{args.ntheta} (Lmax={sw['basis'].Lmax}) fp64 RK222, 1 B200",
+    print(json.dumps(dict(metric=f"timesteps/sec {args.problem} {args.nphi}x{args.ntheta}" + (f"x{args.nr}" if args.problem == "shell_convection" else "") +
+                                 f" (Lmax={sw['basis'].Lmax}) fp64, 1 B200",
                           value=args.steps / (ms * 1e-3), unit="steps/s", ms_per_step=ms / args.steps, steps=args.steps,
                           gpu_launches_per_step=launches / args.steps, setup_seconds=setup_s, kernels=kernels,
-                          pencil_systems=solver.bset.nsys, band=(solver.bset.kl, solver.bset.ku), max_n=solver.bset.max_n,
+                          pencil_systems=solver.bset.nsys, band=(getattr(solver.bset, 'kl', None), getattr(solver.bset, 'ku', None)),
+                          max_n=getattr(solver.bset, 'max_n', getattr(solver.bset, 'n', None)),
                           factor_backward_error=solver.bset.last_verify, finite=bool(np_finite(u) and np_finite(h)),
                           steps_taken=int(solver.iteration))))
 

@@ -33,6 +33,13 @@ def test_shallow_water_rk443_with_timestep_changes_matches_oracle():
     S.check_against_oracle(16, 8, "RK443", [dt, dt, dt / 2, dt / 2, dt])
 
 
+def test_shallow_water_with_shifted_packing_matches_oracle():
+    """Ntheta > Nphi / 2: the folded triangular packing has shift > 0 and wavenumber Nphi/2 - 1 lives in the extra columns of pair 0."""
+    dt = 1 / 12
+    solver = S.check_against_oracle(16, 12, "RK222", [dt, dt / 2])
+    assert solver.bset.nsys == 8
+
+
 class _EmuArrays:
     """numpy arrays + the emulated library, behind the small interface sphere_cases.check_banded_* use."""
     lib = property(lambda self: E.emu())
