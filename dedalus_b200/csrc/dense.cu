@@ -9,6 +9,7 @@
 //     matvec :  y = A x for one or two matrices (M.X, L.X)
 // Vectors of system s: element (i, r) at vec_off + i * ncols + r  (ncols = right-hand sides of that system).
 #include "db_common.cuh"
+#include <cstdlib>
 
 #define DN_THREADS 256
 
@@ -100,20 +101,30 @@ extern "C" int db_dense_factor(int32_t nsys, int32_t n, double* a, int32_t* ipiv
 // Solve for all columns: thread = one column of one system (CTA = 32 columns).  b = P (sum_k coef_k v_k) is built in x, then
 // forward (unit lower) and backward sweeps run in place; rows of L / U are the same for every lane (broadcast loads).
 // ---------------------------------------------------------------------------------------------------------
+template <bool SMEM>
 __global__ void __launch_bounds__(32)
 k_dense_solve(const db_dense_sys* __restrict__ sys, int n, const double* __restrict__ lu_all, const int32_t* __restrict__ ipiv_all,
               db_veccomb rhs, double* __restrict__ x_all)
 {
+    // SMEM: the 32 columns of the CTA live in shared memory ([n][32], conflict-free: lane = column) for both sweeps, so the only
+    // global traffic of the sweeps is the factor rows, read once per CTA as broadcast loads; otherwise the columns stay in x.
+    DB_SMEM(double, xs);
     const db_dense_sys S = sys[blockIdx.x];
-    const int r = blockIdx.y * 32 + threadIdx.x;
-    if (r >= S.ncols) return;
+    const int lane = threadIdx.x;
+    const int r = blockIdx.y * 32 + lane;
+    if (blockIdx.y * 32 >= S.ncols) return;
+    const bool live = r < S.ncols;
     const double* __restrict__ LU = lu_all + (int64_t)blockIdx.x * n * n;
     const int32_t* __restrict__ ipiv = ipiv_all + (int64_t)blockIdx.x * n;
-    double* __restrict__ x = x_all + S.vec_off + r;
-    const int64_t ld = S.ncols;
+    double* __restrict__ xg = x_all + S.vec_off + (live ? r : 0);
+    const int64_t ldg = S.ncols;
+    double* __restrict__ x = SMEM ? xs + lane : xg;
+    const int64_t ld = SMEM ? 32 : ldg;
+    if (!SMEM && !live) return;
     for (int i = 0; i < n; ++i) {
         double acc = 0.0;
-        for (int k = 0; k < rhs.nvec; ++k) acc = fma(rhs.coef[k], rhs.vec[k][S.vec_off + (int64_t)i * ld + r], acc);
+        if (live)
+            for (int k = 0; k < rhs.nvec; ++k) acc = fma(rhs.coef[k], rhs.vec[k][S.vec_off + (int64_t)i * ldg + r], acc);
         x[(int64_t)i * ld] = acc;
     }
     for (int k = 0; k < n; ++k) {
@@ -122,16 +133,32 @@ k_dense_solve(const db_dense_sys* __restrict__ sys, int n, const double* __restr
     }
     for (int i = 1; i < n; ++i) {
         const double* __restrict__ row = LU + (int64_t)i * n;
-        double acc = x[(int64_t)i * ld];
-        for (int j = 0; j < i; ++j) acc = fma(-row[j], x[(int64_t)j * ld], acc);
-        x[(int64_t)i * ld] = acc;
+        double a0 = x[(int64_t)i * ld], a1 = 0.0, a2 = 0.0, a3 = 0.0;           // four chains: the FMA latency is not the bound
+        int j = 0;
+        for (; j + 4 <= i; j += 4) {
+            a0 = fma(-row[j], x[(int64_t)j * ld], a0);
+            a1 = fma(-row[j + 1], x[(int64_t)(j + 1) * ld], a1);
+            a2 = fma(-row[j + 2], x[(int64_t)(j + 2) * ld], a2);
+            a3 = fma(-row[j + 3], x[(int64_t)(j + 3) * ld], a3);
+        }
+        for (; j < i; ++j) a0 = fma(-row[j], x[(int64_t)j * ld], a0);
+        x[(int64_t)i * ld] = (a0 + a1) + (a2 + a3);
     }
     for (int i = n - 1; i >= 0; --i) {
         const double* __restrict__ row = LU + (int64_t)i * n;
-        double acc = x[(int64_t)i * ld];
-        for (int j = i + 1; j < n; ++j) acc = fma(-row[j], x[(int64_t)j * ld], acc);
-        x[(int64_t)i * ld] = acc / row[i];
+        double a0 = x[(int64_t)i * ld], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int j = i + 1;
+        for (; j + 4 <= n; j += 4) {
+            a0 = fma(-row[j], x[(int64_t)j * ld], a0);
+            a1 = fma(-row[j + 1], x[(int64_t)(j + 1) * ld], a1);
+            a2 = fma(-row[j + 2], x[(int64_t)(j + 2) * ld], a2);
+            a3 = fma(-row[j + 3], x[(int64_t)(j + 3) * ld], a3);
+        }
+        for (; j < n; ++j) a0 = fma(-row[j], x[(int64_t)j * ld], a0);
+        x[(int64_t)i * ld] = ((a0 + a1) + (a2 + a3)) / row[i];
     }
+    if (SMEM && live)
+        for (int i = 0; i < n; ++i) xg[(int64_t)i * ldg] = x[(int64_t)i * ld];
 }
 
 extern "C" int db_dense_solve(const db_dense_sys* sys, int32_t nsys, int32_t n, int32_t max_ncols, const double* lu, const int32_t* ipiv,
@@ -139,7 +166,16 @@ extern "C" int db_dense_solve(const db_dense_sys* sys, int32_t nsys, int32_t n, 
 {
     if (nsys <= 0 || n <= 0 || max_ncols <= 0) return 0;
     if (rhs->nvec < 1 || rhs->nvec > 16) { db_set_error("dense_solve: 1..16 right-hand-side vectors"); return 1; }
-    DB_LAUNCH(k_dense_solve, dim3((unsigned)nsys, (unsigned)((max_ncols + 31) / 32)), dim3(32), 0, stream, sys, n, lu, ipiv, *rhs, x);
+    const dim3 grid((unsigned)nsys, (unsigned)((max_ncols + 31) / 32));
+    const size_t smem = (size_t)n * 32 * sizeof(double);
+    const char* env = getenv("DB_DENSE_SOLVE_SMEM");          // "0": keep the columns in global memory (the path taken for n > 800)
+    if (smem <= 200 * 1024 && !(env && env[0] == '0')) {
+        static bool attr_set = false;
+        if (!attr_set) { DB_SET_SMEM_ATTR(k_dense_solve<true>); attr_set = true; }
+        DB_LAUNCH(k_dense_solve<true>, grid, dim3(32), smem, stream, sys, n, lu, ipiv, *rhs, x);
+    } else {
+        DB_LAUNCH(k_dense_solve<false>, grid, dim3(32), 0, stream, sys, n, lu, ipiv, *rhs, x);
+    }
     return db_check_launch("dense_solve");
 }
 

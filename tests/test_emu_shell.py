@@ -31,6 +31,9 @@ def test_shell_convection_matches_reference(golden, tag, scheme):
     assert solver.bset.last_verify < 1e-12
 
 
-def test_dense_kernels_against_numpy():
+@pytest.mark.parametrize("smem", ["1", "0"])
+def test_dense_kernels_against_numpy(smem, monkeypatch):
+    """smem = 0: the solve variant that keeps the columns in global memory (systems too large for shared memory)."""
     from test_emu_sphere import _EmuArrays
+    monkeypatch.setenv("DB_DENSE_SOLVE_SMEM", smem)
     SC.check_dense_kernels(_EmuArrays())
