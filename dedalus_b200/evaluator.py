@@ -581,4 +581,9 @@ class RHSPlan:
 
 
 def evaluate_expression(expr):
-    raise NotImplementedError("Stand-alone expression evaluation is not implemented yet; use solver RHS plans.")
+    """Stand-alone evaluation (reference Future.evaluate): separable operator expressions of sphere fields only."""
+    from .sphere import sphere_basis_of, evaluate_linear_expression
+    if sphere_basis_of(expr) is not None:
+        return evaluate_linear_expression(expr)
+    raise NotImplementedError("Stand-alone expression evaluation is only implemented for separable operators of sphere fields; "
+                              "other expressions are evaluated inside the solver's RHS plan.")

@@ -7,8 +7,9 @@ state field from grid-space data of one write).
 
 The reference writes HDF5 through h5py, which is not installable in this image; the SAME logical layout is written as one
 `.npz` archive per set (`<base>/<base>_s<set>[_p<rank>].npz`, keys `scales/...`, `tasks/...`), or as real HDF5 when h5py is
-importable.  Tasks are fields (or components of the state); general operator expressions are evaluated only inside the
-solver's RHS plan and are not accepted here.  The data come from the fields' device buffers through the same transform
+importable.  Tasks are fields, or operator expressions that `evaluator.evaluate_expression` can evaluate on the device (separable
+operators of sphere fields, e.g. the vorticity task of the stock shallow-water script); other expressions are evaluated only
+inside the solver's RHS plan and raise here.  The data come from the fields' device buffers through the same transform
 kernels as everything else (`field['g']` / `field['c']`); nothing is recomputed on the host."""
 import pathlib
 import time
@@ -48,11 +49,17 @@ class Handler:
 
     def add_task(self, task, layout='g', name=None, scales=None):
         from .field import Field
-        if not isinstance(task, Field):
-            raise NotImplementedError("output tasks must be fields (operator expressions are only evaluated inside the RHS plan)")
+        from .operators import Operand
+        if not isinstance(task, Operand):
+            raise ValueError("output tasks must be fields or operator expressions")
         if layout not in ('g', 'c'):
             raise ValueError("layout must be 'g' or 'c'")
-        self.tasks.append(dict(field=task, layout=layout, name=name or task.name or f"task{len(self.tasks)}", scales=scales))
+        if isinstance(task, Field):
+            self.tasks.append(dict(field=task, layout=layout, name=name or task.name or f"task{len(self.tasks)}", scales=scales))
+        else:
+            # operator expression: evaluated on the device when the handler fires (separable sphere operators, e.g. the vorticity
+            # -div(skew(u)) of the stock shallow-water script; evaluator.evaluate_expression raises for anything else)
+            self.tasks.append(dict(expr=task, layout=layout, name=name or f"task{len(self.tasks)}", scales=scales))
 
     def add_tasks(self, tasks, **kw):
         for t in tasks:
@@ -61,7 +68,7 @@ class Handler:
     def _evaluate(self):
         out = {}
         for t in self.tasks:
-            f = t['field']
+            f = t['field'] if 'field' in t else t['expr'].evaluate()
             if t['layout'] == 'g':
                 f.change_scales(t['scales'] if t['scales'] is not None else 1)
                 out[t['name']] = np.array(f['g'])
@@ -131,7 +138,6 @@ class FileHandler(Handler):
         data = {f"scales/{k}": np.asarray(v) for k, v in self._pending['scales'].items()}
         data["scales/set_number"] = np.asarray(self.set_num)
         for t in self.tasks:
-            f = t['field']
             data[f"layouts/{t['name']}"] = np.asarray(t['layout'])
             data[f"task_scales/{t['name']}"] = np.asarray(1.0 if t['scales'] is None else t['scales'], dtype=float)
         for name, arrs in self._pending['tasks'].items():

@@ -1058,3 +1058,48 @@ def _has(e, types):
     if isinstance(e, types):
         return True
     return any(_has(a, types) for a in getattr(e, 'args', []) if isinstance(a, ops.Operand))
+
+
+def evaluate_linear_expression(expr):
+    """Evaluate an expression built from separable sphere operators (gradient, divergence, Laplacian, skew, sums, numeric
+    factors) of fields into a new Field in coefficient space: one db_pair_lincomb launch (analysis tasks such as the vorticity
+    -div(skew(u)) of the stock shallow-water script; reference: Future.evaluate, core/future.py:149-206)."""
+    import torch
+    from .field import Field
+    basis = sphere_basis_of(expr)
+    dist = expr.dist
+    is_field = lambda e: isinstance(e, Field)
+    rows = diag_linear(expr, basis, is_field)
+    leaves, comp0 = [], {}
+    for terms in rows:
+        for leaf, c, coef, sym in terms:
+            if id(leaf) not in comp0:
+                comp0[id(leaf)] = sum(max(l.ncomp, 1) for l in leaves)
+                leaves.append(leaf)
+    j0, j1 = basis.local_pairs(dist)
+    Nc0, Nc1 = 2 * (j1 - j0), basis.coeff_shape[1]
+    for leaf in leaves:
+        leaf.change_layout('c')
+    dev = leaves[0].device_data().device
+    src = torch.cat([l.device_data().reshape(max(l.ncomp, 1), Nc0, Nc1) for l in leaves], dim=0).contiguous()
+    _, ell_map = basis.elements_to_groups()
+    ell_pairs = ell_map[0::2][j0:j1]
+    in_range = ell_pairs <= basis.Lmax
+    sym_arrays, sym_index = [], {}
+
+    def sym_off(sym):
+        if np.all(sym == 1):
+            return -1
+        key = sym.tobytes()
+        if key not in sym_index:
+            sym_index[key] = len(sym_arrays) * ell_pairs.size
+            sym_arrays.append(np.where(in_range, sym[np.minimum(ell_pairs, basis.Lmax)], 0.0).ravel())
+        return sym_index[key]
+    prog_rows = [[(comp0[id(leaf)] + c, coef, sym_off(sym)) for leaf, c, coef, sym in terms] for terms in rows]
+    syms = torch.from_numpy(np.concatenate(sym_arrays) if sym_arrays else np.zeros(1)).to(dev)
+    out = torch.empty((len(rows), Nc0, Nc1), dtype=torch.float64, device=dev)
+    PairProgram(prog_rows, dev, syms).apply(src, out, Nc0 // 2, Nc1)
+    result = Field(dist, bases=(basis,), tensorsig=expr.tensorsig, dtype=expr.dtype)
+    dist._fields.pop()
+    result.set_device_data(out.reshape(result.tshape + (Nc0, Nc1)), 'c')
+    return result

@@ -385,6 +385,10 @@ def shallow_water(Nphi, Ntheta, steps, scheme="RK222", dump_mats=(), dealias=3/2
     for i in range(steps):
         solver.step(timestep)
     out.update(u1=u['c'].copy(), h1=h['c'].copy())
+    # analysis tasks of the stock script (lines 90-92): vorticity, and a Laplacian, evaluated on the final state
+    v = (-d3.div(d3.skew(u))).evaluate(); v.change_layout('c')
+    l = d3.lap(h).evaluate(); l.change_layout('c')
+    out.update(vort1=v.data.copy(), laph1=l.data.copy())
     return out
 
 

@@ -207,3 +207,20 @@ def check_against_oracle(Nphi, Ntheta, scheme, dts, seed=7):
         got = sw[name]['c']
         assert np.allclose(got, ref[name], rtol=1e-8, atol=1e-12 * np.abs(ref[name]).max()), (name, np.abs(got - ref[name]).max())
     return solver
+
+
+def check_analysis_tasks(g, tag="sw16"):
+    """The stock script's output tasks on the reference's final state: a field, the vorticity -div(skew(u)) and a Laplacian,
+    evaluated on the device through a dictionary handler (reference Future.evaluate / Handler.add_task)."""
+    sw = examples.shallow_water(*(int(v) for v in g[f"{tag}_meta"][:2]))
+    solver = sw['problem'].build_solver(d3.RK222)
+    sw['u']['c'] = g[f"{tag}_u1"]; sw['h']['c'] = g[f"{tag}_h1"]
+    handler = solver.evaluator.add_dictionary_handler(iter=1)
+    handler.add_task(sw['h'], layout='c', name='height')
+    handler.add_task(-d3.div(d3.skew(sw['u'])), layout='c', name='vorticity')
+    handler.add_task(d3.lap(sw['h']), layout='c', name='lap_h')
+    solver.evaluator.evaluate_handlers(iteration=0, wall_time=0.0, sim_time=0.0, timestep=0.0)
+    assert np.array_equal(handler.fields['height'], g[f"{tag}_h1"])
+    for name, key in (('vorticity', 'vort1'), ('lap_h', 'laph1')):
+        ref = g[f"{tag}_{key}"]
+        assert np.allclose(handler.fields[name], ref, rtol=1e-13, atol=1e-15 * np.abs(ref).max()), name

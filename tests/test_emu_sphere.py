@@ -40,6 +40,10 @@ def test_shallow_water_with_shifted_packing_matches_oracle():
     assert solver.bset.nsys == 8
 
 
+def test_analysis_tasks_with_operator_expressions(golden):
+    S.check_analysis_tasks(golden("sphere.npz"))
+
+
 class _EmuArrays:
     """numpy arrays + the emulated library, behind the small interface sphere_cases.check_banded_* use."""
     lib = property(lambda self: E.emu())

@@ -43,3 +43,8 @@ def test_two_gpu_curvilinear_matches_reference(which):
            "--master-port", str(port), str(root / "tests" / "dist_worker.py"), which]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, DB_DIST_BACKEND="nccl"))
     assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_sphere_analysis_tasks_with_operator_expressions(golden):
+    import sphere_cases as S
+    S.check_analysis_tasks(golden("sphere.npz"))
