@@ -15,7 +15,6 @@ time, to blocks  (output component, variable, variable component) -> radial matr
 with the radial operators D+-, E of libraries/dedalus_sphere/shell.py:21-73 composed from the Jacobi operators of
 dedalus_b200/jacobi.py.  R = regularity total of the component, Q(l) = dedalus_b200/shell.py Intertwiner.
 """
-import itertools
 import numpy as np
 from scipy import sparse
 from . import jacobi

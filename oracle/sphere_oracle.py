@@ -150,7 +150,6 @@ class ShallowWaterOracle:
             return self._mats[m]
         nl = self.Lmax + 1 - m
         ell = self._ell(m)
-        Z = np.zeros((nl, nl))
         L = np.zeros((3 * nl, 3 * nl), dtype=complex)
         blk = lambda r, c: (slice(r * nl, (r + 1) * nl), slice(c * nl, (c + 1) * nl))
         for q, s in enumerate((-1, +1)):
