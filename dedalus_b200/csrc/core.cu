@@ -124,3 +124,47 @@ extern "C" int db_cfl_max(const double* const* u, const double* const* inv_dx, i
     DB_LAUNCH(k_cfl_max, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), stream, a, reinterpret_cast<unsigned long long*>(out));
     return db_check_launch("cfl_max");
 }
+
+// advective CFL frequency maximum on spheres and spherical shells: sqrt(u_phi^2 + u_theta^2) * inv_h[ir] + |u_r| * inv_dr[ir]
+// (S2AdvectiveCFL / Spherical3DAdvectiveCFL.compute_cfl_frequency, core/basis.py:6175-6212); arrays (n_ang, n_r), u_r may be NULL
+__global__ void k_cfl_max_spherical(const double* __restrict__ up, const double* __restrict__ ut, const double* __restrict__ ur,
+                                    const double* __restrict__ inv_h, const double* __restrict__ inv_dr, int64_t n_ang, int64_t n_r,
+                                    unsigned long long* __restrict__ out)
+{
+    DB_SMEM(double, red);
+    const int64_t total = n_ang * n_r;
+    double m = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ir = e % n_r;
+        double f = sqrt(up[e] * up[e] + ut[e] * ut[e]) * inv_h[ir];
+        if (ur) f += fabs(ur[e]) * inv_dr[ir];
+        m = (f > m) ? f : m;
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { double o = red[threadIdx.x + s]; if (o > red[threadIdx.x]) red[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long bits; double v = red[0];
+        memcpy(&bits, &v, sizeof(bits));
+#ifdef DB_EMU
+        if (bits > *out) *out = bits;
+#else
+        atomicMax(out, bits);
+#endif
+    }
+}
+
+extern "C" int db_cfl_max_spherical(const double* u_phi, const double* u_theta, const double* u_r, const double* inv_h, const double* inv_dr,
+                                    int64_t n_ang, int64_t n_r, double* out, void* stream)
+{
+    const int64_t total = n_ang * n_r;
+    if (total <= 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    DB_LAUNCH(k_cfl_max_spherical, dim3((unsigned)blocks), dim3(256), 256 * sizeof(double), stream, u_phi, u_theta, u_r, inv_h, inv_dr,
+              n_ang, n_r, reinterpret_cast<unsigned long long*>(out));
+    return db_check_launch("cfl_max_spherical");
+}

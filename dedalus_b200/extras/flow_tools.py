@@ -42,6 +42,9 @@ class CFL:
             scales = u.dealias
             # grid values of every component at dealias scales (own buffers: the state stays in coefficient space)
             g = self._to_grid(u)
+            if getattr(u.tensorsig[0], 'curvilinear', False):
+                self._spherical_frequency(u, g, out)
+                continue
             dim = dist.dim
             comps = [g[i] for i in range(g.shape[0])]
             inv = []
@@ -61,6 +64,34 @@ class CFL:
             import torch.distributed as td
             td.all_reduce(out, op=td.ReduceOp.MAX)
         self.max_freq = out       # read lazily in compute_timestep (one host sync every `cadence` steps)
+
+    def _spherical_frequency(self, u, g, out):
+        """Velocities on a sphere or in a spherical shell: sqrt(u_phi^2 + u_theta^2) sqrt(Lmax (Lmax + 1)) / r + |u_r| / dr_eff
+        (reference S2AdvectiveCFL / Spherical3DAdvectiveCFL, core/basis.py:6156-6212), one reduction kernel."""
+        import torch
+        from ..lib import get_lib, current_stream
+        from ..sphere import sphere_basis_of
+        from ..shell import shell_basis_of
+        dev = g.device
+        shell = shell_basis_of(u)
+        if shell is not None:
+            scale = shell.dealias[2]
+            r = shell.global_grid_radius(scale)
+            L = shell.Lmax
+            inv_h = (np.sqrt(L * (L + 1)) / r) if L > 0 else np.zeros_like(r)
+            inv_dr = 1.0 / np.abs(np.gradient(r, edge_order=2) * scale)
+            n_r = r.size
+            ur = g[2].contiguous()
+        else:
+            sb = sphere_basis_of(u)
+            L = sb.Lmax
+            inv_h = np.array([np.sqrt(L * (L + 1)) / sb.radius if L > 0 else 0.0])
+            inv_dr, n_r, ur = np.zeros(1), 1, None
+        up, ut = g[0].contiguous(), g[1].contiguous()
+        ih = torch.from_numpy(np.ascontiguousarray(inv_h)).to(dev)
+        idr = torch.from_numpy(np.ascontiguousarray(inv_dr)).to(dev)
+        get_lib().call("db_cfl_max_spherical", up.data_ptr(), ut.data_ptr(), ur.data_ptr() if ur is not None else None, ih.data_ptr(),
+                       idr.data_ptr(), up.numel() // n_r, n_r, out.data_ptr(), current_stream())
 
     @staticmethod
     def _cfl_spacing(basis, dealias):

@@ -126,6 +126,7 @@ SIGNATURES = {
     "db_pair_lincomb": (C.c_int, [vp, vp, i64, i64, i32, vp, vp, vp, i64, vp]),
     "db_absmax": (C.c_int, [vp, i64, vp, vp]),
     "db_cfl_max": (C.c_int, [C.POINTER(vp), C.POINTER(vp), i32, i64, i64, i64, vp, vp]),
+    "db_cfl_max_spherical": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp]),
 }
 
 

@@ -382,6 +382,12 @@ int db_absmax(const double* x, int64_t count, double* out, void* stream);
 int db_cfl_max(const double* const* u, const double* const* inv_dx, int32_t ncomp, int64_t g0, int64_t g1, int64_t g2,
                double* out, void* stream);
 
+/* The same on spheres / spherical shells: max of sqrt(u_phi^2 + u_theta^2) * inv_h[ir] + |u_r| * inv_dr[ir] over arrays of shape
+ * (n_ang, n_r); inv_h = sqrt(Lmax (Lmax + 1)) / r, inv_dr = 1 / effective radial spacing (S2AdvectiveCFL, Spherical3DAdvectiveCFL,
+ * core/basis.py:6156-6212); u_r / inv_dr may be NULL on the 2-sphere.  `out` must be zero-initialised. */
+int db_cfl_max_spherical(const double* u_phi, const double* u_theta, const double* u_r, const double* inv_h, const double* inv_dr,
+                         int64_t n_ang, int64_t n_r, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

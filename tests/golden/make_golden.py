@@ -572,3 +572,29 @@ def gen_shell_ivp():
 
 if __name__ == "__main__" and "shell_ivp" in sys.argv[1:]:
     gen_shell_ivp()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Advective CFL frequency on the sphere and in the shell (core/basis.py:6156-6212)
+# ----------------------------------------------------------------------------------------------------------
+def gen_cfl_curvilinear():
+    """Grid maximum of the reference's AdvectiveCFL operator for random velocities (the quantity extras/flow_tools.CFL reduces)."""
+    out = {}
+    c = d3.S2Coordinates('phi', 'theta'); d = d3.Distributor(c, dtype=np.float64)
+    b = d3.SphereBasis(c, (32, 16), radius=2.5, dealias=1.5, dtype=np.float64)
+    u = d.VectorField(c, bases=b); u.fill_random(layout='g', seed=3)
+    uc = u['c'].copy()
+    f = d3.AdvectiveCFL(u, c).evaluate(); f.change_scales(1.5)
+    out['sphere_u_c'] = uc; out['sphere_fmax'] = np.max(f['g'])
+    c3 = d3.SphericalCoordinates('phi', 'theta', 'r'); d = d3.Distributor(c3, dtype=np.float64)
+    b = d3.ShellBasis(c3, (32, 16, 12), radii=(14, 15), dealias=1.5, dtype=np.float64)
+    u = d.VectorField(c3, bases=b); u.fill_random(layout='g', seed=4)
+    uc = u['c'].copy()
+    f = d3.AdvectiveCFL(u, c3).evaluate(); f.change_scales(1.5)
+    out['shell_u_c'] = uc; out['shell_fmax'] = np.max(f['g'])
+    np.savez_compressed(HERE / "cfl_curvilinear.npz", **out)
+    print({k: (v.shape if getattr(v, 'shape', ()) else float(v)) for k, v in out.items()})
+
+
+if __name__ == "__main__" and "cfl_curvilinear" in sys.argv[1:]:
+    gen_cfl_curvilinear()

@@ -224,3 +224,25 @@ def check_analysis_tasks(g, tag="sw16"):
     for name, key in (('vorticity', 'vort1'), ('lap_h', 'laph1')):
         ref = g[f"{tag}_{key}"]
         assert np.allclose(handler.fields[name], ref, rtol=1e-13, atol=1e-15 * np.abs(ref).max()), name
+
+
+def check_cfl_curvilinear(g):
+    """extras.flow_tools.CFL on a sphere and in a shell: the device reduction equals the grid maximum of the reference's
+    AdvectiveCFL operator (core/basis.py:6156-6212) for the same random velocity."""
+    sw = examples.shallow_water(32, 16)
+    sw['basis'].radius = 2.5            # only the CFL spacing reads it here: the fixture's sphere has radius 2.5
+    solver = sw['problem'].build_solver(d3.RK222)
+    solver._init_device()
+    sw['u']['c'] = g['sphere_u_c']
+    cfl = d3.CFL(solver, initial_dt=1.0, cadence=1)
+    cfl.add_velocity(sw['u'])
+    cfl._on_step(solver)
+    assert np.isclose(float(cfl.max_freq.item()), float(g['sphere_fmax']), rtol=1e-12)
+    sc = examples.shell_convection(32, 16, 12)
+    solver = sc['problem'].build_solver(d3.SBDF2)
+    solver._init_device()
+    sc['u']['c'] = g['shell_u_c']
+    cfl = d3.CFL(solver, initial_dt=1.0, cadence=1)
+    cfl.add_velocity(sc['u'])
+    cfl._on_step(solver)
+    assert np.isclose(float(cfl.max_freq.item()), float(g['shell_fmax']), rtol=1e-12)

@@ -44,6 +44,10 @@ def test_analysis_tasks_with_operator_expressions(golden):
     S.check_analysis_tasks(golden("sphere.npz"))
 
 
+def test_cfl_on_sphere_and_shell_matches_reference(golden):
+    S.check_cfl_curvilinear(golden("cfl_curvilinear.npz"))
+
+
 class _EmuArrays:
     """numpy arrays + the emulated library, behind the small interface sphere_cases.check_banded_* use."""
     lib = property(lambda self: E.emu())

@@ -48,3 +48,8 @@ def test_two_gpu_curvilinear_matches_reference(which):
 def test_sphere_analysis_tasks_with_operator_expressions(golden):
     import sphere_cases as S
     S.check_analysis_tasks(golden("sphere.npz"))
+
+
+def test_cfl_on_sphere_and_shell_matches_reference(golden):
+    import sphere_cases as S
+    S.check_cfl_curvilinear(golden("cfl_curvilinear.npz"))
