@@ -20,6 +20,21 @@ EMU_LIB = EMU_DIR / "libdedalus_b200_emu.so"
 HEADERS = [CSRC / "db_common.cuh", CSRC / "tw96.inc", ROOT / "include" / "dedalus_b200.h"]
 
 
+def source_hash():
+    """sha256 over every CUDA source and header of the library: the built .so carries it in a side file so that a stale
+    library (sources edited after the last build; file times do not survive every copy) is detected when it is loaded."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in [CSRC / s for s in SOURCES] + HEADERS:
+        h.update(f.name.encode()); h.update(pathlib.Path(f).read_bytes())
+    return h.hexdigest()
+
+
+def lib_is_current():
+    stamp = pathlib.Path(str(LIB) + ".hash")
+    return LIB.exists() and stamp.exists() and stamp.read_text().strip() == source_hash()
+
+
 def _newer(target, deps):
     if not target.exists():
         return True
@@ -54,12 +69,13 @@ def build(force=False, verbose=False):
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append((cmd, obj))
-    if not jobs and not _newer(LIB, objs):
+    if not jobs and not _newer(LIB, objs) and lib_is_current():
         return LIB
     if not pathlib.Path(nvcc).exists():
         raise RuntimeError("nvcc not found: cannot build libdedalus_b200.so")
     _compile_all(jobs)
     _link([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [str(o) for o in objs], LIB)
+    pathlib.Path(str(LIB) + ".hash").write_text(source_hash() + "\n")
     return LIB
 
 

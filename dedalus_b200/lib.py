@@ -204,10 +204,16 @@ class CudaBackend:
 
     def lib(self):
         if CudaBackend._lib is None:
-            if not LIB_PATH.exists():
-                raise DedalusB200Error(
-                    f"{LIB_PATH} not found: build it with `python -m dedalus_b200.build` (nvcc, sm_100a). "
-                    "dedalus_b200 has no CPU fallback.")
+            from . import build as _build
+            if not _build.lib_is_current():
+                # missing, or built from other sources than the ones in the tree (a stale library would lack entry points or,
+                # worse, run old kernels): rebuild it if nvcc is here, else say so -- never continue with it
+                try:
+                    _build.build(force=not LIB_PATH.exists())
+                except Exception as exc:
+                    raise DedalusB200Error(
+                        f"{LIB_PATH} is missing or was not built from the current sources and could not be rebuilt ({exc}): "
+                        "run `python -m dedalus_b200.build` (nvcc, sm_100a).  dedalus_b200 has no CPU fallback.")
             CudaBackend._lib = bind(LIB_PATH)
         return CudaBackend._lib
 

@@ -61,6 +61,14 @@ double emu_shfl_exchange(double v, int src_lane) {
 
 void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     const size_t nthreads = (size_t)block.x * block.y * block.z;
+    // the launch limits of the real device (sm_100): a launch that violates them fails on the GPU with "invalid configuration
+    // argument" while a host loop would just run zero or too many iterations
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0 || nthreads == 0 || nthreads > 1024 || block.z > 64 || grid.y > 65535 || grid.z > 65535 ||
+        smem > 227 * 1024) {
+        fprintf(stderr, "emu_launch: invalid CUDA launch configuration grid=(%u,%u,%u) block=(%u,%u,%u) smem=%zu\n",
+                grid.x, grid.y, grid.z, block.x, block.y, block.z, smem);
+        abort();
+    }
     std::vector<unsigned char> shared(smem + 64);
     std::vector<Fiber> fibers(nthreads);
     for (size_t i = 0; i < nthreads; ++i) fibers[i].stack = get_stack(i);
