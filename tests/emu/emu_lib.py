@@ -61,6 +61,31 @@ class EmuBackend:
 
 
 _saved = None
+_torch_saved = None
+
+
+def _poison_uninitialised():
+    """torch.empty / empty_like return NaN-filled floating tensors while the emulation is installed: freshly mapped host
+    memory is usually zero, freshly allocated DEVICE memory is not -- code that relies on it must fail here too."""
+    global _torch_saved
+    import torch
+    if _torch_saved is not None:
+        return
+    _torch_saved = (torch.empty, torch.empty_like)
+    e, el = _torch_saved
+
+    def empty(*a, **k):
+        t = e(*a, **k)
+        if t.is_floating_point() or t.is_complex():
+            t.fill_(float('nan'))
+        return t
+
+    def empty_like(*a, **k):
+        t = el(*a, **k)
+        if t.is_floating_point() or t.is_complex():
+            t.fill_(float('nan'))
+        return t
+    torch.empty, torch.empty_like = empty, empty_like
 
 
 def install():
@@ -69,10 +94,15 @@ def install():
     if _saved is None:
         _saved = dlib._BACKEND
     dlib._BACKEND = EmuBackend()
+    _poison_uninitialised()
 
 
 def uninstall():
-    global _saved
+    global _saved, _torch_saved
     if _saved is not None:
         dlib._BACKEND = _saved
         _saved = None
+    if _torch_saved is not None:
+        import torch
+        torch.empty, torch.empty_like = _torch_saved
+        _torch_saved = None
