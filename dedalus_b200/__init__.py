@@ -12,8 +12,9 @@ from .field import Field
 from .operators import (Differentiate, Gradient, Divergence, Laplacian, Trace, TransposeComponents,
                         Interpolate, Integrate, Lift, Convert, TimeDerivative, DotProduct, Multiply, Skew, MulCosine,
                         grad, div, lap, skew, trace, transpose, integ, ave, dot, interp)
-from .problems import IVP
+from .problems import IVP, LBVP
 InitialValueProblem = IVP
+LinearBoundaryValueProblem = LBVP
 from .timesteppers import (schemes, CNAB1, SBDF1, CNAB2, MCNAB2, SBDF2, CNLF2, SBDF3, SBDF4,
                            RK111, RK222, RK443, RKSMR, RKGFY)
 

@@ -1,4 +1,5 @@
-"""Initial value problems  M.dt(X) + L.X = F(X, t)   (reference core/problems.py:40-362, IVP 270-362).
+"""Initial value problems  M.dt(X) + L.X = F(X, t)   (reference core/problems.py:40-362, IVP 270-362) and the linear
+boundary value problems  L.X = F  the stock scripts use to balance their initial conditions (LBVP, problems.py:155-203).
 
 `add_equation("LHS = RHS")` evaluates both sides in the user namespace (exactly like the reference,
 problems.py:66-100), splits the LHS into the dt-terms (M) and the rest (L) and keeps the RHS as the explicit
@@ -74,3 +75,22 @@ class IVP:
     def build_solver(self, timestepper, **kw):
         from .solvers import InitialValueSolver
         return InitialValueSolver(self, timestepper, **kw)
+
+
+class LBVP(IVP):
+    """L.X = F with F independent of X (reference core/problems.py:155-203).  Same namespace and equation parsing as the IVP;
+    time derivatives are not allowed."""
+
+    def __init__(self, variables, namespace=None):
+        super().__init__(variables, time='t', namespace=namespace)
+
+    def add_equation(self, equation, condition=None):
+        eq = super().add_equation(equation, condition)
+        from .sphere import _has
+        if _has(eq['LHS'], (ops.TimeDerivative,)):
+            raise ValueError("LBVP LHS must not contain time derivatives.")
+        return eq
+
+    def build_solver(self, **kw):
+        from .solvers import LinearBoundaryValueSolver
+        return LinearBoundaryValueSolver(self, **kw)

@@ -615,3 +615,41 @@ class InitialValueSolver:
                          speed_mode_stages_per_sec=self.total_modes * stages * max(its, 0) / max(run_time, 1e-30))
         self.stats = stats
         return stats
+
+
+class _DirectSolve:
+    """Placeholder 'scheme' of the boundary value solver: one factorisation of L, no history."""
+    kind, steps, stages = "lbvp", 1, 0
+
+
+class LinearBoundaryValueSolver(InitialValueSolver):
+    """L.X = F on the device (reference LinearBoundaryValueSolver, core/solvers.py:286-375): `solve()` evaluates F, solves every
+    pencil system with the factorised L and scatters the solution into the problem variables.  Sphere problems only in this
+    build (the balanced-height problem of the stock shallow-water script); F may read any sphere field but not the unknowns."""
+
+    rhs_reads_state = False
+
+    def __init__(self, problem, **kw):
+        super().__init__(problem, _DirectSolve, **kw)
+        if not self.curvilinear or self.shell:
+            raise NotImplementedError("LBVPs are built for sphere (S2) problems in this build")
+
+    def step(self, dt):
+        raise TypeError("boundary value solvers have no time step; call solve()")
+
+    def solve(self, rebuild_matrices=False):
+        if not self._device_ready:
+            self._init_device()
+        if self.bset is None or rebuild_matrices:
+            from .sphere import SphereSystems
+            self.bset = SphereSystems(self, 4, 1)         # slots: 0 F, 1 X, 2 / 3 probe products
+            self.total_modes = self.bset.total_modes
+            self.bset.factor_verified([(0, 0.0, 1.0)], (0, 1, 2, 3))
+        bs = self.bset
+        self.rhs_plan.evaluate(self.eq_t)
+        bs.move(1, True, 0, self.eq_t)
+        bs.solve(0, 1, [(0, 1.0)])
+        bs.move(0, False, 1, self.state_t)
+        for v, view in zip(self.state, self.state_views):      # the unknowns keep their scales (reference solvers.py:397-398: preset_layout only)
+            v.set_device_data(view, 'c')
+        self.iteration += 1

@@ -547,20 +547,40 @@ def lhs_blocks(e, variables, basis, m):
     def scale(blocks, f):
         return {t: {k: f(k, B) for k, B in d.items()} for t, d in blocks.items()}
 
+    def constant(x):
+        return all(b is None for b in x.bases)
+    E00 = sparse.csr_matrix(([1.0 + 0j], ([0], [0])), shape=(NL, NL))       # the (l = 0) -> (l = 0) entry, wavenumber 0 only
+
     def rec(e):
         for iv, v in enumerate(variables):
             if e is v:
+                if constant(v):
+                    # a constant unknown lives in the (m = 0, l = 0) cosine coefficient (LBVP gauge constants: "+ c", "ave(h) = 0")
+                    if v.tensorsig:
+                        raise NotImplementedError("constant tensor unknowns in sphere problems")
+                    return {0: {(0, iv, 0): E00}} if m == 0 else {}
                 return {0: {(c, iv, c): sparse.identity(NL, dtype=complex, format='csr') for c in range(max(v.ncomp, 1))}}
         if isinstance(e, ops.Add):
             out = {}
             for a in e.args:
                 if not isinstance(a, ops.Operand):
                     raise ValueError("LHS must be homogeneous in the variables")
+                # constant + sphere field: the constant is converted, unit amplitude 1 / constant_mode_value = sqrt(2)
+                # (reference ConvertConstantSphere.symbol, basis.py:3293-3296)
+                lift = np.sqrt(2.0) if (constant(a) and not constant(e)) else 1.0
                 for t, d in rec(a).items():
                     o = out.setdefault(t, {})
                     for k, B in d.items():
+                        B = B * lift if lift != 1.0 else B
                         o[k] = o[k] + B if k in o else B
             return out
+        if isinstance(e, ops.Integrate):
+            if not (e.average and sphere_basis_of(e.args[0]) is not None and not e.args[0].tensorsig):
+                raise NotImplementedError("only ave(scalar sphere field) is supported on the LHS of sphere problems")
+            if m != 0:
+                return {}
+            # reference SphereAverage.symbol (basis.py:5315-5317): 1 at l = 0, the l = 0 coefficient passes through
+            return {t: {k: E00 @ B for k, B in d.items()} for t, d in rec(e.args[0]).items()}
         if isinstance(e, ops.ScalarMul):
             return scale(rec(e.args[0]), lambda k, B: B * e.c)
         if isinstance(e, ops.Convert):
@@ -621,7 +641,7 @@ class SphereSystems:
         from .lib import BandedSys
         self.solver = solver
         problem = solver.problem
-        basis = sphere_basis_of(problem.variables[0])
+        basis = next(b for b in map(sphere_basis_of, problem.variables) if b is not None)
         self.basis = basis
         dev = solver.device
         variables = problem.variables
@@ -638,7 +658,12 @@ class SphereSystems:
         eq_rank = [len(eq['tensorsig']) for eq in problem.equations
                    for _ in range(max(int(np.prod([cs.dim for cs in eq['tensorsig']], dtype=int)), 1))]
         var_base = np.cumsum([0] + [max(v.ncomp, 1) for v in variables])
+        # constants (no bases): one number, carried by the (m = 0, l = 0) cosine slot of their component
+        var_const = np.array([all(b is None for b in variables[iv].bases) for iv, c in var_comps])
+        eq_const = np.array([all(b is None for b in problem.equations[ie]['bases']) for ie, c in eq_comps])
         dist = solver.dist
+        if (var_const.any() or eq_const.any()) and dist.size > 1:
+            raise NotImplementedError("constant unknowns / equations of sphere problems are single-GPU in this build")
         j0, j1 = basis.local_pairs(dist)
         plane = 2 * (j1 - j0) * basis.coeff_shape[1]                 # the rank's block of the coefficient packing
         var_off = [solver.var_arena.offsets[iv] + c * plane for iv, c in var_comps]
@@ -666,10 +691,11 @@ class SphereSystems:
             lidx = np.arange(n) // (2 * NC) + m
             comp = (np.arange(n) // 2) % NC
             part = np.arange(n) % 2
-            def validity(spin, rank):
+            def validity(spin, rank, const):
                 sp = np.asarray(spin)[comp]; rk = np.asarray(rank)[comp]
-                return (lidx >= np.maximum(m, np.abs(sp))) & ~((lidx == 0) & (part == 1) & (rk <= 1))
-            vcol, vrow = validity(var_spin, var_rank), validity(eq_spin, eq_rank)
+                ok = (lidx >= np.maximum(m, np.abs(sp))) & ~((lidx == 0) & (part == 1) & (rk <= 1))
+                return ok & ~(const[comp] & ~((lidx == 0) & (part == 0)))
+            vcol, vrow = validity(var_spin, var_rank, var_const), validity(eq_spin, eq_rank, eq_const)
             if not np.array_equal(vcol, vrow):
                 raise NotImplementedError("equations and variables of a sphere problem must pair up component by component")
             mats = {}
@@ -693,8 +719,8 @@ class SphereSystems:
             j, cols = basis.mode_columns(m)
             col_of = cols[lidx - m]
             pos = (2 * (j - j0) + part) * basis.coeff_shape[1] + col_of
-            xi = np.where(vcol, np.asarray(var_off)[comp] + pos, -1)
-            fi = np.where(vrow, np.asarray(eq_off)[comp] + pos, -1)
+            xi = np.where(vcol, np.asarray(var_off)[comp] + np.where(var_const[comp], 0, pos), -1)
+            fi = np.where(vrow, np.asarray(eq_off)[comp] + np.where(eq_const[comp], 0, pos), -1)
             systems.append(dict(m=m, n=n, L=mats[0], M=mats[1], xi=xi, fi=fi))
             total_valid += int(vcol.sum())
         self.total_modes = total_valid
@@ -819,7 +845,7 @@ class SphereRHSPlan:
         self.solver = solver
         problem = solver.problem
         dev = solver.device
-        basis = self.basis = sphere_basis_of(problem.variables[0])
+        basis = self.basis = next(b for b in map(sphere_basis_of, problem.variables) if b is not None)
         variables = problem.variables
         dist = self.dist = solver.dist
         ax = dist.get_basis_axis(basis)
@@ -832,12 +858,29 @@ class SphereRHSPlan:
         self.Nc0 = 2 * (j1 - j0)
         self.rowsA = 2 * len(basis.local_wavenumbers(dist))
         plane_c = self.Nc0 * basis.coeff_shape[1]
+        # sources of the grid operands: problem variables are read in place from the state arena (IVPs); any other sphere field
+        # (LBVP right-hand sides: e.g. the velocity in the balance equation of the stock shallow-water script) is appended to a
+        # source buffer that is refreshed before every evaluation
         state_comp0 = {}
         for iv, v in enumerate(variables):
-            assert solver.var_arena.offsets[iv] % plane_c == 0
-            state_comp0[id(v)] = solver.var_arena.offsets[iv] // plane_c
-        is_state = lambda e: isinstance(e, Field) and id(e) in state_comp0
-        nonlinear = (ops.Multiply, ops.DotProduct, ops.Power)
+            if sphere_basis_of(v) is not None:
+                assert solver.var_arena.offsets[iv] % plane_c == 0
+                state_comp0[id(v)] = solver.var_arena.offsets[iv] // plane_c
+        self.extra_sources = []
+        self.use_state = getattr(solver, 'rhs_reads_state', True)
+        if not self.use_state:
+            state_comp0 = {}
+
+        def is_state(e):
+            if not (isinstance(e, Field) and sphere_basis_of(e) is not None):
+                return False
+            if id(e) not in state_comp0:
+                base = (len(solver.state_t) // plane_c if self.use_state else 0) + sum(max(f.ncomp, 1) for f in self.extra_sources)
+                state_comp0[id(e)] = base
+                self.extra_sources.append(e)
+            return True
+        nonlinear = (ops.Multiply, ops.DotProduct, ops.Power, ops.MulCosine)
+        cos_id = [None]
 
         operands, operand_ids = [], {}        # grid operands: (expr, comps range start, spins, rank)
         n_gcomp = [0]
@@ -871,6 +914,12 @@ class SphereRHSPlan:
                 for _ in range(e.n - 1):
                     cur = [(x * y, fx + fy) for x, fx in cur for y, fy in base]
                 return {0: cur}
+            if isinstance(e, ops.MulCosine):
+                # on the right-hand side cos(theta) X is formed on the dealiased grid (exact: the product raises the degree by
+                # one and the forward transform truncates at Lmax, as the reference's truncated operator matrix does)
+                if cos_id[0] is None:
+                    cos_id[0] = -1                      # resolved to the last grid input once all operands are known
+                return {c: [(x, f + ('cos',)) for x, f in t] for c, t in poly(e.args[0]).items()}
             if isinstance(e, ops.Add) and any(_has(a, nonlinear) for a in e.args if isinstance(a, ops.Operand)):
                 out = {}
                 for a in e.args:
@@ -897,9 +946,18 @@ class SphereRHSPlan:
 
         is_product = lambda e: isinstance(e, nonlinear)
         self.post_rows = []
+        const_seen = False
         for eq in problem.equations:
             ncomp = max(int(np.prod([cs.dim for cs in eq['tensorsig']], dtype=int)), 1)
             rhs = eq['RHS']
+            if all(b is None for b in eq['bases']):
+                # constant equations ("ave(h) = 0") sit behind the sphere equations in the arena and keep a zero right-hand side
+                if isinstance(rhs, ops.Operand) or rhs != 0:
+                    raise NotImplementedError("constant equations of sphere problems need a zero right-hand side")
+                const_seen = True
+                continue
+            if const_seen:
+                raise NotImplementedError("constant equations must follow the sphere equations")
             if not isinstance(rhs, ops.Operand):
                 if rhs != 0:
                     raise NotImplementedError("nonzero numeric right-hand sides on the sphere")
@@ -910,6 +968,11 @@ class SphereRHSPlan:
                 self.post_rows.append([(product(leaf)['p0'] + c, coef, sym) for leaf, c, coef, sym in terms])
         self.operands, self.products = operands, products
         self.n_g, self.n_p = n_gcomp[0], n_pcomp[0]
+        self.has_cos = cos_id[0] is not None
+        if self.has_cos:                                  # cos(theta) rides as one more grid input
+            for pr in products:
+                pr['poly'] = {c: [(x, tuple(self.n_g if q == 'cos' else q for q in f)) for x, f in t] for c, t in pr['poly'].items()}
+            self.n_g += 1
         if self.n_p == 0:
             self.trivial = True
             return
@@ -985,8 +1048,13 @@ class SphereRHSPlan:
         Ngp, tb = self.gshape
         Ngt, rowsA = self.Ngt_full, self.rowsA
         z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
-        self.c_pre, self.cg_a, self.cg_b = z(self.n_g, Nc0, Nc1), z(self.n_g, rowsA, Ngt), z(self.n_g, rowsA, Ngt)
+        n_t = self.n_g - (1 if self.has_cos else 0)          # transformed operands (the cos(theta) plane is static)
+        self.n_t = n_t
+        self.c_pre, self.cg_a, self.cg_b = z(n_t, Nc0, Nc1), z(n_t, rowsA, Ngt), z(n_t, rowsA, Ngt)
         self.g_in, self.g_out = z(self.n_g, Ngp, tb), z(self.n_p, Ngp, tb)
+        if self.has_cos:
+            theta = basis.global_grid_colatitude(self.scales[1])[dist.grid_local_slice(ax + 1, basis, self.scales[1])]
+            self.g_in[n_t] = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.cos(theta)[None, :], (Ngp, tb)))).to(dev)
         self.pg_a, self.pg_b, self.c_post = z(self.n_p, basis.shape[0], tb), z(self.n_p, rowsA, Ngt), z(self.n_p, Nc0, Nc1)
 
     def set_static(self, eq_t):
@@ -1015,8 +1083,15 @@ class SphereRHSPlan:
         Ngt, rowsA = self.Ngt_full, self.rowsA
         multi = dist.size > 1
         npair_c, npair_a = Nc0 // 2, rowsA // 2
-        with Timed(prof, "sphere_symbols", 8 * Nc0 * Nc1 * (self.n_g + len(solver.state_t) // (Nc0 * Nc1))):
-            self.pre.apply(solver.state_t, self.c_pre, npair_c, Nc1)
+        src = solver.state_t
+        if self.extra_sources:                 # fields that are not problem variables: appended behind (or instead of) the state arena
+            import torch
+            for f in self.extra_sources:
+                f.change_layout('c')
+            parts = ([solver.state_t] if self.use_state else []) + [f.device_data().reshape(-1) for f in self.extra_sources]
+            src = torch.cat(parts)
+        with Timed(prof, "sphere_symbols", 8 * Nc0 * Nc1 * (self.n_g + len(src) // (Nc0 * Nc1))):
+            self.pre.apply(src, self.c_pre, npair_c, Nc1)
         for s, c0, c1 in self._groups(self.pre_spins):
             plan = basis.colatitude_plan(Ngt, s, dist)
             with Timed(prof, "swsh_backward", plan.matrix_bytes() + 8 * (c1 - c0) * (Nc0 * Nc1 + rowsA * Ngt)):
@@ -1028,7 +1103,7 @@ class SphereRHSPlan:
             with Timed(prof, "sphere_transpose", 16 * self.cg_b.numel()):
                 cgB = basis.hop(dist).to_grid_side(self.cg_b.unsqueeze(-1)).squeeze(-1).contiguous()
         with Timed(prof, "azimuth_backward", 8 * (cgB.numel() + self.g_in.numel())):
-            basis.azimuth_plan(Ngp).backward(cgB, self.g_in, 1)
+            basis.azimuth_plan(Ngp).backward(cgB, self.g_in[:self.n_t], 1)
         with Timed(prof, "pointwise", 8 * self.npoints * (self.n_g + self.n_p)):
             if self.pairs is not None and self.g_in.data_ptr() % 16 == 0 and self.g_out.data_ptr() % 16 == 0:
                 get_lib().call("db_pointwise_pairs", self.g_in.data_ptr(), self.g_out.data_ptr(), self.npoints, self.n_g, self.n_p,

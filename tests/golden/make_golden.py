@@ -433,6 +433,60 @@ if __name__ == "__main__" and "sphere" in sys.argv[1:]:
     gen_sphere()
 
 
+def shallow_water_balanced(Nphi, Ntheta, steps, dealias=3/2):
+    """The stock script start to finish (examples/ivp_sphere_shallow_water/shallow_water.py:45-86): zonal jet, the LBVP for the
+    balanced height with its gauge constant, the height perturbation, then `steps` RK222 steps."""
+    meter = 1 / 6.37122e6; hour = 1; second = hour / 3600
+    R = 6.37122e6 * meter; Omega = 7.292e-5 / second; nu = 1e5 * meter**2 / second / 32**2
+    g = 9.80616 * meter / second**2; H = 1e4 * meter; timestep = 600 * second * min(1.0, 128 / Ntheta)
+    coords = d3.S2Coordinates('phi', 'theta')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    basis = d3.SphereBasis(coords, (Nphi, Ntheta), radius=R, dealias=dealias, dtype=np.float64)
+    u = dist.VectorField(coords, name='u', bases=basis)
+    h = dist.Field(name='h', bases=basis)
+    zcross = lambda A: d3.MulCosine(d3.skew(A))
+    phi, theta = dist.local_grids(basis)
+    lat = np.pi / 2 - theta + 0*phi
+    umax = 80 * meter / second
+    lat0 = np.pi / 7; lat1 = np.pi / 2 - lat0
+    en = np.exp(-4 / (lat1 - lat0)**2)
+    jet = (lat0 <= lat) * (lat <= lat1)
+    u_jet = umax / en * np.exp(1 / (lat[jet] - lat0) / (lat[jet] - lat1))
+    u['g'][0][jet] = u_jet
+    c = dist.Field(name='c')
+    problem = d3.LBVP([h, c], namespace=locals())
+    problem.add_equation("g*lap(h) + c = - div(u@grad(u) + 2*Omega*zcross(u))")
+    problem.add_equation("ave(h) = 0")
+    solver = problem.build_solver()
+    solver.solve()
+    out = dict(meta=np.array([Nphi, Ntheta, dealias, steps, timestep]), h_bal=h['c'].copy(), c_bal=c['c'].copy(), u_bal=u['c'].copy())
+    lat2 = np.pi / 4; hpert = 120 * meter; alpha = 1 / 3; beta = 1 / 15
+    h.change_scales(1); u.change_scales(1)
+    h['g'] += hpert * np.cos(lat) * np.exp(-(phi/alpha)**2) * np.exp(-((lat2-lat)/beta)**2)
+    problem = d3.IVP([u, h], namespace=locals())
+    problem.add_equation("dt(u) + nu*lap(lap(u)) + g*grad(h) + 2*Omega*zcross(u) = - u@grad(u)")
+    problem.add_equation("dt(h) + nu*lap(lap(h)) + H*div(u) = - div(h*u)")
+    solver = problem.build_solver(d3.RK222)
+    out.update(u0=u['c'].copy(), h0=h['c'].copy())
+    for i in range(steps):
+        solver.step(timestep)
+    out.update(u1=u['c'].copy(), h1=h['c'].copy())
+    return out
+
+
+def gen_sphere_lbvp():
+    out = {}
+    for tag, kw in dict(bal32=dict(Nphi=32, Ntheta=16, steps=3), bal64=dict(Nphi=64, Ntheta=32, steps=2)).items():
+        for k, v in shallow_water_balanced(**kw).items():
+            out[f"{tag}_{k}"] = v
+    np.savez_compressed(HERE / "sphere_lbvp.npz", **out)
+    print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
+
+
+if __name__ == "__main__" and "sphere_lbvp" in sys.argv[1:]:
+    gen_sphere_lbvp()
+
+
 # ----------------------------------------------------------------------------------------------------------
 # Complex-dtype pencil path (T3): ComplexFourier x ChebyshevT in complex128, complex LHS coefficients, cubic RHS
 # ----------------------------------------------------------------------------------------------------------

@@ -246,3 +246,53 @@ def check_cfl_curvilinear(g):
     cfl.add_velocity(sc['u'])
     cfl._on_step(solver)
     assert np.isclose(float(cfl.max_freq.item()), float(g['shell_fmax']), rtol=1e-12)
+
+
+def check_balanced_shallow_water(g, tag):
+    """The stock script start to finish (examples/ivp_sphere_shallow_water/shallow_water.py:45-86): zonal jet -> LBVP for the
+    balanced height ("g*lap(h) + c = - div(u@grad(u) + 2*Omega*zcross(u))", "ave(h) = 0") -> perturbation -> RK222 steps.
+    Expected values: tests/golden/sphere_lbvp.npz (make_golden.py shallow_water_balanced, unmodified reference)."""
+    Nphi, Ntheta, dealias, steps, timestep = g[f"{tag}_meta"]
+    Nphi, Ntheta, steps = int(Nphi), int(Ntheta), int(steps)
+    meter = 1 / 6.37122e6; hour = 1; second = hour / 3600
+    R = 6.37122e6 * meter; Omega = 7.292e-5 / second; nu = 1e5 * meter**2 / second / 32**2
+    g_ = 9.80616 * meter / second**2; H = 1e4 * meter
+    coords = d3.S2Coordinates('phi', 'theta')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    basis = d3.SphereBasis(coords, (Nphi, Ntheta), radius=R, dealias=float(dealias), dtype=np.float64)
+    u = dist.VectorField(coords, name='u', bases=basis)
+    h = dist.Field(name='h', bases=basis)
+    zcross = lambda A: d3.MulCosine(d3.skew(A))
+    phi, theta = dist.local_grids(basis)
+    lat = np.pi / 2 - theta + 0*phi
+    umax = 80 * meter / second
+    lat0 = np.pi / 7; lat1 = np.pi / 2 - lat0
+    en = np.exp(-4 / (lat1 - lat0)**2)
+    jet = (lat0 <= lat) * (lat <= lat1)
+    u_jet = umax / en * np.exp(1 / (lat[jet] - lat0) / (lat[jet] - lat1))
+    u['g'][0][jet] = u_jet
+    c = dist.Field(name='c')
+    ns = dict(g=g_, Omega=Omega, zcross=zcross, u=u, h=h, c=c, nu=nu, H=H)
+    problem = d3.LBVP([h, c], namespace=ns)
+    problem.add_equation("g*lap(h) + c = - div(u@grad(u) + 2*Omega*zcross(u))")
+    problem.add_equation("ave(h) = 0")
+    solver = problem.build_solver()
+    solver.solve()
+    ref = g[f"{tag}_h_bal"]
+    got = h['c']
+    assert np.allclose(got, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max()), ("balanced height", np.abs(got - ref).max(), np.abs(ref).max())
+    assert abs(float(np.asarray(c['c']).ravel()[0])) <= 1e-12 * np.abs(ref).max()
+    assert np.allclose(u['c'], g[f"{tag}_u_bal"], rtol=1e-11, atol=1e-14)          # the right-hand side field is left untouched
+    lat2 = np.pi / 4; hpert = 120 * meter; alpha = 1 / 3; beta = 1 / 15
+    h.change_scales(1); u.change_scales(1)
+    h['g'] += hpert * np.cos(lat) * np.exp(-(phi/alpha)**2) * np.exp(-((lat2-lat)/beta)**2)
+    problem = d3.IVP([u, h], namespace=ns)
+    problem.add_equation("dt(u) + nu*lap(lap(u)) + g*grad(h) + 2*Omega*zcross(u) = - u@grad(u)")
+    problem.add_equation("dt(h) + nu*lap(lap(h)) + H*div(u) = - div(h*u)")
+    solver = problem.build_solver(d3.RK222)
+    for _ in range(steps):
+        solver.step(float(timestep))
+    for name, f in (('u', u), ('h', h)):
+        ref = g[f"{tag}_{name}1"]
+        got = f['c']
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-11 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
