@@ -127,6 +127,16 @@ def lower(expr):
         if isinstance(e, ops.Trace):
             sub = rec(e.args[0]); d = e.args[0].tensorsig[0].dim; nrest = e.ncomp
             return {r: [t for i in range(d) for t in sub.get((i * d + i) * nrest + r, [])] for r in range(nrest)}
+        if isinstance(e, ops.Skew):
+            # Cartesian skew (reference CartesianSkew.operate, operators.py:2112-2122): out_x = -arg_y, out_y = arg_x
+            if e.index != 0 or getattr(e.cs, 'curvilinear', False):
+                raise NonPolynomialError("Skew: Cartesian vectors, index 0 only")
+            sub = rec(e.args[0]); nrest = e.ncomp // 2
+            out = {}
+            for r in range(nrest):
+                out[r] = [(-c, f) for c, f in sub.get(nrest + r, [])]
+                out[nrest + r] = list(sub.get(r, []))
+            return out
         if isinstance(e, ops.TransposeComponents):
             sub = rec(e.args[0]); d0, d1 = e.args[0].tensorsig[0].dim, e.args[0].tensorsig[1].dim
             nrest = e.ncomp // (d0 * d1)
@@ -261,7 +271,12 @@ class RHSPlan:
         dim = self.dist.dim
         levels = [dict() for _ in range(dim)]
         self.leaf_of_input = []
-        for (f, c, dv) in self.input_keys:
+        self.grid_leaves = []        # (input slot, field, comp): grid-function results enter the products without a coefficient round trip
+        for slot, (f, c, dv) in enumerate(self.input_keys):
+            if getattr(f, '_grid_leaf', False) and not any(dv):
+                self.leaf_of_input.append(('gridleaf', id(f), c))
+                self.grid_leaves.append((slot, f, c))
+                continue
             parent = None
             for lvl, ax in enumerate(self.axes_order):
                 key = (id(f), c) + tuple(dv[a] for a in self.axes_order[:lvl + 1])
@@ -282,8 +297,9 @@ class RHSPlan:
             arena_tensor[off] = val
 
     # ------------------------------------------------------------------------------------------------
-    def evaluate(self, eq_arena_tensor):
-        """Evaluate all RHS outputs into eq_arena_tensor (state fields must be in coefficient space on device)."""
+    def evaluate(self, eq_arena_tensor, grid_only=False):
+        """Evaluate all RHS outputs into eq_arena_tensor (state fields must be in coefficient space on device).
+        grid_only: stop after the products and return the (n_out, grid) values on the dealiased grid."""
         import torch, ctypes as C
         from .transforms import cached_plan, _dptr, _stream
         from .lib import get_lib
@@ -294,11 +310,16 @@ class RHSPlan:
         dev = self.device
         last = dim - 1
         # ---- phase 1: backward transforms along the prefix tree
-        for f in {id(k[0]): k[0] for k in self.input_keys}.values():
+        for slot, f, c in self.grid_leaves:
+            if f.layout != 'g' or tuple(f.scales) != tuple(self.dealias):
+                raise RuntimeError("grid-function result is not on the dealiased grid")
+            self.grid_in[slot].copy_(f.device_data()[self._comp_index(f, c)])
+        in_tree = {id(nd['field']): nd['field'] for nd in self.levels[0].values()}
+        for f in in_tree.values():
             if f.layout != 'c':
                 f.change_layout('c')          # non-state fields (forcings, NCCs) may have been set on the grid
         bufs = [None] * dim
-        for lvl, ax in enumerate(self.axes_order):
+        for lvl, ax in enumerate(self.axes_order if in_tree else []):
             nodes = self.levels[lvl]
             final = (lvl == dim - 1)
             prev = bufs[lvl - 1] if lvl > 0 else None
@@ -340,6 +361,8 @@ class RHSPlan:
           else:
               get_lib().call("db_pointwise", _dptr(self.grid_in), _dptr(self.grid_out), self.npoints, self.n_in, self.n_out,
                              _dptr(self.term_ptr), _dptr(self.coef), _dptr(self.fac_ptr), _dptr(self.fac), self.nfac, _stream())
+        if grid_only:
+            return self.grid_out
         # ---- phase 3: forward transforms (axes first -> last), all outputs stacked
         cur = self.grid_out
         blocked_fwd = self.P > 1 and dim >= 3 and self._blocked_fwd_ok()
@@ -580,10 +603,104 @@ class RHSPlan:
         return self._slot[leaf_key]
 
 
+class _ExpressionHost:
+    """What RHSPlan needs from a solver, for expressions evaluated outside a solver (analysis tasks, flow properties)."""
+
+    def __init__(self, expr):
+        from types import SimpleNamespace
+        from .pencils import Arena
+        from .lib import compute_device
+        dist = expr.dist
+        self.dist = dist
+        self.device = compute_device()
+        dist.device = self.device
+        self.prof = None
+        self.problem = SimpleNamespace(dist=dist, equations=[dict(RHS=expr, bases=expr.bases, tensorsig=expr.tensorsig)])
+        self.eq_arena = Arena(dist, [(tuple(cs.dim for cs in expr.tensorsig), expr.bases)])
+
+
+# numpy ufunc -> torch function applied to the device grid values
+_TORCH_NAMES = {'absolute': 'abs', 'arcsin': 'asin', 'arccos': 'acos', 'arctan': 'atan', 'arcsinh': 'asinh', 'arccosh': 'acosh',
+                'arctanh': 'atanh', 'conjugate': 'conj'}
+
+
+class ExpressionProgram:
+    """Stand-alone evaluation of an operator expression of Cartesian fields into a new Field (reference Future.evaluate,
+    core/future.py:149-206, used by output handlers and flow properties -- not part of the per-step path).
+
+    The expression is compiled once: every grid function np.f(arg) (reference UnaryGridFunction, operators.py:505-640)
+    becomes a stage "polynomial part of arg on the dealiased grid -> f pointwise -> temporary field", and what remains is a
+    polynomial expression of fields that one RHSPlan evaluates into coefficient space -- the same transform and product
+    kernels as the solver's right-hand sides."""
+
+    def __init__(self, expr):
+        import copy
+        self.stages = []           # (plan, torch function, temporary field)
+
+        def sub(e):
+            if isinstance(e, ops.UnaryGridFunction):
+                arg = sub(e.args[0])
+                plan = self._plan(arg)
+                if plan.static_entries:
+                    raise NotImplementedError("constants inside grid functions")
+                name = getattr(e.func, '__name__', str(e.func))
+                import torch
+                fn = getattr(torch, _TORCH_NAMES.get(name, name), None)
+                if fn is None:
+                    raise NotImplementedError(f"grid function {name!r} has no device implementation")
+                if any(b is None for b in e.bases):
+                    raise NotImplementedError("grid functions of lower-dimensional operands")
+                tmp = Field(e.dist, bases=tuple(dict.fromkeys(e.bases)), tensorsig=e.tensorsig, dtype=e.dtype)
+                e.dist._fields.pop()
+                tmp._grid_leaf = True
+                self.stages.append((plan, fn, tmp))
+                return tmp
+            if isinstance(e, Field) or not isinstance(e, Operand):
+                return e
+            new = copy.copy(e)
+            new.args = [sub(a) for a in e.args]
+            return new
+        final = sub(expr)
+        self.result_field = final if isinstance(final, Field) else None
+        if self.result_field is None:
+            self.final = self._plan(final)
+            host = self.final.solver
+            import torch
+            self.out_t = torch.zeros(host.eq_arena.size, dtype=torch.float64, device=host.device)
+            self.final.set_static(self.out_t)
+            self.out = Field(expr.dist, bases=tuple(dict.fromkeys(b for b in expr.bases if b is not None)), tensorsig=expr.tensorsig, dtype=expr.dtype)
+            expr.dist._fields.pop()
+            tsh, shp = host.eq_arena.shapes[0]
+            self.out_view = self.out_t.view(tuple(tsh) + tuple(shp))
+
+    @staticmethod
+    def _plan(e):
+        plan = RHSPlan(_ExpressionHost(e))
+        if plan.n_out == 0 and not plan.static_entries:
+            raise NotImplementedError("expression evaluates to zero")
+        return plan
+
+    def run(self):
+        for plan, fn, tmp in self.stages:
+            g = plan.evaluate(None, grid_only=True)
+            vals = fn(g)
+            tmp.set_device_data(vals.reshape(tuple(cs.dim for cs in tmp.tensorsig) + tuple(plan.gshape)), 'g', scales=plan.dealias)
+        if self.result_field is not None:
+            return self.result_field
+        self.final.evaluate(self.out_t)
+        self.out.set_device_data(self.out_view, 'c')
+        return self.out
+
+
 def evaluate_expression(expr):
-    """Stand-alone evaluation (reference Future.evaluate): separable operator expressions of sphere fields only."""
+    """Stand-alone evaluation (reference Future.evaluate): separable operator expressions of sphere fields, and any polynomial /
+    grid-function expression of Cartesian fields.  The compiled program is cached on the expression."""
     from .sphere import sphere_basis_of, evaluate_linear_expression
     if sphere_basis_of(expr) is not None:
         return evaluate_linear_expression(expr)
-    raise NotImplementedError("Stand-alone expression evaluation is only implemented for separable operators of sphere fields; "
-                              "other expressions are evaluated inside the solver's RHS plan.")
+    if getattr(expr.dist.coordsys, 'curvilinear', False):
+        raise NotImplementedError("Stand-alone expression evaluation on curvilinear domains is limited to separable sphere operators.")
+    prog = getattr(expr, '_program', None)
+    if prog is None:
+        prog = expr._program = ExpressionProgram(expr)
+    return prog.run()

@@ -130,34 +130,56 @@ class CFL:
 
 
 class GlobalFlowProperty:
-    """Scalar reductions of grid-space quantities (reference flow_tools.py:64-130): max / min / mean of a field."""
+    """Scalar reductions of grid-space quantities (reference flow_tools.py:64-150): max / min / mean of a field or of an operator
+    expression (`np.sqrt(u@u)/nu` in the stock scripts).  Expressions are evaluated on the device every `cadence` iterations at
+    the start of the step, like the reference's dictionary handler (iter=cadence), and reduced at scale 1; the reductions
+    return the value of the last scheduled evaluation.  A field property is read when the reduction is called, as in the
+    reference, where the handler's output IS the field."""
 
     def __init__(self, solver, cadence=1):
         self.solver = solver
         self.cadence = cadence
         self.properties = {}
+        self._values = {}
+        solver.step_hooks.append(self._on_step)
 
-    def add_property(self, field, name):
-        self.properties[name] = field
+    def add_property(self, property, name, precompute_integral=False):
+        from ..operators import Operand
+        if not isinstance(property, Operand):
+            raise ValueError("flow properties must be fields or operator expressions")
+        self.properties[name] = property
+
+    def _on_step(self, solver):
+        if solver.iteration % self.cadence != 0:
+            return
+        for name, p in self.properties.items():
+            if not hasattr(p, 'copy_device_to_grid'):
+                self._values[name] = p.evaluate().copy_device_to_grid(scales=1)
 
     def _grid(self, name):
-        f = self.properties[name]
-        if not hasattr(f, 'copy_device_to_grid'):
-            raise NotImplementedError("Only fields are supported as flow properties on the hot path.")
-        return f.copy_device_to_grid()
+        p = self.properties[name]
+        if hasattr(p, 'copy_device_to_grid'):
+            return p.copy_device_to_grid()
+        if name not in self._values:              # asked before the first scheduled evaluation
+            self._values[name] = p.evaluate().copy_device_to_grid(scales=1)
+        return self._values[name]
+
+    def _reduce(self, v, op):
+        if self.solver.dist.size > 1:
+            import torch.distributed as td
+            td.all_reduce(v, op=getattr(td.ReduceOp, op))
+        return float(v.item())
 
     def max(self, name):
-        import torch
-        v = self._grid(name).max()
-        if self.solver.dist.size > 1:
-            import torch.distributed as td
-            td.all_reduce(v, op=td.ReduceOp.MAX)
-        return float(v.item())
+        return self._reduce(self._grid(name).max(), 'MAX')
 
     def min(self, name):
+        return self._reduce(self._grid(name).min(), 'MIN')
+
+    def grid_average(self, name):
+        """Mean over all grid points (reference flow_tools.py:112-115)."""
         import torch
-        v = self._grid(name).min()
-        if self.solver.dist.size > 1:
-            import torch.distributed as td
-            td.all_reduce(v, op=td.ReduceOp.MIN)
-        return float(v.item())
+        g = self._grid(name)
+        total = self._reduce(g.sum(), 'SUM')
+        count = self._reduce(torch.tensor(float(g.numel()), dtype=torch.float64, device=g.device), 'SUM')
+        return total / count

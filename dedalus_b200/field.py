@@ -172,13 +172,13 @@ class Field(Operand):
         self.preset_layout(layout)
         np.copyto(self.data, value)
 
-    def copy_device_to_grid(self):
-        """Grid values (dealias scales) of this field as a NEW device tensor; the field itself is left untouched."""
+    def copy_device_to_grid(self, scales=None):
+        """Grid values (dealias scales by default) of this field as a NEW device tensor; the field itself is left untouched."""
         tmp = Field(self.dist, bases=self.unique_bases(), tensorsig=self.tensorsig, dtype=self.dtype)
         self.dist._fields.pop()
         if self.layout != 'c':
             self.change_layout('c')
-        tmp.scales = self.dealias
+        tmp.scales = self.dealias if scales is None else self.dist.remedy_scales(scales)
         tmp.set_device_data(self.device_data().clone(), 'c')
         tmp.change_layout('g')
         return tmp.device_data()

@@ -67,6 +67,23 @@ class Operand:
     def __pow__(self, n):
         return Power(self, n)
 
+    def __array_ufunc__(self, ufunc, method, *inputs, **kw):
+        """numpy ufuncs on operands (reference field.py:60-88): unary ufuncs become grid functions, np.sqrt(u@u); the binary
+        arithmetic ufuncs numpy dispatches for `np.float64(2) * field` go back to the Python overloads."""
+        import operator
+        if method != '__call__' or kw:
+            return NotImplemented
+        inputs = tuple(x.item() if isinstance(x, np.generic) else x for x in inputs)
+        if len(inputs) == 1:
+            if ufunc is np.negative:
+                return -inputs[0]
+            return UnaryGridFunction(ufunc, inputs[0])
+        binary = {np.add: operator.add, np.subtract: operator.sub, np.multiply: operator.mul, np.true_divide: operator.truediv,
+                  np.power: operator.pow, np.matmul: operator.matmul}
+        if ufunc in binary and len(inputs) == 2:
+            return binary[ufunc](*inputs)
+        return NotImplemented
+
     def __call__(self, **positions):
         out = self
         for name, pos in positions.items():
@@ -120,6 +137,17 @@ def _merge_bases(op, bases_list):
 
 class Future(Operand):
     pass
+
+
+class UnaryGridFunction(Future):
+    """func(arg) pointwise on the dealiased grid (reference operators.py:505-640).  Evaluated by evaluator.ExpressionProgram;
+    not available inside equations (the hot path's right-hand sides are polynomial)."""
+    def __init__(self, func, arg):
+        if not isinstance(arg, Operand):
+            raise ValueError("UnaryGridFunction needs an operand argument.")
+        self.func = func
+        self.args = [arg]
+        self.dist, self.dtype, self.tensorsig, self.bases = arg.dist, arg.dtype, arg.tensorsig, arg.bases
 
 
 class Add(Future):

@@ -1,0 +1,36 @@
+"""Shared body of the stand-alone expression tests (emulation: tests/test_emu_expressions.py, GPU: tests/test_gpu_t8_expressions.py).
+Expected values: tests/golden/expressions.npz (make_golden.py gen_expressions, unmodified reference)."""
+import numpy as np
+import dedalus_b200 as d3
+
+
+def setup(g):
+    Nx, Nz = (int(v) for v in g['meta'])
+    coords = d3.CartesianCoordinates('x', 'z')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    xb = d3.RealFourier(coords['x'], size=Nx, bounds=(0, 4), dealias=3/2)
+    zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, 1), dealias=3/2)
+    u = dist.VectorField(coords, name='u', bases=(xb, zb))
+    b = dist.Field(name='b', bases=(xb, zb))
+    u['c'] = g['u_c']; b['c'] = g['b_c']
+    nu = 0.37
+    tasks = dict(vorticity=-d3.div(d3.skew(u)), Re=np.sqrt(u@u)/nu, ke=0.5*(u@u), sinb_b=np.sin(b)*b + b,
+                 grad_mag=np.sqrt(d3.grad(b)@d3.grad(b)), absdiv=np.abs(d3.div(u)) * 2.0)
+    return dist, u, b, tasks
+
+
+def check_expressions(g):
+    """The output-task expressions of the stock Rayleigh-Benard script (rayleigh_benard.py:93-103) and other grid-function
+    expressions: grid data at scale 1 and coefficient data as the reference's Future.evaluate returns them."""
+    dist, u, b, tasks = setup(g)
+    for name, op in tasks.items():
+        for rep in range(2):                    # the second evaluation reuses the compiled program
+            f = op.evaluate()
+            ref_c = g[f"{name}_c"]
+            assert np.allclose(f['c'], ref_c, rtol=1e-10, atol=1e-12 * np.abs(ref_c).max()), (name, "c", np.abs(f['c'] - ref_c).max())
+            f.change_scales(1)
+            ref_g = g[f"{name}_g"]
+            assert np.allclose(f['g'], ref_g, rtol=1e-10, atol=1e-12 * np.abs(ref_g).max()), (name, "g", np.abs(f['g'] - ref_g).max())
+    # numpy scalars on the left keep dispatching to the operand overloads
+    e = np.float64(2.0) * b + np.float64(1.0) * b
+    assert np.allclose(e.evaluate()['c'], 3 * g['b_c'], rtol=1e-13, atol=1e-14)

@@ -652,3 +652,82 @@ def gen_cfl_curvilinear():
 
 if __name__ == "__main__" and "cfl_curvilinear" in sys.argv[1:]:
     gen_cfl_curvilinear()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Stand-alone expression evaluation (analysis tasks / flow properties of the stock Rayleigh-Benard script)
+# ----------------------------------------------------------------------------------------------------------
+def gen_expressions():
+    """Output-task expressions of examples/ivp_2d_rayleigh_benard/rayleigh_benard.py:93-103 (vorticity, Reynolds number) and a
+    few more grid-function expressions, evaluated by the reference on seeded random fields (RealFourier x ChebyshevT, dealias 3/2):
+    coefficient data and grid data at scale 1, as the reference's handlers deliver them."""
+    out = {}
+    Nx, Nz = 32, 16
+    coords = d3.CartesianCoordinates('x', 'z')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    xb = d3.RealFourier(coords['x'], size=Nx, bounds=(0, 4), dealias=3/2)
+    zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, 1), dealias=3/2)
+    u = dist.VectorField(coords, name='u', bases=(xb, zb))
+    b = dist.Field(name='b', bases=(xb, zb))
+    u.fill_random('g', seed=11, distribution='normal', scale=1.0); u.low_pass_filter(scales=0.75)
+    b.fill_random('g', seed=12, distribution='normal', scale=1.0); b.low_pass_filter(scales=0.75)
+    out['u_c'] = u['c'].copy(); out['b_c'] = b['c'].copy(); out['meta'] = np.array([Nx, Nz])
+    nu = 0.37
+    tasks = dict(vorticity=-d3.div(d3.skew(u)), Re=np.sqrt(u@u)/nu, ke=0.5*(u@u), sinb_b=np.sin(b)*b + b,
+                 grad_mag=np.sqrt(d3.grad(b)@d3.grad(b)), absdiv=np.abs(d3.div(u)) * 2.0)
+    for name, op in tasks.items():
+        f = op.evaluate()
+        f.change_scales(1)
+        out[f"{name}_g"] = f['g'].copy()
+        out[f"{name}_c"] = f['c'].copy()
+    np.savez_compressed(HERE / "expressions.npz", **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__" and "expressions" in sys.argv[1:]:
+    gen_expressions()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Stock example scripts, executed by the reference with reduced sizes (the test executes the same source with the import changed)
+# ----------------------------------------------------------------------------------------------------------
+STOCK = {
+    "rb2d": ("examples/ivp_2d_rayleigh_benard/rayleigh_benard.py",
+             [("Nx, Nz = 256, 64", "Nx, Nz = 32, 16"), ("stop_sim_time = 50", "stop_sim_time = 2")], ("b", "u", "p")),
+    "kdv": ("examples/ivp_1d_kdv_burgers/kdv_burgers.py",
+            [("Nx = 1024", "Nx = 64"), ("stop_sim_time = 10", "stop_sim_time = 0.05")], ("u",)),
+}
+
+
+def run_stock(tag):
+    """Execute a stock script of the reference with the substitutions above; output handlers need h5py, which the shim does not
+    have, so the lines creating file handlers are dropped for the reference run only."""
+    import re
+    rel, subs, names = STOCK[tag]
+    src = (pathlib.Path("/root/reference") / rel).read_text()
+    for old, new in subs:
+        assert src.count(old) == 1, old
+        src = src.replace(old, new)
+    src = "\n".join(l for l in src.splitlines() if not re.match(r"\s*snapshots(\.| =)", l))
+    src = src.replace("import matplotlib.pyplot as plt", "plt = None").split("# Plot")[0]
+    ns = {"__name__": "__main__"}
+    exec(compile(src, rel, "exec"), ns)
+    out = {f"{tag}_{n}": ns[n]['c'].copy() for n in names}
+    out[f"{tag}_iteration"] = np.array(ns['solver'].iteration)
+    out[f"{tag}_sim_time"] = np.array(ns['solver'].sim_time)
+    for extra in ("max_Re", "timestep"):
+        if extra in ns:
+            out[f"{tag}_{extra}"] = np.array(float(ns[extra]))
+    return out
+
+
+def gen_stock():
+    out = {}
+    for tag in STOCK:
+        out.update(run_stock(tag))
+    np.savez_compressed(HERE / "stock_scripts.npz", **out)
+    print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
+
+
+if __name__ == "__main__" and "stock" in sys.argv[1:]:
+    gen_stock()

@@ -1,0 +1,15 @@
+"""Stand-alone expression evaluation (analysis tasks, flow properties) through the CPU emulation of the kernels."""
+import numpy as np, pytest
+from emu import emu_lib as E
+import expression_cases as X
+
+
+@pytest.fixture(autouse=True)
+def emulation():
+    E.install()
+    yield
+    E.uninstall()
+
+
+def test_task_expressions_match_reference(golden):
+    X.check_expressions(golden("expressions.npz"))

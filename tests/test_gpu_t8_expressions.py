@@ -1,0 +1,10 @@
+"""Stand-alone expression evaluation on the GPU (analysis tasks / flow properties of the stock Rayleigh-Benard script: vorticity,
+np.sqrt(u@u)/nu, ...) against the unmodified reference (tests/golden/expressions.npz)."""
+import pytest
+import expression_cases as X
+
+pytestmark = pytest.mark.gpu
+
+
+def test_task_expressions_match_reference(golden):
+    X.check_expressions(golden("expressions.npz"))
