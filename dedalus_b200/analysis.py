@@ -1,0 +1,240 @@
+"""Stand-alone evaluation of output expressions on curvilinear domains (sphere, spherical shell): the analysis tasks and flow
+properties of the stock scripts -- `b(r=(Ri+Ro)/2)`, `flux(r=Ro)`, `flux(phi=0)` with `flux = er @ (-kappa*grad(b) + u*b)`,
+`np.sqrt(u@u)/nu` (examples/ivp_shell_convection/shell_convection.py:82-109) -- evaluated when a handler fires, not inside a step.
+
+Reference: Future.evaluate (core/future.py:149-206) walking the tree with the layout rules of each node:
+  * products, powers and grid functions act on the dealiased grid values of their operands (arithmetic.py:560-580, 666-674,
+    855-866; operators.py:505-640), with lower-dimensional operands (the radial unit vector) broadcast;
+  * sums that contain such a term meet their operands on the grid: the conversions the reference inserts between different
+    radial bases (arithmetic.py:94-98) are plain copies in grid space (operators.py:1628-1638), so nothing is truncated;
+  * linear operators act on coefficients: shell gradient (dedalus_b200/shell_ivp.py ShellGradient), the separable sphere
+    operators (dedalus_b200/sphere.py evaluate_linear_expression), radial interpolation of a scalar (ShellRadialInterpolate,
+    core/basis.py:5823-5889);
+  * azimuthal interpolation acts on grid values and returns a field locked to the grid (InterpolateAzimuth, basis.py:5578-5635).
+Transforms are the library's own kernels (field layout changes); the elementwise arithmetic between whole grids is done with
+torch tensor expressions on the device -- cadence-scheduled output, never part of the time step."""
+import numpy as np
+from . import operators as ops
+from .field import Field
+
+_TORCH_NAMES = {'absolute': 'abs', 'arcsin': 'asin', 'arccos': 'acos', 'arctan': 'atan', 'arcsinh': 'asinh', 'arccosh': 'acosh',
+                'arctanh': 'atanh', 'conjugate': 'conj'}
+_NONLINEAR = (ops.Multiply, ops.DotProduct, ops.Power, ops.UnaryGridFunction)
+
+
+class LockedField:
+    """Result of an azimuthal interpolation: grid data only (reference LockedField, core/field.py:1046-1075)."""
+
+    def __init__(self, tensor, scales, tensorsig):
+        self._dev, self.scales, self.tensorsig, self.layout = tensor, tuple(scales), tensorsig, 'g'
+
+    def change_scales(self, scales):
+        if isinstance(scales, (int, float)):
+            scales = (scales,) * len(self.scales)
+        if tuple(scales) != self.scales:
+            raise ValueError("Cannot change the scales of a field locked to the grid.")
+
+    def change_layout(self, layout):
+        if layout not in ('g', 'grid'):
+            raise ValueError("Cannot change locked axis to coeff space.")
+
+    def device_data(self):
+        return self._dev
+
+    @property
+    def data(self):
+        return self._dev.detach().cpu().numpy()
+
+    def __getitem__(self, key):
+        layout = key[0] if isinstance(key, tuple) else key
+        if isinstance(key, tuple):
+            self.change_scales(key[1])
+        self.change_layout(layout)
+        return self.data
+
+
+def _const(x):
+    return all(b is None for b in x.bases)
+
+
+def _full_basis(e):
+    from .sphere import sphere_basis_of
+    from .shell import shell_basis_of
+    return shell_basis_of(e) or sphere_basis_of(e)
+
+
+def _temp_field(e, bases):
+    f = Field(e.dist, bases=bases, tensorsig=e.tensorsig, dtype=e.dtype)
+    e.dist._fields.pop()
+    return f
+
+
+class CurvilinearEvaluation:
+    def __init__(self, dist):
+        self.dist = dist
+
+    # ---- grid side ---------------------------------------------------------------------------------------------------
+    def grid(self, e):
+        """Coordinate components of e on the dealiased grid: tensor of shape tshape + grid (size-1 axes where e is constant)."""
+        import torch
+        if not isinstance(e, ops.Operand):
+            return float(e)
+        if isinstance(e, Field):
+            return e.copy_device_to_grid()
+        if isinstance(e, ops.ScalarMul):
+            return e.c * self.grid(e.args[0])
+        if isinstance(e, ops.Add):
+            total = None
+            for a in e.args:
+                g = self.grid(a)
+                total = g if total is None else total + g
+            return total
+        if isinstance(e, ops.Multiply):
+            A, B = e.args
+            ga, gb = self.grid(A), self.grid(B)
+            if torch.is_tensor(ga) and torch.is_tensor(gb):       # tensor product: A's indices first
+                ra, rb = len(A.tensorsig), len(B.tensorsig)
+                ga = ga.reshape(tuple(ga.shape[:ra]) + (1,) * rb + tuple(ga.shape[ra:]))
+                gb = gb.reshape((1,) * ra + tuple(gb.shape))
+            return ga * gb
+        if isinstance(e, ops.DotProduct):
+            A, B = e.args
+            ga, gb = self.grid(A), self.grid(B)
+            ra, rb = len(A.tensorsig), len(B.tensorsig)
+            ga = ga.reshape(tuple(ga.shape[:ra]) + (1,) * (rb - 1) + tuple(ga.shape[ra:]))
+            gb = gb.reshape((1,) * (ra - 1) + tuple(gb.shape))
+            return (ga * gb).sum(dim=ra - 1)
+        if isinstance(e, ops.Power):
+            return self.grid(e.args[0]) ** e.n
+        if isinstance(e, ops.UnaryGridFunction):
+            name = getattr(e.func, '__name__', str(e.func))
+            fn = getattr(torch, _TORCH_NAMES.get(name, name), None)
+            if fn is None:
+                raise NotImplementedError(f"grid function {name!r} has no device implementation")
+            return fn(self.grid(e.args[0]))
+        if isinstance(e, ops.Interpolate) and self._azimuthal(e):
+            g = self.grid(e.args[0])
+            basis = _full_basis(e.args[0])
+            nt = len(e.tensorsig)
+            w = torch.from_numpy(self._azimuth_weights(basis, g.shape[nt], e.position)).to(g.device)
+            shape = [1] * g.dim(); shape[nt] = -1
+            return (g * w.reshape(shape)).sum(dim=nt, keepdim=True)
+        return self.field(e).copy_device_to_grid()
+
+    def _azimuthal(self, e):
+        basis = _full_basis(e.args[0])
+        return basis is not None and e.axis == self.dist.get_basis_axis(basis)
+
+    @staticmethod
+    def _azimuth_weights(basis, Ng, position):
+        """Interpolation to azimuth `position` from Ng equispaced grid values of a function band-limited to |m| < Nphi / 2:
+        interpolation row of the real Fourier basis times its forward transform matrix (reference basis.py:5615-5624)."""
+        K = basis.shape[0] // 2 - 1
+        phi_j = 2 * np.pi * np.arange(Ng) / Ng
+        w = np.ones(Ng)
+        for k in range(1, K + 1):
+            w += 2 * np.cos(k * (position - phi_j))
+        return w / Ng
+
+    # ---- coefficient side --------------------------------------------------------------------------------------------
+    def field(self, e):
+        """e as a Field (coefficient data available through the usual layout changes)."""
+        from .sphere import sphere_basis_of, evaluate_linear_expression
+        from .shell import shell_basis_of
+        if isinstance(e, Field):
+            return e
+        if isinstance(e, ops.Convert):
+            return self.field(e.args[0])
+        nonlinear_top = isinstance(e, _NONLINEAR) or (isinstance(e, (ops.Add, ops.ScalarMul)) and self._has_nonlinear(e))
+        if nonlinear_top:
+            return self._materialize(e, self.grid(e))
+        shell = shell_basis_of(e.args[0]) if getattr(e, 'args', None) else None
+        if isinstance(e, ops.Interpolate) and self._azimuthal(e):
+            raise NotImplementedError("azimuthal interpolation returns grid data only; use it as the outermost operator of a task")
+        if shell is not None:
+            if isinstance(e, ops.Gradient):
+                return self._shell_gradient(self.field(e.args[0]), e)
+            if isinstance(e, ops.Interpolate) and e.axis == self.dist.get_basis_axis(shell) + 2:
+                return self._shell_radial_interpolation(self.field(e.args[0]), e)
+            if isinstance(e, (ops.Add, ops.ScalarMul)):
+                return self._materialize(e, self.grid(e))
+            raise NotImplementedError(f"{type(e).__name__} of shell fields in output expressions")
+        if sphere_basis_of(e) is not None:
+            return evaluate_linear_expression(self._with_field_leaves(e))
+        raise NotImplementedError(f"{type(e).__name__} in curvilinear output expressions")
+
+    def _has_nonlinear(self, e):
+        if isinstance(e, _NONLINEAR):
+            return True
+        if isinstance(e, ops.Interpolate) and self._azimuthal(e):
+            return True
+        return any(self._has_nonlinear(a) for a in getattr(e, 'args', []) if isinstance(a, ops.Operand))
+
+    def _with_field_leaves(self, e):
+        """Replace the nonlinear subtrees of a separable-operator expression by fields."""
+        import copy
+        if isinstance(e, Field) or not isinstance(e, ops.Operand):
+            return e
+        if isinstance(e, _NONLINEAR):
+            return self.field(e)
+        new = copy.copy(e)
+        new.args = [self._with_field_leaves(a) for a in e.args]
+        return new
+
+    def _materialize(self, e, g):
+        """Grid values (dealias scales) -> a temporary field on e's bases."""
+        basis = _full_basis(e)
+        if basis is None or any(b is None for b in e.bases):
+            raise NotImplementedError("lower-dimensional results of grid expressions")
+        f = _temp_field(e, (basis,))
+        ax = self.dist.get_basis_axis(basis)
+        scales = tuple(basis.dealias)
+        full = f.tshape + tuple(self.dist.grid_local_slice(ax + i, basis, scales[i]).stop - self.dist.grid_local_slice(ax + i, basis, scales[i]).start
+                                for i in range(basis.dim))
+        f.set_device_data(g.expand(full).contiguous(), 'g', scales=self.dist.remedy_scales(scales))
+        return f
+
+    def _shell_gradient(self, f, e):
+        from .shell import shell_basis_of
+        from .shell_ivp import ShellGradient, RadialOps
+        basis = shell_basis_of(f)
+        if any(b is not None and b is not basis for b in f.bases):
+            raise NotImplementedError("gradients of fields that are not on the full shell basis")
+        rops = RadialOps(basis.shape[2], basis.radii, basis.alpha)
+        f.change_layout('c')
+        dev = f.device_data()
+        rank = len(f.tensorsig)
+        prog = ShellGradient.cached(basis, rops, rank, self.dist, dev.device)
+        c = dev.reshape((3 ** rank,) + tuple(dev.shape[rank:])).contiguous()
+        out = prog.apply(c)
+        res = _temp_field(e, (basis.derivative_basis(1),))
+        res.set_device_data(out.reshape(res.tshape + tuple(out.shape[1:])), 'c')
+        return res
+
+    def _shell_radial_interpolation(self, f, e):
+        """Scalar field at radius r0: sum_n c[m, l, n] (dR / r0)^k P_n^(alpha + k)(z(r0))  (reference basis.py:5823-5889)."""
+        import torch
+        from .shell import shell_basis_of
+        from .shell_ivp import RadialOps
+        if f.tensorsig:
+            raise NotImplementedError("radial interpolation of tensor fields in output expressions")
+        basis = shell_basis_of(f)
+        rops = RadialOps(basis.shape[2], basis.radii, basis.alpha)
+        f.change_layout('c')
+        c = f.device_data()
+        vec = torch.from_numpy(np.ascontiguousarray(rops.basis_functions(basis.k, e.position)[0])).to(c.device)
+        out = (c * vec).sum(dim=-1, keepdim=True)
+        res = _temp_field(e, (basis.S2_basis(radius=e.position),))
+        res.set_device_data(out.contiguous(), 'c')
+        return res
+
+    # ---- entry -------------------------------------------------------------------------------------------------------
+    def evaluate(self, e):
+        if isinstance(e, ops.Interpolate) and self._azimuthal(e):
+            basis = _full_basis(e.args[0])
+            return LockedField(self.grid(e), self.dist.remedy_scales(tuple(basis.dealias)), e.tensorsig)
+        return self.field(e)
+
+
+def evaluate_curvilinear(expr):
+    return CurvilinearEvaluation(expr.dist).evaluate(expr)

@@ -693,13 +693,11 @@ class ExpressionProgram:
 
 
 def evaluate_expression(expr):
-    """Stand-alone evaluation (reference Future.evaluate): separable operator expressions of sphere fields, and any polynomial /
-    grid-function expression of Cartesian fields.  The compiled program is cached on the expression."""
-    from .sphere import sphere_basis_of, evaluate_linear_expression
-    if sphere_basis_of(expr) is not None:
-        return evaluate_linear_expression(expr)
+    """Stand-alone evaluation (reference Future.evaluate): output expressions on the sphere / shell (dedalus_b200/analysis.py), and
+    any polynomial / grid-function expression of Cartesian fields (compiled program cached on the expression)."""
     if getattr(expr.dist.coordsys, 'curvilinear', False):
-        raise NotImplementedError("Stand-alone expression evaluation on curvilinear domains is limited to separable sphere operators.")
+        from .analysis import evaluate_curvilinear
+        return evaluate_curvilinear(expr)
     prog = getattr(expr, '_program', None)
     if prog is None:
         prog = expr._program = ExpressionProgram(expr)

@@ -551,6 +551,76 @@ class ShellSystems:
 # ------------------------------------------------------------------------------------------------------------
 # Right-hand sides:  sum coef * (state field | grad(state field)) products, evaluated on the dealiased grid
 # ------------------------------------------------------------------------------------------------------------
+class ShellGradient:
+    """Gradient of a shell field of tensor rank `rank` (radial basis k = 0) in coefficient space, regularity components
+    (reference SphericalGradient, core/operators.py:3280-3310): two l-independent radial matrices per sign and the
+    multiplication AB / dR (db_mmt_apply along r), then ONE db_pair_lincomb with the per-(m, l) symbols xi(mu, l + R) and
+    xi(mu, l + R) (l + R).  Output: (3 * 3^rank, pairs, l, r) in the basis k = 1, gradient index first."""
+
+    _cache = {}
+
+    @classmethod
+    def cached(cls, basis, rops, rank, dist, dev):
+        key = (basis, rank, dist.rank, dist.size, str(dev))
+        if key not in cls._cache:
+            cls._cache[key] = cls(basis, rops, rank, dist, dev)
+        return cls._cache[key]
+
+    def __init__(self, basis, rops, rank, dist, dev):
+        import torch
+        from .sphere import PairProgram
+        if basis.k != 0:
+            raise NotImplementedError("gradients of shell fields in a k > 0 radial basis")
+        sb = basis.sphere_basis
+        j0, j1 = sb.local_pairs(dist)
+        self.cshape = (2 * (j1 - j0), basis.coeff_shape[1], basis.coeff_shape[2])
+        self.device = dev
+        _, ell_map = sb.elements_to_groups()
+        ell_pairs = ell_map[0::2][j0:j1]
+        in_range = ell_pairs <= sb.Lmax
+        lidx = np.minimum(ell_pairs, sb.Lmax)
+        q = rops._parts(0)
+        dense = lambda M: torch.from_numpy(np.ascontiguousarray(M.toarray())).to(dev)
+        self.D0 = {mu: dense((q['DZ'] - (1 - (1 if mu == -1 else 0)) * q['AB']) / rops.dR) for mu in (-1, +1)}
+        self.ABm = dense(q['AB'] / rops.dR)
+        nin = self.nin = 3 ** rank
+        syms, rows = [], []
+        for a, mu in ((0, -1), (1, +1), (2, 0)):
+            for ci in range(nin):
+                rin = tuple(np.unravel_index(ci, (3,) * rank)) if rank else ()
+                R = regtotal(rin)
+                if mu == 0:
+                    rows.append([])
+                    continue
+                rout = (a,) + rin
+                tab = np.zeros(sb.Lmax + 1); tab2 = np.zeros(sb.Lmax + 1)
+                for ell in range(sb.Lmax + 1):
+                    if regularity_allowed(ell, rin) and regularity_allowed(ell, rout):
+                        tab[ell] = xi(mu, ell + R)
+                        tab2[ell] = xi(mu, ell + R) * (ell + R)
+                off1 = len(syms) * ell_pairs.size; syms.append(np.where(in_range, tab[lidx], 0.0).ravel())
+                off2 = len(syms) * ell_pairs.size; syms.append(np.where(in_range, tab2[lidx], 0.0).ravel())
+                src_D = (0 if mu == -1 else 1) * nin + ci
+                rows.append([(src_D, 1.0, off1), (2 * nin + ci, -float(mu), off2)])
+        self.prog = PairProgram(rows, dev, torch.from_numpy(np.concatenate(syms)).to(dev))
+
+    def _mmt(self, mat, inp, out):
+        from .lib import get_lib, current_stream
+        n_out, n_in = mat.shape
+        get_lib().call("db_mmt_apply", mat.data_ptr(), n_out, n_in, inp.data_ptr(), out.data_ptr(), inp.numel() // n_in, 1, current_stream())
+
+    def apply(self, c):
+        """c: (3^rank, pairs, l, r) contiguous regularity components."""
+        import torch
+        Nc0, Nc1, Nr = self.cshape
+        nin = self.nin
+        stack = torch.empty((3 * nin, Nc0, Nc1, Nr), dtype=torch.float64, device=self.device)
+        self._mmt(self.D0[-1], c, stack[0:nin]); self._mmt(self.D0[+1], c, stack[nin:2 * nin]); self._mmt(self.ABm, c, stack[2 * nin:])
+        out = torch.empty((3 * nin, Nc0, Nc1, Nr), dtype=torch.float64, device=self.device)
+        self.prog.apply(stack, out, Nc0 // 2, Nc1 * Nr, sym_div=Nr)
+        return out
+
+
 class ShellRHSPlan:
     """Explicit terms of a shell IVP (reference: Evaluator walking the RHS trees, core/evaluator.py:95-146).
       1. gradients of state fields in coefficient space: two l-independent radial matrices per sign (db_mmt_apply along r) and
@@ -642,43 +712,11 @@ class ShellRHSPlan:
         self.n_p = sum(p['ncomp'] for p in self.products)
         if self.n_p == 0:
             return
-        # ---- gradient programs: stacked input [D0_- x, D0_+ x, AB x / dR] per field
-        _, ell_map = sb.elements_to_groups()
-        ell_pairs = ell_map[0::2][j0:j1]
-        in_range = ell_pairs <= sb.Lmax
-        lidx = np.minimum(ell_pairs, sb.Lmax)
+        # ---- gradient programs, one per tensor rank of the differentiated fields
         self.grads = {}
-        ro = self.rops
-        q = ro._parts(0)
-        dense = lambda M: torch.from_numpy(np.ascontiguousarray(M.toarray())).to(dev)
-        self.D0 = {mu: dense((q['DZ'] - (1 - (1 if mu == -1 else 0)) * q['AB']) / ro.dR) for mu in (-1, +1)}
-        self.ABm = dense(q['AB'] / ro.dR)
         for o in operands:
-            if o['kind'] != 'grad' or id(o['field']) in self.grads:
-                continue
-            f = o['field']
-            rin_rank = len(f.tensorsig)
-            nin = 3 ** rin_rank
-            syms, rows = [], []
-            for a, mu in ((0, -1), (1, +1), (2, 0)):
-                for ci in range(nin):
-                    rin = tuple(np.unravel_index(ci, (3,) * rin_rank)) if rin_rank else ()
-                    R = regtotal(rin)
-                    if mu == 0:
-                        rows.append([])
-                        continue
-                    rout = (a,) + rin
-                    tab = np.zeros(sb.Lmax + 1); tab2 = np.zeros(sb.Lmax + 1)
-                    for ell in range(sb.Lmax + 1):
-                        if regularity_allowed(ell, rin) and regularity_allowed(ell, rout):
-                            tab[ell] = xi(mu, ell + R)
-                            tab2[ell] = xi(mu, ell + R) * (ell + R)
-                    off1 = len(syms) * ell_pairs.size; syms.append(np.where(in_range, tab[lidx], 0.0).ravel())
-                    off2 = len(syms) * ell_pairs.size; syms.append(np.where(in_range, tab2[lidx], 0.0).ravel())
-                    src_D = (0 if mu == -1 else 1) * nin + ci
-                    rows.append([(src_D, 1.0, off1), (2 * nin + ci, -float(mu), off2)])
-            from .sphere import PairProgram
-            self.grads[id(f)] = dict(nin=nin, prog=PairProgram(rows, dev, torch.from_numpy(np.concatenate(syms)).to(dev)))
+            if o['kind'] == 'grad' and id(o['field']) not in self.grads:
+                self.grads[id(o['field'])] = ShellGradient.cached(basis, self.rops, len(o['field'].tensorsig), dist, dev)
         # ---- pointwise program (general kernel)
         coef, fac_ptr, fac, term_ptr = [], [0], [], [0]
         for p in self.products:
@@ -694,6 +732,8 @@ class ShellRHSPlan:
         self.g_in = torch.zeros((self.n_g,) + self.gshape, dtype=torch.float64, device=dev)
         self.g_out = torch.zeros((self.n_p,) + self.gshape, dtype=torch.float64, device=dev)
         # ---- conversions product basis -> equation basis (sign folded in: F enters as +F, the minus signs sit in the polynomial)
+        ro = self.rops
+        dense = lambda M: torch.from_numpy(np.ascontiguousarray(M.toarray())).to(dev)
         self.convert = {}
         for p in self.products:
             key = (p['k'], p['k_eq'])
@@ -751,14 +791,8 @@ class ShellRHSPlan:
             c = views[id(f)].reshape((-1, Nc0, Nc1, Nr))
             if o['kind'] == 'grad':
                 if id(f) not in grads:
-                    G = self.grads[id(f)]
-                    nin = G['nin']
-                    stack = torch.empty((3 * nin, Nc0, Nc1, Nr), dtype=torch.float64, device=self.device)
                     with Timed(prof, "shell_gradient", 8 * 4 * c.numel()):
-                        self._mmt(self.D0[-1], c, stack[0:nin]); self._mmt(self.D0[+1], c, stack[nin:2 * nin]); self._mmt(self.ABm, c, stack[2 * nin:])
-                        out = torch.empty((3 * nin, Nc0, Nc1, Nr), dtype=torch.float64, device=self.device)
-                        G['prog'].apply(stack, out, Nc0 // 2, Nc1 * Nr, sym_div=Nr)
-                    grads[id(f)] = out
+                        grads[id(f)] = self.grads[id(f)].apply(c)
                 c = grads[id(f)]
             with Timed(prof, "shell_backward", 8 * (c.numel() + 3 ** o['rank'] * self.npoints)):
                 g = shell_components_to_grid(self._basis_k(o['k']), c.contiguous(), o['rank'], self.scales, self.dist)

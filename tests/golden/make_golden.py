@@ -694,6 +694,9 @@ if __name__ == "__main__" and "expressions" in sys.argv[1:]:
 STOCK = {
     "rb2d": ("examples/ivp_2d_rayleigh_benard/rayleigh_benard.py",
              [("Nx, Nz = 256, 64", "Nx, Nz = 32, 16"), ("stop_sim_time = 50", "stop_sim_time = 2")], ("b", "u", "p")),
+    "shell": ("examples/ivp_shell_convection/shell_convection.py",
+              [("Nphi, Ntheta, Nr = 192, 96, 6", "Nphi, Ntheta, Nr = 16, 8, 6"), ("stop_sim_time = 2000", "stop_sim_time = 12")],
+              ("p", "b", "u")),
     "kdv": ("examples/ivp_1d_kdv_burgers/kdv_burgers.py",
             [("Nx = 1024", "Nx = 64"), ("stop_sim_time = 10", "stop_sim_time = 0.05")], ("u",)),
 }
@@ -731,3 +734,42 @@ def gen_stock():
 
 if __name__ == "__main__" and "stock" in sys.argv[1:]:
     gen_stock()
+
+
+def gen_shell_tasks():
+    """Output tasks and the flow property of examples/ivp_shell_convection/shell_convection.py:82-109 -- radial interpolation of a
+    field and of a flux built from a radial unit vector, a gradient and a product; azimuthal interpolation; np.sqrt(u@u)/nu --
+    evaluated by the reference on a state a few steps into the run (16 x 8 x 6, dealias 3/2), at the scales the script asks for."""
+    res = shell_convection((16, 8, 6), 4)
+    Ri, Ro = 14, 15
+    Rayleigh = 3500; Prandtl = 1; dealias = 3/2
+    coords = d3.SphericalCoordinates('phi', 'theta', 'r')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    shell = d3.ShellBasis(coords, shape=(16, 8, 6), radii=(Ri, Ro), dealias=dealias, dtype=np.float64)
+    b = dist.Field(name='b', bases=shell); u = dist.VectorField(coords, name='u', bases=shell)
+    b['c'] = res['b1']; u['c'] = res['u1'] * 1e3          # amplified: the velocity is still tiny after four steps
+    kappa = (Rayleigh * Prandtl)**(-1/2); nu = (Rayleigh / Prandtl)**(-1/2)
+    er = dist.VectorField(coords, bases=shell.radial_basis); er['g'][2] = 1
+    flux = er @ (-kappa*d3.grad(b) + u*b)
+    out = dict(b_c=b['c'].copy(), u_c=u['c'].copy())
+    tasks = dict(bmid=(b(r=(Ri+Ro)/2), dealias), flux_r_outer=(flux(r=Ro), dealias), flux_r_inner=(flux(r=Ri), dealias),
+                 flux_phi_start=(flux(phi=0), dealias), flux_phi_end=(flux(phi=3*np.pi/2), dealias), Re=(np.sqrt(u@u)/nu, 1),
+                 flux=(flux, 1))
+    # evaluated the way the script's file handler evaluates them: scheduled, not forced -- the evaluator walks all tasks from
+    # coefficient space to the grid and back, so sums that contain a product are formed on the grid (a forced .evaluate() adds in
+    # the layout of the first operand instead, core/arithmetic.py:240-244)
+    problem = d3.IVP([b, u], namespace=locals())
+    problem.add_equation("dt(b) = 0"); problem.add_equation("dt(u) = 0")
+    solver = problem.build_solver(d3.SBDF1)
+    handler = solver.evaluator.add_dictionary_handler(iter=1)
+    for name, (op, scales) in tasks.items():
+        handler.add_task(op, layout='g', name=name, scales=scales)
+    solver.evaluator.evaluate_handlers([handler], iteration=0, wall_time=0, sim_time=0, timestep=1)
+    for name in tasks:
+        out[f"{name}_g"] = handler.fields[name]['g'].copy()
+    np.savez_compressed(HERE / "shell_tasks.npz", **out)
+    print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
+
+
+if __name__ == "__main__" and "shell_tasks" in sys.argv[1:]:
+    gen_shell_tasks()

@@ -1,6 +1,7 @@
 """Shared body of the spherical-shell transform tests (emulation: tests/test_emu_shell.py, GPU: tests/test_gpu_t6_shell.py)."""
 import numpy as np
 import dedalus_b200 as d3
+import pytest
 
 
 def check_shell_field_transforms(g, tag):
@@ -153,3 +154,30 @@ def check_dense_kernels(B):
         assert np.abs(xg - xr).max() <= 1e-10 * np.abs(xr).max(), (i, np.abs(xg - xr).max())
         assert np.allclose(yah[o:o + n * nc].reshape(n, nc), A[i] @ xg, rtol=1e-12, atol=1e-12)
         assert np.allclose(ybh[o:o + n * nc].reshape(n, nc), Bm[i] @ xg, rtol=1e-12, atol=1e-12)
+
+
+def check_shell_tasks(g):
+    """Output tasks and the flow property of the stock shell-convection script (shell_convection.py:82-109) on a stored state:
+    radial interpolations, the flux built from a radial unit vector, a gradient and a product, azimuthal interpolation (a field
+    locked to the grid) and np.sqrt(u@u)/nu, against the unmodified reference (tests/golden/shell_tasks.npz)."""
+    Ri, Ro = 14, 15
+    Rayleigh = 3500; Prandtl = 1; dealias = 3/2
+    coords = d3.SphericalCoordinates('phi', 'theta', 'r')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    shell = d3.ShellBasis(coords, shape=(16, 8, 6), radii=(Ri, Ro), dealias=dealias, dtype=np.float64)
+    b = dist.Field(name='b', bases=shell); u = dist.VectorField(coords, name='u', bases=shell)
+    b['c'] = g['b_c']; u['c'] = g['u_c']
+    kappa = (Rayleigh * Prandtl)**(-1/2); nu = (Rayleigh / Prandtl)**(-1/2)
+    er = dist.VectorField(coords, bases=shell.radial_basis); er['g'][2] = 1
+    flux = er @ (-kappa*d3.grad(b) + u*b)
+    tasks = dict(bmid=(b(r=(Ri+Ro)/2), dealias), flux_r_outer=(flux(r=Ro), dealias), flux_r_inner=(flux(r=Ri), dealias),
+                 flux_phi_start=(flux(phi=0), dealias), flux_phi_end=(flux(phi=3*np.pi/2), dealias), Re=(np.sqrt(u@u)/nu, 1),
+                 flux=(flux, 1))
+    for name, (op, scales) in tasks.items():
+        f = op.evaluate()
+        f.change_scales(scales)
+        got, ref = np.asarray(f['g']), g[f"{name}_g"]
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        assert np.allclose(got, ref, rtol=1e-9, atol=1e-11 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
+    with pytest.raises(ValueError):
+        f = flux(phi=0).evaluate(); f['c']

@@ -37,3 +37,7 @@ def test_dense_kernels_against_numpy(smem, monkeypatch):
     from test_emu_sphere import _EmuArrays
     monkeypatch.setenv("DB_DENSE_SOLVE_SMEM", smem)
     SC.check_dense_kernels(_EmuArrays())
+
+
+def test_shell_output_tasks_match_reference(golden):
+    SC.check_shell_tasks(golden("shell_tasks.npz"))

@@ -53,3 +53,9 @@ def test_sphere_analysis_tasks_with_operator_expressions(golden):
 def test_cfl_on_sphere_and_shell_matches_reference(golden):
     import sphere_cases as S
     S.check_cfl_curvilinear(golden("cfl_curvilinear.npz"))
+
+
+def test_shell_output_tasks_match_reference(golden):
+    """Tasks and flow property of the stock shell-convection script (radial / azimuthal interpolation of a flux, np.sqrt(u@u)/nu)."""
+    import shell_cases as SC
+    SC.check_shell_tasks(golden("shell_tasks.npz"))
