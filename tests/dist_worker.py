@@ -45,6 +45,57 @@ def main():
             print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
         dist.destroy_process_group()
         return
+    if which.startswith("tasks:"):
+        # stand-alone output expressions on a distributed domain: every rank holds its block of the reference's grid / coefficient data
+        kind = which.split(":")[1]
+        ok = True
+        if kind == "cartesian":
+            import expression_cases as X
+            g = np.load(ROOT / "tests" / "golden" / "expressions.npz")
+            Nx, Nz = (int(v) for v in g['meta'])
+            coords = d3.CartesianCoordinates('x', 'z')
+            dd = d3.Distributor(coords, dtype=np.float64, mesh=(world,))
+            xb = d3.RealFourier(coords['x'], size=Nx, bounds=(0, 4), dealias=3/2)
+            zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, 1), dealias=3/2)
+            u = dd.VectorField(coords, name='u', bases=(xb, zb)); b = dd.Field(name='b', bases=(xb, zb))
+            cs = dd.coeff_local_slice(0, xb)
+            u['c'] = g['u_c'][:, cs]; b['c'] = g['b_c'][cs]
+            tasks = dict(vorticity=-d3.div(d3.skew(u)), Re=np.sqrt(u@u)/0.37, sinb_b=np.sin(b)*b + b)
+            for name, op in tasks.items():
+                f = op.evaluate()
+                ref_c = g[f"{name}_c"]
+                ok = ok and bool(np.allclose(f['c'], ref_c[cs], rtol=1e-10, atol=1e-12 * np.abs(ref_c).max()))
+                f.change_scales(1)
+                got = np.asarray(f['g'])
+                gs = tuple(dd.grid_local_slice(ax, bb, 1) for ax, bb in enumerate((xb, zb)))
+                ref_g = g[f"{name}_g"]
+                ok = ok and bool(np.allclose(got, ref_g[gs], rtol=1e-10, atol=1e-12 * np.abs(ref_g).max()))
+        if kind == "shell":
+            g = np.load(ROOT / "tests" / "golden" / "shell_tasks.npz")
+            Ri, Ro, dealias = 14, 15, 3/2
+            coords = d3.SphericalCoordinates('phi', 'theta', 'r')
+            dd = d3.Distributor(coords, dtype=np.float64, mesh=(world,))
+            shell = d3.ShellBasis(coords, shape=(16, 8, 6), radii=(Ri, Ro), dealias=dealias, dtype=np.float64)
+            b = dd.Field(name='b', bases=shell); u = dd.VectorField(coords, name='u', bases=shell)
+            rows = dd.coeff_local_slice(0, shell)
+            b['c'] = g['b_c'][rows]; u['c'] = g['u_c'][:, rows]
+            kappa = nu = 3500 ** (-1/2)
+            er = dd.VectorField(coords, bases=shell.radial_basis); er['g'][2] = 1
+            flux = er @ (-kappa*d3.grad(b) + u*b)
+            tasks = dict(bmid=(b(r=(Ri+Ro)/2), dealias), flux_r_outer=(flux(r=Ro), dealias), flux_phi_end=(flux(phi=3*np.pi/2), dealias),
+                         Re=(np.sqrt(u@u)/nu, 1), flux=(flux, 1))
+            for name, (op, scales) in tasks.items():
+                f = op.evaluate()
+                f.change_scales(scales)
+                got, ref = np.asarray(f['g']), g[f"{name}_g"]
+                th = dd.grid_local_slice(1, shell, scales)
+                ok = ok and got.shape == ref[:, th].shape and bool(np.allclose(got, ref[:, th], rtol=1e-9, atol=1e-11 * np.abs(ref).max()))
+        flag = torch.tensor([1 if ok else 0], device='cuda' if backend == "nccl" else 'cpu')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
+        dist.destroy_process_group()
+        return
     if which.startswith("sphere:"):
         # S2 shallow water distributed over the azimuthal pairs (coefficients) / colatitude (grid) against the reference state of
         # the same global problem
