@@ -1,5 +1,5 @@
 """Shared bodies of the sphere (S2) parity tests: the same checks run through the CPU emulation of the kernels
-(tests/test_emu_sphere.py) and on the GPU (tests/test_gpu_2_sphere.py).  All expected values come from the unmodified
+(tests/test_emu_sphere.py) and on the GPU (tests/test_gpu_t2_sphere.py).  All expected values come from the unmodified
 reference (tests/golden/sphere.npz, written by tests/golden/make_golden.py gen_sphere)."""
 import numpy as np
 import dedalus_b200 as d3

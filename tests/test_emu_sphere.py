@@ -1,5 +1,5 @@
 """Sphere (S2) path -- SphereBasis, spin recombination, SWSH transforms, per-m banded pencil systems, RHS plan -- executed
-on the CPU through the test-only kernel emulation against reference data; GPU versions: tests/test_gpu_2_sphere.py."""
+on the CPU through the test-only kernel emulation against reference data; GPU versions: tests/test_gpu_t2_sphere.py."""
 import ctypes as C
 import numpy as np, pytest
 from emu import emu_lib as E

@@ -14,7 +14,7 @@ def test_shell_field_transforms(golden, tag):
 
 @pytest.mark.parametrize("smem", ["1", "0"])
 def test_dense_kernels_against_numpy(smem, monkeypatch):
-    from test_gpu_2_sphere import _CudaArrays
+    from test_gpu_t2_sphere import _CudaArrays
     monkeypatch.setenv("DB_DENSE_SOLVE_SMEM", smem)
     SC.check_dense_kernels(_CudaArrays())
 
