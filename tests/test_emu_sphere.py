@@ -28,13 +28,10 @@ def test_shallow_water_matches_reference(golden, tag, scheme):
     assert solver.bset.last_verify < 1e-12
 
 
-def test_balanced_height_lbvp_then_ivp_matches_reference(golden):
-    """The whole stock script: LBVP with a gauge constant and an average condition, MulCosine on the right-hand side."""
-    S.check_balanced_shallow_water(golden("sphere_lbvp.npz"), "bal32")
-
-
 def test_stock_shallow_water_script_runs_with_only_the_import_changed(golden, tmp_path, monkeypatch):
-    """examples/ivp_sphere_shallow_water/shallow_water.py of the reference, read where it lies (this container only; the file is
+    """The whole stock script: LBVP with a gauge constant and an average condition, MulCosine on its right-hand side, then the IVP
+    (the same calls run on the GPU through sphere_cases.check_balanced_shallow_water, tests/test_gpu_t7_sphere_lbvp.py).
+    examples/ivp_sphere_shallow_water/shallow_water.py of the reference, read where it lies (this container only; the file is
     not copied), executed with `dedalus.public` -> `dedalus_b200` and the resolution / stop time reduced to the golden case."""
     import pathlib
     script = pathlib.Path("/root/reference/examples/ivp_sphere_shallow_water/shallow_water.py")
