@@ -11,7 +11,7 @@ from .shell import ShellBasis
 from .field import Field
 from .operators import (Differentiate, Gradient, Divergence, Laplacian, Trace, TransposeComponents,
                         Interpolate, Integrate, Lift, Convert, TimeDerivative, DotProduct, Multiply, Skew, MulCosine,
-                        grad, div, lap, skew, trace, transpose, integ, ave, dot, interp)
+                        grad, div, lap, skew, trace, transpose, integ, ave, dot, interp, Average, UnaryGridFunction)
 from .problems import IVP, LBVP
 InitialValueProblem = IVP
 LinearBoundaryValueProblem = LBVP

@@ -636,6 +636,20 @@ class ExpressionProgram:
     def __init__(self, expr):
         import copy
         self.stages = []           # (plan, torch function, temporary field)
+        # outer reductions -- integ / ave / interpolation, possibly nested and scaled (Nusselt numbers, profiles, mid-plane values):
+        # contractions of the coefficient data with the basis' row vectors (reference IntegrateJacobi / InterpolateRealFourier ...,
+        # core/basis.py:721-789, 1037-1290), applied to the result of the remaining expression
+        self.reductions = []
+        while True:
+            if isinstance(expr, ops.ScalarMul) and isinstance(expr.args[0], (ops.Integrate, ops.Interpolate)):
+                self.reductions.append(('scale', expr.c)); expr = expr.args[0]
+            elif isinstance(expr, ops.Integrate):
+                self.reductions.append(('integ', expr.axes, expr.average)); expr = expr.args[0]
+            elif isinstance(expr, ops.Interpolate) and not expr.trivial:
+                self.reductions.append(('interp', expr.axis, expr.position)); expr = expr.args[0]
+            else:
+                break
+        self.reductions.reverse()
 
         def sub(e):
             if isinstance(e, ops.UnaryGridFunction):
@@ -686,10 +700,52 @@ class ExpressionProgram:
             vals = fn(g)
             tmp.set_device_data(vals.reshape(tuple(cs.dim for cs in tmp.tensorsig) + tuple(plan.gshape)), 'g', scales=plan.dealias)
         if self.result_field is not None:
-            return self.result_field
-        self.final.evaluate(self.out_t)
-        self.out.set_device_data(self.out_view, 'c')
-        return self.out
+            out = self.result_field
+        else:
+            self.final.evaluate(self.out_t)
+            self.out.set_device_data(self.out_view, 'c')
+            out = self.out
+        return self._reduce(out) if self.reductions else out
+
+    def _reduce(self, f):
+        """Apply the outer integrations / averages / interpolations to the coefficient data of f."""
+        import torch
+        dist = f.dist
+        f.change_layout('c')
+        data = f.device_data()
+        bases = list(f.bases)
+        nt = len(f.tshape)
+        for red in self.reductions:
+            if red[0] == 'scale':
+                data = data * red[1]
+                continue
+            axes = red[1] if red[0] == 'integ' else (red[1],)
+            for ax in axes:
+                b = bases[ax]
+                if b is None:
+                    continue
+                if red[0] == 'interp':
+                    row = b.interpolation_vector(red[2])
+                elif red[2] and hasattr(b, 'average_vector'):
+                    row = b.average_vector()
+                else:
+                    row = b.integration_vector()
+                    if red[2]:
+                        row = row / b.COV.problem_length
+                row = np.asarray(row.todense()).ravel()
+                if np.iscomplexobj(row) and not np.iscomplexobj(np.zeros(0, dtype=f.dtype)):
+                    row = row.real
+                w = torch.from_numpy(np.ascontiguousarray(row[dist.coeff_local_slice(ax, b)])).to(data.device).to(data.dtype)
+                shape = [1] * data.dim(); shape[nt + ax] = -1
+                data = (data * w.reshape(shape)).sum(dim=nt + ax, keepdim=True)
+                if ax == 0 and dist.size > 1:
+                    import torch.distributed as td
+                    td.all_reduce(data, op=td.ReduceOp.SUM)
+                bases[ax] = None
+        out = Field(dist, bases=tuple(dict.fromkeys(b for b in bases if b is not None)), tensorsig=f.tensorsig, dtype=f.dtype)
+        dist._fields.pop()
+        out.set_device_data(data.contiguous(), 'c')
+        return out
 
 
 def evaluate_expression(expr):

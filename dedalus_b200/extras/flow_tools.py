@@ -141,6 +141,7 @@ class GlobalFlowProperty:
         self.cadence = cadence
         self.properties = {}
         self._values = {}
+        self._fields = {}
         solver.step_hooks.append(self._on_step)
 
     def add_property(self, property, name, precompute_integral=False):
@@ -154,14 +155,16 @@ class GlobalFlowProperty:
             return
         for name, p in self.properties.items():
             if not hasattr(p, 'copy_device_to_grid'):
-                self._values[name] = p.evaluate().copy_device_to_grid(scales=1)
+                self._fields[name] = p.evaluate()
+                self._values[name] = self._fields[name].copy_device_to_grid(scales=1)
 
     def _grid(self, name):
         p = self.properties[name]
         if hasattr(p, 'copy_device_to_grid'):
             return p.copy_device_to_grid()
         if name not in self._values:              # asked before the first scheduled evaluation
-            self._values[name] = p.evaluate().copy_device_to_grid(scales=1)
+            self._fields[name] = p.evaluate()
+            self._values[name] = self._fields[name].copy_device_to_grid(scales=1)
         return self._values[name]
 
     def _reduce(self, v, op):
@@ -183,3 +186,18 @@ class GlobalFlowProperty:
         total = self._reduce(g.sum(), 'SUM')
         count = self._reduce(torch.tensor(float(g.numel()), dtype=torch.float64, device=g.device), 'SUM')
         return total / count
+
+    def volume_integral(self, name):
+        """Volume integral of a property (reference flow_tools.py:117-130: Integrate of the handler's output field), Cartesian
+        domains."""
+        from ..operators import Integrate
+        p = self.properties[name]
+        if not hasattr(p, 'copy_device_to_grid'):
+            self._grid(name)
+            p = self._fields[name]
+        if getattr(p, 'copy_device_to_grid', None) is None or getattr(p.dist.coordsys, 'curvilinear', False):
+            raise NotImplementedError("volume integrals of flow properties on curvilinear domains")
+        return float(np.asarray(Integrate(p).evaluate()['g']).ravel()[0])
+
+    def volume_average(self, name):
+        raise NotImplementedError("missing definition of hypervolume")      # as in the reference (flow_tools.py:132-137)

@@ -398,6 +398,7 @@ def transpose(A): return TransposeComponents(A)
 def dt(A): return TimeDerivative(A)
 def integ(A, coords=None): return Integrate(A, coords)
 def ave(A, coords=None): return Integrate(A, coords, average=True)
+def Average(A, coords=None): return Integrate(A, coords, average=True)
 def dot(A, B): return DotProduct(A, B)
 def interp(A, **positions): return A(**positions)
 

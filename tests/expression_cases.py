@@ -31,6 +31,36 @@ def check_expressions(g):
             f.change_scales(1)
             ref_g = g[f"{name}_g"]
             assert np.allclose(f['g'], ref_g, rtol=1e-10, atol=1e-12 * np.abs(ref_g).max()), (name, "g", np.abs(f['g'] - ref_g).max())
+    # reductions of expressions: volume integral, horizontal average (a profile), mid-plane value, a point value ...
+    coords = dist.coordsys
+    x, z = coords['x'], coords['z']
+    reductions = dict(int_bb=d3.Integrate(d3.Integrate(b*b, x), z), prof_b=d3.Average(b, x), mid_uu=(u@u)(z=0.3),
+                      avg_speed=2.0*d3.Average(np.sqrt(u@u), x), point=b(x=1.3)(z=0.6), vol_avg=d3.Average(d3.Average(b, z), x),
+                      int_dzb=d3.Integrate(d3.Differentiate(b, z), z))
+    for name, op in reductions.items():
+        f = op.evaluate()
+        f.change_scales(1)
+        ref = g[f"red_{name}_g"]
+        got = np.asarray(f['g'])
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        assert np.allclose(got, ref, rtol=1e-10, atol=1e-12 * max(np.abs(ref).max(), 1e-3)), (name, np.abs(got - ref).max(), np.abs(ref).max())
     # numpy scalars on the left keep dispatching to the operand overloads
     e = np.float64(2.0) * b + np.float64(1.0) * b
     assert np.allclose(e.evaluate()['c'], 3 * g['b_c'], rtol=1e-13, atol=1e-14)
+
+
+def check_flow_property_reductions(g):
+    """GlobalFlowProperty with an expression property: max / min / grid_average of the scale-1 grid values and the volume integral
+    (reference extras/flow_tools.py:92-130) against numpy reductions of the reference's task output."""
+    from dedalus_b200 import examples
+    dist, u, b, tasks = setup(g)
+    pb = examples.rayleigh_benard(dim=2, Nh=16, Nz=16, Rayleigh=1e5)          # any solver: the properties hang on its step hooks
+    solver = pb['problem'].build_solver(d3.RK222)
+    flow = d3.GlobalFlowProperty(solver, cadence=1)
+    flow.add_property(tasks['Re'], name='Re')
+    ref = g['Re_g']
+    assert np.isclose(flow.max('Re'), ref.max(), rtol=1e-10)
+    assert np.isclose(flow.min('Re'), ref.min(), rtol=1e-10, atol=1e-13)
+    assert np.isclose(flow.grid_average('Re'), ref.mean(), rtol=1e-10)
+    flow.add_property(b * b, name='bb')
+    assert np.isclose(flow.volume_integral('bb'), float(g['red_int_bb_g'].ravel()[0]), rtol=1e-10)

@@ -680,6 +680,15 @@ def gen_expressions():
         f.change_scales(1)
         out[f"{name}_g"] = f['g'].copy()
         out[f"{name}_c"] = f['c'].copy()
+    # reductions: integrals, averages, interpolation (profiles, mid-plane values, volume integrals)
+    x, z = coords['x'], coords['z']
+    reductions = dict(int_bb=d3.Integrate(d3.Integrate(b*b, x), z), prof_b=d3.Average(b, x), mid_uu=(u@u)(z=0.3),
+                      avg_speed=2.0*d3.Average(np.sqrt(u@u), x), point=b(x=1.3)(z=0.6), vol_avg=d3.Average(d3.Average(b, z), x),
+                      int_dzb=d3.Integrate(d3.Differentiate(b, z), z))
+    for name, op in reductions.items():
+        f = op.evaluate()
+        f.change_scales(1)
+        out[f"red_{name}_g"] = f['g'].copy()
     np.savez_compressed(HERE / "expressions.npz", **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -13,3 +13,7 @@ def emulation():
 
 def test_task_expressions_match_reference(golden):
     X.check_expressions(golden("expressions.npz"))
+
+
+def test_flow_property_reductions_of_expressions(golden):
+    X.check_flow_property_reductions(golden("expressions.npz"))

@@ -8,3 +8,7 @@ pytestmark = pytest.mark.gpu
 
 def test_task_expressions_match_reference(golden):
     X.check_expressions(golden("expressions.npz"))
+
+
+def test_flow_property_reductions_of_expressions(golden):
+    X.check_flow_property_reductions(golden("expressions.npz"))
