@@ -706,6 +706,8 @@ STOCK = {
     "shell": ("examples/ivp_shell_convection/shell_convection.py",
               [("Nphi, Ntheta, Nr = 192, 96, 6", "Nphi, Ntheta, Nr = 16, 8, 6"), ("stop_sim_time = 2000", "stop_sim_time = 12")],
               ("p", "b", "u")),
+    "shear": ("examples/ivp_2d_shear_flow/shear_flow.py",
+              [("Nx, Nz = 128, 256", "Nx, Nz = 16, 32"), ("stop_sim_time = 20", "stop_sim_time = 0.12")], ("u", "s", "p")),
     "kdv": ("examples/ivp_1d_kdv_burgers/kdv_burgers.py",
             [("Nx = 1024", "Nx = 64"), ("stop_sim_time = 10", "stop_sim_time = 0.05")], ("u",)),
 }
@@ -727,7 +729,7 @@ def run_stock(tag):
     out = {f"{tag}_{n}": ns[n]['c'].copy() for n in names}
     out[f"{tag}_iteration"] = np.array(ns['solver'].iteration)
     out[f"{tag}_sim_time"] = np.array(ns['solver'].sim_time)
-    for extra in ("max_Re", "timestep"):
+    for extra in ("max_Re", "max_w", "timestep"):
         if extra in ns:
             out[f"{tag}_{extra}"] = np.array(float(ns[extra]))
     return out

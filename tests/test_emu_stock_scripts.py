@@ -13,6 +13,8 @@ STOCK = {
     "shell": ("examples/ivp_shell_convection/shell_convection.py",
               [("Nphi, Ntheta, Nr = 192, 96, 6", "Nphi, Ntheta, Nr = 16, 8, 6"), ("stop_sim_time = 2000", "stop_sim_time = 12")],
               ("p", "b", "u")),
+    "shear": ("examples/ivp_2d_shear_flow/shear_flow.py",
+              [("Nx, Nz = 128, 256", "Nx, Nz = 16, 32"), ("stop_sim_time = 20", "stop_sim_time = 0.12")], ("u", "s", "p")),
     "kdv": ("examples/ivp_1d_kdv_burgers/kdv_burgers.py",
             [("Nx = 1024", "Nx = 64"), ("stop_sim_time = 10", "stop_sim_time = 0.05")], ("u",)),
 }
@@ -58,8 +60,8 @@ def test_stock_script_with_only_the_import_changed(golden, tag, tmp_path, monkey
         got = ns[n]["c"]
         atol = 1e-11 * np.abs(ref).max() if tag != "shell" else 1e-10 * np.abs(g[f"{tag}_b"]).max()    # shell: u ~ 1e-6 b, as in shell_cases
         assert np.allclose(got, ref, rtol=1e-8, atol=atol), (n, np.abs(got - ref).max(), np.abs(ref).max())
-    for extra in ("max_Re", "timestep"):            # the CFL time step and the flow property the main loop logs
+    for extra in ("max_Re", "max_w", "timestep"):            # the CFL time step and the flow property the main loop logs
         if f"{tag}_{extra}" in g.files:
             assert np.isclose(float(ns[extra]), float(g[f"{tag}_{extra}"]), rtol=1e-9), extra
-    if tag in ("rb2d", "shell"):
+    if tag in ("rb2d", "shell", "shear"):
         assert list((tmp_path / "snapshots").iterdir())
