@@ -159,6 +159,7 @@ class RHSPlan:
         self.device = solver.device
         arena = solver.eq_arena
         self.static_entries = []      # (arena offset, value) for constant RHS
+        self.linear_copies = {}       # (equation, comp) -> [(coef, field, field comp)]: coefficient-space right-hand sides
         inputs = {}                   # (id(field), comp, derivs) -> index
         self.input_keys = []
         outputs = []                  # (eq index, comp, terms)
@@ -176,6 +177,18 @@ class RHSPlan:
                     self._add_constant(ie, eq, float(const), comp)
                 if not terms:
                     continue
+                if any(b is None for b in eq['bases']):
+                    # lower-dimensional equation (boundary conditions with data, "b(z=0) = g"): terms linear in fields that live on
+                    # exactly the equation's bases are copied in coefficient space -- no transforms (reference: the F expression of
+                    # such an equation is the field itself, core/problems.py:84-100)
+                    for coef, facs in terms:
+                        ok = len(facs) == 1 and not any(facs[0][2]) and all(
+                            (fb is None and eb is None) or (fb is not None and eb is not None and fb == eb)
+                            for fb, eb in zip(facs[0][0].bases, eq['bases']))
+                        if not ok:
+                            raise NotImplementedError("Right-hand sides of lower-dimensional equations must be linear in fields on the equation's bases.")
+                        self.linear_copies.setdefault((ie, comp), []).append((float(coef), facs[0][0], facs[0][1]))
+                    continue
                 tl = []
                 for coef, facs in terms:
                     idxs = []
@@ -188,11 +201,13 @@ class RHSPlan:
                             self.input_keys.append((f, c, dv))
                         idxs.append(inputs[key])
                     tl.append((coef, idxs))
-                if any(b is None for b in eq['bases']):
-                    raise NotImplementedError("Field-dependent RHS of a lower-dimensional equation is not supported yet.")
                 outputs.append((ie, comp, tl))
         self.outputs = outputs
         self.n_in, self.n_out = len(self.input_keys), len(outputs)
+        self.copy_dest = {}
+        for (ie, comp) in self.linear_copies:
+            tsh, shp = arena.shapes[ie]
+            self.copy_dest[(ie, comp)] = (arena.offsets[ie] + comp * int(np.prod(shp)), shp)
         if self.n_out == 0:
             return
         # ---- bases / shapes (all inputs share the variable bases up to Jacobi parameters)
@@ -304,6 +319,17 @@ class RHSPlan:
         from .transforms import cached_plan, _dptr, _stream
         from .lib import get_lib
         from .solvers import Timed
+        for key, terms in self.linear_copies.items():
+            off, shp = self.copy_dest[key]
+            dst = eq_arena_tensor[off:off + int(np.prod(shp))].view(shp)
+            for i, (coef, f, c) in enumerate(terms):
+                if f.layout != 'c':
+                    f.change_layout('c')
+                src = f.device_data()[self._comp_index(f, c)].reshape(shp)
+                if i == 0:
+                    torch.mul(src, coef, out=dst)
+                else:
+                    dst.add_(src, alpha=coef)
         if self.n_out == 0:
             return
         dim = self.dist.dim

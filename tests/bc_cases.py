@@ -1,0 +1,58 @@
+"""Boundary conditions with data -- lower-dimensional equations whose right-hand side is a field (reference: such an F is carried
+in coefficient space like any other, core/problems.py:84-100).  The problem definition is shared by the fixture generator
+(tests/golden/make_golden.py gen_bc_data, run with the unmodified reference) and the tests (run with dedalus_b200)."""
+import numpy as np
+
+
+def rb2d_bc_data(d3mod, Nx=16, Nz=16, steps=5, tstep=0.02):
+    """2-D Rayleigh-Benard as in examples/ivp_2d_rayleigh_benard/rayleigh_benard.py:44-82 with a non-uniform bottom temperature
+    b(z=0) = g(x) and a moving lid u(z=Lz) = (U(x), 0); shared by the generator (reference) and the test (dedalus_b200)."""
+    d3 = d3mod
+    Lx, Lz = 4, 1
+    Rayleigh, Prandtl = 2e5, 1
+    coords = d3.CartesianCoordinates('x', 'z')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    xbasis = d3.RealFourier(coords['x'], size=Nx, bounds=(0, Lx), dealias=3/2)
+    zbasis = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, Lz), dealias=3/2)
+    p = dist.Field(name='p', bases=(xbasis, zbasis)); b = dist.Field(name='b', bases=(xbasis, zbasis))
+    u = dist.VectorField(coords, name='u', bases=(xbasis, zbasis))
+    tau_p = dist.Field(name='tau_p')
+    tau_b1 = dist.Field(name='tau_b1', bases=xbasis); tau_b2 = dist.Field(name='tau_b2', bases=xbasis)
+    tau_u1 = dist.VectorField(coords, name='tau_u1', bases=xbasis); tau_u2 = dist.VectorField(coords, name='tau_u2', bases=xbasis)
+    kappa = (Rayleigh * Prandtl)**(-1/2); nu = (Rayleigh / Prandtl)**(-1/2)
+    x, z = dist.local_grids(xbasis, zbasis)
+    ex, ez = coords.unit_vector_fields(dist)
+    lift_basis = zbasis.derivative_basis(1)
+    lift = lambda A: d3.Lift(A, lift_basis, -1)
+    grad_u = d3.grad(u) + ez*lift(tau_u1)
+    grad_b = d3.grad(b) + ez*lift(tau_b1)
+    g = dist.Field(name='g', bases=xbasis)
+    g['g'] = Lz + 0.2 * np.sin(2 * np.pi * x / Lx) + 0.1 * np.cos(6 * np.pi * x / Lx)
+    lid = dist.VectorField(coords, name='lid', bases=xbasis)
+    lid['g'][0] = 0.05 * np.cos(2 * np.pi * x / Lx)
+    problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
+    problem.add_equation("trace(grad_u) + tau_p = 0")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*ez + lift(tau_u2) = - u@grad(u)")
+    problem.add_equation("b(z=0) = g")
+    problem.add_equation("u(z=0) = 0")
+    problem.add_equation("b(z=Lz) = 0")
+    problem.add_equation("u(z=Lz) = 2*lid")
+    problem.add_equation("integ(p) = 0")
+    solver = problem.build_solver(d3.RK222)
+    b.fill_random('g', seed=42, distribution='normal', scale=1e-3)
+    b['g'] *= z * (Lz - z)
+    b['g'] += Lz - z
+    for _ in range(steps):
+        solver.step(tstep)
+    return dict(p=p, b=b, u=u)
+
+
+
+
+def check_bc_data(d3, g):
+    res = rb2d_bc_data(d3)
+    for name, f in res.items():
+        ref = g[name]
+        got = f['c']
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-11 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())

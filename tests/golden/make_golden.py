@@ -784,3 +784,21 @@ def gen_shell_tasks():
 
 if __name__ == "__main__" and "shell_tasks" in sys.argv[1:]:
     gen_shell_tasks()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Boundary conditions with data: lower-dimensional equations whose right-hand side is a field
+# ----------------------------------------------------------------------------------------------------------
+sys.path.insert(0, str(HERE.parent))
+from bc_cases import rb2d_bc_data
+
+
+def gen_bc_data():
+    res = rb2d_bc_data(d3)
+    out = {k: v['c'].copy() for k, v in res.items()}
+    np.savez_compressed(HERE / "bc_data.npz", **out)
+    print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
+
+
+if __name__ == "__main__" and "bc_data" in sys.argv[1:]:
+    gen_bc_data()

@@ -12,3 +12,8 @@ def test_task_expressions_match_reference(golden):
 
 def test_flow_property_reductions_of_expressions(golden):
     X.check_flow_property_reductions(golden("expressions.npz"))
+
+
+def test_boundary_conditions_with_data_match_reference(golden):
+    import bc_cases, dedalus_b200 as d3
+    bc_cases.check_bc_data(d3, golden("bc_data.npz"))
