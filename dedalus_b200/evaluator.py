@@ -193,8 +193,9 @@ class RHSPlan:
                 for coef, facs in terms:
                     idxs = []
                     for (f, c, dv) in facs:
-                        if any(b is None for b in f.bases):
-                            raise NotImplementedError("RHS factors must have bases along every axis (no broadcasting on the hot path yet).")
+                        if any(b is None for b in f.bases) and (any(dv) or dist.size > 1):
+                            raise NotImplementedError("RHS factors without bases along some axis (background profiles, forcings) are broadcast "
+                                                      "on the grid on one GPU and cannot be differentiated: precompute the derivative field.")
                         key = (id(f), c, dv)
                         if key not in inputs:
                             inputs[key] = len(self.input_keys)
@@ -287,10 +288,17 @@ class RHSPlan:
         levels = [dict() for _ in range(dim)]
         self.leaf_of_input = []
         self.grid_leaves = []        # (input slot, field, comp): grid-function results enter the products without a coefficient round trip
+        self.broadcast_leaves = []   # (input slot, field, comp): factors without bases along some axis
         for slot, (f, c, dv) in enumerate(self.input_keys):
             if getattr(f, '_grid_leaf', False) and not any(dv):
                 self.leaf_of_input.append(('gridleaf', id(f), c))
                 self.grid_leaves.append((slot, f, c))
+                continue
+            if any(b is None for b in f.bases):
+                # a factor that is constant along some axis (a background profile b0(z), a forcing f(x)): its own low-dimensional
+                # transform, then broadcast into the product's input slot (reference: numpy broadcasting in MultiplyFields.operate)
+                self.leaf_of_input.append(('broadcast', id(f), c))
+                self.broadcast_leaves.append((slot, f, c))
                 continue
             parent = None
             for lvl, ax in enumerate(self.axes_order):
@@ -340,6 +348,12 @@ class RHSPlan:
             if f.layout != 'g' or tuple(f.scales) != tuple(self.dealias):
                 raise RuntimeError("grid-function result is not on the dealiased grid")
             self.grid_in[slot].copy_(f.device_data()[self._comp_index(f, c)])
+        if self.broadcast_leaves:
+            grids = {}
+            for slot, f, c in self.broadcast_leaves:
+                if id(f) not in grids:
+                    grids[id(f)] = f.copy_device_to_grid()
+                self.grid_in[slot].copy_(grids[id(f)][self._comp_index(f, c)].expand(self.gshape))
         in_tree = {id(nd['field']): nd['field'] for nd in self.levels[0].values()}
         for f in in_tree.values():
             if f.layout != 'c':

@@ -17,3 +17,8 @@ def test_flow_property_reductions_of_expressions(golden):
 def test_boundary_conditions_with_data_match_reference(golden):
     import bc_cases, dedalus_b200 as d3
     bc_cases.check_bc_data(d3, golden("bc_data.npz"))
+
+
+def test_right_hand_side_factors_without_a_basis_along_some_axis(golden):
+    import bc_cases, dedalus_b200 as d3
+    bc_cases.check_background(d3, golden("bc_data.npz"))
