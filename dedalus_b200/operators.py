@@ -518,6 +518,82 @@ def _const_values(field):
     return data.reshape(field.ncomp)
 
 
+def _product_selector(e, ncc, arg, ncc_left, vals):
+    """Component matrix of  ncc * arg / ncc @ arg / arg * ncc / arg @ ncc  for constant tensor components `vals` of the coefficient."""
+    nn, na = ncc.ncomp, arg.ncomp
+    if isinstance(e, Multiply):
+        col = sparse.csr_matrix(vals.reshape(nn, 1))
+        K = sparse.kron(col, sparse.identity(na)) if ncc_left else sparse.kron(sparse.identity(na), col)
+    elif ncc_left:       # ncc_(..., i) arg_(i, ...)
+        d = ncc.tensorsig[-1].dim
+        K = sparse.kron(sparse.csr_matrix(vals.reshape(nn // d, d)), sparse.identity(na // d))
+    else:                # arg_(..., i) ncc_(i, ...)
+        d = ncc.tensorsig[0].dim
+        K = sparse.kron(sparse.identity(na // d), sparse.csr_matrix(vals.reshape(d, nn // d).T))
+    return sparse.csr_matrix(K)
+
+
+def _ncc_product(e, ncc, arg, ncc_left, sub, coupled_axis):
+    """LHS product with a coefficient that varies along the coupled (Jacobi) axis only -- background profiles N^2(z), dzB(z).
+    Reference: Jacobi.ncc_matrix via Clenshaw on the N x N Jacobi matrix J of the operand's basis (core/basis.py:560-628,
+    tools/clenshaw.py:24-41), padded to Nmat = 3 ceil(N / 2) and truncated to N x N: f(J) = V diag(f(z_q)) V^T with the Gauss nodes
+    z_q of that basis, i.e. the Nmat-point Gauss quadrature of <P_i, f P_j>, i, j < N; the product stays in the operand's basis
+    (basis.py:546-557)."""
+    from . import jacobi
+    from .basis import Jacobi
+    nb = ncc.bases[coupled_axis]
+    if not isinstance(nb, Jacobi) or any(b is not None for ax, b in enumerate(ncc.bases) if ax != coupled_axis):
+        raise NotImplementedError("Non-constant LHS coefficients may only vary along the coupled (last, Jacobi) axis.")
+    coeffs = np.asarray(ncc['c']).reshape(max(ncc.ncomp, 1), -1)                     # (components, Nz) in the coefficient's own basis
+    active = [c for c in range(coeffs.shape[0]) if np.abs(coeffs[c]).max() > 0]
+    cache = {}
+
+    def matrix(c, tb):
+        key = (c, tb)
+        if key not in cache:
+            if tb is None:                                                          # operand constant along z: f itself, in f's basis
+                cache[key] = (sparse.csr_matrix(coeffs[c][:, None]), nb)
+            else:
+                if not (isinstance(tb, Jacobi) and tb.grid_params == nb.grid_params):
+                    raise NotImplementedError("coefficient and operand live on different axes / grids")
+                N = tb.size
+                Nmat = 3 * ((N + 1) // 2)                                            # the reference's padded size (basis.py:620-628)
+                z, w = jacobi.gauss_grid(Nmat, tb.a, tb.b)
+                P = jacobi.polynomials(N, tb.a, tb.b, z)                             # (N modes, Nmat nodes), orthonormal
+                f = coeffs[c] @ jacobi.polynomials(nb.size, nb.a, nb.b, z)
+                M = (P * (w * f)[None, :]) @ P.T
+                M[np.abs(M) < 1e-14 * np.abs(M).max()] = 0
+                cache[key] = (sparse.csr_matrix(M), tb)
+        return cache[key]
+
+    out = {}
+    for k, terms in sub.items():
+        new = []
+        for c in active:
+            unit = np.zeros(coeffs.shape[0]); unit[c] = 1.0
+            K = _product_selector(e, ncc, arg, ncc_left, unit)
+            for t in terms:
+                u = t.copy()
+                u.comp = sparse.csr_matrix(K @ u.comp)
+                if u.comp.nnz == 0:
+                    continue
+                M, ob = matrix(c, u.bases[coupled_axis])
+                u.ops[coupled_axis] = M @ u.ops[coupled_axis]
+                bases = list(u.bases); bases[coupled_axis] = ob
+                u.bases = tuple(bases)
+                new.append(u)
+        # up to the expression's bases where that is a conversion upwards; terms already above them stay (the parent sum converts)
+        conv = []
+        for u in new:
+            tb, eb = u.bases[coupled_axis], e.bases[coupled_axis]
+            if isinstance(tb, Jacobi) and isinstance(eb, Jacobi) and (eb.a < tb.a or eb.b < tb.b):
+                conv.append(u)
+            else:
+                conv.extend(_convert_terms([u], e.bases, coupled_axis))
+        out[k] = conv
+    return out
+
+
 def linear_map(expr, variables, coupled_axis):
     """Return {var: [LinTerm]} for an expression that is linear in `variables` (all terms in expr.bases)."""
     varids = {id(v): v for v in variables}
@@ -554,7 +630,9 @@ def linear_map(expr, variables, coupled_axis):
             ncc, arg, ncc_left = (A, B, True) if b_var else (B, A, False)
             from .field import Field as _F
             if not isinstance(ncc, _F):
-                raise NotImplementedError("Only plain constant fields are supported as LHS coefficients.")
+                raise NotImplementedError("Only plain fields are supported as LHS coefficients.")
+            if any(b is not None for b in ncc.bases):
+                return _ncc_product(e, ncc, arg, ncc_left, rec(arg), coupled_axis)
             vals = _const_values(ncc)
             sub = rec(arg)
             nn, na = ncc.ncomp, arg.ncomp
