@@ -664,6 +664,121 @@ _TORCH_NAMES = {'absolute': 'abs', 'arcsin': 'asin', 'arccos': 'acos', 'arctan':
                 'arctanh': 'atanh', 'conjugate': 'conj'}
 
 
+class Stager:
+    """Rewrites an expression into stages + a polynomial remainder that one RHSPlan can evaluate:
+      * a grid function np.f(arg) (reference UnaryGridFunction, operators.py:505-640) becomes "polynomial part of arg on the
+        dealiased grid -> f pointwise -> temporary field on the grid", which enters later products without a coefficient round trip;
+      * a differential operator applied to a product (div(u*b), the reference evaluates the product, transforms it to coefficient
+        space and differentiates there) becomes "product -> temporary field in coefficient space".
+    Stages run in order before the remainder; every stage is an RHSPlan of its own (same transform / product kernels)."""
+
+    _DIFF = (ops.Differentiate, ops.Gradient, ops.Divergence, ops.Laplacian)
+    _PRODUCTS = (ops.Multiply, ops.DotProduct, ops.Power)
+
+    def __init__(self):
+        self.stages = []           # ('grid', plan, torch function, field) | ('coeff', plan, arena tensor, view, field)
+
+    @staticmethod
+    def plan(e):
+        plan = RHSPlan(_ExpressionHost(e))
+        if plan.n_out == 0 and not plan.static_entries:
+            raise NotImplementedError("expression evaluates to zero")
+        return plan
+
+    @classmethod
+    def _has_product(cls, e):
+        if isinstance(e, cls._PRODUCTS) or getattr(e, '_grid_leaf', False):
+            return True
+        return any(cls._has_product(a) for a in getattr(e, 'args', []) if isinstance(a, Operand))
+
+    def rewrite(self, e):
+        import copy, torch
+        if isinstance(e, ops.UnaryGridFunction):
+            arg = self.rewrite(e.args[0])
+            plan = self.plan(arg)
+            if plan.static_entries:
+                raise NotImplementedError("constants inside grid functions")
+            name = getattr(e.func, '__name__', str(e.func))
+            fn = getattr(torch, _TORCH_NAMES.get(name, name), None)
+            if fn is None:
+                raise NotImplementedError(f"grid function {name!r} has no device implementation")
+            if any(b is None for b in e.bases):
+                raise NotImplementedError("grid functions of lower-dimensional operands")
+            tmp = Field(e.dist, bases=tuple(dict.fromkeys(e.bases)), tensorsig=e.tensorsig, dtype=e.dtype)
+            e.dist._fields.pop()
+            tmp._grid_leaf = True
+            self.stages.append(('grid', plan, fn, tmp))
+            return tmp
+        if isinstance(e, Field) or not isinstance(e, Operand):
+            return e
+        new = copy.copy(e)
+        new.args = [self.rewrite(a) for a in e.args]
+        if isinstance(e, self._DIFF) and self._has_product(new.args[0]):
+            inner = new.args[0]
+            if any(b is None for b in inner.bases):
+                raise NotImplementedError("derivatives of lower-dimensional products")
+            plan = self.plan(inner)
+            host = plan.solver
+            out_t = torch.zeros(host.eq_arena.size, dtype=torch.float64, device=host.device)
+            plan.set_static(out_t)
+            tmp = Field(inner.dist, bases=tuple(dict.fromkeys(inner.bases)), tensorsig=inner.tensorsig, dtype=inner.dtype)
+            inner.dist._fields.pop()
+            tsh, shp = host.eq_arena.shapes[0]
+            self.stages.append(('coeff', plan, out_t, out_t.view(tuple(tsh) + tuple(shp)), tmp))
+            new.args = [tmp]
+        return new
+
+    @staticmethod
+    def run(stages):
+        for st in stages:
+            if st[0] == 'grid':
+                _, plan, fn, tmp = st
+                vals = fn(plan.evaluate(None, grid_only=True))
+                tmp.set_device_data(vals.reshape(tuple(cs.dim for cs in tmp.tensorsig) + tuple(plan.gshape)), 'g', scales=plan.dealias)
+            else:
+                _, plan, out_t, view, tmp = st
+                plan.evaluate(out_t)
+                tmp.set_device_data(view, 'c')
+
+
+class StagedRHSPlan:
+    """Right-hand sides that are not polynomial in derivatives of fields -- grid functions (np.tanh(b)) and derivatives of products
+    (div(u*b)): the Stager's stages, then the ordinary RHSPlan over the rewritten equations.  Same interface as RHSPlan."""
+
+    def __init__(self, solver):
+        stager = Stager()
+        eqs = []
+        for eq in solver.problem.equations:
+            new = dict(eq)
+            if isinstance(eq['RHS'], Operand):
+                new['RHS'] = stager.rewrite(eq['RHS'])
+            eqs.append(new)
+        self.stages = stager.stages
+        self.plan = RHSPlan(_ProfProxy(solver, eqs))
+
+    def set_static(self, arena_tensor):
+        self.plan.set_static(arena_tensor)
+
+    def evaluate(self, eq_arena_tensor):
+        Stager.run(self.stages)
+        self.plan.evaluate(eq_arena_tensor)
+
+    def __getattr__(self, name):                      # bench / tests look at the main plan's attributes (_blocked_bwd_ok, ...)
+        return getattr(self.plan, name)
+
+
+class _ProfProxy:
+    """The solver as the main RHSPlan sees it, with the rewritten equations."""
+
+    def __init__(self, solver, equations):
+        from types import SimpleNamespace
+        self._solver = solver
+        self.problem = SimpleNamespace(dist=solver.problem.dist, equations=equations)
+
+    def __getattr__(self, name):
+        return getattr(self._solver, name)
+
+
 class ExpressionProgram:
     """Stand-alone evaluation of an operator expression of Cartesian fields into a new Field (reference Future.evaluate,
     core/future.py:149-206, used by output handlers and flow properties -- not part of the per-step path).
@@ -674,8 +789,6 @@ class ExpressionProgram:
     kernels as the solver's right-hand sides."""
 
     def __init__(self, expr):
-        import copy
-        self.stages = []           # (plan, torch function, temporary field)
         # outer reductions -- integ / ave / interpolation, possibly nested and scaled (Nusselt numbers, profiles, mid-plane values):
         # contractions of the coefficient data with the basis' row vectors (reference IntegrateJacobi / InterpolateRealFourier ...,
         # core/basis.py:721-789, 1037-1290), applied to the result of the remaining expression
@@ -691,29 +804,9 @@ class ExpressionProgram:
                 break
         self.reductions.reverse()
 
-        def sub(e):
-            if isinstance(e, ops.UnaryGridFunction):
-                arg = sub(e.args[0])
-                plan = self._plan(arg)
-                if plan.static_entries:
-                    raise NotImplementedError("constants inside grid functions")
-                name = getattr(e.func, '__name__', str(e.func))
-                import torch
-                fn = getattr(torch, _TORCH_NAMES.get(name, name), None)
-                if fn is None:
-                    raise NotImplementedError(f"grid function {name!r} has no device implementation")
-                if any(b is None for b in e.bases):
-                    raise NotImplementedError("grid functions of lower-dimensional operands")
-                tmp = Field(e.dist, bases=tuple(dict.fromkeys(e.bases)), tensorsig=e.tensorsig, dtype=e.dtype)
-                e.dist._fields.pop()
-                tmp._grid_leaf = True
-                self.stages.append((plan, fn, tmp))
-                return tmp
-            if isinstance(e, Field) or not isinstance(e, Operand):
-                return e
-            new = copy.copy(e)
-            new.args = [sub(a) for a in e.args]
-            return new
+        stager = Stager()
+        self.stages = stager.stages
+        sub = stager.rewrite
         final = sub(expr)
         self.result_field = final if isinstance(final, Field) else None
         if self.result_field is None:
@@ -729,16 +822,10 @@ class ExpressionProgram:
 
     @staticmethod
     def _plan(e):
-        plan = RHSPlan(_ExpressionHost(e))
-        if plan.n_out == 0 and not plan.static_entries:
-            raise NotImplementedError("expression evaluates to zero")
-        return plan
+        return Stager.plan(e)
 
     def run(self):
-        for plan, fn, tmp in self.stages:
-            g = plan.evaluate(None, grid_only=True)
-            vals = fn(g)
-            tmp.set_device_data(vals.reshape(tuple(cs.dim for cs in tmp.tensorsig) + tuple(plan.gshape)), 'g', scales=plan.dealias)
+        Stager.run(self.stages)
         if self.result_field is not None:
             out = self.result_field
         else:

@@ -27,6 +27,11 @@ class IVP:
             if not k.startswith('_'):
                 self.namespace[k] = getattr(pkg, k)
         self.namespace['dt'] = ops.dt
+        # numpy ufuncs by name, as the reference's parsing namespace has them (core/operators.py:558-560: 'sin', 'tanh', 'abs', ...)
+        for name in ('absolute', 'sign', 'exp', 'exp2', 'log', 'log2', 'log10', 'sqrt', 'square', 'sin', 'cos', 'tan', 'arcsin',
+                     'arccos', 'arctan', 'sinh', 'cosh', 'tanh', 'arcsinh', 'arccosh', 'arctanh'):
+            self.namespace[name] = getattr(np, name)
+        self.namespace['abs'] = np.absolute
         self.namespace[self.time.name] = self.time
         for v in self.variables:
             if v.name:

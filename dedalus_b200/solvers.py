@@ -385,8 +385,12 @@ class InitialValueSolver:
             from .complex_path import ComplexRHSPlan
             self.rhs_plan = ComplexRHSPlan(self)
         else:
-            from .evaluator import RHSPlan
-            self.rhs_plan = RHSPlan(self)
+            from .evaluator import RHSPlan, StagedRHSPlan, NonPolynomialError
+            try:
+                self.rhs_plan = RHSPlan(self)
+            except NonPolynomialError:
+                # grid functions or derivatives of products on the right-hand side: evaluated in stages (evaluator.Stager)
+                self.rhs_plan = StagedRHSPlan(self)
         self.rhs_plan.set_static(self.eq_t)
         self.bset = None
         self._device_ready = True
