@@ -50,8 +50,6 @@ def lower(expr):
             return out
         if isinstance(e, ops.ScalarMul):
             return {c: [(coef * e.c, f) for coef, f in terms] for c, terms in rec(e.args[0]).items()}
-        if isinstance(e, (ops.Convert, ops.TransposeComponents, ops.Trace)) and False:
-            pass
         if isinstance(e, ops.Convert):
             return rec(e.args[0])
         if isinstance(e, ops.Multiply):
