@@ -142,6 +142,76 @@ class TransposePlanner:
         lib.call("db_transpose_unpack_rev", recv.data_ptr(), out.data_ptr(), B, n1 // P, n2loc * P, n3, P, current_stream())
 
 
+class B200Transpose:
+    """The reference's transpose plugin contract (core/transposes.pyx:22-246 FFTWTranspose, selected as `TransposePlanner` in
+    core/distributor.py:22-30):
+
+        plan = B200Transpose(global_shape, chunk_shape, dtype, axis, comm_sub)
+        plan.localize_columns(RL, CL)      # row-local (distributed along `axis`) -> column-local (distributed along axis + 1)
+        plan.localize_rows(CL, RL)         # and back
+
+    over the pack -> NCCL all-to-all -> unpack kernels of this file.  `comm_sub` is a torch.distributed process group (None: the
+    default group); arrays are numpy arrays (staged through the device) or device tensors; the block distribution is the
+    reference's (whole chunks per rank, transposes.pyx:73-93) and must be even here."""
+
+    def __init__(self, global_shape, chunk_shape, dtype, axis, comm_sub=None):
+        import torch.distributed as td
+        from types import SimpleNamespace
+        self.global_shape = tuple(int(v) for v in global_shape)
+        self.axis = axis
+        self.datasize = {np.float64: 1, np.complex128: 2}[np.dtype(dtype).type]
+        self.dtype = np.dtype(dtype)
+        self.group = comm_sub
+        self.P = td.get_world_size(comm_sub) if td.is_initialized() else 1
+        self.rank = td.get_rank(comm_sub) if td.is_initialized() else 0
+        if td.is_initialized() and self.P != td.get_world_size():
+            raise NotImplementedError("sub-communicators (meshes with more than one distributed axis) are not supported: 1-D meshes only")
+        gs = self.global_shape
+        self.N0 = int(np.prod(gs[:axis], dtype=np.int64)); self.N1 = gs[axis]; self.N2 = gs[axis + 1]
+        self.N3 = int(np.prod(gs[axis + 2:], dtype=np.int64)) * self.datasize
+        C1, C2 = int(chunk_shape[axis]), int(chunk_shape[axis + 1])
+        for N, Cc in ((self.N1, C1), (self.N2, C2)):
+            if N % Cc or (N // Cc) % self.P:
+                raise ValueError(f"B200Transpose needs an even block distribution: {N} entries in chunks of {Cc} over {self.P} ranks")
+        self.RL_reduced_shape = (self.N0, self.N1 // self.P, self.N2, self.N3)
+        self.CL_reduced_shape = (self.N0, self.N1, self.N2 // self.P, self.N3)
+        self._planner = TransposePlanner(SimpleNamespace(size=self.P)) if self.P > 1 else None
+
+    def _dev(self, a, shape):
+        import torch
+        from .lib import compute_device
+        if torch.is_tensor(a):
+            t = a
+            if t.is_complex():
+                t = torch.view_as_real(t)
+            return t.reshape(shape), None
+        host = np.ascontiguousarray(a).view(np.float64).reshape(shape)
+        return torch.from_numpy(host).to(compute_device()), a
+
+    @staticmethod
+    def _store(dev, host):
+        if host is not None:
+            np.copyto(host, dev.cpu().numpy().view(host.dtype).reshape(host.shape))
+
+    def localize_columns(self, RL, CL):
+        rl, _ = self._dev(RL, self.RL_reduced_shape)
+        cl, host = self._dev(CL, self.CL_reduced_shape)
+        if self.P == 1:
+            cl.copy_(rl)
+        else:
+            self._planner.localize_columns(rl.contiguous(), cl)
+        self._store(cl, host)
+
+    def localize_rows(self, CL, RL):
+        cl, _ = self._dev(CL, self.CL_reduced_shape)
+        rl, host = self._dev(RL, self.RL_reduced_shape)
+        if self.P == 1:
+            rl.copy_(cl)
+        else:
+            self._planner.localize_rows(cl.contiguous(), rl)
+        self._store(rl, host)
+
+
 def get_planner(dist):
     """One planner per Distributor, stored ON the distributor (a cache keyed by id(dist) could hand a stale planner to a new
     distributor that reuses the id of a garbage-collected one)."""

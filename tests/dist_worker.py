@@ -45,6 +45,35 @@ def main():
             print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
         dist.destroy_process_group()
         return
+    if which == "plugin:transpose":
+        # the reference's Transpose plugin contract (core/transposes.pyx:22-246) on this mesh: the same global array on every rank
+        # (seeded), row-local block in, column-local block out and back
+        from dedalus_b200.transposes import B200Transpose
+        ok = True
+        for dtype, shape, axis in ((np.float64, (3, 8, 12, 5), 1), (np.float64, (16, 6), 0), (np.complex128, (2, 4, 8, 3), 1)):
+            rng = np.random.default_rng(5)
+            G = rng.standard_normal(shape).astype(dtype)
+            if dtype is np.complex128:
+                G = G + 1j * rng.standard_normal(shape)
+            chunk = [1] * len(shape); chunk[axis] = 2
+            plan = B200Transpose(shape, chunk, dtype, axis, None)
+            n1, n2 = shape[axis], shape[axis + 1]
+            rs = slice(rank * n1 // world, (rank + 1) * n1 // world)
+            cs = slice(rank * n2 // world, (rank + 1) * n2 // world)
+            idx_r = [slice(None)] * len(shape); idx_r[axis] = rs
+            idx_c = [slice(None)] * len(shape); idx_c[axis + 1] = cs
+            RL = np.ascontiguousarray(G[tuple(idx_r)]); CL = np.zeros_like(np.ascontiguousarray(G[tuple(idx_c)]))
+            plan.localize_columns(RL, CL)
+            ok = ok and bool(np.array_equal(CL, G[tuple(idx_c)]))
+            back = np.zeros_like(RL)
+            plan.localize_rows(CL, back)
+            ok = ok and bool(np.array_equal(back, RL))
+        flag = torch.tensor([1 if ok else 0], device='cuda' if backend == "nccl" else 'cpu')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
+        dist.destroy_process_group()
+        return
     if which.startswith("tasks:"):
         # stand-alone output expressions on a distributed domain: every rank holds its block of the reference's grid / coefficient data
         kind = which.split(":")[1]
