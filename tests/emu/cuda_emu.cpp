@@ -49,14 +49,16 @@ void emu_syncthreads() {
     while (bar_generation == gen) emu_yield();
 }
 
-static double shfl_slots[4096];
+static double shfl_slots[2][4096];
+static unsigned char shfl_parity[4096];
 double emu_shfl_exchange(double v, int src_lane) {
+    // two slot sets used alternately: a lane overwrites set p again only in its call after next, i.e. after the yield of the
+    // call in between, by which every lane of the warp has finished reading set p -- one yield per exchange is enough
     const unsigned tid = emu_cur.tid.x;            // 1-D blocks only
-    shfl_slots[tid] = v;
+    const unsigned p = shfl_parity[tid] ^= 1;
+    shfl_slots[p][tid] = v;
     emu_yield();                                   // every lane of the warp has published (lanes run in lockstep)
-    const double r = shfl_slots[(tid & ~31u) + (unsigned)src_lane];
-    emu_yield();                                   // every lane has read before any slot is overwritten
-    return r;
+    return shfl_slots[p][(tid & ~31u) + (unsigned)src_lane];
 }
 
 void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
@@ -77,6 +79,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
     for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned bx = 0; bx < grid.x; ++bx) {
         std::memset(shared.data(), 0xA5, shared.size());   // poison shared memory
+        std::memset(shfl_parity, 0, sizeof(shfl_parity));
         size_t i = 0;
         for (unsigned tz = 0; tz < block.z; ++tz)
         for (unsigned ty = 0; ty < block.y; ++ty)
