@@ -96,9 +96,13 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
         }
         size_t remaining = nthreads;
         bar_arrived = 0; bar_live = nthreads;
+        // DB_EMU_ORDER=reverse: the threads of a block take their turns in descending order.  Code that is correct only because a
+        // lower-numbered thread happens to run first (a missing __syncthreads / __syncwarp) passes in one order and fails in the other.
+        static const bool reverse_order = [] { const char* e = getenv("DB_EMU_ORDER"); return e && e[0] == 'r'; }();
         while (remaining) {
             size_t finished_this_round = 0, waiting = 0;
-            for (auto& f : fibers) {
+            for (size_t fi = 0; fi < fibers.size(); ++fi) {
+                Fiber& f = fibers[reverse_order ? fibers.size() - 1 - fi : fi];
                 if (f.done) continue;
                 running = &f;
                 emu_cur = f.st;
