@@ -75,9 +75,13 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
     std::vector<Fiber> fibers(nthreads);
     for (size_t i = 0; i < nthreads; ++i) fibers[i].stack = get_stack(i);
     cur_body = &body;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
+    static const bool reverse_blocks = [] { const char* e = getenv("DB_EMU_ORDER"); return e && e[0] == 'r'; }();
+    for (unsigned bzi = 0; bzi < grid.z; ++bzi)
+    for (unsigned byi = 0; byi < grid.y; ++byi)
+    for (unsigned bxi = 0; bxi < grid.x; ++bxi) {
+        // blocks of a grid run one after the other here; on the GPU their order is arbitrary: reversed with DB_EMU_ORDER=reverse
+        const unsigned bz = reverse_blocks ? grid.z - 1 - bzi : bzi, by = reverse_blocks ? grid.y - 1 - byi : byi,
+                       bx = reverse_blocks ? grid.x - 1 - bxi : bxi;
         std::memset(shared.data(), 0xA5, shared.size());   // poison shared memory
         std::memset(shfl_parity, 0, sizeof(shfl_parity));
         size_t i = 0;
