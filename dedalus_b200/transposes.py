@@ -38,7 +38,10 @@ class PeerExchange:
     @staticmethod
     def create(dist):
         import os
-        if os.environ.get("DB_PEER_TRANSPOSE", "1") == "0" or dist.size > 8:
+        mode = os.environ.get("DB_PEER_TRANSPOSE", "1")
+        # measured on 2 and 4 GPUs (profiles/README.md); on 8 the NCCL all-to-all path is the measured one, so the peer stores are
+        # opt-in there (DB_PEER_TRANSPOSE=force) until they have run on that many GPUs
+        if mode == "0" or dist.size > 8 or (dist.size > 4 and mode != "force"):
             return None
         try:
             import torch.distributed as td
