@@ -209,7 +209,11 @@ class CudaBackend:
                 # missing, or built from other sources than the ones in the tree (a stale library would lack entry points or,
                 # worse, run old kernels): rebuild it if nvcc is here, else say so -- never continue with it
                 try:
-                    _build.build(force=not LIB_PATH.exists())
+                    import fcntl
+                    with open(str(LIB_PATH) + ".lock", "w") as lock:       # several ranks may get here at once: one builds, the others wait
+                        fcntl.flock(lock, fcntl.LOCK_EX)
+                        if not _build.lib_is_current():
+                            _build.build(force=not LIB_PATH.exists())
                 except Exception as exc:
                     raise DedalusB200Error(
                         f"{LIB_PATH} is missing or was not built from the current sources and could not be rebuilt ({exc}): "
