@@ -830,6 +830,13 @@ class ExpressionProgram:
             self.final.evaluate(self.out_t)
             self.out.set_device_data(self.out_view, 'c')
             out = self.out
+        # like the reference's evaluation, which moves the operands to the dealiased grid in place (core/future.py:149-206): the
+        # fields of the expression are left at their dealias scales (their coefficients are untouched)
+        plans = [st[1] for st in self.stages] + ([self.final] if self.result_field is None else [])
+        for plan in plans:
+            for f, c, dv in getattr(plan, 'input_keys', []):
+                if not getattr(f, '_grid_leaf', False) and f.layout == 'c':
+                    f.change_scales(f.dealias)
         return self._reduce(out) if self.reductions else out
 
     def _reduce(self, f):

@@ -220,3 +220,92 @@ class Field(Operand):
             loc = gdata[sl + (slice(None),)]
             self.data.real[...] = loc[..., 0]
             self.data.imag[...] = loc[..., 1]
+
+    # ---- global data, norms and spectral filters (reference core/field.py:624-630, 746-876, 945-986) --------------------------
+    def evaluate(self):
+        return self
+
+    def _full_slices(self):
+        return tuple(slice(None) for _ in self.tensorsig) + self.local_slices(self.layout, self.scales)
+
+    def set_global_data(self, global_data):
+        np.copyto(self.data, np.asarray(global_data)[self._full_slices()])
+
+    def load_from_global_grid_data(self, global_data, pre_slices=()):
+        self.preset_layout('g')
+        np.copyto(self.data, np.asarray(global_data)[tuple(pre_slices) + self._full_slices()])
+
+    def load_from_global_coeff_data(self, global_data, pre_slices=()):
+        self.preset_layout('c')
+        np.copyto(self.data, np.asarray(global_data)[tuple(pre_slices) + self._full_slices()])
+
+    def _host_allreduce(self, array, op):
+        """All-reduce of a host array over the ranks of the mesh (through the device for NCCL)."""
+        import torch, torch.distributed as td
+        dev = 'cuda' if td.get_backend() == 'nccl' else 'cpu'
+        t = torch.from_numpy(np.ascontiguousarray(array)).to(dev)
+        if t.is_complex():
+            t = torch.view_as_real(t).contiguous()
+        td.all_reduce(t, op=getattr(td.ReduceOp, op))
+        out = t.cpu().numpy()
+        return out.view(array.dtype).reshape(array.shape) if np.iscomplexobj(array) else out
+
+    def allgather_data(self, layout=None):
+        """The global data on every rank (reference field.py:782-800)."""
+        if layout is not None:
+            self.change_layout(layout)
+        if self.dist.size == 1:
+            return self.data.copy()
+        send = np.zeros(self.tshape + self.global_shape(self.layout, self.scales), dtype=self.dtype)
+        send[self._full_slices()] = self.data
+        return self._host_allreduce(send, 'SUM')
+
+    def gather_data(self, root=0, layout=None):
+        """The global data on rank `root`, None elsewhere (reference field.py:802-818)."""
+        data = self.allgather_data(layout)
+        return data if self.dist.rank == root else None
+
+    def allreduce_data_norm(self, layout=None, order=2):
+        if layout is not None:
+            self.change_layout(layout)
+        a = np.abs(self.data)
+        if order == np.inf:
+            norm = np.array([a.max() if a.size else 0.0])
+            return float(self._host_allreduce(norm, 'MAX')[0]) if self.dist.size > 1 else float(norm[0])
+        norm = np.array([np.sum(a ** order)])
+        if self.dist.size > 1:
+            norm = self._host_allreduce(norm, 'SUM')
+        return float(norm[0] ** (1 / order))
+
+    def allreduce_data_max(self, layout=None):
+        return self.allreduce_data_norm(layout=layout, order=np.inf)
+
+    def allreduce_L2_norm(self, normalize_volume=True):
+        """sqrt of the volume average (or integral) of |f|^2 (reference field.py:844-862), real fields up to rank 1."""
+        from . import operators as ops
+        if not self.is_real or len(self.tensorsig) > 1:
+            raise NotImplementedError("L2 norms of complex or rank-2 fields")
+        inner = (self * self) if not self.tensorsig else ops.DotProduct(self, self)
+        red = ops.Integrate(inner, average=bool(normalize_volume)).evaluate()
+        return float(red.allreduce_data_max(layout='g')) ** 0.5
+
+    def normalize(self, normalize_volume=True):
+        norm = self.allreduce_L2_norm(normalize_volume=normalize_volume)
+        self.data[...] = self.data / norm
+
+    def low_pass_filter(self, shape=None, scales=None):
+        """Zero the modes above the given relative scales: a round trip through a grid of that size (reference field.py:945-967)."""
+        original = self.scales
+        if shape is not None:
+            if scales is not None:
+                raise ValueError("Specify either shape or scales.")
+            scales = tuple(np.array(shape) / np.array(self.global_shape('g', self.dist.remedy_scales(1))))
+        self.change_scales(scales)
+        self.change_layout('g')
+        self.change_scales(original)
+
+    def high_pass_filter(self, shape=None, scales=None):
+        orig = np.array(self['c'])
+        self.low_pass_filter(shape=shape, scales=scales)
+        filt = np.array(self['c'])
+        self['c'] = orig - filt

@@ -64,3 +64,26 @@ def check_flow_property_reductions(g):
     assert np.isclose(flow.grid_average('Re'), ref.mean(), rtol=1e-10)
     flow.add_property(b * b, name='bb')
     assert np.isclose(flow.volume_integral('bb'), float(g['red_int_bb_g'].ravel()[0]), rtol=1e-10)
+
+
+def check_field_helpers(g):
+    """fill_random + low_pass_filter reproduce the reference's fields (the fixture's inputs were made that way); norms, high-pass
+    filter and global data access against the reference's values (core/field.py:782-986)."""
+    Nx, Nz = (int(v) for v in g['meta'])
+    coords = d3.CartesianCoordinates('x', 'z')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    xb = d3.RealFourier(coords['x'], size=Nx, bounds=(0, 4), dealias=3/2)
+    zb = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, 1), dealias=3/2)
+    u = dist.VectorField(coords, name='u', bases=(xb, zb)); b = dist.Field(name='b', bases=(xb, zb))
+    u.fill_random('g', seed=11, distribution='normal', scale=1.0); u.low_pass_filter(scales=0.75)
+    b.fill_random('g', seed=12, distribution='normal', scale=1.0); b.low_pass_filter(scales=0.75)
+    assert np.allclose(u['c'], g['u_c'], rtol=1e-12, atol=1e-14) and np.allclose(b['c'], g['b_c'], rtol=1e-12, atol=1e-14)
+    got = [b.allreduce_L2_norm(), b.allreduce_L2_norm(normalize_volume=False), u.allreduce_L2_norm(),
+           b.allreduce_data_norm('c', 2), b.allreduce_data_max('g')]
+    assert np.allclose(got, g['norms'], rtol=1e-11), (got, g['norms'])
+    hp = b.copy(); hp.high_pass_filter(shape=(16, 8))
+    assert np.allclose(hp['c'], g['b_highpass_c'], rtol=1e-12, atol=1e-14)
+    full = b.allgather_data('g')
+    c = dist.Field(bases=(xb, zb)); c.preset_scales(b.scales); c.load_from_global_grid_data(full)
+    assert np.allclose(c['c'], b['c'], rtol=1e-12, atol=1e-14)
+    assert b.evaluate() is b

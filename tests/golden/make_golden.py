@@ -672,6 +672,9 @@ def gen_expressions():
     u.fill_random('g', seed=11, distribution='normal', scale=1.0); u.low_pass_filter(scales=0.75)
     b.fill_random('g', seed=12, distribution='normal', scale=1.0); b.low_pass_filter(scales=0.75)
     out['u_c'] = u['c'].copy(); out['b_c'] = b['c'].copy(); out['meta'] = np.array([Nx, Nz])
+    out['norms'] = np.array([b.allreduce_L2_norm(), b.allreduce_L2_norm(normalize_volume=False), u.allreduce_L2_norm(),
+                             b.allreduce_data_norm('c', 2), b.allreduce_data_max('g')])
+    hp = b.copy(); hp.high_pass_filter(shape=(16, 8)); out['b_highpass_c'] = hp['c'].copy()
     nu = 0.37
     tasks = dict(vorticity=-d3.div(d3.skew(u)), Re=np.sqrt(u@u)/nu, ke=0.5*(u@u), sinb_b=np.sin(b)*b + b,
                  grad_mag=np.sqrt(d3.grad(b)@d3.grad(b)), absdiv=np.abs(d3.div(u)) * 2.0)

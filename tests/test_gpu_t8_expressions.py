@@ -32,3 +32,7 @@ def test_left_hand_side_coefficients_varying_along_the_coupled_axis(golden):
 def test_right_hand_sides_with_grid_functions_and_derivatives_of_products(golden):
     import bc_cases, dedalus_b200 as d3
     bc_cases.check_conservative(d3, golden("bc_data.npz"))
+
+
+def test_field_filters_norms_and_global_data(golden):
+    X.check_field_helpers(golden("expressions.npz"))
