@@ -33,9 +33,25 @@ class Basis:
             raise ValueError("Non-integer grid size: scale * size must be an integer.")
         return int(g)
 
-    def global_grid(self, scale=None):
+    def global_grid(self, dist_or_scale=None, scale=None):
+        """global_grid(scale): the 1-D grid; global_grid(dist, scale): the reference's form (core/basis.py:364-368), shaped for
+        broadcasting along this basis' axis of the distributor."""
+        dist = None
+        if dist_or_scale is not None and not isinstance(dist_or_scale, (int, float, np.integer, np.floating)):
+            dist = dist_or_scale
+        elif scale is None:
+            scale = dist_or_scale
         scale = self.dealias[0] if scale is None else scale
-        return self.COV.problem_coord(self._native_grid(scale))
+        grid = self.COV.problem_coord(self._native_grid(scale))
+        if dist is None:
+            return grid
+        shape = [1] * dist.dim
+        shape[dist.get_basis_axis(self)] = grid.size
+        return grid.reshape(shape)
+
+    def local_grid(self, dist, scale=None):
+        """The reference's basis.local_grid(dist, scale) (core/basis.py:374-380)."""
+        return dist.local_grid(self, scale)
 
     def clone_with(self, **kw):
         args = dict(self._ctor_args)

@@ -46,6 +46,9 @@ class Distributor:
         self.rank, self.size = rank, size if mesh else 1
         self.device = device
         self._fields = []
+        # the reference's scripts ask `dist.comm.rank == 0` / `dist.comm.size` (mpi4py communicator): the same two numbers here
+        from types import SimpleNamespace
+        self.comm = self.comm_cart = SimpleNamespace(rank=rank, size=size, Get_rank=lambda: rank, Get_size=lambda: size)
 
     # ---- coordinate bookkeeping --------------------------------------------------------------------
     def get_coord(self, name):

@@ -628,15 +628,16 @@ class _DirectSolve:
 
 class LinearBoundaryValueSolver(InitialValueSolver):
     """L.X = F on the device (reference LinearBoundaryValueSolver, core/solvers.py:286-375): `solve()` evaluates F, solves every
-    pencil system with the factorised L and scatters the solution into the problem variables.  Sphere problems only in this
-    build (the balanced-height problem of the stock shallow-water script); F may read any sphere field but not the unknowns."""
+    pencil system with the factorised L and scatters the solution into the problem variables.  Real Cartesian problems (the stock
+    Poisson script) and sphere problems (the balanced-height problem of the stock shallow-water script); F may read any field but
+    not the unknowns."""
 
     rhs_reads_state = False
 
     def __init__(self, problem, **kw):
         super().__init__(problem, _DirectSolve, **kw)
-        if not self.curvilinear or self.shell:
-            raise NotImplementedError("LBVPs are built for sphere (S2) problems in this build")
+        if self.shell or self.complex:
+            raise NotImplementedError("LBVPs are built for real Cartesian and sphere (S2) problems in this build")
 
     def step(self, dt):
         raise TypeError("boundary value solvers have no time step; call solve()")
@@ -645,9 +646,12 @@ class LinearBoundaryValueSolver(InitialValueSolver):
         if not self._device_ready:
             self._init_device()
         if self.bset is None or rebuild_matrices:
-            from .sphere import SphereSystems
-            self.bset = SphereSystems(self, 4, 1)         # slots: 0 F, 1 X, 2 / 3 probe products
-            self.total_modes = self.bset.total_modes
+            if self.curvilinear:
+                from .sphere import SphereSystems
+                self.bset = SphereSystems(self, 4, 1)         # slots: 0 F, 1 X, 2 / 3 probe products
+                self.total_modes = self.bset.total_modes
+            else:
+                self.bset = BatchSet(self, 0.0, 1.0, 4, 1)    # the Cartesian pencil batches with M = 0: ordering chosen for L alone
             self.bset.factor_verified([(0, 0.0, 1.0)], (0, 1, 2, 3))
         bs = self.bset
         self.rhs_plan.evaluate(self.eq_t)

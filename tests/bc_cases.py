@@ -207,3 +207,37 @@ def check_bc_data(d3, g):
         ref = g[name]
         got = f['c']
         assert np.allclose(got, ref, rtol=1e-8, atol=1e-11 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
+
+
+def check_poisson_lbvp(d3, g):
+    """examples/lbvp_2d_poisson/poisson.py:25-65 at 32 x 16: randomly forced Poisson equation with mixed boundary data, against the
+    reference executing the stock script (tests/golden/stock_scripts.npz, tag poisson)."""
+    Lx, Ly = 2*np.pi, np.pi
+    Nx, Ny = 32, 16
+    coords = d3.CartesianCoordinates('x', 'y')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    xbasis = d3.RealFourier(coords['x'], size=Nx, bounds=(0, Lx))
+    ybasis = d3.Chebyshev(coords['y'], size=Ny, bounds=(0, Ly))
+    u = dist.Field(name='u', bases=(xbasis, ybasis))
+    tau_1 = dist.Field(name='tau_1', bases=xbasis)
+    tau_2 = dist.Field(name='tau_2', bases=xbasis)
+    x, y = dist.local_grids(xbasis, ybasis)
+    f = dist.Field(bases=(xbasis, ybasis))
+    g_ = dist.Field(bases=xbasis)
+    h = dist.Field(bases=xbasis)
+    f.fill_random('g', seed=40)
+    f.low_pass_filter(shape=(16, 8))
+    g_['g'] = np.sin(8*x) * 0.025
+    h['g'] = 0
+    dy = lambda A: d3.Differentiate(A, coords['y'])
+    lift_basis = ybasis.derivative_basis(2)
+    lift = lambda A, n: d3.Lift(A, lift_basis, n)
+    problem = d3.LBVP([u, tau_1, tau_2], namespace=dict(u=u, tau_1=tau_1, tau_2=tau_2, f=f, g=g_, h=h, dy=dy, lift=lift, Ly=Ly))
+    problem.add_equation("lap(u) + lift(tau_1,-1) + lift(tau_2,-2) = f")
+    problem.add_equation("u(y=0) = g")
+    problem.add_equation("dy(u)(y=Ly) = h")
+    solver = problem.build_solver()
+    solver.solve()
+    for name, fld in (("u", u), ("tau_1", tau_1), ("tau_2", tau_2)):
+        ref = g[f"poisson_{name}"]
+        assert np.allclose(fld['c'], ref, rtol=1e-9, atol=1e-12 * np.abs(g["poisson_u"]).max()), (name, np.abs(fld['c'] - ref).max())

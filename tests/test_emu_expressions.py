@@ -41,3 +41,8 @@ def test_right_hand_sides_with_grid_functions_and_derivatives_of_products(golden
 
 def test_field_filters_norms_and_global_data(golden):
     X.check_field_helpers(golden("expressions.npz"))
+
+
+def test_cartesian_lbvp_poisson_matches_reference(golden):
+    import bc_cases, dedalus_b200 as d3
+    bc_cases.check_poisson_lbvp(d3, golden("stock_scripts.npz"))

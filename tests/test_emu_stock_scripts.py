@@ -15,6 +15,9 @@ STOCK = {
               ("p", "b", "u")),
     "shear": ("examples/ivp_2d_shear_flow/shear_flow.py",
               [("Nx, Nz = 128, 256", "Nx, Nz = 16, 32"), ("stop_sim_time = 20", "stop_sim_time = 0.12")], ("u", "s", "p")),
+    "poisson": ("examples/lbvp_2d_poisson/poisson.py",
+                [("Nx, Ny = 256, 128", "Nx, Ny = 32, 16"), ("f.low_pass_filter(shape=(64, 32))", "f.low_pass_filter(shape=(16, 8))")],
+                ("u", "tau_1", "tau_2")),
     "kdv": ("examples/ivp_1d_kdv_burgers/kdv_burgers.py",
             [("Nx = 1024", "Nx = 64"), ("stop_sim_time = 10", "stop_sim_time = 0.05")], ("u",)),
 }
