@@ -5,7 +5,7 @@ Public surface mirrors `dedalus.public` (reference dedalus/public.py:4-15) for t
 from .coords import Coordinate, CartesianCoordinates, S2Coordinates, SphericalCoordinates
 from .distributor import Distributor
 from .basis import (RealFourier, ComplexFourier, Jacobi, Legendre, Ultraspherical,
-                    ChebyshevT, ChebyshevU, ChebyshevV, Chebyshev)
+                    ChebyshevT, ChebyshevU, ChebyshevV, Chebyshev, Fourier)
 from .sphere import SphereBasis
 from .shell import ShellBasis
 from .field import Field

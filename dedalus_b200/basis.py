@@ -322,3 +322,12 @@ def ChebyshevV(*args, **kw):
 
 
 Chebyshev = ChebyshevT
+
+
+def Fourier(*args, dtype=None, **kw):
+    """Fourier basis factory (reference core/basis.py:1293-1300): real or complex by dtype."""
+    if dtype is None:
+        raise ValueError("dtype must be specified")
+    if np.issubdtype(np.dtype(dtype), np.complexfloating):
+        return ComplexFourier(*args, **kw)
+    return RealFourier(*args, **kw)

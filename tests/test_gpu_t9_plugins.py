@@ -11,3 +11,12 @@ def test_matsolver_registry_contract():
 
 def test_transpose_plugin_single_rank():
     P.check_transpose_single_rank()
+
+
+def test_reference_lbvp_cases():
+    """The reference's own Cartesian LBVP tests (dedalus/tests/test_lbvp.py:38-111)."""
+    import lbvp_cases as L
+    L.check_algebraic()
+    L.check_poisson_fourier()
+    L.check_poisson_jacobi(-1/2, -1/2)
+    L.check_poisson_jacobi(0, 0)
