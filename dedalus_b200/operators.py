@@ -136,7 +136,9 @@ def _merge_bases(op, bases_list):
 
 
 class Future(Operand):
-    pass
+    def __getitem__(self, key):
+        """op['g'] / op['c']: evaluate, then index the result (reference core/future.py Future / FutureField)."""
+        return self.evaluate()[key]
 
 
 class UnaryGridFunction(Future):

@@ -20,3 +20,11 @@ def test_reference_lbvp_cases():
     L.check_poisson_fourier()
     L.check_poisson_jacobi(-1/2, -1/2)
     L.check_poisson_jacobi(0, 0)
+
+
+def test_reference_ufunc_cases():
+    """The reference's ufunc tests (dedalus/tests/test_grid_operators.py:35-85), Jacobi and shell, N as in the reference."""
+    import grid_operator_cases as G
+    G.check_jacobi_ufunc_field(-1/2, -1/2)
+    G.check_jacobi_ufunc_field(0, 0)
+    G.check_shell_ufuncs(N=16)
