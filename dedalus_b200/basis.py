@@ -28,10 +28,11 @@ class Basis:
         return self.group_size
 
     def grid_size(self, scale):
+        """ceil(scale * size), as the reference rounds (core/basis.py:141-144); size-1 bases stay at 1."""
+        if self.size == 1:
+            return 1
         g = float(scale) * self.size
-        if not g.is_integer():
-            raise ValueError("Non-integer grid size: scale * size must be an integer.")
-        return int(g)
+        return int(np.ceil(g - 1e-12))
 
     def global_grid(self, dist_or_scale=None, scale=None):
         """global_grid(scale): the 1-D grid; global_grid(dist, scale): the reference's form (core/basis.py:364-368), shaped for

@@ -798,6 +798,8 @@ class ExpressionProgram:
                 self.reductions.append(('integ', expr.axes, expr.average)); expr = expr.args[0]
             elif isinstance(expr, ops.Interpolate) and not expr.trivial:
                 self.reductions.append(('interp', expr.axis, expr.position)); expr = expr.args[0]
+            elif isinstance(expr, ops.Lift):
+                self.reductions.append(('lift', expr.axis, expr.basis, expr.n)); expr = expr.args[0]
             else:
                 break
         self.reductions.reverse()
@@ -850,6 +852,17 @@ class ExpressionProgram:
         for red in self.reductions:
             if red[0] == 'scale':
                 data = data * red[1]
+                continue
+            if red[0] == 'lift':
+                # operand times the n-th polynomial of the lift basis: its value lands in mode n (reference LiftJacobi, basis.py:790-814)
+                _, ax, lb, n = red
+                if lb.dim != 1 or bases[ax] is not None:
+                    raise NotImplementedError("stand-alone Lift: one-dimensional lift bases over an axis without basis")
+                shape = list(data.shape); shape[nt + ax] = lb.size
+                lifted = torch.zeros(shape, dtype=data.dtype, device=data.device)
+                lifted.select(nt + ax, n % lb.size).copy_(data.select(nt + ax, 0))
+                data = lifted
+                bases[ax] = lb
                 continue
             axes = red[1] if red[0] == 'integ' else (red[1],)
             for ax in axes:

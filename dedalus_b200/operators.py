@@ -384,9 +384,17 @@ class Lift(LinearOperator):
 
 
 class Convert(LinearOperator):
+    """Convert(A, bases): per-axis tuple of output bases, or -- the reference's form (core/operators.py:1533-1560) -- ONE output
+    basis, which replaces the operand's basis along that basis' axis."""
     def __init__(self, A, bases):
         self.args = [A]
         self.dist, self.dtype, self.tensorsig = A.dist, A.dtype, A.tensorsig
+        if not isinstance(bases, (tuple, list)):
+            out = list(A.bases)
+            ax = A.dist.get_basis_axis(bases)
+            for sub in range(getattr(bases, 'dim', 1)):
+                out[ax + sub] = bases
+            bases = out
         self.bases = tuple(bases)
 
 

@@ -296,12 +296,31 @@ class JacobiMatrixTransform:
         poly = jacobi.polynomials(M, a, b, grid)
         poly[N:, :] = 0
         self.backward_matrix = np.ascontiguousarray(poly.T)
+        self.stretch = stretch
+        self._grid = grid
         self._dev = {}
+
+    def _derivative_backward(self, d):
+        """Grid values of the d-th derivative from (a, b) coefficients: the backward matrix of the basis (a + d, b + d) times the
+        differentiation matrices in between (reference DifferentiateJacobi, core/basis.py:701-718, followed by the transform)."""
+        a, b = self.a, self.b
+        chain = np.eye(self.M)
+        for i in range(d):
+            chain = (jacobi.differentiation_matrix(self.M, a + i, b + i) / self.stretch) @ chain
+        poly = jacobi.polynomials(self.M, a + d, b + d, self._grid)
+        poly[self.N:, :] = 0
+        return np.ascontiguousarray(poly.T @ chain)
 
     def _mat(self, which, device):
         k = (which, str(device))
         if k not in self._dev:
-            self._dev[k] = _torch().from_numpy(self.forward_matrix if which == 'f' else self.backward_matrix).to(device)
+            if which == 'f':
+                m = self.forward_matrix
+            elif which == 'b':
+                m = self.backward_matrix
+            else:
+                m = self._derivative_backward(which)
+            self._dev[k] = _torch().from_numpy(m).to(device)
         return self._dev[k]
 
     def forward(self, gdata, cdata, axis):
@@ -310,11 +329,10 @@ class JacobiMatrixTransform:
         get_lib().call("db_mmt_apply", _dptr(self._mat('f', gdata.device)), self.M, self.N, _dptr(gdata), _dptr(cdata), outer, inner, _stream())
 
     def backward(self, cdata, gdata, axis, deriv=0):
-        if deriv:
-            raise NotImplementedError("fused derivative is only available in the fast Chebyshev transform")
         _check(gdata, "gdata"); _check(cdata, "cdata")
         outer, inner = _split(gdata.shape, axis)
-        get_lib().call("db_mmt_apply", _dptr(self._mat('b', gdata.device)), self.N, self.M, _dptr(cdata), _dptr(gdata), outer, inner, _stream())
+        mat = self._mat(int(deriv) if deriv else 'b', gdata.device)        # derivatives fold into the matrix
+        get_lib().call("db_mmt_apply", _dptr(mat), self.N, self.M, _dptr(cdata), _dptr(gdata), outer, inner, _stream())
 
 
 class SWSHColatitudeTransform:

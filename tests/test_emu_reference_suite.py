@@ -1,4 +1,4 @@
-"""The reference's own Cartesian LBVP tests (tests/lbvp_cases.py) and ufunc tests (tests/grid_operator_cases.py) through the CPU emulation."""
+"""Cases of the reference's OWN test suite restated against dedalus_b200 (lbvp_cases, grid_operator_cases, operator_cases), through the CPU emulation."""
 import pytest
 from emu import emu_lib as E
 import lbvp_cases as L
@@ -33,3 +33,16 @@ def test_jacobi_ufunc_field(a, b):
 def test_shell_ufunc_field_and_operator():
     import grid_operator_cases as G
     G.check_shell_ufuncs()
+
+
+def test_fourier_operators():
+    import operator_cases as O
+    O.check_fourier()
+
+
+@pytest.mark.parametrize("N", [8, 9])
+@pytest.mark.parametrize("a,b", [(-1/2, -1/2), (0, 0)])
+@pytest.mark.parametrize("k", [0, 1])
+def test_jacobi_operators(N, a, b, k):
+    import operator_cases as O
+    O.check_jacobi(N, a, b, k)

@@ -28,3 +28,13 @@ def test_reference_ufunc_cases():
     G.check_jacobi_ufunc_field(-1/2, -1/2)
     G.check_jacobi_ufunc_field(0, 0)
     G.check_shell_ufuncs(N=16)
+
+
+def test_reference_operator_cases():
+    """The reference's Fourier / Jacobi operator tests (test_fourier_operators.py, test_jacobi_operators.py)."""
+    import operator_cases as O
+    O.check_fourier()
+    for N in (8, 9):
+        for a, b in ((-1/2, -1/2), (0, 0)):
+            for k in (0, 1):
+                O.check_jacobi(N, a, b, k)
