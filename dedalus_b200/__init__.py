@@ -19,4 +19,4 @@ from .timesteppers import (schemes, CNAB1, SBDF1, CNAB2, MCNAB2, SBDF2, CNLF2, S
                            RK111, RK222, RK443, RKSMR, RKGFY)
 
 __version__ = "0.1.0"
-from .extras.flow_tools import CFL, GlobalFlowProperty
+from .extras.flow_tools import CFL, GlobalFlowProperty, AdvectiveCFL

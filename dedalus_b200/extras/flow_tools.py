@@ -201,3 +201,68 @@ class GlobalFlowProperty:
 
     def volume_average(self, name):
         raise NotImplementedError("missing definition of hypervolume")      # as in the reference (flow_tools.py:132-137)
+
+
+class AdvectiveCFL:
+    """The advective CFL frequency as a field on the dealiased grid (reference operators.AdvectiveCFL, core/operators.py:4342-4400;
+    spacings core/basis.py:6078-6212).  `evaluate()` returns the frequency field, `cfl_spacing()` the per-direction spacings it
+    divides by.  The CFL controller above reduces the same expression to its maximum in one kernel without forming this field."""
+
+    def __init__(self, operand, coords=None):
+        if len(operand.tensorsig) != 1:
+            raise ValueError("Velocity must be a vector")
+        self.operand = operand
+        self.coords = coords if coords is not None else operand.tensorsig[0]
+        self.dist = operand.dist
+
+    def _shaped(self, values, axis):
+        shape = [1] * self.dist.dim
+        shape[axis] = len(values)
+        return np.asarray(values, dtype=float).reshape(shape)
+
+    def cfl_spacing(self):
+        from ..sphere import sphere_basis_of
+        from ..shell import shell_basis_of
+        u = self.operand
+        dist = self.dist
+        cs = u.tensorsig[0]
+        if getattr(cs, 'curvilinear', False):
+            shell = shell_basis_of(u)
+            basis = shell if shell is not None else sphere_basis_of(u)
+            L = basis.Lmax
+            ax = dist.get_basis_axis(basis)
+            if shell is not None:
+                scale = shell.dealias[2]
+                r = shell.global_grid_radius(scale)
+                s2 = self._shaped(r / np.sqrt(L * (L + 1)) if L > 0 else np.full(r.size, np.inf), ax + 2)
+                return [s2, self._shaped(np.abs(np.gradient(r, edge_order=2) * scale), ax + 2)]
+            return [np.array(basis.radius / np.sqrt(L * (L + 1)) if L > 0 else np.inf).reshape([1] * dist.dim)]
+        out = []
+        for coord in cs.coords:
+            ax = dist.get_axis(coord)
+            b = u.bases[ax]
+            if b is None:
+                out.append(np.inf)
+                continue
+            scale = b.dealias[0]
+            dx = CFL._cfl_spacing(b, scale)
+            out.append(self._shaped(np.abs(dx[dist.grid_local_slice(ax, b, scale)]), ax))
+        return out
+
+    def evaluate(self):
+        import torch
+        from ..field import Field
+        u = self.operand
+        g = u.copy_device_to_grid()                       # (ncomp, grid) at dealias scales
+        sp = [torch.from_numpy(np.array(np.broadcast_to(s, g.shape[1:]), dtype=float)).to(g.device) for s in self.cfl_spacing()]
+        u.change_scales(u.dealias)      # as in the reference, the operand is left on the dealiased grid scales
+        if getattr(u.tensorsig[0], 'curvilinear', False):
+            freq = torch.sqrt(g[0] ** 2 + g[1] ** 2) / sp[0]
+            if len(sp) > 1:
+                freq = freq + g[2].abs() / sp[1]
+        else:
+            freq = sum(g[i].abs() / sp[i] for i in range(len(sp)))
+        out = Field(self.dist, bases=u.unique_bases(), dtype=u.dtype)
+        self.dist._fields.pop()
+        out.set_device_data(freq.contiguous(), 'g', scales=u.dealias)
+        return out

@@ -46,3 +46,20 @@ def test_fourier_operators():
 def test_jacobi_operators(N, a, b, k):
     import operator_cases as O
     O.check_jacobi(N, a, b, k)
+
+
+@pytest.mark.parametrize("dealias", [1, 3/2])
+def test_cfl_operators(dealias):
+    import cfl_cases as Cc
+    Cc.check_cfl_1d('fourier', dealias)
+    Cc.check_cfl_1d('chebyshev', dealias)
+    Cc.check_cfl_fourier_chebyshev(dealias)
+    Cc.check_cfl_sphere(dealias)
+    Cc.check_cfl_shell(dealias)
+
+
+@pytest.mark.parametrize("dealias", [1, 3/2])
+@pytest.mark.parametrize("safety", [0.2, 0.4])
+def test_full_cfl_fourier_chebyshev(dealias, safety):
+    import cfl_cases as Cc
+    Cc.check_full_cfl_fourier_chebyshev(dealias, safety)

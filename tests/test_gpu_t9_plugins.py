@@ -38,3 +38,16 @@ def test_reference_operator_cases():
         for a, b in ((-1/2, -1/2), (0, 0)):
             for k in (0, 1):
                 O.check_jacobi(N, a, b, k)
+
+
+def test_reference_cfl_cases():
+    """The reference's CFL tests (dedalus/tests/test_cfl.py), real dtype: operator on five kinds of bases and the tool end to end."""
+    import cfl_cases as Cc
+    for dealias in (1, 3/2):
+        Cc.check_cfl_1d('fourier', dealias)
+        Cc.check_cfl_1d('chebyshev', dealias)
+        Cc.check_cfl_fourier_chebyshev(dealias)
+        Cc.check_cfl_sphere(dealias)
+        Cc.check_cfl_shell(dealias, N=16)
+        for safety in (0.2, 0.4):
+            Cc.check_full_cfl_fourier_chebyshev(dealias, safety)
