@@ -741,6 +741,18 @@ def linear_map(expr, variables, coupled_axis):
                     t.comp = sparse.csr_matrix(T @ t.comp)
                 sub[k] = [t for t in terms if t.comp.nnz]
             return sub
+        if isinstance(e, Skew):
+            # Cartesian skew of the first index: kron([[0, -1], [1, 0]], I) on the components (reference CartesianSkew.subproblem_matrix,
+            # core/operators.py:2102-2110)
+            if e.index != 0 or getattr(e.cs, 'curvilinear', False):
+                raise NotImplementedError("Skew on the LHS: Cartesian vectors, index 0")
+            sub = rec(e.args[0])
+            nrest = e.ncomp // 2
+            S = sparse.kron(sparse.csr_matrix(np.array([[0.0, -1.0], [1.0, 0.0]])), sparse.identity(nrest), format='csr')
+            for k, terms in sub.items():
+                for t in terms:
+                    t.comp = sparse.csr_matrix(S @ t.comp)
+            return sub
         if isinstance(e, TransposeComponents):
             sub = rec(e.args[0])
             d0, d1 = e.args[0].tensorsig[0].dim, e.args[0].tensorsig[1].dim

@@ -63,3 +63,15 @@ def test_cfl_operators(dealias):
 def test_full_cfl_fourier_chebyshev(dealias, safety):
     import cfl_cases as Cc
     Cc.check_full_cfl_fourier_chebyshev(dealias, safety)
+
+
+@pytest.mark.parametrize("kind", ["FF", "FC"])
+def test_cartesian_skew(kind):
+    import cartesian_operator_cases as K
+    K.check_skew(kind)
+
+
+@pytest.mark.parametrize("kind", ["FF", "FC", "FFF", "FFC"])
+def test_cartesian_trace_and_transpose(kind):
+    import cartesian_operator_cases as K
+    K.check_trace_and_transpose(kind)

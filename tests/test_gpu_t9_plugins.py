@@ -51,3 +51,12 @@ def test_reference_cfl_cases():
         Cc.check_cfl_shell(dealias, N=16)
         for safety in (0.2, 0.4):
             Cc.check_full_cfl_fourier_chebyshev(dealias, safety)
+
+
+def test_reference_cartesian_tensor_operator_cases():
+    """The reference's skew / trace / transpose tests (dedalus/tests/test_cartesian_operators.py:93-250), explicit and implicit."""
+    import cartesian_operator_cases as K
+    for kind in ("FF", "FC"):
+        K.check_skew(kind)
+    for kind in ("FF", "FC", "FFF", "FFC"):
+        K.check_trace_and_transpose(kind)
