@@ -10,7 +10,7 @@ from .sphere import SphereBasis
 from .shell import ShellBasis
 from .field import Field
 from .operators import (Differentiate, Gradient, Divergence, Laplacian, Trace, TransposeComponents,
-                        Interpolate, Integrate, Lift, Convert, TimeDerivative, DotProduct, Multiply, Skew, MulCosine,
+                        Interpolate, Integrate, Lift, Convert, TimeDerivative, DotProduct, Multiply, Skew, MulCosine, Curl, curl,
                         grad, div, lap, skew, trace, transpose, integ, ave, dot, interp, Average, UnaryGridFunction)
 from .problems import IVP, LBVP
 InitialValueProblem = IVP

@@ -125,6 +125,16 @@ def lower(expr):
         if isinstance(e, ops.Trace):
             sub = rec(e.args[0]); d = e.args[0].tensorsig[0].dim; nrest = e.ncomp
             return {r: [t for i in range(d) for t in sub.get((i * d + i) * nrest + r, [])] for r in range(nrest)}
+        if isinstance(e, ops.Curl):
+            sub = rec(e.args[0]); nrest = e.ncomp // 3
+            out = {}
+            for i in range(3):
+                j, k = (i + 1) % 3, (i + 2) % 3                      # (curl u)_i = d_j u_k - d_k u_j
+                axj, axk = e.dist.get_axis(e.cs.coords[j]), e.dist.get_axis(e.cs.coords[k])
+                for r in range(nrest):
+                    out[i * nrest + r] = diff_terms(sub.get(k * nrest + r, []), axj) + \
+                        [(-c, f) for c, f in diff_terms(sub.get(j * nrest + r, []), axk)]
+            return out
         if isinstance(e, ops.Skew):
             # Cartesian skew (reference CartesianSkew.operate, operators.py:2112-2122): out_x = -arg_y, out_y = arg_x
             if e.index != 0 or getattr(e.cs, 'curvilinear', False):
@@ -158,6 +168,7 @@ class RHSPlan:
         arena = solver.eq_arena
         self.static_entries = []      # (arena offset, value) for constant RHS
         self.linear_copies = {}       # (equation, comp) -> [(coef, field, field comp)]: coefficient-space right-hand sides
+        self.program_copies = {}      # equation -> ExpressionProgram of a lower-dimensional right-hand side
         inputs = {}                   # (id(field), comp, derivs) -> index
         self.input_keys = []
         outputs = []                  # (eq index, comp, terms)
@@ -167,7 +178,14 @@ class RHSPlan:
                 if rhs != 0:
                     self._add_constant(ie, eq, float(rhs))
                 continue
-            low = lower(rhs)
+            try:
+                low = lower(rhs)
+            except NonPolynomialError:
+                if any(b is None for b in eq['bases']):
+                    # boundary data given as an expression ("u(z=0) = f(z=0)"): evaluated stand-alone (reductions of fields), copied in
+                    self.program_copies[ie] = ExpressionProgram(rhs)
+                    continue
+                raise
             for comp, terms in low.items():
                 const = sum(c for c, f in terms if len(f) == 0)
                 terms = [(c, f) for c, f in terms if len(f) > 0]
@@ -325,6 +343,13 @@ class RHSPlan:
         from .transforms import cached_plan, _dptr, _stream
         from .lib import get_lib
         from .solvers import Timed
+        for ie, prog in self.program_copies.items():
+            res = prog.run()
+            res.change_layout('c')
+            tsh, shp = self.solver.eq_arena.shapes[ie]
+            n = int(np.prod(tsh, dtype=int)) * int(np.prod(shp, dtype=int))
+            off = self.solver.eq_arena.offsets[ie]
+            eq_arena_tensor[off:off + n].copy_(res.device_data().reshape(-1))
         for key, terms in self.linear_copies.items():
             off, shp = self.copy_dest[key]
             dst = eq_arena_tensor[off:off + int(np.prod(shp))].view(shp)

@@ -326,6 +326,21 @@ class Skew(LinearOperator):
         self.dist, self.dtype, self.tensorsig, self.bases = A.dist, A.dtype, A.tensorsig, A.bases
 
 
+class Curl(LinearOperator):
+    """Curl of a 3-D Cartesian vector field (reference CartesianCurl, core/operators.py:3640-3720): (curl u)_i = eps_ijk d_j u_k."""
+    def __init__(self, A, index=0):
+        if not A.tensorsig or A.tensorsig[index].dim != 3 or getattr(A.tensorsig[index], 'curvilinear', False) or index != 0:
+            raise NotImplementedError("Curl: first index of 3-D Cartesian vector fields")
+        self.args = [A]
+        self.index = index
+        self.cs = A.tensorsig[index]
+        self.dist, self.dtype, self.tensorsig = A.dist, A.dtype, A.tensorsig
+        b = tuple(A.bases)
+        for coord in self.cs.coords:
+            b = _diff_bases(b, A.dist.get_axis(coord))
+        self.bases = b
+
+
 class MulCosine(LinearOperator):
     """Multiplication by cos(colatitude) on S2 (reference operators.py:2995-3050)."""
     def __init__(self, A, coordsys=None):
@@ -403,6 +418,7 @@ def grad(A, cs=None): return Gradient(A, cs)
 def div(A, index=0): return Divergence(A, index)
 def lap(A, cs=None): return Laplacian(A, cs)
 def skew(A, index=0): return Skew(A, index)
+def curl(A, index=0): return Curl(A, index)
 def trace(A): return Trace(A)
 def transpose(A): return TransposeComponents(A)
 def dt(A): return TimeDerivative(A)
@@ -741,6 +757,27 @@ def linear_map(expr, variables, coupled_axis):
                     t.comp = sparse.csr_matrix(T @ t.comp)
                 sub[k] = [t for t in terms if t.comp.nnz]
             return sub
+        if isinstance(e, Curl):
+            sub = rec(e.args[0])
+            nrest = e.ncomp // 3
+            out = {}
+            for k, terms in sub.items():
+                new = []
+                for i in range(3):
+                    for j, kk, sign in (((i + 1) % 3, (i + 2) % 3, 1.0), ((i + 2) % 3, (i + 1) % 3, -1.0)):      # eps_ijk d_j u_k
+                        ax = e.dist.get_axis(e.cs.coords[j])
+                        pick = _comp_select(3, kk, nrest, row=False)           # component kk of the operand
+                        place = _comp_select(3, i, nrest, row=True)            # into component i of the result
+                        for t in terms:
+                            u = t.copy()
+                            u.comp = sparse.csr_matrix(place @ (pick @ u.comp)) * sign
+                            if u.comp.nnz == 0:
+                                continue
+                            u = _apply_axis(u, ax, ax == coupled_axis, 'diff')
+                            if u is not None:
+                                new.append(u)
+                out[k] = _convert_terms(new, e.bases, coupled_axis)
+            return out
         if isinstance(e, Skew):
             # Cartesian skew of the first index: kron([[0, -1], [1, 0]], I) on the components (reference CartesianSkew.subproblem_matrix,
             # core/operators.py:2102-2110)

@@ -88,3 +88,64 @@ def check_trace_and_transpose(kind, N=16):
     solver = problem.build_solver()
     solver.solve()
     assert np.allclose(u['c'], f['c'])
+
+
+def check_curls():
+    """test_2d_curl_explicit_vector / _scalar (FF, FC), test_curl_explicit (FFF, FFC), test_curl_implicit_FFC
+    (test_cartesian_operators.py:252-400)"""
+    N, dealias = 16, 1
+    kx, ky = 2*np.pi/Lx, 2*np.pi/Ly
+    for kind in ("FF", "FC"):
+        c, d, b, (x, y) = build(kind, N, dealias)
+        f = d.VectorField(c, bases=b)
+        f.preset_scales(dealias)
+        f['g'][0] = (np.sin(2*kx*x)+np.sin(kx*x))*np.cos(ky*y)
+        f['g'][1] = np.sin(kx*x)*np.cos(ky*y)
+        g_op = - d3.div(d3.skew(f))                # z @ curl(f)
+        g = d.Field(bases=b)
+        g.preset_scales(dealias)
+        g['g'] = kx*np.cos(kx*x)*np.cos(ky*y) + ky*(np.sin(2*kx*x)+np.sin(kx*x))*np.sin(ky*y)
+        assert np.allclose(g_op.evaluate()['g'], g['g'])
+        c, d, b, (x, y) = build(kind, 2*N, dealias)
+        f = d.Field(bases=b)
+        f.preset_scales(dealias)
+        f['g'] = (np.sin(2*kx*x)+np.sin(kx*x))*np.cos(ky*y)
+        g_op = - d3.skew(d3.grad(f))               # curl(f*ez)
+        g = d.VectorField(c, bases=b)
+        g.preset_scales(dealias)
+        g['g'][0] = -ky*(np.sin(2*kx*x)+np.sin(kx*x))*np.sin(ky*y)
+        g['g'][1] = -(2*kx*np.cos(2*kx*x)+kx*np.cos(kx*x))*np.cos(ky*y)
+        assert np.allclose(g_op.evaluate()['g'], g['g'])
+    k = 2*np.pi*np.array([1/Lx, 1/Ly, 1/Lz])
+
+    def abc(kind):
+        c, d, b, r = build(kind, N, dealias)
+        f = d.VectorField(c, bases=b)
+        f.preset_scales(dealias)
+        f['g'][0] = np.sin(k[2]*r[2]) + np.cos(k[1]*r[1])
+        f['g'][1] = np.sin(k[0]*r[0]) + np.cos(k[2]*r[2])
+        f['g'][2] = np.sin(k[1]*r[1]) + np.cos(k[0]*r[0])
+        g = d.VectorField(c, bases=b)
+        g.preset_scales(dealias)
+        g['g'][0] = k[2]*np.sin(k[2]*r[2]) + k[1]*np.cos(k[1]*r[1])
+        g['g'][1] = k[0]*np.sin(k[0]*r[0]) + k[2]*np.cos(k[2]*r[2])
+        g['g'][2] = k[1]*np.sin(k[1]*r[1]) + k[0]*np.cos(k[0]*r[0])
+        return c, d, b, r, f, g
+    for kind in ("FFF", "FFC"):
+        c, d, b, r, f, g = abc(kind)
+        assert np.allclose(d3.Curl(f).evaluate()['g'], g['g'])
+    c, d, b, r, f, g = abc("FFC")                  # test_curl_implicit_FFC: Helmholtz LBVP
+    u = d.VectorField(c, name='u', bases=b)
+    phi = d.Field(name='phi', bases=b)
+    tau1 = d.VectorField(c, name='tau1', bases=b[0:2])
+    tau2 = d.Field(name='tau2', bases=b[0:2])
+    lift_basis = b[2].derivative_basis(1)
+    lift = lambda A, n: d3.Lift(A, lift_basis, n)
+    problem = d3.LBVP([u, phi, tau1, tau2], namespace=locals())
+    problem.add_equation("curl(u) + grad(phi) + lift(tau1,-1) = g")
+    problem.add_equation("div(u) + lift(tau2,-1) = 0")
+    problem.add_equation("u(z=0) = f(z=0)")
+    problem.add_equation("phi(z=0) = 0")
+    solver = problem.build_solver()
+    solver.solve()
+    assert np.allclose(u['c'], f['c'])

@@ -75,3 +75,8 @@ def test_cartesian_skew(kind):
 def test_cartesian_trace_and_transpose(kind):
     import cartesian_operator_cases as K
     K.check_trace_and_transpose(kind)
+
+
+def test_cartesian_curls():
+    import cartesian_operator_cases as K
+    K.check_curls()

@@ -60,3 +60,4 @@ def test_reference_cartesian_tensor_operator_cases():
         K.check_skew(kind)
     for kind in ("FF", "FC", "FFF", "FFC"):
         K.check_trace_and_transpose(kind)
+    K.check_curls()
