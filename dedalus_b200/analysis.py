@@ -19,7 +19,7 @@ from .field import Field
 
 _TORCH_NAMES = {'absolute': 'abs', 'arcsin': 'asin', 'arccos': 'acos', 'arctan': 'atan', 'arcsinh': 'asinh', 'arccosh': 'acosh',
                 'arctanh': 'atanh', 'conjugate': 'conj'}
-_NONLINEAR = (ops.Multiply, ops.DotProduct, ops.Power, ops.UnaryGridFunction)
+_NONLINEAR = (ops.Multiply, ops.DotProduct, ops.Power, ops.UnaryGridFunction, ops.MulCosine)
 
 
 class LockedField:
@@ -112,6 +112,17 @@ class CurvilinearEvaluation:
             if fn is None:
                 raise NotImplementedError(f"grid function {name!r} has no device implementation")
             return fn(self.grid(e.args[0]))
+        if isinstance(e, ops.MulCosine):
+            # cos(colatitude) times the operand, formed on the dealiased grid (the product raises the degree by one and the forward
+            # transform truncates it, as the reference's truncated operator matrix does, core/operators.py:2995-3050)
+            g = self.grid(e.args[0])
+            basis = _full_basis(e.args[0])
+            ax = self.dist.get_basis_axis(basis)
+            scale = basis.dealias[1]
+            sb = getattr(basis, 'sphere_basis', basis)
+            theta = sb.global_grid_colatitude(scale)[self.dist.grid_local_slice(ax + 1, basis, scale)]
+            shape = [1] * self.dist.dim; shape[ax + 1] = theta.size
+            return g * torch.from_numpy(np.cos(theta).reshape(shape)).to(g.device)
         if isinstance(e, ops.Interpolate) and self._azimuthal(e):
             g = self.grid(e.args[0])
             basis = _full_basis(e.args[0])
@@ -159,6 +170,8 @@ class CurvilinearEvaluation:
             if isinstance(e, (ops.Add, ops.ScalarMul)):
                 return self._materialize(e, self.grid(e))
             raise NotImplementedError(f"{type(e).__name__} of shell fields in output expressions")
+        if isinstance(e, ops.Integrate) and sphere_basis_of(e.args[0]) is not None and shell is None:
+            return self._sphere_integral(self.field(e.args[0]), e)
         if sphere_basis_of(e) is not None:
             return evaluate_linear_expression(self._with_field_leaves(e))
         raise NotImplementedError(f"{type(e).__name__} in curvilinear output expressions")
@@ -226,6 +239,30 @@ class CurvilinearEvaluation:
         out = (c * vec).sum(dim=-1, keepdim=True)
         res = _temp_field(e, (basis.S2_basis(radius=e.position),))
         res.set_device_data(out.contiguous(), 'c')
+        return res
+
+    def _sphere_integral(self, f, e):
+        """Average / integral of a scalar over the sphere: the (m = 0, l = 0) coefficient times the constant mode value 1 / sqrt 2
+        (reference SphereAverage, core/basis.py:5296-5317; the integral is the average times 4 pi R^2)."""
+        import torch
+        from .sphere import sphere_basis_of
+        if f.tensorsig:
+            raise NotImplementedError("sphere averages of tensor fields")
+        basis = sphere_basis_of(f)
+        f.change_layout('c')
+        c = f.device_data()
+        j, cols = basis.mode_columns(0)
+        j0, j1 = basis.local_pairs(self.dist)
+        val = torch.zeros(1, dtype=c.dtype, device=c.device)
+        if j0 <= j < j1:
+            val = c.reshape(c.shape[0], c.shape[1], -1)[2 * (j - j0), int(cols[0]), :1].clone() / np.sqrt(2.0)
+        if self.dist.size > 1:
+            import torch.distributed as td
+            td.all_reduce(val)
+        if not e.average:
+            val = val * (4 * np.pi * basis.radius ** 2)
+        res = _temp_field(e, ())
+        res.set_device_data(val.reshape(res.local_shape('c', res.scales)), 'c')
         return res
 
     # ---- entry -------------------------------------------------------------------------------------------------------

@@ -944,7 +944,9 @@ class SphereRHSPlan:
                 n_pcomp[0] += len(spins)
             return products[product_ids[id(e)]]
 
-        is_product = lambda e: isinstance(e, nonlinear)
+        # leaves of the separable operators outside: products, or plain sphere fields (right-hand sides linear in a field, "skew(f)",
+        # "f + MulCosine(f)": carried through the grid like a one-factor product)
+        is_product = lambda e: isinstance(e, nonlinear) or is_state(e)
         self.post_rows = []
         const_seen = False
         for eq in problem.equations:

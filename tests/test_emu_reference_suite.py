@@ -80,3 +80,15 @@ def test_cartesian_trace_and_transpose(kind):
 def test_cartesian_curls():
     import cartesian_operator_cases as K
     K.check_curls()
+
+
+@pytest.mark.parametrize("dealias", [1, 3/2])
+def test_sphere_calculus_explicit(dealias):
+    import sphere_calculus_cases as S
+    S.check_explicit(dealias)
+
+
+@pytest.mark.parametrize("dealias", [1, 3/2])
+def test_sphere_calculus_implicit(dealias):
+    import sphere_calculus_cases as S
+    S.check_implicit(dealias)

@@ -61,3 +61,11 @@ def test_reference_cartesian_tensor_operator_cases():
     for kind in ("FF", "FC", "FFF", "FFC"):
         K.check_trace_and_transpose(kind)
     K.check_curls()
+
+
+def test_reference_sphere_calculus_cases():
+    """The reference's S2 calculus tests (dedalus/tests/test_sphere_calculus.py), explicit and through LBVPs."""
+    import sphere_calculus_cases as S
+    for dealias in (1, 3/2):
+        S.check_explicit(dealias)
+        S.check_implicit(dealias)
