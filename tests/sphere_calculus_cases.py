@@ -103,3 +103,22 @@ def check_implicit(dealias, Nphi=32, Ntheta=16):
     solver.solve()
     u.change_scales(dealias); f.change_scales(dealias)
     assert np.allclose(u['g'], -f['g'] / (l*(l+1)) * radius**2)
+
+
+def check_shell_gradient_scalar(dealias, Nphi=16, Ntheta=8, Nr=8):
+    """test_spherical_calculus.py:43-57 with the shell basis (radii 0.5, 3): gradient of 3 x^2 + 2 y z in spherical components."""
+    c = d3.SphericalCoordinates('phi', 'theta', 'r')
+    d = d3.Distributor((c,), dtype=dtype)
+    b = d3.ShellBasis(c, (Nphi, Ntheta, Nr), radii=(0.5, 3), dealias=(dealias, dealias, dealias), dtype=dtype)
+    phi, theta, r = d.local_grids(b, scales=dealias)
+    x, y, z = c.cartesian(phi, theta, r)
+    f = d.Field(bases=b)
+    f.preset_scales(dealias)
+    f['g'] = 3*x**2 + 2*y*z
+    u = d3.Gradient(f, c).evaluate()
+    u.change_scales(dealias)
+    ug = 0 * u['g']
+    ug[2] = (6*x**2+4*y*z)/r
+    ug[1] = -2*(y**3+x**2*(y-3*z)-y*z**2)/(r**2*np.sin(theta))
+    ug[0] = 2*x*(-3*y+z)/(r*np.sin(theta))
+    assert np.allclose(u['g'], ug)

@@ -69,3 +69,4 @@ def test_reference_sphere_calculus_cases():
     for dealias in (1, 3/2):
         S.check_explicit(dealias)
         S.check_implicit(dealias)
+        S.check_shell_gradient_scalar(dealias)
