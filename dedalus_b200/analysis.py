@@ -163,12 +163,12 @@ class CurvilinearEvaluation:
         if isinstance(e, ops.Interpolate) and self._azimuthal(e):
             raise NotImplementedError("azimuthal interpolation returns grid data only; use it as the outermost operator of a task")
         if shell is not None:
-            if isinstance(e, ops.Gradient):
-                return self._shell_gradient(self.field(e.args[0]), e)
-            if isinstance(e, ops.Interpolate) and e.axis == self.dist.get_basis_axis(shell) + 2:
+            if isinstance(e, ops.Gradient) and shell.k == 0 and isinstance(e.args[0], Field):
+                return self._shell_gradient(self.field(e.args[0]), e)          # the kernel path (also used inside time steps)
+            if isinstance(e, ops.Interpolate) and e.axis == self.dist.get_basis_axis(shell) + 2 and not e.tensorsig:
                 return self._shell_radial_interpolation(self.field(e.args[0]), e)
-            if isinstance(e, (ops.Add, ops.ScalarMul)):
-                return self._materialize(e, self.grid(e))
+            if isinstance(e, (ops.Gradient, ops.Divergence, ops.Laplacian, ops.Trace, ops.Add, ops.ScalarMul)):
+                return self._shell_linear(e)
             raise NotImplementedError(f"{type(e).__name__} of shell fields in output expressions")
         if isinstance(e, ops.Integrate) and sphere_basis_of(e.args[0]) is not None and shell is None:
             return self._sphere_integral(self.field(e.args[0]), e)
@@ -239,6 +239,56 @@ class CurvilinearEvaluation:
         out = (c * vec).sum(dim=-1, keepdim=True)
         res = _temp_field(e, (basis.S2_basis(radius=e.position),))
         res.set_device_data(out.contiguous(), 'c')
+        return res
+
+    def _shell_linear(self, e):
+        """Any expression of gradients / divergences / Laplacians / traces / sums of shell fields: for every degree l, the radial
+        block matrices of the per-l lowering that also builds the pencil systems (shell_ivp.ShellLowering: reference
+        SphericalEllOperator subproblem matrices, core/operators.py:3108-3310, 3546-3603) applied to the (m, l) lines of the
+        operands' regularity components.  Nonlinear subtrees are evaluated first and enter as fields."""
+        import torch
+        from types import SimpleNamespace
+        from .shell import shell_basis_of
+        from .shell_ivp import ShellLowering, regularity_allowed
+        e = self._with_field_leaves(e)
+        leaves = []
+        for f in e.atoms():
+            if not any(f is g for g in leaves):
+                leaves.append(f)
+        if any(shell_basis_of(f) is None or any(b is not shell_basis_of(f) for b in f.bases) for f in leaves):
+            raise NotImplementedError("linear shell expressions: operands on the full shell basis only")
+        low = ShellLowering(SimpleNamespace(variables=leaves))
+        basis, sb = low.basis, low.basis.sphere_basis
+        kind, k_out = low.kind_of(e)
+        if kind != 'shell':
+            raise NotImplementedError("linear shell expressions with lower-dimensional results")
+        rank_out = len(e.tensorsig)
+        j0, j1 = sb.local_pairs(self.dist)
+        _, ell_map = sb.elements_to_groups()
+        ell_pairs = ell_map[0::2][j0:j1]                                   # (local pairs, Nl): degree of every (pair, column)
+        data = []
+        for f in leaves:
+            f.change_layout('c')
+            d = f.device_data()
+            data.append(d.reshape((3 ** len(f.tensorsig),) + tuple(d.shape[len(f.tshape):])))
+        dev = data[0].device
+        Nc0, Nc1, Nr = data[0].shape[1:]
+        out = torch.zeros((3 ** rank_out, Nc0, Nc1, Nr), dtype=torch.float64, device=dev)
+        idx_of = lambda c, rank: tuple(np.unravel_index(c, (3,) * rank)) if rank else ()
+        for ell in range(sb.Lmax + 1):
+            pj, pc = np.nonzero(ell_pairs == ell)
+            if pj.size == 0:
+                continue
+            rows = torch.from_numpy(np.concatenate([2 * pj, 2 * pj + 1])).to(dev)
+            cols = torch.from_numpy(np.concatenate([pc, pc])).to(dev)
+            node = low.lower(e, ell)
+            for (co, iv, ci), B in node.blocks.get(0, {}).items():
+                if not (regularity_allowed(ell, idx_of(co, rank_out)) and regularity_allowed(ell, idx_of(ci, len(leaves[iv].tensorsig)))):
+                    continue
+                Bm = torch.from_numpy(np.ascontiguousarray(B.toarray() if hasattr(B, 'toarray') else np.asarray(B))).to(dev)
+                out[co, rows, cols, :] += data[iv][ci, rows, cols, :] @ Bm.T
+        res = _temp_field(e, (basis.clone_with(k=k_out),))
+        res.set_device_data(out.reshape(res.tshape + (Nc0, Nc1, Nr)), 'c')
         return res
 
     def _sphere_integral(self, f, e):

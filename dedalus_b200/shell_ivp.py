@@ -216,6 +216,9 @@ class ShellLowering:
                         out.append((a * ncomp + co, xi(mu, ell + R) * (rops.D(mu, ell + R, n.k) @ B)))
                 return out
             return _map(n, fn, k=n.k + 1, rank=n.rank + 1)
+        if isinstance(e, ops.Laplacian):
+            # div(grad(.)) (reference SphericalLaplacian, core/operators.py:3958-4010: the same composition of D+ / D- blocks)
+            return self.lower(ops.Divergence(ops.Gradient(e.args[0], e.args[0].dist.coordsys)), ell)
         if isinstance(e, ops.Divergence):
             n = self.lower(e.args[0], ell)
             nrest = 3 ** (n.rank - 1)

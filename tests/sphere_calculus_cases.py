@@ -122,3 +122,57 @@ def check_shell_gradient_scalar(dealias, Nphi=16, Ntheta=8, Nr=8):
     ug[1] = -2*(y**3+x**2*(y-3*z)-y*z**2)/(r**2*np.sin(theta))
     ug[0] = 2*x*(-3*y+z)/(r*np.sin(theta))
     assert np.allclose(u['g'], ug)
+
+
+def _shell(dealias, Nphi=16, Ntheta=8, Nr=8):
+    c = d3.SphericalCoordinates('phi', 'theta', 'r')
+    d = d3.Distributor((c,), dtype=dtype)
+    b = d3.ShellBasis(c, (Nphi, Ntheta, Nr), radii=(0.5, 3), dealias=(dealias, dealias, dealias), dtype=dtype)
+    phi, theta, r = d.local_grids(b, scales=dealias)
+    x, y, z = c.cartesian(phi, theta, r)
+    return c, d, b, phi, theta, r, x, y, z
+
+
+def check_shell_calculus(dealias):
+    """test_spherical_calculus.py:78-96, 120-131, 175-186, 206-223 with the shell basis: gradient of a gradient, divergence of a
+    gradient, Laplacians of a scalar and of a vector field, against the analytic answers of the reference's tests."""
+    c, d, b, phi, theta, r, x, y, z = _shell(dealias)
+    grad = lambda A: d3.Gradient(A, c)
+    f = d.Field(bases=b)
+    f.preset_scales(dealias)
+    f['g'] = 3*x**2 + 2*y*z
+    T = grad(grad(f)).evaluate()                                         # test_gradient_vector
+    T.change_scales(dealias)
+    Tg = 0 * T['g']
+    Tg[2,2] = (6*x**2+4*y*z)/r**2
+    Tg[2,1] = Tg[1,2] = -2*(y**3+x**2*(y-3*z)-y*z**2)/(r**3*np.sin(theta))
+    Tg[2,0] = Tg[0,2] = 2*x*(z-3*y)/(r**2*np.sin(theta))
+    Tg[1,1] = 6*x**2/(r**2*np.sin(theta)**2) - (6*x**2+4*y*z)/r**2
+    Tg[1,0] = Tg[0,1] = -2*x*(x**2+y**2+3*y*z)/(r**3*np.sin(theta)**2)
+    Tg[0,0] = 6*y**2/(x**2+y**2)
+    assert np.allclose(T['g'], Tg)
+    f = d.Field(bases=b)                                                 # test_divergence_vector
+    f.preset_scales(dealias)
+    f['g'] = x**3 + 2*y**3 + 3*z**3
+    h = d3.Divergence(grad(f)).evaluate()
+    h.change_scales(dealias)
+    assert np.allclose(h['g'], 6*x + 12*y + 18*z)
+    f = d.Field(bases=b)                                                 # test_laplacian_scalar
+    f.preset_scales(dealias)
+    f['g'] = x**4 + 2*y**4 + 3*z**4
+    h = d3.Laplacian(f, c).evaluate()
+    h.change_scales(dealias)
+    assert np.allclose(h['g'], 12*x**2+24*y**2+36*z**2)
+    u = d.VectorField(c, bases=b)                                        # test_laplacian_vector
+    u.preset_scales(dealias)
+    ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
+    u['g'][2] = r**2*st*(2*ct**2*cp-r*ct**3*sp+r**3*cp**3*st**5*sp**3+r*ct*st**2*(cp**3+sp**3))
+    u['g'][1] = r**2*(2*ct**3*cp-r*cp**3*st**4+r**3*ct*cp**3*st**5*sp**3-1/16*r*np.sin(2*theta)**2*(-7*sp+np.sin(3*phi)))
+    u['g'][0] = r**2*sp*(-2*ct**2+r*ct*cp*st**2*sp-r**3*cp**2*st**5*sp**3)
+    v = d3.Laplacian(u, c).evaluate()
+    v.change_scales(dealias)
+    vg = 0 * v['g']
+    vg[2] = 2*(2+3*r*ct)*cp*st+1/2*r**3*st**4*(4*np.sin(2*phi)+np.sin(4*phi))
+    vg[1] = 2*r*(-3*cp*st**2+sp)+1/2*ct*(8*cp+r**3*st**3*(4*np.sin(2*phi)+np.sin(4*phi)))
+    vg[0] = 2*r*ct*cp+2*sp*(-2-r**3*(2+np.cos(2*phi))*st**3*sp)
+    assert np.allclose(v['g'], vg)

@@ -98,3 +98,9 @@ def test_sphere_calculus_implicit(dealias):
 def test_shell_gradient_scalar(dealias):
     import sphere_calculus_cases as S
     S.check_shell_gradient_scalar(dealias)
+
+
+@pytest.mark.parametrize("dealias", [1, 3/2])
+def test_shell_calculus(dealias):
+    import sphere_calculus_cases as S
+    S.check_shell_calculus(dealias)

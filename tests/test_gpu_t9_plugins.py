@@ -70,3 +70,4 @@ def test_reference_sphere_calculus_cases():
         S.check_explicit(dealias)
         S.check_implicit(dealias)
         S.check_shell_gradient_scalar(dealias)
+        S.check_shell_calculus(dealias)
