@@ -167,7 +167,7 @@ class CurvilinearEvaluation:
                 return self._shell_gradient(self.field(e.args[0]), e)          # the kernel path (also used inside time steps)
             if isinstance(e, ops.Interpolate) and e.axis == self.dist.get_basis_axis(shell) + 2 and not e.tensorsig:
                 return self._shell_radial_interpolation(self.field(e.args[0]), e)
-            if isinstance(e, (ops.Gradient, ops.Divergence, ops.Laplacian, ops.Trace, ops.Add, ops.ScalarMul)):
+            if isinstance(e, (ops.Gradient, ops.Divergence, ops.Laplacian, ops.Trace, ops.TransposeComponents, ops.Add, ops.ScalarMul)):
                 return self._shell_linear(e)
             raise NotImplementedError(f"{type(e).__name__} of shell fields in output expressions")
         if isinstance(e, ops.Integrate) and sphere_basis_of(e.args[0]) is not None and shell is None:

@@ -234,6 +234,18 @@ class ShellLowering:
                     M = xi(+1, ell + R - 1) * rops.D(-1, ell + R, n.k)
                 return [(co % nrest, M @ B)]
             return _map(n, fn, k=n.k + 1, rank=n.rank - 1)
+        if isinstance(e, ops.TransposeComponents):
+            # swap of the first two tensor indices: a permutation of the spin components, conjugated with the intertwiners
+            # (reference SphericalTransposeComponents, core/operators.py:1950-2010)
+            n = self.lower(e.args[0], ell)
+            nrest = 3 ** (n.rank - 2)
+            idx = np.arange(9 * nrest).reshape(3, 3, nrest).transpose(1, 0, 2).ravel()
+            P = np.zeros((9 * nrest, 9 * nrest)); P[np.arange(idx.size), idx] = 1
+            Q = self.Q(ell, n.rank)
+            T = Q.T @ P @ Q
+            def fn(co, B):
+                return [(c, T[c, co] * B) for c in range(9 * nrest) if abs(T[c, co]) > 1e-14]
+            return _map(n, fn)
         if isinstance(e, ops.Trace):
             n = self.lower(e.args[0], ell)
             nrest = 3 ** (n.rank - 2)

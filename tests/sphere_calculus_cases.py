@@ -176,3 +176,54 @@ def check_shell_calculus(dealias):
     vg[1] = 2*r*(-3*cp*st**2+sp)+1/2*ct*(8*cp+r**3*st**3*(4*np.sin(2*phi)+np.sin(4*phi)))
     vg[0] = 2*r*ct*cp+2*sp*(-2-r**3*(2+np.cos(2*phi))*st**3*sp)
     assert np.allclose(v['g'], vg)
+
+
+def check_shell_operators(k, dealias, Nphi=8, Ntheta=4, Nr=10):
+    """test_spherical_operators.py:120-262 with the shell basis (radii 0.5, 1.5; fields in the radial basis k): sums of fields in
+    different radial bases (conversion), trace and transpose of a gradient, in both layouts."""
+    c = d3.SphericalCoordinates('phi', 'theta', 'r')
+    d = d3.Distributor((c,), dtype=dtype)
+    b = d3.ShellBasis(c, (Nphi, Ntheta, Nr), radii=(0.5, 1.5), k=k, dealias=(dealias, dealias, dealias), dtype=dtype)
+    phi, theta, r = d.local_grids(b, scales=dealias)
+    x, y, z = c.cartesian(phi, theta, r)
+    ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
+
+    def vector():
+        u = d.VectorField(c, bases=b)
+        u.preset_scales(dealias)
+        u['g'][2] = r**2*st*(2*ct**2*cp-r*ct**3*sp+r**3*cp**3*st**5*sp**3+r*ct*st**2*(cp**3+sp**3))
+        u['g'][1] = r**2*(2*ct**3*cp-r*cp**3*st**4+r**3*ct*cp**3*st**5*sp**3-1/16*r*np.sin(2*theta)**2*(-7*sp+np.sin(3*phi)))
+        u['g'][0] = r**2*sp*(-2*ct**2+r*ct*cp*st**2*sp-r**3*cp**2*st**5*sp**3)
+        return u
+    for layout in ('c', 'g'):
+        f = d.Field(bases=b)                                             # test_convert_scalar
+        f.preset_scales(dealias)
+        f['g'] = 3*x**2 + 2*y*z
+        g = d3.Laplacian(f, c).evaluate()
+        g.change_scales(dealias)
+        f.change_layout(layout); g.change_layout(layout)
+        h = (f + g).evaluate()
+        h.change_scales(dealias); f.change_scales(dealias); g.change_scales(dealias)
+        assert np.allclose(h['g'], f['g'] + g['g'])
+        u = vector()                                                     # test_convert_vector
+        v = d3.Laplacian(u, c).evaluate()
+        v.change_scales(dealias)
+        u.change_layout(layout); v.change_layout(layout)
+        w = (u + v).evaluate()
+        w.change_scales(dealias); u.change_scales(dealias); v.change_scales(dealias)
+        assert np.allclose(w['g'], u['g'] + v['g'])
+        u = vector()                                                     # test_explicit_trace_tensor
+        T = d3.Gradient(u, c).evaluate()
+        T.change_scales(dealias)
+        fg = T['g'][0,0] + T['g'][1,1] + T['g'][2,2]
+        T.change_layout(layout)
+        f = d3.Trace(T).evaluate()
+        f.change_scales(dealias)
+        assert np.allclose(f['g'], fg)
+        T = d3.Gradient(vector(), c).evaluate()                          # test_explicit_transpose_tensor
+        T.change_scales(dealias)
+        Tg = np.transpose(np.copy(T['g']), (1,0,2,3,4))
+        T.change_layout(layout)
+        T = d3.TransposeComponents(T).evaluate()
+        T.change_scales(dealias)
+        assert np.allclose(T['g'], Tg)

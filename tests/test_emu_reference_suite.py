@@ -104,3 +104,10 @@ def test_shell_gradient_scalar(dealias):
 def test_shell_calculus(dealias):
     import sphere_calculus_cases as S
     S.check_shell_calculus(dealias)
+
+
+@pytest.mark.parametrize("k", [0, 1])
+@pytest.mark.parametrize("dealias", [1, 3/2])
+def test_shell_operators(k, dealias):
+    import sphere_calculus_cases as S
+    S.check_shell_operators(k, dealias)

@@ -71,3 +71,5 @@ def test_reference_sphere_calculus_cases():
         S.check_implicit(dealias)
         S.check_shell_gradient_scalar(dealias)
         S.check_shell_calculus(dealias)
+        for k in (0, 1):
+            S.check_shell_operators(k, dealias)
