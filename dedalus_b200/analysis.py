@@ -194,9 +194,9 @@ class CurvilinearEvaluation:
         new.args = [self._with_field_leaves(a) for a in e.args]
         return new
 
-    def _materialize(self, e, g):
-        """Grid values (dealias scales) -> a temporary field on e's bases."""
-        basis = _full_basis(e)
+    def _materialize(self, e, g, basis=None):
+        """Grid values (dealias scales) -> a temporary field on e's bases (or on `basis`: the same grid, another radial basis k)."""
+        basis = basis if basis is not None else _full_basis(e)
         if basis is None or any(b is None for b in e.bases):
             raise NotImplementedError("lower-dimensional results of grid expressions")
         f = _temp_field(e, (basis,))
@@ -325,3 +325,69 @@ class CurvilinearEvaluation:
 
 def evaluate_curvilinear(expr):
     return CurvilinearEvaluation(expr.dist).evaluate(expr)
+
+
+class GenericCurvilinearRHS:
+    """Right-hand sides of sphere / shell problems that the fused plans (sphere.SphereRHSPlan, shell_ivp.ShellRHSPlan) do not cover --
+    grid functions, forcings, fields that are not problem variables, products with radial profiles, operators applied to products:
+    every equation's F is evaluated with the expression evaluator above (one field per equation), converted to the equation's
+    radial basis (shell: E^dk along r, reference ConvertShell, core/basis.py:3868-3872) and copied into the equation arena.  Same
+    interface as the fused plans; slower (one transform chain per node), used only when they decline an equation."""
+
+    def __init__(self, solver):
+        from .shell import shell_basis_of
+        self.solver = solver
+        self.dist = solver.dist
+        self.eval = CurvilinearEvaluation(solver.dist)
+        self.entries = []                 # (equation index, expression, conversion matrix on the device or None)
+        self.static = []
+        problem = solver.problem
+        for ie, eq in enumerate(problem.equations):
+            rhs = eq['RHS']
+            if not isinstance(rhs, ops.Operand):
+                if rhs != 0:
+                    self._constant(ie, eq, float(rhs))
+                continue
+            if any(b is None for b in eq['bases']):
+                raise NotImplementedError("field right-hand sides of lower-dimensional equations on curvilinear domains")
+            self.entries.append([ie, rhs, None, shell_basis_of(eq['LHS'])])
+
+    def _constant(self, ie, eq, value):
+        from .sphere import sphere_basis_of
+        from .shell import shell_basis_of
+        if eq['tensorsig']:
+            raise NotImplementedError("nonzero constant right-hand side of a tensor equation")
+        off = self.solver.eq_arena.offsets[ie]
+        shell, sphere = shell_basis_of(eq['LHS']), sphere_basis_of(eq['LHS'])
+        basis = shell.sphere_basis if shell is not None else sphere
+        if basis is not None and basis.local_pairs(self.dist)[0] != 0:
+            return
+        from .shell import ShellBasis
+        if all(b is None for b in eq['bases']):
+            self.static.append((off, value))
+        elif not isinstance(eq['bases'][-1], ShellBasis) or len(eq['bases']) == 2:
+            self.static.append((off, value * np.sqrt(2)))                # a field on a sphere: the l = 0 mode, 1 / constant_mode_value
+        else:
+            raise NotImplementedError("nonzero constant right-hand side of a shell-interior equation")
+
+    def set_static(self, eq_t):
+        eq_t.zero_()
+        for off, val in self.static:
+            eq_t[off] = val
+
+    def evaluate(self, eq_t):
+        import torch
+        from .sphere import sphere_basis_of
+        arena = self.solver.eq_arena
+        for ie, rhs, _, eq_shell in self.entries:
+            # F on the dealiased grid, then ONE forward transform in the equation's own basis: the reference converts F to the
+            # equation's bases while it is on the grid (a copy), so no intermediate truncation in the expression's basis happens
+            g = self.eval.grid(rhs)
+            eq = self.solver.problem.equations[ie]
+            basis = eq_shell if eq_shell is not None else sphere_basis_of(eq['LHS'])
+            if not torch.is_tensor(g):
+                raise NotImplementedError("numeric right-hand side expressions")
+            F = self.eval._materialize(rhs, g, basis=basis)
+            F.change_layout('c')
+            c = F.device_data().contiguous()
+            eq_t[arena.offsets[ie]:arena.offsets[ie] + c.numel()].view(c.shape).copy_(c)

@@ -817,12 +817,11 @@ class ShellRHSPlan:
                            self.term_ptr.data_ptr(), self.coef.data_ptr(), self.fac_ptr.data_ptr(), self.fac.data_ptr(), self.nfac, current_stream())
         p0 = 0
         for p in self.products:
+            # straight into the EQUATION's radial basis: the reference converts F to the equation's bases while it is still on the
+            # grid (a copy, core/operators.py:1628-1638), so the one forward transform is the one of basis k_eq -- transforming in the
+            # product's basis first and converting with E afterwards truncates differently (visible once |u| is not tiny)
             with Timed(prof, "shell_forward", 8 * p['ncomp'] * (self.npoints + Nc0 * Nc1 * Nr)):
-                c = shell_grid_to_components(self._basis_k(p['k']), self.g_out[p0:p0 + p['ncomp']].contiguous(), p['rank'], self.dist)
+                c = shell_grid_to_components(self._basis_k(p['k_eq']), self.g_out[p0:p0 + p['ncomp']].contiguous(), p['rank'], self.dist)
             off = solver.eq_arena.offsets[p['eq']]
-            dst = eq_t[off:off + c.numel()].view(c.shape)
-            if p['k_eq'] != p['k']:
-                self._mmt(self.convert[(p['k'], p['k_eq'])], c, dst)
-            else:
-                dst.copy_(c)
+            eq_t[off:off + c.numel()].view(c.shape).copy_(c)
             p0 += p['ncomp']

@@ -375,12 +375,21 @@ class InitialValueSolver:
         for v, off, (tsh, shp) in zip(self.state, self.var_arena.offsets, self.var_arena.shapes):
             n = int(np.prod(tsh, dtype=int)) * int(np.prod(shp, dtype=int))
             self.state_views.append(self.state_t[off:off + n].view(tuple(tsh) + tuple(shp)))
-        if self.shell:
-            from .shell_ivp import ShellRHSPlan
-            self.rhs_plan = ShellRHSPlan(self)
-        elif self.curvilinear:
-            from .sphere import SphereRHSPlan
-            self.rhs_plan = SphereRHSPlan(self)
+        if self.curvilinear:
+            # the fused plans cover products of state fields and their separable derivatives; anything else (grid functions,
+            # forcings, radial profiles, operators of products) goes through the general evaluator, equation by equation
+            try:
+                if self.shell:
+                    from .shell_ivp import ShellRHSPlan
+                    self.rhs_plan = ShellRHSPlan(self)
+                else:
+                    from .sphere import SphereRHSPlan
+                    self.rhs_plan = SphereRHSPlan(self)
+            except NotImplementedError:
+                if self.dist.size > 1:
+                    raise
+                from .analysis import GenericCurvilinearRHS
+                self.rhs_plan = GenericCurvilinearRHS(self)
         elif self.complex:
             from .complex_path import ComplexRHSPlan
             self.rhs_plan = ComplexRHSPlan(self)

@@ -41,3 +41,7 @@ def test_dense_kernels_against_numpy(smem, monkeypatch):
 
 def test_shell_output_tasks_match_reference(golden):
     SC.check_shell_tasks(golden("shell_tasks.npz"))
+
+
+def test_shell_convection_with_strong_flow_matches_reference(golden):
+    SC.check_shell_convection_strong(golden("shell_strong.npz"))

@@ -60,3 +60,8 @@ def test_shell_output_tasks_match_reference(golden):
     """Tasks and flow property of the stock shell-convection script (radial / azimuthal interpolation of a flux, np.sqrt(u@u)/nu)."""
     import shell_cases as SC
     SC.check_shell_tasks(golden("shell_tasks.npz"))
+
+
+def test_shell_convection_with_strong_flow_matches_reference(golden):
+    import shell_cases as SC
+    SC.check_shell_convection_strong(golden("shell_strong.npz"))
