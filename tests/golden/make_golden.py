@@ -848,7 +848,7 @@ if __name__ == "__main__" and "shell_tasks" in sys.argv[1:]:
 # Boundary conditions with data: lower-dimensional equations whose right-hand side is a field
 # ----------------------------------------------------------------------------------------------------------
 sys.path.insert(0, str(HERE.parent))
-from bc_cases import rb2d_bc_data, rb2d_background, rb2d_ncc, rb2d_conservative
+from bc_cases import rb2d_bc_data, rb2d_background, rb2d_ncc, rb2d_conservative, rb2d_strong
 
 
 def gen_bc_data():
@@ -857,6 +857,9 @@ def gen_bc_data():
     out.update({"bg_" + k: v['c'].copy() for k, v in rb2d_background(d3).items()})
     out.update({"ncc_" + k: v['c'].copy() for k, v in rb2d_ncc(d3).items()})
     out.update({"cons_" + k: v['c'].copy() for k, v in rb2d_conservative(d3).items()})
+    strong, init = rb2d_strong(d3)
+    out.update({"strong_" + k: v['c'].copy() for k, v in strong.items()})
+    out.update({"strong_" + k: v for k, v in init.items()})
     np.savez_compressed(HERE / "bc_data.npz", **out)
     print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
 

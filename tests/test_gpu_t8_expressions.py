@@ -41,3 +41,8 @@ def test_field_filters_norms_and_global_data(golden):
 def test_cartesian_lbvp_poisson_matches_reference(golden):
     import bc_cases, dedalus_b200 as d3
     bc_cases.check_poisson_lbvp(d3, golden("stock_scripts.npz"))
+
+
+def test_rayleigh_benard_with_strong_flow_matches_reference(golden):
+    import bc_cases, dedalus_b200 as d3
+    bc_cases.check_strong(d3, golden("bc_data.npz"))

@@ -106,3 +106,15 @@ def test_sphere_oracle_matches_reference(golden, tag, scheme):
     for name in ("u", "h"):
         ref = g[f"{tag}_{name}1"]
         assert np.allclose(out[name], ref, rtol=1e-9, atol=1e-13 * np.abs(ref).max()), name
+
+
+def test_rb_oracle_with_strong_flow_matches_reference(golden):
+    """The Rayleigh-Benard oracle against the reference with O(1) velocities (advection as large as the linear terms): the
+    noise-started fixtures above keep |u| << |b| and would not see a wrong order of truncations in the nonlinear terms.  The bench's
+    parity gate and the GPU tests at sizes without fixtures lean on this oracle at O(1) velocity."""
+    from oracle import rb_oracle
+    g = golden("bc_data.npz")
+    ref = rb_oracle.run(dim=2, Nh=16, Nz=16, Ra=2e5, b0_c=g["strong_b0"], steps=5, dt=0.01, u0_c=g["strong_u0"])
+    for name in ("p", "b", "u"):
+        want = g["strong_" + name]
+        assert np.allclose(ref[name], want, rtol=1e-8, atol=1e-11 * np.abs(want).max()), (name, np.abs(ref[name] - want).max())
