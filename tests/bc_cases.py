@@ -238,6 +238,61 @@ def rb2d_strong(d3mod, Nx=16, Nz=16, steps=5, tstep=0.01):
     return dict(p=p, b=b, u=u), init
 
 
+def rb3d_strong(d3mod, N=8, steps=3, tstep=0.01):
+    """The 3-D problem of the benchmark (Fourier x Fourier x Chebyshev Rayleigh-Benard) started with an O(1)
+    velocity field."""
+    d3 = d3mod
+    Lx, Ly, Lz = 4, 4, 1
+    Rayleigh, Prandtl = 1e6, 1
+    coords = d3.CartesianCoordinates('x', 'y', 'z')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    xbasis = d3.RealFourier(coords['x'], size=N, bounds=(0, Lx), dealias=3/2)
+    ybasis = d3.RealFourier(coords['y'], size=N, bounds=(0, Ly), dealias=3/2)
+    zbasis = d3.ChebyshevT(coords['z'], size=N, bounds=(0, Lz), dealias=3/2)
+    bases = (xbasis, ybasis, zbasis)
+    p = dist.Field(name='p', bases=bases); b = dist.Field(name='b', bases=bases)
+    u = dist.VectorField(coords, name='u', bases=bases)
+    tau_p = dist.Field(name='tau_p')
+    tau_b1 = dist.Field(name='tau_b1', bases=(xbasis, ybasis)); tau_b2 = dist.Field(name='tau_b2', bases=(xbasis, ybasis))
+    tau_u1 = dist.VectorField(coords, name='tau_u1', bases=(xbasis, ybasis)); tau_u2 = dist.VectorField(coords, name='tau_u2', bases=(xbasis, ybasis))
+    kappa = (Rayleigh * Prandtl)**(-1/2); nu = (Rayleigh / Prandtl)**(-1/2)
+    x, y, z = dist.local_grids(xbasis, ybasis, zbasis)
+    ex, ey, ez = coords.unit_vector_fields(dist)
+    lift_basis = zbasis.derivative_basis(1)
+    lift = lambda A: d3.Lift(A, lift_basis, -1)
+    grad_u = d3.grad(u) + ez*lift(tau_u1)
+    grad_b = d3.grad(b) + ez*lift(tau_b1)
+    problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
+    problem.add_equation("trace(grad_u) + tau_p = 0")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*ez + lift(tau_u2) = - u@grad(u)")
+    problem.add_equation("b(z=0) = Lz")
+    problem.add_equation("u(z=0) = 0")
+    problem.add_equation("b(z=Lz) = 0")
+    problem.add_equation("u(z=Lz) = 0")
+    problem.add_equation("integ(p) = 0")
+    solver = problem.build_solver(d3.RK222)
+    b.fill_random('g', seed=42, distribution='normal', scale=0.3)
+    b.low_pass_filter(scales=0.5)
+    b['g'] *= z * (Lz - z)
+    b['g'] += Lz - z
+    u.fill_random('g', seed=43, distribution='normal', scale=0.8)
+    u.low_pass_filter(scales=0.5)
+    u['g'] *= z * (Lz - z)
+    init = dict(b0=np.array(b['c']), u0=np.array(u['c']))
+    for _ in range(steps):
+        solver.step(tstep)
+    return dict(p=p, b=b, u=u), init
+
+
+def check_strong_3d(d3, g):
+    res, init = rb3d_strong(d3)
+    for name, f in res.items():
+        ref = g["strong3d_" + name]
+        got = f['c']
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-11 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
+
+
 def check_strong(d3, g):
     res, init = rb2d_strong(d3)
     for name, f in res.items():

@@ -46,3 +46,8 @@ def test_cartesian_lbvp_poisson_matches_reference(golden):
 def test_rayleigh_benard_with_strong_flow_matches_reference(golden):
     import bc_cases, dedalus_b200 as d3
     bc_cases.check_strong(d3, golden("bc_data.npz"))
+
+
+def test_3d_rayleigh_benard_with_strong_flow_matches_reference(golden):
+    import bc_cases, dedalus_b200 as d3
+    bc_cases.check_strong_3d(d3, golden("bc_data.npz"))

@@ -118,3 +118,13 @@ def test_rb_oracle_with_strong_flow_matches_reference(golden):
     for name in ("p", "b", "u"):
         want = g["strong_" + name]
         assert np.allclose(ref[name], want, rtol=1e-8, atol=1e-11 * np.abs(want).max()), (name, np.abs(ref[name] - want).max())
+
+
+def test_rb3d_oracle_with_strong_flow_matches_reference(golden):
+    """Same in 3-D (the benchmark's problem, 8^3)."""
+    from oracle import rb_oracle
+    g = golden("bc_data.npz")
+    ref = rb_oracle.run(dim=3, Nh=8, Nz=8, Ra=1e6, b0_c=g["strong3d_b0"], steps=3, dt=0.01, u0_c=g["strong3d_u0"])
+    for name in ("p", "b", "u"):
+        want = g["strong3d_" + name]
+        assert np.allclose(ref[name], want, rtol=1e-8, atol=1e-11 * np.abs(want).max()), (name, np.abs(ref[name] - want).max())
