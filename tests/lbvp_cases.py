@@ -64,3 +64,22 @@ def check_poisson_jacobi(a, b, N=32):
     solver = problem.build_solver()
     solver.solve()
     assert np.allclose(u['g'], u_true)
+
+
+def check_solve_jacobi_ncc(a0, b0, k_ncc, N=16, dealias=3/2):
+    """dedalus/tests/test_cartesian_ncc.py:115-135 (k_arg = 0): solve f(x) u(x) = f(x) g(x) with a full-spectrum random coefficient f
+    on the left-hand side (the NCC matrix of the coupled Jacobi axis) and the pseudospectral product on the right."""
+    c = d3.Coordinate('x')
+    d = d3.Distributor(c, dtype=dtype)
+    b = d3.Jacobi(c, size=N, a=a0, b=b0, bounds=(0, 1), dealias=dealias)
+    b_ncc = b.clone_with(a=a0+k_ncc, b=b0+k_ncc)
+    f = d.Field(bases=b_ncc)
+    g = d.Field(bases=b)
+    u = d.Field(bases=b)
+    f.fill_random('g')
+    g.fill_random('g')
+    problem = d3.LBVP([u])
+    problem.add_equation((f*u, f*g))
+    solver = problem.build_solver()
+    solver.solve()
+    assert np.allclose(u['c'], g['c'])

@@ -111,3 +111,9 @@ def test_shell_calculus(dealias):
 def test_shell_operators(k, dealias):
     import sphere_calculus_cases as S
     S.check_shell_operators(k, dealias)
+
+
+@pytest.mark.parametrize("a0,b0", [(-1/2, -1/2), (0, 0)])
+@pytest.mark.parametrize("k_ncc", [0, 1])
+def test_solve_jacobi_ncc(a0, b0, k_ncc):
+    L.check_solve_jacobi_ncc(a0, b0, k_ncc)

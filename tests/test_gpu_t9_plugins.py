@@ -20,6 +20,9 @@ def test_reference_lbvp_cases():
     L.check_poisson_fourier()
     L.check_poisson_jacobi(-1/2, -1/2)
     L.check_poisson_jacobi(0, 0)
+    for a0, b0 in ((-1/2, -1/2), (0, 0)):
+        for k_ncc in (0, 1):
+            L.check_solve_jacobi_ncc(a0, b0, k_ncc)            # test_cartesian_ncc.py:115-135
 
 
 def test_reference_ufunc_cases():
