@@ -848,7 +848,7 @@ if __name__ == "__main__" and "shell_tasks" in sys.argv[1:]:
 # Boundary conditions with data: lower-dimensional equations whose right-hand side is a field
 # ----------------------------------------------------------------------------------------------------------
 sys.path.insert(0, str(HERE.parent))
-from bc_cases import rb2d_bc_data, rb2d_background, rb2d_ncc, rb2d_conservative, rb2d_strong, rb3d_strong
+from bc_cases import rb2d_bc_data, rb2d_background, rb2d_ncc, rb2d_conservative, rb2d_strong, rb3d_strong, shallow_water_forced
 
 
 def gen_bc_data():
@@ -860,6 +860,7 @@ def gen_bc_data():
     strong, init = rb2d_strong(d3)
     out.update({"strong_" + k: v['c'].copy() for k, v in strong.items()})
     out.update({"strong_" + k: v for k, v in init.items()})
+    out.update({"swf_" + k: v['c'].copy() for k, v in shallow_water_forced(d3)[0].items()})
     strong, init = rb3d_strong(d3)
     out.update({"strong3d_" + k: v['c'].copy() for k, v in strong.items()})
     out.update({"strong3d_" + k: v for k, v in init.items()})

@@ -51,3 +51,8 @@ def test_rayleigh_benard_with_strong_flow_matches_reference(golden):
 def test_3d_rayleigh_benard_with_strong_flow_matches_reference(golden):
     import bc_cases, dedalus_b200 as d3
     bc_cases.check_strong_3d(d3, golden("bc_data.npz"))
+
+
+def test_sphere_right_hand_side_with_grid_function_and_forcing(golden):
+    import bc_cases, dedalus_b200 as d3
+    bc_cases.check_shallow_water_forced(d3, golden("bc_data.npz"))
