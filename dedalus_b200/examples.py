@@ -135,7 +135,7 @@ def complex_ginzburg_landau_initial_condition(u, bases):
     u['g'] *= z * (1 - z)
 
 
-def shell_convection(Nphi=256, Ntheta=128, Nr=128, Ri=14, Ro=15, Rayleigh=3500, Prandtl=1, dealias=3/2, dtype=np.float64):
+def shell_convection(Nphi=256, Ntheta=128, Nr=128, Ri=14, Ro=15, Rayleigh=3500, Prandtl=1, dealias=3/2, dtype=np.float64, rhs_b_extra=None):
     """Boussinesq convection in a spherical shell, BASELINE config 5 (examples/ivp_shell_convection/shell_convection.py:33-83)."""
     coords = d3.SphericalCoordinates('phi', 'theta', 'r')
     dist = d3.Distributor(coords, dtype=dtype)
@@ -162,7 +162,7 @@ def shell_convection(Nphi=256, Ntheta=128, Nr=128, Ri=14, Ro=15, Rayleigh=3500, 
     grad_b = d3.grad(b) + rvec*lift(tau_b1)
     problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
     problem.add_equation("trace(grad_u) + tau_p = 0")
-    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)" + (" + " + rhs_b_extra if rhs_b_extra else ""))
     problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*er + lift(tau_u2) = - u@grad(u)")
     problem.add_equation("b(r=Ri) = 1")
     problem.add_equation("u(r=Ri) = 0")

@@ -612,7 +612,7 @@ def shell_convection(shape, steps, scheme="SBDF2", tstep=0.05, dump=()):
     return out
 
 
-def shell_convection_strong(shape=(16, 8, 6), steps=3, tstep=0.02):
+def shell_convection_strong(shape=(16, 8, 6), steps=3, tstep=0.02, forced=False):
     """Shell convection started from the state of tests/golden/shell_tasks.npz with the velocity amplified to O(0.1): the advection
     terms are then as large as the linear ones, which exposes the order of truncations in the right-hand side (the fixtures above
     start from noise and keep |u| ~ 1e-6 |b|)."""
@@ -639,7 +639,10 @@ def shell_convection_strong(shape=(16, 8, 6), steps=3, tstep=0.02):
     grad_b = d3.grad(b) + rvec*lift(tau_b1)
     problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
     problem.add_equation("trace(grad_u) + tau_p = 0")
-    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    if forced:
+        problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b) + 0.05*sin(3*b)")
+    else:
+        problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
     problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*er + lift(tau_u2) = - u@grad(u)")
     problem.add_equation("b(r=Ri) = 1"); problem.add_equation("u(r=Ri) = 0")
     problem.add_equation("b(r=Ro) = 0"); problem.add_equation("u(r=Ro) = 0")
@@ -656,6 +659,7 @@ def shell_convection_strong(shape=(16, 8, 6), steps=3, tstep=0.02):
 
 def gen_shell_strong():
     out = {f"strong_{k}": v for k, v in shell_convection_strong().items()}
+    out.update({f"forced_{k}": v for k, v in shell_convection_strong(forced=True).items() if k.endswith("1")})
     np.savez_compressed(HERE / "shell_strong.npz", **out)
     print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
 

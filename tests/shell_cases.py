@@ -197,3 +197,20 @@ def check_shell_convection_strong(g):
         ref = g[f"strong_{name}1"]
         got = sc[name]['c']
         assert np.allclose(got, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
+
+
+def check_shell_convection_forced(g):
+    """The same start with a grid function on the right-hand side of the buoyancy equation (0.05 sin(3 b)): outside the fused shell
+    plan, carried by the general curvilinear evaluator."""
+    from dedalus_b200 import examples
+    Nphi, Ntheta, Nr, steps, dt = g["strong_meta"]
+    sc = examples.shell_convection(int(Nphi), int(Ntheta), int(Nr), rhs_b_extra="0.05*sin(3*b)")
+    solver = sc['problem'].build_solver(d3.SBDF2)
+    sc['b']['c'] = g["strong_b0"]; sc['u']['c'] = g["strong_u0"]
+    for _ in range(int(steps)):
+        solver.step(float(dt))
+    assert type(solver.rhs_plan).__name__ == "GenericCurvilinearRHS"
+    for name in ('p', 'b', 'u'):
+        ref = g[f"forced_{name}1"]
+        got = sc[name]['c']
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())

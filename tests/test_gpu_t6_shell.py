@@ -65,3 +65,8 @@ def test_shell_output_tasks_match_reference(golden):
 def test_shell_convection_with_strong_flow_matches_reference(golden):
     import shell_cases as SC
     SC.check_shell_convection_strong(golden("shell_strong.npz"))
+
+
+def test_shell_convection_with_grid_function_forcing_matches_reference(golden):
+    import shell_cases as SC
+    SC.check_shell_convection_forced(golden("shell_strong.npz"))
