@@ -238,14 +238,14 @@ def rb2d_strong(d3mod, Nx=16, Nz=16, steps=5, tstep=0.01):
     return dict(p=p, b=b, u=u), init
 
 
-def rb3d_strong(d3mod, N=8, steps=3, tstep=0.01):
+def rb3d_strong(d3mod, N=8, steps=3, tstep=0.01, mesh=None):
     """The 3-D problem of the benchmark (Fourier x Fourier x Chebyshev Rayleigh-Benard) started with an O(1)
     velocity field."""
     d3 = d3mod
     Lx, Ly, Lz = 4, 4, 1
     Rayleigh, Prandtl = 1e6, 1
     coords = d3.CartesianCoordinates('x', 'y', 'z')
-    dist = d3.Distributor(coords, dtype=np.float64)
+    dist = d3.Distributor(coords, dtype=np.float64, mesh=mesh)
     xbasis = d3.RealFourier(coords['x'], size=N, bounds=(0, Lx), dealias=3/2)
     ybasis = d3.RealFourier(coords['y'], size=N, bounds=(0, Ly), dealias=3/2)
     zbasis = d3.ChebyshevT(coords['z'], size=N, bounds=(0, Lz), dealias=3/2)
