@@ -746,16 +746,10 @@ class ShellRHSPlan:
         self.nfac = len(fac)
         self.g_in = torch.zeros((self.n_g,) + self.gshape, dtype=torch.float64, device=dev)
         self.g_out = torch.zeros((self.n_p,) + self.gshape, dtype=torch.float64, device=dev)
-        # ---- conversions product basis -> equation basis (sign folded in: F enters as +F, the minus signs sit in the polynomial)
-        ro = self.rops
-        dense = lambda M: torch.from_numpy(np.ascontiguousarray(M.toarray())).to(dev)
-        self.convert = {}
+        # the products are transformed straight into their equation's radial basis (evaluate): k_eq must not be below the product's
         for p in self.products:
-            key = (p['k'], p['k_eq'])
-            if key not in self.convert and p['k_eq'] != p['k']:
-                if p['k_eq'] < p['k']:
-                    raise NotImplementedError("RHS in a higher radial basis than its equation")
-                self.convert[key] = dense(ro.E(p['k'], p['k_eq'] - p['k']))
+            if p['k_eq'] < p['k']:
+                raise NotImplementedError("RHS in a higher radial basis than its equation")
         self.bases_k = {}
 
     def _basis_k(self, k):
