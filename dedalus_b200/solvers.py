@@ -645,8 +645,8 @@ class LinearBoundaryValueSolver(InitialValueSolver):
 
     def __init__(self, problem, **kw):
         super().__init__(problem, _DirectSolve, **kw)
-        if self.shell or self.complex:
-            raise NotImplementedError("LBVPs are built for real Cartesian and sphere (S2) problems in this build")
+        if self.complex:
+            raise NotImplementedError("LBVPs are built for real-dtype problems in this build")
 
     def step(self, dt):
         raise TypeError("boundary value solvers have no time step; call solve()")
@@ -655,7 +655,11 @@ class LinearBoundaryValueSolver(InitialValueSolver):
         if not self._device_ready:
             self._init_device()
         if self.bset is None or rebuild_matrices:
-            if self.curvilinear:
+            if self.shell:
+                from .shell_ivp import ShellSystems
+                self.bset = ShellSystems(self, 4, 1)          # the per-l dense systems with M = 0
+                self.total_modes = self.bset.total_modes
+            elif self.curvilinear:
                 from .sphere import SphereSystems
                 self.bset = SphereSystems(self, 4, 1)         # slots: 0 F, 1 X, 2 / 3 probe products
                 self.total_modes = self.bset.total_modes

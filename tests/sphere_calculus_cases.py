@@ -227,3 +227,40 @@ def check_shell_operators(k, dealias, Nphi=8, Ntheta=4, Nr=10):
         T = d3.TransposeComponents(T).evaluate()
         T.change_scales(dealias)
         assert np.allclose(T['g'], Tg)
+
+
+def check_shell_implicit(k, dealias, Nphi=8, Ntheta=4, Nr=10):
+    """test_spherical_operators.py:191-208 and 262-283 with the shell basis: LBVPs trace(I*f) = 3 g with a radial-basis identity
+    tensor, and transpose(Tt) = T for the gradient of a vector field."""
+    c = d3.SphericalCoordinates('phi', 'theta', 'r')
+    d = d3.Distributor((c,), dtype=dtype)
+    b = d3.ShellBasis(c, (Nphi, Ntheta, Nr), radii=(0.5, 1.5), k=k, dealias=(dealias, dealias, dealias), dtype=dtype)
+    phi, theta, r = d.local_grids(b, scales=dealias)
+    x, y, z = c.cartesian(phi, theta, r)
+    f = d.Field(bases=b)
+    g = d.Field(bases=b)
+    g.preset_scales(dealias)
+    g['g'] = 3*x**2 + 2*y*z
+    I = d.TensorField((c, c), bases=b.radial_basis)
+    I['g'][0,0] = I['g'][1,1] = I['g'][2,2] = 1
+    problem = d3.LBVP([f])
+    problem.add_equation((d3.Trace(I*f), 3*g))
+    solver = problem.build_solver()
+    solver.solve()
+    assert np.allclose(f['c'], g['c'])
+    ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
+    u = d.VectorField(c, bases=b)
+    u.preset_scales(dealias)
+    u['g'][2] = r**2*st*(2*ct**2*cp-r*ct**3*sp+r**3*cp**3*st**5*sp**3+r*ct*st**2*(cp**3+sp**3))
+    u['g'][1] = r**2*(2*ct**3*cp-r*cp**3*st**4+r**3*ct*cp**3*st**5*sp**3-1/16*r*np.sin(2*theta)**2*(-7*sp+np.sin(3*phi)))
+    u['g'][0] = r**2*sp*(-2*ct**2+r*ct*cp*st**2*sp-r**3*cp**2*st**5*sp**3)
+    T = d3.Gradient(u, c).evaluate()
+    T.change_scales(dealias)
+    Ttg = np.transpose(np.copy(T['g']), (1,0,2,3,4))
+    Tt = d.TensorField((c, c), bases=T.unique_bases())
+    problem = d3.LBVP([Tt])
+    problem.add_equation((d3.TransposeComponents(Tt), T))
+    solver = problem.build_solver()
+    solver.solve()
+    Tt.change_scales(dealias)
+    assert np.allclose(Tt['g'], Ttg)
