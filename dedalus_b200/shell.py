@@ -328,11 +328,11 @@ class ShellRadialBasis(Basis):
 
 
 def shell_basis_of(field_or_bases):
+    """The shell basis of a field or expression.  The per-axis bases of a product with a radial-basis coefficient differ in k along the
+    radial axis only (k adds there); the entry of the radial axis -- the largest k -- is the basis of the whole."""
     bases = getattr(field_or_bases, 'bases', field_or_bases)
-    for b in bases:
-        if isinstance(b, ShellBasis):
-            return b
-    return None
+    found = [b for b in bases if isinstance(b, ShellBasis)]
+    return max(found, key=lambda b: b.k) if found else None
 
 
 def _spin_groups(spins):

@@ -119,7 +119,7 @@ def test_solve_jacobi_ncc(a0, b0, k_ncc):
     L.check_solve_jacobi_ncc(a0, b0, k_ncc)
 
 
-def test_shell_implicit_trace_and_transpose():
-    """Shell LBVPs (k = 0 unknowns; fields in a k = 1 radial basis as unknowns are outside this build)."""
+@pytest.mark.parametrize("k", [0, 1])
+def test_shell_implicit_trace_and_transpose(k):
     import sphere_calculus_cases as S
-    S.check_shell_implicit(0, 3/2)
+    S.check_shell_implicit(k, 3/2)

@@ -76,4 +76,5 @@ def test_reference_sphere_calculus_cases():
         S.check_shell_calculus(dealias)
         for k in (0, 1):
             S.check_shell_operators(k, dealias)
-        S.check_shell_implicit(0, dealias)
+        for k in (0, 1):
+            S.check_shell_implicit(k, dealias)
