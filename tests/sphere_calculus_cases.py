@@ -264,3 +264,49 @@ def check_shell_implicit(k, dealias, Nphi=8, Ntheta=4, Nr=10):
     solver.solve()
     Tt.change_scales(dealias)
     assert np.allclose(Tt['g'], Ttg)
+
+
+def check_shell_arithmetic(dealias, Nphi=16, Ntheta=8, Nr=8):
+    """test_spherical_arithmetic.py:111-250 with the shell basis, real dtype: dot products (vector.vector, tensor.vector), products
+    with numbers and tensor products up to rank 4, against numpy on the grid values."""
+    c = d3.SphericalCoordinates('phi', 'theta', 'r')
+    d = d3.Distributor((c,), dtype=dtype)
+    b = d3.ShellBasis(c, (Nphi, Ntheta, Nr), radii=(0.5, 3), dealias=(dealias, dealias, dealias), dtype=dtype)
+    phi, theta, r = d.local_grids(b, scales=dealias)
+    x, y, z = c.cartesian(phi, theta, r)
+
+    def at(f):
+        f.change_scales(dealias)
+        return np.array(f['g'])
+    f = d.Field(bases=b); f.preset_scales(dealias); f['g'] = z
+    ez = d3.Gradient(f, c).evaluate()
+    u = d.VectorField(c, bases=b); u.preset_scales(dealias)
+    u['g'][2] = (6*x**2+4*y*z)/r
+    u['g'][1] = -2*(y**3+x**2*(y-3*z)-y*z**2)/(r**2*np.sin(theta))
+    u['g'][0] = 2*x*(-3*y+z)/(r*np.sin(theta))
+    h = d3.DotProduct(ez, u).evaluate()                                  # test_dot_product_vector_vector
+    assert np.allclose(at(h), np.sum(at(ez)*at(u), axis=0))
+    T = d.TensorField((c, c), bases=b); T.preset_scales(dealias)
+    T['g'][2,2] = (6*x**2+4*y*z)/r**2
+    T['g'][2,1] = T['g'][1,2] = -2*(y**3+x**2*(y-3*z)-y*z**2)/(r**3*np.sin(theta))
+    T['g'][2,0] = T['g'][0,2] = 2*x*(z-3*y)/(r**2*np.sin(theta))
+    T['g'][1,1] = 6*x**2/(r**2*np.sin(theta)**2) - (6*x**2+4*y*z)/r**2
+    T['g'][1,0] = T['g'][0,1] = -2*x*(x**2+y**2+3*y*z)/(r**3*np.sin(theta)**2)
+    T['g'][0,0] = 6*y**2/(x**2+y**2)
+    v = d3.DotProduct(T, u).evaluate()                                   # test_dot_product_tensor_vector
+    assert np.allclose(at(v), np.sum(at(T)*at(u)[:,None,:,:,:], axis=0))
+    f = d.Field(bases=b); f.preset_scales(dealias); f['g'] = x**3 + 2*y**3 + 3*z**3
+    hg = x**3 + 2*y**3 + 3*z**3
+    assert np.allclose(at((2 * f).evaluate()), 2*hg)                     # test_multiply_number_scalar
+    assert np.allclose(at((f * 2).evaluate()), 2*hg)                     # test_multiply_scalar_number
+    assert np.allclose(at((f * f).evaluate()), hg**2)                    # test_multiply_scalar_scalar
+    u = d3.Gradient(f, c).evaluate()
+    v = (f * u).evaluate()                                               # test_multiply_scalar_vector
+    assert np.allclose(at(v), at(f)[None,...]*at(u))
+    Tt = (u * u).evaluate()                                              # test_multiply_vector_vector
+    assert np.allclose(at(Tt), at(u)[None,...] * at(u)[:,None,...])
+    G = d3.Gradient(u, c).evaluate()
+    Q = (u * G).evaluate()                                               # test_multiply_vector_tensor
+    assert np.allclose(at(Q), at(u)[:,None,None,...] * at(G)[None,...])
+    Q = (G * G).evaluate()                                               # test_multiply_tensor_tensor
+    assert np.allclose(at(Q), at(G)[:,:,None,None,...] * at(G)[None,None,...])

@@ -123,3 +123,9 @@ def test_solve_jacobi_ncc(a0, b0, k_ncc):
 def test_shell_implicit_trace_and_transpose(k):
     import sphere_calculus_cases as S
     S.check_shell_implicit(k, 3/2)
+
+
+def test_shell_arithmetic():
+    """At the reference's sizes (8, 10, 6): Ntheta > Nphi / 2, the folded packing with shift > 0."""
+    import sphere_calculus_cases as S
+    S.check_shell_arithmetic(3/2, Nphi=8, Ntheta=10, Nr=6)

@@ -78,3 +78,4 @@ def test_reference_sphere_calculus_cases():
             S.check_shell_operators(k, dealias)
         for k in (0, 1):
             S.check_shell_implicit(k, dealias)
+        S.check_shell_arithmetic(dealias, Nphi=8, Ntheta=10, Nr=6)
