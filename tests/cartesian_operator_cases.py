@@ -27,67 +27,61 @@ def build(kind, N=16, dealias=1):
     return c, d, b, r
 
 
+def _random(dist, tensorsig, bases, layout=None):
+    field = dist.TensorField(tensorsig, bases=bases) if tensorsig else dist.Field(bases=bases)
+    field.fill_random(layout='g')
+    if layout:
+        field.change_layout(layout)
+    return field
+
+
+def _solve(unknowns, lhs, rhs, **names):
+    bvp = d3.LBVP(unknowns, namespace=names)
+    bvp.add_equation(f"{lhs} = {rhs}")
+    bvp.build_solver().solve()
+
+
 def check_skew(kind):
-    for layout in ('c', 'g'):                                            # test_skew_explicit
-        c, d, b, r = build(kind)
-        f = d.VectorField(c, bases=b)
-        f.fill_random(layout='g')
-        f.change_layout(layout)
-        g = d3.skew(f).evaluate()
-        assert np.allclose(g[layout][0], -f[layout][1])
-        assert np.allclose(g[layout][1], f[layout][0])
-    c, d, b, r = build(kind)                                             # test_skew_implicit
-    f = d.VectorField(c, bases=b)
-    f.fill_random(layout='g')
-    u = d.VectorField(c, bases=b)
-    problem = d3.LBVP([u], namespace=locals())
-    problem.add_equation("skew(u) = skew(f)")
-    solver = problem.build_solver()
-    solver.solve()
-    assert np.allclose(u['c'], f['c'])
+    """test_cartesian_operators.py:93-132: skew(v) = (-v_y, v_x) in either layout; the LBVP skew(u) = skew(v) returns v."""
+    for layout in ('c', 'g'):
+        cs, dist, bases, grids = build(kind)
+        v = _random(dist, (cs,), bases, layout)
+        rotated = d3.skew(v).evaluate()
+        assert np.allclose(rotated[layout][0], -v[layout][1]) and np.allclose(rotated[layout][1], v[layout][0])
+    cs, dist, bases, grids = build(kind)
+    v, u = _random(dist, (cs,), bases), dist.VectorField(cs, bases=bases)
+    _solve([u], "skew(u)", "skew(v)", u=u, v=v)
+    assert np.allclose(u['c'], v['c'])
 
 
 def check_trace_and_transpose(kind, N=16):
+    """test_cartesian_operators.py:134-250: trace of rank-2 / rank-3 tensors and the transpose against numpy, in both layouts; the
+    LBVPs trace(I*u) = dim*f (scalar and vector f) and transpose(u) = transpose(T) return their data."""
     if len(kind) == 3:
         N = 8
     for layout in ('c', 'g'):
-        c, d, b, r = build(kind, N)                                      # test_trace_explicit
-        f = d.TensorField((c, c), bases=b)
-        f.fill_random(layout='g')
-        f.change_layout(layout)
-        g = d3.trace(f).evaluate()
-        assert np.allclose(g[layout], np.trace(f[layout]))
-        f3 = d.TensorField((c, c, c), bases=b)                           # test_trace_rank3_explicit
-        f3.fill_random(layout='g')
-        f3.change_layout(layout)
-        g = d3.trace(f3).evaluate()
-        assert np.allclose(g[layout], np.trace(f3[layout]))
-        g = d3.transpose(f).evaluate()                                   # test_transpose_explicit
-        order = np.arange(2 + len(r))
-        order[:2] = [1, 0]
-        assert np.allclose(g[layout], np.transpose(f[layout], order))
-    c, d, b, r = build(kind, N)                                          # test_trace_implicit / test_trace_rank3_implicit
-    dim = len(r)
-    I = d.TensorField((c, c))
+        cs, dist, bases, grids = build(kind, N)
+        T2 = _random(dist, (cs, cs), bases, layout)
+        assert np.allclose(d3.trace(T2).evaluate()[layout], np.trace(T2[layout]))
+        T3 = _random(dist, (cs, cs, cs), bases, layout)
+        assert np.allclose(d3.trace(T3).evaluate()[layout], np.trace(T3[layout]))
+        axes = list(range(2 + len(grids)))
+        axes[0], axes[1] = 1, 0
+        assert np.allclose(d3.transpose(T2).evaluate()[layout], np.transpose(T2[layout], axes))
+    cs, dist, bases, grids = build(kind, N)
+    dim = len(grids)
+    identity = dist.TensorField((cs, cs))
     for i in range(dim):
-        I['g'][i, i] = 1
-    for make in (lambda: d.Field(bases=b), lambda: d.VectorField(c, bases=b)):
-        f = make()
-        f.fill_random(layout='g')
-        u = make()
-        problem = d3.LBVP([u], namespace=dict(u=u, f=f, I=I, dim=dim))
-        problem.add_equation("trace(I*u) = dim*f")
-        solver = problem.build_solver()
-        solver.solve()
-        assert np.allclose(u['c'], f['c'])
-    f = d.TensorField((c, c), bases=b)                                   # test_transpose_implicit
-    f.fill_random(layout='g')
-    u = d.TensorField((c, c), bases=b)
-    problem = d3.LBVP([u], namespace=locals())
-    problem.add_equation("transpose(u) = transpose(f)")
-    solver = problem.build_solver()
-    solver.solve()
-    assert np.allclose(u['c'], f['c'])
+        identity['g'][i, i] = 1
+    for sig in ((), (cs,)):
+        data = _random(dist, sig, bases)
+        unknown = dist.TensorField(sig, bases=bases) if sig else dist.Field(bases=bases)
+        _solve([unknown], "trace(I*u)", "dim*f", u=unknown, f=data, I=identity, dim=dim)
+        assert np.allclose(unknown['c'], data['c'])
+    T2 = _random(dist, (cs, cs), bases)
+    unknown = dist.TensorField((cs, cs), bases=bases)
+    _solve([unknown], "transpose(u)", "transpose(f)", u=unknown, f=T2)
+    assert np.allclose(unknown['c'], T2['c'])
 
 
 def check_curls():
