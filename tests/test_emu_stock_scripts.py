@@ -11,7 +11,7 @@ STOCK = {
     "rb2d": ("examples/ivp_2d_rayleigh_benard/rayleigh_benard.py",
              [("Nx, Nz = 256, 64", "Nx, Nz = 32, 16"), ("stop_sim_time = 50", "stop_sim_time = 2")], ("b", "u", "p")),
     "shell": ("examples/ivp_shell_convection/shell_convection.py",
-              [("Nphi, Ntheta, Nr = 192, 96, 6", "Nphi, Ntheta, Nr = 16, 8, 6"), ("stop_sim_time = 2000", "stop_sim_time = 12")],
+              [("Nphi, Ntheta, Nr = 192, 96, 6", "Nphi, Ntheta, Nr = 16, 8, 6"), ("stop_sim_time = 2000", "stop_sim_time = 11")],
               ("p", "b", "u")),
     "shear": ("examples/ivp_2d_shear_flow/shear_flow.py",
               [("Nx, Nz = 128, 256", "Nx, Nz = 16, 32"), ("stop_sim_time = 20", "stop_sim_time = 0.12")], ("u", "s", "p")),
