@@ -5,26 +5,45 @@
 thread_local EmuState emu_cur;
 
 namespace {
+// Persistent fibers: one per thread slot of a block, created once (makecontext) and reused by every block of every launch.  All
+// later switches are _setjmp / _longjmp pairs: unlike swapcontext / getcontext they make no system call (glibc saves and restores the
+// signal mask there), which dominated the run time of launches with many short threads.
 struct Fiber {
     ucontext_t ctx;
+    jmp_buf jb;
     unsigned char* stack = nullptr;
     EmuState st;
     bool done = false;
+    bool created = false;
 };
 const size_t STACK = 128 * 1024;
-thread_local std::vector<unsigned char*> stack_pool;    // allocated once, reused by every launch
-unsigned char* get_stack(size_t i) {
-    while (stack_pool.size() <= i) stack_pool.push_back((unsigned char*)malloc(STACK));
-    return stack_pool[i];
-}
-thread_local ucontext_t sched_ctx;
+thread_local Fiber fiber_pool[1024];                    // a block has at most 1024 threads
+thread_local jmp_buf sched_jb;
 thread_local Fiber* running = nullptr;
 thread_local const std::function<void()>* cur_body = nullptr;
 
-void fiber_entry() {
-    (*cur_body)();
-    running->done = true;
-    swapcontext(&running->ctx, &sched_ctx);
+void fiber_main() {
+    for (;;) {                                          // one iteration per (launch, block) this slot takes part in
+        (*cur_body)();
+        running->done = true;
+        if (!_setjmp(running->jb)) _longjmp(sched_jb, 1);      // parked until the next block resumes this slot
+    }
+}
+
+// scheduler side: run fiber f until it yields or finishes
+void resume(Fiber& f) {
+    running = &f;
+    emu_cur = f.st;
+    if (_setjmp(sched_jb)) return;                      // the fiber came back
+    if (f.created) _longjmp(f.jb, 1);
+    f.created = true;
+    if (!f.stack) f.stack = (unsigned char*)malloc(STACK);
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = STACK;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, (void (*)())fiber_main, 0);
+    setcontext(&f.ctx);                                 // first entry of this slot; never returns here
 }
 }  // namespace
 
@@ -32,7 +51,7 @@ void fiber_entry() {
 void emu_yield() {
     Fiber* f = running;
     f->st = emu_cur;
-    swapcontext(&f->ctx, &sched_ctx);
+    if (!_setjmp(f->jb)) _longjmp(sched_jb, 1);
     emu_cur = f->st;
 }
 
@@ -72,8 +91,7 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
         abort();
     }
     std::vector<unsigned char> shared(smem + 64);
-    std::vector<Fiber> fibers(nthreads);
-    for (size_t i = 0; i < nthreads; ++i) fibers[i].stack = get_stack(i);
+    Fiber* fibers = fiber_pool;
     cur_body = &body;
     static const bool reverse_blocks = [] { const char* e = getenv("DB_EMU_ORDER"); return e && e[0] == 'r'; }();
     for (unsigned bzi = 0; bzi < grid.z; ++bzi)
@@ -92,11 +110,6 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
             f.done = false;
             f.st.tid = {tx, ty, tz}; f.st.bid = {bx, by, bz}; f.st.bdim = block; f.st.gdim = grid;
             f.st.smem = shared.data();
-            getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack;
-            f.ctx.uc_stack.ss_size = STACK;
-            f.ctx.uc_link = &sched_ctx;
-            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
         size_t remaining = nthreads;
         bar_arrived = 0; bar_live = nthreads;
@@ -105,12 +118,10 @@ void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>&
         static const bool reverse_order = [] { const char* e = getenv("DB_EMU_ORDER"); return e && e[0] == 'r'; }();
         while (remaining) {
             size_t finished_this_round = 0, waiting = 0;
-            for (size_t fi = 0; fi < fibers.size(); ++fi) {
-                Fiber& f = fibers[reverse_order ? fibers.size() - 1 - fi : fi];
+            for (size_t fi = 0; fi < nthreads; ++fi) {
+                Fiber& f = fibers[reverse_order ? nthreads - 1 - fi : fi];
                 if (f.done) continue;
-                running = &f;
-                emu_cur = f.st;
-                swapcontext(&sched_ctx, &f.ctx);
+                resume(f);
                 if (f.done) { ++finished_this_round; --bar_live; bar_release_if_complete(); } else { ++waiting; }
             }
             remaining -= finished_this_round;

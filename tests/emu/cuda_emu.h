@@ -6,6 +6,7 @@
 // tests/emu/libdedalus_b200_emu.so and loaded only by tests (tests/emu/emu_lib.py).
 #pragma once
 #include <ucontext.h>
+#include <csetjmp>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
