@@ -82,32 +82,32 @@ def test_cartesian_curls():
     K.check_curls()
 
 
-@pytest.mark.parametrize("dealias", [3/2])           # dealias = 1 as well in the GPU suite
+@pytest.mark.parametrize("dealias", [1, 3/2])
 def test_sphere_calculus_explicit(dealias):
     import sphere_calculus_cases as S
     S.check_explicit(dealias)
 
 
-@pytest.mark.parametrize("dealias", [3/2])           # dealias = 1 as well in the GPU suite
+@pytest.mark.parametrize("dealias", [1, 3/2])
 def test_sphere_calculus_implicit(dealias):
     import sphere_calculus_cases as S
     S.check_implicit(dealias)
 
 
-@pytest.mark.parametrize("dealias", [3/2])           # dealias = 1 as well in the GPU suite
+@pytest.mark.parametrize("dealias", [1, 3/2])
 def test_shell_gradient_scalar(dealias):
     import sphere_calculus_cases as S
     S.check_shell_gradient_scalar(dealias)
 
 
-@pytest.mark.parametrize("dealias", [3/2])           # dealias = 1 as well in the GPU suite
+@pytest.mark.parametrize("dealias", [1, 3/2])
 def test_shell_calculus(dealias):
     import sphere_calculus_cases as S
     S.check_shell_calculus(dealias)
 
 
 @pytest.mark.parametrize("k", [0, 1])
-@pytest.mark.parametrize("dealias", [3/2])
+@pytest.mark.parametrize("dealias", [1, 3/2])
 def test_shell_operators(k, dealias):
     import sphere_calculus_cases as S
     S.check_shell_operators(k, dealias)

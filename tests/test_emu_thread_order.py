@@ -11,7 +11,7 @@ def test_kernels_pass_with_reversed_thread_order():
     env = dict(os.environ, DB_EMU_ORDER="reverse")
     cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
            str(ROOT / "tests" / "test_emu_shell.py"), str(ROOT / "tests" / "test_emu_sphere.py"), str(ROOT / "tests" / "test_emu_plugins.py"),
-           "-k", "a_sbdf2 or banded or matsolver"]
+           "-k", "a_sbdf2 or banded or sw16 or matsolver or transforms"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env, cwd=str(ROOT))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout
