@@ -25,7 +25,7 @@ def test_shell_pencil_matrices(golden):
     SC.check_shell_pencil_matrices(golden("shell_ivp.npz"))
 
 
-@pytest.mark.parametrize("tag,scheme", [("a_sbdf2", "SBDF2")])       # RK222 and 32 x 16 x 12: GPU suite only (emulation time)
+@pytest.mark.parametrize("tag,scheme", [("a_sbdf2", "SBDF2"), ("a_rk222", "RK222"), ("b_sbdf2", "SBDF2")])
 def test_shell_convection_matches_reference(golden, tag, scheme):
     solver = SC.check_shell_convection(golden("shell_ivp.npz"), tag, scheme)
     assert solver.bset.last_verify < 1e-12

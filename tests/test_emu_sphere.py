@@ -22,7 +22,7 @@ def test_sphere_pencil_matrices(golden):
     S.check_pencil_matrices(golden("sphere.npz"))
 
 
-@pytest.mark.parametrize("tag,scheme", [("sw16", "RK222"), ("sw32sbdf2", "SBDF2")])       # sw32 / RK222: GPU suite only (emulation time)
+@pytest.mark.parametrize("tag,scheme", [("sw16", "RK222"), ("sw32", "RK222"), ("sw32sbdf2", "SBDF2")])
 def test_shallow_water_matches_reference(golden, tag, scheme):
     sw, solver = S.check_shallow_water(golden("sphere.npz"), tag, scheme)
     assert solver.bset.last_verify < 1e-12
