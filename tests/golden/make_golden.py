@@ -657,9 +657,54 @@ def shell_convection_strong(shape=(16, 8, 6), steps=3, tstep=0.02, forced=False)
     return out
 
 
+def shell_convection_big(shape=(64, 32, 24), steps=2, tstep=0.02):
+    """A larger shell (Lmax = 30, 24 radial modes: dense systems of 128 unknowns, up to 62 columns each) with an O(0.05) flow."""
+    Ri, Ro = 14, 15
+    Nphi, Ntheta, Nr = shape
+    Rayleigh = 3500; Prandtl = 1; dealias = 3/2
+    coords = d3.SphericalCoordinates('phi', 'theta', 'r')
+    dist = d3.Distributor(coords, dtype=np.float64)
+    shell = d3.ShellBasis(coords, shape=(Nphi, Ntheta, Nr), radii=(Ri, Ro), dealias=dealias, dtype=np.float64)
+    sphere = shell.outer_surface
+    p = dist.Field(name='p', bases=shell); b = dist.Field(name='b', bases=shell)
+    u = dist.VectorField(coords, name='u', bases=shell)
+    tau_p = dist.Field(name='tau_p')
+    tau_b1 = dist.Field(name='tau_b1', bases=sphere); tau_b2 = dist.Field(name='tau_b2', bases=sphere)
+    tau_u1 = dist.VectorField(coords, name='tau_u1', bases=sphere); tau_u2 = dist.VectorField(coords, name='tau_u2', bases=sphere)
+    kappa = (Rayleigh * Prandtl)**(-1/2); nu = (Rayleigh / Prandtl)**(-1/2)
+    phi, theta, r = dist.local_grids(shell)
+    er = dist.VectorField(coords, bases=shell.radial_basis); er['g'][2] = 1
+    rvec = dist.VectorField(coords, bases=shell.radial_basis); rvec['g'][2] = r
+    lift_basis = shell.derivative_basis(1)
+    lift = lambda A: d3.Lift(A, lift_basis, -1)
+    grad_u = d3.grad(u) + rvec*lift(tau_u1)
+    grad_b = d3.grad(b) + rvec*lift(tau_b1)
+    problem = d3.IVP([p, b, u, tau_p, tau_b1, tau_b2, tau_u1, tau_u2], namespace=locals())
+    problem.add_equation("trace(grad_u) + tau_p = 0")
+    problem.add_equation("dt(b) - kappa*div(grad_b) + lift(tau_b2) = - u@grad(b)")
+    problem.add_equation("dt(u) - nu*div(grad_u) + grad(p) - b*er + lift(tau_u2) = - u@grad(u)")
+    problem.add_equation("b(r=Ri) = 1"); problem.add_equation("u(r=Ri) = 0")
+    problem.add_equation("b(r=Ro) = 0"); problem.add_equation("u(r=Ro) = 0")
+    problem.add_equation("integ(p) = 0")
+    solver = problem.build_solver(d3.SBDF2)
+    b.fill_random('g', seed=42, distribution='normal', scale=1e-3)
+    b['g'] *= (r - Ri) * (Ro - r)
+    b['g'] += (Ri - Ri*Ro/r) / (Ri - Ro)
+    u.fill_random('g', seed=7, distribution='normal', scale=0.5)
+    u.low_pass_filter(scales=0.5)
+    u['g'] *= (r - Ri) * (Ro - r)
+    out = dict(b0=b['c'].copy(), u0=u['c'].copy(), meta=np.array(list(shape) + [steps, tstep]))
+    for i in range(steps):
+        solver.step(tstep)
+    for f in (p, b, u):
+        out[f.name + "1"] = f['c'].copy()
+    return out
+
+
 def gen_shell_strong():
     out = {f"strong_{k}": v for k, v in shell_convection_strong().items()}
     out.update({f"forced_{k}": v for k, v in shell_convection_strong(forced=True).items() if k.endswith("1")})
+    out.update({f"big_{k}": v for k, v in shell_convection_big().items()})
     np.savez_compressed(HERE / "shell_strong.npz", **out)
     print({k: (v.shape, float(np.abs(v).max())) for k, v in out.items()})
 

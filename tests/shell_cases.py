@@ -214,3 +214,19 @@ def check_shell_convection_forced(g):
         ref = g[f"forced_{name}1"]
         got = sc[name]['c']
         assert np.allclose(got, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
+
+
+def check_shell_convection_big(g):
+    """64 x 32 x 24 (Lmax = 30, 24 radial modes, up to 62 right-hand-side columns per degree) from an O(0.05) flow: 2 SBDF2 steps."""
+    from dedalus_b200 import examples
+    Nphi, Ntheta, Nr, steps, dt = g["big_meta"]
+    sc = examples.shell_convection(int(Nphi), int(Ntheta), int(Nr))
+    solver = sc['problem'].build_solver(d3.SBDF2)
+    sc['b']['c'] = g["big_b0"]; sc['u']['c'] = g["big_u0"]
+    for _ in range(int(steps)):
+        solver.step(float(dt))
+    for name in ('p', 'b', 'u'):
+        ref = g[f"big_{name}1"]
+        got = sc[name]['c']
+        assert np.allclose(got, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
+    return solver

@@ -70,3 +70,10 @@ def test_shell_convection_with_strong_flow_matches_reference(golden):
 def test_shell_convection_with_grid_function_forcing_matches_reference(golden):
     import shell_cases as SC
     SC.check_shell_convection_forced(golden("shell_strong.npz"))
+
+
+def test_shell_convection_64x32x24_matches_reference(golden):
+    """A larger shell with a real flow (passes under emulation in 2 minutes, so it is a GPU-suite case only)."""
+    import shell_cases as SC
+    solver = SC.check_shell_convection_big(golden("shell_strong.npz"))
+    assert solver.bset.last_verify < 1e-12
