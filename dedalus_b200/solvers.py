@@ -386,8 +386,6 @@ class InitialValueSolver:
                     from .sphere import SphereRHSPlan
                     self.rhs_plan = SphereRHSPlan(self)
             except NotImplementedError:
-                if self.dist.size > 1:
-                    raise
                 from .analysis import GenericCurvilinearRHS
                 self.rhs_plan = GenericCurvilinearRHS(self)
         elif self.complex:

@@ -47,6 +47,26 @@ def main():
             print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
         dist.destroy_process_group()
         return
+    if which == "shell:forced":
+        # general curvilinear right-hand sides (grid function on the RHS) on this mesh, strong-flow start, against the reference
+        g = np.load(ROOT / "tests" / "golden" / "shell_strong.npz")
+        Nphi, Ntheta, Nr, steps, dtv = g["strong_meta"]
+        sc = examples.shell_convection(int(Nphi), int(Ntheta), int(Nr), rhs_b_extra="0.05*sin(3*b)")
+        solver = sc['problem'].build_solver(d3.SBDF2)
+        rows = sc['dist'].coeff_local_slice(0, sc['shell'])
+        sc['b']['c'] = g["strong_b0"][rows]; sc['u']['c'] = g["strong_u0"][:, rows]
+        for _ in range(int(steps)):
+            solver.step(float(dtv))
+        ok = type(solver.rhs_plan).__name__ == "GenericCurvilinearRHS"
+        for name in ('p', 'b', 'u'):
+            full = g[f"forced_{name}1"]
+            ok = ok and bool(np.allclose(sc[name]['c'], full[..., rows, :, :], rtol=1e-8, atol=1e-10 * np.abs(full).max()))
+        flag = torch.tensor([1 if ok else 0], device='cuda' if backend == "nccl" else 'cpu')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
+        dist.destroy_process_group()
+        return
     if which == "strong3d":
         # the benchmark's 3-D problem with O(1) velocities on this mesh against the single-rank reference: the noise-started fixtures
         # keep |u| ~ 1e-7 |b| and would not notice a wrong nonlinear term in the distributed layout
