@@ -145,14 +145,14 @@ def check_ncc(d3, g):
         assert np.allclose(got, ref, rtol=1e-8, atol=1e-11 * np.abs(g["ncc_b"]).max()), (name, np.abs(got - ref).max(), np.abs(ref).max())
 
 
-def rb2d_conservative(d3mod, Nx=16, Nz=16, steps=5, tstep=0.02):
+def rb2d_conservative(d3mod, Nx=16, Nz=16, steps=5, tstep=0.02, mesh=None):
     """Right-hand sides that are not polynomials of derivatives of fields: the advection term in conservative form, div(u*b) -- a
     differential operator applied to a product -- and a grid function, sin(3*b)."""
     d3 = d3mod
     Lx, Lz = 4, 1
     Rayleigh, Prandtl = 2e5, 1
     coords = d3.CartesianCoordinates('x', 'z')
-    dist = d3.Distributor(coords, dtype=np.float64)
+    dist = d3.Distributor(coords, dtype=np.float64, mesh=mesh)
     xbasis = d3.RealFourier(coords['x'], size=Nx, bounds=(0, Lx), dealias=3/2)
     zbasis = d3.ChebyshevT(coords['z'], size=Nz, bounds=(0, Lz), dealias=3/2)
     p = dist.Field(name='p', bases=(xbasis, zbasis)); b = dist.Field(name='b', bases=(xbasis, zbasis))

@@ -47,6 +47,22 @@ def main():
             print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
         dist.destroy_process_group()
         return
+    if which == "staged2d":
+        # staged right-hand sides (grid function + derivative of a product) on this mesh against the single-rank reference
+        import bc_cases
+        g = np.load(ROOT / "tests" / "golden" / "bc_data.npz")
+        res = bc_cases.rb2d_conservative(d3, mesh=(world,))
+        ok = True
+        for name, f in res.items():
+            full = g["cons_" + name]
+            rows = f.dist.coeff_local_slice(0, f.bases[0])
+            ok = ok and bool(np.allclose(f['c'], full[..., rows, :], rtol=1e-8, atol=1e-11 * np.abs(full).max()))
+        flag = torch.tensor([1 if ok else 0], device='cuda' if backend == "nccl" else 'cpu')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("DIST_OK" if int(flag.item()) == 1 else "DIST_FAIL")
+        dist.destroy_process_group()
+        return
     if which == "shell:forced":
         # general curvilinear right-hand sides (grid function on the RHS) on this mesh, strong-flow start, against the reference
         g = np.load(ROOT / "tests" / "golden" / "shell_strong.npz")

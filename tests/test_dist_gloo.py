@@ -7,7 +7,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.parametrize("which", ["rb3d_8.npz", "rb2d_16x16.npz", "rb3d_16.npz", "blocked:16x32", "sphere:sw16", "shell:a_sbdf2", "tasks:cartesian", "tasks:shell", "plugin:transpose", "strong3d", "shell:forced"])
+@pytest.mark.parametrize("which", ["rb3d_8.npz", "rb2d_16x16.npz", "rb3d_16.npz", "blocked:16x32", "sphere:sw16", "shell:a_sbdf2", "tasks:cartesian", "tasks:shell", "plugin:transpose", "strong3d", "shell:forced", "staged2d"])
 def test_two_rank_solver_matches_reference(which):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(ROOT / "tests" / "dist_worker.py"), which]

@@ -31,7 +31,7 @@ def test_shell_convection_matches_reference(golden, tag, scheme):
 
 
 @pytest.mark.parametrize("which", ["sphere:sw16", "sphere:sw32", "shell:a_sbdf2", "shell:b_sbdf2", "tasks:cartesian", "tasks:shell",
-                                   "plugin:transpose", "strong3d", "shell:forced"])
+                                   "plugin:transpose", "strong3d", "shell:forced", "staged2d"])
 def test_two_gpu_curvilinear_matches_reference(which):
     """Sphere / shell problems on 2 GPUs over NCCL (coefficients distributed over the azimuthal pairs, grid over colatitude)
     against the single-rank reference states."""
